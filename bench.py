@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""Headline benchmark: conservative FGMRES (CGMRES) on the 1e7-DOF linear-KdV system.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n 10000000]
+
+Workload (BASELINE.json configs[1]): periodic P1 linear KdV midpoint step re-assembled in numpy
+(structurepreservingiterativesolvers_b200/problems/lkdv.py, h = 0.8 and dt = 0.01 held fixed, field-blocked
+[u;v;w], n = 10 000 050, nnz = 6 n), fp64, x0 = 0, no preconditioner, constraints = mass + energy,
+`cgmres(k=50, tol=1e-6, contol=10)`: the tolerance is not reached within 50 iterations at this size,
+so every solve runs 49 unconstrained Krylov iterations and one constrained one (solvers.py:230) --
+the same call the survey timed at 0.27 it/s on the reference.
+
+One "step" = one full solve.  `value` = Krylov iterations per second with the system resident in
+HBM (DeviceSession built before the timed region); `e2e` = the same metric through the public
+`solvers.cgmres(A, b, x0, ...)` call with pinned HOST buffers, i.e. including the upload of the CSR
+matrix, vectors and constraint matrices, the solve, and the download of the solution.
+
+The inputs (basis 4 GB, matrix 0.8 GB) are far larger than the 126 MB L2, so no L2 flush is needed
+between timed iterations.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+K_KRYLOV = 50
+TOL = 1e-6
+CONTOL = 10
+
+
+# ------------------------------------------------------------------------------------------------
+def build_system(n_target):
+    from structurepreservingiterativesolvers_b200 import wrappers
+    from structurepreservingiterativesolvers_b200.problems import lkdv
+    M = lkdv.benchmark_size(n_target)
+    dic, prob = lkdv.linforms(space="CG", M=M, mlength=0.8 * M)
+    x0 = np.zeros(dic["b"].size)
+    full = wrappers.lkdv.conlist(dic, x0)
+    conlist = [full[0], full[2]]                       # mass + energy (BASELINE.json configs[1])
+    return dic, x0, conlist
+
+
+def pin_inputs(dic, x0, conlist):
+    """Move every array that crosses the C ABI into pinned host memory (e2e contract)."""
+    import scipy.sparse as sps
+    import torch
+
+    def pin(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t.numpy()
+
+    def pin_csr(Mx):
+        Mx = Mx.tocsr()
+        return sps.csr_matrix((pin(Mx.data.astype(np.float64, copy=False)),
+                               pin(Mx.indices.astype(np.int32, copy=False)),
+                               pin(Mx.indptr.astype(np.int32, copy=False))), shape=Mx.shape, copy=False)
+
+    A = pin_csr(dic["A"])
+    b = pin(dic["b"])
+    x0p = pin(x0)
+    cons = []
+    for c in conlist:
+        c2 = type(c)(c.M if (c.M.nnz == 0 or not c.M.data.any()) else pin_csr(c.M), pin(np.asarray(c.v, dtype=np.float64)), c.c, c.name)
+        cons.append(c2)
+    return A, b, x0p, cons
+
+
+def transfer_bytes(A, b, x0, conlist):
+    h2d = A.data.nbytes + A.indices.nbytes + A.indptr.nbytes + b.nbytes + x0.nbytes
+    for c in conlist:
+        if c.M.nnz and c.M.data.any():
+            h2d += c.M.data.nbytes + c.M.indices.nbytes + c.M.indptr.nbytes
+        if np.any(c.v):
+            h2d += np.asarray(c.v).nbytes
+    d2h = b.nbytes          # the solution vector
+    return int(h2d), int(d2h)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device=0):
+        self.rows, self.proc, self.device = [], None, device
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([f.strip() for f in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); smax.append(float(r[1]))
+            except Exception:
+                continue
+            for name, flag in zip(names, r[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def peak_hbm():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+def time_oracle(dic, x0, conlist, k_sample):
+    """Reference algorithm (numpy/scipy oracle port) on the host cores: a bounded sample of the same
+    workload -- the first `k_sample` Krylov iterations of the same call (k = k_sample makes the last
+    one constrained, exactly like iteration 50 of the full run)."""
+    from oracle import cgmres_oracle as orc
+    t0 = time.perf_counter()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        x, info = orc.cgmres(dic["A"], dic["b"], x0, k_sample, tol=TOL, contol=CONTOL, conlist=conlist, timing=True)
+    dt = time.perf_counter() - t0
+    return info["steps"] / dt, dt, info
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank, world, local = dist_env()
+    if rank != 0:
+        return
+    dic, x0, conlist = build_system(args.n)
+    k_sample = args.cpu_sample_iters
+    for _ in range(min(args.warmup, 1)):
+        time_oracle(dic, x0, conlist, 1)
+    its, secs = 0, 0.0
+    for _ in range(args.steps):
+        rate, dt, info = time_oracle(dic, x0, conlist, k_sample)
+        its += info["steps"]; secs += dt
+    value = its / secs
+    sample = (f"first {k_sample} of {K_KRYLOV} Krylov iterations of the same cgmres call (n={dic['b'].size}, "
+              f"last one constrained); early iterations are the cheapest (m small), so this favours the CPU")
+    line = {
+        "impl": "reference", "metric": "krylov_iters_per_s", "value": value, "unit": "it/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(dic, "cpu"),
+        "cpu_baseline": {"value": value, "unit": "it/s", "cores": blas_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(dic, where):
+    return {"workload": f"lkdv P1 periodic linear KdV, n={dic['b'].size}, nnz={dic['A'].nnz}, "
+                        f"cgmres k={K_KRYLOV} tol={TOL:g} contol={CONTOL} mass+energy constraints, x0=0, no preconditioner",
+            "n": int(dic["b"].size), "nnz": int(dic["A"].nnz), "k": K_KRYLOV,
+            "l2": "working set (basis 4 GB + matrix 0.8 GB) >> 126 MB L2: no flush between iterations",
+            "where": where}
+
+
+def run_ours(args):
+    from structurepreservingiterativesolvers_b200 import _native as nat
+    from structurepreservingiterativesolvers_b200 import solvers
+    rank, world, local = dist_env()
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dic, x0, conlist = build_system(args.n)
+    A, b = dic["A"], dic["b"]
+    n = b.size
+    engine = args.small_solver
+
+    def solve(session=None, mats=None, eng=engine):
+        Ax, bx, x0x, cl = mats if mats is not None else (A, b, x0, conlist)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return solvers.cgmres(Ax, bx, x0x, K_KRYLOV, tol=TOL, contol=CONTOL, conlist=cl,
+                                  small_solver=eng, session=session, device=local)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    # ---- device-resident timing --------------------------------------------------------------
+    sess = solvers.DeviceSession(A, b, x0, K_KRYLOV, conlist=conlist, device=local, profile=True)
+    ctx = sess.ctx
+    for _ in range(args.warmup):
+        solve(sess)
+    ctx.reset_profile()
+    barrier(); ctx.sync()
+    iters = 0
+    with ClockSampler(local) as clk:
+        t0 = time.perf_counter()
+        ctx.timer_start()
+        for _ in range(args.steps):
+            x, info = solve(sess)
+            iters += info["steps"]
+        ctx.sync()
+        ev_ms = ctx.timer_stop()
+        wall = time.perf_counter() - t0
+    prof = ctx.profile()
+    final_res = float(info["res"][-1])
+    secs = max(wall, ev_ms * 1e-3)
+    if dist is not None:
+        import torch
+        t = torch.tensor([secs], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs = float(t.item())
+        it = torch.tensor([iters], dtype=torch.float64, device="cuda")
+        dist.all_reduce(it, op=dist.ReduceOp.SUM)
+        iters_all = float(it.item())
+    else:
+        iters_all = float(iters)
+    value = iters_all / secs
+    launches = int(sum(v["launches"] for v in prof.values()))
+
+    # parity-mode (scipy SLSQP small solves, the reference's exact host arithmetic) for context
+    parity = None
+    if rank == 0 and engine != "slsqp" and not args.skip_parity_mode:
+        t0 = time.perf_counter()
+        xs, infos = solve(sess, eng="slsqp")
+        ctx.sync()
+        ps = time.perf_counter() - t0
+        parity = {"small_solver": "slsqp", "value": infos["steps"] / ps, "unit": "it/s", "solve_s": ps,
+                  "rel_diff_vs_headline_solver": float(np.linalg.norm(xs - x) / np.linalg.norm(x))}
+    sess.close()
+
+    # ---- end-to-end through the public API, pinned host buffers --------------------------------
+    e2e = None
+    if not args.skip_e2e:
+        mats = pin_inputs(dic, x0, conlist)
+        h2d, d2h = transfer_bytes(*mats)
+        for _ in range(1):
+            solve(None, mats)
+        barrier()
+        e_it, t0 = 0, time.perf_counter()
+        for _ in range(args.e2e_steps):
+            xe, infoe = solve(None, mats)
+            _ = float(infoe["res"][-1])
+            e_it += infoe["steps"]
+        e_secs = time.perf_counter() - t0
+        if dist is not None:
+            import torch
+            t = torch.tensor([e_secs], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_secs = float(t.item())
+            e_it *= world
+        e2e = {"value": e_it / e_secs, "unit": "it/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "solve_s": e_secs / args.e2e_steps}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel class ---------------------------------------------------
+    peak, peak_src = peak_hbm()
+    classes = {k: v for k, v in prof.items() if v["launches"] > 0}
+    dom = max(classes, key=lambda k: classes[k]["ms"])
+    d = classes[dom]
+    kernel_ms = sum(v["ms"] for v in classes.values())
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": d["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": d["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "avg_launch_ms": d["ms"] / d["launches"], "launches": d["launches"],
+                "share_of_kernel_time": d["ms"] / kernel_ms}
+    kernels = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
+                   "gbs": v["gbs"], "frac_of_peak": (v["gbs"] / peak if v["gbs"] else None)} for k, v in classes.items()}
+
+    # ---- CPU baseline: the oracle port on this box's host cores (bounded sample) -----------------
+    cpu = None
+    if not args.skip_cpu:
+        rate, dt, cinfo = time_oracle(dic, x0, conlist, args.cpu_sample_iters)
+        cpu = {"value": rate, "unit": "it/s", "cores": blas_threads(), "kind": "port",
+               "sample": (f"first {args.cpu_sample_iters} of {K_KRYLOV} Krylov iterations of the same cgmres call "
+                          f"(n={n}, last one constrained), {dt:.1f} s; early iterations are the cheapest, so this favours the CPU")}
+
+    line = {
+        "metric": "krylov_iters_per_s", "value": value, "unit": "it/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": dict(workload_config(dic, "1 B200 per rank"), small_solver=engine,
+                       parallelism=("single GPU" if world == 1 else f"{world} independent replicas")),
+        "solve_time_s": secs / args.steps, "device_event_ms_per_step": ev_ms / args.steps,
+        "kernel_ms_per_step": kernel_ms / args.steps, "final_residual": final_res,
+        "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
+        "gpu_launches": launches, "clocks": clk.summary(), "parity_mode": parity,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=10_000_000)
+    ap.add_argument("--small-solver", default="kkt", choices=["kkt", "slsqp"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-sample-iters", type=int, default=8)
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-parity-mode", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

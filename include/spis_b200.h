@@ -1,0 +1,186 @@
+/*
+ * spis_b200.h -- C ABI of the B200-native conservative-FGMRES ("CGMRES") hot path.
+ *
+ * This is the drop-in boundary below the Python `solvers` module.  The reference
+ * (JamesJackaman/StructurePreservingIterativeSolvers) has no native layer: every O(n)
+ * operation of solvers.py is a numpy/scipy call.  Each entry point below names the
+ * reference lines (solvers.py:<line>) whose arithmetic it replaces.  The host side
+ * (structurepreservingiterativesolvers_b200/solvers.py) binds these with ctypes.
+ *
+ * Conventions
+ *   - every pointer argument is HOST memory owned by the caller (plain or pinned);
+ *     the library never keeps a host pointer after the call returns;
+ *   - all functions return 0 on success, a negative SPIS_E_* code on failure, and
+ *     never throw; spis_last_error(ctx) gives the message of the last failure;
+ *   - a context owns one CUDA stream; calls on one context are synchronous with
+ *     respect to each other (the *_launch/*_wait pairs expose the one place where the
+ *     device runs ahead of the host);
+ *   - doubles are IEEE fp64, CSR indices are int32 (PETSc getValuesCSR ->
+ *     scipy.sparse.csr_matrix, lkdv/lkdv.py:109-110).
+ *
+ * There is deliberately no CPU fallback: if no sm_100 device is present
+ * spis_ctx_create fails with SPIS_E_CUDA.
+ */
+#ifndef SPIS_B200_H
+#define SPIS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define SPIS_ABI_VERSION 1
+
+/* error codes */
+#define SPIS_OK            0
+#define SPIS_E_INVALID    -1   /* bad argument / call order */
+#define SPIS_E_CUDA       -2   /* CUDA runtime error (message has cudaGetErrorString) */
+#define SPIS_E_NOMEM      -3   /* device or pinned allocation failed */
+#define SPIS_E_UNSUPPORTED -4
+
+/* matrix slots: 0 = system matrix A, 1 = sparse preconditioner P (z = P q),
+ * 2.. = constraint matrices M_c (slot 2+c).                                  */
+#define SPIS_SLOT_A      0
+#define SPIS_SLOT_PRE    1
+#define SPIS_SLOT_CON0   2
+#define SPIS_MAX_SLOTS   18
+
+/* vector ids for spis_upload_vec / spis_download_vec */
+#define SPIS_VEC_B        0   /* right-hand side b                       (solvers.py:167) */
+#define SPIS_VEC_X0       1   /* initial guess x0                        (solvers.py:167) */
+#define SPIS_VEC_R0       2   /* r0 = b - A x0 (download only; dict['x'][0], quirk Q1, solvers.py:169) */
+#define SPIS_VEC_Q        3   /* Arnoldi basis vector q[j]               (solvers.py:172) */
+#define SPIS_VEC_Z        4   /* preconditioned vector z[j]              (solvers.py:173) */
+#define SPIS_VEC_X        5   /* most recent iterate x_j                 (solvers.py:287) */
+#define SPIS_VEC_PRE_DIAG 6   /* Jacobi preconditioner: the diagonal d, z = d (.) q */
+#define SPIS_VEC_W        7   /* work vector (download only, for tests)  */
+
+/* preconditioner kinds (solvers.py:149-161: identity / pre.solve / pre @ vec) */
+#define SPIS_PRE_NONE     0   /* identity: z[j] aliases q[j], no copy                  */
+#define SPIS_PRE_JACOBI   1   /* z = d (.) q, d uploaded as SPIS_VEC_PRE_DIAG           */
+#define SPIS_PRE_CSR      2   /* z = P q with sparse P in slot SPIS_SLOT_PRE            */
+#define SPIS_PRE_BLOCK    3   /* z = blockdiag(B_i) q, dense b x b blocks (spis_upload_blocks) */
+#define SPIS_PRE_HOST     4   /* host callback bridge: spis_host_pre_get / _put         */
+
+/* orthogonalisation variants for spis_set_option("orth", ...) */
+#define SPIS_ORTH_CGS2    0   /* classical Gram-Schmidt with reorthogonalisation (default) */
+#define SPIS_ORTH_CGS1    1   /* single classical pass                                      */
+#define SPIS_ORTH_MGS     2   /* modified Gram-Schmidt, the reference's loop solvers.py:193-195 */
+
+/* SpMV storage formats for spis_set_option("spmv_format", ...) */
+#define SPIS_FMT_AUTO     0   /* SELL-32 unless padding overhead > 25 % */
+#define SPIS_FMT_SELL     1
+#define SPIS_FMT_CSR      2
+
+/* timer classes returned by spis_get_profile (CUDA-event time, algorithmic bytes, launches) */
+#define SPIS_PROF_SPMV     0
+#define SPIS_PROF_MDOT     1   /* tall-skinny V^T w                 */
+#define SPIS_PROF_LINCOMB  2   /* w -= V h  and  x = x0 + Z y       */
+#define SPIS_PROF_SCALE    3
+#define SPIS_PROF_PRECOND  4
+#define SPIS_PROF_OTHER    5
+#define SPIS_PROF_CLASSES  6
+
+typedef struct spis_ctx spis_ctx;
+
+/* ---- library / context ------------------------------------------------------------ */
+int         spis_abi_version(void);
+int         spis_device_count(int* count_out);
+/* n = number of unknowns owned by this context, n_halo = extra ghost entries appended to
+ * every SpMV input vector (0 on a single GPU), k_max = maximum Krylov dimension.
+ * stream = a cudaStream_t to launch on (e.g. torch's current stream) or NULL to create one. */
+int         spis_ctx_create(int device, int64_t n, int64_t n_halo, int k_max, void* stream, spis_ctx** ctx_out);
+int         spis_ctx_destroy(spis_ctx* ctx);
+const char* spis_last_error(const spis_ctx* ctx);
+const char* spis_last_global_error(void);            /* for failures of spis_ctx_create itself */
+/* keys: "orth", "spmv_format", "profile", "ctas_per_sm", "mdot_variant", "lincomb_variant", "spmv_variant" */
+int         spis_set_option(spis_ctx* ctx, const char* key, int64_t value);
+int         spis_get_info(const spis_ctx* ctx, const char* key, int64_t* value_out);
+
+/* ---- uploads ------------------------------------------------------------------------ */
+/* CSR matrix -> device (and SELL-32 conversion on device).  Replaces holding `A`, `pre`
+ * and `const.M` as scipy objects (solvers.py:131,150,33).  ncols may exceed nrows by
+ * n_halo (ghost columns).                                                               */
+int spis_upload_csr(spis_ctx* ctx, int slot, int64_t nrows, int64_t ncols, int64_t nnz,
+                    const int32_t* indptr, const int32_t* indices, const double* data);
+int spis_upload_vec(spis_ctx* ctx, int which, const double* host, int64_t n);
+/* dense blocks for SPIS_PRE_BLOCK: nblk blocks of bs x bs (row-major, block-major on the
+ * host); element f of block i is global index i*idx_stride_block + f*idx_stride_field
+ * (contiguous blocks: bs,1; field-blocked [u;v;w] ordering of lkdv/refd.py:17: 1,nblk). */
+int spis_upload_blocks(spis_ctx* ctx, int bs, int64_t nblk, int64_t idx_stride_block,
+                       int64_t idx_stride_field, const double* blocks);
+int spis_set_precond(spis_ctx* ctx, int kind);
+
+/* ---- Krylov loop -------------------------------------------------------------------- */
+/* r0 = b - A x0, beta = ||r0||, q[0] = r0/beta                     (solvers.py:167-177) */
+int spis_solve_begin(spis_ctx* ctx, double* beta_out);
+/* one Arnoldi step j: z[j] = P q[j]; w = A z[j]; orthogonalise against q[0..j];
+ * h[j+1,j] = ||w||; q[j+1] = w/h[j+1,j]                            (solvers.py:190-198).
+ * hcol_out receives h[0..j+1, j] (j+2 doubles).  launch/wait split lets the host run
+ * the small minimisation of step j-1 while the device does step j.                      */
+int spis_arnoldi_launch(spis_ctx* ctx, int j);
+int spis_arnoldi_wait(spis_ctx* ctx, int j, double* hcol_out);
+int spis_arnoldi_step(spis_ctx* ctx, int j, double* hcol_out);
+/* x_j = x0 + Z[:, :m] y ; resnorm = ||A x_j - b||                  (solvers.py:287,290) */
+int spis_iterate_residual(spis_ctx* ctx, int m, const double* y, double* resnorm_out);
+/* only x = x0 + Z[:, :m] y (lazy re-materialisation of dict['x'][j], solvers.py:318)    */
+int spis_form_iterate(spis_ctx* ctx, int m, const double* y);
+
+/* ---- constraint stage (solvers.py:21-36, constraint_container.__init__) ------------- */
+/* class-form constraint c: 1/2 x^T M x + v^T x + cc.  mat_slot < 0: M is identically zero
+ * (lkdv/LinearSolver.py:30 `0*A`); v may be NULL (all zero).                            */
+int spis_constraint_define(spis_ctx* ctx, int c, int mat_slot, const double* v, double cc);
+/* term0 (scalar), term1 (m), term2 (m x m row-major) for Z = z[:m].T, incremental in m:
+ * MZ = M@Z (:33), term0 (:34), term1 = v@Z + x0@MZ (:35), term2 = 1/2 Z.T@MZ (:36)      */
+int spis_constraint_terms(spis_ctx* ctx, int c, int m, double* term0, double* term1, double* term2);
+
+/* ---- downloads / host bridges ------------------------------------------------------- */
+int spis_download_vec(spis_ctx* ctx, int which, int j, double* host, int64_t n);
+/* rows z[j0..j1) as a (j1-j0) x n row-major block (dict-form constraints need Z on the
+ * host: lkdvRK/LinearSolver.py:29-67)                                                   */
+int spis_download_Z(spis_ctx* ctx, int j0, int j1, double* host);
+/* SPIS_PRE_HOST bridge: fetch q[j], store z[j] = pre.solve(q[j])   (solvers.py:152-154) */
+int spis_host_pre_get(spis_ctx* ctx, int j, double* q_host);
+int spis_host_pre_put(spis_ctx* ctx, int j, const double* z_host);
+
+/* ---- multi-GPU hooks (row-block sharding) -------------------------------- */
+/* After every local reduction the library calls allreduce(user, device_ptr, count) with a
+ * DEVICE pointer to `count` doubles that must be summed in place over all ranks, ordered
+ * on the context's stream.  Before every SpMV it calls halo(user, device_vec_ptr) which
+ * must fill entries [n, n+n_halo) of that vector from the neighbouring ranks.  The host
+ * language supplies both (torch.distributed over NCCL).                                 */
+typedef int (*spis_allreduce_fn)(void* user, void* device_ptr, int64_t count);
+typedef int (*spis_halo_fn)(void* user, void* device_vec_ptr);
+int spis_set_collectives(spis_ctx* ctx, spis_allreduce_fn allreduce, spis_halo_fn halo, void* user);
+int spis_sync(spis_ctx* ctx);
+
+/* ---- measurement --------------------------------------------------------------------- */
+/* per class: ms_out[c] CUDA-event milliseconds, bytes_out[c] algorithmic bytes,
+ * launches_out[c] kernel launches since the last spis_reset_profile.                    */
+int spis_get_profile(spis_ctx* ctx, double* ms_out, double* bytes_out, int64_t* launches_out);
+int spis_reset_profile(spis_ctx* ctx);
+/* CUDA-event stopwatch on the context's stream: device time between the two calls.      */
+int spis_timer_start(spis_ctx* ctx);
+int spis_timer_stop(spis_ctx* ctx, double* ms_out);
+
+/* ---- single-kernel entry points (parity tests and tuning; host buffers in and out) --- */
+int spis_op_spmv(spis_ctx* ctx, int slot, const double* x, double* y);                 /* y = M_slot x */
+int spis_op_mdot(spis_ctx* ctx, int m, const double* V /* m x n */, const double* w, double* out /* m+1: V w, w.w */);
+int spis_op_lincomb(spis_ctx* ctx, int m, const double* V, const double* base, const double* coef,
+                    double sign, double* out, double* sumsq_out);
+int spis_op_precond(spis_ctx* ctx, const double* q, double* z);                        /* z = P q */
+/* time `reps` back-to-back launches of one kernel class on resident random data and
+ * return the mean milliseconds per launch (tuning / roofline sweeps).                   */
+int spis_bench_kernel(spis_ctx* ctx, int prof_class, int m, int reps, double* ms_out, double* bytes_out);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPIS_B200_H */

@@ -1,0 +1,141 @@
+"""ctypes binding of the C ABI in include/spis_b200.h (libspis_b200.so).
+
+The binding is deliberately thin: one Python function per exported symbol, numpy arrays in,
+numpy arrays out.  There is no CPU fallback -- if the shared library is missing, or no sm_100
+device is visible, every entry point raises (`NativeLibraryError` / `SpisError`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import numpy as np
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "lib", "libspis_b200.so")
+
+# constants mirrored from include/spis_b200.h
+ABI_VERSION = 1
+OK, E_INVALID, E_CUDA, E_NOMEM, E_UNSUPPORTED = 0, -1, -2, -3, -4
+SLOT_A, SLOT_PRE, SLOT_CON0, MAX_SLOTS = 0, 1, 2, 18
+VEC_B, VEC_X0, VEC_R0, VEC_Q, VEC_Z, VEC_X, VEC_PRE_DIAG, VEC_W = range(8)
+PRE_NONE, PRE_JACOBI, PRE_CSR, PRE_BLOCK, PRE_HOST = range(5)
+ORTH_CGS2, ORTH_CGS1, ORTH_MGS = range(3)
+FMT_AUTO, FMT_SELL, FMT_CSR = range(3)
+PROF_SPMV, PROF_MDOT, PROF_LINCOMB, PROF_SCALE, PROF_PRECOND, PROF_OTHER, PROF_CLASSES = range(7)
+PROF_NAMES = ("spmv", "mdot", "lincomb", "scale", "precond", "other")
+
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64)
+HALO_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p)
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_lp = C.POINTER(C.c_int64)
+_ctx = C.c_void_p
+
+# name -> (restype, argtypes): every symbol declared in include/spis_b200.h
+SIGNATURES = {
+    "spis_abi_version": (C.c_int, []),
+    "spis_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "spis_ctx_create": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.POINTER(_ctx)]),
+    "spis_ctx_destroy": (C.c_int, [_ctx]),
+    "spis_last_error": (C.c_char_p, [_ctx]),
+    "spis_last_global_error": (C.c_char_p, []),
+    "spis_set_option": (C.c_int, [_ctx, C.c_char_p, C.c_int64]),
+    "spis_get_info": (C.c_int, [_ctx, C.c_char_p, _lp]),
+    "spis_upload_csr": (C.c_int, [_ctx, C.c_int, C.c_int64, C.c_int64, C.c_int64, _ip, _ip, _dp]),
+    "spis_upload_vec": (C.c_int, [_ctx, C.c_int, _dp, C.c_int64]),
+    "spis_upload_blocks": (C.c_int, [_ctx, C.c_int, C.c_int64, C.c_int64, C.c_int64, _dp]),
+    "spis_set_precond": (C.c_int, [_ctx, C.c_int]),
+    "spis_solve_begin": (C.c_int, [_ctx, _dp]),
+    "spis_arnoldi_launch": (C.c_int, [_ctx, C.c_int]),
+    "spis_arnoldi_wait": (C.c_int, [_ctx, C.c_int, _dp]),
+    "spis_arnoldi_step": (C.c_int, [_ctx, C.c_int, _dp]),
+    "spis_iterate_residual": (C.c_int, [_ctx, C.c_int, _dp, _dp]),
+    "spis_form_iterate": (C.c_int, [_ctx, C.c_int, _dp]),
+    "spis_constraint_define": (C.c_int, [_ctx, C.c_int, C.c_int, _dp, C.c_double]),
+    "spis_constraint_terms": (C.c_int, [_ctx, C.c_int, C.c_int, _dp, _dp, _dp]),
+    "spis_download_vec": (C.c_int, [_ctx, C.c_int, C.c_int, _dp, C.c_int64]),
+    "spis_download_Z": (C.c_int, [_ctx, C.c_int, C.c_int, _dp]),
+    "spis_host_pre_get": (C.c_int, [_ctx, C.c_int, _dp]),
+    "spis_host_pre_put": (C.c_int, [_ctx, C.c_int, _dp]),
+    "spis_set_collectives": (C.c_int, [_ctx, ALLREDUCE_FN, HALO_FN, C.c_void_p]),
+    "spis_sync": (C.c_int, [_ctx]),
+    "spis_get_profile": (C.c_int, [_ctx, _dp, _dp, _lp]),
+    "spis_reset_profile": (C.c_int, [_ctx]),
+    "spis_timer_start": (C.c_int, [_ctx]),
+    "spis_timer_stop": (C.c_int, [_ctx, _dp]),
+    "spis_op_spmv": (C.c_int, [_ctx, C.c_int, _dp, _dp]),
+    "spis_op_mdot": (C.c_int, [_ctx, C.c_int, _dp, _dp, _dp]),
+    "spis_op_lincomb": (C.c_int, [_ctx, C.c_int, _dp, _dp, _dp, C.c_double, _dp, _dp]),
+    "spis_op_precond": (C.c_int, [_ctx, _dp, _dp]),
+    "spis_bench_kernel": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, _dp, _dp]),
+}
+
+
+class NativeLibraryError(RuntimeError):
+    """libspis_b200.so is missing or does not match this package (there is no CPU fallback)."""
+
+
+class SpisError(RuntimeError):
+    """A C-ABI call returned a negative status."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"[spis {code}] {message}")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library(path: str | None = None):
+    """dlopen the shared library and attach the prototypes (idempotent)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or os.environ.get("SPIS_B200_LIB", LIB_PATH)
+    if not os.path.exists(p):
+        raise NativeLibraryError(
+            f"{p} not found. Build it with `python -m structurepreservingiterativesolvers_b200.build` "
+            "(nvcc, sm_100a). This package has no CPU fallback.")
+    try:
+        lib = C.CDLL(p)
+    except OSError as exc:  # pragma: no cover - depends on the host
+        raise NativeLibraryError(f"cannot load {p}: {exc}") from exc
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as exc:
+            raise NativeLibraryError(f"{p} does not export {name}; rebuild the library") from exc
+        fn.restype = res
+        fn.argtypes = args
+    if lib.spis_abi_version() != ABI_VERSION:
+        raise NativeLibraryError(f"{p} has ABI {lib.spis_abi_version()}, binding expects {ABI_VERSION}")
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def as_f64(a, n=None) -> np.ndarray:
+    out = np.ascontiguousarray(a, dtype=np.float64)
+    if out.ndim != 1:
+        out = out.reshape(-1)
+    if n is not None and out.size != n:
+        raise ValueError(f"expected a vector of length {n}, got {out.size}")
+    return out
+
+
+def dptr(a: np.ndarray):
+    return a.ctypes.data_as(_dp)
+
+
+def iptr(a: np.ndarray):
+    return a.ctypes.data_as(_ip)
+
+
+def device_count() -> int:
+    lib = load_library()
+    cnt = C.c_int(0)
+    rc = lib.spis_device_count(C.byref(cnt))
+    if rc != OK:
+        raise SpisError(rc, lib.spis_last_global_error().decode())
+    return cnt.value

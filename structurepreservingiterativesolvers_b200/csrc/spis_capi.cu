@@ -1,0 +1,981 @@
+// spis_capi.cu -- context object + extern "C" entry points declared in include/spis_b200.h.
+//
+// Host-side orchestration of one Krylov context on one B200: device buffers, the launch
+// sequences for an Arnoldi step / iterate+residual / constraint terms, CUDA-event profiling
+// and the hooks through which the host language supplies halo exchange and all-reduce for
+// row-sharded multi-GPU runs.  No torch types, no exceptions across the ABI, no CPU path.
+#include "../../include/spis_b200.h"
+#include "spis_kernels.cuh"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <initializer_list>
+#include <string>
+#include <vector>
+
+using namespace spis;
+
+namespace {
+
+thread_local char g_global_err[512] = "";
+
+struct Matrix {
+  bool present = false;
+  int fmt = SPIS_FMT_SELL;
+  int64_t nrows = 0, ncols = 0, nnz = 0, nnz_padded = 0;
+  int32_t* indptr = nullptr;   // CSR (kept only for SPIS_FMT_CSR)
+  int32_t* cols = nullptr;
+  double* vals = nullptr;
+  int64_t* slice_off = nullptr;  // SELL-32
+  int32_t* scols = nullptr;
+  double* svals = nullptr;
+  int csr_lanes = 8;
+};
+
+struct Constraint {
+  bool defined = false;
+  int slot = -1;              // matrix slot, <0: M == 0
+  double* v = nullptr;        // device, ld doubles, or null when v == 0
+  double cc = 0.0;
+  double* MZ = nullptr;       // device, kmax x ld, lazily allocated
+  int cols_done = 0;
+  bool term0_done = false;
+  double term0 = 0.0;
+  std::vector<double> T1, T2; // host mirrors, kmax and kmax*kmax
+};
+
+struct ProfRec { int cls; double bytes; cudaEvent_t e0, e1; };
+
+}  // namespace
+
+struct spis_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int nsm = 148;
+  int64_t n = 0, n_halo = 0, hoff = 0, ld = 0;
+  int kmax = 0, K = 0;          // K = kmax + 4 (small-array stride)
+  // options
+  int orth = SPIS_ORTH_CGS2;
+  int fmt_pref = SPIS_FMT_AUTO;
+  int profile = 0;
+  int ctas_per_sm = 4;
+  int spmv_ctas_per_sm = 8;
+  int mdot_variant = 4, lincomb_variant = 4;
+  int x0_is_zero = 0;
+  int fuse_jacobi = 1;
+  // vectors
+  double *V = nullptr, *Z = nullptr, *W = nullptr, *T = nullptr, *R0 = nullptr, *B = nullptr, *X0 = nullptr, *X = nullptr;
+  double* pre_diag = nullptr;
+  double* pre_blocks = nullptr; int pre_bs = 0; int64_t pre_nblk = 0, pre_sb = 0, pre_sf = 0;
+  int pre_kind = SPIS_PRE_NONE;
+  bool z_ready_next = false;    // fused Jacobi already produced z[j] for the coming step
+  int z_ready_index = -1;
+  // small device arrays
+  double* d_small = nullptr;    // [h1 (K) | h2 (K) | scal (8)]
+  double* d_y = nullptr;        // K
+  double* d_cout = nullptr;     // kmax * 2K
+  double* d_partial = nullptr; unsigned* d_counter = nullptr; int pstride = 0; int max_grid = 0;
+  double* h_small = nullptr;    // pinned mirror of d_small
+  double* h_y = nullptr;        // pinned K
+  double* h_cout = nullptr;     // pinned kmax*2K
+  cudaEvent_t ev_arnoldi = nullptr;
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+  int arnoldi_inflight = -1;
+  bool began = false;
+  Matrix mats[SPIS_MAX_SLOTS];
+  Constraint cons[SPIS_MAX_SLOTS];
+  // collectives
+  spis_allreduce_fn allreduce = nullptr; spis_halo_fn halo = nullptr; void* cuser = nullptr;
+  // profiling
+  std::vector<ProfRec> recs; std::vector<cudaEvent_t> evpool;
+  double prof_ms[SPIS_PROF_CLASSES] = {0}; double prof_bytes[SPIS_PROF_CLASSES] = {0}; int64_t prof_launch[SPIS_PROF_CLASSES] = {0};
+  char err[512] = "";
+};
+
+namespace {
+
+int fail(spis_ctx* c, int code, const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt);
+  if (c) vsnprintf(c->err, sizeof(c->err), fmt, ap); else vsnprintf(g_global_err, sizeof(g_global_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(call)                                                                               \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess)                                                                     \
+      return fail(ctx, e_ == cudaErrorMemoryAllocation ? SPIS_E_NOMEM : SPIS_E_CUDA,           \
+                  "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+#define TRY(call) do { int r_ = (call); if (r_ != SPIS_OK) return r_; } while (0)
+#define REQUIRE(cond, ...) do { if (!(cond)) return fail(ctx, SPIS_E_INVALID, __VA_ARGS__); } while (0)
+
+inline int64_t roundup(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+template <class Tp> int dalloc(spis_ctx* ctx, Tp** p, size_t count, bool zero = true) {
+  *p = nullptr;
+  if (count == 0) count = 1;
+  CU(cudaMalloc((void**)p, count * sizeof(Tp)));
+  if (zero) CU(cudaMemsetAsync(*p, 0, count * sizeof(Tp), ctx->stream));
+  return SPIS_OK;
+}
+
+int h2d(spis_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return SPIS_OK;
+}
+int d2h(spis_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return SPIS_OK;
+}
+
+// ---- profiling ------------------------------------------------------------------------
+int prof_begin(spis_ctx* ctx, int cls, double bytes) {
+  ctx->prof_launch[cls] += 1;
+  ctx->prof_bytes[cls] += bytes;
+  if (!ctx->profile) return SPIS_OK;
+  ProfRec r; r.cls = cls; r.bytes = bytes;
+  for (cudaEvent_t* e : {&r.e0, &r.e1}) {
+    if (!ctx->evpool.empty()) { *e = ctx->evpool.back(); ctx->evpool.pop_back(); }
+    else CU(cudaEventCreate(e));
+  }
+  CU(cudaEventRecord(r.e0, ctx->stream));
+  ctx->recs.push_back(r);
+  return SPIS_OK;
+}
+int prof_end(spis_ctx* ctx) {
+  if (!ctx->profile) return SPIS_OK;
+  CU(cudaEventRecord(ctx->recs.back().e1, ctx->stream));
+  return SPIS_OK;
+}
+int prof_resolve(spis_ctx* ctx) {
+  if (ctx->recs.empty()) return SPIS_OK;
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (auto& r : ctx->recs) {
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    ctx->prof_ms[r.cls] += ms;
+    ctx->evpool.push_back(r.e0); ctx->evpool.push_back(r.e1);
+  }
+  ctx->recs.clear();
+  return SPIS_OK;
+}
+
+// ---- kernel launchers -----------------------------------------------------------------
+int grid_for(spis_ctx* ctx, int64_t work_items, int per_sm) {
+  int64_t g = (int64_t)ctx->nsm * per_sm;
+  if (g > ctx->max_grid) g = ctx->max_grid;
+  if (work_items < g) g = work_items;
+  return (int)(g < 1 ? 1 : g);
+}
+
+int do_allreduce(spis_ctx* ctx, double* dev, int64_t count) {
+  if (!ctx->allreduce) return SPIS_OK;
+  int r = ctx->allreduce(ctx->cuser, dev, count);
+  if (r != 0) return fail(ctx, SPIS_E_INVALID, "allreduce callback failed (%d)", r);
+  return SPIS_OK;
+}
+int do_halo(spis_ctx* ctx, double* vec) {
+  if (!ctx->halo || ctx->n_halo == 0) return SPIS_OK;
+  int r = ctx->halo(ctx->cuser, vec);
+  if (r != 0) return fail(ctx, SPIS_E_INVALID, "halo callback failed (%d)", r);
+  return SPIS_OK;
+}
+
+// out[0..m) = V_i.w, then extra.w (if extra), then w.w (if with_sumsq); all-reduced over ranks
+int launch_mdot(spis_ctx* ctx, const double* V, int m, const double* extra, int with_sumsq,
+                const double* w, double* out) {
+  const int nrows = m + (extra ? 1 : 0) + (with_sumsq ? 1 : 0);
+  if (nrows == 0) return SPIS_OK;
+  REQUIRE(nrows <= ctx->pstride, "mdot: %d rows exceed workspace %d", nrows, ctx->pstride);
+  const int64_t ntiles = (ctx->n + kTile - 1) / kTile;
+  const int grid = grid_for(ctx, ntiles, ctx->ctas_per_sm);
+  const size_t smem = (size_t)(kWarps * nrows + kWarps * 32) * sizeof(double);
+  TRY(prof_begin(ctx, SPIS_PROF_MDOT, (double)(m + (extra ? 1 : 0) + 1) * 8.0 * (double)ctx->n));
+  if (ctx->mdot_variant == 8)
+    mdot_kernel<8><<<grid, kThreads, smem, ctx->stream>>>(V, ctx->ld, m, extra, with_sumsq, w, ctx->n, ctx->d_partial, ctx->pstride, ctx->d_counter, out);
+  else if (ctx->mdot_variant == 2)
+    mdot_kernel<2><<<grid, kThreads, smem, ctx->stream>>>(V, ctx->ld, m, extra, with_sumsq, w, ctx->n, ctx->d_partial, ctx->pstride, ctx->d_counter, out);
+  else
+    mdot_kernel<4><<<grid, kThreads, smem, ctx->stream>>>(V, ctx->ld, m, extra, with_sumsq, w, ctx->n, ctx->d_partial, ctx->pstride, ctx->d_counter, out);
+  CU(cudaGetLastError());
+  TRY(prof_end(ctx));
+  return do_allreduce(ctx, out, nrows);
+}
+
+int launch_lincomb(spis_ctx* ctx, const double* V, int m, const double* coef, const double* coef2,
+                   double sign, const double* base, double* out, int with_sumsq, double* sumsq_out) {
+  const int64_t ntiles = (ctx->n + kTile - 1) / kTile;
+  const int grid = grid_for(ctx, ntiles, ctx->ctas_per_sm);
+  const size_t smem = (size_t)(m + 2 + kWarps * 32) * sizeof(double);
+  TRY(prof_begin(ctx, SPIS_PROF_LINCOMB, (double)(m + (base ? 1 : 0) + 1) * 8.0 * (double)ctx->n));
+  if (ctx->lincomb_variant == 8)
+    lincomb_kernel<8><<<grid, kThreads, smem, ctx->stream>>>(V, ctx->ld, m, coef, coef2, sign, base, out, ctx->n, with_sumsq, ctx->d_partial, ctx->d_counter, sumsq_out);
+  else if (ctx->lincomb_variant == 2)
+    lincomb_kernel<2><<<grid, kThreads, smem, ctx->stream>>>(V, ctx->ld, m, coef, coef2, sign, base, out, ctx->n, with_sumsq, ctx->d_partial, ctx->d_counter, sumsq_out);
+  else
+    lincomb_kernel<4><<<grid, kThreads, smem, ctx->stream>>>(V, ctx->ld, m, coef, coef2, sign, base, out, ctx->n, with_sumsq, ctx->d_partial, ctx->d_counter, sumsq_out);
+  CU(cudaGetLastError());
+  TRY(prof_end(ctx));
+  if (with_sumsq) return do_allreduce(ctx, sumsq_out, 1);
+  return SPIS_OK;
+}
+
+template <int MODE>
+int launch_spmv_mode(spis_ctx* ctx, const Matrix& M, const double* x, const double* b, double* y, double* sumsq_out) {
+  if (M.fmt == SPIS_FMT_SELL) {
+    const int64_t nslices = (M.nrows + 31) / 32;
+    const int grid = grid_for(ctx, (nslices + kWarps - 1) / kWarps, ctx->spmv_ctas_per_sm);
+    spmv_sell_kernel<MODE><<<grid, kThreads, 0, ctx->stream>>>(M.slice_off, M.scols, M.svals, M.nrows, x, b, y, ctx->d_partial, ctx->d_counter, sumsq_out);
+  } else {
+    const int T = M.csr_lanes;
+    const int64_t nblocks = (M.nrows + (kThreads / T) - 1) / (kThreads / T);
+    const int grid = grid_for(ctx, nblocks, ctx->spmv_ctas_per_sm);
+#define SPIS_CSR_CASE(TT) case TT: spmv_csr_kernel<TT, MODE><<<grid, kThreads, 0, ctx->stream>>>(M.indptr, M.cols, M.vals, M.nrows, x, b, y, ctx->d_partial, ctx->d_counter, sumsq_out); break;
+    switch (T) { SPIS_CSR_CASE(2) SPIS_CSR_CASE(4) SPIS_CSR_CASE(8) SPIS_CSR_CASE(16) default: SPIS_CSR_CASE(32) }
+#undef SPIS_CSR_CASE
+  }
+  CU(cudaGetLastError());
+  return SPIS_OK;
+}
+
+// mode 0: y = Mx ; 1: y = b - Mx, sumsq ; 2: sumsq = ||Mx - b||^2.  x must have its halo filled.
+int launch_spmv(spis_ctx* ctx, int slot, int mode, const double* x, const double* b, double* y, double* sumsq_out) {
+  const Matrix& M = ctx->mats[slot];
+  REQUIRE(M.present, "matrix slot %d has not been uploaded", slot);
+  const double bytes = 12.0 * (double)M.nnz + 4.0 * (double)(M.nrows + 1) + (mode == 1 ? 24.0 : 16.0) * (double)M.nrows;
+  TRY(prof_begin(ctx, SPIS_PROF_SPMV, bytes));
+  if (mode == 0) TRY(launch_spmv_mode<0>(ctx, M, x, b, y, sumsq_out));
+  else if (mode == 1) TRY(launch_spmv_mode<1>(ctx, M, x, b, y, sumsq_out));
+  else TRY(launch_spmv_mode<2>(ctx, M, x, b, y, sumsq_out));
+  TRY(prof_end(ctx));
+  if (mode != 0) return do_allreduce(ctx, sumsq_out, 1);
+  return SPIS_OK;
+}
+
+int launch_scale(spis_ctx* ctx, double* v, const double* sumsq, const double* jac, double* znext) {
+  const int grid = grid_for(ctx, (ctx->n + 2 * kThreads - 1) / (2 * kThreads), 8);
+  TRY(prof_begin(ctx, SPIS_PROF_SCALE, (jac ? 32.0 : 16.0) * (double)ctx->n));
+  scale_kernel<<<grid, kThreads, 0, ctx->stream>>>(v, sumsq, ctx->n, jac, znext);
+  CU(cudaGetLastError());
+  return prof_end(ctx);
+}
+
+int launch_precond(spis_ctx* ctx, const double* q, double* z) {
+  switch (ctx->pre_kind) {
+    case SPIS_PRE_JACOBI: {
+      REQUIRE(ctx->pre_diag, "Jacobi preconditioner: diagonal not uploaded");
+      const int grid = grid_for(ctx, (ctx->n + 2 * kThreads - 1) / (2 * kThreads), 8);
+      TRY(prof_begin(ctx, SPIS_PROF_PRECOND, 24.0 * (double)ctx->n));
+      jacobi_kernel<<<grid, kThreads, 0, ctx->stream>>>(ctx->pre_diag, q, z, ctx->n);
+      CU(cudaGetLastError());
+      return prof_end(ctx);
+    }
+    case SPIS_PRE_CSR: {
+      // the sparse preconditioner sees q through the same ghost layout as A
+      TRY(do_halo(ctx, const_cast<double*>(q)));
+      const Matrix& M = ctx->mats[SPIS_SLOT_PRE];
+      REQUIRE(M.present, "sparse preconditioner not uploaded");
+      const double bytes = 12.0 * (double)M.nnz + 4.0 * (double)(M.nrows + 1) + 16.0 * (double)M.nrows;
+      TRY(prof_begin(ctx, SPIS_PROF_PRECOND, bytes));
+      TRY(launch_spmv_mode<0>(ctx, M, q, nullptr, z, nullptr));
+      return prof_end(ctx);
+    }
+    case SPIS_PRE_BLOCK: {
+      REQUIRE(ctx->pre_blocks, "block preconditioner not uploaded");
+      const int grid = grid_for(ctx, (ctx->pre_nblk + kThreads - 1) / kThreads, 8);
+      const int bs = ctx->pre_bs;
+      TRY(prof_begin(ctx, SPIS_PROF_PRECOND, (8.0 * bs * bs + 16.0 * bs) * (double)ctx->pre_nblk));
+#define SPIS_BLK_CASE(BB) case BB: blockdiag_kernel<BB><<<grid, kThreads, 0, ctx->stream>>>(ctx->pre_blocks, ctx->pre_nblk, ctx->pre_sb, ctx->pre_sf, q, z); break;
+      switch (bs) { SPIS_BLK_CASE(1) SPIS_BLK_CASE(2) SPIS_BLK_CASE(3) SPIS_BLK_CASE(4) SPIS_BLK_CASE(5) SPIS_BLK_CASE(6) SPIS_BLK_CASE(7) SPIS_BLK_CASE(8)
+        default: return fail(ctx, SPIS_E_UNSUPPORTED, "block size %d not supported (1..8)", bs); }
+#undef SPIS_BLK_CASE
+      CU(cudaGetLastError());
+      return prof_end(ctx);
+    }
+    default:
+      return fail(ctx, SPIS_E_INVALID, "launch_precond called for kind %d", ctx->pre_kind);
+  }
+}
+
+void free_matrix(Matrix& M) {
+  cudaFree(M.indptr); cudaFree(M.cols); cudaFree(M.vals);
+  cudaFree(M.slice_off); cudaFree(M.scols); cudaFree(M.svals);
+  M = Matrix();
+}
+
+inline double* zbase(spis_ctx* ctx) { return ctx->pre_kind == SPIS_PRE_NONE ? ctx->V : ctx->Z; }
+
+int ensure_Z(spis_ctx* ctx) {
+  if (ctx->pre_kind != SPIS_PRE_NONE && !ctx->Z) TRY(dalloc(ctx, &ctx->Z, (size_t)ctx->kmax * ctx->ld));
+  return SPIS_OK;
+}
+
+}  // namespace
+
+// =========================================================================================
+extern "C" {
+
+int spis_abi_version(void) { return SPIS_ABI_VERSION; }
+
+const char* spis_last_error(const spis_ctx* ctx) { return ctx ? ctx->err : g_global_err; }
+const char* spis_last_global_error(void) { return g_global_err; }
+
+int spis_device_count(int* count_out) {
+  spis_ctx* ctx = nullptr;
+  if (!count_out) return fail(ctx, SPIS_E_INVALID, "count_out is null");
+  CU(cudaGetDeviceCount(count_out));
+  return SPIS_OK;
+}
+
+int spis_ctx_create(int device, int64_t n, int64_t n_halo, int k_max, void* stream, spis_ctx** ctx_out) {
+  spis_ctx* ctx = nullptr;
+  if (!ctx_out) return fail(ctx, SPIS_E_INVALID, "ctx_out is null");
+  *ctx_out = nullptr;
+  if (n <= 0 || n_halo < 0 || k_max <= 0 || k_max > 2048) return fail(ctx, SPIS_E_INVALID, "bad sizes n=%lld n_halo=%lld k_max=%d", (long long)n, (long long)n_halo, k_max);
+  if (n + n_halo + 64 >= (int64_t)INT32_MAX) return fail(ctx, SPIS_E_UNSUPPORTED, "n + n_halo must fit int32 column indices");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail(ctx, SPIS_E_CUDA, "no CUDA device available (%s); this library has no CPU path", cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(ctx, SPIS_E_INVALID, "device %d out of range (%d devices)", device, ndev);
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail(ctx, SPIS_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return fail(ctx, SPIS_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major < 10) return fail(ctx, SPIS_E_UNSUPPORTED, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
+
+  spis_ctx* c = new spis_ctx();
+  ctx = c;
+  c->device = device;
+  c->nsm = prop.multiProcessorCount;
+  c->n = n; c->n_halo = n_halo;
+  c->hoff = roundup(n, 16);
+  c->ld = roundup(c->hoff + n_halo, 16);
+  c->kmax = k_max; c->K = k_max + 4;
+  c->pstride = c->K;
+  c->max_grid = c->nsm * 16;
+  auto bail = [&](int code) { std::string msg = c->err; spis_ctx_destroy(c); snprintf(g_global_err, sizeof(g_global_err), "%s", msg.c_str()); return code; };
+#define CTRY(call) do { int r_ = (call); if (r_ != SPIS_OK) return bail(r_); } while (0)
+#define CCU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(c, e_ == cudaErrorMemoryAllocation ? SPIS_E_NOMEM : SPIS_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); return bail(e_ == cudaErrorMemoryAllocation ? SPIS_E_NOMEM : SPIS_E_CUDA); } } while (0)
+  if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
+  else { CCU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+  CCU(cudaEventCreateWithFlags(&c->ev_arnoldi, cudaEventDisableTiming));
+  CCU(cudaEventCreate(&c->ev_t0));
+  CCU(cudaEventCreate(&c->ev_t1));
+  const size_t ld = (size_t)c->ld;
+  CTRY(dalloc(c, &c->V, (size_t)(k_max + 1) * ld));
+  CTRY(dalloc(c, &c->W, ld));
+  CTRY(dalloc(c, &c->T, ld));
+  CTRY(dalloc(c, &c->R0, ld));
+  CTRY(dalloc(c, &c->B, ld));
+  CTRY(dalloc(c, &c->X0, ld));
+  CTRY(dalloc(c, &c->X, ld));
+  CTRY(dalloc(c, &c->d_small, (size_t)2 * c->K + 8));
+  CTRY(dalloc(c, &c->d_y, (size_t)c->K));
+  CTRY(dalloc(c, &c->d_cout, (size_t)k_max * 2 * c->K));
+  CTRY(dalloc(c, &c->d_partial, (size_t)c->max_grid * c->pstride));
+  CTRY(dalloc(c, &c->d_counter, 4));
+  CCU(cudaMallocHost((void**)&c->h_small, ((size_t)2 * c->K + 8) * sizeof(double)));
+  CCU(cudaMallocHost((void**)&c->h_y, (size_t)c->K * sizeof(double)));
+  CCU(cudaMallocHost((void**)&c->h_cout, (size_t)k_max * 2 * c->K * sizeof(double)));
+  // mdot needs up to (8*(K)+256)*8 bytes of dynamic shared memory
+  const int smem_need = (kWarps * c->K + kWarps * 32) * (int)sizeof(double);
+  if (smem_need > 48 * 1024) {
+    CCU(cudaFuncSetAttribute(mdot_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_need));
+    CCU(cudaFuncSetAttribute(mdot_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_need));
+    CCU(cudaFuncSetAttribute(mdot_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_need));
+  }
+  CCU(cudaStreamSynchronize(c->stream));
+#undef CTRY
+#undef CCU
+  *ctx_out = c;
+  return SPIS_OK;
+}
+
+int spis_ctx_destroy(spis_ctx* ctx) {
+  if (!ctx) return SPIS_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (auto& r : ctx->recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  for (auto& e : ctx->evpool) cudaEventDestroy(e);
+  for (auto& M : ctx->mats) free_matrix(M);
+  for (auto& c : ctx->cons) { cudaFree(c.v); cudaFree(c.MZ); }
+  cudaFree(ctx->V); cudaFree(ctx->Z); cudaFree(ctx->W); cudaFree(ctx->T); cudaFree(ctx->R0);
+  cudaFree(ctx->B); cudaFree(ctx->X0); cudaFree(ctx->X); cudaFree(ctx->pre_diag); cudaFree(ctx->pre_blocks);
+  cudaFree(ctx->d_small); cudaFree(ctx->d_y); cudaFree(ctx->d_cout); cudaFree(ctx->d_partial); cudaFree(ctx->d_counter);
+  cudaFreeHost(ctx->h_small); cudaFreeHost(ctx->h_y); cudaFreeHost(ctx->h_cout);
+  if (ctx->ev_arnoldi) cudaEventDestroy(ctx->ev_arnoldi);
+  if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
+  if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return SPIS_OK;
+}
+
+int spis_set_option(spis_ctx* ctx, const char* key, int64_t value) {
+  if (!ctx || !key) return SPIS_E_INVALID;
+  std::string k(key);
+  if (k == "orth") { REQUIRE(value >= 0 && value <= 2, "orth must be 0..2"); ctx->orth = (int)value; }
+  else if (k == "spmv_format") { REQUIRE(value >= 0 && value <= 2, "spmv_format must be 0..2"); ctx->fmt_pref = (int)value; }
+  else if (k == "profile") { ctx->profile = value ? 1 : 0; }
+  else if (k == "ctas_per_sm") { REQUIRE(value >= 1 && value <= 16, "ctas_per_sm must be 1..16"); ctx->ctas_per_sm = (int)value; }
+  else if (k == "spmv_ctas_per_sm") { REQUIRE(value >= 1 && value <= 16, "spmv_ctas_per_sm must be 1..16"); ctx->spmv_ctas_per_sm = (int)value; }
+  else if (k == "mdot_variant") { REQUIRE(value == 2 || value == 4 || value == 8, "mdot_variant must be 2, 4 or 8"); ctx->mdot_variant = (int)value; }
+  else if (k == "lincomb_variant") { REQUIRE(value == 2 || value == 4 || value == 8, "lincomb_variant must be 2, 4 or 8"); ctx->lincomb_variant = (int)value; }
+  else if (k == "x0_is_zero") { ctx->x0_is_zero = value ? 1 : 0; }
+  else if (k == "fuse_jacobi") { ctx->fuse_jacobi = value ? 1 : 0; }
+  else return fail(ctx, SPIS_E_INVALID, "unknown option '%s'", key);
+  return SPIS_OK;
+}
+
+int spis_get_info(const spis_ctx* cctx, const char* key, int64_t* value_out) {
+  spis_ctx* ctx = const_cast<spis_ctx*>(cctx);
+  if (!ctx || !key || !value_out) return SPIS_E_INVALID;
+  std::string k(key);
+  if (k == "n") *value_out = ctx->n;
+  else if (k == "ld") *value_out = ctx->ld;
+  else if (k == "hoff") *value_out = ctx->hoff;
+  else if (k == "n_halo") *value_out = ctx->n_halo;
+  else if (k == "k_max") *value_out = ctx->kmax;
+  else if (k == "num_sms") *value_out = ctx->nsm;
+  else if (k == "device") *value_out = ctx->device;
+  else if (k.rfind("fmt:", 0) == 0 || k.rfind("nnz_padded:", 0) == 0 || k.rfind("nnz:", 0) == 0) {
+    const int slot = atoi(k.c_str() + k.find(':') + 1);
+    REQUIRE(slot >= 0 && slot < SPIS_MAX_SLOTS && ctx->mats[slot].present, "slot %d not uploaded", slot);
+    if (k[0] == 'f') *value_out = ctx->mats[slot].fmt;
+    else if (k.rfind("nnz_padded:", 0) == 0) *value_out = ctx->mats[slot].nnz_padded;
+    else *value_out = ctx->mats[slot].nnz;
+  }
+  else if (k == "device_ptr:small") *value_out = (int64_t)(intptr_t)ctx->d_small;
+  else return fail(ctx, SPIS_E_INVALID, "unknown info key '%s'", key);
+  return SPIS_OK;
+}
+
+// ---- uploads --------------------------------------------------------------------------
+int spis_upload_csr(spis_ctx* ctx, int slot, int64_t nrows, int64_t ncols, int64_t nnz,
+                    const int32_t* indptr, const int32_t* indices, const double* data) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(slot >= 0 && slot < SPIS_MAX_SLOTS, "slot %d out of range", slot);
+  REQUIRE(nrows == ctx->n, "matrix has %lld rows, context owns %lld", (long long)nrows, (long long)ctx->n);
+  REQUIRE(ncols >= 0 && ncols <= ctx->n + ctx->n_halo, "matrix has %lld columns, context allows %lld", (long long)ncols, (long long)(ctx->n + ctx->n_halo));
+  REQUIRE(nnz >= 0 && nnz < (int64_t)INT32_MAX, "nnz %lld must fit int32 row pointers", (long long)nnz);
+  REQUIRE(indptr && (nnz == 0 || (indices && data)), "null CSR arrays");
+  CU(cudaSetDevice(ctx->device));
+  Matrix& M = ctx->mats[slot];
+  free_matrix(M);
+  M.nrows = nrows; M.ncols = ncols; M.nnz = nnz;
+  TRY(dalloc(ctx, &M.indptr, (size_t)nrows + 1, false));
+  TRY(dalloc(ctx, &M.cols, (size_t)nnz, false));
+  TRY(dalloc(ctx, &M.vals, (size_t)nnz, false));
+  CU(cudaMemcpyAsync(M.indptr, indptr, ((size_t)nrows + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  if (nnz) {
+    CU(cudaMemcpyAsync(M.cols, indices, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(M.vals, data, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (ctx->n_halo > 0 && ctx->hoff != ctx->n && nnz)
+    remap_cols_kernel<<<ctx->nsm * 8, 256, 0, ctx->stream>>>(M.cols, nnz, (int32_t)ctx->n, (int32_t)(ctx->hoff - ctx->n));
+  // SELL-32 slice widths -> offsets (tiny scan on the host)
+  const int64_t nslices = (nrows + 31) / 32;
+  int32_t* d_width = nullptr;
+  TRY(dalloc(ctx, &d_width, (size_t)nslices, false));
+  const int cgrid = (int)((nslices * 32 + 255) / 256);
+  sell_width_kernel<<<cgrid, 256, 0, ctx->stream>>>(M.indptr, nrows, d_width);
+  CU(cudaGetLastError());
+  std::vector<int32_t> width((size_t)nslices);
+  CU(cudaMemcpyAsync(width.data(), d_width, (size_t)nslices * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_width);
+  std::vector<int64_t> off((size_t)nslices + 1);
+  off[0] = 0;
+  for (int64_t s = 0; s < nslices; ++s) off[s + 1] = off[s] + (int64_t)width[s] * 32;
+  M.nnz_padded = off[nslices];
+  int fmt = ctx->fmt_pref;
+  if (fmt == SPIS_FMT_AUTO) fmt = ((double)M.nnz_padded <= 1.25 * (double)(nnz > 0 ? nnz : 1) + 32.0 * 64.0) ? SPIS_FMT_SELL : SPIS_FMT_CSR;
+  M.fmt = fmt;
+  if (fmt == SPIS_FMT_SELL) {
+    TRY(dalloc(ctx, &M.slice_off, (size_t)nslices + 1, false));
+    TRY(dalloc(ctx, &M.scols, (size_t)M.nnz_padded, false));
+    TRY(dalloc(ctx, &M.svals, (size_t)M.nnz_padded, false));
+    CU(cudaMemcpyAsync(M.slice_off, off.data(), ((size_t)nslices + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    sell_fill_kernel<<<cgrid, 256, 0, ctx->stream>>>(M.indptr, M.cols, M.vals, nrows, M.slice_off, M.scols, M.svals);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(M.indptr); cudaFree(M.cols); cudaFree(M.vals);
+    M.indptr = nullptr; M.cols = nullptr; M.vals = nullptr;
+  } else {
+    const double avg = nrows ? (double)nnz / (double)nrows : 0.0;
+    M.csr_lanes = avg <= 3 ? 2 : avg <= 6 ? 4 : avg <= 12 ? 8 : avg <= 24 ? 16 : 32;
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  M.present = true;
+  return SPIS_OK;
+}
+
+int spis_upload_vec(spis_ctx* ctx, int which, const double* host, int64_t n) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(host, "host pointer is null");
+  REQUIRE(n == ctx->n, "vector length %lld != n %lld", (long long)n, (long long)ctx->n);
+  CU(cudaSetDevice(ctx->device));
+  double* dst = nullptr;
+  switch (which) {
+    case SPIS_VEC_B: dst = ctx->B; break;
+    case SPIS_VEC_X0: dst = ctx->X0; break;
+    case SPIS_VEC_PRE_DIAG:
+      if (!ctx->pre_diag) TRY(dalloc(ctx, &ctx->pre_diag, (size_t)ctx->ld));
+      dst = ctx->pre_diag; break;
+    default: return fail(ctx, SPIS_E_INVALID, "vector id %d cannot be uploaded", which);
+  }
+  return h2d(ctx, dst, host, (size_t)n * sizeof(double));
+}
+
+int spis_upload_blocks(spis_ctx* ctx, int bs, int64_t nblk, int64_t sb, int64_t sf, const double* blocks) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(bs >= 1 && bs <= 8, "block size %d not supported (1..8)", bs);
+  REQUIRE(blocks && nblk > 0, "null blocks");
+  REQUIRE((nblk - 1) * sb + (bs - 1) * sf < ctx->n, "block index map exceeds n");
+  CU(cudaSetDevice(ctx->device));
+  cudaFree(ctx->pre_blocks); ctx->pre_blocks = nullptr;
+  TRY(dalloc(ctx, &ctx->pre_blocks, (size_t)bs * bs * nblk, false));
+  // host layout [i][r][c] -> device structure-of-arrays [(r*bs+c)][i]
+  std::vector<double> soa((size_t)bs * bs * nblk);
+  for (int64_t i = 0; i < nblk; ++i)
+    for (int rc = 0; rc < bs * bs; ++rc) soa[(size_t)rc * nblk + i] = blocks[(size_t)i * bs * bs + rc];
+  TRY(h2d(ctx, ctx->pre_blocks, soa.data(), soa.size() * sizeof(double)));
+  ctx->pre_bs = bs; ctx->pre_nblk = nblk; ctx->pre_sb = sb; ctx->pre_sf = sf;
+  return SPIS_OK;
+}
+
+int spis_set_precond(spis_ctx* ctx, int kind) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(kind >= SPIS_PRE_NONE && kind <= SPIS_PRE_HOST, "unknown preconditioner kind %d", kind);
+  CU(cudaSetDevice(ctx->device));
+  ctx->pre_kind = kind;
+  ctx->began = false;
+  return ensure_Z(ctx);
+}
+
+// ---- Krylov loop ----------------------------------------------------------------------
+int spis_solve_begin(spis_ctx* ctx, double* beta_out) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(beta_out, "beta_out is null");
+  CU(cudaSetDevice(ctx->device));
+  TRY(ensure_Z(ctx));
+  double* scal = ctx->d_small + 2 * ctx->K;
+  TRY(do_halo(ctx, ctx->X0));
+  TRY(launch_spmv(ctx, SPIS_SLOT_A, 1, ctx->X0, ctx->B, ctx->R0, scal + 1));
+  TRY(prof_begin(ctx, SPIS_PROF_OTHER, 16.0 * (double)ctx->n));
+  CU(cudaMemcpyAsync(ctx->V, ctx->R0, (size_t)ctx->hoff * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  TRY(prof_end(ctx));
+  ctx->z_ready_index = -1;
+  const bool fuse = ctx->pre_kind == SPIS_PRE_JACOBI && ctx->fuse_jacobi && ctx->pre_diag;
+  TRY(launch_scale(ctx, ctx->V, scal + 1, fuse ? ctx->pre_diag : nullptr, fuse ? ctx->Z : nullptr));
+  if (fuse) ctx->z_ready_index = 0;
+  CU(cudaMemcpyAsync(ctx->h_small + 2 * ctx->K, scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  *beta_out = std::sqrt(ctx->h_small[2 * ctx->K + 1]);
+  for (auto& c : ctx->cons) { c.cols_done = 0; c.term0_done = false; }
+  ctx->began = true;
+  ctx->arnoldi_inflight = -1;
+  return SPIS_OK;
+}
+
+int spis_arnoldi_launch(spis_ctx* ctx, int j) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(ctx->began, "spis_solve_begin has not been called");
+  REQUIRE(j >= 0 && j < ctx->kmax, "Arnoldi index %d out of range [0,%d)", j, ctx->kmax);
+  REQUIRE(ctx->arnoldi_inflight < 0, "Arnoldi step %d is still in flight", ctx->arnoldi_inflight);
+  CU(cudaSetDevice(ctx->device));
+  const int m = j + 1;
+  const size_t ld = (size_t)ctx->ld;
+  double* qj = ctx->V + (size_t)j * ld;
+  double* qn = ctx->V + (size_t)(j + 1) * ld;
+  double* zj = zbase(ctx) + (size_t)j * ld;
+  double* h1 = ctx->d_small;
+  double* h2 = ctx->d_small + ctx->K;
+  double* scal = ctx->d_small + 2 * ctx->K;
+  // z[j] = P q[j]                                                  (solvers.py:190)
+  if (ctx->pre_kind != SPIS_PRE_NONE && ctx->pre_kind != SPIS_PRE_HOST && ctx->z_ready_index != j)
+    TRY(launch_precond(ctx, qj, zj));
+  // w = A z[j]                                                     (solvers.py:191)
+  TRY(do_halo(ctx, zj));
+  TRY(launch_spmv(ctx, SPIS_SLOT_A, 0, zj, nullptr, ctx->W, nullptr));
+  // orthogonalise w against q[0..j]                                (solvers.py:193-196)
+  if (ctx->orth == SPIS_ORTH_MGS) {
+    CU(cudaMemsetAsync(h2, 0, (size_t)ctx->K * sizeof(double), ctx->stream));
+    for (int i = 0; i < m; ++i) {
+      const double* qi = ctx->V + (size_t)i * ld;
+      TRY(launch_mdot(ctx, qi, 1, nullptr, 0, ctx->W, h1 + i));
+      const bool last = (i == m - 1);
+      TRY(launch_lincomb(ctx, qi, 1, h1 + i, nullptr, -1.0, ctx->W, last ? qn : ctx->W, last ? 1 : 0, scal));
+    }
+  } else if (ctx->orth == SPIS_ORTH_CGS1) {
+    CU(cudaMemsetAsync(h2, 0, (size_t)ctx->K * sizeof(double), ctx->stream));
+    TRY(launch_mdot(ctx, ctx->V, m, nullptr, 0, ctx->W, h1));
+    TRY(launch_lincomb(ctx, ctx->V, m, h1, nullptr, -1.0, ctx->W, qn, 1, scal));
+  } else {
+    TRY(launch_mdot(ctx, ctx->V, m, nullptr, 0, ctx->W, h1));
+    TRY(launch_lincomb(ctx, ctx->V, m, h1, nullptr, -1.0, ctx->W, ctx->W, 0, nullptr));
+    TRY(launch_mdot(ctx, ctx->V, m, nullptr, 0, ctx->W, h2));
+    TRY(launch_lincomb(ctx, ctx->V, m, h2, nullptr, -1.0, ctx->W, qn, 1, scal));
+  }
+  // q[j+1] = w / ||w||                                             (solvers.py:196-198)
+  const bool fuse = ctx->pre_kind == SPIS_PRE_JACOBI && ctx->fuse_jacobi && ctx->pre_diag && (j + 1 < ctx->kmax);
+  TRY(launch_scale(ctx, qn, scal, fuse ? ctx->pre_diag : nullptr, fuse ? ctx->Z + (size_t)(j + 1) * ld : nullptr));
+  ctx->z_ready_index = fuse ? j + 1 : -1;
+  CU(cudaMemcpyAsync(ctx->h_small, ctx->d_small, ((size_t)2 * ctx->K + 8) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaEventRecord(ctx->ev_arnoldi, ctx->stream));
+  ctx->arnoldi_inflight = j;
+  return SPIS_OK;
+}
+
+int spis_arnoldi_wait(spis_ctx* ctx, int j, double* hcol_out) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(hcol_out, "hcol_out is null");
+  REQUIRE(ctx->arnoldi_inflight == j, "Arnoldi step %d was not launched (in flight: %d)", j, ctx->arnoldi_inflight);
+  CU(cudaEventSynchronize(ctx->ev_arnoldi));
+  const int m = j + 1;
+  for (int i = 0; i < m; ++i) hcol_out[i] = ctx->h_small[i] + ctx->h_small[ctx->K + i];
+  hcol_out[m] = std::sqrt(ctx->h_small[2 * ctx->K]);
+  ctx->arnoldi_inflight = -1;
+  return SPIS_OK;
+}
+
+int spis_arnoldi_step(spis_ctx* ctx, int j, double* hcol_out) {
+  TRY(spis_arnoldi_launch(ctx, j));
+  return spis_arnoldi_wait(ctx, j, hcol_out);
+}
+
+static int form_iterate_impl(spis_ctx* ctx, int m, const double* y) {
+  REQUIRE(ctx->began, "spis_solve_begin has not been called");
+  REQUIRE(m >= 0 && m <= ctx->kmax && (y || m == 0), "bad iterate arguments (m=%d)", m);
+  CU(cudaSetDevice(ctx->device));
+  if (m) {
+    // h_y may still be the source of an earlier async copy only if the stream has not
+    // drained; every path that uses it synchronises before returning, so it is free here.
+    memcpy(ctx->h_y, y, (size_t)m * sizeof(double));
+    CU(cudaMemcpyAsync(ctx->d_y, ctx->h_y, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  // x_j = x0 + Z y                                                 (solvers.py:287)
+  TRY(launch_lincomb(ctx, zbase(ctx), m, ctx->d_y, nullptr, 1.0, ctx->x0_is_zero ? nullptr : ctx->X0, ctx->X, 0, nullptr));
+  return SPIS_OK;
+}
+
+int spis_form_iterate(spis_ctx* ctx, int m, const double* y) {
+  if (!ctx) return SPIS_E_INVALID;
+  TRY(form_iterate_impl(ctx, m, y));
+  CU(cudaStreamSynchronize(ctx->stream));   // h_y staging is free again when this returns
+  return SPIS_OK;
+}
+
+int spis_iterate_residual(spis_ctx* ctx, int m, const double* y, double* resnorm_out) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(resnorm_out, "resnorm_out is null");
+  TRY(form_iterate_impl(ctx, m, y));
+  double* scal = ctx->d_small + 2 * ctx->K;
+  // ||A x_j - b||                                                  (solvers.py:290)
+  TRY(do_halo(ctx, ctx->X));
+  TRY(launch_spmv(ctx, SPIS_SLOT_A, 2, ctx->X, ctx->B, nullptr, scal + 2));
+  CU(cudaMemcpyAsync(ctx->h_small + 2 * ctx->K + 2, scal + 2, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  *resnorm_out = std::sqrt(ctx->h_small[2 * ctx->K + 2]);
+  return SPIS_OK;
+}
+
+// ---- constraint stage -----------------------------------------------------------------
+int spis_constraint_define(spis_ctx* ctx, int c, int mat_slot, const double* v, double cc) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(c >= 0 && c < SPIS_MAX_SLOTS, "constraint index %d out of range", c);
+  REQUIRE(mat_slot < SPIS_MAX_SLOTS, "matrix slot %d out of range", mat_slot);
+  REQUIRE(mat_slot < 0 || ctx->mats[mat_slot].present, "constraint matrix slot %d not uploaded", mat_slot);
+  CU(cudaSetDevice(ctx->device));
+  Constraint& C = ctx->cons[c];
+  C.defined = true; C.slot = mat_slot; C.cc = cc; C.cols_done = 0; C.term0_done = false;
+  if (v) {
+    if (!C.v) TRY(dalloc(ctx, &C.v, (size_t)ctx->ld));
+    TRY(h2d(ctx, C.v, v, (size_t)ctx->n * sizeof(double)));
+  } else if (C.v) { cudaFree(C.v); C.v = nullptr; }
+  if (mat_slot < 0 && C.MZ) { cudaFree(C.MZ); C.MZ = nullptr; }
+  C.T1.assign((size_t)ctx->kmax, 0.0);
+  C.T2.assign((size_t)ctx->kmax * ctx->kmax, 0.0);
+  return SPIS_OK;
+}
+
+int spis_constraint_terms(spis_ctx* ctx, int c, int m, double* term0, double* term1, double* term2) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(c >= 0 && c < SPIS_MAX_SLOTS && ctx->cons[c].defined, "constraint %d not defined", c);
+  REQUIRE(ctx->began, "spis_solve_begin has not been called");
+  REQUIRE(m >= 1 && m <= ctx->kmax, "m=%d out of range", m);
+  REQUIRE(term0 && term1 && term2, "null output");
+  CU(cudaSetDevice(ctx->device));
+  Constraint& C = ctx->cons[c];
+  const size_t ld = (size_t)ctx->ld;
+  const int K = ctx->K;
+  const bool hasM = C.slot >= 0;
+  const bool x0nz = !ctx->x0_is_zero;
+  double* Zb = zbase(ctx);
+  if (hasM && !C.MZ) TRY(dalloc(ctx, &C.MZ, (size_t)ctx->kmax * ld));
+  // term0 = 1/2 x0.M x0 + c + v.x0                                 (solvers.py:34)
+  if (!C.term0_done) {
+    double t = C.cc;
+    if (x0nz && (hasM || C.v)) {
+      double* o = ctx->d_cout;  // scratch: first 2 entries
+      if (hasM) {
+        TRY(do_halo(ctx, ctx->X0));
+        TRY(launch_spmv(ctx, C.slot, 0, ctx->X0, nullptr, ctx->T, nullptr));
+      }
+      TRY(launch_mdot(ctx, ctx->T, hasM ? 1 : 0, C.v, 0, ctx->X0, o));
+      TRY(d2h(ctx, ctx->h_cout, o, 2 * sizeof(double)));
+      int idx = 0;
+      if (hasM) t += 0.5 * ctx->h_cout[idx++];
+      if (C.v) t += ctx->h_cout[idx++];
+    }
+    C.term0 = t; C.term0_done = true;
+  }
+  const int c0 = C.cols_done;
+  for (int col = c0; col < m; ++col) {
+    double* zc = Zb + (size_t)col * ld;
+    double* oA = ctx->d_cout + (size_t)col * 2 * K;
+    double* oB = oA + K;
+    if (hasM) {
+      double* mz = C.MZ + (size_t)col * ld;
+      // MZ[:,col] = M z_col   (z_col's ghost entries were filled by the Arnoldi step)    (:33)
+      TRY(launch_spmv(ctx, C.slot, 0, zc, nullptr, mz, nullptr));
+      // column col of Z^T MZ, and x0.MZ_col                                               (:35-36)
+      TRY(launch_mdot(ctx, Zb, col + 1, x0nz ? ctx->X0 : nullptr, 0, mz, oA));
+      // row col of Z^T MZ (MZ_i.z_col, i<col), and v.z_col
+      if (col > 0 || C.v) TRY(launch_mdot(ctx, C.MZ, col, C.v, 0, zc, oB));
+    } else if (C.v) {
+      TRY(launch_mdot(ctx, nullptr, 0, C.v, 0, zc, oB));
+    }
+  }
+  if (m > c0) {
+    TRY(d2h(ctx, ctx->h_cout + (size_t)c0 * 2 * K, ctx->d_cout + (size_t)c0 * 2 * K, (size_t)(m - c0) * 2 * K * sizeof(double)));
+    const int km = ctx->kmax;
+    for (int col = c0; col < m; ++col) {
+      const double* oA = ctx->h_cout + (size_t)col * 2 * K;
+      const double* oB = oA + K;
+      double t1 = 0.0;
+      if (hasM) {
+        for (int i = 0; i <= col; ++i) C.T2[(size_t)i * km + col] = 0.5 * oA[i];
+        if (x0nz) t1 += oA[col + 1];
+        for (int i = 0; i < col; ++i) C.T2[(size_t)col * km + i] = 0.5 * oB[i];
+        if (C.v) t1 += oB[col];
+      } else if (C.v) {
+        t1 += oB[0];
+      }
+      C.T1[col] = t1;
+    }
+    C.cols_done = m;
+  }
+  *term0 = C.term0;
+  for (int i = 0; i < m; ++i) term1[i] = C.T1[i];
+  for (int i = 0; i < m; ++i)
+    for (int k = 0; k < m; ++k) term2[(size_t)i * m + k] = C.T2[(size_t)i * ctx->kmax + k];
+  return SPIS_OK;
+}
+
+// ---- downloads / host bridges ---------------------------------------------------------
+int spis_download_vec(spis_ctx* ctx, int which, int j, double* host, int64_t n) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(host && n == ctx->n, "bad download arguments");
+  CU(cudaSetDevice(ctx->device));
+  const double* src = nullptr;
+  switch (which) {
+    case SPIS_VEC_B: src = ctx->B; break;
+    case SPIS_VEC_X0: src = ctx->X0; break;
+    case SPIS_VEC_R0: src = ctx->R0; break;
+    case SPIS_VEC_X: src = ctx->X; break;
+    case SPIS_VEC_W: src = ctx->W; break;
+    case SPIS_VEC_Q: REQUIRE(j >= 0 && j <= ctx->kmax, "q index %d out of range", j); src = ctx->V + (size_t)j * ctx->ld; break;
+    case SPIS_VEC_Z: REQUIRE(j >= 0 && j < ctx->kmax, "z index %d out of range", j); src = zbase(ctx) + (size_t)j * ctx->ld; break;
+    default: return fail(ctx, SPIS_E_INVALID, "vector id %d cannot be downloaded", which);
+  }
+  return d2h(ctx, host, src, (size_t)n * sizeof(double));
+}
+
+int spis_download_Z(spis_ctx* ctx, int j0, int j1, double* host) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(host && j0 >= 0 && j0 <= j1 && j1 <= ctx->kmax, "bad Z range [%d,%d)", j0, j1);
+  CU(cudaSetDevice(ctx->device));
+  if (j1 == j0) return SPIS_OK;
+  CU(cudaMemcpy2DAsync(host, (size_t)ctx->n * sizeof(double), zbase(ctx) + (size_t)j0 * ctx->ld, (size_t)ctx->ld * sizeof(double),
+                       (size_t)ctx->n * sizeof(double), (size_t)(j1 - j0), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return SPIS_OK;
+}
+
+int spis_host_pre_get(spis_ctx* ctx, int j, double* q_host) {
+  return spis_download_vec(ctx, SPIS_VEC_Q, j, q_host, ctx ? ctx->n : 0);
+}
+
+int spis_host_pre_put(spis_ctx* ctx, int j, const double* z_host) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(ctx->pre_kind == SPIS_PRE_HOST, "host preconditioner bridge is not selected");
+  REQUIRE(z_host && j >= 0 && j < ctx->kmax, "bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  TRY(ensure_Z(ctx));
+  return h2d(ctx, ctx->Z + (size_t)j * ctx->ld, z_host, (size_t)ctx->n * sizeof(double));
+}
+
+int spis_set_collectives(spis_ctx* ctx, spis_allreduce_fn allreduce, spis_halo_fn halo, void* user) {
+  if (!ctx) return SPIS_E_INVALID;
+  ctx->allreduce = allreduce; ctx->halo = halo; ctx->cuser = user;
+  return SPIS_OK;
+}
+
+int spis_sync(spis_ctx* ctx) {
+  if (!ctx) return SPIS_E_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return SPIS_OK;
+}
+
+// ---- measurement ----------------------------------------------------------------------
+int spis_get_profile(spis_ctx* ctx, double* ms_out, double* bytes_out, int64_t* launches_out) {
+  if (!ctx) return SPIS_E_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  TRY(prof_resolve(ctx));
+  for (int i = 0; i < SPIS_PROF_CLASSES; ++i) {
+    if (ms_out) ms_out[i] = ctx->prof_ms[i];
+    if (bytes_out) bytes_out[i] = ctx->prof_bytes[i];
+    if (launches_out) launches_out[i] = ctx->prof_launch[i];
+  }
+  return SPIS_OK;
+}
+
+int spis_reset_profile(spis_ctx* ctx) {
+  if (!ctx) return SPIS_E_INVALID;
+  TRY(prof_resolve(ctx));
+  for (int i = 0; i < SPIS_PROF_CLASSES; ++i) { ctx->prof_ms[i] = 0; ctx->prof_bytes[i] = 0; ctx->prof_launch[i] = 0; }
+  return SPIS_OK;
+}
+
+int spis_timer_start(spis_ctx* ctx) {
+  if (!ctx) return SPIS_E_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaEventRecord(ctx->ev_t0, ctx->stream));
+  return SPIS_OK;
+}
+
+int spis_timer_stop(spis_ctx* ctx, double* ms_out) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(ms_out, "ms_out is null");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaEventRecord(ctx->ev_t1, ctx->stream));
+  CU(cudaEventSynchronize(ctx->ev_t1));
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1));
+  *ms_out = ms;
+  return SPIS_OK;
+}
+
+// ---- single-kernel entry points ---------------------------------------------------------
+int spis_op_spmv(spis_ctx* ctx, int slot, const double* x, double* y) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(x && y, "null argument");
+  REQUIRE(slot >= 0 && slot < SPIS_MAX_SLOTS && ctx->mats[slot].present, "matrix slot %d not uploaded", slot);
+  CU(cudaSetDevice(ctx->device));
+  // x has ncols entries: owned part then ghost part
+  const Matrix& M = ctx->mats[slot];
+  CU(cudaMemsetAsync(ctx->T, 0, (size_t)ctx->ld * sizeof(double), ctx->stream));
+  const int64_t nown = M.ncols < ctx->n ? M.ncols : ctx->n;
+  CU(cudaMemcpyAsync(ctx->T, x, (size_t)nown * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (M.ncols > ctx->n)
+    CU(cudaMemcpyAsync(ctx->T + ctx->hoff, x + ctx->n, (size_t)(M.ncols - ctx->n) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  TRY(launch_spmv(ctx, slot, 0, ctx->T, nullptr, ctx->W, nullptr));
+  return d2h(ctx, y, ctx->W, (size_t)ctx->n * sizeof(double));
+}
+
+int spis_op_mdot(spis_ctx* ctx, int m, const double* V, const double* w, double* out) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(m >= 0 && m <= ctx->kmax && w && out && (V || m == 0), "bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  if (m)
+    CU(cudaMemcpy2DAsync(ctx->V, (size_t)ctx->ld * sizeof(double), V, (size_t)ctx->n * sizeof(double), (size_t)ctx->n * sizeof(double), (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->W, w, (size_t)ctx->n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  TRY(launch_mdot(ctx, ctx->V, m, nullptr, 1, ctx->W, ctx->d_small));
+  return d2h(ctx, out, ctx->d_small, (size_t)(m + 1) * sizeof(double));
+}
+
+int spis_op_lincomb(spis_ctx* ctx, int m, const double* V, const double* base, const double* coef,
+                    double sign, double* out, double* sumsq_out) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(m >= 0 && m <= ctx->kmax && out && (m == 0 || (V && coef)), "bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  if (m) {
+    CU(cudaMemcpy2DAsync(ctx->V, (size_t)ctx->ld * sizeof(double), V, (size_t)ctx->n * sizeof(double), (size_t)ctx->n * sizeof(double), (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_y, coef, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (base) CU(cudaMemcpyAsync(ctx->W, base, (size_t)ctx->n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  double* scal = ctx->d_small + 2 * ctx->K;
+  TRY(launch_lincomb(ctx, ctx->V, m, ctx->d_y, nullptr, sign, base ? ctx->W : nullptr, ctx->T, sumsq_out ? 1 : 0, scal + 3));
+  TRY(d2h(ctx, out, ctx->T, (size_t)ctx->n * sizeof(double)));
+  if (sumsq_out) TRY(d2h(ctx, sumsq_out, scal + 3, sizeof(double)));
+  return SPIS_OK;
+}
+
+int spis_op_precond(spis_ctx* ctx, const double* q, double* z) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(q && z, "null argument");
+  REQUIRE(ctx->pre_kind == SPIS_PRE_JACOBI || ctx->pre_kind == SPIS_PRE_CSR || ctx->pre_kind == SPIS_PRE_BLOCK, "no device preconditioner selected");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemsetAsync(ctx->T, 0, (size_t)ctx->ld * sizeof(double), ctx->stream));
+  CU(cudaMemsetAsync(ctx->W, 0, (size_t)ctx->ld * sizeof(double), ctx->stream));
+  CU(cudaMemcpyAsync(ctx->T, q, (size_t)ctx->n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  TRY(launch_precond(ctx, ctx->T, ctx->W));
+  return d2h(ctx, z, ctx->W, (size_t)ctx->n * sizeof(double));
+}
+
+int spis_bench_kernel(spis_ctx* ctx, int cls, int m, int reps, double* ms_out, double* bytes_out) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(ms_out && reps >= 1 && m >= 0 && m <= ctx->kmax, "bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  const size_t ld = (size_t)ctx->ld;
+  // resident pseudo-random operands; pads stay zero because only [0,n) of each row is filled
+  for (int i = 0; i <= (m < ctx->kmax ? m : ctx->kmax); ++i)
+    fill_kernel<<<ctx->nsm * 8, 256, 0, ctx->stream>>>(ctx->V + (size_t)i * ld, ctx->n, 0x1234ull + (uint64_t)i);
+  fill_kernel<<<ctx->nsm * 8, 256, 0, ctx->stream>>>(ctx->W, ctx->n, 0x9999ull);
+  fill_kernel<<<ctx->nsm * 8, 256, 0, ctx->stream>>>(ctx->d_y, ctx->K, 0x77ull);
+  CU(cudaGetLastError());
+  double* scal = ctx->d_small + 2 * ctx->K;
+  const double one = 1.0;
+  CU(cudaMemcpyAsync(scal + 4, &one, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  const int saved_profile = ctx->profile;
+  spis_allreduce_fn saved_ar = ctx->allreduce; spis_halo_fn saved_halo = ctx->halo;
+  ctx->profile = 0; ctx->allreduce = nullptr; ctx->halo = nullptr;
+  double bytes0[SPIS_PROF_CLASSES]; for (int i = 0; i < SPIS_PROF_CLASSES; ++i) bytes0[i] = ctx->prof_bytes[i];
+  int rc = SPIS_OK;
+  for (int rep = -2; rep < reps && rc == SPIS_OK; ++rep) {
+    if (rep == 0) { for (int i = 0; i < SPIS_PROF_CLASSES; ++i) bytes0[i] = ctx->prof_bytes[i]; cudaEventRecord(e0, ctx->stream); }
+    switch (cls) {
+      case SPIS_PROF_SPMV: rc = launch_spmv(ctx, SPIS_SLOT_A, 0, ctx->V, nullptr, ctx->T, nullptr); break;
+      case SPIS_PROF_MDOT: rc = launch_mdot(ctx, ctx->V, m, nullptr, 0, ctx->W, ctx->d_small); break;
+      case SPIS_PROF_LINCOMB: rc = launch_lincomb(ctx, ctx->V, m, ctx->d_y, nullptr, -1.0, ctx->W, ctx->T, 1, scal + 3); break;
+      case SPIS_PROF_SCALE: rc = launch_scale(ctx, ctx->V, scal + 4, nullptr, nullptr); break;
+      case SPIS_PROF_PRECOND: rc = launch_precond(ctx, ctx->V, ctx->T); break;
+      default: rc = fail(ctx, SPIS_E_INVALID, "class %d cannot be benchmarked", cls);
+    }
+  }
+  cudaEventRecord(e1, ctx->stream);
+  ctx->profile = saved_profile; ctx->allreduce = saved_ar; ctx->halo = saved_halo;
+  if (rc != SPIS_OK) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
+  CU(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *ms_out = (double)ms / reps;
+  if (bytes_out) *bytes_out = (ctx->prof_bytes[cls] - bytes0[cls]) / reps;
+  return SPIS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,490 @@
+// spis_kernels.cuh -- sm_100a device code for the conservative-FGMRES Krylov loop.
+//
+// Every kernel here is HBM-bandwidth bound fp64 streaming work (no tensor cores: nothing on
+// this path is a dense contraction).  Design rules used throughout:
+//   * persistent grids sized as (#SMs x ctas_per_sm); each CTA grid-strides over tiles;
+//   * all streaming loads are 128-bit (double2), laid out so that one warp instruction covers
+//     512 contiguous bytes, with >= 8 independent loads in flight per thread;
+//   * basis vectors are read with the streaming/evict-first policy (__ldcs) because the
+//     Krylov basis (m x n doubles) never fits in L2, the work vector with __ldg;
+//   * reductions are deterministic: warp shuffle -> per-warp shared accumulators ->
+//     per-CTA partials in global memory -> the last CTA to finish sums the partials in a
+//     fixed order (threadfence + atomic ticket), so a launch needs no second kernel and
+//     results do not depend on CTA scheduling.
+//
+// Layout: every n-vector lives in a buffer of `ld` doubles (ld % 16 == 0); entries [n, hoff)
+// with hoff = roundup(n,16) are zero padding that all kernels preserve, entries
+// [hoff, hoff+n_halo) are ghost values used only as SpMV input.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace spis {
+
+constexpr int kThreads = 256;
+constexpr int kWarps   = kThreads / 32;
+constexpr int kTileE   = 4;                       // doubles per thread per tile (2 x double2)
+constexpr int kTile    = kThreads * kTileE;       // 1024 elements per CTA tile
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ double2 ld_stream(const double* p) {
+  return __ldcs(reinterpret_cast<const double2*>(p));
+}
+__device__ __forceinline__ double2 ld_keep(const double* p) {
+  return __ldg(reinterpret_cast<const double2*>(p));
+}
+
+// Deterministic cross-CTA reduction tail.  Each CTA has already written its `nout` partial
+// sums to partial[blockIdx.x*pstride + i].  The last CTA to take a ticket sums them in a
+// fixed order (8 warps over contiguous CTA ranges, then warp 0..7 in order) into out[i].
+__device__ __forceinline__ void finish_reduction(double* __restrict__ partial, int pstride, int nout,
+                                                 unsigned* counter, double* __restrict__ out,
+                                                 double* sred /* kWarps*32 doubles */) {
+  __shared__ unsigned s_ticket;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(counter, 1u);
+  __syncthreads();
+  if (s_ticket != gridDim.x - 1) return;
+  __threadfence();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nb = gridDim.x;
+  const int per = (nb + kWarps - 1) / kWarps;
+  const int b0 = warp * per;
+  const int b1 = min(nb, b0 + per);
+  for (int i0 = 0; i0 < nout; i0 += 32) {
+    const int i = i0 + lane;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    if (i < nout) {
+      int b = b0;
+      for (; b + 4 <= b1; b += 4) {
+        a0 += __ldcg(partial + (size_t)(b + 0) * pstride + i);
+        a1 += __ldcg(partial + (size_t)(b + 1) * pstride + i);
+        a2 += __ldcg(partial + (size_t)(b + 2) * pstride + i);
+        a3 += __ldcg(partial + (size_t)(b + 3) * pstride + i);
+      }
+      for (; b < b1; ++b) a0 += __ldcg(partial + (size_t)b * pstride + i);
+    }
+    sred[warp * 32 + lane] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (warp == 0 && i < nout) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) s += sred[w * 32 + lane];
+      out[i] = s;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *counter = 0u;   // ready for the next launch on this stream
+}
+
+// ------------------------------------------------------------------------------------------
+// K3a  tall-skinny multi-dot:  out[i] = row_i . w   for i in [0, nrows)
+//   row_i = V + i*ld (i < m), then the optional `extra` vector, then (with_sumsq) w itself.
+// Replaces the m np.dot calls of the Gram-Schmidt loop (solvers.py:193-194), the norm
+// (solvers.py:196) and the Z^T (MZ) / v^T Z products of the constraint stage (:35-36).
+// Algorithmic bytes: (nrows_from_memory + 1) * 8 n.
+// ------------------------------------------------------------------------------------------
+template <int IU, bool FULL>
+__device__ __forceinline__ void mdot_tile(const double* __restrict__ V, int64_t ld, int m,
+                                          const double* __restrict__ extra, const double* __restrict__ w,
+                                          int64_t n, int nrows, int64_t tile, double* sacc_warp, int lane) {
+  const int64_t e0 = tile * kTile + 2 * threadIdx.x;          // first double2 of this thread
+  const int64_t e1 = e0 + 2 * kThreads;                        // second double2
+  const bool p0 = FULL || e0 < n, p1 = FULL || e1 < n;
+  double2 w0 = make_double2(0.0, 0.0), w1 = make_double2(0.0, 0.0);
+  if (p0) w0 = ld_keep(w + e0);
+  if (p1) w1 = ld_keep(w + e1);
+  for (int i0 = 0; i0 < nrows; i0 += IU) {
+    const double* row[IU];
+#pragma unroll
+    for (int u = 0; u < IU; ++u) {
+      const int i = min(i0 + u, nrows - 1);
+      row[u] = (i < m) ? (V + (size_t)i * ld) : ((extra && i == m) ? extra : w);
+    }
+    double2 a[IU], b[IU];
+#pragma unroll
+    for (int u = 0; u < IU; ++u) {
+      if (FULL) {
+        a[u] = ld_stream(row[u] + e0);
+        b[u] = ld_stream(row[u] + e1);
+      } else {
+        a[u] = p0 ? ld_stream(row[u] + e0) : make_double2(0.0, 0.0);
+        b[u] = p1 ? ld_stream(row[u] + e1) : make_double2(0.0, 0.0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < IU; ++u) {
+      double s = a[u].x * w0.x;
+      s = fma(a[u].y, w0.y, s);
+      s = fma(b[u].x, w1.x, s);
+      s = fma(b[u].y, w1.y, s);
+      s = warp_sum(s);
+      if (lane == 0 && i0 + u < nrows) sacc_warp[i0 + u] += s;
+    }
+  }
+}
+
+template <int IU>
+__global__ void __launch_bounds__(kThreads)
+mdot_kernel(const double* __restrict__ V, int64_t ld, int m, const double* __restrict__ extra,
+            int with_sumsq, const double* __restrict__ w, int64_t n,
+            double* __restrict__ partial, int pstride, unsigned* counter, double* __restrict__ out) {
+  extern __shared__ double smem[];
+  const int nrows = m + (extra ? 1 : 0) + (with_sumsq ? 1 : 0);
+  double* sacc = smem;                       // [kWarps][nrows]
+  double* sred = smem + kWarps * nrows;      // [kWarps*32]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* sacc_warp = sacc + warp * nrows;
+  for (int i = lane; i < nrows; i += 32) sacc_warp[i] = 0.0;
+  __syncwarp();
+
+  const int64_t ntiles = (n + kTile - 1) / kTile;
+  const int64_t nfull = n / kTile;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    if (tile < nfull) mdot_tile<IU, true>(V, ld, m, extra, w, n, nrows, tile, sacc_warp, lane);
+    else mdot_tile<IU, false>(V, ld, m, extra, w, n, nrows, tile, sacc_warp, lane);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nrows; i += kThreads) {
+    double s = 0.0;
+#pragma unroll
+    for (int wv = 0; wv < kWarps; ++wv) s += sacc[wv * nrows + i];
+    partial[(size_t)blockIdx.x * pstride + i] = s;
+  }
+  finish_reduction(partial, pstride, nrows, counter, out, sred);
+}
+
+// ------------------------------------------------------------------------------------------
+// K3b / K5  tall-skinny linear combination:
+//     out = base + sign * sum_{i<m} coef[i] * V_i        (+ optional sum of squares of out)
+// Replaces `y = y - h[i,j]*q[i]` (solvers.py:195) for all i at once and `Z @ yk + x0`
+// (solvers.py:287).  coef lives in device memory (written by mdot_kernel or uploaded).
+// Algorithmic bytes: (m + 2) * 8 n   (m + 1 when base is null).
+// ------------------------------------------------------------------------------------------
+template <int IU, bool FULL>
+__device__ __forceinline__ void lincomb_tile(const double* __restrict__ V, int64_t ld, int m,
+                                             const double* sc, const double* base, double* out,
+                                             int64_t n, int64_t tile, int with_sumsq, double& ss) {
+  const int64_t e0 = tile * kTile + 2 * threadIdx.x;
+  const int64_t e1 = e0 + 2 * kThreads;
+  const bool p0 = FULL || e0 < n, p1 = FULL || e1 < n;
+  double2 r0 = make_double2(0.0, 0.0), r1 = make_double2(0.0, 0.0);
+  if (base) {
+    if (p0) r0 = ld_keep(base + e0);
+    if (p1) r1 = ld_keep(base + e1);
+  }
+  const double* row = V;
+  int i0 = 0;
+  for (; i0 + IU <= m; i0 += IU) {
+    double2 a[IU], b[IU];
+#pragma unroll
+    for (int u = 0; u < IU; ++u) {
+      if (FULL) {
+        a[u] = ld_stream(row + (size_t)u * ld + e0);
+        b[u] = ld_stream(row + (size_t)u * ld + e1);
+      } else {
+        a[u] = p0 ? ld_stream(row + (size_t)u * ld + e0) : make_double2(0.0, 0.0);
+        b[u] = p1 ? ld_stream(row + (size_t)u * ld + e1) : make_double2(0.0, 0.0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < IU; ++u) {
+      const double c = sc[i0 + u];
+      r0.x = fma(c, a[u].x, r0.x); r0.y = fma(c, a[u].y, r0.y);
+      r1.x = fma(c, b[u].x, r1.x); r1.y = fma(c, b[u].y, r1.y);
+    }
+    row += (size_t)IU * ld;
+  }
+  for (; i0 < m; ++i0) {
+    const double c = sc[i0];
+    if (p0) { double2 a = ld_stream(row + e0); r0.x = fma(c, a.x, r0.x); r0.y = fma(c, a.y, r0.y); }
+    if (p1) { double2 b = ld_stream(row + e1); r1.x = fma(c, b.x, r1.x); r1.y = fma(c, b.y, r1.y); }
+    row += ld;
+  }
+  if (p0) *reinterpret_cast<double2*>(out + e0) = r0;
+  if (p1) *reinterpret_cast<double2*>(out + e1) = r1;
+  if (with_sumsq) {
+    // entries in [n, roundup(n,2)) are zero padding, so whole double2s can be squared
+    if (p0) { ss = fma(r0.x, r0.x, ss); ss = fma(r0.y, r0.y, ss); }
+    if (p1) { ss = fma(r1.x, r1.x, ss); ss = fma(r1.y, r1.y, ss); }
+  }
+}
+
+template <int IU>
+__global__ void __launch_bounds__(kThreads)
+lincomb_kernel(const double* __restrict__ V, int64_t ld, int m, const double* __restrict__ coef,
+               const double* __restrict__ coef2 /* optional, added to coef */, double sign,
+               const double* base, double* out, int64_t n, int with_sumsq,
+               double* __restrict__ partial, unsigned* counter, double* __restrict__ sumsq_out) {
+  extern __shared__ double smem[];
+  double* sc = smem;                  // [m]
+  double* sred = smem + m + (m & 1);  // [kWarps*32]
+  for (int i = threadIdx.x; i < m; i += kThreads)
+    sc[i] = sign * (coef[i] + (coef2 ? coef2[i] : 0.0));
+  __syncthreads();
+
+  double ss = 0.0;
+  const int64_t ntiles = (n + kTile - 1) / kTile;
+  const int64_t nfull = n / kTile;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    if (tile < nfull) lincomb_tile<IU, true>(V, ld, m, sc, base, out, n, tile, with_sumsq, ss);
+    else lincomb_tile<IU, false>(V, ld, m, sc, base, out, n, tile, with_sumsq, ss);
+  }
+  if (!with_sumsq) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  ss = warp_sum(ss);
+  if (lane == 0) sred[warp] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int wv = 0; wv < kWarps; ++wv) s += sred[wv];
+    partial[blockIdx.x] = s;
+  }
+  __syncthreads();
+  finish_reduction(partial, 1, 1, counter, sumsq_out, sred);
+}
+
+// ------------------------------------------------------------------------------------------
+// K4  q[j+1] = w / h[j+1,j]  (solvers.py:198), in place, h^2 read from device memory.
+// If the squared norm is exactly zero (breakdown, solvers.py:199-202) the vector is left as
+// is; the host sees h[j+1,j] == 0 and stops before using it.  Optionally also writes the
+// Jacobi-preconditioned vector z = d (.) q of the NEXT step (saves one read of q).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+scale_kernel(double* __restrict__ v, const double* __restrict__ sumsq, int64_t n,
+             const double* __restrict__ jac_diag, double* __restrict__ z_next) {
+  const double s2 = *sumsq;
+  if (!(s2 != 0.0)) return;
+  const double inv = 1.0 / sqrt(s2);
+  const int64_t stride = (int64_t)gridDim.x * kThreads * 2;
+  for (int64_t e = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 2; e < n; e += stride) {
+    double2 a = *reinterpret_cast<const double2*>(v + e);
+    a.x *= inv; a.y *= inv;
+    *reinterpret_cast<double2*>(v + e) = a;
+    if (jac_diag) {
+      double2 d = ld_keep(jac_diag + e);
+      *reinterpret_cast<double2*>(z_next + e) = make_double2(a.x * d.x, a.y * d.y);
+    }
+  }
+}
+
+// K2  Jacobi: z = d (.) q     (the `pre @ vec` branch of solvers.py:156-161 for a diagonal pre)
+__global__ void __launch_bounds__(kThreads)
+jacobi_kernel(const double* __restrict__ d, const double* __restrict__ q, double* __restrict__ z, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * kThreads * 2;
+  for (int64_t e = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 2; e < n; e += stride) {
+    double2 a = ld_keep(q + e), b = ld_keep(d + e);
+    *reinterpret_cast<double2*>(z + e) = make_double2(a.x * b.x, a.y * b.y);
+  }
+}
+
+// K2  block-diagonal preconditioner, dense BS x BS blocks stored structure-of-arrays:
+//   blk[(r*BS + c)*nblk + i] = B_i[r][c];  element f of block i is vector index i*sb + f*sf.
+template <int BS>
+__global__ void __launch_bounds__(kThreads)
+blockdiag_kernel(const double* __restrict__ blk, int64_t nblk, int64_t sb, int64_t sf,
+                 const double* __restrict__ q, double* __restrict__ z) {
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < nblk; i += stride) {
+    double x[BS];
+#pragma unroll
+    for (int f = 0; f < BS; ++f) x[f] = __ldg(q + i * sb + f * sf);
+#pragma unroll
+    for (int r = 0; r < BS; ++r) {
+      double s = 0.0;
+#pragma unroll
+      for (int c = 0; c < BS; ++c) s = fma(__ldcs(blk + (size_t)(r * BS + c) * nblk + i), x[c], s);
+      z[i * sb + r * sf] = s;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1  SpMV, SELL-32-1 storage (sliced ELLPACK, slice height 32 = one warp, column-major
+// inside a slice): thread r of a warp owns row 32*slice + r and walks the slice width; every
+// warp load of values (256 B) and column indices (128 B) is one fully coalesced request.
+// x is gathered through the read-only path; for FEM band structure the gathers of
+// neighbouring rows hit the same L1 lines.
+//   MODE 0: y = A x                        (solvers.py:191, A @ z[j];  :33 M @ Z column)
+//   MODE 1: y = b - A x, sumsq = ||y||^2   (solvers.py:167,170)
+//   MODE 2: sumsq = ||A x - b||^2, no store (solvers.py:290)
+// Algorithmic bytes: 12 nnz_padded + 8 (n/32) + 8 n (x) + 8 n (y or b) [+ 8 n b in mode 1].
+// ------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+spmv_sell_kernel(const int64_t* __restrict__ slice_off, const int32_t* __restrict__ cols,
+                 const double* __restrict__ vals, int64_t nrows, const double* __restrict__ x,
+                 const double* __restrict__ b, double* __restrict__ y,
+                 double* __restrict__ partial, unsigned* counter, double* __restrict__ sumsq_out) {
+  __shared__ double sred[kWarps * 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t nslices = (nrows + 31) >> 5;
+  const int64_t nblocks = (nslices + kWarps - 1) / kWarps;
+  double ss = 0.0;
+  for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    const int64_t slice = blk * kWarps + warp;
+    if (slice < nslices) {
+      const int64_t off = __ldg(slice_off + slice);
+      const int width = (int)((__ldg(slice_off + slice + 1) - off) >> 5);
+      const int32_t* c = cols + off + lane;
+      const double* v = vals + off + lane;
+      double acc0 = 0.0, acc1 = 0.0;
+      int k = 0;
+      for (; k + 4 <= width; k += 4) {
+        const int32_t c0 = __ldcs(c + (k + 0) * 32), c1 = __ldcs(c + (k + 1) * 32);
+        const int32_t c2 = __ldcs(c + (k + 2) * 32), c3 = __ldcs(c + (k + 3) * 32);
+        const double v0 = __ldcs(v + (k + 0) * 32), v1 = __ldcs(v + (k + 1) * 32);
+        const double v2 = __ldcs(v + (k + 2) * 32), v3 = __ldcs(v + (k + 3) * 32);
+        const double x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
+        acc0 = fma(v0, x0, acc0); acc1 = fma(v1, x1, acc1);
+        acc0 = fma(v2, x2, acc0); acc1 = fma(v3, x3, acc1);
+      }
+      for (; k < width; ++k) acc0 = fma(__ldcs(v + k * 32), __ldg(x + __ldcs(c + k * 32)), acc0);
+      const double ax = acc0 + acc1;
+      const int64_t row = (slice << 5) + lane;
+      if (row < nrows) {
+        if (MODE == 0) {
+          y[row] = ax;
+        } else if (MODE == 1) {
+          const double r = __ldg(b + row) - ax;
+          y[row] = r;
+          ss = fma(r, r, ss);
+        } else {
+          const double r = ax - __ldg(b + row);
+          ss = fma(r, r, ss);
+        }
+      }
+    }
+  }
+  if (MODE == 0) return;
+  ss = warp_sum(ss);
+  if (lane == 0) sred[warp] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int wv = 0; wv < kWarps; ++wv) s += sred[wv];
+    partial[blockIdx.x] = s;
+  }
+  __syncthreads();
+  finish_reduction(partial, 1, 1, counter, sumsq_out, sred);
+}
+
+// K1 fallback: CSR "vector" kernel, T lanes per row (T = 2..32), for matrices whose row
+// lengths vary so much inside a 32-row slice that SELL padding would waste bandwidth.
+template <int T, int MODE>
+__global__ void __launch_bounds__(kThreads)
+spmv_csr_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ cols,
+                const double* __restrict__ vals, int64_t nrows, const double* __restrict__ x,
+                const double* __restrict__ b, double* __restrict__ y,
+                double* __restrict__ partial, unsigned* counter, double* __restrict__ sumsq_out) {
+  __shared__ double sred[kWarps * 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = threadIdx.x & (T - 1);
+  constexpr int kRowsPerCta = kThreads / T;
+  const int64_t nblocks = (nrows + kRowsPerCta - 1) / kRowsPerCta;
+  double ss = 0.0;
+  for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    const int64_t row = blk * kRowsPerCta + threadIdx.x / T;
+    double acc = 0.0;
+    if (row < nrows) {
+      const int32_t p0 = __ldg(indptr + row), p1 = __ldg(indptr + row + 1);
+      for (int32_t p = p0 + sub; p < p1; p += T) acc = fma(__ldcs(vals + p), __ldg(x + __ldcs(cols + p)), acc);
+    }
+#pragma unroll
+    for (int o = T / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, T);
+    if (sub == 0 && row < nrows) {
+      if (MODE == 0) {
+        y[row] = acc;
+      } else if (MODE == 1) {
+        const double r = __ldg(b + row) - acc;
+        y[row] = r;
+        ss = fma(r, r, ss);
+      } else {
+        const double r = acc - __ldg(b + row);
+        ss = fma(r, r, ss);
+      }
+    }
+  }
+  if (MODE == 0) return;
+  ss = warp_sum(ss);
+  if (lane == 0) sred[warp] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int wv = 0; wv < kWarps; ++wv) s += sred[wv];
+    partial[blockIdx.x] = s;
+  }
+  __syncthreads();
+  finish_reduction(partial, 1, 1, counter, sumsq_out, sred);
+}
+
+// ------------------------------------------------------------------------------------------
+// CSR -> SELL-32 conversion (once per uploaded matrix, on device)
+// ------------------------------------------------------------------------------------------
+// remap ghost columns: col >= n_owned -> col + (hoff - n_owned)
+__global__ void remap_cols_kernel(int32_t* __restrict__ cols, int64_t nnz, int32_t n_owned, int32_t shift) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nnz; p += stride) {
+    const int32_t c = cols[p];
+    if (c >= n_owned) cols[p] = c + shift;
+  }
+}
+
+__global__ void sell_width_kernel(const int32_t* __restrict__ indptr, int64_t nrows, int32_t* __restrict__ width) {
+  const int64_t slice = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t nslices = (nrows + 31) >> 5;
+  if (slice >= nslices) return;
+  const int64_t row = (slice << 5) + lane;
+  int len = 0;
+  if (row < nrows) len = indptr[row + 1] - indptr[row];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+  if (lane == 0) width[slice] = len;
+}
+
+__global__ void sell_fill_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ cols_in,
+                                 const double* __restrict__ vals_in, int64_t nrows,
+                                 const int64_t* __restrict__ slice_off, int32_t* __restrict__ cols,
+                                 double* __restrict__ vals) {
+  const int64_t slice = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t nslices = (nrows + 31) >> 5;
+  if (slice >= nslices) return;
+  const int64_t row = (slice << 5) + lane;
+  const int64_t off = slice_off[slice];
+  const int width = (int)((slice_off[slice + 1] - off) >> 5);
+  int32_t p0 = 0, len = 0;
+  if (row < nrows) { p0 = indptr[row]; len = indptr[row + 1] - p0; }
+  int32_t padcol = 0;                         // padded entries: value 0, a column that is valid and local
+  if (len > 0) padcol = cols_in[p0 + len - 1];
+  for (int k = 0; k < width; ++k) {
+    int32_t c = padcol; double v = 0.0;
+    if (k < len) { c = cols_in[p0 + k]; v = vals_in[p0 + k]; }
+    cols[off + (int64_t)k * 32 + lane] = c;
+    vals[off + (int64_t)k * 32 + lane] = v;
+  }
+}
+
+// deterministic pseudo-random fill in (-1, 1) for spis_bench_kernel
+__global__ void fill_kernel(double* __restrict__ p, int64_t n, uint64_t seed) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    uint64_t z = (uint64_t)i * 0x9E3779B97F4A7C15ull + seed;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    p[i] = (double)(int64_t)(z >> 11) * (1.0 / 4503599627370496.0) - 1.0;
+  }
+}
+
+}  // namespace spis

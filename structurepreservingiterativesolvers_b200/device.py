@@ -1,0 +1,276 @@
+"""KrylovContext: Python owner of one `spis_ctx` (one linear system resident on one B200).
+
+Every method is a direct call into libspis_b200.so; arrays crossing this boundary are host
+numpy arrays.  See include/spis_b200.h for the contract of each entry point and the
+reference lines (solvers.py:<line>) it replaces.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import numpy as np
+import scipy.sparse as sps
+
+from . import _native as nat
+
+
+def _csr_arrays(A):
+    """Return (csr, indptr int32, indices int32, data f64) views suitable for the C ABI."""
+    if not sps.issparse(A):
+        A = sps.csr_matrix(np.asarray(A, dtype=np.float64))
+    A = A.tocsr()
+    if A.nnz >= 2**31 - 1:
+        raise ValueError("matrices with nnz >= 2^31 must be row-sharded over several GPUs")
+    indptr = np.ascontiguousarray(A.indptr, dtype=np.int32)
+    indices = np.ascontiguousarray(A.indices, dtype=np.int32)
+    data = np.ascontiguousarray(A.data, dtype=np.float64)
+    return A, indptr, indices, data
+
+
+class KrylovContext:
+    """One GPU-resident Krylov workspace: A, b, x0, basis q/z, constraint matrices."""
+
+    def __init__(self, n: int, k_max: int, device: int = 0, n_halo: int = 0, stream=None):
+        self._lib = nat.load_library()
+        self._h = C.c_void_p()
+        self.n, self.k_max, self.device, self.n_halo = int(n), int(k_max), int(device), int(n_halo)
+        rc = self._lib.spis_ctx_create(self.device, self.n, self.n_halo, self.k_max,
+                                       C.c_void_p(stream) if stream else None, C.byref(self._h))
+        if rc != nat.OK:
+            self._h = C.c_void_p()
+            raise nat.SpisError(rc, self._lib.spis_last_global_error().decode())
+        self._callbacks = None   # keep CFUNCTYPE objects alive
+        self.generation = 0
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.spis_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):  # pragma: no cover - interpreter shutdown ordering
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def closed(self) -> bool:
+        return not self._h
+
+    def _check(self, rc: int):
+        if rc != nat.OK:
+            raise nat.SpisError(rc, self._lib.spis_last_error(self._h).decode())
+
+    def _live(self):
+        if not self._h:
+            raise RuntimeError("KrylovContext is closed")
+
+    # -- options / info -----------------------------------------------------------------------
+    def set_option(self, key: str, value: int):
+        self._live()
+        self._check(self._lib.spis_set_option(self._h, key.encode(), int(value)))
+
+    def info(self, key: str) -> int:
+        self._live()
+        out = C.c_int64(0)
+        self._check(self._lib.spis_get_info(self._h, key.encode(), C.byref(out)))
+        return out.value
+
+    # -- uploads --------------------------------------------------------------------------------
+    def upload_matrix(self, slot: int, A):
+        self._live()
+        A, indptr, indices, data = _csr_arrays(A)
+        if A.shape[0] != self.n:
+            raise ValueError(f"matrix has {A.shape[0]} rows, context owns {self.n}")
+        self._check(self._lib.spis_upload_csr(self._h, slot, A.shape[0], A.shape[1], A.nnz,
+                                              nat.iptr(indptr), nat.iptr(indices), nat.dptr(data)))
+
+    def upload_vec(self, which: int, v):
+        self._live()
+        v = nat.as_f64(v, self.n)
+        self._check(self._lib.spis_upload_vec(self._h, which, nat.dptr(v), self.n))
+
+    def upload_blocks(self, blocks: np.ndarray, stride_block: int, stride_field: int):
+        self._live()
+        blocks = np.ascontiguousarray(blocks, dtype=np.float64)
+        nblk, bs, bs2 = blocks.shape
+        if bs != bs2:
+            raise ValueError("blocks must be (nblk, bs, bs)")
+        self._check(self._lib.spis_upload_blocks(self._h, bs, nblk, stride_block, stride_field, nat.dptr(blocks)))
+
+    def set_precond(self, kind: int):
+        self._live()
+        self._check(self._lib.spis_set_precond(self._h, kind))
+
+    # -- Krylov loop ------------------------------------------------------------------------------
+    def solve_begin(self) -> float:
+        self._live()
+        beta = C.c_double(0.0)
+        self._check(self._lib.spis_solve_begin(self._h, C.byref(beta)))
+        self.generation += 1
+        return beta.value
+
+    def arnoldi_launch(self, j: int):
+        self._check(self._lib.spis_arnoldi_launch(self._h, j))
+
+    def arnoldi_wait(self, j: int) -> np.ndarray:
+        out = np.empty(j + 2, dtype=np.float64)
+        self._check(self._lib.spis_arnoldi_wait(self._h, j, nat.dptr(out)))
+        return out
+
+    def arnoldi_step(self, j: int) -> np.ndarray:
+        out = np.empty(j + 2, dtype=np.float64)
+        self._check(self._lib.spis_arnoldi_step(self._h, j, nat.dptr(out)))
+        return out
+
+    def iterate_residual(self, y) -> float:
+        y = nat.as_f64(y)
+        res = C.c_double(0.0)
+        self._check(self._lib.spis_iterate_residual(self._h, y.size, nat.dptr(y), C.byref(res)))
+        return res.value
+
+    def form_iterate(self, y):
+        y = nat.as_f64(y)
+        self._check(self._lib.spis_form_iterate(self._h, y.size, nat.dptr(y)))
+
+    # -- constraints ------------------------------------------------------------------------------
+    def constraint_define(self, c: int, mat_slot: int, v, cc: float):
+        self._live()
+        vp = None
+        if v is not None:
+            v = nat.as_f64(v, self.n)
+            vp = nat.dptr(v)
+        self._check(self._lib.spis_constraint_define(self._h, c, mat_slot, vp, float(cc)))
+
+    def constraint_terms(self, c: int, m: int):
+        t0 = C.c_double(0.0)
+        t1 = np.empty(m, dtype=np.float64)
+        t2 = np.empty((m, m), dtype=np.float64)
+        self._check(self._lib.spis_constraint_terms(self._h, c, m, C.byref(t0), nat.dptr(t1), nat.dptr(t2)))
+        return t0.value, t1, t2
+
+    # -- downloads / bridges ------------------------------------------------------------------------
+    def download(self, which: int, j: int = 0) -> np.ndarray:
+        self._live()
+        out = np.empty(self.n, dtype=np.float64)
+        self._check(self._lib.spis_download_vec(self._h, which, j, nat.dptr(out), self.n))
+        return out
+
+    def download_Z(self, j0: int, j1: int) -> np.ndarray:
+        self._live()
+        out = np.empty((j1 - j0, self.n), dtype=np.float64)
+        self._check(self._lib.spis_download_Z(self._h, j0, j1, nat.dptr(out)))
+        return out
+
+    def host_pre_get(self, j: int) -> np.ndarray:
+        out = np.empty(self.n, dtype=np.float64)
+        self._check(self._lib.spis_host_pre_get(self._h, j, nat.dptr(out)))
+        return out
+
+    def host_pre_put(self, j: int, z):
+        z = nat.as_f64(z, self.n)
+        self._check(self._lib.spis_host_pre_put(self._h, j, nat.dptr(z)))
+
+    def set_collectives(self, allreduce, halo):
+        """allreduce(device_ptr:int, count:int) and halo(device_vec_ptr:int) are Python callables."""
+        self._live()
+
+        def _ar(_user, ptr, count):
+            try:
+                allreduce(ptr, count)
+                return 0
+            except Exception:  # pragma: no cover - surfaced as SpisError by the caller
+                import traceback
+                traceback.print_exc()
+                return 1
+
+        def _halo(_user, ptr):
+            try:
+                halo(ptr)
+                return 0
+            except Exception:  # pragma: no cover
+                import traceback
+                traceback.print_exc()
+                return 1
+
+        cb = (nat.ALLREDUCE_FN(_ar) if allreduce else nat.ALLREDUCE_FN(),
+              nat.HALO_FN(_halo) if halo else nat.HALO_FN())
+        self._callbacks = cb
+        self._check(self._lib.spis_set_collectives(self._h, cb[0], cb[1], None))
+
+    def sync(self):
+        self._live()
+        self._check(self._lib.spis_sync(self._h))
+
+    # -- measurement --------------------------------------------------------------------------------
+    def profile(self) -> dict:
+        """{class: {'ms', 'bytes', 'launches', 'gbs'}} accumulated since reset_profile()."""
+        self._live()
+        ms = np.zeros(nat.PROF_CLASSES)
+        by = np.zeros(nat.PROF_CLASSES)
+        ln = np.zeros(nat.PROF_CLASSES, dtype=np.int64)
+        self._check(self._lib.spis_get_profile(self._h, nat.dptr(ms), nat.dptr(by), ln.ctypes.data_as(C.POINTER(C.c_int64))))
+        out = {}
+        for i, name in enumerate(nat.PROF_NAMES):
+            out[name] = {"ms": float(ms[i]), "bytes": float(by[i]), "launches": int(ln[i]),
+                         "gbs": float(by[i] / ms[i] * 1e-6) if ms[i] > 0 else None}
+        return out
+
+    def timer_start(self):
+        self._check(self._lib.spis_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_double(0.0)
+        self._check(self._lib.spis_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def reset_profile(self):
+        self._live()
+        self._check(self._lib.spis_reset_profile(self._h))
+
+    # -- single-kernel entry points (tests / tuning) ----------------------------------------------
+    def op_spmv(self, slot: int, x) -> np.ndarray:
+        x = nat.as_f64(x)
+        y = np.empty(self.n, dtype=np.float64)
+        self._check(self._lib.spis_op_spmv(self._h, slot, nat.dptr(x), nat.dptr(y)))
+        return y
+
+    def op_mdot(self, V, w) -> np.ndarray:
+        V = np.ascontiguousarray(V, dtype=np.float64).reshape(-1, self.n) if np.size(V) else np.zeros((0, self.n))
+        w = nat.as_f64(w, self.n)
+        out = np.empty(V.shape[0] + 1, dtype=np.float64)
+        self._check(self._lib.spis_op_mdot(self._h, V.shape[0], nat.dptr(V) if V.shape[0] else None, nat.dptr(w), nat.dptr(out)))
+        return out
+
+    def op_lincomb(self, V, base, coef, sign: float = 1.0, want_sumsq: bool = True):
+        V = np.ascontiguousarray(V, dtype=np.float64).reshape(-1, self.n) if np.size(V) else np.zeros((0, self.n))
+        m = V.shape[0]
+        coef = nat.as_f64(coef, m)
+        out = np.empty(self.n, dtype=np.float64)
+        ss = C.c_double(0.0)
+        bp = None
+        if base is not None:
+            base = nat.as_f64(base, self.n)
+            bp = nat.dptr(base)
+        self._check(self._lib.spis_op_lincomb(self._h, m, nat.dptr(V) if m else None, bp, nat.dptr(coef) if m else None,
+                                              float(sign), nat.dptr(out), C.byref(ss) if want_sumsq else None))
+        return (out, ss.value) if want_sumsq else out
+
+    def op_precond(self, q) -> np.ndarray:
+        q = nat.as_f64(q, self.n)
+        z = np.empty(self.n, dtype=np.float64)
+        self._check(self._lib.spis_op_precond(self._h, nat.dptr(q), nat.dptr(z)))
+        return z
+
+    def bench_kernel(self, prof_class: int, m: int, reps: int = 20):
+        """(ms per launch, algorithmic bytes per launch) for one kernel class on resident data."""
+        ms = C.c_double(0.0)
+        by = C.c_double(0.0)
+        self._check(self._lib.spis_bench_kernel(self._h, prof_class, m, reps, C.byref(ms), C.byref(by)))
+        return ms.value, by.value

@@ -1,0 +1,574 @@
+"""B200-native drop-in for the reference's ``solvers.py`` (FGMRES / CGMRES / prototypical CGMRES).
+
+Same public names, keyword names, constraint-list conventions and ``(x, dict)`` return
+contract as /root/reference/solvers.py:
+
+    gmres(A, b, x0, k, tol=1e-50, pre=None)                                   solvers.py:58
+    cgmres(A, b, x0, k, tol=1e-8, contol=10, conlist=[], pre=None, timing=None)  solvers.py:131
+    cgmres_p(A, b, x0, k, conlist=[], pre=None)                               solvers.py:328
+    constraint_container(const, x0, Z), constraint_checker(x, const_list)     solvers.py:21,14
+
+so each experiment's ``LinearSolver.py`` (lkdv, lkdvRK, swe, heat) can ``import`` this module
+as ``solvers`` unchanged.  Every O(n) operation -- SpMV, preconditioner, Gram-Schmidt, the
+iterate x0 + Z y, the true residual and the constraint Gram/projection terms -- runs as a
+hand-written sm_100a kernel behind the C ABI of include/spis_b200.h; the host keeps the control
+flow of the reference loop and the k-dimensional (constrained) least-squares solve.
+
+Extra keyword-only arguments (all optional, defaults keep reference semantics):
+    session       a DeviceSession with the system already resident on the GPU
+    small_solver  'slsqp' (reference's scipy SLSQP calls, default) or 'kkt' (QR + Newton-KKT)
+    lookahead     overlap Arnoldi step j+1 with the host solve of step j (default True)
+    history       'lazy' (default: dict['x'] materialises iterates on demand) or 'eager'
+    device        CUDA device ordinal
+
+There is no CPU fallback: without libspis_b200.so or without an sm_100 GPU every solver raises.
+"""
+from __future__ import annotations
+
+import collections.abc
+import warnings
+from time import time
+
+import numpy as np
+import scipy.sparse as sps
+
+from . import _native as nat
+from . import smallsolve
+from .device import KrylovContext
+from .preconditioners import BlockJacobiPreconditioner, JacobiPreconditioner
+
+__all__ = ["gmres", "cgmres", "cgmres_p", "constraint_container", "constraint_checker",
+           "DeviceSession", "configure"]
+
+_CONFIG = {
+    "small_solver": "slsqp",
+    "lookahead": True,
+    "history": "lazy",
+    "device": 0,
+    "orth": "cgs2",
+    "spmv_format": "auto",
+    "profile": False,
+}
+_ORTH = {"cgs2": nat.ORTH_CGS2, "cgs1": nat.ORTH_CGS1, "mgs": nat.ORTH_MGS}
+_FMT = {"auto": nat.FMT_AUTO, "sell": nat.FMT_SELL, "csr": nat.FMT_CSR}
+_BREAKDOWN = ("GMRES broke down, either initial guess is exact or , more likely, "
+              "something has gone wrong.")
+
+
+def configure(**kwargs):
+    """Set module-wide defaults for the extension keywords (e.g. small_solver='kkt')."""
+    for key, val in kwargs.items():
+        if key not in _CONFIG:
+            raise KeyError(f"unknown option {key!r}; known: {sorted(_CONFIG)}")
+        _CONFIG[key] = val
+    return dict(_CONFIG)
+
+
+def _opt(name, value):
+    return _CONFIG[name] if value is None else value
+
+
+# ==============================================================================================
+# constraint helpers (solvers.py:14-53)
+# ==============================================================================================
+def constraint_checker(x, const_list):
+    """Largest signed constraint value over a list of {'fun': ...} dicts (solvers.py:14-18)."""
+    dev = 0
+    for const in const_list:
+        dev = max(dev, const["fun"](x))
+    return dev
+
+
+def _classify_constraint(const):
+    """'class' (object with M, v, c), 'dict' ({'func','jac'} callbacks) or 'invalid' (solvers.py:24-30)."""
+    if hasattr(const, "__dict__"):
+        return "class"
+    if type(const) is dict:
+        return "dict"
+    return "invalid"
+
+
+class constraint_container:
+    """API-compatible stand-alone container (solvers.py:21-53) for a HOST matrix Z (n x m).
+
+    Class-form constraints get term0/term1/term2 from the same device kernels the solvers use
+    (SpMV for M@Z, tall-skinny dots for Z^T MZ); dict-form constraints just store their callbacks.
+    Inside gmres/cgmres/cgmres_p the equivalent object is built incrementally by DeviceSession.
+    """
+
+    def __init__(self, const, x0, Z, device=None):
+        kind = _classify_constraint(const)
+        if kind == "invalid":
+            raise NotImplementedError("Constraints must be either dictionaries or classes")
+        self.optimise = True if kind == "class" else None
+        if not self.optimise:
+            self.const, self.x0, self.Z = const, x0, Z
+            return
+        Zc = np.ascontiguousarray(np.asarray(Z, dtype=np.float64).T)        # rows = columns of Z
+        m, n = Zc.shape
+        x0 = nat.as_f64(x0, n)
+        v = nat.as_f64(const.v, n)
+        with KrylovContext(n, max(m, 1), device=_opt("device", device)) as ctx:
+            ctx.upload_matrix(nat.SLOT_CON0, const.M)
+            MZ = np.empty((m, n))
+            for i in range(m):
+                MZ[i] = ctx.op_spmv(nat.SLOT_CON0, Zc[i])
+            Mx0 = ctx.op_spmv(nat.SLOT_CON0, x0)
+            gram = np.empty((m, m))
+            for i in range(m):
+                gram[:, i] = ctx.op_mdot(Zc, MZ[i])[:m]                    # Z^T (M z_i)
+            self.term0 = 0.5 * ctx.op_mdot(Mx0[None, :], x0)[0] + const.c + ctx.op_mdot(v[None, :], x0)[0]
+            self.term1 = ctx.op_mdot(Zc, v)[:m] + ctx.op_mdot(MZ, x0)[:m]
+            self.term2 = 0.5 * gram
+            self.MZ = MZ.T
+
+    def constraint_func(self, z):
+        if self.optimise:
+            return self.term0 + self.term1 @ z + z @ self.term2 @ z
+        return self.const["func"](z, self.x0, self.Z)
+
+    def constraint_jac(self, z):
+        if self.optimise:
+            return self.term1 + 2 * z @ self.term2
+        return self.const["jac"](z, self.x0, self.Z)
+
+
+# ==============================================================================================
+# device session: one linear system + constraints resident on one GPU
+# ==============================================================================================
+class DeviceSession:
+    """Uploads A, b, x0, the preconditioner and the class-form constraint data once.
+
+    Replaces the host-resident scipy/numpy objects the reference keeps between iterations
+    (solvers.py:149-181).  Re-usable across several solves of the same system (bench.py's
+    device-resident timing; time stepping with a fixed operator).
+    """
+
+    def __init__(self, A, b, x0, k, conlist=(), pre=None, *, device=None, orth=None,
+                 spmv_format=None, profile=None, ctx_factory=KrylovContext):
+        b = nat.as_f64(b)
+        n = b.size
+        self.n, self.k = n, int(k)
+        self.x0_host = nat.as_f64(x0, n)
+        self.ctx = ctx_factory(n, self.k, device=_opt("device", device))
+        ctx = self.ctx
+        ctx.set_option("orth", _ORTH[_opt("orth", orth)])
+        ctx.set_option("spmv_format", _FMT[_opt("spmv_format", spmv_format)])
+        ctx.set_option("profile", 1 if _opt("profile", profile) else 0)
+        if not (sps.issparse(A) or isinstance(A, np.ndarray)):
+            raise TypeError("A must be a scipy.sparse matrix (or a dense array); got %r" % type(A))
+        if A.shape != (n, n):
+            raise ValueError(f"A has shape {A.shape}, expected {(n, n)}")
+        ctx.upload_matrix(nat.SLOT_A, A)
+        ctx.upload_vec(nat.VEC_B, b)
+        ctx.upload_vec(nat.VEC_X0, self.x0_host)
+        ctx.set_option("x0_is_zero", 0 if self.x0_host.any() else 1)
+        self._host_pre = None
+        self._setup_precond(pre)
+        self._cons = []
+        self._setup_constraints(list(conlist))
+        self._Zhost = None
+        self._Zrows = 0
+
+    # -- preconditioner: solvers.py:149-161 ------------------------------------------------------
+    def _setup_precond(self, pre):
+        ctx = self.ctx
+        if pre is None:
+            ctx.set_precond(nat.PRE_NONE)
+        elif isinstance(pre, JacobiPreconditioner):
+            ctx.upload_vec(nat.VEC_PRE_DIAG, pre.dinv)
+            ctx.set_precond(nat.PRE_JACOBI)
+        elif isinstance(pre, BlockJacobiPreconditioner):
+            ctx.upload_blocks(pre.inv_blocks, pre.stride_block, pre.stride_field)
+            ctx.set_precond(nat.PRE_BLOCK)
+        elif hasattr(pre, "solve"):
+            self._host_pre = pre.solve                      # e.g. SuperLU from spilu (swe/TimedSolve.py:23)
+            ctx.set_precond(nat.PRE_HOST)
+        elif sps.issparse(pre) or (isinstance(pre, np.ndarray) and pre.ndim == 2):
+            P = sps.csr_matrix(pre)
+            if P.shape != (self.n, self.n):
+                raise ValueError("Preconditioner not supported")
+            coo = P.tocoo()
+            if np.array_equal(coo.row, coo.col):
+                ctx.upload_vec(nat.VEC_PRE_DIAG, P.diagonal())
+                ctx.set_precond(nat.PRE_JACOBI)
+            else:
+                ctx.upload_matrix(nat.SLOT_PRE, P)
+                ctx.set_precond(nat.PRE_CSR)
+        else:
+            def apply(vec, _pre=pre):                       # LinearOperator, pyamg, ... (heat/TimedSolve.py:30-31)
+                try:
+                    return _pre @ vec
+                except Exception:
+                    raise ValueError("Preconditioner not supported")
+            self._host_pre = apply
+            ctx.set_precond(nat.PRE_HOST)
+
+    # -- constraints: solvers.py:22-40 -----------------------------------------------------------
+    def _setup_constraints(self, conlist):
+        if len(conlist) > nat.MAX_SLOTS - nat.SLOT_CON0:
+            raise ValueError("too many constraints")
+        for idx, const in enumerate(conlist):
+            kind = _classify_constraint(const)
+            entry = {"kind": kind, "const": const, "error": None}
+            if kind == "class":
+                try:
+                    M, v, c = const.M, const.v, const.c
+                    if sps.issparse(M):
+                        M_zero = M.nnz == 0 or not M.data.any()
+                    else:
+                        M = np.asarray(M, dtype=np.float64)
+                        M_zero = not M.any()
+                    slot = -1
+                    if not M_zero:
+                        slot = nat.SLOT_CON0 + idx
+                        self.ctx.upload_matrix(slot, M)
+                    v = nat.as_f64(v, self.n)
+                    self.ctx.constraint_define(idx, slot, v if v.any() else None, float(c))
+                except nat.NativeLibraryError:
+                    raise
+                except Exception as exc:                    # surfaces where the reference builds containers
+                    entry["error"] = exc
+            self._cons.append(entry)
+
+    def containers(self, m):
+        """Reduced constraints for Z = z[:m].T (the reference rebuilds these per step, solvers.py:242-247)."""
+        out = []
+        for idx, entry in enumerate(self._cons):
+            if entry["kind"] == "invalid":
+                raise NotImplementedError("Constraints must be either dictionaries or classes")
+            if entry["error"] is not None:
+                raise entry["error"]
+            if entry["kind"] == "class":
+                t0, t1, t2 = self.ctx.constraint_terms(idx, m)
+                out.append(smallsolve.ReducedConstraint(t0, t1, t2))
+            else:
+                out.append(smallsolve.ReducedConstraint(callbacks=entry["const"], x0=self.x0_host,
+                                                        Z=self._host_Z(m)))
+        return out
+
+    def _host_Z(self, m):
+        """Host copy of Z (n x m, Fortran-ordered view like np.transpose(z[:m]), solvers.py:207)."""
+        if self._Zhost is None:
+            self._Zhost = np.empty((self.k, self.n))
+        if m > self._Zrows:
+            self._Zhost[self._Zrows:m] = self.ctx.download_Z(self._Zrows, m)
+            self._Zrows = m
+        return self._Zhost[:m].T
+
+    @property
+    def n_constraints(self):
+        return len(self._cons)
+
+    # -- Krylov primitives ------------------------------------------------------------------------
+    def begin(self):
+        self._Zrows = 0
+        return self.ctx.solve_begin()
+
+    def arnoldi_launch(self, j):
+        if self._host_pre is not None:
+            q = self.ctx.host_pre_get(j)
+            self.ctx.host_pre_put(j, np.asarray(self._host_pre(q)))
+        self.ctx.arnoldi_launch(j)
+
+    def arnoldi_wait(self, j):
+        return self.ctx.arnoldi_wait(j)
+
+    def close(self):
+        self.ctx.close()
+
+
+class IterateHistory(collections.abc.Sequence):
+    """dict['x'] of the reference (solvers.py:165-169,287,318): [r0, x_1, ..., x_steps].
+
+    The iterates stay on the device as their Krylov coefficients; item access re-forms
+    x_j = x0 + Z[:, :m_j] y_j with the same kernel that produced it and downloads it.
+    """
+
+    def __init__(self, session):
+        self._session = session
+        self._gen = session.ctx.generation
+        self._ys = [None]                 # entry 0 is r0 (quirk: x[0] is the initial residual)
+        self._cache = {}
+
+    def _append(self, y):
+        self._ys.append(np.array(y, dtype=np.float64, copy=True))
+
+    def _set_cached(self, idx, arr):
+        self._cache[idx % len(self._ys)] = arr
+
+    def __len__(self):
+        return len(self._ys)
+
+    def __getitem__(self, idx):
+        if isinstance(idx, slice):
+            return [self[i] for i in range(*idx.indices(len(self)))]
+        idx = int(idx)
+        if idx < 0:
+            idx += len(self)
+        if not 0 <= idx < len(self):
+            raise IndexError("iterate index out of range")
+        if idx in self._cache:
+            return self._cache[idx]
+        ctx = self._session.ctx
+        if ctx.closed or ctx.generation != self._gen:
+            raise RuntimeError("the device session that holds these iterates was closed or reused; "
+                               "use history='eager' to copy all iterates to the host")
+        if idx == 0:
+            arr = ctx.download(nat.VEC_R0)
+        else:
+            ctx.form_iterate(self._ys[idx])
+            arr = ctx.download(nat.VEC_X)
+        self._cache[idx] = arr
+        return arr
+
+    def materialise(self):
+        return [self[i] for i in range(len(self))]
+
+
+# ==============================================================================================
+# shared Arnoldi driver
+# ==============================================================================================
+class _Arnoldi:
+    """Feeds Hessenberg columns to the solvers; hides launch/wait lookahead (solvers.py:190-198)."""
+
+    def __init__(self, sess, k, lookahead):
+        self.sess, self.k, self.lookahead = sess, k, bool(lookahead)
+        self.H = np.zeros((k + 1, k))
+        self._inflight = None
+
+    def column(self, j):
+        if self._inflight != j:
+            self.sess.arnoldi_launch(j)
+        col = self.sess.arnoldi_wait(j)
+        self._inflight = None
+        self.H[: j + 2, j] = col
+        return col
+
+    def prefetch(self, j):
+        if self.lookahead and j < self.k and self._inflight is None:
+            self.sess.arnoldi_launch(j)
+            self._inflight = j
+
+    def drain(self):
+        if self._inflight is not None:
+            self.sess.arnoldi_wait(self._inflight)
+            self._inflight = None
+
+
+def _acquire(session, A, b, x0, k, conlist, pre, device, orth):
+    if session is not None:
+        if session.k < k:
+            raise ValueError(f"session was created for k={session.k} < {k}")
+        return session
+    return DeviceSession(A, b, x0, k, conlist=conlist, pre=pre, device=device, orth=orth)
+
+
+def _finish_history(hist, history_mode, x_last):
+    if x_last is not None:
+        hist._set_cached(len(hist) - 1, x_last)
+    if history_mode == "eager":
+        return hist.materialise()
+    if history_mode != "lazy":
+        raise ValueError("history must be 'lazy' or 'eager'")
+    return hist
+
+
+def _unconstrained(engine, Hj, beta, y0, ftol):
+    if engine == "slsqp":
+        return smallsolve.slsqp(Hj, beta, y0, (), ftol=ftol, tol=None)
+    return smallsolve.lstsq(Hj, beta)
+
+
+def _constrained(engine, Hj, beta, y0, cons, ftol, tol):
+    if engine == "slsqp":
+        return smallsolve.slsqp(Hj, beta, y0, cons, ftol=ftol, tol=tol)
+    return smallsolve.kkt(Hj, beta, y0, cons)
+
+
+def _warn_message(j, res):
+    if not smallsolve.message_is_quiet(res.message):
+        warnings.warn("Iteration %d failed with message '%s'" % (j, res.message), RuntimeWarning)
+
+
+# ==============================================================================================
+# FGMRES (solvers.py:58-127)
+# ==============================================================================================
+def gmres(A, b, x0, k, tol=1e-50, pre=None, *, session=None, lookahead=None, history=None,
+          device=None, orth=None, small_solver=None):
+    """Right-preconditioned flexible GMRES; returns (x_last, {'name','x','res','steps'})."""
+    sess = _acquire(session, A, b, x0, k, (), pre, device, orth)
+    arn = _Arnoldi(sess, k, _opt("lookahead", lookahead))
+    beta = sess.begin()                                   # r0, ||r0||, q0       (solvers.py:78-88)
+    hist = IterateHistory(sess)
+    residual = [beta]
+    steps = 0
+    x_last = None
+    for j in range(k):
+        steps = j + 1
+        col = arn.column(j)                               # (solvers.py:94-100)
+        if not col[j + 1] != 0:
+            warnings.warn(_BREAKDOWN)                     # (solvers.py:104-106)
+            break
+        arn.prefetch(j + 1)
+        yk = smallsolve.lstsq(arn.H[: j + 2, : j + 1], beta).x        # (solvers.py:113)
+        residual.append(sess.ctx.iterate_residual(yk))    # x_j and ||A x_j - b|| (solvers.py:115-116)
+        hist._append(yk)
+        if residual[-1] < tol:
+            break
+    arn.drain()
+    if len(hist) > 1:
+        x_last = sess.ctx.download(nat.VEC_X)
+    else:
+        x_last = hist[0]
+    info = {"name": "gmres",
+            "x": _finish_history(hist, _opt("history", history), x_last),
+            "res": residual[1:],
+            "steps": steps}
+    return x_last, info
+
+
+# ==============================================================================================
+# CGMRES (solvers.py:131-323)
+# ==============================================================================================
+def cgmres(A, b, x0, k, tol=1e-8, contol=10, conlist=[], pre=None, timing=None, *,
+           session=None, small_solver=None, lookahead=None, history=None, device=None, orth=None):
+    """Conservative FGMRES: unconstrained until residual <= contol*tol, then the reduced
+    quadratic invariants are imposed as equality constraints on the Krylov coefficients."""
+    ctol = 1e-12                                          # (solvers.py:138)
+    engine = _opt("small_solver", small_solver)
+    if engine not in ("slsqp", "kkt"):
+        raise ValueError("small_solver must be 'slsqp' or 'kkt'")
+    if timing:
+        jit = {"start": time(), "start_iter": [], "end_iter": [],
+               "start_constraints": [], "end_constraints": []}
+    sess = _acquire(session, A, b, x0, k, conlist, pre, device, orth)
+    arn = _Arnoldi(sess, k, _opt("lookahead", lookahead))
+    safety = None                                         # (solvers.py:163)
+    beta = sess.begin()
+    hist = IterateHistory(sess)
+    residual = [beta]
+    constrained_steps = 0
+    steps = 0
+    yk = None
+    for j in range(k):
+        if timing:
+            jit["start_iter"].append(time())
+        steps = j + 1
+        col = arn.column(j)
+        if not col[j + 1] != 0:
+            warnings.warn(_BREAKDOWN)                     # (solvers.py:199-202)
+            break
+        Hj = arn.H[: j + 2, : j + 1]
+        y0 = np.zeros(j + 1)
+        if j != 0:
+            y0[:-1] = yk                                  # warm start (solvers.py:225-227)
+        if residual[-1] > contol * tol and j < k - 1 and safety is None:      # (solvers.py:230)
+            arn.prefetch(j + 1)
+            res = _unconstrained(engine, Hj, beta, y0, ctol ** 2)
+        else:
+            try:
+                if timing:
+                    constrained_steps += 1
+                    jit["start_constraints"].append(time())
+                cons = sess.containers(j + 1)             # (solvers.py:242-247)
+                if timing:
+                    jit["end_constraints"].append(time())
+                arn.prefetch(j + 1)
+                res = _constrained(engine, Hj, beta, y0, cons, ctol ** 2, None)   # (solvers.py:251-255)
+                if not timing and np.isnan(max(res.x)):
+                    raise ValueError("constrained solve returned NaN")           # (solvers.py:258-260)
+                safety = True
+                if not timing:
+                    dev = constraint_checker(res.x, [c.as_scipy() for c in cons])
+                    if dev > ctol:
+                        # The reference sets safety=False and then dies on a missing attribute
+                        # inside its try block, i.e. lands in the unconstrained fallback
+                        # (solvers.py:266-278).  Same outcome here.
+                        safety = False
+                        raise RuntimeError("Iteration %d failed to preserve constraints with "
+                                           "deviation of %e" % (j, dev))
+            except (nat.SpisError, nat.NativeLibraryError):
+                raise                                     # device failures are never swallowed
+            except Exception:
+                warnings.warn("Constrained solve failed, defaulted to standard solve for iteration %d."
+                              " Problem likely overconstrained, a smaller solver tolerance may be "
+                              "required." % j, RuntimeWarning)
+                if timing and len(jit["end_constraints"]) < len(jit["start_constraints"]):
+                    jit["end_constraints"].append(time())
+                arn.prefetch(j + 1)
+                res = _unconstrained(engine, Hj, beta, y0, ctol ** 2)         # (solvers.py:274-278)
+        _warn_message(j, res)
+        yk = res.x
+        residual.append(sess.ctx.iterate_residual(yk))    # (solvers.py:287,290)
+        hist._append(yk)
+        if timing:
+            jit["end_iter"].append(time())
+        if residual[-1] < tol and safety is True:         # (solvers.py:296-297)
+            break
+    arn.drain()
+    if timing:                                            # (solvers.py:300-312)
+        jit["end"] = time()
+        iter_time = np.asarray(jit["end_iter"]) - np.asarray(jit["start_iter"][: len(jit["end_iter"])])
+        iter_unconstrained = iter_time[:-constrained_steps]
+        assembly = np.asarray(jit["end_constraints"]) - np.asarray(jit["start_constraints"])
+        iter_constrained = iter_time[len(iter_unconstrained):] - assembly
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)
+            timings = {"runtime": jit["end"] - jit["start"],
+                       "iter_time_unconstrained": np.mean(iter_unconstrained),
+                       "iter_time_constrained": np.mean(iter_constrained),
+                       "constraint_building": np.mean(assembly),
+                       "constrained_steps": constrained_steps}
+    else:
+        timings = None
+    if len(hist) > 1:
+        x_last = sess.ctx.download(nat.VEC_X)
+    else:
+        x_last = hist[0]
+    info = {"name": "cgmres",
+            "x": _finish_history(hist, _opt("history", history), x_last),
+            "res": residual[1:],
+            "steps": steps,
+            "timings": timings}
+    return x_last, info
+
+
+# ==============================================================================================
+# prototypical CGMRES (solvers.py:328-445)
+# ==============================================================================================
+def cgmres_p(A, b, x0, k, conlist=[], pre=None, *, session=None, small_solver=None,
+             lookahead=None, history=None, device=None, orth=None):
+    """Constraints are switched on one per iteration (clist[:j]); always runs k iterations."""
+    engine = _opt("small_solver", small_solver)
+    if engine not in ("slsqp", "kkt"):
+        raise ValueError("small_solver must be 'slsqp' or 'kkt'")
+    sess = _acquire(session, A, b, x0, k, conlist, pre, device, orth)
+    arn = _Arnoldi(sess, k, _opt("lookahead", lookahead))
+    beta = sess.begin()
+    hist = IterateHistory(sess)
+    residual = []                                         # no initial residual (solvers.py:352)
+    yk = None
+    for j in range(k):
+        col = arn.column(j)                               # no break on breakdown (solvers.py:376-377)
+        Hj = arn.H[: j + 2, : j + 1]
+        cons = sess.containers(j + 1)                     # all constraints, every step (solvers.py:397-401)
+        if col[j + 1] != 0:
+            arn.prefetch(j + 1)
+        y0 = np.zeros(j + 1)
+        if j != 0:
+            y0[:-1] = yk
+        res = _constrained(engine, Hj, beta, y0, cons[:j], 1e-20, 1e-15)      # (solvers.py:411-415)
+        if np.isnan(max(res.x)):                          # (solvers.py:418-424)
+            warnings.warn("Constrained solve silently failed on iteration %d" % j)
+            res = _unconstrained(engine, Hj, beta, y0, 1e-20)
+        _warn_message(j, res)
+        yk = res.x
+        residual.append(sess.ctx.iterate_residual(yk))    # (solvers.py:434-437)
+        hist._append(yk)
+    arn.drain()
+    x_last = sess.ctx.download(nat.VEC_X) if len(hist) > 1 else hist[0]
+    info = {"name": "geosolve",
+            "x": _finish_history(hist, _opt("history", history), x_last),
+            "res": residual}
+    return x_last, info

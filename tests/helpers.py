@@ -1,0 +1,80 @@
+"""Shared helpers for the parity tests."""
+import warnings
+
+import numpy as np
+
+import cases
+from structurepreservingiterativesolvers_b200 import solvers, wrappers
+
+
+def run_product(name, ctx_factory=None, **ext):
+    """Solve a golden case through the package's wrapper mirror; returns (x, info, dic, prob)."""
+    spec, dic, prob, x0, pre = cases.instantiate(name)
+    kw = cases.wrapper_kwargs(spec, x0, pre, prob)
+    wrap = getattr(wrappers, spec["exp"])
+    fn = wrap.cgmresWrapper if spec["kind"] == "cgmres" else wrap.gmresWrapper
+    if ctx_factory is not None:
+        # build the session by hand so the test double can be injected
+        cl = []
+        if spec["kind"] == "cgmres":
+            cl = wrap.conlist(dic, x0, prob) if spec["exp"] == "lkdvRK" else wrap.conlist(dic, x0)
+        ext = dict(ext)
+        ext["session"] = solvers.DeviceSession(dic["A"], dic["b"], x0, spec["k"], conlist=cl, pre=pre,
+                                               ctx_factory=ctx_factory)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        x, info = fn(dic, **kw, **ext)
+    return x, info, dic, prob
+
+
+def run_oracle(name):
+    """Solve a golden case with the numpy oracle and the same constraint list."""
+    from oracle import cgmres_oracle as orc
+    spec, dic, prob, x0, pre = cases.instantiate(name)
+    wrap = getattr(wrappers, spec["exp"])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        if spec["kind"] == "gmres":
+            return orc.fgmres(dic["A"], dic["b"], x0, spec["k"], tol=spec["tol"], pre=pre)
+        cl = wrap.conlist(dic, x0, prob) if spec["exp"] == "lkdvRK" else wrap.conlist(dic, x0)
+        proto = (spec["tol"] <= 1e-20) if spec["exp"] in ("lkdv", "lkdvRK") else (spec["tol"] < 1e-20)
+        if proto:
+            return orc.cgmres_prototype(dic["A"], dic["b"], x0, spec["k"], conlist=cl, pre=pre)
+        kw = {}
+        if "contol" in spec and spec["exp"] in ("lkdv", "lkdvRK"):
+            kw["contol"] = spec["contol"]
+        return orc.cgmres(dic["A"], dic["b"], x0, spec["k"], tol=spec["tol"], conlist=cl, pre=pre,
+                          timing=spec.get("timing"), **kw)
+
+
+def rel_diff(a, b):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def fingerprint(dic):
+    return np.array([dic["A"].data.sum(), np.abs(dic["A"].data).sum(), dic["b"].sum(),
+                     np.abs(dic["b"]).sum(), float(dic["A"].nnz)])
+
+
+def check_histories(name, info, dic, golden, intermediate_tol=1e-6):
+    """Residual and iterate histories against the golden reference output.
+
+    Intermediate iterates are reproducible only to ~1e-7: constrained ones come out of SLSQP runs
+    that stop on `maxiter`, and once GMRES has converged to round-off the new basis vectors are
+    noise (measured: 4.5e-7 between the reference's MGS and a CGS2 Arnoldi).  The
+    final iterate is held to tolerance(name).  Residual norms are compared absolutely, bounded by
+    |A|_1 * |x_j - X_j| (the residual cannot differ by more than the iterates do)."""
+    from tolerances import tolerance
+    import scipy.sparse.linalg as spsla
+    X = golden[f"{name}/X"]
+    ref_res = golden[f"{name}/res"]
+    offset = len(X) - len(ref_res)                 # 1: x[0] is r0 and res has no entry for it
+    normA = spsla.norm(dic["A"], 1)
+    xs = info["x"]
+    for j in range(1, len(X)):
+        dx = np.linalg.norm(np.asarray(xs[j]) - X[j])
+        tol_j = tolerance(name) if j == len(X) - 1 else intermediate_tol
+        assert dx <= tol_j * np.linalg.norm(X[j]), (name, j, dx)
+        dr = abs(info["res"][j - offset] - ref_res[j - offset])
+        assert dr <= normA * dx + 1e-12 * np.linalg.norm(dic["b"]), (name, j, dr, dx)

@@ -1,0 +1,178 @@
+"""Kernel-level parity through the C ABI: each sm_100a kernel against numpy/scipy on seeded inputs.
+
+fp64 tolerances: a dot product of n terms summed in a different order differs by <= ~n*eps*|a||b|;
+the bounds below are 1e-13 relative to the natural scale of each quantity.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+from structurepreservingiterativesolvers_b200 import _native as nat
+from structurepreservingiterativesolvers_b200.device import KrylovContext
+from structurepreservingiterativesolvers_b200.preconditioners import BlockJacobiPreconditioner
+from structurepreservingiterativesolvers_b200.problems import heat, lkdv
+
+pytestmark = pytest.mark.gpu
+
+
+def ragged_matrix(n, seed, max_len=40, empty_every=7):
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(0, max_len, size=n)
+    lens[::empty_every] = 0                       # empty rows
+    lens[n // 2] = 3 * max_len                    # one long row
+    indptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    cols = rng.integers(0, n, size=indptr[-1])
+    vals = rng.standard_normal(indptr[-1])
+    return sps.csr_matrix((vals, cols, indptr), shape=(n, n))
+
+
+@pytest.mark.parametrize("fmt", [nat.FMT_SELL, nat.FMT_CSR, nat.FMT_AUTO])
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 1000, 4097])
+def test_spmv_ragged(n, fmt):
+    A = ragged_matrix(n, seed=n) if n > 40 else sps.random(n, n, density=0.6, random_state=n, format="csr")
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal(n)
+    with KrylovContext(n, 2) as ctx:
+        ctx.set_option("spmv_format", fmt)
+        ctx.upload_matrix(nat.SLOT_A, A)
+        y = ctx.op_spmv(nat.SLOT_A, x)
+    ref = A @ x
+    scale = np.abs(A) @ np.abs(x) + 1e-300
+    assert np.max(np.abs(y - ref) / scale) <= 1e-14
+
+
+def test_spmv_duplicates_and_unsorted_indices():
+    n = 257
+    rng = np.random.default_rng(5)
+    rows = rng.integers(0, n, 4000); cols = rng.integers(0, n, 4000); vals = rng.standard_normal(4000)
+    A = sps.coo_matrix((vals, (rows, cols)), shape=(n, n))
+    csr = sps.csr_matrix((vals, cols, np.searchsorted(np.sort(rows), np.arange(n + 1))), shape=(n, n))   # duplicates kept, unsorted
+    csr = sps.csr_matrix((vals[np.argsort(rows, kind="stable")], cols[np.argsort(rows, kind="stable")], csr.indptr), shape=(n, n))
+    x = rng.standard_normal(n)
+    with KrylovContext(n, 2) as ctx:
+        ctx.upload_matrix(nat.SLOT_A, csr)
+        y = ctx.op_spmv(nat.SLOT_A, x)
+    np.testing.assert_allclose(y, A @ x, rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("fmt", [nat.FMT_SELL, nat.FMT_CSR])
+def test_spmv_fem_operators(fmt):
+    d, _ = lkdv.linforms(space="CG", M=33_350, mlength=0.8 * 33_350)        # n = 100 050
+    h, _ = heat.linforms(M=150)
+    rng = np.random.default_rng(2)
+    for A in (d["A"], d["L"] - d["M"], h["A"]):
+        n = A.shape[0]
+        x = rng.standard_normal(n)
+        with KrylovContext(n, 2) as ctx:
+            ctx.set_option("spmv_format", fmt)
+            ctx.upload_matrix(nat.SLOT_A, A)
+            y1 = ctx.op_spmv(nat.SLOT_A, x)
+            y2 = ctx.op_spmv(nat.SLOT_A, x)
+            assert ctx.info(f"fmt:{nat.SLOT_A}") == fmt
+        np.testing.assert_array_equal(y1, y2)                      # deterministic
+        scale = np.abs(A) @ np.abs(x) + 1e-300
+        assert np.max(np.abs(y1 - A @ x) / scale) <= 1e-14
+
+
+@pytest.mark.parametrize("n", [2, 1023, 1024, 1025, 2049, 300_007])
+@pytest.mark.parametrize("m", [0, 1, 3, 4, 5, 21])
+def test_mdot(n, m):
+    rng = np.random.default_rng(n + m)
+    V = rng.standard_normal((m, n))
+    w = rng.standard_normal(n)
+    with KrylovContext(n, 24) as ctx:
+        out1 = ctx.op_mdot(V, w)
+        out2 = ctx.op_mdot(V, w)
+    np.testing.assert_array_equal(out1, out2)                      # fixed summation order
+    ref = np.concatenate([V @ w, [w @ w]])
+    scale = np.concatenate([np.abs(V) @ np.abs(w), [w @ w]]) + 1e-300
+    assert np.max(np.abs(out1 - ref) / scale) <= 1e-13
+
+
+@pytest.mark.parametrize("variant", [2, 4, 8])
+def test_mdot_variants_and_grid_sizes(variant):
+    n, m = 70_001, 13
+    rng = np.random.default_rng(7)
+    V = rng.standard_normal((m, n)); w = rng.standard_normal(n)
+    ref = np.concatenate([V @ w, [w @ w]])
+    for ctas in (1, 4, 16):
+        with KrylovContext(n, 16) as ctx:
+            ctx.set_option("mdot_variant", variant)
+            ctx.set_option("ctas_per_sm", ctas)
+            out = ctx.op_mdot(V, w)
+        np.testing.assert_allclose(out, ref, rtol=1e-12)
+
+
+@pytest.mark.parametrize("n", [2, 1023, 1025, 4096, 300_007])
+@pytest.mark.parametrize("m", [0, 1, 4, 7, 21])
+@pytest.mark.parametrize("with_base", [True, False])
+def test_lincomb(n, m, with_base):
+    rng = np.random.default_rng(n * 31 + m)
+    V = rng.standard_normal((m, n))
+    base = rng.standard_normal(n) if with_base else None
+    coef = rng.standard_normal(m)
+    with KrylovContext(n, 24) as ctx:
+        out, ss = ctx.op_lincomb(V, base, coef, sign=-1.0)
+    ref = (base if with_base else 0.0) - coef @ V if m else (base if with_base else np.zeros(n))
+    ref = np.asarray(ref, dtype=float) * np.ones(n)
+    scale = (np.abs(base) if with_base else 0.0) + np.abs(coef) @ np.abs(V) + 1e-300 if m else np.ones(n)
+    assert np.max(np.abs(out - ref) / scale) <= 1e-14
+    assert abs(ss - ref @ ref) <= 1e-12 * max(ref @ ref, 1e-300)
+
+
+@pytest.mark.parametrize("variant", [2, 4, 8])
+def test_lincomb_variants(variant):
+    n, m = 50_003, 11
+    rng = np.random.default_rng(9)
+    V = rng.standard_normal((m, n)); base = rng.standard_normal(n); coef = rng.standard_normal(m)
+    with KrylovContext(n, 16) as ctx:
+        ctx.set_option("lincomb_variant", variant)
+        out, ss = ctx.op_lincomb(V, base, coef, sign=1.0)
+    np.testing.assert_allclose(out, base + coef @ V, rtol=1e-12, atol=1e-12)
+
+
+def test_preconditioner_kernels():
+    d, _ = lkdv.linforms(space="CG", M=1000, mlength=800.0)
+    A = d["A"]
+    n = A.shape[0]
+    rng = np.random.default_rng(4)
+    q = rng.standard_normal(n)
+    with KrylovContext(n, 2) as ctx:
+        ctx.upload_vec(nat.VEC_PRE_DIAG, 1.0 / A.diagonal())
+        ctx.set_precond(nat.PRE_JACOBI)
+        np.testing.assert_allclose(ctx.op_precond(q), q / A.diagonal(), rtol=1e-15)
+        for layout, bs in (("field", 3), ("contiguous", 3), ("contiguous", 8), ("contiguous", 1)):
+            P = BlockJacobiPreconditioner(A, bs, layout)
+            ctx.upload_blocks(P.inv_blocks, P.stride_block, P.stride_field)
+            ctx.set_precond(nat.PRE_BLOCK)
+            np.testing.assert_allclose(ctx.op_precond(q), P @ q, rtol=1e-12, atol=1e-12)
+        Pm = sps.tril(A).tocsr()
+        ctx.upload_matrix(nat.SLOT_PRE, Pm)
+        ctx.set_precond(nat.PRE_CSR)
+        np.testing.assert_allclose(ctx.op_precond(q), Pm @ q, rtol=1e-12, atol=1e-12)
+
+
+def test_errors_are_reported_not_swallowed():
+    with KrylovContext(100, 4) as ctx:
+        with pytest.raises(nat.SpisError):
+            ctx.arnoldi_step(0)                                     # before solve_begin
+        with pytest.raises(ValueError):
+            ctx.upload_vec(nat.VEC_B, np.zeros(99))
+        with pytest.raises(ValueError):
+            ctx.upload_matrix(nat.SLOT_A, sps.identity(99, format="csr"))
+        with pytest.raises(nat.SpisError):
+            ctx.op_spmv(3, np.zeros(100))                           # slot never uploaded
+        with pytest.raises(nat.SpisError):
+            ctx.set_option("no_such_option", 1)
+    with pytest.raises(nat.SpisError):
+        KrylovContext(100, 4, device=99)
+
+
+def test_bench_kernel_entry_point():
+    d, _ = lkdv.linforms(space="CG", M=33_350, mlength=0.8 * 33_350)
+    n = d["A"].shape[0]
+    with KrylovContext(n, 8) as ctx:
+        ctx.upload_matrix(nat.SLOT_A, d["A"])
+        for cls in (nat.PROF_SPMV, nat.PROF_MDOT, nat.PROF_LINCOMB, nat.PROF_SCALE):
+            ms, by = ctx.bench_kernel(cls, 6, reps=3)
+            assert ms > 0 and by > 0

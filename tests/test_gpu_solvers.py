@@ -1,0 +1,177 @@
+"""Solver-level parity on the GPU: CUDA path vs the reference's golden outputs and vs the oracle."""
+import warnings
+
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+import cases
+import helpers
+from tolerances import tolerance
+from oracle import cgmres_oracle as orc
+from structurepreservingiterativesolvers_b200 import _native as nat
+from structurepreservingiterativesolvers_b200 import solvers, wrappers
+from structurepreservingiterativesolvers_b200.preconditioners import (BlockJacobiPreconditioner,
+                                                                      JacobiPreconditioner)
+from structurepreservingiterativesolvers_b200.problems import heat, lkdv
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("engine", ["slsqp", "kkt"])
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_cuda_path_matches_reference_output(name, engine, golden):
+    x, info, dic, prob = helpers.run_product(name, small_solver=engine)
+    assert info.get("steps", -1) == int(golden[f"{name}/steps"])
+    assert len(info["res"]) == len(golden[f"{name}/res"])
+    assert helpers.rel_diff(x, golden[f"{name}/x_last"]) <= tolerance(name)      # north_star: 1e-10 (+ reference self-noise)
+    assert helpers.rel_diff(info["x"][0], golden[f"{name}/X"][0]) <= 1e-13       # r0
+    if engine == "slsqp" or info["name"] != "geosolve":
+        helpers.check_histories(name, info, dic, golden)
+
+
+@pytest.mark.parametrize("name", ["lkdv_cg_tol6", "lkdv_cg_tol8_n1500", "heat_tol7_jacobi"])
+def test_mgs_option_tracks_reference_arithmetic(name, golden):
+    """With the reference's own orthogonalisation (modified Gram-Schmidt) the only differences left
+    are summation orders inside dots: the unconstrained iterates agree to ~1e-13."""
+    x, info, dic, prob = helpers.run_product(name, orth="mgs", lookahead=False)
+    X = golden[f"{name}/X"]
+    for j in range(1, 4):
+        assert helpers.rel_diff(info["x"][j], X[j]) <= 1e-12
+    assert helpers.rel_diff(x, golden[f"{name}/x_last"]) <= tolerance(name)
+
+
+def test_conserved_quantities_at_reference_level(golden):
+    """CGMRES holds mass/momentum/energy to ~1e-14 where plain GMRES drifts by ~1e-8
+    (lkdv/SingleSolve.py:44-56 printout; SURVEY 8c soft KAT)."""
+    x, info, dic, prob = helpers.run_product("lkdv_cg_tol6")
+    xg, infog, *_ = helpers.run_product("lkdv_cg_gmres_n1500")
+    inv = lkdv.compute_invariants(dic, x)
+    ref = lkdv.compute_invariants(dic, golden["lkdv_cg_tol6/x_last"])
+    for key, target in (("mass", dic["m0"]), ("momentum", dic["mo0"]), ("energy", dic["e0"])):
+        mag = max(abs(target), 1.0)
+        assert abs(inv[key] - target) <= 1e-12 * mag               # north_star: 1e-12 level
+        assert abs(inv[key] - target) <= 10 * abs(ref[key] - target) + 1e-13 * mag
+
+
+def test_session_reuse_and_profile():
+    spec, dic, prob, x0, pre = cases.instantiate("lkdv_cg_tol8_n1500")
+    cl = wrappers.lkdv.conlist(dic, x0)
+    sess = solvers.DeviceSession(dic["A"], dic["b"], x0, 50, conlist=cl, profile=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        x1, i1 = solvers.cgmres(dic["A"], dic["b"], x0, 50, tol=1e-8, conlist=cl, session=sess)
+        x2, i2 = solvers.cgmres(dic["A"], dic["b"], x0, 50, tol=1e-8, conlist=cl, session=sess)
+    np.testing.assert_array_equal(x1, x2)                           # deterministic kernels
+    prof = sess.ctx.profile()
+    assert prof["spmv"]["launches"] > 0 and prof["mdot"]["ms"] > 0 and prof["lincomb"]["gbs"] > 0
+    sess.close()
+    with pytest.raises(RuntimeError):
+        i2["x"][1]                                                  # lazy history needs the session
+
+
+def test_device_preconditioner_classes_match_oracle():
+    d, _ = lkdv.linforms(space="CG", M=400, mlength=320.0)
+    A, b = d["A"], d["b"]
+    x0 = np.zeros(b.size)
+    for pre in (JacobiPreconditioner(A), BlockJacobiPreconditioner(A, 3, "field"),
+                BlockJacobiPreconditioner(A, 3, "contiguous")):
+        xo, io = orc.fgmres(A, b, x0, 30, tol=1e-8, pre=pre)       # host `@` of the same object
+        xg, ig = solvers.gmres(A, b, x0, 30, tol=1e-8, pre=pre)
+        assert ig["steps"] == io["steps"]
+        assert helpers.rel_diff(xg, xo) <= 1e-10
+
+
+def test_constraint_container_api():
+    d, _ = lkdv.linforms(space="CG", M=60)
+    n = d["b"].size
+    rng = np.random.default_rng(0)
+    Z = np.asfortranarray(rng.standard_normal((n, 5)))
+    x0 = rng.standard_normal(n)
+    for const in wrappers.lkdv.conlist(d, x0):
+        ours = solvers.constraint_container(const, x0, Z)
+        ref = orc.ReducedInvariant(const, x0, Z)
+        assert abs(ours.term0 - ref.term0) <= 1e-12 * max(abs(ref.term0), 1.0)
+        np.testing.assert_allclose(ours.term1, ref.term1, rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(ours.term2, ref.term2, rtol=1e-12, atol=1e-12)
+        y = rng.standard_normal(5)
+        assert abs(ours.constraint_func(y) - ref.fun(y)) <= 1e-11 * max(abs(ref.fun(y)), 1.0)
+    with pytest.raises(NotImplementedError):
+        solvers.constraint_container(3.0, x0, Z)
+
+
+def test_nonsymmetric_constraint_matrix_terms():
+    """term2 = 1/2 Z^T (M Z) keeps both triangles for a non-symmetric M, as the reference does."""
+    d, _ = heat.linforms(M=10)
+    A, b = d["A"], d["b"]
+    n = b.size
+    Mns = (d["M"] + 0.3 * sps.triu(d["L"], 1)).tocsr()
+
+    class C:
+        pass
+    c = C(); c.M = Mns; c.v = 0.1 * np.arange(n) / n; c.c = -1.0
+    x0 = 0.01 * np.cos(np.arange(n))
+    sess = solvers.DeviceSession(A, b, x0, 6, conlist=[c])
+    sess.begin()
+    for j in range(4):
+        sess.arnoldi_launch(j); sess.arnoldi_wait(j)
+    t0, t1, t2 = sess.ctx.constraint_terms(0, 3)
+    t0b, t1b, t2b = sess.ctx.constraint_terms(0, 4)                  # incremental update
+    Z = sess.ctx.download_Z(0, 4).T
+    ref = orc.ReducedInvariant(c, x0, Z)
+    np.testing.assert_allclose(t2b, ref.term2, rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(t1b, ref.term1, rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(t2b[:3, :3], t2, rtol=0, atol=0)
+    assert abs(t0b - ref.term0) <= 1e-12 * abs(ref.term0)
+    sess.close()
+
+
+@pytest.mark.parametrize("engine", ["slsqp", "kkt"])
+def test_midsize_against_oracle(engine):
+    """n = 300 000 (oracle: ~2 s): solution parity, residual consistency, conservation."""
+    M = 100_000
+    d, _ = lkdv.linforms(space="CG", M=M, mlength=0.8 * M)
+    A, b = d["A"], d["b"]
+    n = b.size
+    x0 = np.zeros(n)
+    cl = wrappers.lkdv.conlist(d, x0)
+    tol = 1e-6 * np.sqrt(n / 150)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        xo, io = orc.cgmres(A, b, x0, 50, tol=tol, contol=10, conlist=cl)
+        xg, ig = solvers.cgmres(A, b, x0, 50, tol=tol, contol=10, conlist=cl, small_solver=engine)
+    assert ig["steps"] == io["steps"]
+    assert helpers.rel_diff(xg, xo) <= 1e-10
+    assert abs(ig["res"][-1] - np.linalg.norm(A @ xg - b)) <= 1e-12 * np.linalg.norm(b)
+    inv = lkdv.compute_invariants(d, xg)
+    for key, target in (("mass", d["m0"]), ("momentum", d["mo0"]), ("energy", d["e0"])):
+        assert abs(inv[key] - target) <= 1e-12 * max(abs(target), 1.0)
+
+
+def test_full_size_properties():
+    """BASELINE configs[1] size (1e7 DOFs): size-independent properties instead of an oracle run --
+    the true residual returned by the device equals ||A x - b|| recomputed on the host, Krylov
+    residuals decrease monotonically (GMRES optimality), invariants are conserved, and the Arnoldi
+    basis is orthonormal to round-off."""
+    M = lkdv.benchmark_size()
+    d, _ = lkdv.linforms(space="CG", M=M, mlength=0.8 * M)
+    A, b = d["A"], d["b"]
+    n = b.size
+    x0 = np.zeros(n)
+    cl = [wrappers.lkdv.conlist(d, x0)[i] for i in (0, 2)]          # mass + energy (BASELINE configs[1])
+    k = 12
+    sess = solvers.DeviceSession(A, b, x0, k, conlist=cl)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        x, info = solvers.cgmres(A, b, x0, k, tol=1e-9, contol=10, conlist=cl, small_solver="kkt", session=sess)
+    assert info["steps"] == k
+    res = np.asarray(info["res"])
+    assert np.all(np.diff(res[:-1]) <= 1e-12 * res[0])              # unconstrained phase is monotone
+    host_res = np.linalg.norm(A @ x - b)
+    assert abs(host_res - res[-1]) <= 1e-11 * np.linalg.norm(b)
+    inv = lkdv.compute_invariants(d, x)
+    assert abs(inv["mass"] - d["m0"]) <= 1e-12 * abs(d["m0"])       # last step is constrained (j = k-1)
+    assert abs(inv["energy"] - d["e0"]) <= 1e-12 * max(abs(d["e0"]), abs(d["mo0"]))
+    q3, q7 = sess.ctx.download(nat.VEC_Q, 3), sess.ctx.download(nat.VEC_Q, 7)
+    assert abs(q3 @ q3 - 1.0) <= 1e-13 and abs(q3 @ q7) <= 1e-13
+    sess.close()

