@@ -24,6 +24,7 @@
 #ifndef SPIS_B200_H
 #define SPIS_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -100,6 +101,15 @@ const char* spis_last_global_error(void);            /* for failures of spis_ctx
 /* keys: "orth", "spmv_format", "profile", "ctas_per_sm", "mdot_variant", "lincomb_variant", "spmv_variant" */
 int         spis_set_option(spis_ctx* ctx, const char* key, int64_t value);
 int         spis_get_info(const spis_ctx* ctx, const char* key, int64_t* value_out);
+
+/* Page-locked host buffers from a process-wide pool (results of spis_download_vec land at full
+ * PCIe speed when the destination comes from here; pageable destinations run at ~4 GB/s).     */
+int         spis_pinned_alloc(size_t bytes, void** ptr_out);
+int         spis_pinned_free(void* ptr);
+int         spis_pinned_trim(void);            /* release every unused pooled buffer */
+/* host utility: *out = 1 if any of the n doubles is non-zero (multi-threaded scan; used to
+ * recognise the explicit-zero constraint matrix `0*A` of lkdv/LinearSolver.py:30)             */
+int         spis_host_any_nonzero(const double* data, size_t n, int* out);
 
 /* ---- uploads ------------------------------------------------------------------------ */
 /* CSR matrix -> device (and SELL-32 conversion on device).  Replaces holding `A`, `pre`

@@ -40,6 +40,10 @@ SIGNATURES = {
     "spis_ctx_destroy": (C.c_int, [_ctx]),
     "spis_last_error": (C.c_char_p, [_ctx]),
     "spis_last_global_error": (C.c_char_p, []),
+    "spis_pinned_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "spis_pinned_free": (C.c_int, [C.c_void_p]),
+    "spis_pinned_trim": (C.c_int, []),
+    "spis_host_any_nonzero": (C.c_int, [_dp, C.c_size_t, C.POINTER(C.c_int)]),
     "spis_set_option": (C.c_int, [_ctx, C.c_char_p, C.c_int64]),
     "spis_get_info": (C.c_int, [_ctx, C.c_char_p, _lp]),
     "spis_upload_csr": (C.c_int, [_ctx, C.c_int, C.c_int64, C.c_int64, C.c_int64, _ip, _ip, _dp]),
@@ -139,3 +143,44 @@ def device_count() -> int:
     if rc != OK:
         raise SpisError(rc, lib.spis_last_global_error().decode())
     return cnt.value
+
+
+class _PinnedOwner:
+    """Owns one pooled page-locked buffer; exposes it to numpy through __array_interface__."""
+
+    def __init__(self, lib, ptr, n):
+        self._lib, self._ptr = lib, ptr
+        self.__array_interface__ = {"data": (ptr, False), "shape": (n,), "typestr": "<f8", "version": 3}
+
+    def __del__(self):  # pragma: no cover - finaliser
+        try:
+            self._lib.spis_pinned_free(C.c_void_p(self._ptr))
+        except Exception:
+            pass
+
+
+_PINNED_LIMIT = 2 << 30          # bytes of result buffers handed out from the pool at any time
+_pinned_out = 0
+
+
+def pinned_empty(n: int) -> np.ndarray:
+    """float64 vector in page-locked memory (falls back to a normal array over the budget)."""
+    global _pinned_out
+    lib = load_library()
+    if n * 8 > _PINNED_LIMIT:
+        return np.empty(n, dtype=np.float64)
+    ptr = C.c_void_p()
+    if lib.spis_pinned_alloc(n * 8, C.byref(ptr)) != OK or not ptr.value:
+        return np.empty(n, dtype=np.float64)
+    return np.asarray(_PinnedOwner(lib, ptr.value, n))
+
+
+def any_nonzero(a) -> bool:
+    """Fast `np.any(a)` for large float64 buffers (threads in the C library)."""
+    a = np.asarray(a)
+    if a.dtype != np.float64 or not a.flags.c_contiguous or a.size < (1 << 16):
+        return bool(np.any(a))
+    out = C.c_int(0)
+    if load_library().spis_host_any_nonzero(dptr(a), a.size, C.byref(out)) != OK:
+        return bool(np.any(a))
+    return bool(out.value)

@@ -12,6 +12,9 @@
 #include <cstdio>
 #include <cstring>
 #include <initializer_list>
+#include <atomic>
+#include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -63,7 +66,7 @@ struct spis_ctx {
   int profile = 0;
   int ctas_per_sm = 4;
   int spmv_ctas_per_sm = 8;
-  int mdot_variant = 4, lincomb_variant = 4;
+  int mdot_variant = 0, lincomb_variant = 4;   // mdot 0 = auto (tools/tune.py sweep, profiles/tune_r1.md)
   int x0_is_zero = 0;
   int fuse_jacobi = 1;
   // vectors
@@ -116,12 +119,29 @@ int fail(spis_ctx* c, int code, const char* fmt, ...) {
 
 inline int64_t roundup(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 
+// Device memory comes from the device's default stream-ordered memory pool with the release
+// threshold raised to "never": a context that is created per solve (the reference's call pattern:
+// one solvers.cgmres call per time step, lkdv/Evolve.py:39-56) re-uses the ~10 GB of the previous
+// one instead of paying cudaMalloc/cudaFree (measured 100+ ms per solve) every time.
+int pool_init(spis_ctx* ctx) {
+  cudaMemPool_t pool;
+  CU(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+  uint64_t keep = UINT64_MAX;
+  CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  return SPIS_OK;
+}
+
 template <class Tp> int dalloc(spis_ctx* ctx, Tp** p, size_t count, bool zero = true) {
   *p = nullptr;
   if (count == 0) count = 1;
-  CU(cudaMalloc((void**)p, count * sizeof(Tp)));
+  CU(cudaMallocAsync((void**)p, count * sizeof(Tp), ctx->stream));
   if (zero) CU(cudaMemsetAsync(*p, 0, count * sizeof(Tp), ctx->stream));
   return SPIS_OK;
+}
+
+template <class Tp> void dfree(spis_ctx* ctx, Tp*& p) {
+  if (p) cudaFreeAsync((void*)p, ctx->stream);
+  p = nullptr;
 }
 
 int h2d(spis_ctx* ctx, void* dst, const void* src, size_t bytes) {
@@ -195,12 +215,15 @@ int launch_mdot(spis_ctx* ctx, const double* V, int m, const double* extra, int 
   if (nrows == 0) return SPIS_OK;
   REQUIRE(nrows <= ctx->pstride, "mdot: %d rows exceed workspace %d", nrows, ctx->pstride);
   const int64_t ntiles = (ctx->n + kTile - 1) / kTile;
-  const int grid = grid_for(ctx, ntiles, ctx->ctas_per_sm);
+  // measured on B200 (n = 1e7): few rows want more loads per thread on fewer CTAs, many rows the opposite
+  int variant = ctx->mdot_variant, per_sm = ctx->ctas_per_sm;
+  if (variant == 0) { variant = nrows <= 6 ? 4 : 2; per_sm = nrows <= 6 ? (ctx->ctas_per_sm > 2 ? 2 : ctx->ctas_per_sm) : ctx->ctas_per_sm; }
+  const int grid = grid_for(ctx, ntiles, per_sm);
   const size_t smem = (size_t)(kWarps * nrows + kWarps * 32) * sizeof(double);
   TRY(prof_begin(ctx, SPIS_PROF_MDOT, (double)(m + (extra ? 1 : 0) + 1) * 8.0 * (double)ctx->n));
-  if (ctx->mdot_variant == 8)
+  if (variant == 8)
     mdot_kernel<8><<<grid, kThreads, smem, ctx->stream>>>(V, ctx->ld, m, extra, with_sumsq, w, ctx->n, ctx->d_partial, ctx->pstride, ctx->d_counter, out);
-  else if (ctx->mdot_variant == 2)
+  else if (variant == 2)
     mdot_kernel<2><<<grid, kThreads, smem, ctx->stream>>>(V, ctx->ld, m, extra, with_sumsq, w, ctx->n, ctx->d_partial, ctx->pstride, ctx->d_counter, out);
   else
     mdot_kernel<4><<<grid, kThreads, smem, ctx->stream>>>(V, ctx->ld, m, extra, with_sumsq, w, ctx->n, ctx->d_partial, ctx->pstride, ctx->d_counter, out);
@@ -304,9 +327,9 @@ int launch_precond(spis_ctx* ctx, const double* q, double* z) {
   }
 }
 
-void free_matrix(Matrix& M) {
-  cudaFree(M.indptr); cudaFree(M.cols); cudaFree(M.vals);
-  cudaFree(M.slice_off); cudaFree(M.scols); cudaFree(M.svals);
+void free_matrix(spis_ctx* ctx, Matrix& M) {
+  dfree(ctx, M.indptr); dfree(ctx, M.cols); dfree(ctx, M.vals);
+  dfree(ctx, M.slice_off); dfree(ctx, M.scols); dfree(ctx, M.svals);
   M = Matrix();
 }
 
@@ -319,8 +342,87 @@ int ensure_Z(spis_ctx* ctx) {
 
 }  // namespace
 
-// =========================================================================================
+// ---- process-wide pool of page-locked host buffers -----------------------------------------
+// cudaMallocHost costs ~0.3 ms/MB; results (the 8n-byte solution vector) and the small staging
+// buffers are recycled across contexts instead.
+namespace {
+struct PinnedBlock { void* p; size_t cap; bool used; };
+std::mutex g_pin_mu;
+std::vector<PinnedBlock> g_pin;
+}  // namespace
+
 extern "C" {
+
+int spis_pinned_alloc(size_t bytes, void** out) {
+  if (!out) return SPIS_E_INVALID;
+  *out = nullptr;
+  if (bytes == 0) bytes = 8;
+  std::lock_guard<std::mutex> lk(g_pin_mu);
+  PinnedBlock* best = nullptr;
+  for (auto& b : g_pin)
+    if (!b.used && b.cap >= bytes && b.cap <= 2 * bytes + 4096 && (!best || b.cap < best->cap)) best = &b;
+  if (best) { best->used = true; *out = best->p; return SPIS_OK; }
+  void* p = nullptr;
+  cudaError_t e = cudaMallocHost(&p, bytes);
+  if (e != cudaSuccess) { spis_ctx* ctx = nullptr; return fail(ctx, SPIS_E_NOMEM, "cudaMallocHost(%zu): %s", bytes, cudaGetErrorString(e)); }
+  g_pin.push_back({p, bytes, true});
+  *out = p;
+  return SPIS_OK;
+}
+
+int spis_pinned_free(void* p) {
+  if (!p) return SPIS_OK;
+  std::lock_guard<std::mutex> lk(g_pin_mu);
+  for (auto& b : g_pin)
+    if (b.p == p) { b.used = false; return SPIS_OK; }
+  return SPIS_E_INVALID;
+}
+
+int spis_pinned_trim(void) {
+  std::lock_guard<std::mutex> lk(g_pin_mu);
+  std::vector<PinnedBlock> keep;
+  for (auto& b : g_pin) { if (b.used) keep.push_back(b); else cudaFreeHost(b.p); }
+  g_pin.swap(keep);
+  return SPIS_OK;
+}
+
+// Multi-threaded "does this host buffer hold any non-zero double?" (-0.0 counts as zero, NaN as
+// non-zero).  The reference's mass constraint is `0*A`, a CSR with A's pattern and all-zero data
+// (lkdv/LinearSolver.py:30); recognising it (to skip its SpMM) means scanning
+// 8*nnz bytes, which numpy's any() does at ~8 GB/s on one core.
+int spis_host_any_nonzero(const double* p, size_t n, int* out) {
+  if (!out || (!p && n)) return SPIS_E_INVALID;
+  std::atomic<int> found(0);
+  auto scan = [&](size_t lo, size_t hi) {
+    const uint64_t* q = reinterpret_cast<const uint64_t*>(p);
+    const size_t blk = 8192;
+    for (size_t i = lo; i < hi && !found.load(std::memory_order_relaxed); i += blk) {
+      const size_t e = i + blk < hi ? i + blk : hi;
+      uint64_t acc = 0;
+      for (size_t k = i; k < e; ++k) acc |= q[k];
+      if (acc & 0x7fffffffffffffffull) {
+        for (size_t k = i; k < e; ++k)
+          if (q[k] & 0x7fffffffffffffffull) { found.store(1); break; }
+      }
+    }
+  };
+  unsigned nt = std::thread::hardware_concurrency();
+  if (nt == 0) nt = 4;
+  if (nt > 16) nt = 16;
+  if (n < (size_t)1 << 20) nt = 1;
+  if (nt == 1) scan(0, n);
+  else {
+    std::vector<std::thread> th;
+    const size_t per = (n + nt - 1) / nt;
+    for (unsigned t = 0; t < nt; ++t) {
+      const size_t lo = (size_t)t * per, hi = lo + per < n ? lo + per : n;
+      if (lo < hi) th.emplace_back(scan, lo, hi);
+    }
+    for (auto& t : th) t.join();
+  }
+  *out = found.load();
+  return SPIS_OK;
+}
 
 int spis_abi_version(void) { return SPIS_ABI_VERSION; }
 
@@ -382,9 +484,13 @@ int spis_ctx_create(int device, int64_t n, int64_t n_halo, int k_max, void* stre
   CTRY(dalloc(c, &c->d_cout, (size_t)k_max * 2 * c->K));
   CTRY(dalloc(c, &c->d_partial, (size_t)c->max_grid * c->pstride));
   CTRY(dalloc(c, &c->d_counter, 4));
-  CCU(cudaMallocHost((void**)&c->h_small, ((size_t)2 * c->K + 8) * sizeof(double)));
-  CCU(cudaMallocHost((void**)&c->h_y, (size_t)c->K * sizeof(double)));
-  CCU(cudaMallocHost((void**)&c->h_cout, (size_t)k_max * 2 * c->K * sizeof(double)));
+  CTRY(pool_init(c));
+  if (spis_pinned_alloc(((size_t)2 * c->K + 8) * sizeof(double), (void**)&c->h_small) != SPIS_OK ||
+      spis_pinned_alloc((size_t)c->K * sizeof(double), (void**)&c->h_y) != SPIS_OK ||
+      spis_pinned_alloc((size_t)k_max * 2 * c->K * sizeof(double), (void**)&c->h_cout) != SPIS_OK) {
+    fail(c, SPIS_E_NOMEM, "pinned host allocation failed: %s", g_global_err);
+    return bail(SPIS_E_NOMEM);
+  }
   // mdot needs up to (8*(K)+256)*8 bytes of dynamic shared memory
   const int smem_need = (kWarps * c->K + kWarps * 32) * (int)sizeof(double);
   if (smem_need > 48 * 1024) {
@@ -405,12 +511,15 @@ int spis_ctx_destroy(spis_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (auto& r : ctx->recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   for (auto& e : ctx->evpool) cudaEventDestroy(e);
-  for (auto& M : ctx->mats) free_matrix(M);
-  for (auto& c : ctx->cons) { cudaFree(c.v); cudaFree(c.MZ); }
-  cudaFree(ctx->V); cudaFree(ctx->Z); cudaFree(ctx->W); cudaFree(ctx->T); cudaFree(ctx->R0);
-  cudaFree(ctx->B); cudaFree(ctx->X0); cudaFree(ctx->X); cudaFree(ctx->pre_diag); cudaFree(ctx->pre_blocks);
-  cudaFree(ctx->d_small); cudaFree(ctx->d_y); cudaFree(ctx->d_cout); cudaFree(ctx->d_partial); cudaFree(ctx->d_counter);
-  cudaFreeHost(ctx->h_small); cudaFreeHost(ctx->h_y); cudaFreeHost(ctx->h_cout);
+  if (ctx->stream) {
+    for (auto& M : ctx->mats) free_matrix(ctx, M);
+    for (auto& c : ctx->cons) { dfree(ctx, c.v); dfree(ctx, c.MZ); }
+    dfree(ctx, ctx->V); dfree(ctx, ctx->Z); dfree(ctx, ctx->W); dfree(ctx, ctx->T); dfree(ctx, ctx->R0);
+    dfree(ctx, ctx->B); dfree(ctx, ctx->X0); dfree(ctx, ctx->X); dfree(ctx, ctx->pre_diag); dfree(ctx, ctx->pre_blocks);
+    dfree(ctx, ctx->d_small); dfree(ctx, ctx->d_y); dfree(ctx, ctx->d_cout); dfree(ctx, ctx->d_partial); dfree(ctx, ctx->d_counter);
+    cudaStreamSynchronize(ctx->stream);
+  }
+  spis_pinned_free(ctx->h_small); spis_pinned_free(ctx->h_y); spis_pinned_free(ctx->h_cout);
   if (ctx->ev_arnoldi) cudaEventDestroy(ctx->ev_arnoldi);
   if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
   if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
@@ -427,7 +536,7 @@ int spis_set_option(spis_ctx* ctx, const char* key, int64_t value) {
   else if (k == "profile") { ctx->profile = value ? 1 : 0; }
   else if (k == "ctas_per_sm") { REQUIRE(value >= 1 && value <= 16, "ctas_per_sm must be 1..16"); ctx->ctas_per_sm = (int)value; }
   else if (k == "spmv_ctas_per_sm") { REQUIRE(value >= 1 && value <= 16, "spmv_ctas_per_sm must be 1..16"); ctx->spmv_ctas_per_sm = (int)value; }
-  else if (k == "mdot_variant") { REQUIRE(value == 2 || value == 4 || value == 8, "mdot_variant must be 2, 4 or 8"); ctx->mdot_variant = (int)value; }
+  else if (k == "mdot_variant") { REQUIRE(value == 0 || value == 2 || value == 4 || value == 8, "mdot_variant must be 0 (auto), 2, 4 or 8"); ctx->mdot_variant = (int)value; }
   else if (k == "lincomb_variant") { REQUIRE(value == 2 || value == 4 || value == 8, "lincomb_variant must be 2, 4 or 8"); ctx->lincomb_variant = (int)value; }
   else if (k == "x0_is_zero") { ctx->x0_is_zero = value ? 1 : 0; }
   else if (k == "fuse_jacobi") { ctx->fuse_jacobi = value ? 1 : 0; }
@@ -469,7 +578,7 @@ int spis_upload_csr(spis_ctx* ctx, int slot, int64_t nrows, int64_t ncols, int64
   REQUIRE(indptr && (nnz == 0 || (indices && data)), "null CSR arrays");
   CU(cudaSetDevice(ctx->device));
   Matrix& M = ctx->mats[slot];
-  free_matrix(M);
+  free_matrix(ctx, M);
   M.nrows = nrows; M.ncols = ncols; M.nnz = nnz;
   TRY(dalloc(ctx, &M.indptr, (size_t)nrows + 1, false));
   TRY(dalloc(ctx, &M.cols, (size_t)nnz, false));
@@ -491,7 +600,7 @@ int spis_upload_csr(spis_ctx* ctx, int slot, int64_t nrows, int64_t ncols, int64
   std::vector<int32_t> width((size_t)nslices);
   CU(cudaMemcpyAsync(width.data(), d_width, (size_t)nslices * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  cudaFree(d_width);
+  dfree(ctx, d_width);
   std::vector<int64_t> off((size_t)nslices + 1);
   off[0] = 0;
   for (int64_t s = 0; s < nslices; ++s) off[s + 1] = off[s] + (int64_t)width[s] * 32;
@@ -507,8 +616,7 @@ int spis_upload_csr(spis_ctx* ctx, int slot, int64_t nrows, int64_t ncols, int64
     sell_fill_kernel<<<cgrid, 256, 0, ctx->stream>>>(M.indptr, M.cols, M.vals, nrows, M.slice_off, M.scols, M.svals);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(ctx->stream));
-    cudaFree(M.indptr); cudaFree(M.cols); cudaFree(M.vals);
-    M.indptr = nullptr; M.cols = nullptr; M.vals = nullptr;
+    dfree(ctx, M.indptr); dfree(ctx, M.cols); dfree(ctx, M.vals);
   } else {
     const double avg = nrows ? (double)nnz / (double)nrows : 0.0;
     M.csr_lanes = avg <= 3 ? 2 : avg <= 6 ? 4 : avg <= 12 ? 8 : avg <= 24 ? 16 : 32;
@@ -541,7 +649,7 @@ int spis_upload_blocks(spis_ctx* ctx, int bs, int64_t nblk, int64_t sb, int64_t 
   REQUIRE(blocks && nblk > 0, "null blocks");
   REQUIRE((nblk - 1) * sb + (bs - 1) * sf < ctx->n, "block index map exceeds n");
   CU(cudaSetDevice(ctx->device));
-  cudaFree(ctx->pre_blocks); ctx->pre_blocks = nullptr;
+  dfree(ctx, ctx->pre_blocks);
   TRY(dalloc(ctx, &ctx->pre_blocks, (size_t)bs * bs * nblk, false));
   // host layout [i][r][c] -> device structure-of-arrays [(r*bs+c)][i]
   std::vector<double> soa((size_t)bs * bs * nblk);
@@ -700,8 +808,8 @@ int spis_constraint_define(spis_ctx* ctx, int c, int mat_slot, const double* v, 
   if (v) {
     if (!C.v) TRY(dalloc(ctx, &C.v, (size_t)ctx->ld));
     TRY(h2d(ctx, C.v, v, (size_t)ctx->n * sizeof(double)));
-  } else if (C.v) { cudaFree(C.v); C.v = nullptr; }
-  if (mat_slot < 0 && C.MZ) { cudaFree(C.MZ); C.MZ = nullptr; }
+  } else if (C.v) { dfree(ctx, C.v); }
+  if (mat_slot < 0 && C.MZ) { dfree(ctx, C.MZ); }
   C.T1.assign((size_t)ctx->kmax, 0.0);
   C.T2.assign((size_t)ctx->kmax * ctx->kmax, 0.0);
   return SPIS_OK;

@@ -156,9 +156,9 @@ class KrylovContext:
         return t0.value, t1, t2
 
     # -- downloads / bridges ------------------------------------------------------------------------
-    def download(self, which: int, j: int = 0) -> np.ndarray:
+    def download(self, which: int, j: int = 0, pinned: bool = False) -> np.ndarray:
         self._live()
-        out = np.empty(self.n, dtype=np.float64)
+        out = nat.pinned_empty(self.n) if pinned else np.empty(self.n, dtype=np.float64)
         self._check(self._lib.spis_download_vec(self._h, which, j, nat.dptr(out), self.n))
         return out
 

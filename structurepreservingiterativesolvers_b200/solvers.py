@@ -26,6 +26,8 @@ There is no CPU fallback: without libspis_b200.so or without an sm_100 GPU every
 from __future__ import annotations
 
 import collections.abc
+import os
+import sys
 import warnings
 from time import time
 
@@ -66,6 +68,22 @@ def configure(**kwargs):
 
 def _opt(name, value):
     return _CONFIG[name] if value is None else value
+
+
+_TRACE = bool(os.environ.get("SPIS_TRACE"))
+
+
+class _Trace:
+    """SPIS_TRACE=1 prints the wall-clock of each host-side phase to stderr."""
+
+    def __init__(self):
+        self.t = time()
+
+    def __call__(self, label):
+        if _TRACE:
+            now = time()
+            sys.stderr.write("[spis trace] %-34s %8.2f ms\n" % (label, (now - self.t) * 1e3))
+            self.t = now
 
 
 # ==============================================================================================
@@ -146,12 +164,14 @@ class DeviceSession:
 
     def __init__(self, A, b, x0, k, conlist=(), pre=None, *, device=None, orth=None,
                  spmv_format=None, profile=None, ctx_factory=KrylovContext):
+        tr = _Trace()
         b = nat.as_f64(b)
         n = b.size
         self.n, self.k = n, int(k)
         self.x0_host = nat.as_f64(x0, n)
         self.ctx = ctx_factory(n, self.k, device=_opt("device", device))
         ctx = self.ctx
+        tr("context create")
         ctx.set_option("orth", _ORTH[_opt("orth", orth)])
         ctx.set_option("spmv_format", _FMT[_opt("spmv_format", spmv_format)])
         ctx.set_option("profile", 1 if _opt("profile", profile) else 0)
@@ -160,13 +180,17 @@ class DeviceSession:
         if A.shape != (n, n):
             raise ValueError(f"A has shape {A.shape}, expected {(n, n)}")
         ctx.upload_matrix(nat.SLOT_A, A)
+        tr("upload A")
         ctx.upload_vec(nat.VEC_B, b)
         ctx.upload_vec(nat.VEC_X0, self.x0_host)
-        ctx.set_option("x0_is_zero", 0 if self.x0_host.any() else 1)
+        ctx.set_option("x0_is_zero", 0 if nat.any_nonzero(self.x0_host) else 1)
+        tr("upload b, x0")
         self._host_pre = None
         self._setup_precond(pre)
+        tr("preconditioner")
         self._cons = []
         self._setup_constraints(list(conlist))
+        tr("constraints")
         self._Zhost = None
         self._Zrows = 0
 
@@ -215,7 +239,7 @@ class DeviceSession:
                 try:
                     M, v, c = const.M, const.v, const.c
                     if sps.issparse(M):
-                        M_zero = M.nnz == 0 or not M.data.any()
+                        M_zero = M.nnz == 0 or not nat.any_nonzero(M.data)
                     else:
                         M = np.asarray(M, dtype=np.float64)
                         M_zero = not M.any()
@@ -224,7 +248,7 @@ class DeviceSession:
                         slot = nat.SLOT_CON0 + idx
                         self.ctx.upload_matrix(slot, M)
                     v = nat.as_f64(v, self.n)
-                    self.ctx.constraint_define(idx, slot, v if v.any() else None, float(c))
+                    self.ctx.constraint_define(idx, slot, v if nat.any_nonzero(v) else None, float(c))
                 except nat.NativeLibraryError:
                     raise
                 except Exception as exc:                    # surfaces where the reference builds containers
@@ -418,7 +442,7 @@ def gmres(A, b, x0, k, tol=1e-50, pre=None, *, session=None, lookahead=None, his
             break
     arn.drain()
     if len(hist) > 1:
-        x_last = sess.ctx.download(nat.VEC_X)
+        x_last = sess.ctx.download(nat.VEC_X, pinned=True)
     else:
         x_last = hist[0]
     info = {"name": "gmres",
@@ -523,7 +547,7 @@ def cgmres(A, b, x0, k, tol=1e-8, contol=10, conlist=[], pre=None, timing=None, 
     else:
         timings = None
     if len(hist) > 1:
-        x_last = sess.ctx.download(nat.VEC_X)
+        x_last = sess.ctx.download(nat.VEC_X, pinned=True)
     else:
         x_last = hist[0]
     info = {"name": "cgmres",
@@ -567,7 +591,7 @@ def cgmres_p(A, b, x0, k, conlist=[], pre=None, *, session=None, small_solver=No
         residual.append(sess.ctx.iterate_residual(yk))    # (solvers.py:434-437)
         hist._append(yk)
     arn.drain()
-    x_last = sess.ctx.download(nat.VEC_X) if len(hist) > 1 else hist[0]
+    x_last = sess.ctx.download(nat.VEC_X, pinned=True) if len(hist) > 1 else hist[0]
     info = {"name": "geosolve",
             "x": _finish_history(hist, _opt("history", history), x_last),
             "res": residual}

@@ -173,7 +173,7 @@ class FakeKrylovContext:
         return float(t0), C["T1"][:m].copy(), C["T2"][:m, :m].copy()
 
     # ---- downloads
-    def download(self, which, j=0):
+    def download(self, which, j=0, pinned=False):
         if which == nat.VEC_R0:
             return self.r0.copy()
         if which == nat.VEC_X:
