@@ -318,7 +318,7 @@ blockdiag_kernel(const double* __restrict__ blk, int64_t nblk, int64_t sb, int64
 // Algorithmic bytes: 12 nnz_padded + 8 (n/32) + 8 n (x) + 8 n (y or b) [+ 8 n b in mode 1].
 // ------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 8)   // 32 registers: all 2048 threads of an SM resident
 spmv_sell_kernel(const int64_t* __restrict__ slice_off, const int32_t* __restrict__ cols,
                  const double* __restrict__ vals, int64_t nrows, const double* __restrict__ x,
                  const double* __restrict__ b, double* __restrict__ y,

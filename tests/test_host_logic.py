@@ -220,3 +220,16 @@ def test_configure_rejects_unknown_keys():
         assert info["steps"] == 10
     finally:
         solvers.configure(small_solver=old)
+
+
+def test_system_export_roundtrip(tmp_path):
+    from structurepreservingiterativesolvers_b200 import io
+    d, _ = lkdv.linforms(space="DG", M=10)
+    io.save_system(tmp_path / "sys.npz", d)
+    e = io.load_system(tmp_path / "sys.npz")
+    assert set(e) == set(d)
+    for key in d:
+        if sps.issparse(d[key]):
+            assert (abs(d[key] - e[key])).nnz == 0 and e[key].nnz == d[key].nnz
+        else:
+            np.testing.assert_array_equal(np.asarray(d[key]), np.asarray(e[key]))
