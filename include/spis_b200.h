@@ -158,14 +158,19 @@ int spis_host_pre_get(spis_ctx* ctx, int j, double* q_host);
 int spis_host_pre_put(spis_ctx* ctx, int j, const double* z_host);
 
 /* ---- multi-GPU hooks (row-block sharding) -------------------------------- */
-/* After every local reduction the library calls allreduce(user, device_ptr, count) with a
- * DEVICE pointer to `count` doubles that must be summed in place over all ranks, ordered
- * on the context's stream.  Before every SpMV it calls halo(user, device_vec_ptr) which
- * must fill entries [n, n+n_halo) of that vector from the neighbouring ranks.  The host
- * language supplies both (torch.distributed over NCCL).                                 */
+/* Reductions: after every local reduction the library calls allreduce(user, device_ptr, count)
+ * with a DEVICE pointer to `count` doubles that must be summed in place over all ranks, ordered
+ * on the context's stream.
+ * Halo: spis_halo_set_plan uploads the local indices this rank must send (concatenated per
+ * destination rank).  Before every SpMV the library gathers those entries of the input vector
+ * into a contiguous device buffer (halo_pack_kernel) and calls halo(user, send_dev, recv_dev):
+ * the callback must deliver the peers' packed entries into recv_dev = &vec[hoff], n_halo
+ * doubles ordered by source rank.  The host language supplies both callbacks
+ * (torch.distributed over NCCL in distributed.py).                                        */
 typedef int (*spis_allreduce_fn)(void* user, void* device_ptr, int64_t count);
-typedef int (*spis_halo_fn)(void* user, void* device_vec_ptr);
+typedef int (*spis_halo_fn)(void* user, void* send_device_ptr, void* recv_device_ptr);
 int spis_set_collectives(spis_ctx* ctx, spis_allreduce_fn allreduce, spis_halo_fn halo, void* user);
+int spis_halo_set_plan(spis_ctx* ctx, const int32_t* send_idx, int64_t n_send);
 int spis_sync(spis_ctx* ctx);
 
 /* ---- measurement --------------------------------------------------------------------- */

@@ -25,7 +25,7 @@ PROF_SPMV, PROF_MDOT, PROF_LINCOMB, PROF_SCALE, PROF_PRECOND, PROF_OTHER, PROF_C
 PROF_NAMES = ("spmv", "mdot", "lincomb", "scale", "precond", "other")
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64)
-HALO_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p)
+HALO_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p)
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -63,6 +63,7 @@ SIGNATURES = {
     "spis_host_pre_get": (C.c_int, [_ctx, C.c_int, _dp]),
     "spis_host_pre_put": (C.c_int, [_ctx, C.c_int, _dp]),
     "spis_set_collectives": (C.c_int, [_ctx, ALLREDUCE_FN, HALO_FN, C.c_void_p]),
+    "spis_halo_set_plan": (C.c_int, [_ctx, _ip, C.c_int64]),
     "spis_sync": (C.c_int, [_ctx]),
     "spis_get_profile": (C.c_int, [_ctx, _dp, _dp, _lp]),
     "spis_reset_profile": (C.c_int, [_ctx]),

@@ -92,6 +92,7 @@ struct spis_ctx {
   Constraint cons[SPIS_MAX_SLOTS];
   // collectives
   spis_allreduce_fn allreduce = nullptr; spis_halo_fn halo = nullptr; void* cuser = nullptr;
+  int32_t* d_send_idx = nullptr; double* d_send = nullptr; int64_t n_send = 0;
   // profiling
   std::vector<ProfRec> recs; std::vector<cudaEvent_t> evpool;
   double prof_ms[SPIS_PROF_CLASSES] = {0}; double prof_bytes[SPIS_PROF_CLASSES] = {0}; int64_t prof_launch[SPIS_PROF_CLASSES] = {0};
@@ -202,8 +203,14 @@ int do_allreduce(spis_ctx* ctx, double* dev, int64_t count) {
   return SPIS_OK;
 }
 int do_halo(spis_ctx* ctx, double* vec) {
-  if (!ctx->halo || ctx->n_halo == 0) return SPIS_OK;
-  int r = ctx->halo(ctx->cuser, vec);
+  if (!ctx->halo || (ctx->n_halo == 0 && ctx->n_send == 0)) return SPIS_OK;
+  if (ctx->n_send > 0) {
+    const int grid = (int)((ctx->n_send + 255) / 256 < (int64_t)ctx->nsm * 8 ? (ctx->n_send + 255) / 256 : (int64_t)ctx->nsm * 8);
+    halo_pack_kernel<<<grid, 256, 0, ctx->stream>>>(vec, ctx->d_send_idx, ctx->n_send, ctx->d_send);
+    CU(cudaGetLastError());
+    ctx->prof_launch[SPIS_PROF_OTHER] += 1;
+  }
+  int r = ctx->halo(ctx->cuser, ctx->d_send, vec + ctx->hoff);
   if (r != 0) return fail(ctx, SPIS_E_INVALID, "halo callback failed (%d)", r);
   return SPIS_OK;
 }
@@ -516,6 +523,7 @@ int spis_ctx_destroy(spis_ctx* ctx) {
     for (auto& c : ctx->cons) { dfree(ctx, c.v); dfree(ctx, c.MZ); }
     dfree(ctx, ctx->V); dfree(ctx, ctx->Z); dfree(ctx, ctx->W); dfree(ctx, ctx->T); dfree(ctx, ctx->R0);
     dfree(ctx, ctx->B); dfree(ctx, ctx->X0); dfree(ctx, ctx->X); dfree(ctx, ctx->pre_diag); dfree(ctx, ctx->pre_blocks);
+    dfree(ctx, ctx->d_send_idx); dfree(ctx, ctx->d_send);
     dfree(ctx, ctx->d_small); dfree(ctx, ctx->d_y); dfree(ctx, ctx->d_cout); dfree(ctx, ctx->d_partial); dfree(ctx, ctx->d_counter);
     cudaStreamSynchronize(ctx->stream);
   }
@@ -563,6 +571,8 @@ int spis_get_info(const spis_ctx* cctx, const char* key, int64_t* value_out) {
     else *value_out = ctx->mats[slot].nnz;
   }
   else if (k == "device_ptr:small") *value_out = (int64_t)(intptr_t)ctx->d_small;
+  else if (k == "stream") *value_out = (int64_t)(intptr_t)ctx->stream;
+  else if (k == "n_send") *value_out = ctx->n_send;
   else return fail(ctx, SPIS_E_INVALID, "unknown info key '%s'", key);
   return SPIS_OK;
 }
@@ -935,6 +945,22 @@ int spis_host_pre_put(spis_ctx* ctx, int j, const double* z_host) {
 int spis_set_collectives(spis_ctx* ctx, spis_allreduce_fn allreduce, spis_halo_fn halo, void* user) {
   if (!ctx) return SPIS_E_INVALID;
   ctx->allreduce = allreduce; ctx->halo = halo; ctx->cuser = user;
+  return SPIS_OK;
+}
+
+int spis_halo_set_plan(spis_ctx* ctx, const int32_t* send_idx, int64_t n_send) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(n_send >= 0 && (send_idx || n_send == 0), "bad halo plan");
+  CU(cudaSetDevice(ctx->device));
+  for (int64_t i = 0; i < n_send; ++i)
+    REQUIRE(send_idx[i] >= 0 && send_idx[i] < ctx->n, "halo send index %lld out of range", (long long)send_idx[i]);
+  dfree(ctx, ctx->d_send_idx); dfree(ctx, ctx->d_send);
+  ctx->n_send = n_send;
+  if (n_send) {
+    TRY(dalloc(ctx, &ctx->d_send_idx, (size_t)n_send, false));
+    TRY(dalloc(ctx, &ctx->d_send, (size_t)n_send));
+    TRY(h2d(ctx, ctx->d_send_idx, send_idx, (size_t)n_send * sizeof(int32_t)));
+  }
   return SPIS_OK;
 }
 

@@ -475,6 +475,14 @@ __global__ void sell_fill_kernel(const int32_t* __restrict__ indptr, const int32
   }
 }
 
+// halo pack: send[i] = vec[idx[i]]  (entries of a vector that neighbouring ranks need as ghosts)
+__global__ void halo_pack_kernel(const double* __restrict__ vec, const int32_t* __restrict__ idx,
+                                 int64_t n_send, double* __restrict__ send) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_send; i += stride)
+    send[i] = vec[idx[i]];
+}
+
 // deterministic pseudo-random fill in (-1, 1) for spis_bench_kernel
 __global__ void fill_kernel(double* __restrict__ p, int64_t n, uint64_t seed) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;

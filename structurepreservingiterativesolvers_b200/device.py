@@ -178,7 +178,8 @@ class KrylovContext:
         self._check(self._lib.spis_host_pre_put(self._h, j, nat.dptr(z)))
 
     def set_collectives(self, allreduce, halo):
-        """allreduce(device_ptr:int, count:int) and halo(device_vec_ptr:int) are Python callables."""
+        """allreduce(device_ptr:int, count:int) sums a device buffer over all ranks in place;
+        halo(send_ptr:int, recv_ptr:int) exchanges the packed ghost entries (see spis_b200.h)."""
         self._live()
 
         def _ar(_user, ptr, count):
@@ -190,9 +191,9 @@ class KrylovContext:
                 traceback.print_exc()
                 return 1
 
-        def _halo(_user, ptr):
+        def _halo(_user, send_ptr, recv_ptr):
             try:
-                halo(ptr)
+                halo(send_ptr, recv_ptr)
                 return 0
             except Exception:  # pragma: no cover
                 import traceback
@@ -203,6 +204,11 @@ class KrylovContext:
               nat.HALO_FN(_halo) if halo else nat.HALO_FN())
         self._callbacks = cb
         self._check(self._lib.spis_set_collectives(self._h, cb[0], cb[1], None))
+
+    def halo_set_plan(self, send_idx):
+        self._live()
+        send_idx = np.ascontiguousarray(send_idx, dtype=np.int32)
+        self._check(self._lib.spis_halo_set_plan(self._h, nat.iptr(send_idx), send_idx.size))
 
     def sync(self):
         self._live()

@@ -177,13 +177,13 @@ class DeviceSession:
         ctx.set_option("profile", 1 if _opt("profile", profile) else 0)
         if not (sps.issparse(A) or isinstance(A, np.ndarray)):
             raise TypeError("A must be a scipy.sparse matrix (or a dense array); got %r" % type(A))
-        if A.shape != (n, n):
-            raise ValueError(f"A has shape {A.shape}, expected {(n, n)}")
+        if A.shape[0] != n or A.shape[1] != n + getattr(ctx, "n_halo", 0):
+            raise ValueError(f"A has shape {A.shape}, expected {(n, n + getattr(ctx, 'n_halo', 0))}")
         ctx.upload_matrix(nat.SLOT_A, A)
         tr("upload A")
         ctx.upload_vec(nat.VEC_B, b)
         ctx.upload_vec(nat.VEC_X0, self.x0_host)
-        ctx.set_option("x0_is_zero", 0 if nat.any_nonzero(self.x0_host) else 1)
+        ctx.set_option("x0_is_zero", 0 if self._any_rank(nat.any_nonzero(self.x0_host)) else 1)
         tr("upload b, x0")
         self._host_pre = None
         self._setup_precond(pre)
@@ -193,6 +193,11 @@ class DeviceSession:
         tr("constraints")
         self._Zhost = None
         self._Zrows = 0
+
+    def _any_rank(self, flag):
+        """Logical OR of a host-side decision over all ranks (identity on one GPU).  Every decision
+        that changes the sequence of device reductions must be taken identically on all ranks."""
+        return bool(flag)
 
     # -- preconditioner: solvers.py:149-161 ------------------------------------------------------
     def _setup_precond(self, pre):
@@ -239,16 +244,16 @@ class DeviceSession:
                 try:
                     M, v, c = const.M, const.v, const.c
                     if sps.issparse(M):
-                        M_zero = M.nnz == 0 or not nat.any_nonzero(M.data)
+                        M_zero = not self._any_rank(M.nnz != 0 and nat.any_nonzero(M.data))
                     else:
                         M = np.asarray(M, dtype=np.float64)
-                        M_zero = not M.any()
+                        M_zero = not self._any_rank(M.any())
                     slot = -1
                     if not M_zero:
                         slot = nat.SLOT_CON0 + idx
                         self.ctx.upload_matrix(slot, M)
                     v = nat.as_f64(v, self.n)
-                    self.ctx.constraint_define(idx, slot, v if nat.any_nonzero(v) else None, float(c))
+                    self.ctx.constraint_define(idx, slot, v if self._any_rank(nat.any_nonzero(v)) else None, float(c))
                 except nat.NativeLibraryError:
                     raise
                 except Exception as exc:                    # surfaces where the reference builds containers

@@ -14,7 +14,10 @@ from structurepreservingiterativesolvers_b200 import _native as nat
 
 class FakeKrylovContext:
     def __init__(self, n, k_max, device=0, n_halo=0, stream=None):
-        self.n, self.k_max = n, k_max
+        self.n, self.k_max, self.n_halo = n, k_max, n_halo
+        self.nt = n + n_halo              # vectors carry their ghost entries at [n, n + n_halo)
+        self.send_idx = np.zeros(0, dtype=np.int64)
+        self.halo_cb = None
         self.generation = 0
         self.closed = False
         self.opts = {"orth": nat.ORTH_CGS2}
@@ -23,8 +26,8 @@ class FakeKrylovContext:
         self.pre_kind = nat.PRE_NONE
         self.blocks = None
         self.cons = {}
-        self.V = np.zeros((k_max + 1, n))
-        self.Zs = np.zeros((k_max, n))
+        self.V = np.zeros((k_max + 1, self.nt))
+        self.Zs = np.zeros((k_max, self.nt))
         self.log = []
         self._pending = None
         self.allreduce = None
@@ -60,6 +63,28 @@ class FakeKrylovContext:
     def sync(self):
         pass
 
+    def set_collectives(self, allreduce, halo):
+        self.allreduce, self.halo_cb = allreduce, halo
+
+    def halo_set_plan(self, send_idx):
+        self.send_idx = np.asarray(send_idx, dtype=np.int64)
+
+    def _ar(self, arr):
+        """all-reduce (sum over ranks) of a small array, in place"""
+        arr = np.ascontiguousarray(np.atleast_1d(arr), dtype=float)
+        if self.allreduce is not None:
+            self.allreduce(arr, arr.size)
+        return arr
+
+    def _spmv(self, slot, vec):
+        """vec has nt entries; refresh its ghosts, multiply"""
+        if self.halo_cb is not None and (self.n_halo or self.send_idx.size):
+            send = np.ascontiguousarray(vec[self.send_idx])
+            recv = np.zeros(self.n_halo)
+            self.halo_cb(send, recv)
+            vec[self.n:] = recv
+        return self.mats[slot] @ vec[: self.mats[slot].shape[1]]
+
     # ---- Krylov
     def _Z(self):
         return self.V if self.pre_kind == nat.PRE_NONE else self.Zs
@@ -79,17 +104,20 @@ class FakeKrylovContext:
         raise AssertionError
 
     def solve_begin(self):
-        A, b, x0 = self.mats[nat.SLOT_A], self.vecs[nat.VEC_B], self.vecs[nat.VEC_X0]
-        self.r0 = b - A @ x0
-        beta = np.sqrt(self.r0 @ self.r0)
+        n = self.n
+        b = self.vecs[nat.VEC_B]
+        self.x0 = np.zeros(self.nt); self.x0[:n] = self.vecs[nat.VEC_X0]
+        self.r0 = b - self._spmv(nat.SLOT_A, self.x0)
+        beta = np.sqrt(self._ar(self.r0 @ self.r0)[0])
         self.V[:] = 0
-        self.V[0] = self.r0 / beta
+        self.V[0, :n] = self.r0 / beta
         self.generation += 1
         for c in self.cons.values():
             c["done"] = 0
             c["T1"] = np.zeros(self.k_max)
             c["T2"] = np.zeros((self.k_max, self.k_max))
             c["MZ"] = np.zeros((self.k_max, self.n))
+            c["t0"] = None
         self.log.append(("begin",))
         return float(beta)
 
@@ -97,28 +125,29 @@ class FakeKrylovContext:
         assert self._pending is None
         self.log.append(("launch", j))
         m = j + 1
+        n = self.n
         if self.pre_kind not in (nat.PRE_NONE, nat.PRE_HOST):
-            self.Zs[j] = self._apply_pre(self.V[j])
-        w = self.mats[nat.SLOT_A] @ self._Z()[j]
-        Vm = self.V[:m]
+            self.Zs[j, :n] = self._apply_pre(self.V[j, :n])
+        w = self._spmv(nat.SLOT_A, self._Z()[j])
+        Vm = self.V[:m, :n]
         orth = self.opts.get("orth", nat.ORTH_CGS2)
         if orth == nat.ORTH_MGS:
             h = np.zeros(m)
             for i in range(m):
-                h[i] = Vm[i] @ w
+                h[i] = self._ar(Vm[i] @ w)[0]
                 w = w - h[i] * Vm[i]
         else:
-            h = Vm @ w
+            h = self._ar(Vm @ w)
             w = w - Vm.T @ h
             if orth == nat.ORTH_CGS2:
-                h2 = Vm @ w
+                h2 = self._ar(Vm @ w)
                 w = w - Vm.T @ h2
                 h = h + h2
-        nrm = np.sqrt(w @ w)
+        nrm = np.sqrt(self._ar(w @ w)[0])
         if nrm != 0:
-            self.V[j + 1] = w / nrm
+            self.V[j + 1, :n] = w / nrm
         else:
-            self.V[j + 1] = w
+            self.V[j + 1, :n] = w
         self._pending = (j, np.concatenate([h, [nrm]]))
 
     def arnoldi_wait(self, j):
@@ -134,13 +163,15 @@ class FakeKrylovContext:
 
     def form_iterate(self, y):
         y = np.asarray(y, dtype=float)
-        self.X = self.vecs[nat.VEC_X0] + self._Z()[: y.size].T @ y
+        self.Xfull = np.zeros(self.nt)
+        self.Xfull[: self.n] = self.vecs[nat.VEC_X0] + self._Z()[: y.size, : self.n].T @ y
+        self.X = self.Xfull[: self.n]
 
     def iterate_residual(self, y):
         self.form_iterate(y)
         self.log.append(("iterate", len(y)))
-        r = self.mats[nat.SLOT_A] @ self.X - self.vecs[nat.VEC_B]
-        return float(np.sqrt(r @ r))
+        r = self._spmv(nat.SLOT_A, self.Xfull) - self.vecs[nat.VEC_B]
+        return float(np.sqrt(self._ar(r @ r)[0]))
 
     # ---- constraints
     def constraint_define(self, c, slot, v, cc):
@@ -150,23 +181,50 @@ class FakeKrylovContext:
 
     def constraint_terms(self, c, m):
         C = self.cons[c]
+        n = self.n
         x0 = self.vecs[nat.VEC_X0]
+        x0nz = not self.opts.get("x0_is_zero", 0)
         Z = self._Z()
-        M = self.mats[C["slot"]] if C["slot"] >= 0 else None
-        t0 = C["c"]
-        if M is not None:
-            t0 += 0.5 * x0 @ (M @ x0)
-        if C["v"] is not None:
-            t0 += C["v"] @ x0
+        slot = C["slot"]
+        hasM = slot >= 0
+        if C.get("t0") is None:
+            t0 = C["c"]
+            if x0nz and (hasM or C["v"] is not None):
+                parts = []
+                if hasM:
+                    parts.append(x0 @ self._spmv(slot, self.x0))
+                if C["v"] is not None:
+                    parts.append(C["v"] @ x0)
+                parts = self._ar(np.array(parts))
+                i = 0
+                if hasM:
+                    t0 += 0.5 * parts[i]; i += 1
+                if C["v"] is not None:
+                    t0 += parts[i]
+            C["t0"] = t0
+        t0 = C["t0"]
         for col in range(C["done"], m):
             t1 = 0.0
-            if M is not None:
-                C["MZ"][col] = M @ Z[col]
-                C["T2"][: col + 1, col] = 0.5 * (Z[: col + 1] @ C["MZ"][col])
-                C["T2"][col, :col] = 0.5 * (C["MZ"][:col] @ Z[col])
-                t1 += x0 @ C["MZ"][col]
-            if C["v"] is not None:
-                t1 += C["v"] @ Z[col]
+            if hasM:
+                # ghosts of z_col were filled when the Arnoldi step multiplied it by A
+                C["MZ"][col] = self.mats[slot] @ Z[col][: self.mats[slot].shape[1]]
+                a = [Z[i, :n] @ C["MZ"][col] for i in range(col + 1)]
+                if x0nz:
+                    a.append(x0 @ C["MZ"][col])
+                a = self._ar(np.array(a))
+                C["T2"][: col + 1, col] = 0.5 * a[: col + 1]
+                if x0nz:
+                    t1 += a[col + 1]
+                if col > 0 or C["v"] is not None:
+                    bb = [C["MZ"][i] @ Z[col, :n] for i in range(col)]
+                    if C["v"] is not None:
+                        bb.append(C["v"] @ Z[col, :n])
+                    bb = self._ar(np.array(bb))
+                    C["T2"][col, :col] = 0.5 * bb[:col]
+                    if C["v"] is not None:
+                        t1 += bb[col]
+            elif C["v"] is not None:
+                t1 += self._ar(C["v"] @ Z[col, :n])[0]
             C["T1"][col] = t1
         C["done"] = max(C["done"], m)
         self.log.append(("terms", c, m))
@@ -179,19 +237,19 @@ class FakeKrylovContext:
         if which == nat.VEC_X:
             return self.X.copy()
         if which == nat.VEC_Q:
-            return self.V[j].copy()
+            return self.V[j, : self.n].copy()
         if which == nat.VEC_Z:
-            return self._Z()[j].copy()
+            return self._Z()[j, : self.n].copy()
         raise KeyError(which)
 
     def download_Z(self, j0, j1):
-        return self._Z()[j0:j1].copy()
+        return self._Z()[j0:j1, : self.n].copy()
 
     def host_pre_get(self, j):
-        return self.V[j].copy()
+        return self.V[j, : self.n].copy()
 
     def host_pre_put(self, j, z):
-        self.Zs[j] = z
+        self.Zs[j, : self.n] = z
 
     def profile(self):
         return {}

@@ -1,0 +1,73 @@
+#!/usr/bin/env python
+"""Multi-GPU parity check (torchrun, NCCL): row-sharded CGMRES vs the single-GPU solve.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        tools/dist_gpu_check.py [n_target]
+"""
+import os
+import sys
+import time
+import warnings
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from structurepreservingiterativesolvers_b200 import solvers, wrappers  # noqa: E402
+from structurepreservingiterativesolvers_b200.distributed import DistributedSession, TorchComm, cgmres_distributed  # noqa: E402
+from structurepreservingiterativesolvers_b200.partition import FieldBlockPartition  # noqa: E402
+from structurepreservingiterativesolvers_b200.problems import lkdv  # noqa: E402
+
+
+class Inv:
+    def __init__(self, M, v, c):
+        self.M, self.v, self.c = M, v, c
+
+
+def main():
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    comm = TorchComm(device=local)
+    rank, world = comm.rank, comm.world
+    warnings.simplefilter("ignore")
+    n_target = int(sys.argv[1]) if len(sys.argv) > 1 else 300_000
+    M = lkdv.benchmark_size(n_target)
+    d, _ = lkdv.linforms(space="CG", M=M, mlength=0.8 * M)
+    n = d["b"].size
+    x0 = np.zeros(n)
+    cl = wrappers.lkdv.conlist(d, x0)
+    tol = 1e-6 * np.sqrt(n / 150)
+    part = FieldBlockPartition(3, M, world)
+    ids = part.global_ids(rank)
+    cl_loc = [Inv(c.M.tocsr()[ids], np.asarray(c.v).reshape(-1)[ids], c.c) for c in cl]
+    sess = DistributedSession(d["A"][ids], d["b"][ids], x0[ids], 50, part, comm, conlist=cl_loc, profile=True)
+    for rep in range(3):
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        x_loc, info = cgmres_distributed(None, d["b"][ids], x0[ids], 50, part, comm, tol=tol, contol=10, conlist=cl_loc,
+                                         small_solver="kkt", timing=True, session=sess)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    xg = sess.gather(x_loc)
+    ok = True
+    if rank == 0:
+        xs, infos = solvers.cgmres(d["A"], d["b"], x0, 50, tol=tol, contol=10, conlist=cl, small_solver="kkt", timing=True, device=local)
+        rel = np.linalg.norm(xg - xs) / np.linalg.norm(xs)
+        inv = lkdv.compute_invariants(d, xg)
+        dev = max(abs(inv["mass"] - d["m0"]) / abs(d["m0"]), abs(inv["energy"] - d["e0"]) / max(abs(d["e0"]), abs(d["mo0"])))
+        ok = (info["steps"] == infos["steps"]) and rel <= 1e-10 and dev <= 1e-11
+        print(f"world={world} n={n} steps={info['steps']} (single {infos['steps']}) rel.diff={rel:.2e} invariant dev={dev:.2e} "
+              f"solve={dt*1e3:.1f} ms collectives={comm.counts} halo={sess.plan.n_halo} -> {'OK' if ok else 'FAIL'}", flush=True)
+        prof = sess.ctx.profile()
+        print({k: (round(v['ms'], 2), v['launches']) for k, v in prof.items() if v['launches']}, flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
