@@ -171,6 +171,19 @@ typedef int (*spis_allreduce_fn)(void* user, void* device_ptr, int64_t count);
 typedef int (*spis_halo_fn)(void* user, void* send_device_ptr, void* recv_device_ptr);
 int spis_set_collectives(spis_ctx* ctx, spis_allreduce_fn allreduce, spis_halo_fn halo, void* user);
 int spis_halo_set_plan(spis_ctx* ctx, const int32_t* send_idx, int64_t n_send);
+/* NVLink peer-memory communicator (one process per GPU on one node).  Each rank creates a comm
+ * buffer and exports it as a CUDA IPC handle (64 bytes); the host language all-gathers the
+ * handles and hands the concatenation (world x 64 bytes, rank order) to spis_xcomm_connect.
+ * From then on the all-reduces are FUSED into the tail of the producing kernels (the last CTA
+ * stores its partial sums into every peer, flags, waits, sums in rank order) and the halo
+ * exchange is a push kernel writing straight into the neighbours' buffers: no callbacks, no NCCL
+ * launches on the hot path.  spis_xcomm_set_halo gives, for each entry of the send plan, the
+ * destination rank and its position in that rank's ghost ordering, plus 0/1 masks of the ranks
+ * this rank sends to / receives from.                                                        */
+int spis_xcomm_create(spis_ctx* ctx, int rank, int world, int64_t halo_cap, void* handle_out, int64_t handle_capacity);
+int spis_xcomm_connect(spis_ctx* ctx, const void* handles);
+int spis_xcomm_set_halo(spis_ctx* ctx, const int32_t* dest_rank, const int32_t* dest_off,
+                        const int32_t* send_to, const int32_t* recv_from);
 int spis_sync(spis_ctx* ctx);
 
 /* ---- measurement --------------------------------------------------------------------- */

@@ -64,6 +64,9 @@ SIGNATURES = {
     "spis_host_pre_put": (C.c_int, [_ctx, C.c_int, _dp]),
     "spis_set_collectives": (C.c_int, [_ctx, ALLREDUCE_FN, HALO_FN, C.c_void_p]),
     "spis_halo_set_plan": (C.c_int, [_ctx, _ip, C.c_int64]),
+    "spis_xcomm_create": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int64]),
+    "spis_xcomm_connect": (C.c_int, [_ctx, C.c_void_p]),
+    "spis_xcomm_set_halo": (C.c_int, [_ctx, _ip, _ip, _ip, _ip]),
     "spis_sync": (C.c_int, [_ctx]),
     "spis_get_profile": (C.c_int, [_ctx, _dp, _dp, _lp]),
     "spis_reset_profile": (C.c_int, [_ctx]),

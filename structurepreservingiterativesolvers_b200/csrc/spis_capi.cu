@@ -93,6 +93,13 @@ struct spis_ctx {
   // collectives
   spis_allreduce_fn allreduce = nullptr; spis_halo_fn halo = nullptr; void* cuser = nullptr;
   int32_t* d_send_idx = nullptr; double* d_send = nullptr; int64_t n_send = 0;
+  bool defer_allreduce = false;   // constraint stage: one all-reduce for a whole batch of dot blocks
+  // NVLink peer-memory collectives (spis_xcomm_*)
+  bool xactive = false;
+  double* xbuf = nullptr; void* xpeer[kMaxRanks] = {nullptr};
+  XView xv;
+  unsigned long long xseq = 1, hseq = 1;
+  int32_t *d_dest_rank = nullptr, *d_dest_off = nullptr, *d_send_to = nullptr, *d_recv_from = nullptr;
   // profiling
   std::vector<ProfRec> recs; std::vector<cudaEvent_t> evpool;
   double prof_ms[SPIS_PROF_CLASSES] = {0}; double prof_bytes[SPIS_PROF_CLASSES] = {0}; int64_t prof_launch[SPIS_PROF_CLASSES] = {0};
@@ -196,13 +203,44 @@ int grid_for(spis_ctx* ctx, int64_t work_items, int per_sm) {
   return (int)(g < 1 ? 1 : g);
 }
 
-int do_allreduce(spis_ctx* ctx, double* dev, int64_t count) {
-  if (!ctx->allreduce) return SPIS_OK;
+// view + sequence number handed to a reducing kernel: cross-GPU part fused into its tail unless the
+// reduction is being batched (constraint stage)
+inline XView fused_view(spis_ctx* ctx) { return (ctx->xactive && !ctx->defer_allreduce) ? ctx->xv : XView(); }
+inline unsigned long long fused_seq(spis_ctx* ctx) {
+  if (ctx->xactive && !ctx->defer_allreduce) return ctx->xseq++;
+  return 0;
+}
+
+int do_allreduce(spis_ctx* ctx, double* dev, int64_t count, bool force = false) {
+  if (ctx->xactive) {
+    if (!force) return SPIS_OK;                    // already reduced inside the producing kernel
+    const unsigned long long chunks = (unsigned long long)((count + ctx->xv.red_cap - 1) / ctx->xv.red_cap);
+    xreduce_kernel<<<1, kThreads, 0, ctx->stream>>>(dev, count, ctx->xv, ctx->xseq);
+    CU(cudaGetLastError());
+    ctx->xseq += chunks;
+    ctx->prof_launch[SPIS_PROF_OTHER] += 1;
+    return SPIS_OK;
+  }
+  if (!ctx->allreduce || (ctx->defer_allreduce && !force)) return SPIS_OK;
   int r = ctx->allreduce(ctx->cuser, dev, count);
   if (r != 0) return fail(ctx, SPIS_E_INVALID, "allreduce callback failed (%d)", r);
   return SPIS_OK;
 }
 int do_halo(spis_ctx* ctx, double* vec) {
+  if (ctx->xactive) {
+    if (ctx->n_halo == 0 && ctx->n_send == 0) return SPIS_OK;
+    const unsigned long long seq = ctx->hseq++;
+    if (ctx->n_send > 0) {
+      const int64_t g = (ctx->n_send + 255) / 256;
+      const int grid = (int)(g < (int64_t)ctx->nsm * 8 ? g : (int64_t)ctx->nsm * 8);
+      halo_push_kernel<<<grid, 256, 0, ctx->stream>>>(vec, ctx->d_send_idx, ctx->d_dest_rank, ctx->d_dest_off, ctx->n_send, ctx->xv, seq);
+      CU(cudaGetLastError());
+    }
+    halo_pull_kernel<<<1, 1024, 0, ctx->stream>>>(vec + ctx->hoff, ctx->n_halo, ctx->d_send_to, ctx->d_recv_from, ctx->xv, seq);
+    CU(cudaGetLastError());
+    ctx->prof_launch[SPIS_PROF_OTHER] += 2;
+    return SPIS_OK;
+  }
   if (!ctx->halo || (ctx->n_halo == 0 && ctx->n_send == 0)) return SPIS_OK;
   if (ctx->n_send > 0) {
     const int grid = (int)((ctx->n_send + 255) / 256 < (int64_t)ctx->nsm * 8 ? (ctx->n_send + 255) / 256 : (int64_t)ctx->nsm * 8);
@@ -228,12 +266,14 @@ int launch_mdot(spis_ctx* ctx, const double* V, int m, const double* extra, int 
   const int grid = grid_for(ctx, ntiles, per_sm);
   const size_t smem = (size_t)(kWarps * nrows + kWarps * 32) * sizeof(double);
   TRY(prof_begin(ctx, SPIS_PROF_MDOT, (double)(m + (extra ? 1 : 0) + 1) * 8.0 * (double)ctx->n));
+  const XView xv = fused_view(ctx);
+  const unsigned long long seq = fused_seq(ctx);
   if (variant == 8)
-    mdot_kernel<8><<<grid, kThreads, smem, ctx->stream>>>(V, ctx->ld, m, extra, with_sumsq, w, ctx->n, ctx->d_partial, ctx->pstride, ctx->d_counter, out);
+    mdot_kernel<8><<<grid, kThreads, smem, ctx->stream>>>(V, ctx->ld, m, extra, with_sumsq, w, ctx->n, ctx->d_partial, ctx->pstride, ctx->d_counter, out, xv, seq);
   else if (variant == 2)
-    mdot_kernel<2><<<grid, kThreads, smem, ctx->stream>>>(V, ctx->ld, m, extra, with_sumsq, w, ctx->n, ctx->d_partial, ctx->pstride, ctx->d_counter, out);
+    mdot_kernel<2><<<grid, kThreads, smem, ctx->stream>>>(V, ctx->ld, m, extra, with_sumsq, w, ctx->n, ctx->d_partial, ctx->pstride, ctx->d_counter, out, xv, seq);
   else
-    mdot_kernel<4><<<grid, kThreads, smem, ctx->stream>>>(V, ctx->ld, m, extra, with_sumsq, w, ctx->n, ctx->d_partial, ctx->pstride, ctx->d_counter, out);
+    mdot_kernel<4><<<grid, kThreads, smem, ctx->stream>>>(V, ctx->ld, m, extra, with_sumsq, w, ctx->n, ctx->d_partial, ctx->pstride, ctx->d_counter, out, xv, seq);
   CU(cudaGetLastError());
   TRY(prof_end(ctx));
   return do_allreduce(ctx, out, nrows);
@@ -245,12 +285,14 @@ int launch_lincomb(spis_ctx* ctx, const double* V, int m, const double* coef, co
   const int grid = grid_for(ctx, ntiles, ctx->ctas_per_sm);
   const size_t smem = (size_t)(m + 2 + kWarps * 32) * sizeof(double);
   TRY(prof_begin(ctx, SPIS_PROF_LINCOMB, (double)(m + (base ? 1 : 0) + 1) * 8.0 * (double)ctx->n));
+  const XView xv = with_sumsq ? fused_view(ctx) : XView();
+  const unsigned long long seq = with_sumsq ? fused_seq(ctx) : 0;
   if (ctx->lincomb_variant == 8)
-    lincomb_kernel<8><<<grid, kThreads, smem, ctx->stream>>>(V, ctx->ld, m, coef, coef2, sign, base, out, ctx->n, with_sumsq, ctx->d_partial, ctx->d_counter, sumsq_out);
+    lincomb_kernel<8><<<grid, kThreads, smem, ctx->stream>>>(V, ctx->ld, m, coef, coef2, sign, base, out, ctx->n, with_sumsq, ctx->d_partial, ctx->d_counter, sumsq_out, xv, seq);
   else if (ctx->lincomb_variant == 2)
-    lincomb_kernel<2><<<grid, kThreads, smem, ctx->stream>>>(V, ctx->ld, m, coef, coef2, sign, base, out, ctx->n, with_sumsq, ctx->d_partial, ctx->d_counter, sumsq_out);
+    lincomb_kernel<2><<<grid, kThreads, smem, ctx->stream>>>(V, ctx->ld, m, coef, coef2, sign, base, out, ctx->n, with_sumsq, ctx->d_partial, ctx->d_counter, sumsq_out, xv, seq);
   else
-    lincomb_kernel<4><<<grid, kThreads, smem, ctx->stream>>>(V, ctx->ld, m, coef, coef2, sign, base, out, ctx->n, with_sumsq, ctx->d_partial, ctx->d_counter, sumsq_out);
+    lincomb_kernel<4><<<grid, kThreads, smem, ctx->stream>>>(V, ctx->ld, m, coef, coef2, sign, base, out, ctx->n, with_sumsq, ctx->d_partial, ctx->d_counter, sumsq_out, xv, seq);
   CU(cudaGetLastError());
   TRY(prof_end(ctx));
   if (with_sumsq) return do_allreduce(ctx, sumsq_out, 1);
@@ -259,15 +301,17 @@ int launch_lincomb(spis_ctx* ctx, const double* V, int m, const double* coef, co
 
 template <int MODE>
 int launch_spmv_mode(spis_ctx* ctx, const Matrix& M, const double* x, const double* b, double* y, double* sumsq_out) {
+  const XView xv = MODE != 0 ? fused_view(ctx) : XView();
+  const unsigned long long seq = MODE != 0 ? fused_seq(ctx) : 0;
   if (M.fmt == SPIS_FMT_SELL) {
     const int64_t nslices = (M.nrows + 31) / 32;
     const int grid = grid_for(ctx, (nslices + kWarps - 1) / kWarps, ctx->spmv_ctas_per_sm);
-    spmv_sell_kernel<MODE><<<grid, kThreads, 0, ctx->stream>>>(M.slice_off, M.scols, M.svals, M.nrows, x, b, y, ctx->d_partial, ctx->d_counter, sumsq_out);
+    spmv_sell_kernel<MODE><<<grid, kThreads, 0, ctx->stream>>>(M.slice_off, M.scols, M.svals, M.nrows, x, b, y, ctx->d_partial, ctx->d_counter, sumsq_out, xv, seq);
   } else {
     const int T = M.csr_lanes;
     const int64_t nblocks = (M.nrows + (kThreads / T) - 1) / (kThreads / T);
     const int grid = grid_for(ctx, nblocks, ctx->spmv_ctas_per_sm);
-#define SPIS_CSR_CASE(TT) case TT: spmv_csr_kernel<TT, MODE><<<grid, kThreads, 0, ctx->stream>>>(M.indptr, M.cols, M.vals, M.nrows, x, b, y, ctx->d_partial, ctx->d_counter, sumsq_out); break;
+#define SPIS_CSR_CASE(TT) case TT: spmv_csr_kernel<TT, MODE><<<grid, kThreads, 0, ctx->stream>>>(M.indptr, M.cols, M.vals, M.nrows, x, b, y, ctx->d_partial, ctx->d_counter, sumsq_out, xv, seq); break;
     switch (T) { SPIS_CSR_CASE(2) SPIS_CSR_CASE(4) SPIS_CSR_CASE(8) SPIS_CSR_CASE(16) default: SPIS_CSR_CASE(32) }
 #undef SPIS_CSR_CASE
   }
@@ -524,9 +568,13 @@ int spis_ctx_destroy(spis_ctx* ctx) {
     dfree(ctx, ctx->V); dfree(ctx, ctx->Z); dfree(ctx, ctx->W); dfree(ctx, ctx->T); dfree(ctx, ctx->R0);
     dfree(ctx, ctx->B); dfree(ctx, ctx->X0); dfree(ctx, ctx->X); dfree(ctx, ctx->pre_diag); dfree(ctx, ctx->pre_blocks);
     dfree(ctx, ctx->d_send_idx); dfree(ctx, ctx->d_send);
+    dfree(ctx, ctx->d_dest_rank); dfree(ctx, ctx->d_dest_off); dfree(ctx, ctx->d_send_to); dfree(ctx, ctx->d_recv_from);
     dfree(ctx, ctx->d_small); dfree(ctx, ctx->d_y); dfree(ctx, ctx->d_cout); dfree(ctx, ctx->d_partial); dfree(ctx, ctx->d_counter);
     cudaStreamSynchronize(ctx->stream);
   }
+  for (int r = 0; r < kMaxRanks; ++r)
+    if (ctx->xpeer[r]) cudaIpcCloseMemHandle(ctx->xpeer[r]);
+  if (ctx->xbuf) cudaFree(ctx->xbuf);
   spis_pinned_free(ctx->h_small); spis_pinned_free(ctx->h_y); spis_pinned_free(ctx->h_cout);
   if (ctx->ev_arnoldi) cudaEventDestroy(ctx->ev_arnoldi);
   if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
@@ -748,6 +796,8 @@ int spis_arnoldi_launch(spis_ctx* ctx, int j) {
   TRY(launch_scale(ctx, qn, scal, fuse ? ctx->pre_diag : nullptr, fuse ? ctx->Z + (size_t)(j + 1) * ld : nullptr));
   ctx->z_ready_index = fuse ? j + 1 : -1;
   CU(cudaMemcpyAsync(ctx->h_small, ctx->d_small, ((size_t)2 * ctx->K + 8) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (ctx->xactive)   // peer-timeout word of the NVLink collectives rides along (slot scal[7] is unused)
+    CU(cudaMemcpyAsync(ctx->h_small + 2 * ctx->K + 7, ctx->xbuf + ctx->xv.flags_off() + 4 * ctx->xv.world, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaEventRecord(ctx->ev_arnoldi, ctx->stream));
   ctx->arnoldi_inflight = j;
   return SPIS_OK;
@@ -758,6 +808,10 @@ int spis_arnoldi_wait(spis_ctx* ctx, int j, double* hcol_out) {
   REQUIRE(hcol_out, "hcol_out is null");
   REQUIRE(ctx->arnoldi_inflight == j, "Arnoldi step %d was not launched (in flight: %d)", j, ctx->arnoldi_inflight);
   CU(cudaEventSynchronize(ctx->ev_arnoldi));
+  if (ctx->xactive) {
+    unsigned long long w; memcpy(&w, ctx->h_small + 2 * ctx->K + 7, sizeof(w));
+    if (w >> 63) return fail(ctx, SPIS_E_CUDA, "NVLink collective %llu timed out waiting for a peer rank", w & ~(1ull << 63));
+  }
   const int m = j + 1;
   for (int i = 0; i < m; ++i) hcol_out[i] = ctx->h_small[i] + ctx->h_small[ctx->K + i];
   hcol_out[m] = std::sqrt(ctx->h_small[2 * ctx->K]);
@@ -857,23 +911,33 @@ int spis_constraint_terms(spis_ctx* ctx, int c, int m, double* term0, double* te
     C.term0 = t; C.term0_done = true;
   }
   const int c0 = C.cols_done;
-  for (int col = c0; col < m; ++col) {
+  // rows of the output block that are not written below must not carry stale data into the
+  // batched all-reduce
+  if (m > c0 && ctx->allreduce)
+    CU(cudaMemsetAsync(ctx->d_cout + (size_t)c0 * 2 * K, 0, (size_t)(m - c0) * 2 * K * sizeof(double), ctx->stream));
+  ctx->defer_allreduce = true;
+  int rc_loop = SPIS_OK;
+  for (int col = c0; col < m && rc_loop == SPIS_OK; ++col) {
     double* zc = Zb + (size_t)col * ld;
     double* oA = ctx->d_cout + (size_t)col * 2 * K;
     double* oB = oA + K;
     if (hasM) {
       double* mz = C.MZ + (size_t)col * ld;
       // MZ[:,col] = M z_col   (z_col's ghost entries were filled by the Arnoldi step)    (:33)
-      TRY(launch_spmv(ctx, C.slot, 0, zc, nullptr, mz, nullptr));
+      rc_loop = launch_spmv(ctx, C.slot, 0, zc, nullptr, mz, nullptr);
       // column col of Z^T MZ, and x0.MZ_col                                               (:35-36)
-      TRY(launch_mdot(ctx, Zb, col + 1, x0nz ? ctx->X0 : nullptr, 0, mz, oA));
+      if (rc_loop == SPIS_OK) rc_loop = launch_mdot(ctx, Zb, col + 1, x0nz ? ctx->X0 : nullptr, 0, mz, oA);
       // row col of Z^T MZ (MZ_i.z_col, i<col), and v.z_col
-      if (col > 0 || C.v) TRY(launch_mdot(ctx, C.MZ, col, C.v, 0, zc, oB));
+      if (rc_loop == SPIS_OK && (col > 0 || C.v)) rc_loop = launch_mdot(ctx, C.MZ, col, C.v, 0, zc, oB);
     } else if (C.v) {
-      TRY(launch_mdot(ctx, nullptr, 0, C.v, 0, zc, oB));
+      rc_loop = launch_mdot(ctx, nullptr, 0, C.v, 0, zc, oB);
     }
   }
+  ctx->defer_allreduce = false;
+  if (rc_loop != SPIS_OK) return rc_loop;
   if (m > c0) {
+    // one all-reduce for every dot block of this call (row-sharded runs)
+    TRY(do_allreduce(ctx, ctx->d_cout + (size_t)c0 * 2 * K, (int64_t)(m - c0) * 2 * K, true));
     TRY(d2h(ctx, ctx->h_cout + (size_t)c0 * 2 * K, ctx->d_cout + (size_t)c0 * 2 * K, (size_t)(m - c0) * 2 * K * sizeof(double)));
     const int km = ctx->kmax;
     for (int col = c0; col < m; ++col) {
@@ -961,6 +1025,69 @@ int spis_halo_set_plan(spis_ctx* ctx, const int32_t* send_idx, int64_t n_send) {
     TRY(dalloc(ctx, &ctx->d_send, (size_t)n_send));
     TRY(h2d(ctx, ctx->d_send_idx, send_idx, (size_t)n_send * sizeof(int32_t)));
   }
+  return SPIS_OK;
+}
+
+int spis_xcomm_create(spis_ctx* ctx, int rank, int world, int64_t halo_cap, void* handle_out, int64_t handle_capacity) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world, "bad rank %d / world %d (max %d ranks)", rank, world, kMaxRanks);
+  REQUIRE(handle_out && handle_capacity >= (int64_t)sizeof(cudaIpcMemHandle_t), "handle buffer too small (%zu bytes needed)", sizeof(cudaIpcMemHandle_t));
+  REQUIRE(!ctx->xbuf, "peer-memory communicator already created");
+  REQUIRE(halo_cap >= ctx->n_halo, "halo capacity %lld < n_halo %lld", (long long)halo_cap, (long long)ctx->n_halo);
+  CU(cudaSetDevice(ctx->device));
+  XView xv;
+  xv.world = world; xv.rank = rank;
+  xv.red_cap = ctx->K > 1024 ? ctx->K : 1024;
+  xv.halo_cap = halo_cap > 0 ? roundup(halo_cap, 16) : 16;
+  const size_t bytes = xv.total_doubles() * sizeof(double);
+  CU(cudaMalloc((void**)&ctx->xbuf, bytes));          // plain cudaMalloc: pool memory cannot be exported
+  CU(cudaMemset(ctx->xbuf, 0, bytes));
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, ctx->xbuf));
+  memcpy(handle_out, &h, sizeof(h));
+  ctx->xv = xv;
+  ctx->xv.base[rank] = ctx->xbuf;
+  return SPIS_OK;
+}
+
+int spis_xcomm_connect(spis_ctx* ctx, const void* handles) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(ctx->xbuf && handles, "spis_xcomm_create must come first");
+  CU(cudaSetDevice(ctx->device));
+  const char* hb = static_cast<const char*>(handles);
+  for (int r = 0; r < ctx->xv.world; ++r) {
+    if (r == ctx->xv.rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, hb + (size_t)r * sizeof(h), sizeof(h));
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->xpeer[r] = p;
+    ctx->xv.base[r] = static_cast<double*>(p);
+  }
+  ctx->xactive = ctx->xv.world > 1;
+  ctx->xseq = 1; ctx->hseq = 1;
+  return SPIS_OK;
+}
+
+int spis_xcomm_set_halo(spis_ctx* ctx, const int32_t* dest_rank, const int32_t* dest_off,
+                        const int32_t* send_to, const int32_t* recv_from) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(ctx->xbuf && send_to && recv_from, "spis_xcomm_create must come first");
+  REQUIRE(ctx->n_send == 0 || (dest_rank && dest_off), "null destination arrays");
+  CU(cudaSetDevice(ctx->device));
+  for (int64_t i = 0; i < ctx->n_send; ++i)
+    REQUIRE(dest_rank[i] >= 0 && dest_rank[i] < ctx->xv.world && dest_off[i] >= 0, "bad halo destination at %lld", (long long)i);
+  dfree(ctx, ctx->d_dest_rank); dfree(ctx, ctx->d_dest_off); dfree(ctx, ctx->d_send_to); dfree(ctx, ctx->d_recv_from);
+  if (ctx->n_send) {
+    TRY(dalloc(ctx, &ctx->d_dest_rank, (size_t)ctx->n_send, false));
+    TRY(dalloc(ctx, &ctx->d_dest_off, (size_t)ctx->n_send, false));
+    TRY(h2d(ctx, ctx->d_dest_rank, dest_rank, (size_t)ctx->n_send * sizeof(int32_t)));
+    TRY(h2d(ctx, ctx->d_dest_off, dest_off, (size_t)ctx->n_send * sizeof(int32_t)));
+  }
+  TRY(dalloc(ctx, &ctx->d_send_to, (size_t)kMaxRanks));
+  TRY(dalloc(ctx, &ctx->d_recv_from, (size_t)kMaxRanks));
+  TRY(h2d(ctx, ctx->d_send_to, send_to, (size_t)ctx->xv.world * sizeof(int32_t)));
+  TRY(h2d(ctx, ctx->d_recv_from, recv_from, (size_t)ctx->xv.world * sizeof(int32_t)));
   return SPIS_OK;
 }
 
@@ -1086,7 +1213,8 @@ int spis_bench_kernel(spis_ctx* ctx, int cls, int m, int reps, double* ms_out, d
   CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
   const int saved_profile = ctx->profile;
   spis_allreduce_fn saved_ar = ctx->allreduce; spis_halo_fn saved_halo = ctx->halo;
-  ctx->profile = 0; ctx->allreduce = nullptr; ctx->halo = nullptr;
+  const bool saved_x = ctx->xactive;
+  ctx->profile = 0; ctx->allreduce = nullptr; ctx->halo = nullptr; ctx->xactive = false;
   double bytes0[SPIS_PROF_CLASSES]; for (int i = 0; i < SPIS_PROF_CLASSES; ++i) bytes0[i] = ctx->prof_bytes[i];
   int rc = SPIS_OK;
   for (int rep = -2; rep < reps && rc == SPIS_OK; ++rep) {
@@ -1101,7 +1229,7 @@ int spis_bench_kernel(spis_ctx* ctx, int cls, int m, int reps, double* ms_out, d
     }
   }
   cudaEventRecord(e1, ctx->stream);
-  ctx->profile = saved_profile; ctx->allreduce = saved_ar; ctx->halo = saved_halo;
+  ctx->profile = saved_profile; ctx->allreduce = saved_ar; ctx->halo = saved_halo; ctx->xactive = saved_x;
   if (rc != SPIS_OK) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
   CU(cudaEventSynchronize(e1));
   float ms = 0.f;

@@ -39,12 +39,101 @@ __device__ __forceinline__ double2 ld_keep(const double* p) {
   return __ldg(reinterpret_cast<const double2*>(p));
 }
 
+// ------------------------------------------------------------------------------------------
+// Cross-GPU exchange over NVLink peer memory (row-sharded runs, one process per GPU).
+// Every rank owns one "comm buffer" (plain cudaMalloc, exported with CUDA IPC) that its peers
+// write into directly with st.global over NVLink:
+//     red payload   [2 phases][world sources][red_cap doubles]
+//     halo payload  [2 phases][halo_cap doubles]         (sources write at their ghost offset)
+//     red flags     [2][world] u64,  halo flags [2][world] u64,  error word
+// A collective with sequence number `seq` uses phase seq&1: each rank stores its contribution
+// into slot [phase][my rank] of EVERY peer, fences at system scope, then release-stores `seq`
+// into the peer's flag; it then acquire-spins on its own flags and sums the `world` slots in
+// rank order -- the same order on every rank, so all ranks get bit-identical sums, which keeps
+// the replicated host-side small solves in lock step.  Double buffering is enough: a peer can
+// only start collective seq+2 after it has seen my flag for seq+1, which I store after I have
+// finished reading seq.
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxRanks = 8;
+
+struct XView {
+  int world = 1, rank = 0;
+  int red_cap = 0;               // doubles per reduce slot
+  long long halo_cap = 0;        // doubles per halo phase
+  double* base[kMaxRanks] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  __host__ __device__ size_t red_off(int phase, int src) const { return ((size_t)phase * world + src) * (size_t)red_cap; }
+  __host__ __device__ size_t halo_off(int phase) const { return (size_t)2 * world * red_cap + (size_t)phase * halo_cap; }
+  __host__ __device__ size_t flags_off() const { return (size_t)2 * world * red_cap + (size_t)2 * halo_cap; }
+  __host__ __device__ size_t total_doubles() const { return flags_off() + 4 * (size_t)world + 8; }
+  __device__ unsigned long long* red_flag(int owner, int phase, int src) const {
+    return reinterpret_cast<unsigned long long*>(base[owner] + flags_off()) + phase * world + src;
+  }
+  __device__ unsigned long long* halo_flag(int owner, int phase, int src) const {
+    return reinterpret_cast<unsigned long long*>(base[owner] + flags_off()) + 2 * world + phase * world + src;
+  }
+  __device__ unsigned long long* err_word(int owner) const {
+    return reinterpret_cast<unsigned long long*>(base[owner] + flags_off()) + 4 * world;
+  }
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_volatile(const double* p) {
+  double v;
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// spin until *flag == seq; gives up after ~20 s of SM clock and records the failure
+__device__ __forceinline__ bool wait_flag(const unsigned long long* flag, unsigned long long seq,
+                                          unsigned long long* err) {
+  const long long t0 = clock64();
+  while (ld_acquire_sys(flag) != seq) {
+    if (clock64() - t0 > 40000000000ll) { *err = seq | (1ull << 63); return false; }
+    __nanosleep(64);
+  }
+  return true;
+}
+
+// All-reduce (sum) of buf[0..count) across ranks, executed by ONE CTA; count <= red_cap.
+// Must be called by all threads of the CTA.  On return buf holds the global sums.
+__device__ __forceinline__ void cta_xreduce(double* buf, int count, const XView& xv, unsigned long long seq) {
+  if (xv.world <= 1) return;
+  const int phase = (int)(seq & 1ull);
+  __syncthreads();
+  for (int p = 0; p < xv.world; ++p) {
+    double* dst = xv.base[p] + xv.red_off(phase, xv.rank);
+    for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = buf[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < xv.world) {
+    st_release_sys(xv.red_flag(threadIdx.x, phase, xv.rank), seq);
+    wait_flag(xv.red_flag(xv.rank, phase, threadIdx.x), seq, xv.err_word(xv.rank));
+  }
+  __syncthreads();
+  const double* mine = xv.base[xv.rank];
+  for (int i = threadIdx.x; i < count; i += blockDim.x) {
+    double s = 0.0;
+    for (int r = 0; r < xv.world; ++r) s += ld_volatile(mine + xv.red_off(phase, r) + i);
+    buf[i] = s;
+  }
+  __syncthreads();
+}
+
 // Deterministic cross-CTA reduction tail.  Each CTA has already written its `nout` partial
 // sums to partial[blockIdx.x*pstride + i].  The last CTA to take a ticket sums them in a
 // fixed order (8 warps over contiguous CTA ranges, then warp 0..7 in order) into out[i].
 __device__ __forceinline__ void finish_reduction(double* __restrict__ partial, int pstride, int nout,
-                                                 unsigned* counter, double* __restrict__ out,
-                                                 double* sred /* kWarps*32 doubles */) {
+                                                 unsigned* counter, double* out,
+                                                 double* sred /* kWarps*32 doubles */,
+                                                 const XView& xv, unsigned long long seq) {
   __shared__ unsigned s_ticket;
   __threadfence();
   __syncthreads();
@@ -81,6 +170,8 @@ __device__ __forceinline__ void finish_reduction(double* __restrict__ partial, i
     __syncthreads();
   }
   if (threadIdx.x == 0) *counter = 0u;   // ready for the next launch on this stream
+  // row-sharded runs: the same CTA finishes the job across GPUs over NVLink (fused dot + all-reduce)
+  cta_xreduce(out, nout, xv, seq);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -134,7 +225,8 @@ template <int IU>
 __global__ void __launch_bounds__(kThreads)
 mdot_kernel(const double* __restrict__ V, int64_t ld, int m, const double* __restrict__ extra,
             int with_sumsq, const double* __restrict__ w, int64_t n,
-            double* __restrict__ partial, int pstride, unsigned* counter, double* __restrict__ out) {
+            double* __restrict__ partial, int pstride, unsigned* counter, double* out,
+            XView xv, unsigned long long seq) {
   extern __shared__ double smem[];
   const int nrows = m + (extra ? 1 : 0) + (with_sumsq ? 1 : 0);
   double* sacc = smem;                       // [kWarps][nrows]
@@ -157,7 +249,7 @@ mdot_kernel(const double* __restrict__ V, int64_t ld, int m, const double* __res
     for (int wv = 0; wv < kWarps; ++wv) s += sacc[wv * nrows + i];
     partial[(size_t)blockIdx.x * pstride + i] = s;
   }
-  finish_reduction(partial, pstride, nrows, counter, out, sred);
+  finish_reduction(partial, pstride, nrows, counter, out, sred, xv, seq);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -221,7 +313,8 @@ __global__ void __launch_bounds__(kThreads)
 lincomb_kernel(const double* __restrict__ V, int64_t ld, int m, const double* __restrict__ coef,
                const double* __restrict__ coef2 /* optional, added to coef */, double sign,
                const double* base, double* out, int64_t n, int with_sumsq,
-               double* __restrict__ partial, unsigned* counter, double* __restrict__ sumsq_out) {
+               double* __restrict__ partial, unsigned* counter, double* sumsq_out,
+               XView xv, unsigned long long seq) {
   extern __shared__ double smem[];
   double* sc = smem;                  // [m]
   double* sred = smem + m + (m & 1);  // [kWarps*32]
@@ -248,7 +341,7 @@ lincomb_kernel(const double* __restrict__ V, int64_t ld, int m, const double* __
     partial[blockIdx.x] = s;
   }
   __syncthreads();
-  finish_reduction(partial, 1, 1, counter, sumsq_out, sred);
+  finish_reduction(partial, 1, 1, counter, sumsq_out, sred, xv, seq);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -322,7 +415,8 @@ __global__ void __launch_bounds__(kThreads, 8)   // 32 registers: all 2048 threa
 spmv_sell_kernel(const int64_t* __restrict__ slice_off, const int32_t* __restrict__ cols,
                  const double* __restrict__ vals, int64_t nrows, const double* __restrict__ x,
                  const double* __restrict__ b, double* __restrict__ y,
-                 double* __restrict__ partial, unsigned* counter, double* __restrict__ sumsq_out) {
+                 double* __restrict__ partial, unsigned* counter, double* sumsq_out,
+                 XView xv, unsigned long long seq) {
   __shared__ double sred[kWarps * 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t nslices = (nrows + 31) >> 5;
@@ -374,7 +468,7 @@ spmv_sell_kernel(const int64_t* __restrict__ slice_off, const int32_t* __restric
     partial[blockIdx.x] = s;
   }
   __syncthreads();
-  finish_reduction(partial, 1, 1, counter, sumsq_out, sred);
+  finish_reduction(partial, 1, 1, counter, sumsq_out, sred, xv, seq);
 }
 
 // K1 fallback: CSR "vector" kernel, T lanes per row (T = 2..32), for matrices whose row
@@ -384,7 +478,8 @@ __global__ void __launch_bounds__(kThreads)
 spmv_csr_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ cols,
                 const double* __restrict__ vals, int64_t nrows, const double* __restrict__ x,
                 const double* __restrict__ b, double* __restrict__ y,
-                double* __restrict__ partial, unsigned* counter, double* __restrict__ sumsq_out) {
+                double* __restrict__ partial, unsigned* counter, double* sumsq_out,
+                XView xv, unsigned long long seq) {
   __shared__ double sred[kWarps * 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = threadIdx.x & (T - 1);
@@ -424,7 +519,7 @@ spmv_csr_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
     partial[blockIdx.x] = s;
   }
   __syncthreads();
-  finish_reduction(partial, 1, 1, counter, sumsq_out, sred);
+  finish_reduction(partial, 1, 1, counter, sumsq_out, sred, xv, seq);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -473,6 +568,44 @@ __global__ void sell_fill_kernel(const int32_t* __restrict__ indptr, const int32
     cols[off + (int64_t)k * 32 + lane] = c;
     vals[off + (int64_t)k * 32 + lane] = v;
   }
+}
+
+// stand-alone all-reduce of a device buffer in chunks of red_cap (batched constraint terms)
+__global__ void __launch_bounds__(kThreads)
+xreduce_kernel(double* buf, int64_t count, XView xv, unsigned long long seq0) {
+  unsigned long long seq = seq0;
+  for (int64_t c0 = 0; c0 < count; c0 += xv.red_cap, ++seq) {
+    const int cnt = (int)((count - c0) < xv.red_cap ? (count - c0) : xv.red_cap);
+    cta_xreduce(buf + c0, cnt, xv, seq);
+  }
+}
+
+// halo push: the entries of `vec` my neighbours need go straight into THEIR comm buffers over
+// NVLink (dest_rank[i], dest_off[i] = position in that rank's ghost ordering)
+__global__ void halo_push_kernel(const double* __restrict__ vec, const int32_t* __restrict__ idx,
+                                 const int32_t* __restrict__ dest_rank, const int32_t* __restrict__ dest_off,
+                                 int64_t n_send, XView xv, unsigned long long seq) {
+  const int phase = (int)(seq & 1ull);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_send; i += stride)
+    xv.base[dest_rank[i]][xv.halo_off(phase) + dest_off[i]] = vec[idx[i]];
+  __threadfence_system();
+}
+
+// halo pull (one CTA): tell every destination that my entries have landed (the push kernel has
+// completed), wait for every source, then copy the ghosts next to the owned part of the vector
+__global__ void __launch_bounds__(1024)
+halo_pull_kernel(double* __restrict__ ghost_dst, int64_t n_halo, const int32_t* __restrict__ send_to,
+                 const int32_t* __restrict__ recv_from, XView xv, unsigned long long seq) {
+  const int phase = (int)(seq & 1ull);
+  __threadfence_system();
+  if ((int)threadIdx.x < xv.world) {
+    if (send_to[threadIdx.x]) st_release_sys(xv.halo_flag(threadIdx.x, phase, xv.rank), seq);
+    if (recv_from[threadIdx.x]) wait_flag(xv.halo_flag(xv.rank, phase, threadIdx.x), seq, xv.err_word(xv.rank));
+  }
+  __syncthreads();
+  const double* src = xv.base[xv.rank] + xv.halo_off(phase);
+  for (int64_t i = threadIdx.x; i < n_halo; i += blockDim.x) ghost_dst[i] = ld_volatile(src + i);
 }
 
 // halo pack: send[i] = vec[idx[i]]  (entries of a vector that neighbouring ranks need as ghosts)

@@ -210,6 +210,23 @@ class KrylovContext:
         send_idx = np.ascontiguousarray(send_idx, dtype=np.int32)
         self._check(self._lib.spis_halo_set_plan(self._h, nat.iptr(send_idx), send_idx.size))
 
+    def xcomm_create(self, rank: int, world: int, halo_cap: int) -> bytes:
+        """Allocate this rank's NVLink comm buffer; returns its CUDA IPC handle (64 bytes)."""
+        self._live()
+        buf = C.create_string_buffer(64)
+        self._check(self._lib.spis_xcomm_create(self._h, rank, world, int(halo_cap), buf, 64))
+        return buf.raw
+
+    def xcomm_connect(self, handles: bytes):
+        self._live()
+        self._check(self._lib.spis_xcomm_connect(self._h, C.c_char_p(handles)))
+
+    def xcomm_set_halo(self, dest_rank, dest_off, send_to, recv_from):
+        self._live()
+        a = [np.ascontiguousarray(x, dtype=np.int32) for x in (dest_rank, dest_off, send_to, recv_from)]
+        self._check(self._lib.spis_xcomm_set_halo(self._h, nat.iptr(a[0]) if a[0].size else None,
+                                                  nat.iptr(a[1]) if a[1].size else None, nat.iptr(a[2]), nat.iptr(a[3])))
+
     def sync(self):
         self._live()
         self._check(self._lib.spis_sync(self._h))

@@ -120,6 +120,28 @@ class TorchComm:
         self.dist.all_gather_object(gathered, [np.asarray(r, dtype=np.int64) for r in requests], group=self.group)
         return [gathered[s][self.rank] for s in range(self.world)]
 
+    def setup_peer_memory(self, ctx, plan):
+        """Switch a context to the NVLink peer-memory collectives (spis_xcomm_*): all-reduces fused
+        into the reducing kernels, halo pushed straight into the neighbours' buffers.  Only the
+        one-off exchange of IPC handles and ghost offsets goes through torch.distributed."""
+        handle = ctx.xcomm_create(self.rank, self.world, plan.n_halo)
+        info = [None] * self.world
+        self.dist.all_gather_object(info, (handle, [int(c) for c in plan.recv_counts]), group=self.group)
+        ctx.xcomm_connect(b"".join(h for h, _ in info))
+        dest_rank, dest_off = [], []
+        for peer in range(self.world):
+            cnt = int(plan.send_counts[peer])
+            if cnt:
+                # my entries land after those of lower-ranked sources in the peer's ghost ordering
+                base = sum(info[peer][1][:self.rank])
+                dest_rank.append(np.full(cnt, peer, dtype=np.int32))
+                dest_off.append(base + np.arange(cnt, dtype=np.int32))
+        dest_rank = np.concatenate(dest_rank) if dest_rank else np.zeros(0, dtype=np.int32)
+        dest_off = np.concatenate(dest_off) if dest_off else np.zeros(0, dtype=np.int32)
+        ctx.xcomm_set_halo(dest_rank, dest_off, (plan.send_counts > 0).astype(np.int32),
+                           (plan.recv_counts > 0).astype(np.int32))
+        self.dist.barrier(group=self.group)          # every rank connected before the first collective
+
     def allgather_vec(self, local):
         parts = [None] * self.world
         self.dist.all_gather_object(parts, np.asarray(local), group=self.group)
@@ -136,8 +158,13 @@ class DistributedSession(solvers.DeviceSession):
     """
 
     def __init__(self, A_rows, b_loc, x0_loc, k, part, comm, conlist=(), pre=None, *, orth=None,
-                 spmv_format=None, profile=None, ctx_factory=KrylovContext):
+                 spmv_format=None, profile=None, ctx_factory=KrylovContext, transport="auto"):
+        """transport: 'p2p' = NVLink peer-memory collectives inside the kernels (GPUs on one node),
+        'nccl' = torch.distributed callbacks, 'auto' = p2p on GPUs, callbacks otherwise."""
         self.comm, self.part = comm, part
+        if transport == "auto":
+            transport = "p2p" if (comm.cuda and comm.world > 1 and ctx_factory is KrylovContext) else "nccl"
+        self.transport = transport
         rank = comm.rank
         conlist = list(conlist)
         for c in conlist:
@@ -159,7 +186,10 @@ class DistributedSession(solvers.DeviceSession):
             ctx = ctx_factory(n, kk, device=(comm.device if comm.cuda else 0), n_halo=plan.n_halo,
                               stream=comm.stream_handle())
             ctx.halo_set_plan(plan.send_idx)
-            ctx.set_collectives(comm.allreduce, comm.make_halo(plan))
+            if transport == "p2p":
+                comm.setup_peer_memory(ctx, plan)
+            else:
+                ctx.set_collectives(comm.allreduce, comm.make_halo(plan))
             return ctx
 
         super().__init__(A_loc, b_loc, x0_loc, k, conlist=cons_loc, pre=pre, orth=orth,

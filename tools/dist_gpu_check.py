@@ -44,7 +44,9 @@ def main():
     part = FieldBlockPartition(3, M, world)
     ids = part.global_ids(rank)
     cl_loc = [Inv(c.M.tocsr()[ids], np.asarray(c.v).reshape(-1)[ids], c.c) for c in cl]
-    sess = DistributedSession(d["A"][ids], d["b"][ids], x0[ids], 50, part, comm, conlist=cl_loc, profile=True)
+    transport = sys.argv[2] if len(sys.argv) > 2 else "auto"
+    sess = DistributedSession(d["A"][ids], d["b"][ids], x0[ids], 50, part, comm, conlist=cl_loc, profile=True,
+                              transport=transport)
     for rep in range(3):
         dist.barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -61,7 +63,7 @@ def main():
         dev = max(abs(inv["mass"] - d["m0"]) / abs(d["m0"]), abs(inv["energy"] - d["e0"]) / max(abs(d["e0"]), abs(d["mo0"])))
         ok = (info["steps"] == infos["steps"]) and rel <= 1e-10 and dev <= 1e-11
         print(f"world={world} n={n} steps={info['steps']} (single {infos['steps']}) rel.diff={rel:.2e} invariant dev={dev:.2e} "
-              f"solve={dt*1e3:.1f} ms collectives={comm.counts} halo={sess.plan.n_halo} -> {'OK' if ok else 'FAIL'}", flush=True)
+              f"solve={dt*1e3:.1f} ms transport={sess.transport} collectives={comm.counts} halo={sess.plan.n_halo} -> {'OK' if ok else 'FAIL'}", flush=True)
         prof = sess.ctx.profile()
         print({k: (round(v['ms'], 2), v['launches']) for k, v in prof.items() if v['launches']}, flush=True)
     dist.barrier()
