@@ -471,10 +471,12 @@ def cgmres(A, b, x0, k, tol=1e-8, contol=10, conlist=[], pre=None, timing=None, 
     if timing:
         jit = {"start": time(), "start_iter": [], "end_iter": [],
                "start_constraints": [], "end_constraints": []}
+    tr = _Trace()
     sess = _acquire(session, A, b, x0, k, conlist, pre, device, orth)
     arn = _Arnoldi(sess, k, _opt("lookahead", lookahead))
     safety = None                                         # (solvers.py:163)
     beta = sess.begin()
+    tr("cgmres: session + r0")
     hist = IterateHistory(sess)
     residual = [beta]
     constrained_steps = 0
@@ -536,6 +538,7 @@ def cgmres(A, b, x0, k, tol=1e-8, contol=10, conlist=[], pre=None, timing=None, 
         if residual[-1] < tol and safety is True:         # (solvers.py:296-297)
             break
     arn.drain()
+    tr("cgmres: Krylov loop (%d steps)" % steps)
     if timing:                                            # (solvers.py:300-312)
         jit["end"] = time()
         iter_time = np.asarray(jit["end_iter"]) - np.asarray(jit["start_iter"][: len(jit["end_iter"])])
@@ -555,6 +558,7 @@ def cgmres(A, b, x0, k, tol=1e-8, contol=10, conlist=[], pre=None, timing=None, 
         x_last = sess.ctx.download(nat.VEC_X, pinned=True)
     else:
         x_last = hist[0]
+    tr("cgmres: download x")
     info = {"name": "cgmres",
             "x": _finish_history(hist, _opt("history", history), x_last),
             "res": residual[1:],

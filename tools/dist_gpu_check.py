@@ -57,7 +57,13 @@ def main():
     xg = sess.gather(x_loc)
     ok = True
     if rank == 0:
-        xs, infos = solvers.cgmres(d["A"], d["b"], x0, 50, tol=tol, contol=10, conlist=cl, small_solver="kkt", timing=True, device=local)
+        s1 = solvers.DeviceSession(d["A"], d["b"], x0, 50, conlist=cl, device=local)
+        for _ in range(3):
+            t0 = time.perf_counter()
+            xs, infos = solvers.cgmres(d["A"], d["b"], x0, 50, tol=tol, contol=10, conlist=cl, small_solver="kkt", timing=True, session=s1)
+            t_single = time.perf_counter() - t0
+        print("single-GPU solve %.1f ms, timings %s" % (t_single * 1e3, {k: round(float(v), 5) for k, v in infos["timings"].items()}), flush=True)
+        print("sharded timings %s" % {k: round(float(v), 5) for k, v in info["timings"].items()}, flush=True)
         rel = np.linalg.norm(xg - xs) / np.linalg.norm(xs)
         inv = lkdv.compute_invariants(d, xg)
         dev = max(abs(inv["mass"] - d["m0"]) / abs(d["m0"]), abs(inv["energy"] - d["e0"]) / max(abs(d["e0"]), abs(d["mo0"])))
