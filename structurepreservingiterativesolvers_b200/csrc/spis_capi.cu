@@ -42,7 +42,8 @@ struct Constraint {
   int slot = -1;              // matrix slot, <0: M == 0
   double* v = nullptr;        // device, ld doubles, or null when v == 0
   double cc = 0.0;
-  double* MZ = nullptr;       // device, kmax x ld, lazily allocated
+  double* MZ = nullptr;       // device, kmax x ld, lazily allocated (non-symmetric M only)
+  int symmetric = -1;         // -1 not tested yet, 1: M == M^T to round-off (probabilistic device test)
   int cols_done = 0;
   bool term0_done = false;
   double term0 = 0.0;
@@ -69,8 +70,10 @@ struct spis_ctx {
   int mdot_variant = 0, lincomb_variant = 4;   // mdot 0 = auto (tools/tune.py sweep, profiles/tune_r1.md)
   int x0_is_zero = 0;
   int fuse_jacobi = 1;
+  int force_nonsymmetric = 0;   // tests: take the general (stored M Z) path of the constraint stage
   // vectors
   double *V = nullptr, *Z = nullptr, *W = nullptr, *T = nullptr, *R0 = nullptr, *B = nullptr, *X0 = nullptr, *X = nullptr;
+  double* G = nullptr;          // 4 x ld group buffer of the constraint stage (lazy)
   double* pre_diag = nullptr;
   double* pre_blocks = nullptr; int pre_bs = 0; int64_t pre_nblk = 0, pre_sb = 0, pre_sf = 0;
   int pre_kind = SPIS_PRE_NONE;
@@ -277,6 +280,29 @@ int launch_mdot(spis_ctx* ctx, const double* V, int m, const double* extra, int 
   CU(cudaGetLastError());
   TRY(prof_end(ctx));
   return do_allreduce(ctx, out, nrows);
+}
+
+// out[c*nrows + i] = row_i . W_c  for nw (2 or 4) vectors W_c = W + c*wstride; rows = V[0..m) (+ extra)
+int launch_mdotm(spis_ctx* ctx, int nw, const double* V, int m, const double* extra, const double* W,
+                 int64_t wstride, double* out) {
+  const int nrows = m + (extra ? 1 : 0);
+  if (nrows == 0) return SPIS_OK;
+  const int nout = nw * nrows;
+  REQUIRE(nout <= ctx->pstride, "mdotm: %d outputs exceed workspace %d", nout, ctx->pstride);
+  const int64_t ntiles = (ctx->n + kTile - 1) / kTile;
+  const int grid = grid_for(ctx, ntiles, ctx->ctas_per_sm > 2 ? 2 : ctx->ctas_per_sm);
+  const size_t smem = (size_t)(kWarps * nout + kWarps * 32) * sizeof(double);
+  REQUIRE(smem <= 227 * 1024, "mdotm: %zu bytes of shared memory needed", smem);
+  TRY(prof_begin(ctx, SPIS_PROF_MDOT, (double)(nrows + nw) * 8.0 * (double)ctx->n));
+  const XView xv = fused_view(ctx);
+  const unsigned long long seq = fused_seq(ctx);
+  if (nw == 4)
+    mdotm_kernel<4><<<grid, kThreads, smem, ctx->stream>>>(V, ctx->ld, m, extra, W, wstride, ctx->n, ctx->d_partial, ctx->pstride, ctx->d_counter, out, xv, seq);
+  else
+    mdotm_kernel<2><<<grid, kThreads, smem, ctx->stream>>>(V, ctx->ld, m, extra, W, wstride, ctx->n, ctx->d_partial, ctx->pstride, ctx->d_counter, out, xv, seq);
+  CU(cudaGetLastError());
+  TRY(prof_end(ctx));
+  return do_allreduce(ctx, out, nout);
 }
 
 int launch_lincomb(spis_ctx* ctx, const double* V, int m, const double* coef, const double* coef2,
@@ -512,7 +538,7 @@ int spis_ctx_create(int device, int64_t n, int64_t n_halo, int k_max, void* stre
   c->hoff = roundup(n, 16);
   c->ld = roundup(c->hoff + n_halo, 16);
   c->kmax = k_max; c->K = k_max + 4;
-  c->pstride = c->K;
+  c->pstride = 4 * c->K;        // mdotm_kernel<4> reduces 4 x (m+1) sums per launch
   c->max_grid = c->nsm * 16;
   auto bail = [&](int code) { std::string msg = c->err; spis_ctx_destroy(c); snprintf(g_global_err, sizeof(g_global_err), "%s", msg.c_str()); return code; };
 #define CTRY(call) do { int r_ = (call); if (r_ != SPIS_OK) return bail(r_); } while (0)
@@ -542,7 +568,14 @@ int spis_ctx_create(int device, int64_t n, int64_t n_halo, int k_max, void* stre
     fail(c, SPIS_E_NOMEM, "pinned host allocation failed: %s", g_global_err);
     return bail(SPIS_E_NOMEM);
   }
-  // mdot needs up to (8*(K)+256)*8 bytes of dynamic shared memory
+  // mdot needs up to (8*K+256)*8 bytes of dynamic shared memory, mdotm<4> four times the K part
+  {
+    const int need4 = (kWarps * 4 * c->K + kWarps * 32) * (int)sizeof(double);
+    if (need4 > 48 * 1024 && need4 <= 227 * 1024) {
+      CCU(cudaFuncSetAttribute(mdotm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, need4));
+      CCU(cudaFuncSetAttribute(mdotm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, need4));
+    }
+  }
   const int smem_need = (kWarps * c->K + kWarps * 32) * (int)sizeof(double);
   if (smem_need > 48 * 1024) {
     CCU(cudaFuncSetAttribute(mdot_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_need));
@@ -566,7 +599,7 @@ int spis_ctx_destroy(spis_ctx* ctx) {
     for (auto& M : ctx->mats) free_matrix(ctx, M);
     for (auto& c : ctx->cons) { dfree(ctx, c.v); dfree(ctx, c.MZ); }
     dfree(ctx, ctx->V); dfree(ctx, ctx->Z); dfree(ctx, ctx->W); dfree(ctx, ctx->T); dfree(ctx, ctx->R0);
-    dfree(ctx, ctx->B); dfree(ctx, ctx->X0); dfree(ctx, ctx->X); dfree(ctx, ctx->pre_diag); dfree(ctx, ctx->pre_blocks);
+    dfree(ctx, ctx->B); dfree(ctx, ctx->X0); dfree(ctx, ctx->X); dfree(ctx, ctx->G); dfree(ctx, ctx->pre_diag); dfree(ctx, ctx->pre_blocks);
     dfree(ctx, ctx->d_send_idx); dfree(ctx, ctx->d_send);
     dfree(ctx, ctx->d_dest_rank); dfree(ctx, ctx->d_dest_off); dfree(ctx, ctx->d_send_to); dfree(ctx, ctx->d_recv_from);
     dfree(ctx, ctx->d_small); dfree(ctx, ctx->d_y); dfree(ctx, ctx->d_cout); dfree(ctx, ctx->d_partial); dfree(ctx, ctx->d_counter);
@@ -596,6 +629,7 @@ int spis_set_option(spis_ctx* ctx, const char* key, int64_t value) {
   else if (k == "lincomb_variant") { REQUIRE(value == 2 || value == 4 || value == 8, "lincomb_variant must be 2, 4 or 8"); ctx->lincomb_variant = (int)value; }
   else if (k == "x0_is_zero") { ctx->x0_is_zero = value ? 1 : 0; }
   else if (k == "fuse_jacobi") { ctx->fuse_jacobi = value ? 1 : 0; }
+  else if (k == "force_nonsymmetric") { ctx->force_nonsymmetric = value ? 1 : 0; }
   else return fail(ctx, SPIS_E_INVALID, "unknown option '%s'", key);
   return SPIS_OK;
 }
@@ -868,7 +902,7 @@ int spis_constraint_define(spis_ctx* ctx, int c, int mat_slot, const double* v, 
   REQUIRE(mat_slot < 0 || ctx->mats[mat_slot].present, "constraint matrix slot %d not uploaded", mat_slot);
   CU(cudaSetDevice(ctx->device));
   Constraint& C = ctx->cons[c];
-  C.defined = true; C.slot = mat_slot; C.cc = cc; C.cols_done = 0; C.term0_done = false;
+  C.defined = true; C.slot = mat_slot; C.cc = cc; C.cols_done = 0; C.term0_done = false; C.symmetric = -1;
   if (v) {
     if (!C.v) TRY(dalloc(ctx, &C.v, (size_t)ctx->ld));
     TRY(h2d(ctx, C.v, v, (size_t)ctx->n * sizeof(double)));
@@ -876,6 +910,34 @@ int spis_constraint_define(spis_ctx* ctx, int c, int mat_slot, const double* v, 
   if (mat_slot < 0 && C.MZ) { dfree(ctx, C.MZ); }
   C.T1.assign((size_t)ctx->kmax, 0.0);
   C.T2.assign((size_t)ctx->kmax * ctx->kmax, 0.0);
+  return SPIS_OK;
+}
+
+// Is the constraint matrix symmetric?  u^T (M w) == w^T (M u) for two pseudo-random vectors, to
+// 1e-11 of |Mu||w| + |Mw||u| (a matrix whose asymmetry is >= 1e-6 relative fails this with
+// overwhelming probability at any n; anything closer to symmetric is symmetric for our purposes:
+// only the symmetric part of term2 enters y^T term2 y).  All mass/stiffness forms of the reference's
+// experiments are symmetric; then the rows of Z^T (M Z) equal its columns and M Z need not be kept.
+static int test_symmetry(spis_ctx* ctx, Constraint& C) {
+  const size_t ld = (size_t)ctx->ld;
+  double *u = ctx->G, *w = ctx->G + ld, *Mu = ctx->G + 2 * ld, *Mw = ctx->G + 3 * ld;
+  CU(cudaMemsetAsync(ctx->G, 0, 4 * ld * sizeof(double), ctx->stream));
+  fill_kernel<<<ctx->nsm * 8, 256, 0, ctx->stream>>>(u, ctx->n, 0xA5A5ull);
+  fill_kernel<<<ctx->nsm * 8, 256, 0, ctx->stream>>>(w, ctx->n, 0x5A5Aull);
+  CU(cudaGetLastError());
+  TRY(do_halo(ctx, u));
+  TRY(do_halo(ctx, w));
+  TRY(launch_spmv(ctx, C.slot, 0, u, nullptr, Mu, nullptr));
+  TRY(launch_spmv(ctx, C.slot, 0, w, nullptr, Mw, nullptr));
+  double* o = ctx->d_cout;
+  TRY(launch_mdot(ctx, Mu, 1, nullptr, 1, w, o));          // [Mu.w, w.w]
+  TRY(launch_mdot(ctx, Mw, 1, nullptr, 1, u, o + 2));      // [Mw.u, u.u]
+  TRY(launch_mdot(ctx, nullptr, 0, nullptr, 1, Mu, o + 4)); // [Mu.Mu]
+  TRY(launch_mdot(ctx, nullptr, 0, nullptr, 1, Mw, o + 5)); // [Mw.Mw]
+  TRY(d2h(ctx, ctx->h_cout, o, 6 * sizeof(double)));
+  const double* h = ctx->h_cout;
+  const double scale = std::sqrt(h[4] * h[1]) + std::sqrt(h[5] * h[3]);
+  C.symmetric = std::fabs(h[0] - h[2]) <= 1e-11 * scale ? 1 : 0;
   return SPIS_OK;
 }
 
@@ -889,10 +951,16 @@ int spis_constraint_terms(spis_ctx* ctx, int c, int m, double* term0, double* te
   Constraint& C = ctx->cons[c];
   const size_t ld = (size_t)ctx->ld;
   const int K = ctx->K;
+  const int km = ctx->kmax;
   const bool hasM = C.slot >= 0;
   const bool x0nz = !ctx->x0_is_zero;
   double* Zb = zbase(ctx);
-  if (hasM && !C.MZ) TRY(dalloc(ctx, &C.MZ, (size_t)ctx->kmax * ld));
+  if (hasM && !ctx->G) TRY(dalloc(ctx, &ctx->G, 4 * ld));
+  if (hasM && C.symmetric < 0) {
+    if (ctx->force_nonsymmetric) C.symmetric = 0; else TRY(test_symmetry(ctx, C));
+  }
+  const bool sym = hasM && C.symmetric == 1;
+  if (hasM && !sym && !C.MZ) TRY(dalloc(ctx, &C.MZ, (size_t)ctx->kmax * ld));
   // term0 = 1/2 x0.M x0 + c + v.x0                                 (solvers.py:34)
   if (!C.term0_done) {
     double t = C.cc;
@@ -911,48 +979,94 @@ int spis_constraint_terms(spis_ctx* ctx, int c, int m, double* term0, double* te
     C.term0 = t; C.term0_done = true;
   }
   const int c0 = C.cols_done;
-  // rows of the output block that are not written below must not carry stale data into the
-  // batched all-reduce
-  if (m > c0 && ctx->allreduce)
-    CU(cudaMemsetAsync(ctx->d_cout + (size_t)c0 * 2 * K, 0, (size_t)(m - c0) * 2 * K * sizeof(double), ctx->stream));
-  ctx->defer_allreduce = true;
-  int rc_loop = SPIS_OK;
-  for (int col = c0; col < m && rc_loop == SPIS_OK; ++col) {
-    double* zc = Zb + (size_t)col * ld;
-    double* oA = ctx->d_cout + (size_t)col * 2 * K;
-    double* oB = oA + K;
-    if (hasM) {
-      double* mz = C.MZ + (size_t)col * ld;
-      // MZ[:,col] = M z_col   (z_col's ghost entries were filled by the Arnoldi step)    (:33)
-      rc_loop = launch_spmv(ctx, C.slot, 0, zc, nullptr, mz, nullptr);
-      // column col of Z^T MZ, and x0.MZ_col                                               (:35-36)
-      if (rc_loop == SPIS_OK) rc_loop = launch_mdot(ctx, Zb, col + 1, x0nz ? ctx->X0 : nullptr, 0, mz, oA);
-      // row col of Z^T MZ (MZ_i.z_col, i<col), and v.z_col
-      if (rc_loop == SPIS_OK && (col > 0 || C.v)) rc_loop = launch_mdot(ctx, C.MZ, col, C.v, 0, zc, oB);
-    } else if (C.v) {
-      rc_loop = launch_mdot(ctx, nullptr, 0, C.v, 0, zc, oB);
-    }
-  }
-  ctx->defer_allreduce = false;
-  if (rc_loop != SPIS_OK) return rc_loop;
   if (m > c0) {
+    // rows of the output block that are not written below must not carry stale data into the
+    // batched all-reduce
+    if (ctx->allreduce || ctx->xactive)
+      CU(cudaMemsetAsync(ctx->d_cout + (size_t)c0 * 2 * K, 0, (size_t)(m - c0) * 2 * K * sizeof(double), ctx->stream));
+    struct Group { int g0, g1, nr; };
+    std::vector<Group> groups;
+    ctx->defer_allreduce = true;
+    int rc = SPIS_OK;
+    if (sym) {
+      // symmetric M: groups of up to 4 new columns; M z_col lives only in the group buffer; one
+      // pass over Z[0..g1) serves the whole group (each basis row is read once per group)
+      for (int g0 = c0; g0 < m && rc == SPIS_OK;) {
+        const int left = m - g0;
+        const int nw = left >= 4 ? 4 : left >= 2 ? 2 : 1;
+        const int g1 = g0 + nw;
+        double* base = ctx->d_cout + (size_t)g0 * 2 * K;
+        for (int cc2 = 0; cc2 < nw && rc == SPIS_OK; ++cc2)      // M z_col (ghosts filled by the Arnoldi step) (:33)
+          rc = launch_spmv(ctx, C.slot, 0, Zb + (size_t)(g0 + cc2) * ld, nullptr, ctx->G + (size_t)cc2 * ld, nullptr);
+        const double* extra = x0nz ? ctx->X0 : nullptr;
+        const int nr = g1 + (extra ? 1 : 0);
+        if (rc == SPIS_OK) {
+          if (nw == 1) rc = launch_mdot(ctx, Zb, g1, extra, 0, ctx->G, base);        // (:35-36)
+          else rc = launch_mdotm(ctx, nw, Zb, g1, extra, ctx->G, (int64_t)ld, base);
+        }
+        if (rc == SPIS_OK && C.v) {                                // v.z_col for the group
+          double* bB = base + (size_t)nw * K;
+          if (nw == 1) rc = launch_mdot(ctx, nullptr, 0, C.v, 0, Zb + (size_t)g0 * ld, bB);
+          else rc = launch_mdotm(ctx, nw, C.v, 1, nullptr, Zb + (size_t)g0 * ld, (int64_t)ld, bB);
+        }
+        groups.push_back({g0, g1, nr});
+        g0 = g1;
+      }
+    } else {
+      for (int col = c0; col < m && rc == SPIS_OK; ++col) {
+        double* zc = Zb + (size_t)col * ld;
+        double* oA = ctx->d_cout + (size_t)col * 2 * K;
+        double* oB = oA + K;
+        if (hasM) {
+          double* mz = C.MZ + (size_t)col * ld;
+          rc = launch_spmv(ctx, C.slot, 0, zc, nullptr, mz, nullptr);                               // (:33)
+          // column col of Z^T MZ, and x0.MZ_col                                                    (:35-36)
+          if (rc == SPIS_OK) rc = launch_mdot(ctx, Zb, col + 1, x0nz ? ctx->X0 : nullptr, 0, mz, oA);
+          // row col of Z^T MZ (MZ_i.z_col, i<col), and v.z_col
+          if (rc == SPIS_OK && (col > 0 || C.v)) rc = launch_mdot(ctx, C.MZ, col, C.v, 0, zc, oB);
+        } else if (C.v) {
+          rc = launch_mdot(ctx, nullptr, 0, C.v, 0, zc, oB);
+        }
+      }
+    }
+    ctx->defer_allreduce = false;
+    if (rc != SPIS_OK) return rc;
     // one all-reduce for every dot block of this call (row-sharded runs)
     TRY(do_allreduce(ctx, ctx->d_cout + (size_t)c0 * 2 * K, (int64_t)(m - c0) * 2 * K, true));
     TRY(d2h(ctx, ctx->h_cout + (size_t)c0 * 2 * K, ctx->d_cout + (size_t)c0 * 2 * K, (size_t)(m - c0) * 2 * K * sizeof(double)));
-    const int km = ctx->kmax;
-    for (int col = c0; col < m; ++col) {
-      const double* oA = ctx->h_cout + (size_t)col * 2 * K;
-      const double* oB = oA + K;
-      double t1 = 0.0;
-      if (hasM) {
-        for (int i = 0; i <= col; ++i) C.T2[(size_t)i * km + col] = 0.5 * oA[i];
-        if (x0nz) t1 += oA[col + 1];
-        for (int i = 0; i < col; ++i) C.T2[(size_t)col * km + i] = 0.5 * oB[i];
-        if (C.v) t1 += oB[col];
-      } else if (C.v) {
-        t1 += oB[0];
+    if (sym) {
+      for (const Group& g : groups) {
+        const int nw = g.g1 - g.g0;
+        const double* base = ctx->h_cout + (size_t)g.g0 * 2 * K;
+        const double* bB = base + (size_t)nw * K;
+        for (int cc2 = 0; cc2 < nw; ++cc2) {
+          const int col = g.g0 + cc2;
+          const double* oA = base + (size_t)cc2 * g.nr;
+          for (int i = 0; i <= col; ++i) {
+            C.T2[(size_t)i * km + col] = 0.5 * oA[i];
+            C.T2[(size_t)col * km + i] = 0.5 * oA[i];
+          }
+          double t1 = 0.0;
+          if (x0nz) t1 += oA[g.g1];
+          if (C.v) t1 += bB[cc2];
+          C.T1[col] = t1;
+        }
       }
-      C.T1[col] = t1;
+    } else {
+      for (int col = c0; col < m; ++col) {
+        const double* oA = ctx->h_cout + (size_t)col * 2 * K;
+        const double* oB = oA + K;
+        double t1 = 0.0;
+        if (hasM) {
+          for (int i = 0; i <= col; ++i) C.T2[(size_t)i * km + col] = 0.5 * oA[i];
+          if (x0nz) t1 += oA[col + 1];
+          for (int i = 0; i < col; ++i) C.T2[(size_t)col * km + i] = 0.5 * oB[i];
+          if (C.v) t1 += oB[col];
+        } else if (C.v) {
+          t1 += oB[0];
+        }
+        C.T1[col] = t1;
+      }
     }
     C.cols_done = m;
   }

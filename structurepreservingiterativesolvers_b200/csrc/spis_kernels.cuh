@@ -253,6 +253,120 @@ mdot_kernel(const double* __restrict__ V, int64_t ld, int m, const double* __res
 }
 
 // ------------------------------------------------------------------------------------------
+// K7  multi-right-hand-side variant of mdot: out[c*nrows + i] = row_i . w_c for NW vectors
+// w_c = W + c*wstride at once, so every basis row is read ONCE for NW columns.  Used when the
+// constraint stage has to catch up several Krylov columns of Z^T (M Z) at the first constrained
+// step (solvers.py:33-36 rebuilds all of it; here: groups of NW columns).  The NW partial sums
+// of a lane are reduced with a transposing butterfly (6 exchanges for 4 sums instead of 20).
+// Algorithmic bytes: (nrows + NW) * 8 n.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double shfl_x(double v, int mask) { return __shfl_xor_sync(0xffffffffu, v, mask); }
+
+// returns, in every lane, the warp total of s[(lane>>4&1)*2 + (lane>>3&1)]  (NW == 4)
+__device__ __forceinline__ double warp_sum4_transposed(double s0, double s1, double s2, double s3, int lane) {
+  const bool hi4 = lane & 16, hi3 = lane & 8;
+  const double keep0 = hi4 ? s2 : s0, keep1 = hi4 ? s3 : s1;
+  const double send0 = hi4 ? s0 : s2, send1 = hi4 ? s1 : s3;
+  const double a0 = keep0 + shfl_x(send0, 16), a1 = keep1 + shfl_x(send1, 16);
+  const double keep = hi3 ? a1 : a0, send = hi3 ? a0 : a1;
+  double v = keep + shfl_x(send, 8);
+  v += shfl_x(v, 4); v += shfl_x(v, 2); v += shfl_x(v, 1);
+  return v;
+}
+// NW == 2: every lane gets the total of s[lane>>4&1]
+__device__ __forceinline__ double warp_sum2_transposed(double s0, double s1, int lane) {
+  const bool hi4 = lane & 16;
+  double v = (hi4 ? s1 : s0) + shfl_x(hi4 ? s0 : s1, 16);
+  v += shfl_x(v, 8); v += shfl_x(v, 4); v += shfl_x(v, 2); v += shfl_x(v, 1);
+  return v;
+}
+
+template <int NW, bool FULL>
+__device__ __forceinline__ void mdotm_tile(const double* __restrict__ V, int64_t ld, int m,
+                                           const double* __restrict__ extra, const double* __restrict__ W,
+                                           int64_t wstride, int64_t n, int nrows, int64_t tile,
+                                           double* sacc_warp, int lane) {
+  const int64_t e0 = tile * kTile + 2 * threadIdx.x;
+  const int64_t e1 = e0 + 2 * kThreads;
+  const bool p0 = FULL || e0 < n, p1 = FULL || e1 < n;
+  double2 w0[NW], w1[NW];
+#pragma unroll
+  for (int c = 0; c < NW; ++c) {
+    w0[c] = p0 ? ld_keep(W + c * wstride + e0) : make_double2(0.0, 0.0);
+    w1[c] = p1 ? ld_keep(W + c * wstride + e1) : make_double2(0.0, 0.0);
+  }
+  for (int i0 = 0; i0 < nrows; i0 += 2) {
+    const int ia = i0, ib = min(i0 + 1, nrows - 1);
+    const double* ra = (ia < m) ? (V + (size_t)ia * ld) : extra;
+    const double* rb = (ib < m) ? (V + (size_t)ib * ld) : extra;
+    double2 a0, a1, b0, b1;
+    if (FULL) {
+      a0 = ld_stream(ra + e0); a1 = ld_stream(ra + e1); b0 = ld_stream(rb + e0); b1 = ld_stream(rb + e1);
+    } else {
+      a0 = p0 ? ld_stream(ra + e0) : make_double2(0.0, 0.0); a1 = p1 ? ld_stream(ra + e1) : make_double2(0.0, 0.0);
+      b0 = p0 ? ld_stream(rb + e0) : make_double2(0.0, 0.0); b1 = p1 ? ld_stream(rb + e1) : make_double2(0.0, 0.0);
+    }
+    double sa[NW], sb[NW];
+#pragma unroll
+    for (int c = 0; c < NW; ++c) {
+      sa[c] = fma(a1.y, w1[c].y, fma(a1.x, w1[c].x, fma(a0.y, w0[c].y, a0.x * w0[c].x)));
+      sb[c] = fma(b1.y, w1[c].y, fma(b1.x, w1[c].x, fma(b0.y, w0[c].y, b0.x * w0[c].x)));
+    }
+    double ta, tb;
+    int cidx;
+    if (NW == 4) {
+      ta = warp_sum4_transposed(sa[0], sa[1], sa[2], sa[3], lane);
+      tb = warp_sum4_transposed(sb[0], sb[1], sb[2], sb[3], lane);
+      cidx = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+      if ((lane & 7) == 0) {                         // lanes 0, 8, 16, 24 hold columns 0, 1, 2, 3
+        sacc_warp[cidx * nrows + ia] += ta;
+        if (i0 + 1 < nrows) sacc_warp[cidx * nrows + ib] += tb;
+      }
+    } else {
+      ta = warp_sum2_transposed(sa[0], sa[1], lane);
+      tb = warp_sum2_transposed(sb[0], sb[1], lane);
+      cidx = (lane >> 4) & 1;
+      if ((lane & 15) == 0) {
+        sacc_warp[cidx * nrows + ia] += ta;
+        if (i0 + 1 < nrows) sacc_warp[cidx * nrows + ib] += tb;
+      }
+    }
+  }
+}
+
+template <int NW>
+__global__ void __launch_bounds__(kThreads)
+mdotm_kernel(const double* __restrict__ V, int64_t ld, int m, const double* __restrict__ extra,
+             const double* __restrict__ W, int64_t wstride, int64_t n,
+             double* __restrict__ partial, int pstride, unsigned* counter, double* out,
+             XView xv, unsigned long long seq) {
+  extern __shared__ double smem[];
+  const int nrows = m + (extra ? 1 : 0);
+  const int nout = NW * nrows;
+  double* sacc = smem;                      // [kWarps][NW*nrows]
+  double* sred = smem + kWarps * nout;      // [kWarps*32]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* sacc_warp = sacc + warp * nout;
+  for (int i = lane; i < nout; i += 32) sacc_warp[i] = 0.0;
+  __syncwarp();
+  const int64_t ntiles = (n + kTile - 1) / kTile;
+  const int64_t nfull = n / kTile;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    if (tile < nfull) mdotm_tile<NW, true>(V, ld, m, extra, W, wstride, n, nrows, tile, sacc_warp, lane);
+    else mdotm_tile<NW, false>(V, ld, m, extra, W, wstride, n, nrows, tile, sacc_warp, lane);
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nout; i += kThreads) {
+    double s = 0.0;
+#pragma unroll
+    for (int wv = 0; wv < kWarps; ++wv) s += sacc[wv * nout + i];
+    partial[(size_t)blockIdx.x * pstride + i] = s;
+  }
+  finish_reduction(partial, pstride, nout, counter, out, sred, xv, seq);
+}
+
+// ------------------------------------------------------------------------------------------
 // K3b / K5  tall-skinny linear combination:
 //     out = base + sign * sum_{i<m} coef[i] * V_i        (+ optional sum of squares of out)
 // Replaces `y = y - h[i,j]*q[i]` (solvers.py:195) for all i at once and `Z @ yk + x0`

@@ -73,6 +73,24 @@ def _opt(name, value):
 _TRACE = bool(os.environ.get("SPIS_TRACE"))
 
 
+class _Buckets:
+    """SPIS_TRACE=1: wall-clock spent in each phase of the Krylov loop, summed over iterations."""
+
+    def __init__(self):
+        self.acc = {}
+        self.t = time()
+
+    def mark(self, label):
+        if _TRACE:
+            now = time()
+            self.acc[label] = self.acc.get(label, 0.0) + (now - self.t)
+            self.t = now
+
+    def report(self, name):
+        if _TRACE and self.acc:
+            sys.stderr.write("[spis trace] %s loop: %s\n" % (name, ", ".join("%s %.2f ms" % (k, v * 1e3) for k, v in self.acc.items())))
+
+
 class _Trace:
     """SPIS_TRACE=1 prints the wall-clock of each host-side phase to stderr."""
 
@@ -482,11 +500,14 @@ def cgmres(A, b, x0, k, tol=1e-8, contol=10, conlist=[], pre=None, timing=None, 
     constrained_steps = 0
     steps = 0
     yk = None
+    bk = _Buckets()
     for j in range(k):
         if timing:
             jit["start_iter"].append(time())
         steps = j + 1
+        bk.mark("host")
         col = arn.column(j)
+        bk.mark("arnoldi wait")
         if not col[j + 1] != 0:
             warnings.warn(_BREAKDOWN)                     # (solvers.py:199-202)
             break
@@ -502,7 +523,9 @@ def cgmres(A, b, x0, k, tol=1e-8, contol=10, conlist=[], pre=None, timing=None, 
                 if timing:
                     constrained_steps += 1
                     jit["start_constraints"].append(time())
+                bk.mark("host")
                 cons = sess.containers(j + 1)             # (solvers.py:242-247)
+                bk.mark("constraint terms")
                 if timing:
                     jit["end_constraints"].append(time())
                 arn.prefetch(j + 1)
@@ -531,13 +554,16 @@ def cgmres(A, b, x0, k, tol=1e-8, contol=10, conlist=[], pre=None, timing=None, 
                 res = _unconstrained(engine, Hj, beta, y0, ctol ** 2)         # (solvers.py:274-278)
         _warn_message(j, res)
         yk = res.x
+        bk.mark("small solve + host")
         residual.append(sess.ctx.iterate_residual(yk))    # (solvers.py:287,290)
+        bk.mark("iterate+residual")
         hist._append(yk)
         if timing:
             jit["end_iter"].append(time())
         if residual[-1] < tol and safety is True:         # (solvers.py:296-297)
             break
     arn.drain()
+    bk.report("cgmres")
     tr("cgmres: Krylov loop (%d steps)" % steps)
     if timing:                                            # (solvers.py:300-312)
         jit["end"] = time()

@@ -178,3 +178,34 @@ def test_full_size_properties():
     q3, q7 = sess.ctx.download(nat.VEC_Q, 3), sess.ctx.download(nat.VEC_Q, 7)
     assert abs(q3 @ q3 - 1.0) <= 1e-13 and abs(q3 @ q7) <= 1e-13
     sess.close()
+
+
+@pytest.mark.parametrize("x0_zero", [True, False])
+def test_symmetric_fast_path_equals_general_path(x0_zero):
+    """Constraint terms via the symmetric-M path (multi-RHS dots, no stored M Z, groups of 4/2/1
+    columns) must equal the general path (stored M Z, row + column passes) and the oracle."""
+    d, _ = heat.linforms(M=40)
+    A, b = d["A"], d["b"]
+    n = b.size
+    x0 = np.zeros(n) if x0_zero else 0.01 * np.cos(np.arange(n))
+    cl = wrappers.heat.conlist(d, x0)              # energy: M + dt/2 L (symmetric), v != 0
+    out = {}
+    for force in (0, 1):
+        sess = solvers.DeviceSession(A, b, x0, 12, conlist=cl)
+        sess.ctx.set_option("force_nonsymmetric", force)
+        sess.begin()
+        for j in range(8):
+            sess.arnoldi_launch(j); sess.arnoldi_wait(j)
+        first = sess.ctx.constraint_terms(1, 7)      # catch-up of 7 columns: groups 4 + 2 + 1
+        second = sess.ctx.constraint_terms(1, 8)     # incremental: one more column
+        Z = sess.ctx.download_Z(0, 8).T
+        out[force] = (first, second)
+        sess.close()
+    ref = orc.ReducedInvariant(cl[1], x0, Z)
+    for force in (0, 1):
+        t0, t1, t2 = out[force][1]
+        assert abs(t0 - ref.term0) <= 1e-12 * max(abs(ref.term0), 1.0)
+        np.testing.assert_allclose(t1, ref.term1, rtol=1e-11, atol=1e-12 * np.abs(ref.term1).max())
+        np.testing.assert_allclose(t2, ref.term2, rtol=1e-11, atol=1e-12 * np.abs(ref.term2).max())
+        np.testing.assert_array_equal(out[force][0][2], t2[:7, :7])
+    np.testing.assert_allclose(out[0][1][2], out[1][1][2], rtol=1e-12, atol=1e-13 * np.abs(ref.term2).max())
