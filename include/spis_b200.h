@@ -107,6 +107,9 @@ int         spis_get_info(const spis_ctx* ctx, const char* key, int64_t* value_o
 int         spis_pinned_alloc(size_t bytes, void** ptr_out);
 int         spis_pinned_free(void* ptr);
 int         spis_pinned_trim(void);            /* release every unused pooled buffer */
+/* Device buffers of destroyed contexts are cached for the next context (exact-size reuse); this
+ * returns all cached device memory to the driver.                                              */
+int         spis_device_trim(void);
 /* host utility: *out = 1 if any of the n doubles is non-zero (multi-threaded scan; used to
  * recognise the explicit-zero constraint matrix `0*A` of lkdv/LinearSolver.py:30)             */
 int         spis_host_any_nonzero(const double* data, size_t n, int* out);

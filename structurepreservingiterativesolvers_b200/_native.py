@@ -43,6 +43,7 @@ SIGNATURES = {
     "spis_pinned_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "spis_pinned_free": (C.c_int, [C.c_void_p]),
     "spis_pinned_trim": (C.c_int, []),
+    "spis_device_trim": (C.c_int, []),
     "spis_host_any_nonzero": (C.c_int, [_dp, C.c_size_t, C.POINTER(C.c_int)]),
     "spis_set_option": (C.c_int, [_ctx, C.c_char_p, C.c_int64]),
     "spis_get_info": (C.c_int, [_ctx, C.c_char_p, _lp]),

@@ -51,8 +51,11 @@ struct Constraint {
 };
 
 struct ProfRec { int cls; double bytes; cudaEvent_t e0, e1; };
+struct DevBlock { void* p; size_t bytes; int device; };
 
 }  // namespace
+
+extern "C" int spis_device_trim(void);
 
 struct spis_ctx {
   int device = 0;
@@ -105,6 +108,7 @@ struct spis_ctx {
   int32_t *d_dest_rank = nullptr, *d_dest_off = nullptr, *d_send_to = nullptr, *d_recv_from = nullptr;
   // profiling
   std::vector<ProfRec> recs; std::vector<cudaEvent_t> evpool;
+  std::vector<DevBlock> owned;   // device blocks currently held by this context
   double prof_ms[SPIS_PROF_CLASSES] = {0}; double prof_bytes[SPIS_PROF_CLASSES] = {0}; int64_t prof_launch[SPIS_PROF_CLASSES] = {0};
   char err[512] = "";
 };
@@ -130,28 +134,59 @@ int fail(spis_ctx* c, int code, const char* fmt, ...) {
 
 inline int64_t roundup(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 
-// Device memory comes from the device's default stream-ordered memory pool with the release
-// threshold raised to "never": a context that is created per solve (the reference's call pattern:
-// one solvers.cgmres call per time step, lkdv/Evolve.py:39-56) re-uses the ~10 GB of the previous
-// one instead of paying cudaMalloc/cudaFree (measured 100+ ms per solve) every time.
-int pool_init(spis_ctx* ctx) {
-  cudaMemPool_t pool;
-  CU(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
-  uint64_t keep = UINT64_MAX;
-  CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-  return SPIS_OK;
-}
+// Device memory comes from a process-wide cache of exact-size blocks.  The reference's call pattern
+// is one solver call per time step (lkdv/Evolve.py:39-56), i.e. one context per solve with the SAME
+// buffer sizes every time; cudaMalloc/cudaFree of ~10 GB per solve costs 100+ ms (measured), and the
+// stream-ordered pool (cudaMallocAsync) stalled for up to a second when it had to grow or could not
+// coalesce.  Freed blocks are kept (spis_device_trim releases them) and handed out again on an
+// exact size match, so from the second solve on allocation is free.
+std::mutex g_dev_mu;
+std::vector<DevBlock> g_dev_free;
 
 template <class Tp> int dalloc(spis_ctx* ctx, Tp** p, size_t count, bool zero = true) {
   *p = nullptr;
   if (count == 0) count = 1;
-  CU(cudaMallocAsync((void**)p, count * sizeof(Tp), ctx->stream));
-  if (zero) CU(cudaMemsetAsync(*p, 0, count * sizeof(Tp), ctx->stream));
+  const size_t bytes = (count * sizeof(Tp) + 255) / 256 * 256;
+  void* q = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    for (size_t i = 0; i < g_dev_free.size(); ++i)
+      if (g_dev_free[i].bytes == bytes && g_dev_free[i].device == ctx->device) {
+        q = g_dev_free[i].p;
+        g_dev_free[i] = g_dev_free.back();
+        g_dev_free.pop_back();
+        break;
+      }
+  }
+  if (!q) {
+    cudaError_t e = cudaMalloc(&q, bytes);
+    if (e == cudaErrorMemoryAllocation) {          // give cached blocks back to the driver and retry
+      cudaGetLastError();
+      spis_device_trim();
+      e = cudaMalloc(&q, bytes);
+    }
+    if (e != cudaSuccess) return fail(ctx, e == cudaErrorMemoryAllocation ? SPIS_E_NOMEM : SPIS_E_CUDA,
+                                      "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+  }
+  *p = static_cast<Tp*>(q);
+  ctx->owned.push_back({q, bytes, ctx->device});
+  if (zero) CU(cudaMemsetAsync(q, 0, bytes, ctx->stream));
   return SPIS_OK;
 }
 
+// Return a block to the cache.  The caller guarantees that the context's stream has drained every
+// kernel that touched it (all call sites follow a stream synchronisation, or synchronise here).
 template <class Tp> void dfree(spis_ctx* ctx, Tp*& p) {
-  if (p) cudaFreeAsync((void*)p, ctx->stream);
+  if (!p) return;
+  cudaStreamSynchronize(ctx->stream);
+  for (size_t i = 0; i < ctx->owned.size(); ++i)
+    if (ctx->owned[i].p == (void*)p) {
+      std::lock_guard<std::mutex> lk(g_dev_mu);
+      g_dev_free.push_back(ctx->owned[i]);
+      ctx->owned[i] = ctx->owned.back();
+      ctx->owned.pop_back();
+      break;
+    }
   p = nullptr;
 }
 
@@ -455,6 +490,16 @@ int spis_pinned_free(void* p) {
   return SPIS_E_INVALID;
 }
 
+int spis_device_trim(void) {
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  for (auto& b : g_dev_free) { cudaSetDevice(b.device); cudaFree(b.p); }
+  g_dev_free.clear();
+  cudaSetDevice(dev);
+  return SPIS_OK;
+}
+
 int spis_pinned_trim(void) {
   std::lock_guard<std::mutex> lk(g_pin_mu);
   std::vector<PinnedBlock> keep;
@@ -561,7 +606,6 @@ int spis_ctx_create(int device, int64_t n, int64_t n_halo, int k_max, void* stre
   CTRY(dalloc(c, &c->d_cout, (size_t)k_max * 2 * c->K));
   CTRY(dalloc(c, &c->d_partial, (size_t)c->max_grid * c->pstride));
   CTRY(dalloc(c, &c->d_counter, 4));
-  CTRY(pool_init(c));
   if (spis_pinned_alloc(((size_t)2 * c->K + 8) * sizeof(double), (void**)&c->h_small) != SPIS_OK ||
       spis_pinned_alloc((size_t)c->K * sizeof(double), (void**)&c->h_y) != SPIS_OK ||
       spis_pinned_alloc((size_t)k_max * 2 * c->K * sizeof(double), (void**)&c->h_cout) != SPIS_OK) {
@@ -604,6 +648,9 @@ int spis_ctx_destroy(spis_ctx* ctx) {
     dfree(ctx, ctx->d_dest_rank); dfree(ctx, ctx->d_dest_off); dfree(ctx, ctx->d_send_to); dfree(ctx, ctx->d_recv_from);
     dfree(ctx, ctx->d_small); dfree(ctx, ctx->d_y); dfree(ctx, ctx->d_cout); dfree(ctx, ctx->d_partial); dfree(ctx, ctx->d_counter);
     cudaStreamSynchronize(ctx->stream);
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    for (auto& b : ctx->owned) g_dev_free.push_back(b);
+    ctx->owned.clear();
   }
   for (int r = 0; r < kMaxRanks; ++r)
     if (ctx->xpeer[r]) cudaIpcCloseMemHandle(ctx->xpeer[r]);

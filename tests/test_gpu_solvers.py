@@ -138,8 +138,11 @@ def test_midsize_against_oracle(engine):
     tol = 1e-6 * np.sqrt(n / 150)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        xo, io = orc.cgmres(A, b, x0, 50, tol=tol, contol=10, conlist=cl)
-        xg, ig = solvers.cgmres(A, b, x0, 50, tol=tol, contol=10, conlist=cl, small_solver=engine)
+        # timing=True on both sides: at |invariant| ~ 1e5 the reference's absolute 1e-12 check on the
+        # SIGNED violation (solvers.py:266-270, quirk Q4) is a coin flip on the last bit and would
+        # make the step count itself noise-dependent
+        xo, io = orc.cgmres(A, b, x0, 50, tol=tol, contol=10, conlist=cl, timing=True)
+        xg, ig = solvers.cgmres(A, b, x0, 50, tol=tol, contol=10, conlist=cl, small_solver=engine, timing=True)
     assert ig["steps"] == io["steps"]
     assert helpers.rel_diff(xg, xo) <= 1e-10
     assert abs(ig["res"][-1] - np.linalg.norm(A @ xg - b)) <= 1e-12 * np.linalg.norm(b)
