@@ -34,7 +34,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define SPIS_ABI_VERSION 1
+#define SPIS_ABI_VERSION 2
 
 /* error codes */
 #define SPIS_OK            0
@@ -84,7 +84,8 @@ extern "C" {
 #define SPIS_PROF_SCALE    3
 #define SPIS_PROF_PRECOND  4
 #define SPIS_PROF_OTHER    5
-#define SPIS_PROF_CLASSES  6
+#define SPIS_PROF_ORTHMID  6   /* fused  w -= V h1 ; h2 = V^T w  (middle of CGS2, one pass over V) */
+#define SPIS_PROF_CLASSES  7
 
 typedef struct spis_ctx spis_ctx;
 
@@ -98,7 +99,8 @@ int         spis_ctx_create(int device, int64_t n, int64_t n_halo, int k_max, vo
 int         spis_ctx_destroy(spis_ctx* ctx);
 const char* spis_last_error(const spis_ctx* ctx);
 const char* spis_last_global_error(void);            /* for failures of spis_ctx_create itself */
-/* keys: "orth", "spmv_format", "profile", "ctas_per_sm", "mdot_variant", "lincomb_variant", "spmv_variant" */
+/* keys: "orth", "spmv_format", "profile", "ctas_per_sm", "spmv_ctas_per_sm", "mdot_variant", "lincomb_variant",
+ *       "x0_is_zero", "fuse_jacobi", "orth_fused", "orth_mid_max_stages", "force_nonsymmetric" */
 int         spis_set_option(spis_ctx* ctx, const char* key, int64_t value);
 int         spis_get_info(const spis_ctx* ctx, const char* key, int64_t* value_out);
 
@@ -204,6 +206,9 @@ int spis_op_mdot(spis_ctx* ctx, int m, const double* V /* m x n */, const double
 int spis_op_lincomb(spis_ctx* ctx, int m, const double* V, const double* base, const double* coef,
                     double sign, double* out, double* sumsq_out);
 int spis_op_precond(spis_ctx* ctx, const double* q, double* z);                        /* z = P q */
+/* fused middle of CGS2 (solvers.py:193-195 applied twice): w_out = w - V^T coef, dots_out[i] = V_i . w_out */
+int spis_op_orth_mid(spis_ctx* ctx, int m, const double* V, const double* w, const double* coef,
+                     double* w_out, double* dots_out);
 /* time `reps` back-to-back launches of one kernel class on resident random data and
  * return the mean milliseconds per launch (tuning / roofline sweeps).                   */
 int spis_bench_kernel(spis_ctx* ctx, int prof_class, int m, int reps, double* ms_out, double* bytes_out);

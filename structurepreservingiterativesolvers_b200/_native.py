@@ -14,15 +14,15 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "lib", "libspis_b200.so")
 
 # constants mirrored from include/spis_b200.h
-ABI_VERSION = 1
+ABI_VERSION = 2
 OK, E_INVALID, E_CUDA, E_NOMEM, E_UNSUPPORTED = 0, -1, -2, -3, -4
 SLOT_A, SLOT_PRE, SLOT_CON0, MAX_SLOTS = 0, 1, 2, 18
 VEC_B, VEC_X0, VEC_R0, VEC_Q, VEC_Z, VEC_X, VEC_PRE_DIAG, VEC_W = range(8)
 PRE_NONE, PRE_JACOBI, PRE_CSR, PRE_BLOCK, PRE_HOST = range(5)
 ORTH_CGS2, ORTH_CGS1, ORTH_MGS = range(3)
 FMT_AUTO, FMT_SELL, FMT_CSR = range(3)
-PROF_SPMV, PROF_MDOT, PROF_LINCOMB, PROF_SCALE, PROF_PRECOND, PROF_OTHER, PROF_CLASSES = range(7)
-PROF_NAMES = ("spmv", "mdot", "lincomb", "scale", "precond", "other")
+PROF_SPMV, PROF_MDOT, PROF_LINCOMB, PROF_SCALE, PROF_PRECOND, PROF_OTHER, PROF_ORTHMID, PROF_CLASSES = range(8)
+PROF_NAMES = ("spmv", "mdot", "lincomb", "scale", "precond", "other", "orthmid")
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64)
 HALO_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p)
@@ -77,6 +77,7 @@ SIGNATURES = {
     "spis_op_mdot": (C.c_int, [_ctx, C.c_int, _dp, _dp, _dp]),
     "spis_op_lincomb": (C.c_int, [_ctx, C.c_int, _dp, _dp, _dp, C.c_double, _dp, _dp]),
     "spis_op_precond": (C.c_int, [_ctx, _dp, _dp]),
+    "spis_op_orth_mid": (C.c_int, [_ctx, C.c_int, _dp, _dp, _dp, _dp, _dp]),
     "spis_bench_kernel": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, _dp, _dp]),
 }
 

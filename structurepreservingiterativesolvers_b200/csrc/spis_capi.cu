@@ -74,6 +74,10 @@ struct spis_ctx {
   int x0_is_zero = 0;
   int fuse_jacobi = 1;
   int force_nonsymmetric = 0;   // tests: take the general (stored M Z) path of the constraint stage
+  int orth_fused = 1;           // CGS2: fuse (w -= V h1) with (h2 = V^T w) through TMA-staged tiles
+  int orth_mid_max_stages = 8;
+  int orth_mid_probe = 0;       // tuning: stream the tiles through shared memory without consuming them
+  int orth_mid_force_e = 0;     // tuning: 1 or 2 doubles per thread per tile (0 = choose)
   // vectors
   double *V = nullptr, *Z = nullptr, *W = nullptr, *T = nullptr, *R0 = nullptr, *B = nullptr, *X0 = nullptr, *X = nullptr;
   double* G = nullptr;          // 4 x ld group buffer of the constraint stage (lazy)
@@ -360,6 +364,63 @@ int launch_lincomb(spis_ctx* ctx, const double* V, int m, const double* coef, co
   return SPIS_OK;
 }
 
+// Fused middle of CGS2 (orth_mid_kernel): w <- w - V coef, out[i] = V_i . w(new).  Picks the widest
+// tile that still leaves a ring of staging slots in shared memory; returns SPIS_E_UNSUPPORTED (and
+// launches nothing) when m is too large for one slot pair, so the caller takes the two-kernel path.
+constexpr size_t kOrthMidSmemBudget = 225 * 1024;
+template <int MB>
+int launch_orth_mid_mb(spis_ctx* ctx, int E, int grid, size_t smem, const double* V, int m, const double* coef,
+                       double* w, int nstages, double* out, const XView& xv, unsigned long long seq) {
+  if (E == 2)
+    orth_mid_kernel<MB, 2><<<grid, kOrthMidThreads, smem, ctx->stream>>>(V, ctx->ld, m, coef, w, ctx->hoff, nstages, ctx->orth_mid_probe, ctx->d_partial, ctx->pstride, ctx->d_counter, out, xv, seq);
+  else
+    orth_mid_kernel<MB, 1><<<grid, kOrthMidThreads, smem, ctx->stream>>>(V, ctx->ld, m, coef, w, ctx->hoff, nstages, ctx->orth_mid_probe, ctx->d_partial, ctx->pstride, ctx->d_counter, out, xv, seq);
+  CU(cudaGetLastError());
+  return SPIS_OK;
+}
+
+bool orth_mid_plan(const spis_ctx* ctx, int m, int* E_out, int* stages_out, int* MB_out, size_t* smem_out) {
+  if (m < 1 || m > 64) return false;
+  const int MB = (m + 7) / 8 * 8;
+  for (int E = 2; E >= 1; --E) {
+    if (ctx->orth_mid_force_e && E != ctx->orth_mid_force_e) continue;
+    const size_t fixed = orth_mid_smem(MB, E, m, 0);
+    const size_t stage = (size_t)(m + 1) * kThreads * E * sizeof(double) + 2 * sizeof(uint64_t);
+    if (fixed + stage > kOrthMidSmemBudget) continue;
+    int stages = (int)((kOrthMidSmemBudget - fixed) / stage);
+    if (stages > ctx->orth_mid_max_stages) stages = ctx->orth_mid_max_stages;
+    if (stages < 2) continue;
+    *E_out = E; *stages_out = stages; *MB_out = MB; *smem_out = orth_mid_smem(MB, E, m, stages);
+    return true;
+  }
+  return false;
+}
+
+int launch_orth_mid(spis_ctx* ctx, const double* V, int m, const double* coef, double* w, double* out) {
+  int E = 0, stages = 0, MB = 0; size_t smem = 0;
+  if (!orth_mid_plan(ctx, m, &E, &stages, &MB, &smem)) return fail(ctx, SPIS_E_UNSUPPORTED, "orth_mid: m=%d does not fit shared memory", m);
+  const int T = kThreads * E;
+  const int64_t ntiles = (ctx->hoff + T - 1) / T;
+  const int grid = grid_for(ctx, ntiles, 1);
+  TRY(prof_begin(ctx, SPIS_PROF_ORTHMID, (double)(m + 2) * 8.0 * (double)ctx->n));
+  const XView xv = fused_view(ctx);
+  const unsigned long long seq = fused_seq(ctx);
+  int rc;
+  switch (MB) {
+    case 8: rc = launch_orth_mid_mb<8>(ctx, E, grid, smem, V, m, coef, w, stages, out, xv, seq); break;
+    case 16: rc = launch_orth_mid_mb<16>(ctx, E, grid, smem, V, m, coef, w, stages, out, xv, seq); break;
+    case 24: rc = launch_orth_mid_mb<24>(ctx, E, grid, smem, V, m, coef, w, stages, out, xv, seq); break;
+    case 32: rc = launch_orth_mid_mb<32>(ctx, E, grid, smem, V, m, coef, w, stages, out, xv, seq); break;
+    case 40: rc = launch_orth_mid_mb<40>(ctx, E, grid, smem, V, m, coef, w, stages, out, xv, seq); break;
+    case 48: rc = launch_orth_mid_mb<48>(ctx, E, grid, smem, V, m, coef, w, stages, out, xv, seq); break;
+    case 56: rc = launch_orth_mid_mb<56>(ctx, E, grid, smem, V, m, coef, w, stages, out, xv, seq); break;
+    default: rc = launch_orth_mid_mb<64>(ctx, E, grid, smem, V, m, coef, w, stages, out, xv, seq); break;
+  }
+  TRY(rc);
+  TRY(prof_end(ctx));
+  return do_allreduce(ctx, out, m);
+}
+
 template <int MODE>
 int launch_spmv_mode(spis_ctx* ctx, const Matrix& M, const double* x, const double* b, double* y, double* sumsq_out) {
   const XView xv = MODE != 0 ? fused_view(ctx) : XView();
@@ -626,6 +687,11 @@ int spis_ctx_create(int device, int64_t n, int64_t n_halo, int k_max, void* stre
     CCU(cudaFuncSetAttribute(mdot_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_need));
     CCU(cudaFuncSetAttribute(mdot_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_need));
   }
+#define SPIS_OM_ATTR(MBV) \
+  CCU(cudaFuncSetAttribute(orth_mid_kernel<MBV, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOrthMidSmemBudget)); \
+  CCU(cudaFuncSetAttribute(orth_mid_kernel<MBV, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOrthMidSmemBudget));
+  SPIS_OM_ATTR(8) SPIS_OM_ATTR(16) SPIS_OM_ATTR(24) SPIS_OM_ATTR(32) SPIS_OM_ATTR(40) SPIS_OM_ATTR(48) SPIS_OM_ATTR(56) SPIS_OM_ATTR(64)
+#undef SPIS_OM_ATTR
   CCU(cudaStreamSynchronize(c->stream));
 #undef CTRY
 #undef CCU
@@ -677,6 +743,10 @@ int spis_set_option(spis_ctx* ctx, const char* key, int64_t value) {
   else if (k == "x0_is_zero") { ctx->x0_is_zero = value ? 1 : 0; }
   else if (k == "fuse_jacobi") { ctx->fuse_jacobi = value ? 1 : 0; }
   else if (k == "force_nonsymmetric") { ctx->force_nonsymmetric = value ? 1 : 0; }
+  else if (k == "orth_fused") { ctx->orth_fused = value ? 1 : 0; }
+  else if (k == "orth_mid_probe") { ctx->orth_mid_probe = value ? 1 : 0; }
+  else if (k == "orth_mid_force_e") { REQUIRE(value >= 0 && value <= 2, "orth_mid_force_e must be 0..2"); ctx->orth_mid_force_e = (int)value; }
+  else if (k == "orth_mid_max_stages") { REQUIRE(value >= 2 && value <= 64, "orth_mid_max_stages must be 2..64"); ctx->orth_mid_max_stages = (int)value; }
   else return fail(ctx, SPIS_E_INVALID, "unknown option '%s'", key);
   return SPIS_OK;
 }
@@ -868,8 +938,13 @@ int spis_arnoldi_launch(spis_ctx* ctx, int j) {
     TRY(launch_lincomb(ctx, ctx->V, m, h1, nullptr, -1.0, ctx->W, qn, 1, scal));
   } else {
     TRY(launch_mdot(ctx, ctx->V, m, nullptr, 0, ctx->W, h1));
-    TRY(launch_lincomb(ctx, ctx->V, m, h1, nullptr, -1.0, ctx->W, ctx->W, 0, nullptr));
-    TRY(launch_mdot(ctx, ctx->V, m, nullptr, 0, ctx->W, h2));
+    int E_ = 0, st_ = 0, mb_ = 0; size_t sm_ = 0;
+    if (ctx->orth_fused && orth_mid_plan(ctx, m, &E_, &st_, &mb_, &sm_)) {
+      TRY(launch_orth_mid(ctx, ctx->V, m, h1, ctx->W, h2));           // one pass over V for both
+    } else {
+      TRY(launch_lincomb(ctx, ctx->V, m, h1, nullptr, -1.0, ctx->W, ctx->W, 0, nullptr));
+      TRY(launch_mdot(ctx, ctx->V, m, nullptr, 0, ctx->W, h2));
+    }
     TRY(launch_lincomb(ctx, ctx->V, m, h2, nullptr, -1.0, ctx->W, qn, 1, scal));
   }
   // q[j+1] = w / ||w||                                             (solvers.py:196-198)
@@ -1343,6 +1418,19 @@ int spis_op_lincomb(spis_ctx* ctx, int m, const double* V, const double* base, c
   return SPIS_OK;
 }
 
+int spis_op_orth_mid(spis_ctx* ctx, int m, const double* V, const double* w, const double* coef,
+                     double* w_out, double* dots_out) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(m >= 1 && m <= ctx->kmax && V && w && coef && w_out && dots_out, "bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpy2DAsync(ctx->V, (size_t)ctx->ld * sizeof(double), V, (size_t)ctx->n * sizeof(double), (size_t)ctx->n * sizeof(double), (size_t)m, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_y, coef, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->W, w, (size_t)ctx->n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  TRY(launch_orth_mid(ctx, ctx->V, m, ctx->d_y, ctx->W, ctx->d_small));
+  TRY(d2h(ctx, w_out, ctx->W, (size_t)ctx->n * sizeof(double)));
+  return d2h(ctx, dots_out, ctx->d_small, (size_t)m * sizeof(double));
+}
+
 int spis_op_precond(spis_ctx* ctx, const double* q, double* z) {
   if (!ctx) return SPIS_E_INVALID;
   REQUIRE(q && z, "null argument");
@@ -1385,6 +1473,7 @@ int spis_bench_kernel(spis_ctx* ctx, int cls, int m, int reps, double* ms_out, d
       case SPIS_PROF_MDOT: rc = launch_mdot(ctx, ctx->V, m, nullptr, 0, ctx->W, ctx->d_small); break;
       case SPIS_PROF_LINCOMB: rc = launch_lincomb(ctx, ctx->V, m, ctx->d_y, nullptr, -1.0, ctx->W, ctx->T, 1, scal + 3); break;
       case SPIS_PROF_SCALE: rc = launch_scale(ctx, ctx->V, scal + 4, nullptr, nullptr); break;
+      case SPIS_PROF_ORTHMID: rc = launch_orth_mid(ctx, ctx->V, m, ctx->d_y, ctx->W, ctx->d_small); break;
       case SPIS_PROF_PRECOND: rc = launch_precond(ctx, ctx->V, ctx->T); break;
       default: rc = fail(ctx, SPIS_E_INVALID, "class %d cannot be benchmarked", cls);
     }

@@ -132,7 +132,7 @@ __device__ __forceinline__ void cta_xreduce(double* buf, int count, const XView&
 // fixed order (8 warps over contiguous CTA ranges, then warp 0..7 in order) into out[i].
 __device__ __forceinline__ void finish_reduction(double* __restrict__ partial, int pstride, int nout,
                                                  unsigned* counter, double* out,
-                                                 double* sred /* kWarps*32 doubles */,
+                                                 double* sred /* 32 doubles per warp of the CTA */,
                                                  const XView& xv, unsigned long long seq) {
   __shared__ unsigned s_ticket;
   __threadfence();
@@ -456,6 +456,182 @@ lincomb_kernel(const double* __restrict__ V, int64_t ld, int m, const double* __
   }
   __syncthreads();
   finish_reduction(partial, 1, 1, counter, sumsq_out, sred, xv, seq);
+}
+
+// ------------------------------------------------------------------------------------------
+// K3c  middle of CGS2, one pass over the basis instead of two:
+//     w' = w - sum_i coef[i] V_i           (first projection applied,  solvers.py:195)
+//     out[i] = V_i . w'                     (second projection measured, solvers.py:194 again)
+// Both need the SAME tile of every basis row, so the tile [m rows x T columns] is staged in shared
+// memory by the TMA engine (one 1-D cp.async.bulk per row, completion counted on an mbarrier) and
+// consumed twice from there: HBM sees each basis row once.  One persistent CTA per SM owns up to
+// ~220 KB of staging split into `nstages` ring slots, so the bulk copies of the next tiles are in
+// flight while the current one is consumed; the dot partial sums live in registers (MB of them per
+// thread, MB = m rounded up, a template parameter so the indices are static) and are reduced
+// across the CTA once, after the last tile.  The arithmetic of w' is the same fma chain in the
+// same order as lincomb_kernel, so fused and unfused paths give bit-identical w'.
+// Algorithmic bytes: (m + 2) * 8 n   (m rows + w read, w' written), versus (2m + 3) * 8 n unfused.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "SPIS_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra SPIS_DONE_%=;\n"
+      "bra SPIS_WAIT_%=;\n"
+      "SPIS_DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA engine; bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+
+template <int E> struct VecE;
+template <> struct VecE<1> { using type = double; };
+template <> struct VecE<2> { using type = double2; };
+
+constexpr int kOrthMidProducers = 4;
+constexpr int kOrthMidThreads = kThreads + 32 * kOrthMidProducers;   // 8 consumer warps + 4 producer warps
+
+// shared-memory footprint of orth_mid_kernel<MB, E> with `nstages` ring slots
+__host__ __device__ inline size_t orth_mid_smem(int MB, int E, int m, int nstages) {
+  return (size_t)nstages * (size_t)(m + 1) * kThreads * E * sizeof(double)   // tiles
+         + (size_t)MB * sizeof(double)                                        // coefficients
+         + (size_t)kWarps * MB * sizeof(double)                               // per-warp dot sums
+         + (size_t)(kOrthMidThreads / 32) * 32 * sizeof(double)                // reduction scratch
+         + (size_t)2 * nstages * sizeof(uint64_t) + 16;                       // mbarriers (full, empty)
+}
+
+template <int MB, int E>
+__global__ void __launch_bounds__(kOrthMidThreads, 1)
+orth_mid_kernel(const double* __restrict__ V, int64_t ld, int m, const double* __restrict__ coef,
+                double* w, int64_t npad /* roundup(n,16): pads are zero */, int nstages, int probe,
+                double* __restrict__ partial, int pstride, unsigned* counter, double* out,
+                XView xv, unsigned long long seq) {
+  constexpr int T = kThreads * E;
+  using vec_t = typename VecE<E>::type;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  double* tiles = reinterpret_cast<double*>(smraw);
+  const size_t stage_elems = (size_t)(m + 1) * T;
+  double* sh = tiles + (size_t)nstages * stage_elems;   // [MB] coefficients (zero beyond m)
+  double* sacc = sh + MB;                               // [kWarps][MB]
+  double* sred = sacc + kWarps * MB;                    // [32 per warp]
+  uint64_t* full = reinterpret_cast<uint64_t*>(sred + kOrthMidThreads);
+  uint64_t* empty = full + nstages;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int64_t ntiles = (npad + T - 1) / T;
+  const int64_t my_count = ntiles > (int64_t)blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nstages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, kWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < MB; i += kOrthMidThreads) sh[i] = i < m ? coef[i] : 0.0;
+  __syncthreads();
+
+  double acc[MB];
+#pragma unroll
+  for (int i = 0; i < MB; ++i) acc[i] = 0.0;
+
+  if (warp >= kWarps) {
+    // ---- producer warps: one elected lane each, rows dealt round-robin, keep the ring full ----
+    // (a single issuing thread sustains one 4 KB copy per ~190 cycles but not one 2 KB copy per
+    //  ~93 cycles, which is what HBM delivers to one SM: ~19 instructions go with every UBLKCP)
+    if (lane == 0) {
+      const int pw = warp - kWarps;
+      const uint64_t pol_stream = l2_policy_evict_first();
+      int stage = 0;
+      uint32_t phase = 1;                 // parity of the "slot is free" phase; first lap passes immediately
+      for (int64_t k = 0; k < my_count; ++k) {
+        if (k >= nstages) mbar_wait(empty + stage, phase);
+        const int64_t start = ((int64_t)blockIdx.x + k * gridDim.x) * T;
+        const int64_t left = npad - start;
+        const uint32_t bytes = (uint32_t)((left < T ? left : (int64_t)T) * sizeof(double));
+        if (pw == 0) mbar_arrive_expect_tx(full + stage, bytes * (uint32_t)(m + 1));
+        double* dst = tiles + (size_t)stage * stage_elems + (size_t)pw * T;
+        const double* src = V + (size_t)pw * ld + start;
+        for (int r = pw; r < m; r += kOrthMidProducers, src += (size_t)kOrthMidProducers * ld, dst += (size_t)kOrthMidProducers * T)
+          bulk_g2s(dst, src, bytes, full + stage, pol_stream);
+        if (m % kOrthMidProducers == pw)    // the tile of w sits in row slot m
+          bulk_g2s(tiles + (size_t)stage * stage_elems + (size_t)m * T, w + start, bytes, full + stage, pol_stream);
+        if (++stage == nstages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else {
+    // ---- consumer warps ----------------------------------------------------------------------
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int64_t k = 0; k < my_count; ++k) {
+      mbar_wait(full + stage, phase);
+      const int64_t start = ((int64_t)blockIdx.x + k * gridDim.x) * T;
+      const int64_t left = npad - start;
+      const bool active = (int64_t)threadIdx.x * E < left;      // left % 16 == 0: whole vec_t or nothing
+      const vec_t* st = reinterpret_cast<const vec_t*>(tiles + (size_t)stage * stage_elems) + threadIdx.x;
+      if (active && !probe) {
+        vec_t r = st[(size_t)m * (T / E)];
+        // w' = w - sum_i c_i V_i: one fma chain in row order (same bits as lincomb_kernel)
+        for (int i = 0; i < m; ++i) {
+          const vec_t a = st[(size_t)i * (T / E)];
+          const double c = -sh[i];
+          if constexpr (E == 2) { r.x = fma(c, a.x, r.x); r.y = fma(c, a.y, r.y); }
+          else r = fma(c, a, r);
+        }
+        *reinterpret_cast<vec_t*>(w + start + (int64_t)threadIdx.x * E) = r;
+        // second look at the same staged rows: partial dots with w'
+#pragma unroll
+        for (int i = 0; i < MB; ++i) {
+          if (i < m) {
+            const vec_t a = st[(size_t)i * (T / E)];
+            if constexpr (E == 2) acc[i] = fma(a.y, r.y, fma(a.x, r.x, acc[i]));
+            else acc[i] = fma(a, r, acc[i]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + stage);            // this warp is done with the ring slot
+      if (++stage == nstages) { stage = 0; phase ^= 1u; }
+    }
+  }
+
+  // CTA reduction of the per-thread sums: warp shuffle, then the 8 consumer warps in fixed order
+  if (warp < kWarps) {
+#pragma unroll
+    for (int i = 0; i < MB; ++i) {
+      const double s = warp_sum(acc[i]);
+      if (lane == 0) sacc[warp * MB + i] = s;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < m; i += kOrthMidThreads) {
+    double s = 0.0;
+#pragma unroll
+    for (int wv = 0; wv < kWarps; ++wv) s += sacc[wv * MB + i];
+    partial[(size_t)blockIdx.x * pstride + i] = s;
+  }
+  finish_reduction(partial, pstride, m, counter, out, sred, xv, seq);
 }
 
 // ------------------------------------------------------------------------------------------

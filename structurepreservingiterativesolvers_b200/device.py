@@ -285,6 +285,18 @@ class KrylovContext:
                                               float(sign), nat.dptr(out), C.byref(ss) if want_sumsq else None))
         return (out, ss.value) if want_sumsq else out
 
+    def op_orth_mid(self, V, w, coef):
+        """Fused middle of CGS2: returns (w - coef @ V, V @ (w - coef @ V)) from one pass over V."""
+        V = np.ascontiguousarray(V, dtype=np.float64).reshape(-1, self.n)
+        m = V.shape[0]
+        w = nat.as_f64(w, self.n)
+        coef = nat.as_f64(coef, m)
+        w_out = np.empty(self.n, dtype=np.float64)
+        dots = np.empty(m, dtype=np.float64)
+        self._check(self._lib.spis_op_orth_mid(self._h, m, nat.dptr(V), nat.dptr(w), nat.dptr(coef),
+                                               nat.dptr(w_out), nat.dptr(dots)))
+        return w_out, dots
+
     def op_precond(self, q) -> np.ndarray:
         q = nat.as_f64(q, self.n)
         z = np.empty(self.n, dtype=np.float64)

@@ -131,6 +131,52 @@ def test_lincomb_variants(variant):
     np.testing.assert_allclose(out, base + coef @ V, rtol=1e-12, atol=1e-12)
 
 
+@pytest.mark.parametrize("n", [2, 255, 256, 257, 511, 513, 4096, 300_007])
+@pytest.mark.parametrize("m", [1, 2, 7, 8, 9, 21, 33, 50, 53])
+def test_orth_mid_fused_kernel(n, m):
+    """TMA-staged fused (w -= V c ; dots = V w): same w bits as the lincomb kernel, dots to rounding."""
+    rng = np.random.default_rng(17 * n + m)
+    V = rng.standard_normal((m, n))
+    w = rng.standard_normal(n)
+    coef = rng.standard_normal(m)
+    with KrylovContext(n, 64) as ctx:
+        w1, d1 = ctx.op_orth_mid(V, w, coef)
+        w2, d2 = ctx.op_orth_mid(V, w, coef)
+        wl, _ = ctx.op_lincomb(V, w, coef, sign=-1.0)
+    np.testing.assert_array_equal(w1, w2)
+    np.testing.assert_array_equal(d1, d2)                           # deterministic
+    np.testing.assert_array_equal(w1, wl)                           # same fma chain as the unfused kernel
+    ref_w = w - coef @ V
+    scale = np.abs(w) + np.abs(coef) @ np.abs(V) + 1e-300
+    assert np.max(np.abs(w1 - ref_w) / scale) <= 1e-14
+    ref_d = V @ w1
+    dscale = np.abs(V) @ np.abs(w1) + 1e-300
+    assert np.max(np.abs(d1 - ref_d) / dscale) <= 1e-13
+
+
+def test_orth_mid_refuses_what_does_not_fit():
+    """m = 64 needs 2 x 65 x 2 KB of staging: more than one SM has; the entry point says so and the
+    Arnoldi step takes the two-kernel path on its own (test_gpu_solvers covers k > 55)."""
+    n, m = 1000, 64
+    rng = np.random.default_rng(0)
+    with KrylovContext(n, 64) as ctx:
+        with pytest.raises(nat.SpisError) as err:
+            ctx.op_orth_mid(rng.standard_normal((m, n)), rng.standard_normal(n), rng.standard_normal(m))
+        assert err.value.code == nat.E_UNSUPPORTED
+
+
+@pytest.mark.parametrize("stages", [2, 3, 8])
+def test_orth_mid_ring_depths(stages):
+    n, m = 1_000_003, 5
+    rng = np.random.default_rng(3)
+    V = rng.standard_normal((m, n)); w = rng.standard_normal(n); coef = rng.standard_normal(m)
+    with KrylovContext(n, 8) as ctx:
+        ctx.set_option("orth_mid_max_stages", stages)
+        w1, d1 = ctx.op_orth_mid(V, w, coef)
+    np.testing.assert_allclose(w1, w - coef @ V, rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(d1, V @ w1, rtol=1e-11, atol=1e-9)
+
+
 def test_preconditioner_kernels():
     d, _ = lkdv.linforms(space="CG", M=1000, mlength=800.0)
     A = d["A"]
@@ -173,6 +219,6 @@ def test_bench_kernel_entry_point():
     n = d["A"].shape[0]
     with KrylovContext(n, 8) as ctx:
         ctx.upload_matrix(nat.SLOT_A, d["A"])
-        for cls in (nat.PROF_SPMV, nat.PROF_MDOT, nat.PROF_LINCOMB, nat.PROF_SCALE):
+        for cls in (nat.PROF_SPMV, nat.PROF_MDOT, nat.PROF_LINCOMB, nat.PROF_SCALE, nat.PROF_ORTHMID):
             ms, by = ctx.bench_kernel(cls, 6, reps=3)
             assert ms > 0 and by > 0

@@ -54,6 +54,28 @@ def test_conserved_quantities_at_reference_level(golden):
         assert abs(inv[key] - target) <= 10 * abs(ref[key] - target) + 1e-13 * mag
 
 
+def test_fused_and_unfused_cgs2_agree():
+    """orth_fused=1 (TMA-staged one-pass middle of CGS2) vs the two-kernel path: same iteration count,
+    solutions equal to rounding."""
+    spec, dic, prob, x0, pre = cases.instantiate("lkdv_cg_tol8_n1500")
+    cl = wrappers.lkdv.conlist(dic, x0)
+    out = []
+    for fused in (1, 0):
+        sess = solvers.DeviceSession(dic["A"], dic["b"], x0, 50, conlist=cl, profile=True)
+        sess.ctx.set_option("orth_fused", fused)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            x, info = solvers.cgmres(dic["A"], dic["b"], x0, 50, tol=1e-8, conlist=cl, session=sess)
+        prof = sess.ctx.profile()
+        assert (prof["orthmid"]["launches"] > 0) == bool(fused)
+        out.append((x, info["steps"], np.array(info["res"])))
+        sess.close()
+    assert out[0][1] == out[1][1]
+    # h2 is summed in a different order, and this case's SLSQP solves amplify rounding (self_noise.json)
+    assert helpers.rel_diff(out[0][0], out[1][0]) <= tolerance("lkdv_cg_tol8_n1500")
+    np.testing.assert_allclose(out[0][2], out[1][2], rtol=1e-5)
+
+
 def test_session_reuse_and_profile():
     spec, dic, prob, x0, pre = cases.instantiate("lkdv_cg_tol8_n1500")
     cl = wrappers.lkdv.conlist(dic, x0)
