@@ -35,20 +35,52 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 K_KRYLOV = 50
-TOL = 1e-6
 CONTOL = 10
+TOL = 1e-6                       # default workload (lkdv); WORKLOADS[...]["tol"] is what the code uses
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on
+    "lkdv": dict(tol=1e-6, label="lkdv P1 periodic linear KdV", cons="mass+energy"),
+    # configs[2] / configs[4]: swe/TimedSolve.py:17 tolerance, RT_2 x DG_0 on the periodic square
+    "swe": dict(tol=1e-7, label="swe RT2xDG0 linearised rotating shallow water", cons="mass+energy"),
+}
 
 
 # ------------------------------------------------------------------------------------------------
-def build_system(n_target):
+def build_system(n_target, workload="lkdv", rank=0, world=1):
+    """Returns (dic, x0, conlist, part).  world == 1: the global system.  world > 1: THIS RANK'S rows
+    (global column ids) -- lkdv slices the global matrix, swe assembles its strip directly."""
     from structurepreservingiterativesolvers_b200 import wrappers
-    from structurepreservingiterativesolvers_b200.problems import lkdv
-    M = lkdv.benchmark_size(n_target)
-    dic, prob = lkdv.linforms(space="CG", M=M, mlength=0.8 * M)
+    if workload == "lkdv":
+        from structurepreservingiterativesolvers_b200.problems import lkdv
+        M = lkdv.benchmark_size(n_target)
+        dic, prob = lkdv.linforms(space="CG", M=M, mlength=0.8 * M)
+        x0 = np.zeros(dic["b"].size)
+        full = wrappers.lkdv.conlist(dic, x0)
+        conlist = [full[0], full[2]]                       # mass + energy (BASELINE.json configs[1])
+        part = None
+        if world > 1:
+            from structurepreservingiterativesolvers_b200.partition import FieldBlockPartition
+            part = FieldBlockPartition(3, dic["b"].size // 3, world)
+            ids = part.global_ids(rank)
+            glob = dict(n=int(dic["b"].size), nnz=int(dic["A"].nnz))
+            dic = {"A": dic["A"][ids], "b": dic["b"][ids], **glob}
+            x0 = x0[ids]
+            conlist = [type(c)(c.M.tocsr()[ids], np.asarray(c.v, dtype=np.float64).reshape(-1)[ids], c.c, c.name) for c in conlist]
+        return dic, x0, conlist, part
+    from structurepreservingiterativesolvers_b200.problems import swe
+    M = swe.benchmark_size(n_target)
+    part = None
+    rows = None
+    if world > 1:
+        from structurepreservingiterativesolvers_b200.partition import StripPartition
+        part = StripPartition((swe.NU * M, swe.NR * M), M, world)
+        rows = part.block_range(rank)
+    dic, prob = swe.linforms(M=M, mlength=0.8 * M, rows=rows, sort=False)
+    dic["n"] = 12 * M * M
+    dic["nnz"] = int(12.5 * 12 * M * M)
     x0 = np.zeros(dic["b"].size)
-    full = wrappers.lkdv.conlist(dic, x0)
-    conlist = [full[0], full[2]]                       # mass + energy (BASELINE.json configs[1])
-    return dic, x0, conlist
+    conlist = wrappers.swe.conlist(dic, x0)                # mass + energy (swe/LinearSolver.py:23-36)
+    return dic, x0, conlist, part
 
 
 def pin_inputs(dic, x0, conlist):
@@ -170,7 +202,7 @@ def peak_hbm():
 
 
 # ------------------------------------------------------------------------------------------------
-def time_oracle(dic, x0, conlist, k_sample):
+def time_oracle(dic, x0, conlist, k_sample, tol=TOL):
     """Reference algorithm (numpy/scipy oracle port) on the host cores: a bounded sample of the same
     workload -- the first `k_sample` Krylov iterations of the same call (k = k_sample makes the last
     one constrained, exactly like iteration 50 of the full run)."""
@@ -178,7 +210,7 @@ def time_oracle(dic, x0, conlist, k_sample):
     t0 = time.perf_counter()
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        x, info = orc.cgmres(dic["A"], dic["b"], x0, k_sample, tol=TOL, contol=CONTOL, conlist=conlist, timing=True)
+        x, info = orc.cgmres(dic["A"], dic["b"], x0, k_sample, tol=tol, contol=CONTOL, conlist=conlist, timing=True)
     dt = time.perf_counter() - t0
     return info["steps"] / dt, dt, info
 
@@ -195,13 +227,14 @@ def run_reference(args):
     rank, world, local = dist_env()
     if rank != 0:
         return
-    dic, x0, conlist = build_system(args.n)
+    tol = WORKLOADS[args.workload]["tol"]
+    dic, x0, conlist, _ = build_system(args.n, args.workload)
     k_sample = args.cpu_sample_iters
     for _ in range(min(args.warmup, 1)):
-        time_oracle(dic, x0, conlist, 1)
+        time_oracle(dic, x0, conlist, 1, tol)
     its, secs = 0, 0.0
     for _ in range(args.steps):
-        rate, dt, info = time_oracle(dic, x0, conlist, k_sample)
+        rate, dt, info = time_oracle(dic, x0, conlist, k_sample, tol)
         its += info["steps"]; secs += dt
     value = its / secs
     sample = (f"first {k_sample} of {K_KRYLOV} Krylov iterations of the same cgmres call (n={dic['b'].size}, "
@@ -210,7 +243,7 @@ def run_reference(args):
         "impl": "reference", "metric": "krylov_iters_per_s", "value": value, "unit": "it/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(dic, "cpu"),
+        "config": workload_config(args.workload, dic, "cpu"),
         "cpu_baseline": {"value": value, "unit": "it/s", "cores": blas_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -218,11 +251,14 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(dic, where):
-    return {"workload": f"lkdv P1 periodic linear KdV, n={dic['b'].size}, nnz={dic['A'].nnz}, "
-                        f"cgmres k={K_KRYLOV} tol={TOL:g} contol={CONTOL} mass+energy constraints, x0=0, no preconditioner",
-            "n": int(dic["b"].size), "nnz": int(dic["A"].nnz), "k": K_KRYLOV,
-            "l2": "working set (basis 4 GB + matrix 0.8 GB) >> 126 MB L2: no flush between iterations",
+def workload_config(workload, dic, where):
+    w = WORKLOADS[workload]
+    n = int(dic.get("n", dic["b"].size))
+    nnz = int(dic.get("nnz", dic["A"].nnz))
+    return {"workload": f"{w['label']}, n={n}, nnz={nnz}, cgmres k={K_KRYLOV} tol={w['tol']:g} contol={CONTOL} "
+                        f"{w['cons']} constraints, x0=0, no preconditioner",
+            "n": n, "nnz": nnz, "k": K_KRYLOV,
+            "l2": f"working set (basis {8e-9 * (K_KRYLOV + 1) * n:.1f} GB + matrix {12e-9 * nnz:.1f} GB) >> 126 MB L2: no flush between iterations",
             "where": where}
 
 
@@ -236,23 +272,17 @@ def run_ours(args):
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    dic, x0, conlist = build_system(args.n)
+    tol = WORKLOADS[args.workload]["tol"]
+    dic, x0, conlist, part = build_system(args.n, args.workload, rank, world)
     A, b = dic["A"], dic["b"]
-    n = b.size
+    n = int(dic.get("n", b.size))
     engine = args.small_solver
-    comm = part = None
+    comm = None
     if world > 1:
-        # strong scaling: the SAME system, row-sharded by mesh block (each rank owns the same node
-        # range of every field), NVLink peer-memory collectives inside the kernels
+        # strong scaling: the SAME system, row-sharded by mesh block (each rank owns the same mesh range
+        # of every field), NVLink peer-memory collectives inside the kernels
         from structurepreservingiterativesolvers_b200.distributed import DistributedSession, TorchComm
-        from structurepreservingiterativesolvers_b200.partition import FieldBlockPartition
         comm = TorchComm(device=local)
-        part = FieldBlockPartition(3, n // 3, world)
-        ids = part.global_ids(rank)
-        A = dic["A"][ids]
-        b = dic["b"][ids]
-        x0 = x0[ids]
-        conlist = [type(c)(c.M.tocsr()[ids], np.asarray(c.v, dtype=np.float64).reshape(-1)[ids], c.c, c.name) for c in conlist]
 
     def make_session(mats=None, profile=False):
         Ax, bx, x0x, cl = mats if mats is not None else (A, b, x0, conlist)
@@ -269,7 +299,7 @@ def run_ours(args):
                 session = make_session(mats)            # end-to-end: uploads happen inside the timed call
             # timing=True: the reference's TimedSolve protocol and the survey's 0.27 it/s measurement;
             # it also skips the absolute 1e-12 violation check (solvers.py:266, quirk Q6)
-            return solvers.cgmres(Ax, bx, x0x, K_KRYLOV, tol=TOL, contol=CONTOL, conlist=cl, timing=True,
+            return solvers.cgmres(Ax, bx, x0x, K_KRYLOV, tol=tol, contol=CONTOL, conlist=cl, timing=True,
                                   small_solver=eng, session=session, device=local)
 
     def barrier():
@@ -382,7 +412,7 @@ def run_ours(args):
     # ---- CPU baseline: the oracle port on this box's host cores (bounded sample) -----------------
     cpu = None
     if not args.skip_cpu and world == 1:
-        rate, dt, cinfo = time_oracle(dic, x0, conlist, args.cpu_sample_iters)   # world == 1: global system
+        rate, dt, cinfo = time_oracle(dic, x0, conlist, args.cpu_sample_iters, tol)   # world == 1: global system
         cpu = {"value": rate, "unit": "it/s", "cores": blas_threads(), "kind": "port",
                "sample": (f"first {args.cpu_sample_iters} of {K_KRYLOV} Krylov iterations of the same cgmres call "
                           f"(n={n}, last one constrained), {dt:.1f} s; early iterations are the cheapest, so this favours the CPU")}
@@ -391,7 +421,7 @@ def run_ours(args):
         "metric": "krylov_iters_per_s", "value": value, "unit": "it/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": dict(workload_config(dic, "1 B200 per rank"), small_solver=engine,
+        "config": dict(workload_config(args.workload, dic, "1 B200 per rank"), small_solver=engine,
                        parallelism=("single GPU" if world == 1 else
                                     f"row-sharded over {world} GPUs by mesh block, {sess.transport} transport, halo {sess.plan.n_halo} doubles/rank")),
         "solve_time_s": secs / args.steps, "device_event_ms_per_step": ev_ms / args.steps,
@@ -413,6 +443,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=10_000_000)
+    ap.add_argument("--workload", default="lkdv", choices=sorted(WORKLOADS))
     ap.add_argument("--small-solver", default="kkt", choices=["kkt", "slsqp"])
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample-iters", type=int, default=8)

@@ -74,6 +74,51 @@ class FieldBlockPartition:
         return int(self.nfields * (self.starts[r + 1] - self.starts[r]))
 
 
+class StripPartition:
+    """Several fields of DIFFERENT densities over the same `nblocks` mesh blocks (2-D strips).
+
+    Field f stores block_sizes[f] unknowns per mesh block, block-major; global index =
+    field_off[f] + block*block_sizes[f] + within.  Rank r owns blocks [starts[r], starts[r+1]) of
+    every field; its local order is field-blocked again.  swe (problems/swe.py): mesh block = one
+    row of squares, block_sizes = (10 M, 2 M) for (velocity, density); FieldBlockPartition is the
+    special case block_sizes = (1, ..., 1)."""
+
+    def __init__(self, block_sizes, nblocks, P):
+        self.bs = np.asarray(block_sizes, dtype=np.int64)
+        self.nblocks, self.P = int(nblocks), int(P)
+        self.field_off = np.concatenate([[0], np.cumsum(self.bs * self.nblocks)]).astype(np.int64)
+        self.n = int(self.field_off[-1])
+        self.starts = (np.arange(self.P + 1, dtype=np.int64) * self.nblocks) // self.P
+
+    def _decode(self, g):
+        g = np.asarray(g, dtype=np.int64)
+        f = np.searchsorted(self.field_off, g, side="right") - 1
+        loc = g - self.field_off[f]
+        return f, loc // self.bs[f], loc % self.bs[f]
+
+    def owner_of(self, g):
+        _, blk, _ = self._decode(g)
+        return np.searchsorted(self.starts, blk, side="right") - 1
+
+    def local_of(self, g):
+        f, blk, within = self._decode(g)
+        r = np.searchsorted(self.starts, blk, side="right") - 1
+        width = self.starts[r + 1] - self.starts[r]
+        before = np.concatenate([[0], np.cumsum(self.bs)])[f]          # unknowns per block of earlier fields
+        return before * width + (blk - self.starts[r]) * self.bs[f] + within
+
+    def global_ids(self, r):
+        b0, b1 = self.starts[r], self.starts[r + 1]
+        return np.concatenate([self.field_off[f] + np.arange(b0 * self.bs[f], b1 * self.bs[f], dtype=np.int64)
+                               for f in range(self.bs.size)])
+
+    def n_local(self, r):
+        return int(self.bs.sum() * (self.starts[r + 1] - self.starts[r]))
+
+    def block_range(self, r):
+        return int(self.starts[r]), int(self.starts[r + 1])
+
+
 class HaloPlan:
     """Ghost layout of one rank: ghost global ids ordered by (owner, id), counts per source rank;
     the send side (send_idx, send_counts) is filled in after the ranks have exchanged requests."""

@@ -379,10 +379,15 @@ class IterateHistory(collections.abc.Sequence):
 class _Arnoldi:
     """Feeds Hessenberg columns to the solvers; hides launch/wait lookahead (solvers.py:190-198)."""
 
-    def __init__(self, sess, k, lookahead):
+    def __init__(self, sess, k, lookahead, beta=None):
         self.sess, self.k, self.lookahead = sess, k, bool(lookahead)
         self.H = np.zeros((k + 1, k))
         self._inflight = None
+        # Givens recurrence of the unconstrained least-squares residual |beta e1 - H y|_min: used only
+        # to decide whether launching the NEXT Arnoldi step ahead of time can be wasted work
+        self._cs = np.zeros(k)
+        self._sn = np.zeros(k)
+        self._g = None if beta is None else float(beta)
 
     def column(self, j):
         if self._inflight != j:
@@ -390,7 +395,31 @@ class _Arnoldi:
         col = self.sess.arnoldi_wait(j)
         self._inflight = None
         self.H[: j + 2, j] = col
+        if self._g is not None:
+            r = np.array(col, dtype=np.float64)
+            for i in range(j):
+                a, b = r[i], r[i + 1]
+                r[i] = self._cs[i] * a + self._sn[i] * b
+                r[i + 1] = -self._sn[i] * a + self._cs[i] * b
+            den = np.hypot(r[j], r[j + 1])
+            if den > 0:
+                self._cs[j], self._sn[j] = r[j] / den, r[j + 1] / den
+                self._g = -self._sn[j] * self._g
+            else:
+                self._g = None
         return col
+
+    def ls_residual(self):
+        """min_y |beta e1 - H_j y| after the last column() (inf when not tracked)."""
+        return np.inf if self._g is None else abs(self._g)
+
+    def predicted_residual(self, y, beta):
+        """|beta e1 - H_j y| for a given coefficient vector: the residual the device will report for
+        x0 + Z y up to rounding (Arnoldi relation A Z = V H)."""
+        m = len(y)
+        r = -(self.H[: m + 1, :m] @ y)
+        r[0] += beta
+        return float(np.linalg.norm(r))
 
     def prefetch(self, j):
         if self.lookahead and j < self.k and self._inflight is None:
@@ -445,8 +474,8 @@ def gmres(A, b, x0, k, tol=1e-50, pre=None, *, session=None, lookahead=None, his
           device=None, orth=None, small_solver=None):
     """Right-preconditioned flexible GMRES; returns (x_last, {'name','x','res','steps'})."""
     sess = _acquire(session, A, b, x0, k, (), pre, device, orth)
-    arn = _Arnoldi(sess, k, _opt("lookahead", lookahead))
     beta = sess.begin()                                   # r0, ||r0||, q0       (solvers.py:78-88)
+    arn = _Arnoldi(sess, k, _opt("lookahead", lookahead), beta)
     hist = IterateHistory(sess)
     residual = [beta]
     steps = 0
@@ -457,7 +486,8 @@ def gmres(A, b, x0, k, tol=1e-50, pre=None, *, session=None, lookahead=None, his
         if not col[j + 1] != 0:
             warnings.warn(_BREAKDOWN)                     # (solvers.py:104-106)
             break
-        arn.prefetch(j + 1)
+        if not arn.ls_residual() < tol:                   # this step cannot be the last: run ahead
+            arn.prefetch(j + 1)
         yk = smallsolve.lstsq(arn.H[: j + 2, : j + 1], beta).x        # (solvers.py:113)
         residual.append(sess.ctx.iterate_residual(yk))    # x_j and ||A x_j - b|| (solvers.py:115-116)
         hist._append(yk)
@@ -491,9 +521,9 @@ def cgmres(A, b, x0, k, tol=1e-8, contol=10, conlist=[], pre=None, timing=None, 
                "start_constraints": [], "end_constraints": []}
     tr = _Trace()
     sess = _acquire(session, A, b, x0, k, conlist, pre, device, orth)
-    arn = _Arnoldi(sess, k, _opt("lookahead", lookahead))
     safety = None                                         # (solvers.py:163)
     beta = sess.begin()
+    arn = _Arnoldi(sess, k, _opt("lookahead", lookahead), beta)
     tr("cgmres: session + r0")
     hist = IterateHistory(sess)
     residual = [beta]
@@ -528,8 +558,16 @@ def cgmres(A, b, x0, k, tol=1e-8, contol=10, conlist=[], pre=None, timing=None, 
                 bk.mark("constraint terms")
                 if timing:
                     jit["end_constraints"].append(time())
-                arn.prefetch(j + 1)
+                # The loop can only end in this branch (solvers.py:296).  If even the unconstrained
+                # minimiser is above tol it will not end now, so the next Arnoldi step is launched
+                # before the host solve; otherwise wait for y and launch only if the residual it
+                # implies says the loop goes on (a wrong guess costs overlap, never correctness).
+                may_end = arn.ls_residual() < tol
+                if not may_end:
+                    arn.prefetch(j + 1)
                 res = _constrained(engine, Hj, beta, y0, cons, ctol ** 2, None)   # (solvers.py:251-255)
+                if may_end and not arn.predicted_residual(res.x, beta) < tol:
+                    arn.prefetch(j + 1)
                 if not timing and np.isnan(max(res.x)):
                     raise ValueError("constrained solve returned NaN")           # (solvers.py:258-260)
                 safety = True

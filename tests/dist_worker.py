@@ -18,9 +18,9 @@ from fake_ctx import FakeKrylovContext  # noqa: E402
 from structurepreservingiterativesolvers_b200 import solvers, wrappers  # noqa: E402
 from structurepreservingiterativesolvers_b200.distributed import (DistributedSession, TorchComm,  # noqa: E402
                                                                   cgmres_distributed, gmres_distributed)
-from structurepreservingiterativesolvers_b200.partition import ArrayPartition, FieldBlockPartition, take_rows  # noqa: E402
+from structurepreservingiterativesolvers_b200.partition import ArrayPartition, FieldBlockPartition, StripPartition, take_rows  # noqa: E402
 from structurepreservingiterativesolvers_b200.preconditioners import JacobiPreconditioner  # noqa: E402
-from structurepreservingiterativesolvers_b200.problems import heat, lkdv  # noqa: E402
+from structurepreservingiterativesolvers_b200.problems import heat, lkdv, swe  # noqa: E402
 
 
 class Inv:
@@ -85,6 +85,26 @@ def main():
                                   session=DistributedSession(take_rows(h["A"], part, rank), h["b"][ids], x0[ids], 15, part, comm,
                                                              ctx_factory=FakeKrylovContext))
     checks.append(("gmres x", np.linalg.norm(xd - xs) <= 1e-10 * np.linalg.norm(xs)))
+
+    # ---- case 4: swe RT_2 x DG_0, strips of squares, every rank assembles ONLY its own rows
+    Ms = 10
+    dg, _ = swe.linforms(M=Ms, mlength=0.8 * Ms)
+    x0 = np.zeros(dg["b"].size)
+    clg = wrappers.swe.conlist(dg, x0)
+    xs, infos = solvers.cgmres(dg["A"], dg["b"], x0, 40, tol=1e-7, conlist=clg, small_solver="kkt",
+                               session=solvers.DeviceSession(dg["A"], dg["b"], x0, 40, conlist=clg, ctx_factory=FakeKrylovContext))
+    part = StripPartition((swe.NU * Ms, swe.NR * Ms), Ms, world)
+    dl, _ = swe.linforms(M=Ms, mlength=0.8 * Ms, rows=part.block_range(rank))
+    x0l = np.zeros(dl["b"].size)
+    cll = wrappers.swe.conlist(dl, x0l)
+    dsess = DistributedSession(dl["A"], dl["b"], x0l, 40, part, comm, conlist=cll, ctx_factory=FakeKrylovContext)
+    xd, infod = cgmres_distributed(None, dl["b"], x0l, 40, part, comm, tol=1e-7, conlist=cll, gather=True,
+                                   small_solver="kkt", session=dsess)
+    inv = swe.compute_invariants(dg, xd)
+    checks.append(("swe steps", infod["steps"] == infos["steps"]))
+    checks.append(("swe x", np.linalg.norm(xd - xs) <= 1e-9 * np.linalg.norm(xs)))
+    checks.append(("swe invariants", abs(inv["mass"] - dg["m0"]) <= 1e-11 * abs(dg["m0"]) and abs(inv["energy"] - dg["e0"]) <= 1e-11 * abs(dg["e0"])))
+    checks.append(("swe halo is a strip boundary", world == 1 or 0 < dsess.plan.n_halo <= 2 * 12 * Ms))
 
     bad = [name for name, ok in checks if not ok]
     print(f"rank {rank}/{world}: {len(checks) - len(bad)} ok, failed: {bad}", flush=True)

@@ -10,7 +10,7 @@ import numpy as np
 import scipy.sparse as sps
 import scipy.sparse.linalg as spsla
 
-from structurepreservingiterativesolvers_b200.problems import heat, lkdv, lkdvRK
+from structurepreservingiterativesolvers_b200.problems import heat, lkdv, lkdvRK, swe
 
 
 def _lkdv(space, M, fixed_h=False, **kw):
@@ -44,6 +44,13 @@ CASES = {
     # swe wrapper (mass + energy) with an ILU object exposing .solve (swe/TimedSolve.py:23)
     "swe_like_ilu": dict(exp="swe", build=lambda: _swe_wrap(_lkdv("CG", 100, fixed_h=True)), kind="cgmres", k=20, tol=1e-7, pre="ilu"),
     "swe_like_tol7": dict(exp="swe", build=lambda: _swe_wrap(_lkdv("CG", 100, fixed_h=True)), kind="cgmres", k=40, tol=1e-7),
+    # cfg3: swe RT_2 x DG_0 re-assembly (problems/swe.py), the calls of swe/TimedSolve.py:17-41 (M = 2**3,
+    # tol = 1e-7, k = 20, spilu(drop_tol=1e-2)) and swe/SingleSolve.py:16-37 (tol = 1e-50 -> prototypical)
+    "swe_rt_tol7": dict(exp="swe", build=lambda: swe.linforms(M=8), kind="cgmres", k=20, tol=1e-7),
+    "swe_rt_tol7_ilu": dict(exp="swe", build=lambda: swe.linforms(M=8), kind="cgmres", k=20, tol=1e-7, pre="ilu_swe", timing=True),
+    "swe_rt_gmres_ilu": dict(exp="swe", build=lambda: swe.linforms(M=8), kind="gmres", k=20, tol=1e-7, pre="ilu_swe"),
+    "swe_rt_proto": dict(exp="swe", build=lambda: swe.linforms(M=12), kind="cgmres", k=20, tol=1e-50),
+    "swe_rt_h08_n10800": dict(exp="swe", build=lambda: swe.linforms(M=30, mlength=24.0), kind="cgmres", k=40, tol=1e-7),
     # lkdvRK: dict-form callbacks, non-zero initial guess, ILU preconditioner (lkdvRK/Evolve.py:51-61)
     "lkdvrk_tol6": dict(exp="lkdvRK", build=lambda: lkdvRK.linforms(M=20), kind="cgmres", k=30, tol=1e-6, contol=10, x0="stage", pre="ilu"),
     "lkdvrk_proto": dict(exp="lkdvRK", build=lambda: lkdvRK.linforms(M=10), kind="cgmres", k=8, tol=1e-50, x0="stage"),
@@ -64,6 +71,8 @@ def make_pre(spec, A):
         return sps.diags(1.0 / A.diagonal())            # taken through `pre @ vec` (solvers.py:156-161)
     if spec == "ilu":
         return spsla.spilu(A.tocsc(), drop_tol=1e-4, fill_factor=10)    # lkdvRK/SingleSolve.py:19
+    if spec == "ilu_swe":
+        return spsla.spilu(A.tocsc(), drop_tol=1e-2, fill_factor=10)    # swe/TimedSolve.py:23-24
     raise KeyError(spec)
 
 

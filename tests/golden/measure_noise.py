@@ -70,7 +70,7 @@ def main():
                 cl = wrap.conlist(d2, x0, prob) if spec["exp"] == "lkdvRK" else wrap.conlist(d2, x0)
             x = _solve(spec, A, b, x0, cl, cases.make_pre(spec.get("pre"), A))
             samples.append(("ulp", helpers.rel_diff(x, ref)))
-            if spec["exp"] != "lkdvRK" and spec.get("pre") != "ilu":
+            if spec["exp"] != "lkdvRK" and spec.get("pre") not in ("ilu", "ilu_swe"):
                 p = rng.permutation(n)
                 P = sps.csr_matrix((np.ones(n), (np.arange(n), p)), shape=(n, n))
                 Ap = (P @ dic["A"] @ P.T).tocsr()

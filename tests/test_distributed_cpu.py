@@ -8,9 +8,9 @@ import numpy as np
 import pytest
 import scipy.sparse as sps
 
-from structurepreservingiterativesolvers_b200.partition import (ArrayPartition, FieldBlockPartition, localize,
-                                                                take_rows)
-from structurepreservingiterativesolvers_b200.problems import heat, lkdv
+from structurepreservingiterativesolvers_b200.partition import (ArrayPartition, FieldBlockPartition, StripPartition,
+                                                                localize, take_rows)
+from structurepreservingiterativesolvers_b200.problems import heat, lkdv, swe
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -35,11 +35,46 @@ def test_field_block_partition_is_a_bijection(P):
     assert max(sizes) - min(sizes) <= 3                              # balanced to one node per field
 
 
+@pytest.mark.parametrize("P", [1, 2, 3, 5])
+def test_strip_partition_matches_swe_numbering(P):
+    M = 7
+    part = StripPartition((swe.NU * M, swe.NR * M), M, P)
+    assert part.n == 12 * M * M
+    seen = np.concatenate([part.global_ids(r) for r in range(P)])
+    assert sorted(seen) == list(range(part.n))
+    for r in range(P):
+        g = part.global_ids(r)
+        np.testing.assert_array_equal(g, swe.strip_ids(M, *part.block_range(r)))     # what linforms(rows=...) assembles
+        assert np.all(part.owner_of(g) == r)
+        np.testing.assert_array_equal(part.local_of(g), np.arange(g.size))
+        assert part.n_local(r) == g.size
+    fb, sp = FieldBlockPartition(3, 11, P), StripPartition((1, 1, 1), 11, P)
+    for r in range(P):
+        np.testing.assert_array_equal(fb.global_ids(r), sp.global_ids(r))
+
+
+def test_swe_rows_assembled_locally_equal_global_rows():
+    M, P = 9, 4
+    d, _ = swe.linforms(M=M, mlength=0.8 * M)
+    part = StripPartition((swe.NU * M, swe.NR * M), M, P)
+    for r in range(P):
+        dl, _ = swe.linforms(M=M, mlength=0.8 * M, rows=part.block_range(r))
+        ids = part.global_ids(r)
+        assert abs(dl["A"] - d["A"][ids]).max() == 0 and abs(dl["L"] - d["L"][ids]).max() == 0
+        np.testing.assert_array_equal(dl["b"], d["b"][ids])
+        np.testing.assert_array_equal(dl["omega"], d["omega"][ids])
+        assert dl["m0"] == d["m0"] and dl["e0"] == d["e0"]
+        # a strip needs one row of squares from each neighbouring strip: its halo is O(M), not O(M^2)
+        (A_loc,), plan = localize([dl["A"]], part, r)
+        assert 0 < plan.n_halo <= 2 * 12 * M
+
+
 @pytest.mark.parametrize("P", [2, 4])
 def test_localized_spmv_reproduces_global_product(P):
     """Emulate the halo exchange in-process: every rank's local matrix times [owned | ghosts]."""
     for A, part in ((lkdv.linforms(space="CG", M=40)[0]["A"], FieldBlockPartition(3, 40, P)),
-                    (heat.linforms(M=9)[0]["A"], ArrayPartition(np.arange(100) % P, P))):
+                    (heat.linforms(M=9)[0]["A"], ArrayPartition(np.arange(100) % P, P)),
+                    (swe.linforms(M=8)[0]["A"], StripPartition((swe.NU * 8, swe.NR * 8), 8, P))):
         n = A.shape[0]
         rng = np.random.default_rng(0)
         x = rng.standard_normal(n)

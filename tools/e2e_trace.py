@@ -2,7 +2,7 @@ import os, sys, time, warnings
 sys.path.insert(0, '/root/repo')
 import bench
 from structurepreservingiterativesolvers_b200 import solvers
-dic, x0, conlist = bench.build_system(10_000_000)
+dic, x0, conlist, _ = bench.build_system(10_000_000)
 mats = bench.pin_inputs(dic, x0, conlist)
 warnings.simplefilter("ignore")
 for rep in range(4):

@@ -2,7 +2,7 @@ import os, sys, time, warnings
 sys.path.insert(0, '/root/repo')
 import bench
 from structurepreservingiterativesolvers_b200 import solvers
-dic, x0, conlist = bench.build_system(10_000_000)
+dic, x0, conlist, _ = bench.build_system(10_000_000)
 sess = solvers.DeviceSession(dic["A"], dic["b"], x0, 50, conlist=conlist)
 warnings.simplefilter("ignore")
 def solve():

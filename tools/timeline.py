@@ -13,7 +13,7 @@ def T(label, fn, *a, **k):
     print(f"{label:40s} {dt*1e3:9.2f} ms", flush=True)
     return out
 
-dic, x0, conlist = bench.build_system(int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000)
+dic, x0, conlist, _ = bench.build_system(int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000)
 A, b = dic["A"], dic["b"]; n = b.size
 pinned = bench.pin_inputs(dic, x0, conlist)
 for label, (Ax, bx, x0x, cl) in (("pageable", (A, b, x0, conlist)), ("pinned", pinned)):
