@@ -73,7 +73,8 @@ def test_fused_and_unfused_cgs2_agree():
     assert out[0][1] == out[1][1]
     # h2 is summed in a different order, and this case's SLSQP solves amplify rounding (self_noise.json)
     assert helpers.rel_diff(out[0][0], out[1][0]) <= tolerance("lkdv_cg_tol8_n1500")
-    np.testing.assert_allclose(out[0][2], out[1][2], rtol=1e-5)
+    # residual norms differ by rounding relative to |b|, which is ~1e-5 of the last (1e-8-sized) entries
+    np.testing.assert_allclose(out[0][2], out[1][2], rtol=1e-4, atol=1e-12 * np.linalg.norm(dic["b"]))
 
 
 def test_session_reuse_and_profile():

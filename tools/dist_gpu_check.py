@@ -2,7 +2,9 @@
 """Multi-GPU parity check (torchrun, NCCL): row-sharded CGMRES vs the single-GPU solve.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
-        tools/dist_gpu_check.py [n_target]
+        tools/dist_gpu_check.py [n_target] [transport] [lkdv|swe]
+
+swe: every rank assembles only its own strip of the RT_2 x DG_0 system (problems/swe.py rows=...).
 """
 import os
 import sys
@@ -18,8 +20,8 @@ sys.path.insert(0, ROOT)
 
 from structurepreservingiterativesolvers_b200 import solvers, wrappers  # noqa: E402
 from structurepreservingiterativesolvers_b200.distributed import DistributedSession, TorchComm, cgmres_distributed  # noqa: E402
-from structurepreservingiterativesolvers_b200.partition import FieldBlockPartition  # noqa: E402
-from structurepreservingiterativesolvers_b200.problems import lkdv  # noqa: E402
+from structurepreservingiterativesolvers_b200.partition import FieldBlockPartition, StripPartition  # noqa: E402
+from structurepreservingiterativesolvers_b200.problems import lkdv, swe  # noqa: E402
 
 
 class Inv:
@@ -35,22 +37,40 @@ def main():
     rank, world = comm.rank, comm.world
     warnings.simplefilter("ignore")
     n_target = int(sys.argv[1]) if len(sys.argv) > 1 else 300_000
-    M = lkdv.benchmark_size(n_target)
-    d, _ = lkdv.linforms(space="CG", M=M, mlength=0.8 * M)
-    n = d["b"].size
-    x0 = np.zeros(n)
-    cl = wrappers.lkdv.conlist(d, x0)
-    tol = 1e-6 * np.sqrt(n / 150)
-    part = FieldBlockPartition(3, M, world)
-    ids = part.global_ids(rank)
-    cl_loc = [Inv(c.M.tocsr()[ids], np.asarray(c.v).reshape(-1)[ids], c.c) for c in cl]
+    workload = sys.argv[3] if len(sys.argv) > 3 else "lkdv"
+    if workload == "swe":
+        M = swe.benchmark_size(n_target)
+        part = StripPartition((swe.NU * M, swe.NR * M), M, world)
+        dl, _ = swe.linforms(M=M, mlength=0.8 * M, rows=part.block_range(rank))
+        ids = part.global_ids(rank)
+        n = 12 * M * M
+        tol = 1e-7
+        cl_loc = wrappers.swe.conlist(dl, np.zeros(dl["b"].size))
+        A_loc, b_loc, x0_loc = dl["A"], dl["b"], np.zeros(dl["b"].size)
+        problem_mod = swe
+        if rank == 0:
+            d, _ = swe.linforms(M=M, mlength=0.8 * M)
+            x0 = np.zeros(n)
+            cl = wrappers.swe.conlist(d, x0)
+    else:
+        M = lkdv.benchmark_size(n_target)
+        d, _ = lkdv.linforms(space="CG", M=M, mlength=0.8 * M)
+        n = d["b"].size
+        x0 = np.zeros(n)
+        cl = wrappers.lkdv.conlist(d, x0)
+        tol = 1e-6 * np.sqrt(n / 150)
+        part = FieldBlockPartition(3, M, world)
+        ids = part.global_ids(rank)
+        cl_loc = [Inv(c.M.tocsr()[ids], np.asarray(c.v).reshape(-1)[ids], c.c) for c in cl]
+        A_loc, b_loc, x0_loc = d["A"][ids], d["b"][ids], x0[ids]
+        problem_mod = lkdv
     transport = sys.argv[2] if len(sys.argv) > 2 else "auto"
-    sess = DistributedSession(d["A"][ids], d["b"][ids], x0[ids], 50, part, comm, conlist=cl_loc, profile=True,
+    sess = DistributedSession(A_loc, b_loc, x0_loc, 50, part, comm, conlist=cl_loc, profile=True,
                               transport=transport)
     for rep in range(3):
         dist.barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
-        x_loc, info = cgmres_distributed(None, d["b"][ids], x0[ids], 50, part, comm, tol=tol, contol=10, conlist=cl_loc,
+        x_loc, info = cgmres_distributed(None, b_loc, x0_loc, 50, part, comm, tol=tol, contol=10, conlist=cl_loc,
                                          small_solver="kkt", timing=True, session=sess)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
@@ -65,8 +85,8 @@ def main():
         print("single-GPU solve %.1f ms, timings %s" % (t_single * 1e3, {k: round(float(v), 5) for k, v in infos["timings"].items()}), flush=True)
         print("sharded timings %s" % {k: round(float(v), 5) for k, v in info["timings"].items()}, flush=True)
         rel = np.linalg.norm(xg - xs) / np.linalg.norm(xs)
-        inv = lkdv.compute_invariants(d, xg)
-        dev = max(abs(inv["mass"] - d["m0"]) / abs(d["m0"]), abs(inv["energy"] - d["e0"]) / max(abs(d["e0"]), abs(d["mo0"])))
+        inv = problem_mod.compute_invariants(d, xg)
+        dev = max(abs(inv["mass"] - d["m0"]) / abs(d["m0"]), abs(inv["energy"] - d["e0"]) / max(abs(d["e0"]), abs(d.get("mo0", 0.0))))
         ok = (info["steps"] == infos["steps"]) and rel <= 1e-10 and dev <= 1e-11
         print(f"world={world} n={n} steps={info['steps']} (single {infos['steps']}) rel.diff={rel:.2e} invariant dev={dev:.2e} "
               f"solve={dt*1e3:.1f} ms transport={sess.transport} collectives={comm.counts} halo={sess.plan.n_halo} -> {'OK' if ok else 'FAIL'}", flush=True)
