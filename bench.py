@@ -402,8 +402,17 @@ def run_ours(args):
     dom = max(classes, key=lambda k: classes[k]["ms"])
     d = classes[dom]
     kernel_ms = sum(v["ms"] for v in classes.values())
+    traffic, traffic_src = None, None
+    try:        # measured DRAM bytes per launch of this kernel class: ncu launch list of one solve of this workload
+        with open(os.path.join(ROOT, "profiles", "traffic_r1.json")) as fh:
+            tr = json.load(fh)[args.workload]
+        if world == 1 and args.n == 10_000_000:
+            traffic, traffic_src = tr[dom]["traffic_bytes_per_launch"], tr["_source"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": d["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": d["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "frac": d["gbs"] / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": d["bytes"] / d["launches"], "peak_source": peak_src,
                 "avg_launch_ms": d["ms"] / d["launches"], "launches": d["launches"],
                 "share_of_kernel_time": d["ms"] / kernel_ms}
     kernels = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,

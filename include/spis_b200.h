@@ -78,14 +78,15 @@ extern "C" {
 #define SPIS_FMT_CSR      2
 
 /* timer classes returned by spis_get_profile (CUDA-event time, algorithmic bytes, launches) */
-#define SPIS_PROF_SPMV     0
+#define SPIS_PROF_SPMV     0   /* system matrix A: A z_j, b - A x0, ||A x_j - b||          */
 #define SPIS_PROF_MDOT     1   /* tall-skinny V^T w                 */
 #define SPIS_PROF_LINCOMB  2   /* w -= V h  and  x = x0 + Z y       */
 #define SPIS_PROF_SCALE    3
 #define SPIS_PROF_PRECOND  4
 #define SPIS_PROF_OTHER    5
 #define SPIS_PROF_ORTHMID  6   /* fused  w -= V h1 ; h2 = V^T w  (middle of CGS2, one pass over V) */
-#define SPIS_PROF_CLASSES  7
+#define SPIS_PROF_SPMV_AUX 7   /* constraint matrices M_c z_j (solvers.py:33)                   */
+#define SPIS_PROF_CLASSES  8
 
 typedef struct spis_ctx spis_ctx;
 
@@ -115,6 +116,10 @@ int         spis_device_trim(void);
 /* host utility: *out = 1 if any of the n doubles is non-zero (multi-threaded scan; used to
  * recognise the explicit-zero constraint matrix `0*A` of lkdv/LinearSolver.py:30)             */
 int         spis_host_any_nonzero(const double* data, size_t n, int* out);
+/* same question, answered where it is cheapest: page-locked host buffers are pulled through a device
+ * scratch block by the copy engine and tested there (no host CPU time; runs on the calling thread's
+ * upload stream), pageable ones are scanned by host threads                                        */
+int         spis_any_nonzero(spis_ctx* ctx, const double* data, size_t n, int* out);
 
 /* ---- uploads ------------------------------------------------------------------------ */
 /* CSR matrix -> device (and SELL-32 conversion on device).  Replaces holding `A`, `pre`
@@ -129,6 +134,12 @@ int spis_upload_vec(spis_ctx* ctx, int which, const double* host, int64_t n);
 int spis_upload_blocks(spis_ctx* ctx, int bs, int64_t nblk, int64_t idx_stride_block,
                        int64_t idx_stride_field, const double* blocks);
 int spis_set_precond(spis_ctx* ctx, int kind);
+/* After spis_thread_use_aux_stream(ctx, 1) the upload entry points above and spis_constraint_define,
+ * when called BY THE SAME HOST THREAD, run on the context's auxiliary CUDA stream: a helper thread can
+ * stage the constraint matrices (only needed at the first constrained step, solvers.py:242-247) while
+ * the main thread already drives the Krylov loop.  (ctx, 0) waits for that stream and switches back.
+ * The helper must finish (join) before the first spis_constraint_terms call.                      */
+int spis_thread_use_aux_stream(spis_ctx* ctx, int on);
 
 /* ---- Krylov loop -------------------------------------------------------------------- */
 /* r0 = b - A x0, beta = ||r0||, q[0] = r0/beta                     (solvers.py:167-177) */
@@ -147,7 +158,7 @@ int spis_form_iterate(spis_ctx* ctx, int m, const double* y);
 
 /* ---- constraint stage (solvers.py:21-36, constraint_container.__init__) ------------- */
 /* class-form constraint c: 1/2 x^T M x + v^T x + cc.  mat_slot < 0: M is identically zero
- * (lkdv/LinearSolver.py:30 `0*A`); v may be NULL (all zero).                            */
+ * (lkdv/LinearSolver.py:30 `0*A`); v may be NULL, and an all-zero v is recognised and dropped.      */
 int spis_constraint_define(spis_ctx* ctx, int c, int mat_slot, const double* v, double cc);
 /* term0 (scalar), term1 (m), term2 (m x m row-major) for Z = z[:m].T, incremental in m:
  * MZ = M@Z (:33), term0 (:34), term1 = v@Z + x0@MZ (:35), term2 = 1/2 Z.T@MZ (:36)      */

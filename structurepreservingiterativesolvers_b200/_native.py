@@ -21,8 +21,8 @@ VEC_B, VEC_X0, VEC_R0, VEC_Q, VEC_Z, VEC_X, VEC_PRE_DIAG, VEC_W = range(8)
 PRE_NONE, PRE_JACOBI, PRE_CSR, PRE_BLOCK, PRE_HOST = range(5)
 ORTH_CGS2, ORTH_CGS1, ORTH_MGS = range(3)
 FMT_AUTO, FMT_SELL, FMT_CSR = range(3)
-PROF_SPMV, PROF_MDOT, PROF_LINCOMB, PROF_SCALE, PROF_PRECOND, PROF_OTHER, PROF_ORTHMID, PROF_CLASSES = range(8)
-PROF_NAMES = ("spmv", "mdot", "lincomb", "scale", "precond", "other", "orthmid")
+PROF_SPMV, PROF_MDOT, PROF_LINCOMB, PROF_SCALE, PROF_PRECOND, PROF_OTHER, PROF_ORTHMID, PROF_SPMV_AUX, PROF_CLASSES = range(9)
+PROF_NAMES = ("spmv", "mdot", "lincomb", "scale", "precond", "other", "orthmid", "spmv_aux")
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64)
 HALO_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p)
@@ -45,12 +45,14 @@ SIGNATURES = {
     "spis_pinned_trim": (C.c_int, []),
     "spis_device_trim": (C.c_int, []),
     "spis_host_any_nonzero": (C.c_int, [_dp, C.c_size_t, C.POINTER(C.c_int)]),
+    "spis_any_nonzero": (C.c_int, [_ctx, _dp, C.c_size_t, C.POINTER(C.c_int)]),
     "spis_set_option": (C.c_int, [_ctx, C.c_char_p, C.c_int64]),
     "spis_get_info": (C.c_int, [_ctx, C.c_char_p, _lp]),
     "spis_upload_csr": (C.c_int, [_ctx, C.c_int, C.c_int64, C.c_int64, C.c_int64, _ip, _ip, _dp]),
     "spis_upload_vec": (C.c_int, [_ctx, C.c_int, _dp, C.c_int64]),
     "spis_upload_blocks": (C.c_int, [_ctx, C.c_int, C.c_int64, C.c_int64, C.c_int64, _dp]),
     "spis_set_precond": (C.c_int, [_ctx, C.c_int]),
+    "spis_thread_use_aux_stream": (C.c_int, [_ctx, C.c_int]),
     "spis_solve_begin": (C.c_int, [_ctx, _dp]),
     "spis_arnoldi_launch": (C.c_int, [_ctx, C.c_int]),
     "spis_arnoldi_wait": (C.c_int, [_ctx, C.c_int, _dp]),

@@ -7,7 +7,9 @@
 #include "../../include/spis_b200.h"
 #include "spis_kernels.cuh"
 
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -61,6 +63,8 @@ struct spis_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t aux = nullptr;   // uploads issued by a helper host thread (spis_thread_use_aux_stream)
+  std::mutex mu;                // guards `owned` and the constraint table against that helper thread
   int nsm = 148;
   int64_t n = 0, n_halo = 0, hoff = 0, ld = 0;
   int kmax = 0, K = 0;          // K = kmax + 4 (small-array stride)
@@ -138,6 +142,18 @@ int fail(spis_ctx* c, int code, const char* fmt, ...) {
 
 inline int64_t roundup(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 
+// SPIS_TRACE=1: wall-clock of the phases of the heavier entry points, on stderr
+struct PhaseTrace {
+  bool on; std::chrono::steady_clock::time_point t;
+  PhaseTrace() : on(getenv("SPIS_TRACE") != nullptr), t(std::chrono::steady_clock::now()) {}
+  void mark(const char* what) {
+    if (!on) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[spis trace]   native: %-30s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+    t = now;
+  }
+};
+
 // Device memory comes from a process-wide cache of exact-size blocks.  The reference's call pattern
 // is one solver call per time step (lkdv/Evolve.py:39-56), i.e. one context per solve with the SAME
 // buffer sizes every time; cudaMalloc/cudaFree of ~10 GB per solve costs 100+ ms (measured), and the
@@ -146,6 +162,13 @@ inline int64_t roundup(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 // exact size match, so from the second solve on allocation is free.
 std::mutex g_dev_mu;
 std::vector<DevBlock> g_dev_free;
+std::atomic<long long> g_dev_hits(0), g_dev_misses(0), g_dev_miss_bytes(0);
+
+// Upload entry points (spis_upload_csr / _vec / _blocks, spis_constraint_define) called by a host
+// thread that has switched this on run on the context's AUXILIARY stream, so that a helper thread can
+// stage the constraint data while the main thread drives the Krylov loop on the main stream.
+thread_local bool tl_use_aux = false;
+inline cudaStream_t up_stream(spis_ctx* ctx) { return (tl_use_aux && ctx->aux) ? ctx->aux : ctx->stream; }
 
 template <class Tp> int dalloc(spis_ctx* ctx, Tp** p, size_t count, bool zero = true) {
   *p = nullptr;
@@ -162,7 +185,9 @@ template <class Tp> int dalloc(spis_ctx* ctx, Tp** p, size_t count, bool zero = 
         break;
       }
   }
+  if (q) g_dev_hits++;
   if (!q) {
+    g_dev_misses++; g_dev_miss_bytes += (long long)bytes;
     cudaError_t e = cudaMalloc(&q, bytes);
     if (e == cudaErrorMemoryAllocation) {          // give cached blocks back to the driver and retry
       cudaGetLastError();
@@ -173,30 +198,36 @@ template <class Tp> int dalloc(spis_ctx* ctx, Tp** p, size_t count, bool zero = 
                                       "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
   }
   *p = static_cast<Tp*>(q);
-  ctx->owned.push_back({q, bytes, ctx->device});
-  if (zero) CU(cudaMemsetAsync(q, 0, bytes, ctx->stream));
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->owned.push_back({q, bytes, ctx->device});
+  }
+  if (zero) CU(cudaMemsetAsync(q, 0, bytes, up_stream(ctx)));
   return SPIS_OK;
 }
 
-// Return a block to the cache.  The caller guarantees that the context's stream has drained every
-// kernel that touched it (all call sites follow a stream synchronisation, or synchronise here).
+// Return a block to the cache.  The caller guarantees that the stream it works on has drained every
+// kernel that touched the block (all call sites follow a stream synchronisation, or synchronise here).
 template <class Tp> void dfree(spis_ctx* ctx, Tp*& p) {
   if (!p) return;
-  cudaStreamSynchronize(ctx->stream);
-  for (size_t i = 0; i < ctx->owned.size(); ++i)
-    if (ctx->owned[i].p == (void*)p) {
-      std::lock_guard<std::mutex> lk(g_dev_mu);
-      g_dev_free.push_back(ctx->owned[i]);
-      ctx->owned[i] = ctx->owned.back();
-      ctx->owned.pop_back();
-      break;
-    }
+  cudaStreamSynchronize(up_stream(ctx));
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    for (size_t i = 0; i < ctx->owned.size(); ++i)
+      if (ctx->owned[i].p == (void*)p) {
+        std::lock_guard<std::mutex> lk2(g_dev_mu);
+        g_dev_free.push_back(ctx->owned[i]);
+        ctx->owned[i] = ctx->owned.back();
+        ctx->owned.pop_back();
+        break;
+      }
+  }
   p = nullptr;
 }
 
 int h2d(spis_ctx* ctx, void* dst, const void* src, size_t bytes) {
-  CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, up_stream(ctx)));
+  CU(cudaStreamSynchronize(up_stream(ctx)));
   return SPIS_OK;
 }
 int d2h(spis_ctx* ctx, void* dst, const void* src, size_t bytes) {
@@ -446,7 +477,7 @@ int launch_spmv(spis_ctx* ctx, int slot, int mode, const double* x, const double
   const Matrix& M = ctx->mats[slot];
   REQUIRE(M.present, "matrix slot %d has not been uploaded", slot);
   const double bytes = 12.0 * (double)M.nnz + 4.0 * (double)(M.nrows + 1) + (mode == 1 ? 24.0 : 16.0) * (double)M.nrows;
-  TRY(prof_begin(ctx, SPIS_PROF_SPMV, bytes));
+  TRY(prof_begin(ctx, slot == SPIS_SLOT_A ? SPIS_PROF_SPMV : SPIS_PROF_SPMV_AUX, bytes));
   if (mode == 0) TRY(launch_spmv_mode<0>(ctx, M, x, b, y, sumsq_out));
   else if (mode == 1) TRY(launch_spmv_mode<1>(ctx, M, x, b, y, sumsq_out));
   else TRY(launch_spmv_mode<2>(ctx, M, x, b, y, sumsq_out));
@@ -509,7 +540,13 @@ void free_matrix(spis_ctx* ctx, Matrix& M) {
 inline double* zbase(spis_ctx* ctx) { return ctx->pre_kind == SPIS_PRE_NONE ? ctx->V : ctx->Z; }
 
 int ensure_Z(spis_ctx* ctx) {
-  if (ctx->pre_kind != SPIS_PRE_NONE && !ctx->Z) TRY(dalloc(ctx, &ctx->Z, (size_t)ctx->kmax * ctx->ld));
+  if (ctx->pre_kind != SPIS_PRE_NONE && !ctx->Z) {
+    TRY(dalloc(ctx, &ctx->Z, (size_t)ctx->kmax * ctx->ld, false));
+    if (ctx->ld > ctx->n) {
+      zero_pads_kernel<<<ctx->kmax, 64, 0, ctx->stream>>>(ctx->Z, ctx->n, ctx->ld);
+      CU(cudaGetLastError());
+    }
+  }
   return SPIS_OK;
 }
 
@@ -592,6 +629,11 @@ int spis_host_any_nonzero(const double* p, size_t n, int* out) {
   unsigned nt = std::thread::hardware_concurrency();
   if (nt == 0) nt = 4;
   if (nt > 16) nt = 16;
+  if (tl_use_aux) {                   // helper thread: leave cores to the thread that feeds the GPU
+    const char* env = getenv("SPIS_HELPER_SCAN_THREADS");
+    unsigned cap = env ? (unsigned)atoi(env) : (nt > 4 ? nt - 2 : nt);
+    if (cap >= 1 && nt > cap) nt = cap;
+  }
   if (n < (size_t)1 << 20) nt = 1;
   if (nt == 1) scan(0, n);
   else {
@@ -605,6 +647,71 @@ int spis_host_any_nonzero(const double* p, size_t n, int* out) {
   }
   *out = found.load();
   return SPIS_OK;
+}
+
+static bool is_pinned_host(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// any non-zero among n doubles at `p` (device memory or page-locked host memory), on the calling
+// thread's upload stream
+static int device_any_nonzero(spis_ctx* ctx, const double* p, size_t n, int* out) {
+  cudaStream_t s = up_stream(ctx);
+  int* flag = reinterpret_cast<int*>(ctx->d_counter + (tl_use_aux ? 2 : 1));
+  CU(cudaMemsetAsync(flag, 0, sizeof(int), s));
+  const int64_t want = (int64_t)((n / 2 + 255) / 256);
+  const int grid = (int)(want < 1 ? 1 : want > ctx->nsm ? ctx->nsm : want);
+  any_nonzero_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const unsigned long long*>(p), (int64_t)n, flag);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return SPIS_OK;
+}
+
+// Page-locked host buffer: pulled through a 64 MB device scratch block by the COPY ENGINE and tested
+// there.  (A kernel reading the host buffer directly over PCIe also works, but its CTAs stay resident
+// for milliseconds, and the Krylov kernels are persistent grids that fill every SM: one foreign CTA per
+// SM pushes them into a second wave and doubles their run time -- measured.)
+static int pinned_any_nonzero(spis_ctx* ctx, const double* p, size_t n, int* out) {
+  cudaStream_t s = up_stream(ctx);
+  const size_t chunk = (size_t)8 << 20;                       // doubles per chunk
+  double* scratch = nullptr;
+  TRY(dalloc(ctx, &scratch, chunk < n ? chunk : n, false));
+  int* flag = reinterpret_cast<int*>(ctx->d_counter + (tl_use_aux ? 2 : 1));
+  cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(int), s);
+  size_t done = 0;
+  int found = 0, k = 0;
+  while (e == cudaSuccess && done < n && !found) {
+    const size_t cnt = (n - done) < chunk ? (n - done) : chunk;
+    e = cudaMemcpyAsync(scratch, p + done, cnt * sizeof(double), cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) break;
+    const int64_t want = (int64_t)((cnt / 2 + 255) / 256);
+    const int grid = (int)(want < 1 ? 1 : want > ctx->nsm ? ctx->nsm : want);
+    any_nonzero_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const unsigned long long*>(scratch), (int64_t)cnt, flag);
+    e = cudaGetLastError();
+    done += cnt;
+    ++k;
+    if (e == cudaSuccess && (k == 1 || (k & 3) == 0 || done == n)) {     // look at the flag now and then: non-zero data ends the scan
+      e = cudaMemcpyAsync(&found, flag, sizeof(int), cudaMemcpyDeviceToHost, s);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    }
+  }
+  dfree(ctx, scratch);
+  if (e != cudaSuccess) return fail(ctx, SPIS_E_CUDA, "zero scan failed: %s", cudaGetErrorString(e));
+  *out = found;
+  return SPIS_OK;
+}
+
+int spis_any_nonzero(spis_ctx* ctx, const double* p, size_t n, int* out) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(out && (p || n == 0), "null argument");
+  *out = 0;
+  if (n == 0) return SPIS_OK;
+  CU(cudaSetDevice(ctx->device));
+  if (n >= ((size_t)1 << 16) && is_pinned_host(p)) return pinned_any_nonzero(ctx, p, n, out);
+  return spis_host_any_nonzero(p, n, out);
 }
 
 int spis_abi_version(void) { return SPIS_ABI_VERSION; }
@@ -631,15 +738,20 @@ int spis_ctx_create(int device, int64_t n, int64_t n_halo, int k_max, void* stre
   if (device < 0 || device >= ndev) return fail(ctx, SPIS_E_INVALID, "device %d out of range (%d devices)", device, ndev);
   e = cudaSetDevice(device);
   if (e != cudaSuccess) return fail(ctx, SPIS_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
-  cudaDeviceProp prop;
-  e = cudaGetDeviceProperties(&prop, device);
-  if (e != cudaSuccess) return fail(ctx, SPIS_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
-  if (prop.major < 10) return fail(ctx, SPIS_E_UNSUPPORTED, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
+  // cudaGetDeviceProperties takes 5-100 ms (it queries every attribute, some through the driver's
+  // global lock); the two attributes needed here cost microseconds
+  int cc_major = 0, cc_minor = 0, n_sm = 0;
+  e = cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&cc_minor, cudaDevAttrComputeCapabilityMinor, device);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+  if (e != cudaSuccess) return fail(ctx, SPIS_E_CUDA, "cudaDeviceGetAttribute: %s", cudaGetErrorString(e));
+  if (cc_major < 10) return fail(ctx, SPIS_E_UNSUPPORTED, "device is sm_%d%d; this library is built for sm_100a only", cc_major, cc_minor);
 
+  PhaseTrace pt;
   spis_ctx* c = new spis_ctx();
   ctx = c;
   c->device = device;
-  c->nsm = prop.multiProcessorCount;
+  c->nsm = n_sm;
   c->n = n; c->n_halo = n_halo;
   c->hoff = roundup(n, 16);
   c->ld = roundup(c->hoff + n_halo, 16);
@@ -651,11 +763,19 @@ int spis_ctx_create(int device, int64_t n, int64_t n_halo, int k_max, void* stre
 #define CCU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(c, e_ == cudaErrorMemoryAllocation ? SPIS_E_NOMEM : SPIS_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); return bail(e_ == cudaErrorMemoryAllocation ? SPIS_E_NOMEM : SPIS_E_CUDA); } } while (0)
   if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
   else { CCU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+  CCU(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
   CCU(cudaEventCreateWithFlags(&c->ev_arnoldi, cudaEventDisableTiming));
   CCU(cudaEventCreate(&c->ev_t0));
   CCU(cudaEventCreate(&c->ev_t1));
+  pt.mark("streams + events");
   const size_t ld = (size_t)c->ld;
-  CTRY(dalloc(c, &c->V, (size_t)(k_max + 1) * ld));
+  // The basis is written before it is read except for the pad entries [n, ld) of each row, which every
+  // kernel relies on being zero: clear those (one strided memset) instead of all (k+1) n doubles.
+  CTRY(dalloc(c, &c->V, (size_t)(k_max + 1) * ld, false));
+  if (c->ld > c->n) {
+    zero_pads_kernel<<<k_max + 1, 64, 0, c->stream>>>(c->V, c->n, c->ld);
+    CCU(cudaGetLastError());
+  }
   CTRY(dalloc(c, &c->W, ld));
   CTRY(dalloc(c, &c->T, ld));
   CTRY(dalloc(c, &c->R0, ld));
@@ -667,12 +787,14 @@ int spis_ctx_create(int device, int64_t n, int64_t n_halo, int k_max, void* stre
   CTRY(dalloc(c, &c->d_cout, (size_t)k_max * 2 * c->K));
   CTRY(dalloc(c, &c->d_partial, (size_t)c->max_grid * c->pstride));
   CTRY(dalloc(c, &c->d_counter, 4));
+  pt.mark("device blocks");
   if (spis_pinned_alloc(((size_t)2 * c->K + 8) * sizeof(double), (void**)&c->h_small) != SPIS_OK ||
       spis_pinned_alloc((size_t)c->K * sizeof(double), (void**)&c->h_y) != SPIS_OK ||
       spis_pinned_alloc((size_t)k_max * 2 * c->K * sizeof(double), (void**)&c->h_cout) != SPIS_OK) {
     fail(c, SPIS_E_NOMEM, "pinned host allocation failed: %s", g_global_err);
     return bail(SPIS_E_NOMEM);
   }
+  pt.mark("pinned mirrors");
   // mdot needs up to (8*K+256)*8 bytes of dynamic shared memory, mdotm<4> four times the K part
   {
     const int need4 = (kWarps * 4 * c->K + kWarps * 32) * (int)sizeof(double);
@@ -692,7 +814,9 @@ int spis_ctx_create(int device, int64_t n, int64_t n_halo, int k_max, void* stre
   CCU(cudaFuncSetAttribute(orth_mid_kernel<MBV, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOrthMidSmemBudget));
   SPIS_OM_ATTR(8) SPIS_OM_ATTR(16) SPIS_OM_ATTR(24) SPIS_OM_ATTR(32) SPIS_OM_ATTR(40) SPIS_OM_ATTR(48) SPIS_OM_ATTR(56) SPIS_OM_ATTR(64)
 #undef SPIS_OM_ATTR
+  pt.mark("kernel attributes");
   CCU(cudaStreamSynchronize(c->stream));
+  pt.mark("stream drain");
 #undef CTRY
 #undef CCU
   *ctx_out = c;
@@ -702,6 +826,7 @@ int spis_ctx_create(int device, int64_t n, int64_t n_halo, int k_max, void* stre
 int spis_ctx_destroy(spis_ctx* ctx) {
   if (!ctx) return SPIS_OK;
   cudaSetDevice(ctx->device);
+  if (ctx->aux) cudaStreamSynchronize(ctx->aux);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (auto& r : ctx->recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   for (auto& e : ctx->evpool) cudaEventDestroy(e);
@@ -725,6 +850,7 @@ int spis_ctx_destroy(spis_ctx* ctx) {
   if (ctx->ev_arnoldi) cudaEventDestroy(ctx->ev_arnoldi);
   if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
   if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
+  if (ctx->aux) cudaStreamDestroy(ctx->aux);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return SPIS_OK;
@@ -769,6 +895,9 @@ int spis_get_info(const spis_ctx* cctx, const char* key, int64_t* value_out) {
     else if (k.rfind("nnz_padded:", 0) == 0) *value_out = ctx->mats[slot].nnz_padded;
     else *value_out = ctx->mats[slot].nnz;
   }
+  else if (k == "alloc_hits") *value_out = g_dev_hits.load();
+  else if (k == "alloc_misses") *value_out = g_dev_misses.load();
+  else if (k == "alloc_miss_bytes") *value_out = g_dev_miss_bytes.load();
   else if (k == "device_ptr:small") *value_out = (int64_t)(intptr_t)ctx->d_small;
   else if (k == "stream") *value_out = (int64_t)(intptr_t)ctx->stream;
   else if (k == "n_send") *value_out = ctx->n_send;
@@ -786,29 +915,30 @@ int spis_upload_csr(spis_ctx* ctx, int slot, int64_t nrows, int64_t ncols, int64
   REQUIRE(nnz >= 0 && nnz < (int64_t)INT32_MAX, "nnz %lld must fit int32 row pointers", (long long)nnz);
   REQUIRE(indptr && (nnz == 0 || (indices && data)), "null CSR arrays");
   CU(cudaSetDevice(ctx->device));
+  cudaStream_t s = up_stream(ctx);
   Matrix& M = ctx->mats[slot];
   free_matrix(ctx, M);
   M.nrows = nrows; M.ncols = ncols; M.nnz = nnz;
   TRY(dalloc(ctx, &M.indptr, (size_t)nrows + 1, false));
   TRY(dalloc(ctx, &M.cols, (size_t)nnz, false));
   TRY(dalloc(ctx, &M.vals, (size_t)nnz, false));
-  CU(cudaMemcpyAsync(M.indptr, indptr, ((size_t)nrows + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(M.indptr, indptr, ((size_t)nrows + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
   if (nnz) {
-    CU(cudaMemcpyAsync(M.cols, indices, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(M.vals, data, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(M.cols, indices, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(M.vals, data, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, s));
   }
   if (ctx->n_halo > 0 && ctx->hoff != ctx->n && nnz)
-    remap_cols_kernel<<<ctx->nsm * 8, 256, 0, ctx->stream>>>(M.cols, nnz, (int32_t)ctx->n, (int32_t)(ctx->hoff - ctx->n));
+    remap_cols_kernel<<<ctx->nsm * 8, 256, 0, s>>>(M.cols, nnz, (int32_t)ctx->n, (int32_t)(ctx->hoff - ctx->n));
   // SELL-32 slice widths -> offsets (tiny scan on the host)
   const int64_t nslices = (nrows + 31) / 32;
   int32_t* d_width = nullptr;
   TRY(dalloc(ctx, &d_width, (size_t)nslices, false));
   const int cgrid = (int)((nslices * 32 + 255) / 256);
-  sell_width_kernel<<<cgrid, 256, 0, ctx->stream>>>(M.indptr, nrows, d_width);
+  sell_width_kernel<<<cgrid, 256, 0, s>>>(M.indptr, nrows, d_width);
   CU(cudaGetLastError());
   std::vector<int32_t> width((size_t)nslices);
-  CU(cudaMemcpyAsync(width.data(), d_width, (size_t)nslices * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaMemcpyAsync(width.data(), d_width, (size_t)nslices * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
   dfree(ctx, d_width);
   std::vector<int64_t> off((size_t)nslices + 1);
   off[0] = 0;
@@ -821,15 +951,15 @@ int spis_upload_csr(spis_ctx* ctx, int slot, int64_t nrows, int64_t ncols, int64
     TRY(dalloc(ctx, &M.slice_off, (size_t)nslices + 1, false));
     TRY(dalloc(ctx, &M.scols, (size_t)M.nnz_padded, false));
     TRY(dalloc(ctx, &M.svals, (size_t)M.nnz_padded, false));
-    CU(cudaMemcpyAsync(M.slice_off, off.data(), ((size_t)nslices + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
-    sell_fill_kernel<<<cgrid, 256, 0, ctx->stream>>>(M.indptr, M.cols, M.vals, nrows, M.slice_off, M.scols, M.svals);
+    CU(cudaMemcpyAsync(M.slice_off, off.data(), ((size_t)nslices + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    sell_fill_kernel<<<cgrid, 256, 0, s>>>(M.indptr, M.cols, M.vals, nrows, M.slice_off, M.scols, M.svals);
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(s));
     dfree(ctx, M.indptr); dfree(ctx, M.cols); dfree(ctx, M.vals);
   } else {
     const double avg = nrows ? (double)nnz / (double)nrows : 0.0;
     M.csr_lanes = avg <= 3 ? 2 : avg <= 6 ? 4 : avg <= 12 ? 8 : avg <= 24 ? 16 : 32;
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(s));
   }
   M.present = true;
   return SPIS_OK;
@@ -897,7 +1027,10 @@ int spis_solve_begin(spis_ctx* ctx, double* beta_out) {
   CU(cudaMemcpyAsync(ctx->h_small + 2 * ctx->K, scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   *beta_out = std::sqrt(ctx->h_small[2 * ctx->K + 1]);
-  for (auto& c : ctx->cons) { c.cols_done = 0; c.term0_done = false; }
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    for (auto& c : ctx->cons) { c.cols_done = 0; c.term0_done = false; }
+  }
   ctx->began = true;
   ctx->arnoldi_inflight = -1;
   return SPIS_OK;
@@ -1024,10 +1157,22 @@ int spis_constraint_define(spis_ctx* ctx, int c, int mat_slot, const double* v, 
   REQUIRE(mat_slot < 0 || ctx->mats[mat_slot].present, "constraint matrix slot %d not uploaded", mat_slot);
   CU(cudaSetDevice(ctx->device));
   Constraint& C = ctx->cons[c];
-  C.defined = true; C.slot = mat_slot; C.cc = cc; C.cols_done = 0; C.term0_done = false; C.symmetric = -1;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    C.defined = true; C.slot = mat_slot; C.cc = cc; C.cols_done = 0; C.term0_done = false; C.symmetric = -1;
+  }
   if (v) {
-    if (!C.v) TRY(dalloc(ctx, &C.v, (size_t)ctx->ld));
-    TRY(h2d(ctx, C.v, v, (size_t)ctx->n * sizeof(double)));
+    // an all-zero v is dropped (term1 then needs no v.Z pass).  Page-locked source: upload, then test the
+    // device copy at HBM speed; pageable source: scan on the host first and skip the slow staged copy.
+    int nz = 1;
+    const bool pinned = is_pinned_host(v);
+    if (!pinned) TRY(spis_host_any_nonzero(v, (size_t)ctx->n, &nz));
+    if (nz) {
+      if (!C.v) TRY(dalloc(ctx, &C.v, (size_t)ctx->ld));
+      TRY(h2d(ctx, C.v, v, (size_t)ctx->n * sizeof(double)));
+      if (pinned) TRY(device_any_nonzero(ctx, C.v, (size_t)ctx->n, &nz));
+    }
+    if (!nz && C.v) dfree(ctx, C.v);
   } else if (C.v) { dfree(ctx, C.v); }
   if (mat_slot < 0 && C.MZ) { dfree(ctx, C.MZ); }
   C.T1.assign((size_t)ctx->kmax, 0.0);
@@ -1324,6 +1469,16 @@ int spis_xcomm_set_halo(spis_ctx* ctx, const int32_t* dest_rank, const int32_t* 
   TRY(dalloc(ctx, &ctx->d_recv_from, (size_t)kMaxRanks));
   TRY(h2d(ctx, ctx->d_send_to, send_to, (size_t)ctx->xv.world * sizeof(int32_t)));
   TRY(h2d(ctx, ctx->d_recv_from, recv_from, (size_t)ctx->xv.world * sizeof(int32_t)));
+  return SPIS_OK;
+}
+
+int spis_thread_use_aux_stream(spis_ctx* ctx, int on) {
+  if (!ctx) return SPIS_E_INVALID;
+  tl_use_aux = on != 0;
+  if (!on) {                     // leaving: everything this thread queued on the auxiliary stream is complete
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->aux));
+  }
   return SPIS_OK;
 }
 

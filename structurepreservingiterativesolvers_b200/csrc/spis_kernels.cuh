@@ -906,6 +906,32 @@ __global__ void halo_pack_kernel(const double* __restrict__ vec, const int32_t* 
     send[i] = vec[idx[i]];
 }
 
+// rows of a (rows x ld) buffer: clear the pad entries [n, ld) of row blockIdx.x (ld - n < ld of course;
+// with n_halo == 0 that is at most 15 + 15 doubles)
+__global__ void zero_pads_kernel(double* __restrict__ base, int64_t n, int64_t ld) {
+  double* row = base + (size_t)blockIdx.x * ld;
+  for (int64_t e = n + threadIdx.x; e < ld; e += blockDim.x) row[e] = 0.0;
+}
+
+// flag |= (any of p[0..n) has a bit set besides the sign bit).  p may be page-locked HOST memory (read
+// over PCIe by the load instructions themselves: no staging buffer, no host CPU time) or device memory.
+__global__ void __launch_bounds__(256)
+any_nonzero_kernel(const unsigned long long* __restrict__ p, int64_t n, int* flag) {
+  unsigned long long acc = 0ull;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 2;
+  int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if ((reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
+    for (; i + 1 < n; i += stride) {
+      const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p + i);
+      acc |= v.x | v.y;
+    }
+    if (i < n) acc |= p[i];
+  } else {
+    for (; i < n; i += stride) { acc |= p[i]; if (i + 1 < n) acc |= p[i + 1]; }
+  }
+  if (acc & 0x7fffffffffffffffull) *flag = 1;
+}
+
 // deterministic pseudo-random fill in (-1, 1) for spis_bench_kernel
 __global__ void fill_kernel(double* __restrict__ p, int64_t n, uint64_t seed) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;

@@ -104,6 +104,21 @@ class KrylovContext:
             raise ValueError("blocks must be (nblk, bs, bs)")
         self._check(self._lib.spis_upload_blocks(self._h, bs, nblk, stride_block, stride_field, nat.dptr(blocks)))
 
+    def any_nonzero(self, a) -> bool:
+        """`np.any(a)` for a float64 buffer: page-locked arrays are scanned by the GPU over PCIe."""
+        self._live()
+        a = np.asarray(a)
+        if a.dtype != np.float64 or not a.flags.c_contiguous or a.size < (1 << 16):
+            return bool(np.any(a))
+        out = C.c_int(0)
+        self._check(self._lib.spis_any_nonzero(self._h, nat.dptr(a), a.size, C.byref(out)))
+        return bool(out.value)
+
+    def use_aux_stream(self, on: bool):
+        """Uploads issued by the CALLING THREAD go to the auxiliary stream (see spis_b200.h)."""
+        self._live()
+        self._check(self._lib.spis_thread_use_aux_stream(self._h, 1 if on else 0))
+
     def set_precond(self, kind: int):
         self._live()
         self._check(self._lib.spis_set_precond(self._h, kind))

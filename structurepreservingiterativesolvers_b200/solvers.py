@@ -28,6 +28,7 @@ from __future__ import annotations
 import collections.abc
 import os
 import sys
+import threading
 import warnings
 from time import time
 
@@ -50,6 +51,7 @@ _CONFIG = {
     "orth": "cgs2",
     "spmv_format": "auto",
     "profile": False,
+    "async_setup": True,
 }
 _ORTH = {"cgs2": nat.ORTH_CGS2, "cgs1": nat.ORTH_CGS1, "mgs": nat.ORTH_MGS}
 _FMT = {"auto": nat.FMT_AUTO, "sell": nat.FMT_SELL, "csr": nat.FMT_CSR}
@@ -181,7 +183,7 @@ class DeviceSession:
     """
 
     def __init__(self, A, b, x0, k, conlist=(), pre=None, *, device=None, orth=None,
-                 spmv_format=None, profile=None, ctx_factory=KrylovContext):
+                 spmv_format=None, profile=None, ctx_factory=KrylovContext, async_setup=None):
         tr = _Trace()
         b = nat.as_f64(b)
         n = b.size
@@ -190,6 +192,9 @@ class DeviceSession:
         self.ctx = ctx_factory(n, self.k, device=_opt("device", device))
         ctx = self.ctx
         tr("context create")
+        if _TRACE and hasattr(ctx, "info"):
+            sys.stderr.write("[spis trace] device block cache: %d hits, %d misses (%.1f MB) so far\n"
+                             % (ctx.info("alloc_hits"), ctx.info("alloc_misses"), ctx.info("alloc_miss_bytes") / 1e6))
         ctx.set_option("orth", _ORTH[_opt("orth", orth)])
         ctx.set_option("spmv_format", _FMT[_opt("spmv_format", spmv_format)])
         ctx.set_option("profile", 1 if _opt("profile", profile) else 0)
@@ -200,17 +205,33 @@ class DeviceSession:
         ctx.upload_matrix(nat.SLOT_A, A)
         tr("upload A")
         ctx.upload_vec(nat.VEC_B, b)
-        ctx.upload_vec(nat.VEC_X0, self.x0_host)
-        ctx.set_option("x0_is_zero", 0 if self._any_rank(nat.any_nonzero(self.x0_host)) else 1)
+        x0_nonzero = self._any_rank(nat.any_nonzero(self.x0_host))
+        if x0_nonzero:                       # a new context's x0 buffer is already zero on the device
+            ctx.upload_vec(nat.VEC_X0, self.x0_host)
+        ctx.set_option("x0_is_zero", 0 if x0_nonzero else 1)
         tr("upload b, x0")
         self._host_pre = None
         self._setup_precond(pre)
         tr("preconditioner")
         self._cons = []
-        self._setup_constraints(list(conlist))
-        tr("constraints")
         self._Zhost = None
         self._Zrows = 0
+        # The constraint data is first needed at the first constrained step (solvers.py:242-247), many
+        # Krylov iterations from now: a helper thread scans and uploads it on the context's auxiliary
+        # stream while the caller's thread already runs the loop.  (Row-sharded sessions take collective
+        # decisions in _any_rank and stay on one thread.)
+        self._bg = None
+        self._bg_error = None
+        conlist = list(conlist)
+        if len(conlist) > nat.MAX_SLOTS - nat.SLOT_CON0:
+            raise ValueError("too many constraints")
+        if conlist and _opt("async_setup", async_setup) and type(self) is DeviceSession and hasattr(ctx, "use_aux_stream"):
+            self._bg = threading.Thread(target=self._setup_constraints_bg, args=(conlist,), daemon=True)
+            self._bg.start()
+            tr("constraints (handed to helper thread)")
+        else:
+            self._setup_constraints(conlist)
+            tr("constraints")
 
     def _any_rank(self, flag):
         """Logical OR of a host-side decision over all ranks (identity on one GPU).  Every decision
@@ -252,26 +273,50 @@ class DeviceSession:
             ctx.set_precond(nat.PRE_HOST)
 
     # -- constraints: solvers.py:22-40 -----------------------------------------------------------
+    def _setup_constraints_bg(self, conlist):
+        try:
+            self.ctx.use_aux_stream(True)
+            try:
+                self._setup_constraints(conlist)
+            finally:
+                self.ctx.use_aux_stream(False)
+        except BaseException as exc:                       # re-raised on the caller's thread by _join_setup
+            self._bg_error = exc
+
+    def _join_setup(self):
+        if self._bg is not None:
+            self._bg.join()
+            self._bg = None
+        if self._bg_error is not None:
+            exc, self._bg_error = self._bg_error, None
+            raise exc
+
     def _setup_constraints(self, conlist):
-        if len(conlist) > nat.MAX_SLOTS - nat.SLOT_CON0:
-            raise ValueError("too many constraints")
+        tr = _Trace()
         for idx, const in enumerate(conlist):
             kind = _classify_constraint(const)
             entry = {"kind": kind, "const": const, "error": None}
             if kind == "class":
                 try:
                     M, v, c = const.M, const.v, const.c
+                    anynz = getattr(self.ctx, "any_nonzero", nat.any_nonzero)
                     if sps.issparse(M):
-                        M_zero = not self._any_rank(M.nnz != 0 and nat.any_nonzero(M.data))
+                        M_zero = not self._any_rank(M.nnz != 0 and anynz(M.data))
                     else:
                         M = np.asarray(M, dtype=np.float64)
                         M_zero = not self._any_rank(M.any())
+                    tr("  constraint %d: is M zero? %s" % (idx, M_zero))
                     slot = -1
                     if not M_zero:
                         slot = nat.SLOT_CON0 + idx
                         self.ctx.upload_matrix(slot, M)
+                        tr("  constraint %d: upload M" % idx)
                     v = nat.as_f64(v, self.n)
-                    self.ctx.constraint_define(idx, slot, v if self._any_rank(nat.any_nonzero(v)) else None, float(c))
+                    if type(self) is DeviceSession:        # the library recognises an all-zero v itself
+                        self.ctx.constraint_define(idx, slot, v, float(c))
+                    else:                                  # row-sharded: every rank must take the same decision
+                        self.ctx.constraint_define(idx, slot, v if self._any_rank(nat.any_nonzero(v)) else None, float(c))
+                    tr("  constraint %d: v" % idx)
                 except nat.NativeLibraryError:
                     raise
                 except Exception as exc:                    # surfaces where the reference builds containers
@@ -280,6 +325,7 @@ class DeviceSession:
 
     def containers(self, m):
         """Reduced constraints for Z = z[:m].T (the reference rebuilds these per step, solvers.py:242-247)."""
+        self._join_setup()
         out = []
         for idx, entry in enumerate(self._cons):
             if entry["kind"] == "invalid":
@@ -305,6 +351,7 @@ class DeviceSession:
 
     @property
     def n_constraints(self):
+        self._join_setup()
         return len(self._cons)
 
     # -- Krylov primitives ------------------------------------------------------------------------
@@ -322,7 +369,10 @@ class DeviceSession:
         return self.ctx.arnoldi_wait(j)
 
     def close(self):
-        self.ctx.close()
+        try:
+            self._join_setup()
+        finally:
+            self.ctx.close()
 
 
 class IterateHistory(collections.abc.Sequence):

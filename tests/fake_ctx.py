@@ -22,7 +22,7 @@ class FakeKrylovContext:
         self.closed = False
         self.opts = {"orth": nat.ORTH_CGS2}
         self.mats = {}
-        self.vecs = {}
+        self.vecs = {nat.VEC_X0: np.zeros(n)}
         self.pre_kind = nat.PRE_NONE
         self.blocks = None
         self.cons = {}
@@ -44,6 +44,11 @@ class FakeKrylovContext:
 
     def set_option(self, key, value):
         self.opts[key] = value
+
+    def use_aux_stream(self, on):
+        """DeviceSession stages the constraints from a helper thread when the context offers this."""
+        import threading
+        self.aux_threads = getattr(self, "aux_threads", set()) | {threading.get_ident()}
 
     def info(self, key):
         return {"n": self.n, "k_max": self.k_max}.get(key, 0)
@@ -112,7 +117,7 @@ class FakeKrylovContext:
         self.V[:] = 0
         self.V[0, :n] = self.r0 / beta
         self.generation += 1
-        for c in self.cons.values():
+        for c in list(self.cons.values()):          # a helper thread may be defining constraints right now
             c["done"] = 0
             c["T1"] = np.zeros(self.k_max)
             c["T2"] = np.zeros((self.k_max, self.k_max))

@@ -198,6 +198,32 @@ def test_preconditioner_kernels():
         np.testing.assert_allclose(ctx.op_precond(q), Pm @ q, rtol=1e-12, atol=1e-12)
 
 
+def test_any_nonzero_host_and_pinned_paths():
+    """Zero detection of constraint data (`0*A`, lkdv/LinearSolver.py:30): pageable buffers on the host
+    threads, page-locked ones by a kernel reading host memory over PCIe; -0.0 is zero, NaN is not."""
+    import torch
+    n = 300_001
+    with KrylovContext(1000, 2) as ctx:
+        for pinned in (False, True):
+            def buf(a):
+                return torch.from_numpy(a).pin_memory().numpy() if pinned else a
+            z = buf(np.zeros(n))
+            assert ctx.any_nonzero(z) is False
+            z[:] = -0.0
+            assert ctx.any_nonzero(z) is False
+            for pos in (0, 1, n // 2, n - 2, n - 1):
+                z[:] = 0.0
+                z[pos] = 1e-300
+                assert ctx.any_nonzero(z) is True
+            z[:] = 0.0
+            z[n - 1] = np.nan
+            assert ctx.any_nonzero(z) is True
+            z[:] = 0.0
+            assert ctx.any_nonzero(z[1:]) is False                   # 8-byte aligned only
+            z[5] = 2.0
+            assert ctx.any_nonzero(z[1:]) is True and ctx.any_nonzero(z[6:]) is False
+
+
 def test_errors_are_reported_not_swallowed():
     with KrylovContext(100, 4) as ctx:
         with pytest.raises(nat.SpisError):

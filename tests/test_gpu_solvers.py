@@ -134,7 +134,7 @@ def test_nonsymmetric_constraint_matrix_terms():
         pass
     c = C(); c.M = Mns; c.v = 0.1 * np.arange(n) / n; c.c = -1.0
     x0 = 0.01 * np.cos(np.arange(n))
-    sess = solvers.DeviceSession(A, b, x0, 6, conlist=[c])
+    sess = solvers.DeviceSession(A, b, x0, 6, conlist=[c], async_setup=False)
     sess.begin()
     for j in range(4):
         sess.arnoldi_launch(j); sess.arnoldi_wait(j)
@@ -217,7 +217,7 @@ def test_symmetric_fast_path_equals_general_path(x0_zero):
     cl = wrappers.heat.conlist(d, x0)              # energy: M + dt/2 L (symmetric), v != 0
     out = {}
     for force in (0, 1):
-        sess = solvers.DeviceSession(A, b, x0, 12, conlist=cl)
+        sess = solvers.DeviceSession(A, b, x0, 12, conlist=cl, async_setup=False)   # the context is driven by hand below
         sess.ctx.set_option("force_nonsymmetric", force)
         sess.begin()
         for j in range(8):

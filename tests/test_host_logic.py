@@ -128,6 +128,39 @@ def test_constraints_only_built_in_constrained_phase():
     assert sess.ctx.cons[0]["slot"] < 0 and sess.ctx.cons[1]["slot"] >= 0
 
 
+def test_constraints_are_staged_by_a_helper_thread():
+    """DeviceSession hands the constraint scan + upload to a helper thread (auxiliary stream on the GPU)
+    and joins it before the reduced constraints are first needed; async_setup=False keeps one thread."""
+    import threading
+    spec, dic, prob, x0, pre = cases.instantiate("lkdv_cg_tol6")
+    cl = wrappers.lkdv.conlist(dic, x0)
+    results = []
+    for async_setup in (True, False):
+        sess = solvers.DeviceSession(dic["A"], dic["b"], x0, 50, conlist=cl, ctx_factory=FakeKrylovContext,
+                                     async_setup=async_setup)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            x, info = solvers.cgmres(dic["A"], dic["b"], x0, 50, tol=1e-6, conlist=cl, session=sess)
+        helpers_threads = getattr(sess.ctx, "aux_threads", set())
+        assert (len(helpers_threads) == 1 and threading.get_ident() not in helpers_threads) == async_setup
+        assert sess.n_constraints == 3
+        results.append(x)
+        sess.close()
+    np.testing.assert_array_equal(results[0], results[1])
+
+
+def test_helper_thread_errors_surface_on_the_callers_thread():
+    spec, dic, prob, x0, pre = cases.instantiate("lkdv_cg_tol6")
+
+    class Broken:
+        M, c = dic["M"], 0.0
+        v = np.zeros(7)                       # wrong length: the reference fails when it builds the container
+    sess = solvers.DeviceSession(dic["A"], dic["b"], x0, 10, conlist=[Broken()], ctx_factory=FakeKrylovContext)
+    with pytest.raises(ValueError):
+        sess.containers(1)
+    sess.close()
+
+
 def test_invalid_constraint_type():
     spec, dic, prob, x0, pre = cases.instantiate("lkdv_cg_tol6")
     bad = [("not", "a", "constraint")]
