@@ -76,6 +76,7 @@ extern "C" {
 #define SPIS_FMT_AUTO     0   /* SELL-32 unless padding overhead > 25 % */
 #define SPIS_FMT_SELL     1
 #define SPIS_FMT_CSR      2
+#define SPIS_FMT_SELL2     3   /* SELL-32 with the entries of a row packed in pairs (128-bit value loads) */
 
 /* timer classes returned by spis_get_profile (CUDA-event time, algorithmic bytes, launches) */
 #define SPIS_PROF_SPMV     0   /* system matrix A: A z_j, b - A x0, ||A x_j - b||          */

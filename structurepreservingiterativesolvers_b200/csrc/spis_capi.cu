@@ -77,6 +77,9 @@ struct spis_ctx {
   int mdot_variant = 0, lincomb_variant = 4;   // mdot 0 = auto (tools/tune.py sweep, profiles/tune_r1.md)
   int x0_is_zero = 0;
   int fuse_jacobi = 1;
+  int mdotm_ctas_per_sm = 4;       // tools/tune_mdotm.py: 5.1-5.5 TB/s at 4, 3.5-4.8 at 2, 3.8-4.3 at 8
+  int bench_mdotm_nw = 0;       // tuning: spis_bench_kernel(SPIS_PROF_MDOT) times mdotm_kernel<nw> instead
+  int auto_sell2 = 0;           // spmv_format=auto picks the pair-packed SELL layout
   int force_nonsymmetric = 0;   // tests: take the general (stored M Z) path of the constraint stage
   int orth_fused = 1;           // CGS2: fuse (w -= V h1) with (h2 = V^T w) through TMA-staged tiles
   int orth_mid_max_stages = 8;
@@ -360,7 +363,7 @@ int launch_mdotm(spis_ctx* ctx, int nw, const double* V, int m, const double* ex
   const int nout = nw * nrows;
   REQUIRE(nout <= ctx->pstride, "mdotm: %d outputs exceed workspace %d", nout, ctx->pstride);
   const int64_t ntiles = (ctx->n + kTile - 1) / kTile;
-  const int grid = grid_for(ctx, ntiles, ctx->ctas_per_sm > 2 ? 2 : ctx->ctas_per_sm);
+  const int grid = grid_for(ctx, ntiles, ctx->mdotm_ctas_per_sm);
   const size_t smem = (size_t)(kWarps * nout + kWarps * 32) * sizeof(double);
   REQUIRE(smem <= 227 * 1024, "mdotm: %zu bytes of shared memory needed", smem);
   TRY(prof_begin(ctx, SPIS_PROF_MDOT, (double)(nrows + nw) * 8.0 * (double)ctx->n));
@@ -460,6 +463,10 @@ int launch_spmv_mode(spis_ctx* ctx, const Matrix& M, const double* x, const doub
     const int64_t nslices = (M.nrows + 31) / 32;
     const int grid = grid_for(ctx, (nslices + kWarps - 1) / kWarps, ctx->spmv_ctas_per_sm);
     spmv_sell_kernel<MODE><<<grid, kThreads, 0, ctx->stream>>>(M.slice_off, M.scols, M.svals, M.nrows, x, b, y, ctx->d_partial, ctx->d_counter, sumsq_out, xv, seq);
+  } else if (M.fmt == SPIS_FMT_SELL2) {
+    const int64_t nslices = (M.nrows + 31) / 32;
+    const int grid = grid_for(ctx, (nslices + kWarps - 1) / kWarps, ctx->spmv_ctas_per_sm);
+    spmv_sell2_kernel<MODE><<<grid, kThreads, 0, ctx->stream>>>(M.slice_off, reinterpret_cast<const int2*>(M.scols), reinterpret_cast<const double2*>(M.svals), M.nrows, x, b, y, ctx->d_partial, ctx->d_counter, sumsq_out, xv, seq);
   } else {
     const int T = M.csr_lanes;
     const int64_t nblocks = (M.nrows + (kThreads / T) - 1) / (kThreads / T);
@@ -860,7 +867,10 @@ int spis_set_option(spis_ctx* ctx, const char* key, int64_t value) {
   if (!ctx || !key) return SPIS_E_INVALID;
   std::string k(key);
   if (k == "orth") { REQUIRE(value >= 0 && value <= 2, "orth must be 0..2"); ctx->orth = (int)value; }
-  else if (k == "spmv_format") { REQUIRE(value >= 0 && value <= 2, "spmv_format must be 0..2"); ctx->fmt_pref = (int)value; }
+  else if (k == "spmv_format") { REQUIRE(value >= 0 && value <= 3, "spmv_format must be 0..3"); ctx->fmt_pref = (int)value; }
+  else if (k == "auto_sell2") { ctx->auto_sell2 = value ? 1 : 0; }
+  else if (k == "mdotm_ctas_per_sm") { REQUIRE(value >= 1 && value <= 8, "mdotm_ctas_per_sm must be 1..8"); ctx->mdotm_ctas_per_sm = (int)value; }
+  else if (k == "bench_mdotm_nw") { REQUIRE(value == 0 || value == 2 || value == 4, "bench_mdotm_nw must be 0, 2 or 4"); ctx->bench_mdotm_nw = (int)value; }
   else if (k == "profile") { ctx->profile = value ? 1 : 0; }
   else if (k == "ctas_per_sm") { REQUIRE(value >= 1 && value <= 16, "ctas_per_sm must be 1..16"); ctx->ctas_per_sm = (int)value; }
   else if (k == "spmv_ctas_per_sm") { REQUIRE(value >= 1 && value <= 16, "spmv_ctas_per_sm must be 1..16"); ctx->spmv_ctas_per_sm = (int)value; }
@@ -942,17 +952,21 @@ int spis_upload_csr(spis_ctx* ctx, int slot, int64_t nrows, int64_t ncols, int64
   dfree(ctx, d_width);
   std::vector<int64_t> off((size_t)nslices + 1);
   off[0] = 0;
-  for (int64_t s = 0; s < nslices; ++s) off[s + 1] = off[s] + (int64_t)width[s] * 32;
-  M.nnz_padded = off[nslices];
   int fmt = ctx->fmt_pref;
-  if (fmt == SPIS_FMT_AUTO) fmt = ((double)M.nnz_padded <= 1.25 * (double)(nnz > 0 ? nnz : 1) + 32.0 * 64.0) ? SPIS_FMT_SELL : SPIS_FMT_CSR;
+  const bool want2 = fmt == SPIS_FMT_SELL2 || (fmt == SPIS_FMT_AUTO && ctx->auto_sell2);
+  for (int64_t s = 0; s < nslices; ++s) off[s + 1] = off[s] + (int64_t)(want2 ? (width[s] + 1) & ~1 : width[s]) * 32;
+  M.nnz_padded = off[nslices];
+  if (fmt == SPIS_FMT_AUTO) fmt = ((double)M.nnz_padded <= 1.25 * (double)(nnz > 0 ? nnz : 1) + 32.0 * 64.0) ? (want2 ? SPIS_FMT_SELL2 : SPIS_FMT_SELL) : SPIS_FMT_CSR;
   M.fmt = fmt;
-  if (fmt == SPIS_FMT_SELL) {
+  if (fmt == SPIS_FMT_SELL || fmt == SPIS_FMT_SELL2) {
     TRY(dalloc(ctx, &M.slice_off, (size_t)nslices + 1, false));
     TRY(dalloc(ctx, &M.scols, (size_t)M.nnz_padded, false));
     TRY(dalloc(ctx, &M.svals, (size_t)M.nnz_padded, false));
     CU(cudaMemcpyAsync(M.slice_off, off.data(), ((size_t)nslices + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-    sell_fill_kernel<<<cgrid, 256, 0, s>>>(M.indptr, M.cols, M.vals, nrows, M.slice_off, M.scols, M.svals);
+    if (fmt == SPIS_FMT_SELL2)
+      sell2_fill_kernel<<<cgrid, 256, 0, s>>>(M.indptr, M.cols, M.vals, nrows, M.slice_off, M.scols, M.svals);
+    else
+      sell_fill_kernel<<<cgrid, 256, 0, s>>>(M.indptr, M.cols, M.vals, nrows, M.slice_off, M.scols, M.svals);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s));
     dfree(ctx, M.indptr); dfree(ctx, M.cols); dfree(ctx, M.vals);
@@ -1271,14 +1285,16 @@ int spis_constraint_terms(spis_ctx* ctx, int c, int m, double* term0, double* te
           if (nw == 1) rc = launch_mdot(ctx, Zb, g1, extra, 0, ctx->G, base);        // (:35-36)
           else rc = launch_mdotm(ctx, nw, Zb, g1, extra, ctx->G, (int64_t)ld, base);
         }
-        if (rc == SPIS_OK && C.v) {                                // v.z_col for the group
-          double* bB = base + (size_t)nw * K;
-          if (nw == 1) rc = launch_mdot(ctx, nullptr, 0, C.v, 0, Zb + (size_t)g0 * ld, bB);
-          else rc = launch_mdotm(ctx, nw, C.v, 1, nullptr, Zb + (size_t)g0 * ld, (int64_t)ld, bB);
-        }
         groups.push_back({g0, g1, nr});
         g0 = g1;
       }
+      // v.z_col for ALL new columns in one pass: rows Z[c0..m) against v (the slot behind the last
+      // column's block is not used by any group)
+      if (rc == SPIS_OK && C.v)
+        rc = launch_mdot(ctx, Zb + (size_t)c0 * ld, m - c0, nullptr, 0, C.v, ctx->d_cout + (size_t)(m - 1) * 2 * K + K);
+    } else if (!hasM) {
+      // M == 0 (mass-type invariants, lkdv/LinearSolver.py:28-32): term1 = v.Z only, one pass for all new columns
+      if (C.v) rc = launch_mdot(ctx, Zb + (size_t)c0 * ld, m - c0, nullptr, 0, C.v, ctx->d_cout + (size_t)c0 * 2 * K);
     } else {
       for (int col = c0; col < m && rc == SPIS_OK; ++col) {
         double* zc = Zb + (size_t)col * ld;
@@ -1291,8 +1307,6 @@ int spis_constraint_terms(spis_ctx* ctx, int c, int m, double* term0, double* te
           if (rc == SPIS_OK) rc = launch_mdot(ctx, Zb, col + 1, x0nz ? ctx->X0 : nullptr, 0, mz, oA);
           // row col of Z^T MZ (MZ_i.z_col, i<col), and v.z_col
           if (rc == SPIS_OK && (col > 0 || C.v)) rc = launch_mdot(ctx, C.MZ, col, C.v, 0, zc, oB);
-        } else if (C.v) {
-          rc = launch_mdot(ctx, nullptr, 0, C.v, 0, zc, oB);
         }
       }
     }
@@ -1302,10 +1316,10 @@ int spis_constraint_terms(spis_ctx* ctx, int c, int m, double* term0, double* te
     TRY(do_allreduce(ctx, ctx->d_cout + (size_t)c0 * 2 * K, (int64_t)(m - c0) * 2 * K, true));
     TRY(d2h(ctx, ctx->h_cout + (size_t)c0 * 2 * K, ctx->d_cout + (size_t)c0 * 2 * K, (size_t)(m - c0) * 2 * K * sizeof(double)));
     if (sym) {
+      const double* vz = ctx->h_cout + (size_t)(m - 1) * 2 * K + K;      // v.z_col, col = c0 .. m-1
       for (const Group& g : groups) {
         const int nw = g.g1 - g.g0;
         const double* base = ctx->h_cout + (size_t)g.g0 * 2 * K;
-        const double* bB = base + (size_t)nw * K;
         for (int cc2 = 0; cc2 < nw; ++cc2) {
           const int col = g.g0 + cc2;
           const double* oA = base + (size_t)cc2 * g.nr;
@@ -1315,23 +1329,22 @@ int spis_constraint_terms(spis_ctx* ctx, int c, int m, double* term0, double* te
           }
           double t1 = 0.0;
           if (x0nz) t1 += oA[g.g1];
-          if (C.v) t1 += bB[cc2];
+          if (C.v) t1 += vz[col - c0];
           C.T1[col] = t1;
         }
       }
+    } else if (!hasM) {
+      const double* vz = ctx->h_cout + (size_t)c0 * 2 * K;
+      for (int col = c0; col < m; ++col) C.T1[col] = C.v ? vz[col - c0] : 0.0;
     } else {
       for (int col = c0; col < m; ++col) {
         const double* oA = ctx->h_cout + (size_t)col * 2 * K;
         const double* oB = oA + K;
         double t1 = 0.0;
-        if (hasM) {
-          for (int i = 0; i <= col; ++i) C.T2[(size_t)i * km + col] = 0.5 * oA[i];
-          if (x0nz) t1 += oA[col + 1];
-          for (int i = 0; i < col; ++i) C.T2[(size_t)col * km + i] = 0.5 * oB[i];
-          if (C.v) t1 += oB[col];
-        } else if (C.v) {
-          t1 += oB[0];
-        }
+        for (int i = 0; i <= col; ++i) C.T2[(size_t)i * km + col] = 0.5 * oA[i];
+        if (x0nz) t1 += oA[col + 1];
+        for (int i = 0; i < col; ++i) C.T2[(size_t)col * km + i] = 0.5 * oB[i];
+        if (C.v) t1 += oB[col];
         C.T1[col] = t1;
       }
     }
@@ -1624,8 +1637,13 @@ int spis_bench_kernel(spis_ctx* ctx, int cls, int m, int reps, double* ms_out, d
   for (int rep = -2; rep < reps && rc == SPIS_OK; ++rep) {
     if (rep == 0) { for (int i = 0; i < SPIS_PROF_CLASSES; ++i) bytes0[i] = ctx->prof_bytes[i]; cudaEventRecord(e0, ctx->stream); }
     switch (cls) {
-      case SPIS_PROF_SPMV: rc = launch_spmv(ctx, SPIS_SLOT_A, 0, ctx->V, nullptr, ctx->T, nullptr); break;
-      case SPIS_PROF_MDOT: rc = launch_mdot(ctx, ctx->V, m, nullptr, 0, ctx->W, ctx->d_small); break;
+      case SPIS_PROF_SPMV: rc = launch_spmv(ctx, SPIS_SLOT_A, m % 3, ctx->V, ctx->W, ctx->T, scal + 3); break;   // m selects the mode
+      case SPIS_PROF_MDOT:
+        if (ctx->bench_mdotm_nw) {       // right-hand sides = the last nw basis rows (resident, distinct from rows 0..m)
+          if (!ctx->G) { rc = dalloc(ctx, &ctx->G, 4 * ld); if (rc != SPIS_OK) break; for (int q = 0; q < 4; ++q) fill_kernel<<<ctx->nsm * 8, 256, 0, ctx->stream>>>(ctx->G + (size_t)q * ld, ctx->n, 0x4242ull + q); }
+          rc = launch_mdotm(ctx, ctx->bench_mdotm_nw, ctx->V, m, nullptr, ctx->G, (int64_t)ld, ctx->d_cout);
+        } else rc = launch_mdot(ctx, ctx->V, m, nullptr, 0, ctx->W, ctx->d_small);
+        break;
       case SPIS_PROF_LINCOMB: rc = launch_lincomb(ctx, ctx->V, m, ctx->d_y, nullptr, -1.0, ctx->W, ctx->T, 1, scal + 3); break;
       case SPIS_PROF_SCALE: rc = launch_scale(ctx, ctx->V, scal + 4, nullptr, nullptr); break;
       case SPIS_PROF_ORTHMID: rc = launch_orth_mid(ctx, ctx->V, m, ctx->d_y, ctx->W, ctx->d_small); break;

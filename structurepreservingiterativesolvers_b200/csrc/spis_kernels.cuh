@@ -719,6 +719,9 @@ spmv_sell_kernel(const int64_t* __restrict__ slice_off, const int32_t* __restric
       const int width = (int)((__ldg(slice_off + slice + 1) - off) >> 5);
       const int32_t* c = cols + off + lane;
       const double* v = vals + off + lane;
+      const int64_t row = (slice << 5) + lane;
+      double bv = 0.0;                               // issued with the first matrix loads, not after the last fma
+      if (MODE != 0 && row < nrows) bv = __ldg(b + row);
       double acc0 = 0.0, acc1 = 0.0;
       int k = 0;
       for (; k + 4 <= width; k += 4) {
@@ -732,16 +735,84 @@ spmv_sell_kernel(const int64_t* __restrict__ slice_off, const int32_t* __restric
       }
       for (; k < width; ++k) acc0 = fma(__ldcs(v + k * 32), __ldg(x + __ldcs(c + k * 32)), acc0);
       const double ax = acc0 + acc1;
-      const int64_t row = (slice << 5) + lane;
       if (row < nrows) {
         if (MODE == 0) {
           y[row] = ax;
         } else if (MODE == 1) {
-          const double r = __ldg(b + row) - ax;
+          const double r = bv - ax;
           y[row] = r;
           ss = fma(r, r, ss);
         } else {
-          const double r = ax - __ldg(b + row);
+          const double r = ax - bv;
+          ss = fma(r, r, ss);
+        }
+      }
+    }
+  }
+  if (MODE == 0) return;
+  ss = warp_sum(ss);
+  if (lane == 0) sred[warp] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int wv = 0; wv < kWarps; ++wv) s += sred[wv];
+    partial[blockIdx.x] = s;
+  }
+  __syncthreads();
+  finish_reduction(partial, 1, 1, counter, sumsq_out, sred, xv, seq);
+}
+
+// K1, pair-packed SELL-32 ("SELL2"): inside a slice the entries of a row are stored two at a time,
+// [pair][lane] -> (value_k, value_k+1) as one double2 and (col_k, col_k+1) as one int2, so a warp moves
+// 512 B of values and 256 B of columns per load instruction: half the memory instructions and half the
+// L1 requests of the scalar layout for the same bytes.  Slice widths are rounded up to even.
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 8)
+spmv_sell2_kernel(const int64_t* __restrict__ slice_off, const int2* __restrict__ cols2,
+                  const double2* __restrict__ vals2, int64_t nrows, const double* __restrict__ x,
+                  const double* __restrict__ b, double* __restrict__ y,
+                  double* __restrict__ partial, unsigned* counter, double* sumsq_out,
+                  XView xv, unsigned long long seq) {
+  __shared__ double sred[kWarps * 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t nslices = (nrows + 31) >> 5;
+  const int64_t nblocks = (nslices + kWarps - 1) / kWarps;
+  double ss = 0.0;
+  for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    const int64_t slice = blk * kWarps + warp;
+    if (slice < nslices) {
+      const int64_t off = __ldg(slice_off + slice);                    // in entries, a multiple of 64
+      const int npair = (int)((__ldg(slice_off + slice + 1) - off) >> 6);
+      const int2* c = cols2 + (off >> 1) + lane;
+      const double2* v = vals2 + (off >> 1) + lane;
+      const int64_t row = (slice << 5) + lane;
+      double bv = 0.0;
+      if (MODE != 0 && row < nrows) bv = __ldg(b + row);
+      double acc0 = 0.0, acc1 = 0.0;
+      int p = 0;
+      for (; p + 2 <= npair; p += 2) {
+        const int2 c0 = __ldcs(c + (p + 0) * 32), c1 = __ldcs(c + (p + 1) * 32);
+        const double2 v0 = __ldcs(v + (p + 0) * 32), v1 = __ldcs(v + (p + 1) * 32);
+        const double x0 = __ldg(x + c0.x), x1 = __ldg(x + c0.y), x2 = __ldg(x + c1.x), x3 = __ldg(x + c1.y);
+        acc0 = fma(v0.x, x0, acc0); acc1 = fma(v0.y, x1, acc1);
+        acc0 = fma(v1.x, x2, acc0); acc1 = fma(v1.y, x3, acc1);
+      }
+      if (p < npair) {
+        const int2 c0 = __ldcs(c + p * 32);
+        const double2 v0 = __ldcs(v + p * 32);
+        acc0 = fma(v0.x, __ldg(x + c0.x), acc0); acc1 = fma(v0.y, __ldg(x + c0.y), acc1);
+      }
+      const double ax = acc0 + acc1;
+      if (row < nrows) {
+        if (MODE == 0) {
+          y[row] = ax;
+        } else if (MODE == 1) {
+          const double r = bv - ax;
+          y[row] = r;
+          ss = fma(r, r, ss);
+        } else {
+          const double r = ax - bv;
           ss = fma(r, r, ss);
         }
       }
@@ -857,6 +928,32 @@ __global__ void sell_fill_kernel(const int32_t* __restrict__ indptr, const int32
     if (k < len) { c = cols_in[p0 + k]; v = vals_in[p0 + k]; }
     cols[off + (int64_t)k * 32 + lane] = c;
     vals[off + (int64_t)k * 32 + lane] = v;
+  }
+}
+
+// pair-packed variant of sell_fill_kernel (slice widths are even): entry k of a row goes to element
+// (k & 1) of pair (k >> 1)
+__global__ void sell2_fill_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ cols_in,
+                                  const double* __restrict__ vals_in, int64_t nrows,
+                                  const int64_t* __restrict__ slice_off, int32_t* __restrict__ cols,
+                                  double* __restrict__ vals) {
+  const int64_t slice = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t nslices = (nrows + 31) >> 5;
+  if (slice >= nslices) return;
+  const int64_t row = (slice << 5) + lane;
+  const int64_t off = slice_off[slice];
+  const int width = (int)((slice_off[slice + 1] - off) >> 5);
+  int32_t p0 = 0, len = 0;
+  if (row < nrows) { p0 = indptr[row]; len = indptr[row + 1] - p0; }
+  int32_t padcol = 0;
+  if (len > 0) padcol = cols_in[p0 + len - 1];
+  for (int k = 0; k < width; ++k) {
+    int32_t c = padcol; double v = 0.0;
+    if (k < len) { c = cols_in[p0 + k]; v = vals_in[p0 + k]; }
+    const int64_t at = off + ((int64_t)(k >> 1) * 32 + lane) * 2 + (k & 1);
+    cols[at] = c;
+    vals[at] = v;
   }
 }
 

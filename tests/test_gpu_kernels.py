@@ -26,7 +26,7 @@ def ragged_matrix(n, seed, max_len=40, empty_every=7):
     return sps.csr_matrix((vals, cols, indptr), shape=(n, n))
 
 
-@pytest.mark.parametrize("fmt", [nat.FMT_SELL, nat.FMT_CSR, nat.FMT_AUTO])
+@pytest.mark.parametrize("fmt", [nat.FMT_SELL, nat.FMT_SELL2, nat.FMT_CSR, nat.FMT_AUTO])
 @pytest.mark.parametrize("n", [1, 31, 32, 33, 1000, 4097])
 def test_spmv_ragged(n, fmt):
     A = ragged_matrix(n, seed=n) if n > 40 else sps.random(n, n, density=0.6, random_state=n, format="csr")
@@ -55,7 +55,7 @@ def test_spmv_duplicates_and_unsorted_indices():
     np.testing.assert_allclose(y, A @ x, rtol=0, atol=1e-12)
 
 
-@pytest.mark.parametrize("fmt", [nat.FMT_SELL, nat.FMT_CSR])
+@pytest.mark.parametrize("fmt", [nat.FMT_SELL, nat.FMT_SELL2, nat.FMT_CSR])
 def test_spmv_fem_operators(fmt):
     d, _ = lkdv.linforms(space="CG", M=33_350, mlength=0.8 * 33_350)        # n = 100 050
     h, _ = heat.linforms(M=150)

@@ -42,7 +42,7 @@ def main():
             up = time.time() - t0
             for ctas in (2, 4, 8, 16):
                 ctx.set_option("spmv_ctas_per_sm", ctas)
-                ms, by = ctx.bench_kernel(nat.PROF_SPMV, 1, reps=20)
+                ms, by = ctx.bench_kernel(nat.PROF_SPMV, 0, reps=20)
                 rows.append(dict(kernel="spmv", fmt=fmt, ctas=ctas, ms=ms, gbs=by / ms * 1e-6, upload_s=up))
                 print(rows[-1], flush=True)
         ctx.set_option("spmv_format", nat.FMT_SELL)

@@ -1,0 +1,26 @@
+#!/usr/bin/env python
+"""SpMV formats x modes x grid sizes on the two benchmark matrices (n = 1e7), resident data."""
+import os, sys, json, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench
+from structurepreservingiterativesolvers_b200 import _native as nat
+from structurepreservingiterativesolvers_b200.device import KrylovContext
+
+rows = []
+for wl in (sys.argv[1:] or ["lkdv", "swe"]):
+    dic, x0, cl, _ = bench.build_system(10_000_000, wl)
+    A = dic["A"]; n = A.shape[0]
+    with KrylovContext(n, 4) as ctx:
+        ctx.upload_vec(nat.VEC_B, dic["b"])
+        for fmt, name in ((nat.FMT_SELL, "sell"), (nat.FMT_SELL2, "sell2")):
+            ctx.set_option("spmv_format", fmt)
+            ctx.upload_matrix(nat.SLOT_A, A)
+            for ctas in (4, 8):
+                ctx.set_option("spmv_ctas_per_sm", ctas)
+                for mode in (0, 2):
+                    ms, by = ctx.bench_kernel(nat.PROF_SPMV, mode, reps=20)
+                    rows.append(dict(workload=wl, fmt=name, ctas=ctas, mode=mode, us=ms * 1e3, gbs=by / ms * 1e-6,
+                                     nnz_padded=ctx.info("nnz_padded:0")))
+                    print(json.dumps(rows[-1]), flush=True)
+json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "tune_spmv.json"), "w"), indent=1)
