@@ -154,6 +154,10 @@ int spis_arnoldi_wait(spis_ctx* ctx, int j, double* hcol_out);
 int spis_arnoldi_step(spis_ctx* ctx, int j, double* hcol_out);
 /* x_j = x0 + Z[:, :m] y ; resnorm = ||A x_j - b||                  (solvers.py:287,290) */
 int spis_iterate_residual(spis_ctx* ctx, int m, const double* y, double* resnorm_out);
+/* the same in two halves: after _launch the host may fetch the next Hessenberg column and queue the
+ * Arnoldi step after it; _wait blocks only until the residual norm of THIS pair has arrived           */
+int spis_iterate_residual_launch(spis_ctx* ctx, int m, const double* y);
+int spis_iterate_residual_wait(spis_ctx* ctx, double* resnorm_out);
 /* only x = x0 + Z[:, :m] y (lazy re-materialisation of dict['x'][j], solvers.py:318)    */
 int spis_form_iterate(spis_ctx* ctx, int m, const double* y);
 

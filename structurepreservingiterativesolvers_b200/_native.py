@@ -58,6 +58,8 @@ SIGNATURES = {
     "spis_arnoldi_wait": (C.c_int, [_ctx, C.c_int, _dp]),
     "spis_arnoldi_step": (C.c_int, [_ctx, C.c_int, _dp]),
     "spis_iterate_residual": (C.c_int, [_ctx, C.c_int, _dp, _dp]),
+    "spis_iterate_residual_launch": (C.c_int, [_ctx, C.c_int, _dp]),
+    "spis_iterate_residual_wait": (C.c_int, [_ctx, _dp]),
     "spis_form_iterate": (C.c_int, [_ctx, C.c_int, _dp]),
     "spis_constraint_define": (C.c_int, [_ctx, C.c_int, C.c_int, _dp, C.c_double]),
     "spis_constraint_terms": (C.c_int, [_ctx, C.c_int, C.c_int, _dp, _dp, _dp]),

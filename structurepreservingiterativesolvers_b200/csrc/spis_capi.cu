@@ -102,6 +102,7 @@ struct spis_ctx {
   double* h_y = nullptr;        // pinned K
   double* h_cout = nullptr;     // pinned kmax*2K
   cudaEvent_t ev_arnoldi = nullptr;
+  cudaEvent_t ev_resid = nullptr; double* h_resid = nullptr; bool resid_inflight = false;   // pinned residual slot of its own
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
   int arnoldi_inflight = -1;
   bool began = false;
@@ -772,6 +773,7 @@ int spis_ctx_create(int device, int64_t n, int64_t n_halo, int k_max, void* stre
   else { CCU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
   CCU(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
   CCU(cudaEventCreateWithFlags(&c->ev_arnoldi, cudaEventDisableTiming));
+  CCU(cudaEventCreateWithFlags(&c->ev_resid, cudaEventDisableTiming));
   CCU(cudaEventCreate(&c->ev_t0));
   CCU(cudaEventCreate(&c->ev_t1));
   pt.mark("streams + events");
@@ -797,6 +799,7 @@ int spis_ctx_create(int device, int64_t n, int64_t n_halo, int k_max, void* stre
   pt.mark("device blocks");
   if (spis_pinned_alloc(((size_t)2 * c->K + 8) * sizeof(double), (void**)&c->h_small) != SPIS_OK ||
       spis_pinned_alloc((size_t)c->K * sizeof(double), (void**)&c->h_y) != SPIS_OK ||
+      spis_pinned_alloc(64, (void**)&c->h_resid) != SPIS_OK ||
       spis_pinned_alloc((size_t)k_max * 2 * c->K * sizeof(double), (void**)&c->h_cout) != SPIS_OK) {
     fail(c, SPIS_E_NOMEM, "pinned host allocation failed: %s", g_global_err);
     return bail(SPIS_E_NOMEM);
@@ -853,8 +856,9 @@ int spis_ctx_destroy(spis_ctx* ctx) {
   for (int r = 0; r < kMaxRanks; ++r)
     if (ctx->xpeer[r]) cudaIpcCloseMemHandle(ctx->xpeer[r]);
   if (ctx->xbuf) cudaFree(ctx->xbuf);
-  spis_pinned_free(ctx->h_small); spis_pinned_free(ctx->h_y); spis_pinned_free(ctx->h_cout);
+  spis_pinned_free(ctx->h_small); spis_pinned_free(ctx->h_y); spis_pinned_free(ctx->h_cout); spis_pinned_free(ctx->h_resid);
   if (ctx->ev_arnoldi) cudaEventDestroy(ctx->ev_arnoldi);
+  if (ctx->ev_resid) cudaEventDestroy(ctx->ev_resid);
   if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
   if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
   if (ctx->aux) cudaStreamDestroy(ctx->aux);
@@ -1047,6 +1051,7 @@ int spis_solve_begin(spis_ctx* ctx, double* beta_out) {
   }
   ctx->began = true;
   ctx->arnoldi_inflight = -1;
+  ctx->resid_inflight = false;
   return SPIS_OK;
 }
 
@@ -1149,18 +1154,35 @@ int spis_form_iterate(spis_ctx* ctx, int m, const double* y) {
   return SPIS_OK;
 }
 
-int spis_iterate_residual(spis_ctx* ctx, int m, const double* y, double* resnorm_out) {
+int spis_iterate_residual_launch(spis_ctx* ctx, int m, const double* y) {
   if (!ctx) return SPIS_E_INVALID;
-  REQUIRE(resnorm_out, "resnorm_out is null");
+  REQUIRE(!ctx->resid_inflight, "an iterate/residual pair is still in flight");
   TRY(form_iterate_impl(ctx, m, y));
   double* scal = ctx->d_small + 2 * ctx->K;
   // ||A x_j - b||                                                  (solvers.py:290)
   TRY(do_halo(ctx, ctx->X));
   TRY(launch_spmv(ctx, SPIS_SLOT_A, 2, ctx->X, ctx->B, nullptr, scal + 2));
-  CU(cudaMemcpyAsync(ctx->h_small + 2 * ctx->K + 2, scal + 2, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
-  *resnorm_out = std::sqrt(ctx->h_small[2 * ctx->K + 2]);
+  CU(cudaMemcpyAsync(ctx->h_resid, scal + 2, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaEventRecord(ctx->ev_resid, ctx->stream));
+  ctx->resid_inflight = true;
   return SPIS_OK;
+}
+
+int spis_iterate_residual_wait(spis_ctx* ctx, double* resnorm_out) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(resnorm_out, "resnorm_out is null");
+  REQUIRE(ctx->resid_inflight, "no iterate/residual pair in flight");
+  CU(cudaEventSynchronize(ctx->ev_resid));      // later work queued on the stream (the next Arnoldi step) is not waited for
+  ctx->resid_inflight = false;
+  *resnorm_out = std::sqrt(*ctx->h_resid);
+  return SPIS_OK;
+}
+
+int spis_iterate_residual(spis_ctx* ctx, int m, const double* y, double* resnorm_out) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(resnorm_out, "resnorm_out is null");
+  TRY(spis_iterate_residual_launch(ctx, m, y));
+  return spis_iterate_residual_wait(ctx, resnorm_out);
 }
 
 // ---- constraint stage -----------------------------------------------------------------

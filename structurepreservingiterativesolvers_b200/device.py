@@ -150,6 +150,15 @@ class KrylovContext:
         self._check(self._lib.spis_iterate_residual(self._h, y.size, nat.dptr(y), C.byref(res)))
         return res.value
 
+    def iterate_residual_launch(self, y):
+        y = nat.as_f64(y)
+        self._check(self._lib.spis_iterate_residual_launch(self._h, y.size, nat.dptr(y)))
+
+    def iterate_residual_wait(self) -> float:
+        res = C.c_double(0.0)
+        self._check(self._lib.spis_iterate_residual_wait(self._h, C.byref(res)))
+        return res.value
+
     def form_iterate(self, y):
         y = nat.as_f64(y)
         self._check(self._lib.spis_form_iterate(self._h, y.size, nat.dptr(y)))

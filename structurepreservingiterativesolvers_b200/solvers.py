@@ -433,6 +433,7 @@ class _Arnoldi:
         self.sess, self.k, self.lookahead = sess, k, bool(lookahead)
         self.H = np.zeros((k + 1, k))
         self._inflight = None
+        self._have = -1
         # Givens recurrence of the unconstrained least-squares residual |beta e1 - H y|_min: used only
         # to decide whether launching the NEXT Arnoldi step ahead of time can be wasted work
         self._cs = np.zeros(k)
@@ -440,10 +441,17 @@ class _Arnoldi:
         self._g = None if beta is None else float(beta)
 
     def column(self, j):
+        if self._have == j:                   # fetched while the previous iterate/residual pair ran
+            return self.H[: j + 2, j].copy()
         if self._inflight != j:
             self.sess.arnoldi_launch(j)
         col = self.sess.arnoldi_wait(j)
         self._inflight = None
+        self._store(j, col)
+        return col
+
+    def _store(self, j, col):
+        self._have = j
         self.H[: j + 2, j] = col
         if self._g is not None:
             r = np.array(col, dtype=np.float64)
@@ -457,7 +465,26 @@ class _Arnoldi:
                 self._g = -self._sn[j] * self._g
             else:
                 self._g = None
-        return col
+
+    def residual(self, yk, j, may_end, tol=None):
+        """x_j = x0 + Z yk and ||A x_j - b|| (solvers.py:287,290).  While the device works on them the host
+        collects Hessenberg column j+1 (its Arnoldi step was queued BEFORE this pair) and, unless the loop
+        is about to end, queues step j+2 BEHIND the pair: the device never waits for the host."""
+        ctx = self.sess.ctx
+        if not (self.lookahead and hasattr(ctx, "iterate_residual_launch")):
+            return ctx.iterate_residual(yk)
+        ctx.iterate_residual_launch(yk)
+        if self._inflight == j + 1:
+            col = self.sess.arnoldi_wait(j + 1)
+            self._inflight = None
+            self._store(j + 1, col)
+            # step j+2 is only useful if neither this iteration nor the next one ends the loop; the next
+            # one can only end if even its unconstrained minimiser is below tol (known now, from column j+1)
+            next_may_end = tol is not None and self.ls_residual() < tol
+            if not may_end and not next_may_end and col[j + 2] != 0 and j + 2 < self.k:
+                self.sess.arnoldi_launch(j + 2)
+                self._inflight = j + 2
+        return ctx.iterate_residual_wait()
 
     def ls_residual(self):
         """min_y |beta e1 - H_j y| after the last column() (inf when not tracked)."""
@@ -539,7 +566,7 @@ def gmres(A, b, x0, k, tol=1e-50, pre=None, *, session=None, lookahead=None, his
         if not arn.ls_residual() < tol:                   # this step cannot be the last: run ahead
             arn.prefetch(j + 1)
         yk = smallsolve.lstsq(arn.H[: j + 2, : j + 1], beta).x        # (solvers.py:113)
-        residual.append(sess.ctx.iterate_residual(yk))    # x_j and ||A x_j - b|| (solvers.py:115-116)
+        residual.append(arn.residual(yk, j, arn.ls_residual() < tol, tol))   # x_j and ||A x_j - b|| (solvers.py:115-116)
         hist._append(yk)
         if residual[-1] < tol:
             break
@@ -643,7 +670,7 @@ def cgmres(A, b, x0, k, tol=1e-8, contol=10, conlist=[], pre=None, timing=None, 
         _warn_message(j, res)
         yk = res.x
         bk.mark("small solve + host")
-        residual.append(sess.ctx.iterate_residual(yk))    # (solvers.py:287,290)
+        residual.append(arn.residual(yk, j, arn.predicted_residual(yk, beta) < tol, tol))   # (solvers.py:287,290)
         bk.mark("iterate+residual")
         hist._append(yk)
         if timing:
@@ -711,7 +738,7 @@ def cgmres_p(A, b, x0, k, conlist=[], pre=None, *, session=None, small_solver=No
             res = _unconstrained(engine, Hj, beta, y0, 1e-20)
         _warn_message(j, res)
         yk = res.x
-        residual.append(sess.ctx.iterate_residual(yk))    # (solvers.py:434-437)
+        residual.append(arn.residual(yk, j, False))       # (solvers.py:434-437)
         hist._append(yk)
     arn.drain()
     x_last = sess.ctx.download(nat.VEC_X, pinned=True) if len(hist) > 1 else hist[0]

@@ -172,6 +172,15 @@ class FakeKrylovContext:
         self.Xfull[: self.n] = self.vecs[nat.VEC_X0] + self._Z()[: y.size, : self.n].T @ y
         self.X = self.Xfull[: self.n]
 
+    def iterate_residual_launch(self, y):
+        self._resid = self.iterate_residual(y)
+        self.log.append(("iterate_residual_launch", len(y)))
+
+    def iterate_residual_wait(self):
+        r, self._resid = self._resid, None
+        assert r is not None
+        return r
+
     def iterate_residual(self, y):
         self.form_iterate(y)
         self.log.append(("iterate", len(y)))
