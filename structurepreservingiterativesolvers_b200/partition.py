@@ -73,6 +73,11 @@ class FieldBlockPartition:
     def n_local(self, r):
         return int(self.nfields * (self.starts[r + 1] - self.starts[r]))
 
+    def owned_ranges(self, r):
+        """[(global_lo, global_hi, local_start)]: the owned unknowns as contiguous global ranges."""
+        w = int(self.starts[r + 1] - self.starts[r])
+        return [(f * self.N + int(self.starts[r]), f * self.N + int(self.starts[r + 1]), f * w) for f in range(self.nfields)]
+
 
 class StripPartition:
     """Several fields of DIFFERENT densities over the same `nblocks` mesh blocks (2-D strips).
@@ -118,6 +123,16 @@ class StripPartition:
     def block_range(self, r):
         return int(self.starts[r]), int(self.starts[r + 1])
 
+    def owned_ranges(self, r):
+        b0, b1 = int(self.starts[r]), int(self.starts[r + 1])
+        out, lstart = [], 0
+        for f in range(self.bs.size):
+            lo = int(self.field_off[f] + b0 * self.bs[f])
+            hi = int(self.field_off[f] + b1 * self.bs[f])
+            out.append((lo, hi, lstart))
+            lstart += hi - lo
+        return out
+
 
 class HaloPlan:
     """Ghost layout of one rank: ghost global ids ordered by (owner, id), counts per source rank;
@@ -153,13 +168,26 @@ def localize(mats, part, rank):
     for m in mats:
         if m.shape[0] != n_r:
             raise ValueError(f"rank {rank} owns {n_r} rows, matrix has {m.shape[0]}")
-    off = []
-    masks = []
+    # Column classification.  Partitions that own contiguous global ranges (mesh blocks) are handled with
+    # range comparisons on the int32 index arrays as they are -- a 1e8-unknown strip has 6e8 entries, and
+    # the generic path (int64 copies, searchsorted per entry) costs minutes and tens of GB there.
+    ranges = part.owned_ranges(rank) if hasattr(part, "owned_ranges") else None
+    off, news = [], []
     for m in mats:
-        cols = m.indices.astype(np.int64)
-        own = part.owner_of(cols) == rank
-        masks.append(own)
-        off.append(np.unique(cols[~own]))
+        cols = m.indices
+        if ranges is not None:
+            new = np.full(cols.size, -1, dtype=np.int32)
+            for lo, hi, lstart in ranges:
+                sel = (cols >= lo) & (cols < hi)
+                new[sel] = cols[sel] - (lo - lstart)
+            own = new >= 0
+        else:
+            c64 = cols.astype(np.int64)
+            own = part.owner_of(c64) == rank
+            new = np.full(cols.size, -1, dtype=np.int64)
+            new[own] = part.local_of(c64[own])
+        news.append((new, own))
+        off.append(np.unique(cols[~own]).astype(np.int64))
     ghost = np.unique(np.concatenate(off)) if off else np.zeros(0, dtype=np.int64)
     gowner = part.owner_of(ghost) if ghost.size else np.zeros(0, dtype=np.int64)
     order = np.lexsort((ghost, gowner))                   # by owner, then global id
@@ -167,14 +195,11 @@ def localize(mats, part, rank):
     by_gid = np.argsort(ghost, kind="stable")
     ghost_sorted = ghost[by_gid]
     out = []
-    for m, own in zip(mats, masks):
-        cols = m.indices.astype(np.int64)
-        new = np.empty(cols.size, dtype=np.int64)
-        new[own] = part.local_of(cols[own])
+    for m, (new, own) in zip(mats, news):
         if (~own).any():
-            pos = np.searchsorted(ghost_sorted, cols[~own])
+            pos = np.searchsorted(ghost_sorted, m.indices[~own].astype(np.int64))
             new[~own] = n_r + by_gid[pos]
-        out.append(sps.csr_matrix((m.data, new.astype(np.int32), m.indptr), shape=(n_r, n_r + ghost.size)))
+        out.append(sps.csr_matrix((m.data, new.astype(np.int32, copy=False), m.indptr), shape=(n_r, n_r + ghost.size)))
     return out, HaloPlan(rank, part.P, ghost, gowner)
 
 

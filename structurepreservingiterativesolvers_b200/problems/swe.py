@@ -217,19 +217,30 @@ class _Stencil:
         i, j = i.reshape(-1), j.reshape(-1)
         idx_dtype = np.int32 if (NU + NR) * M * M < 2**31 - 1 else np.int64
         blocks = []
+        base_u, base_r = {}, {}                                   # first unknown of the neighbour square, per offset
+
+        def bases(d_i, d_j):
+            key = (int(d_i), int(d_j))
+            if key not in base_u:
+                sq = ((j + d_j) % M) * M + (i + d_i) % M
+                base_u[key] = (NU * sq).astype(idx_dtype)
+                base_r[key] = (nu + NR * sq).astype(idx_dtype)
+            return base_u[key], base_r[key]
+
         for first, last, width in ((0, NU, self.len_u), (NU, NU + NR, self.len_r)):
-            ind = np.empty((nsq, width), dtype=idx_dtype)
-            dat = np.empty((nsq, width))
-            lens = []
+            ind = np.empty((width, nsq), dtype=idx_dtype)         # filled row by row (contiguous), transposed once
+            lens, vrow = [], []
             pos = 0
             for di, dj, is_rho, local, vals in self.rows[first:last]:
                 for e in range(len(di)):
-                    sq = ((j + dj[e]) % M) * M + (i + di[e]) % M
-                    ind[:, pos] = (nu + NR * sq + local[e]) if is_rho[e] else (NU * sq + local[e])
-                    dat[:, pos] = vals[e]
+                    bu, br = bases(di[e], dj[e])
+                    np.add(br if is_rho[e] else bu, idx_dtype(local[e]), out=ind[pos])
                     pos += 1
                 lens.append(len(di))
-            blocks.append((ind.reshape(-1), dat.reshape(-1), np.tile(np.array(lens, dtype=np.int64), nsq)))
+                vrow.append(vals)
+            blocks.append((np.ascontiguousarray(ind.T).reshape(-1), np.tile(np.concatenate(vrow), nsq),
+                           np.tile(np.array(lens, dtype=np.int64), nsq)))
+            del ind
         indices = np.concatenate([blocks[0][0], blocks[1][0]])
         data = np.concatenate([blocks[0][1], blocks[1][1]])
         lens = np.concatenate([blocks[0][2], blocks[1][2]])
@@ -241,6 +252,35 @@ class _Stencil:
         if sort or (sort is None and M <= 400):
             out.sort_indices()
         return out
+
+
+def _stencil_apply(st, M, z, j0=0, j1=None):
+    """(operator @ z) for the rows of strips [j0, j1) without forming the operator: one gather of z per
+    stencil entry.  z is a FULL state vector.  Used for b = B z0 on 1e8-unknown strips, where B would be
+    a second 7.5 GB matrix alive only for this product."""
+    j1 = M if j1 is None else j1
+    nsq = (j1 - j0) * M
+    nu = NU * M * M
+    i, j = np.meshgrid(np.arange(M, dtype=np.int64), np.arange(j0, j1, dtype=np.int64), indexing="xy")
+    i, j = i.reshape(-1), j.reshape(-1)
+    out_u = np.zeros((nsq, NU))
+    out_r = np.zeros((nsq, NR))
+    sq_cache = {}
+    for rt, (di, dj, is_rho, local, vals) in enumerate(st.rows):
+        acc = np.zeros(nsq)
+        for e in range(len(di)):
+            if vals[e] == 0.0:
+                continue
+            key = (int(di[e]), int(dj[e]))
+            if key not in sq_cache:
+                sq_cache[key] = ((j + dj[e]) % M) * M + (i + di[e]) % M
+            sq = sq_cache[key]
+            acc += vals[e] * (z[nu + NR * sq + local[e]] if is_rho[e] else z[NU * sq + local[e]])
+        if rt < NU:
+            out_u[:, rt] = acc
+        else:
+            out_r[:, rt - NU] = acc
+    return np.concatenate([out_u.reshape(-1), out_r.reshape(-1)])
 
 
 _STENCIL_CACHE = {}
@@ -297,8 +337,9 @@ def linforms(N=100, M=50, degree=1, T=10, zinit=None, mlength=None, rows=None, m
         areas2 = None
     else:
         sA, sB, sL, areas2 = _stencils(prob)
-        A, B, L = (s.replicate(M, j0, j1, sort=sort) for s in (sA, sB, sL))
-    b = B @ z0_full
+        A, L = (s.replicate(M, j0, j1, sort=sort) for s in (sA, sL))
+        B = None
+    b = B @ z0_full if B is not None else _stencil_apply(sB, M, z0_full, j0, j1)
     area0, area1 = (0.5 * prob.h ** 2, 0.5 * prob.h ** 2)
     omega_full_rho = np.empty(NR * M * M)
     omega_full_rho[0::2], omega_full_rho[1::2] = area0, area1
