@@ -451,7 +451,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=10_000_000)
+    ap.add_argument("--n", "--dofs", dest="n", type=int, default=10_000_000)   # --dofs: torchrun rejects a bare --n as ambiguous
     ap.add_argument("--workload", default="lkdv", choices=sorted(WORKLOADS))
     ap.add_argument("--small-solver", default="kkt", choices=["kkt", "slsqp"])
     ap.add_argument("--e2e-steps", type=int, default=3)
