@@ -13,7 +13,7 @@ from structurepreservingiterativesolvers_b200 import _native as nat
 from structurepreservingiterativesolvers_b200 import solvers, wrappers
 from structurepreservingiterativesolvers_b200.preconditioners import (BlockJacobiPreconditioner,
                                                                       JacobiPreconditioner)
-from structurepreservingiterativesolvers_b200.problems import heat, lkdv
+from structurepreservingiterativesolvers_b200.problems import heat, lkdv, swe
 
 pytestmark = pytest.mark.gpu
 
@@ -204,6 +204,34 @@ def test_full_size_properties():
     q3, q7 = sess.ctx.download(nat.VEC_Q, 3), sess.ctx.download(nat.VEC_Q, 7)
     assert abs(q3 @ q3 - 1.0) <= 1e-13 and abs(q3 @ q7) <= 1e-13
     sess.close()
+
+
+def test_full_size_properties_swe():
+    """BASELINE configs[2] size (swe RT2 x DG0, n = 10 002 828, 12.5 entries per row): the solve
+    converges, the device residual equals the host-recomputed one, mass and energy are conserved to the
+    reference's level, and both SELL layouts give the same iterate to rounding."""
+    M = swe.benchmark_size(10_000_000)
+    d, _ = swe.linforms(M=M, mlength=0.8 * M, sort=False)
+    A, b = d["A"], d["b"]
+    n = b.size
+    assert n == 12 * M * M and A.nnz == int(12.5 * n)
+    x0 = np.zeros(n)
+    cl = wrappers.swe.conlist(d, x0)
+    xs = {}
+    for fmt in ("sell", "sell2"):
+        sess = solvers.DeviceSession(A, b, x0, 30, conlist=cl, spmv_format=fmt)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            x, info = solvers.cgmres(A, b, x0, 30, tol=1e-7, contol=10, conlist=cl, small_solver="kkt",
+                                     session=sess, timing=True)
+        assert info["steps"] < 30 and info["res"][-1] < 1e-7
+        assert abs(np.linalg.norm(A @ x - b) - info["res"][-1]) <= 1e-11 * np.linalg.norm(b)
+        inv = swe.compute_invariants(d, x)
+        assert abs(inv["mass"] - d["m0"]) <= 1e-12 * abs(d["m0"])
+        assert abs(inv["energy"] - d["e0"]) <= 1e-12 * abs(d["e0"])
+        xs[fmt] = x
+        sess.close()
+    assert helpers.rel_diff(xs["sell"], xs["sell2"]) <= 1e-12
 
 
 @pytest.mark.parametrize("x0_zero", [True, False])
