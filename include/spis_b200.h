@@ -73,10 +73,11 @@ extern "C" {
 #define SPIS_ORTH_MGS     2   /* modified Gram-Schmidt, the reference's loop solvers.py:193-195 */
 
 /* SpMV storage formats for spis_set_option("spmv_format", ...) */
-#define SPIS_FMT_AUTO     0   /* SELL-32 unless padding overhead > 25 % */
+#define SPIS_FMT_AUTO     0   /* row patterns if the matrix has few distinct stencils, else SELL-32, CSR if padding > 25 % */
 #define SPIS_FMT_SELL     1
 #define SPIS_FMT_CSR      2
 #define SPIS_FMT_SELL2     3   /* SELL-32 with the entries of a row packed in pairs (128-bit value loads) */
+#define SPIS_FMT_PATTERN   4   /* 16-bit stencil id per row + stencil table (matrices with <= 4096 distinct rows) */
 
 /* timer classes returned by spis_get_profile (CUDA-event time, algorithmic bytes, launches) */
 #define SPIS_PROF_SPMV     0   /* system matrix A: A z_j, b - A x0, ||A x_j - b||          */

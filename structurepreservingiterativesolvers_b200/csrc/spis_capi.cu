@@ -37,6 +37,9 @@ struct Matrix {
   int32_t* scols = nullptr;
   double* svals = nullptr;
   int csr_lanes = 8;
+  // row-pattern storage (SPIS_FMT_PATTERN)
+  uint16_t* pid = nullptr; int32_t* tab_len = nullptr; int32_t* tab_off = nullptr; double* tab_val = nullptr;
+  int npat = 0, patW = 0;
 };
 
 struct Constraint {
@@ -79,6 +82,7 @@ struct spis_ctx {
   int fuse_jacobi = 1;
   int mdotm_ctas_per_sm = 4;       // tools/tune_mdotm.py: 5.1-5.5 TB/s at 4, 3.5-4.8 at 2, 3.8-4.3 at 8
   int bench_mdotm_nw = 0;       // tuning: spis_bench_kernel(SPIS_PROF_MDOT) times mdotm_kernel<nw> instead
+  int auto_pattern = 1;         // spmv_format=auto first tries the row-pattern storage (few distinct stencils)
   int auto_sell2 = 0;           // spmv_format=auto picks the pair-packed SELL layout
   int force_nonsymmetric = 0;   // tests: take the general (stored M Z) path of the constraint stage
   int orth_fused = 1;           // CGS2: fuse (w -= V h1) with (h2 = V^T w) through TMA-staged tiles
@@ -464,6 +468,10 @@ int launch_spmv_mode(spis_ctx* ctx, const Matrix& M, const double* x, const doub
     const int64_t nslices = (M.nrows + 31) / 32;
     const int grid = grid_for(ctx, (nslices + kWarps - 1) / kWarps, ctx->spmv_ctas_per_sm);
     spmv_sell_kernel<MODE><<<grid, kThreads, 0, ctx->stream>>>(M.slice_off, M.scols, M.svals, M.nrows, x, b, y, ctx->d_partial, ctx->d_counter, sumsq_out, xv, seq);
+  } else if (M.fmt == SPIS_FMT_PATTERN) {
+    const int grid = grid_for(ctx, (M.nrows + kThreads - 1) / kThreads, ctx->spmv_ctas_per_sm);
+    spmv_pattern_kernel<MODE><<<grid, kThreads, 0, ctx->stream>>>(M.pid, M.patW, M.tab_len, M.tab_off, M.tab_val, M.nrows, x, b, y, ctx->d_partial);
+    if (MODE != 0) reduce_partials_kernel<<<1, kThreads, 0, ctx->stream>>>(ctx->d_partial, grid, sumsq_out, xv, seq);
   } else if (M.fmt == SPIS_FMT_SELL2) {
     const int64_t nslices = (M.nrows + 31) / 32;
     const int grid = grid_for(ctx, (nslices + kWarps - 1) / kWarps, ctx->spmv_ctas_per_sm);
@@ -542,6 +550,7 @@ int launch_precond(spis_ctx* ctx, const double* q, double* z) {
 void free_matrix(spis_ctx* ctx, Matrix& M) {
   dfree(ctx, M.indptr); dfree(ctx, M.cols); dfree(ctx, M.vals);
   dfree(ctx, M.slice_off); dfree(ctx, M.scols); dfree(ctx, M.svals);
+  dfree(ctx, M.pid); dfree(ctx, M.tab_len); dfree(ctx, M.tab_off); dfree(ctx, M.tab_val);
   M = Matrix();
 }
 
@@ -871,8 +880,9 @@ int spis_set_option(spis_ctx* ctx, const char* key, int64_t value) {
   if (!ctx || !key) return SPIS_E_INVALID;
   std::string k(key);
   if (k == "orth") { REQUIRE(value >= 0 && value <= 2, "orth must be 0..2"); ctx->orth = (int)value; }
-  else if (k == "spmv_format") { REQUIRE(value >= 0 && value <= 3, "spmv_format must be 0..3"); ctx->fmt_pref = (int)value; }
+  else if (k == "spmv_format") { REQUIRE(value >= 0 && value <= 4, "spmv_format must be 0..4"); ctx->fmt_pref = (int)value; }
   else if (k == "auto_sell2") { ctx->auto_sell2 = value ? 1 : 0; }
+  else if (k == "auto_pattern") { ctx->auto_pattern = value ? 1 : 0; }
   else if (k == "mdotm_ctas_per_sm") { REQUIRE(value >= 1 && value <= 8, "mdotm_ctas_per_sm must be 1..8"); ctx->mdotm_ctas_per_sm = (int)value; }
   else if (k == "bench_mdotm_nw") { REQUIRE(value == 0 || value == 2 || value == 4, "bench_mdotm_nw must be 0, 2 or 4"); ctx->bench_mdotm_nw = (int)value; }
   else if (k == "profile") { ctx->profile = value ? 1 : 0; }
@@ -909,6 +919,11 @@ int spis_get_info(const spis_ctx* cctx, const char* key, int64_t* value_out) {
     else if (k.rfind("nnz_padded:", 0) == 0) *value_out = ctx->mats[slot].nnz_padded;
     else *value_out = ctx->mats[slot].nnz;
   }
+  else if (k.rfind("npat:", 0) == 0) {
+    const int slot = atoi(k.c_str() + 5);
+    REQUIRE(slot >= 0 && slot < SPIS_MAX_SLOTS && ctx->mats[slot].present, "slot %d not uploaded", slot);
+    *value_out = ctx->mats[slot].npat;
+  }
   else if (k == "alloc_hits") *value_out = g_dev_hits.load();
   else if (k == "alloc_misses") *value_out = g_dev_misses.load();
   else if (k == "alloc_miss_bytes") *value_out = g_dev_miss_bytes.load();
@@ -920,6 +935,56 @@ int spis_get_info(const spis_ctx* cctx, const char* key, int64_t* value_out) {
 }
 
 // ---- uploads --------------------------------------------------------------------------
+// Try to store the CSR matrix (already on the device) as row patterns.  *ok_out = 1 on success.
+static int try_pattern_storage(spis_ctx* ctx, Matrix& M, cudaStream_t s, int* ok_out) {
+  *ok_out = 0;
+  const int64_t nrows = M.nrows;
+  if (nrows <= 0 || M.nnz <= 0) return SPIS_OK;
+  unsigned long long* hash = nullptr; unsigned long long* keys = nullptr;
+  int *rep = nullptr, *dense = nullptr, *info = nullptr; int32_t* slot_of_row = nullptr;
+  TRY(dalloc(ctx, &hash, (size_t)nrows, false));
+  TRY(dalloc(ctx, &slot_of_row, (size_t)nrows, false));
+  TRY(dalloc(ctx, &keys, (size_t)kPatternSlots));
+  TRY(dalloc(ctx, &rep, (size_t)kPatternSlots, false));
+  TRY(dalloc(ctx, &dense, (size_t)kPatternSlots, false));
+  TRY(dalloc(ctx, &info, 8));
+  auto cleanup = [&]() { dfree(ctx, hash); dfree(ctx, slot_of_row); dfree(ctx, keys); dfree(ctx, rep); dfree(ctx, dense); dfree(ctx, info); };
+  auto drop = [&]() { dfree(ctx, M.pid); dfree(ctx, M.tab_len); dfree(ctx, M.tab_off); dfree(ctx, M.tab_val); };
+  int rc = SPIS_OK;
+  int h_info[8] = {0};
+  const int grid = ctx->nsm * 8;
+  cudaError_t e = cudaMemsetAsync(rep, 0x7f, (size_t)kPatternSlots * sizeof(int), s);      // "infinity" for atomicMin
+  pattern_hash_kernel<<<grid, 256, 0, s>>>(M.indptr, M.cols, M.vals, nrows, hash);
+  pattern_insert_kernel<<<grid, 256, 0, s>>>(hash, nrows, keys, rep, slot_of_row, info);
+  pattern_number_kernel<<<1, 32, 0, s>>>(keys, dense, info);
+  pattern_maxlen_kernel<<<kPatternSlots / 256, 256, 0, s>>>(M.indptr, rep, keys, info);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h_info, info, sizeof(h_info), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) { cleanup(); return fail(ctx, SPIS_E_CUDA, "pattern detection failed: %s", cudaGetErrorString(e)); }
+  const int npat = h_info[2], maxlen = h_info[3];
+  if (h_info[1] || npat < 1 || npat > kMaxPatterns || maxlen > kMaxPatternWidth) { cleanup(); return SPIS_OK; }
+  const int W = maxlen < 4 ? 4 : (maxlen + 3) / 4 * 4;
+  // worth it only if the stencil table is small next to the matrix it replaces (and so stays in L1)
+  if ((double)npat * W * 8.0 > (double)M.nnz && ctx->fmt_pref != SPIS_FMT_PATTERN) { cleanup(); return SPIS_OK; }
+  rc = dalloc(ctx, &M.pid, (size_t)nrows, false);
+  if (rc == SPIS_OK) rc = dalloc(ctx, &M.tab_len, (size_t)npat, false);
+  if (rc == SPIS_OK) rc = dalloc(ctx, &M.tab_off, (size_t)npat * W, false);
+  if (rc == SPIS_OK) rc = dalloc(ctx, &M.tab_val, (size_t)npat * W, false);
+  if (rc != SPIS_OK) { cleanup(); drop(); return rc; }
+  pattern_table_kernel<<<kPatternSlots / 256, 256, 0, s>>>(M.indptr, M.cols, M.vals, rep, dense, W, M.tab_len, M.tab_off, M.tab_val);
+  pattern_assign_kernel<<<grid, 256, 0, s>>>(M.indptr, M.cols, M.vals, nrows, slot_of_row, dense, W, M.tab_len, M.tab_off, M.tab_val, M.pid, info);
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h_info, info, sizeof(h_info), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cleanup();
+  if (e != cudaSuccess) { drop(); return fail(ctx, SPIS_E_CUDA, "pattern assignment failed: %s", cudaGetErrorString(e)); }
+  if (h_info[1]) { drop(); return SPIS_OK; }              // a hash collision: keep the general storage
+  M.npat = npat; M.patW = W;
+  *ok_out = 1;
+  return SPIS_OK;
+}
+
 int spis_upload_csr(spis_ctx* ctx, int slot, int64_t nrows, int64_t ncols, int64_t nnz,
                     const int32_t* indptr, const int32_t* indices, const double* data) {
   if (!ctx) return SPIS_E_INVALID;
@@ -943,6 +1008,18 @@ int spis_upload_csr(spis_ctx* ctx, int slot, int64_t nrows, int64_t ncols, int64
   }
   if (ctx->n_halo > 0 && ctx->hoff != ctx->n && nnz)
     remap_cols_kernel<<<ctx->nsm * 8, 256, 0, s>>>(M.cols, nnz, (int32_t)ctx->n, (int32_t)(ctx->hoff - ctx->n));
+  if (ctx->fmt_pref == SPIS_FMT_PATTERN || (ctx->fmt_pref == SPIS_FMT_AUTO && ctx->auto_pattern)) {
+    int ok = 0;
+    TRY(try_pattern_storage(ctx, M, s, &ok));
+    if (ok) {
+      dfree(ctx, M.indptr); dfree(ctx, M.cols); dfree(ctx, M.vals);
+      M.fmt = SPIS_FMT_PATTERN;
+      M.nnz_padded = nnz;
+      M.present = true;
+      return SPIS_OK;
+    }
+    REQUIRE(ctx->fmt_pref != SPIS_FMT_PATTERN, "matrix in slot %d has too many distinct row patterns for spmv_format=pattern", slot);
+  }
   // SELL-32 slice widths -> offsets (tiny scan on the host)
   const int64_t nslices = (nrows + 31) / 32;
   int32_t* d_width = nullptr;

@@ -41,6 +41,40 @@ def test_spmv_ragged(n, fmt):
     assert np.max(np.abs(y - ref) / scale) <= 1e-14
 
 
+def test_spmv_pattern_storage_detection_and_fallback():
+    """spmv_format=auto stores a matrix as 16-bit stencil ids + a stencil table only when it has at most
+    4096 distinct rows (verified entry by entry on the device); everything else keeps SELL / CSR."""
+    rng = np.random.default_rng(11)
+    # (a) uniform periodic stencil: one pattern for interior rows, wrap-around variants at the ends
+    n = 20_000
+    T = sps.diags([np.full(n - 1, -1.0), np.full(n, 2.5), np.full(n - 1, -1.25)], [-1, 0, 1], format="lil")
+    T[0, n - 1] = -1.0; T[n - 1, 0] = -1.25
+    T = T.tocsr()
+    x = rng.standard_normal(n)
+    with KrylovContext(n, 2) as ctx:
+        ctx.upload_matrix(nat.SLOT_A, T)
+        assert ctx.info(f"fmt:{nat.SLOT_A}") == nat.FMT_PATTERN and ctx.info(f"npat:{nat.SLOT_A}") == 3
+        np.testing.assert_allclose(ctx.op_spmv(nat.SLOT_A, x), T @ x, rtol=1e-14, atol=1e-14)
+    # (b) variable coefficients: every row its own pattern -> general storage, same answer
+    V = sps.diags([rng.standard_normal(n - 1), rng.standard_normal(n), rng.standard_normal(n - 1)], [-1, 0, 1], format="csr")
+    with KrylovContext(n, 2) as ctx:
+        ctx.upload_matrix(nat.SLOT_A, V)
+        assert ctx.info(f"fmt:{nat.SLOT_A}") in (nat.FMT_SELL, nat.FMT_CSR)
+        np.testing.assert_allclose(ctx.op_spmv(nat.SLOT_A, x), V @ x, rtol=1e-13, atol=1e-13)
+        ctx.set_option("spmv_format", nat.FMT_PATTERN)
+        with pytest.raises(nat.SpisError):
+            ctx.upload_matrix(nat.SLOT_A, V)
+    # (c) values that differ in the last bit are different patterns (lossless or nothing)
+    data = np.full(3 * n - 2, 1.0)
+    W = sps.diags([data[: n - 1], data[: n], data[: n - 1]], [-1, 0, 1], format="csr")
+    W.data[7] = np.nextafter(1.0, 2.0)
+    with KrylovContext(n, 2) as ctx:
+        ctx.upload_matrix(nat.SLOT_A, W)
+        assert ctx.info(f"fmt:{nat.SLOT_A}") == nat.FMT_PATTERN and ctx.info(f"npat:{nat.SLOT_A}") == 4
+        y = ctx.op_spmv(nat.SLOT_A, x)
+    np.testing.assert_allclose(y, W @ x, rtol=1e-14, atol=1e-14)
+
+
 def test_spmv_duplicates_and_unsorted_indices():
     n = 257
     rng = np.random.default_rng(5)
@@ -55,7 +89,7 @@ def test_spmv_duplicates_and_unsorted_indices():
     np.testing.assert_allclose(y, A @ x, rtol=0, atol=1e-12)
 
 
-@pytest.mark.parametrize("fmt", [nat.FMT_SELL, nat.FMT_SELL2, nat.FMT_CSR])
+@pytest.mark.parametrize("fmt", [nat.FMT_SELL, nat.FMT_SELL2, nat.FMT_CSR, nat.FMT_PATTERN])
 def test_spmv_fem_operators(fmt):
     d, _ = lkdv.linforms(space="CG", M=33_350, mlength=0.8 * 33_350)        # n = 100 050
     h, _ = heat.linforms(M=150)

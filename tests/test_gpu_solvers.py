@@ -36,8 +36,11 @@ def test_mgs_option_tracks_reference_arithmetic(name, golden):
     are summation orders inside dots: the first unconstrained iterates agree to ~1e-12."""
     x, info, dic, prob = helpers.run_product(name, orth="mgs", lookahead=False)
     X = golden[f"{name}/X"]
+    # the heat case's early Krylov spaces are nearly degenerate (symmetric data): its iterates move by 1e-9
+    # between SELL, CSR and row-pattern SpMV, i.e. with the association order inside one row
+    bound = 5e-9 if name.startswith("heat") else 1e-11
     for j in range(1, 4):
-        assert helpers.rel_diff(info["x"][j], X[j]) <= 1e-11
+        assert helpers.rel_diff(info["x"][j], X[j]) <= bound
     assert helpers.rel_diff(x, golden[f"{name}/x_last"]) <= tolerance(name)
 
 
@@ -75,6 +78,25 @@ def test_fused_and_unfused_cgs2_agree():
     assert helpers.rel_diff(out[0][0], out[1][0]) <= tolerance("lkdv_cg_tol8_n1500")
     # residual norms differ by rounding relative to |b|, which is ~1e-5 of the last (1e-8-sized) entries
     np.testing.assert_allclose(out[0][2], out[1][2], rtol=1e-4, atol=1e-12 * np.linalg.norm(dic["b"]))
+
+
+@pytest.mark.parametrize("fmt", ["sell", "sell2", "csr", "pattern"])
+@pytest.mark.parametrize("name", ["lkdv_cg_tol8_n1500", "swe_rt_h08_n10800", "heat_tol7_jacobi"])
+def test_every_spmv_storage_reproduces_the_reference(name, fmt, golden):
+    """The golden cases run with spmv_format=auto elsewhere (row patterns for these structured systems);
+    here every storage format is held to the same reference output."""
+    solvers.configure(spmv_format=fmt)
+    try:
+        x, info, dic, prob = helpers.run_product(name, small_solver="kkt")
+    except nat.SpisError as exc:
+        # swe's velocity and density fields have different sizes: column - row is not the same for the same
+        # stencil in different squares, so the matrix is (correctly) refused by the row-pattern storage
+        assert fmt == "pattern" and name.startswith("swe") and "distinct row patterns" in str(exc)
+        return
+    finally:
+        solvers.configure(spmv_format="auto")
+    assert info["steps"] == int(golden[f"{name}/steps"])
+    assert helpers.rel_diff(x, golden[f"{name}/x_last"]) <= tolerance(name)
 
 
 def test_session_reuse_and_profile():
@@ -218,7 +240,7 @@ def test_full_size_properties_swe():
     x0 = np.zeros(n)
     cl = wrappers.swe.conlist(d, x0)
     xs = {}
-    for fmt in ("sell", "sell2"):
+    for fmt in ("sell", "sell2", "auto"):
         sess = solvers.DeviceSession(A, b, x0, 30, conlist=cl, spmv_format=fmt)
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
@@ -232,6 +254,7 @@ def test_full_size_properties_swe():
         xs[fmt] = x
         sess.close()
     assert helpers.rel_diff(xs["sell"], xs["sell2"]) <= 1e-12
+    assert helpers.rel_diff(xs["sell"], xs["auto"]) <= 1e-12
 
 
 @pytest.mark.parametrize("x0_zero", [True, False])

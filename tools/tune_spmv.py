@@ -13,10 +13,11 @@ for wl in (sys.argv[1:] or ["lkdv", "swe"]):
     A = dic["A"]; n = A.shape[0]
     with KrylovContext(n, 4) as ctx:
         ctx.upload_vec(nat.VEC_B, dic["b"])
-        for fmt, name in ((nat.FMT_SELL, "sell"), (nat.FMT_SELL2, "sell2")):
+        for fmt, name in ((nat.FMT_SELL, "sell"), (nat.FMT_SELL2, "sell2"), (nat.FMT_PATTERN, "pattern")):
             ctx.set_option("spmv_format", fmt)
             ctx.upload_matrix(nat.SLOT_A, A)
-            for ctas in (4, 8):
+            print(name, 'npat', ctx.info('npat:0'), flush=True)
+            for ctas in ((4, 8) if name != 'pattern' else (4, 5, 8, 10)):
                 ctx.set_option("spmv_ctas_per_sm", ctas)
                 for mode in (0, 2):
                     ms, by = ctx.bench_kernel(nat.PROF_SPMV, mode, reps=20)
