@@ -77,6 +77,7 @@ extern "C" {
 #define SPIS_FMT_SELL     1
 #define SPIS_FMT_CSR      2
 #define SPIS_FMT_SELL2     3   /* SELL-32 with the entries of a row packed in pairs (128-bit value loads) */
+#define SPIS_FMT_SELLD     5   /* SELL-32 with 8-bit dictionary codes for the values (<= 256 distinct doubles) */
 #define SPIS_FMT_PATTERN   4   /* 16-bit stencil id per row + stencil table (matrices with <= 4096 distinct rows) */
 
 /* timer classes returned by spis_get_profile (CUDA-event time, algorithmic bytes, launches) */

@@ -20,7 +20,7 @@ SLOT_A, SLOT_PRE, SLOT_CON0, MAX_SLOTS = 0, 1, 2, 18
 VEC_B, VEC_X0, VEC_R0, VEC_Q, VEC_Z, VEC_X, VEC_PRE_DIAG, VEC_W = range(8)
 PRE_NONE, PRE_JACOBI, PRE_CSR, PRE_BLOCK, PRE_HOST = range(5)
 ORTH_CGS2, ORTH_CGS1, ORTH_MGS = range(3)
-FMT_AUTO, FMT_SELL, FMT_CSR, FMT_SELL2, FMT_PATTERN = range(5)
+FMT_AUTO, FMT_SELL, FMT_CSR, FMT_SELL2, FMT_PATTERN, FMT_SELLD = range(6)
 PROF_SPMV, PROF_MDOT, PROF_LINCOMB, PROF_SCALE, PROF_PRECOND, PROF_OTHER, PROF_ORTHMID, PROF_SPMV_AUX, PROF_CLASSES = range(9)
 PROF_NAMES = ("spmv", "mdot", "lincomb", "scale", "precond", "other", "orthmid", "spmv_aux")
 

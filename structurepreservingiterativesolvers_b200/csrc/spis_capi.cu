@@ -40,6 +40,8 @@ struct Matrix {
   // row-pattern storage (SPIS_FMT_PATTERN)
   uint16_t* pid = nullptr; int32_t* tab_len = nullptr; int32_t* tab_off = nullptr; double* tab_val = nullptr;
   int npat = 0, patW = 0;
+  // dictionary-coded values (SPIS_FMT_SELLD): scols as in SELL, one code per entry, table of <= 256 doubles
+  uint8_t* codes = nullptr; double* dict = nullptr; int ndict = 0;
 };
 
 struct Constraint {
@@ -82,6 +84,7 @@ struct spis_ctx {
   int fuse_jacobi = 1;
   int mdotm_ctas_per_sm = 4;       // tools/tune_mdotm.py: 5.1-5.5 TB/s at 4, 3.5-4.8 at 2, 3.8-4.3 at 8
   int bench_mdotm_nw = 0;       // tuning: spis_bench_kernel(SPIS_PROF_MDOT) times mdotm_kernel<nw> instead
+  int auto_dict = 1;            // spmv_format=auto codes the values of a SELL matrix with <= 256 distinct ones in 8 bits
   int auto_pattern = 1;         // spmv_format=auto first tries the row-pattern storage (few distinct stencils)
   int auto_sell2 = 0;           // spmv_format=auto picks the pair-packed SELL layout
   int force_nonsymmetric = 0;   // tests: take the general (stored M Z) path of the constraint stage
@@ -468,6 +471,11 @@ int launch_spmv_mode(spis_ctx* ctx, const Matrix& M, const double* x, const doub
     const int64_t nslices = (M.nrows + 31) / 32;
     const int grid = grid_for(ctx, (nslices + kWarps - 1) / kWarps, ctx->spmv_ctas_per_sm);
     spmv_sell_kernel<MODE><<<grid, kThreads, 0, ctx->stream>>>(M.slice_off, M.scols, M.svals, M.nrows, x, b, y, ctx->d_partial, ctx->d_counter, sumsq_out, xv, seq);
+  } else if (M.fmt == SPIS_FMT_SELLD) {
+    const int64_t nslices = (M.nrows + 31) / 32;
+    const int grid = grid_for(ctx, (nslices + kWarps - 1) / kWarps, ctx->spmv_ctas_per_sm);
+    spmv_selld_kernel<MODE><<<grid, kThreads, 0, ctx->stream>>>(M.slice_off, M.scols, M.codes, M.dict, M.nrows, x, b, y, ctx->d_partial);
+    if (MODE != 0) reduce_partials_kernel<<<1, kThreads, 0, ctx->stream>>>(ctx->d_partial, grid, sumsq_out, xv, seq);
   } else if (M.fmt == SPIS_FMT_PATTERN) {
     const int grid = grid_for(ctx, (M.nrows + kThreads - 1) / kThreads, ctx->spmv_ctas_per_sm);
     spmv_pattern_kernel<MODE><<<grid, kThreads, 0, ctx->stream>>>(M.pid, M.patW, M.tab_len, M.tab_off, M.tab_val, M.nrows, x, b, y, ctx->d_partial);
@@ -551,6 +559,7 @@ void free_matrix(spis_ctx* ctx, Matrix& M) {
   dfree(ctx, M.indptr); dfree(ctx, M.cols); dfree(ctx, M.vals);
   dfree(ctx, M.slice_off); dfree(ctx, M.scols); dfree(ctx, M.svals);
   dfree(ctx, M.pid); dfree(ctx, M.tab_len); dfree(ctx, M.tab_off); dfree(ctx, M.tab_val);
+  dfree(ctx, M.codes); dfree(ctx, M.dict);
   M = Matrix();
 }
 
@@ -880,9 +889,10 @@ int spis_set_option(spis_ctx* ctx, const char* key, int64_t value) {
   if (!ctx || !key) return SPIS_E_INVALID;
   std::string k(key);
   if (k == "orth") { REQUIRE(value >= 0 && value <= 2, "orth must be 0..2"); ctx->orth = (int)value; }
-  else if (k == "spmv_format") { REQUIRE(value >= 0 && value <= 4, "spmv_format must be 0..4"); ctx->fmt_pref = (int)value; }
+  else if (k == "spmv_format") { REQUIRE(value >= 0 && value <= 5, "spmv_format must be 0..5"); ctx->fmt_pref = (int)value; }
   else if (k == "auto_sell2") { ctx->auto_sell2 = value ? 1 : 0; }
   else if (k == "auto_pattern") { ctx->auto_pattern = value ? 1 : 0; }
+  else if (k == "auto_dict") { ctx->auto_dict = value ? 1 : 0; }
   else if (k == "mdotm_ctas_per_sm") { REQUIRE(value >= 1 && value <= 8, "mdotm_ctas_per_sm must be 1..8"); ctx->mdotm_ctas_per_sm = (int)value; }
   else if (k == "bench_mdotm_nw") { REQUIRE(value == 0 || value == 2 || value == 4, "bench_mdotm_nw must be 0, 2 or 4"); ctx->bench_mdotm_nw = (int)value; }
   else if (k == "profile") { ctx->profile = value ? 1 : 0; }
@@ -919,6 +929,11 @@ int spis_get_info(const spis_ctx* cctx, const char* key, int64_t* value_out) {
     else if (k.rfind("nnz_padded:", 0) == 0) *value_out = ctx->mats[slot].nnz_padded;
     else *value_out = ctx->mats[slot].nnz;
   }
+  else if (k.rfind("ndict:", 0) == 0) {
+    const int slot = atoi(k.c_str() + 6);
+    REQUIRE(slot >= 0 && slot < SPIS_MAX_SLOTS && ctx->mats[slot].present, "slot %d not uploaded", slot);
+    *value_out = ctx->mats[slot].ndict;
+  }
   else if (k.rfind("npat:", 0) == 0) {
     const int slot = atoi(k.c_str() + 5);
     REQUIRE(slot >= 0 && slot < SPIS_MAX_SLOTS && ctx->mats[slot].present, "slot %d not uploaded", slot);
@@ -935,6 +950,39 @@ int spis_get_info(const spis_ctx* cctx, const char* key, int64_t* value_out) {
 }
 
 // ---- uploads --------------------------------------------------------------------------
+// SELL matrix on the device -> dictionary-coded values if it holds at most 256 distinct doubles.
+static int try_value_dictionary(spis_ctx* ctx, Matrix& M, cudaStream_t s, int* ok_out) {
+  *ok_out = 0;
+  if (M.nnz_padded <= 0) return SPIS_OK;
+  unsigned long long* keys = nullptr; int *dense = nullptr, *info = nullptr;
+  TRY(dalloc(ctx, &keys, (size_t)kDictSlots));
+  TRY(dalloc(ctx, &dense, (size_t)kDictSlots, false));
+  TRY(dalloc(ctx, &info, 8));
+  TRY(dalloc(ctx, &M.dict, 256));
+  auto cleanup = [&]() { dfree(ctx, keys); dfree(ctx, dense); dfree(ctx, info); };
+  int h_info[8] = {0};
+  const int grid = ctx->nsm * 8;
+  dict_insert_kernel<<<grid, 256, 0, s>>>(M.svals, M.nnz_padded, keys, info);
+  dict_number_kernel<<<1, 32, 0, s>>>(keys, dense, M.dict, info);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h_info, info, sizeof(h_info), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) { cleanup(); dfree(ctx, M.dict); return fail(ctx, SPIS_E_CUDA, "value dictionary failed: %s", cudaGetErrorString(e)); }
+  if (h_info[1] || h_info[2] < 1 || h_info[2] > 256) { cleanup(); dfree(ctx, M.dict); return SPIS_OK; }
+  int rc = dalloc(ctx, &M.codes, (size_t)M.nnz_padded, false);
+  if (rc != SPIS_OK) { cleanup(); dfree(ctx, M.dict); return rc; }
+  dict_encode_kernel<<<grid, 256, 0, s>>>(M.svals, M.nnz_padded, keys, dense, M.codes);
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cleanup();
+  if (e != cudaSuccess) { dfree(ctx, M.codes); dfree(ctx, M.dict); return fail(ctx, SPIS_E_CUDA, "value encoding failed: %s", cudaGetErrorString(e)); }
+  dfree(ctx, M.svals);
+  M.ndict = h_info[2];
+  M.fmt = SPIS_FMT_SELLD;
+  *ok_out = 1;
+  return SPIS_OK;
+}
+
 // Try to store the CSR matrix (already on the device) as row patterns.  *ok_out = 1 on success.
 static int try_pattern_storage(spis_ctx* ctx, Matrix& M, cudaStream_t s, int* ok_out) {
   *ok_out = 0;
@@ -980,6 +1028,9 @@ static int try_pattern_storage(spis_ctx* ctx, Matrix& M, cudaStream_t s, int* ok
   cleanup();
   if (e != cudaSuccess) { drop(); return fail(ctx, SPIS_E_CUDA, "pattern assignment failed: %s", cudaGetErrorString(e)); }
   if (h_info[1]) { drop(); return SPIS_OK; }              // a hash collision: keep the general storage
+  // neighbouring rows must mostly share their stencil (see pattern_assign_kernel); measured: the swe energy
+  // matrix (10 row types in sequence) runs at 310 us as patterns, 262 us as SELL, 180 us as SELLD
+  if ((double)h_info[5] * 8.0 > (double)nrows && ctx->fmt_pref != SPIS_FMT_PATTERN) { drop(); return SPIS_OK; }
   M.npat = npat; M.patW = W;
   *ok_out = 1;
   return SPIS_OK;
@@ -1038,6 +1089,7 @@ int spis_upload_csr(spis_ctx* ctx, int slot, int64_t nrows, int64_t ncols, int64
   for (int64_t s = 0; s < nslices; ++s) off[s + 1] = off[s] + (int64_t)(want2 ? (width[s] + 1) & ~1 : width[s]) * 32;
   M.nnz_padded = off[nslices];
   if (fmt == SPIS_FMT_AUTO) fmt = ((double)M.nnz_padded <= 1.25 * (double)(nnz > 0 ? nnz : 1) + 32.0 * 64.0) ? (want2 ? SPIS_FMT_SELL2 : SPIS_FMT_SELL) : SPIS_FMT_CSR;
+  if (fmt == SPIS_FMT_SELLD) fmt = SPIS_FMT_SELL;      // built as SELL first, values coded afterwards
   M.fmt = fmt;
   if (fmt == SPIS_FMT_SELL || fmt == SPIS_FMT_SELL2) {
     TRY(dalloc(ctx, &M.slice_off, (size_t)nslices + 1, false));
@@ -1051,6 +1103,11 @@ int spis_upload_csr(spis_ctx* ctx, int slot, int64_t nrows, int64_t ncols, int64
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(s));
     dfree(ctx, M.indptr); dfree(ctx, M.cols); dfree(ctx, M.vals);
+    if (fmt == SPIS_FMT_SELL && (ctx->fmt_pref == SPIS_FMT_SELLD || (ctx->fmt_pref == SPIS_FMT_AUTO && ctx->auto_dict))) {
+      int ok = 0;
+      TRY(try_value_dictionary(ctx, M, s, &ok));
+      REQUIRE(ok || ctx->fmt_pref != SPIS_FMT_SELLD, "matrix in slot %d has more than 256 distinct values: spmv_format=selld does not apply", slot);
+    }
   } else {
     const double avg = nrows ? (double)nnz / (double)nrows : 0.0;
     M.csr_lanes = avg <= 3 ? 2 : avg <= 6 ? 4 : avg <= 12 ? 8 : avg <= 24 ? 16 : 32;

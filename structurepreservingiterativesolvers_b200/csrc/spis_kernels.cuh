@@ -954,6 +954,11 @@ __global__ void pattern_assign_kernel(const int32_t* __restrict__ indptr, const 
            (__double_as_longlong(vals[p0 + kk]) == __double_as_longlong(tab_val[(size_t)p * W + kk]));
     if (!ok) atomicExch(info + 1, 1);
     pid[r] = (uint16_t)p;
+    // info[5]: rows whose stencil differs from the previous row's.  The SpMV kernel gives consecutive rows to
+    // consecutive lanes: when neighbours share a stencil the table reads are warp-wide broadcasts, when they
+    // do not (swe: ten row types per square, in sequence) every lane reads its own table row and the kernel
+    // ends up slower than SELL.
+    if (r > 0 && slot_of_row[r - 1] != slot_of_row[r]) atomicAdd(info + 5, 1);
   }
 }
 
@@ -1039,6 +1044,130 @@ reduce_partials_kernel(const double* __restrict__ partial, int nparts, double* o
   }
   if (threadIdx.x == 0) out[0] = sred[0];
   cta_xreduce(out, 1, xv, seq);
+}
+
+// ------------------------------------------------------------------------------------------
+// K1, SELL-32 with dictionary-coded values ("SELLD").  Constant-coefficient operators on uniform meshes
+// hold very few DISTINCT values (swe: the entries of two 8x8 element matrices summed in a handful of
+// ways) even when their rows do not repeat as whole stencils (fields of different sizes).  If the
+// matrix has at most 256 distinct values (bit patterns: lossless), each entry is stored as a 32-bit
+// column and an 8-bit code, 5 bytes instead of 12; the 2 KB table of doubles sits in shared memory.
+// ------------------------------------------------------------------------------------------
+constexpr int kDictSlots = 2048;
+
+// insert the bit pattern of every value into an open-addressing set; info[0] = distinct count, info[1] = overflow
+__global__ void dict_insert_kernel(const double* __restrict__ vals, int64_t count, unsigned long long* keys, int* info) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+    if (info[1]) return;
+    const unsigned long long key = (unsigned long long)__double_as_longlong(vals[i]) ^ 0x8000000000000001ull;   // +0.0 must not look like "empty"
+    unsigned slot = (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 40) % kDictSlots;
+    for (int probes = 0;; ++probes) {
+      unsigned long long cur = keys[slot];
+      if (cur == 0ull) {
+        cur = atomicCAS(keys + slot, 0ull, key);
+        if (cur == 0ull) {
+          if (atomicAdd(info, 1) >= 256) atomicExch(info + 1, 1);
+          cur = key;
+        }
+      }
+      if (cur == key) break;
+      if (probes > 64) { atomicExch(info + 1, 1); return; }
+      slot = (slot + 1) % kDictSlots;
+    }
+  }
+}
+
+// codes in slot order + the table itself (one warp)
+__global__ void dict_number_kernel(const unsigned long long* __restrict__ keys, int* __restrict__ dense,
+                                   double* __restrict__ table, int* info) {
+  if (blockIdx.x || threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  int next = 0;
+  for (int s0 = 0; s0 < kDictSlots; s0 += 32) {
+    const unsigned long long key = keys[s0 + lane];
+    const bool used = key != 0ull;
+    const unsigned m = __ballot_sync(0xffffffffu, used);
+    const int id = next + __popc(m & ((1u << lane) - 1u));
+    dense[s0 + lane] = used ? id : -1;
+    if (used && id < 256) table[id] = __longlong_as_double((long long)(key ^ 0x8000000000000001ull));
+    next += __popc(m);
+  }
+  if (lane == 0) info[2] = next;
+}
+
+__global__ void dict_encode_kernel(const double* __restrict__ vals, int64_t count, const unsigned long long* __restrict__ keys,
+                                   const int* __restrict__ dense, uint8_t* __restrict__ codes) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+    const unsigned long long key = (unsigned long long)__double_as_longlong(vals[i]) ^ 0x8000000000000001ull;
+    unsigned slot = (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 40) % kDictSlots;
+    while (keys[slot] != key) slot = (slot + 1) % kDictSlots;
+    codes[i] = (uint8_t)dense[slot];
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 8)
+spmv_selld_kernel(const int64_t* __restrict__ slice_off, const int32_t* __restrict__ cols,
+                  const uint8_t* __restrict__ codes, const double* __restrict__ table, int64_t nrows,
+                  const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ y,
+                  double* __restrict__ partial) {
+  __shared__ double sdict[256];
+  __shared__ double sred[kWarps];
+  sdict[threadIdx.x] = __ldg(table + threadIdx.x);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t nslices = (nrows + 31) >> 5;
+  const int64_t nblocks = (nslices + kWarps - 1) / kWarps;
+  double ss = 0.0;
+  for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    const int64_t slice = blk * kWarps + warp;
+    if (slice < nslices) {
+      const int64_t off = __ldg(slice_off + slice);
+      const int width = (int)((__ldg(slice_off + slice + 1) - off) >> 5);
+      const int32_t* c = cols + off + lane;
+      const uint8_t* v = codes + off + lane;
+      const int64_t row = (slice << 5) + lane;
+      double bv = 0.0;
+      if (MODE != 0 && row < nrows) bv = __ldg(b + row);
+      double acc0 = 0.0, acc1 = 0.0;
+      int k = 0;
+      for (; k + 4 <= width; k += 4) {
+        const int32_t c0 = __ldcs(c + (k + 0) * 32), c1 = __ldcs(c + (k + 1) * 32);
+        const int32_t c2 = __ldcs(c + (k + 2) * 32), c3 = __ldcs(c + (k + 3) * 32);
+        const unsigned q0 = __ldcs(v + (k + 0) * 32), q1 = __ldcs(v + (k + 1) * 32);
+        const unsigned q2 = __ldcs(v + (k + 2) * 32), q3 = __ldcs(v + (k + 3) * 32);
+        const double x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
+        acc0 = fma(sdict[q0], x0, acc0); acc1 = fma(sdict[q1], x1, acc1);
+        acc0 = fma(sdict[q2], x2, acc0); acc1 = fma(sdict[q3], x3, acc1);
+      }
+      for (; k < width; ++k) acc0 = fma(sdict[__ldcs(v + k * 32)], __ldg(x + __ldcs(c + k * 32)), acc0);
+      const double ax = acc0 + acc1;
+      if (row < nrows) {
+        if (MODE == 0) {
+          y[row] = ax;
+        } else if (MODE == 1) {
+          const double r = bv - ax;
+          y[row] = r;
+          ss = fma(r, r, ss);
+        } else {
+          const double r = ax - bv;
+          ss = fma(r, r, ss);
+        }
+      }
+    }
+  }
+  if (MODE == 0) return;
+  ss = warp_sum(ss);
+  if (lane == 0) sred[warp] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int wv = 0; wv < kWarps; ++wv) t += sred[wv];
+    partial[blockIdx.x] = t;          // reduce_partials_kernel finishes (keeps this kernel at 32 registers)
+  }
 }
 
 // K1 fallback: CSR "vector" kernel, T lanes per row (T = 2..32), for matrices whose row

@@ -54,7 +54,7 @@ _CONFIG = {
     "async_setup": True,
 }
 _ORTH = {"cgs2": nat.ORTH_CGS2, "cgs1": nat.ORTH_CGS1, "mgs": nat.ORTH_MGS}
-_FMT = {"auto": nat.FMT_AUTO, "sell": nat.FMT_SELL, "csr": nat.FMT_CSR, "sell2": nat.FMT_SELL2, "pattern": nat.FMT_PATTERN}
+_FMT = {"auto": nat.FMT_AUTO, "sell": nat.FMT_SELL, "csr": nat.FMT_CSR, "sell2": nat.FMT_SELL2, "pattern": nat.FMT_PATTERN, "selld": nat.FMT_SELLD}
 _BREAKDOWN = ("GMRES broke down, either initial guess is exact or , more likely, "
               "something has gone wrong.")
 

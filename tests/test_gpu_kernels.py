@@ -75,6 +75,37 @@ def test_spmv_pattern_storage_detection_and_fallback():
     np.testing.assert_allclose(y, W @ x, rtol=1e-14, atol=1e-14)
 
 
+def test_spmv_value_dictionary_storage():
+    """SELLD: 8-bit codes for the values when the matrix holds at most 256 distinct doubles (bit patterns)."""
+    from structurepreservingiterativesolvers_b200.problems import swe
+    d, _ = swe.linforms(M=40, mlength=32.0)                          # rows do not repeat as stencils, values do
+    A = d["A"]
+    n = A.shape[0]
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal(n)
+    with KrylovContext(n, 2) as ctx:
+        ctx.upload_matrix(nat.SLOT_A, A)                            # auto
+        assert ctx.info(f"fmt:{nat.SLOT_A}") == nat.FMT_SELLD and 1 <= ctx.info(f"ndict:{nat.SLOT_A}") <= 256
+        y = ctx.op_spmv(nat.SLOT_A, x)
+        ctx.set_option("spmv_format", nat.FMT_SELL)
+        ctx.upload_matrix(nat.SLOT_A, A)
+        np.testing.assert_array_equal(y, ctx.op_spmv(nat.SLOT_A, x))   # same values, same order: same bits
+    scale = np.abs(A) @ np.abs(x)
+    assert np.max(np.abs(y - A @ x) / scale) <= 1e-14
+    # 300 distinct values (incl. -0.0 / +0.0, which are different codes): refused when asked for explicitly
+    B = sps.diags([np.arange(1.0, 301.0)], [0], format="csr")
+    with KrylovContext(300, 2) as ctx:
+        ctx.set_option("spmv_format", nat.FMT_SELLD)
+        with pytest.raises(nat.SpisError):
+            ctx.upload_matrix(nat.SLOT_A, B)
+    Z = sps.csr_matrix((np.array([0.0, -0.0, 2.0, 0.0]), np.array([0, 1, 2, 3]), np.arange(5)), shape=(4, 4))
+    with KrylovContext(4, 2) as ctx:
+        ctx.set_option("spmv_format", nat.FMT_SELLD)
+        ctx.upload_matrix(nat.SLOT_A, Z)
+        assert ctx.info(f"ndict:{nat.SLOT_A}") == 3
+        np.testing.assert_array_equal(ctx.op_spmv(nat.SLOT_A, np.array([1.0, 1.0, 1.0, np.pi])), Z @ np.array([1.0, 1.0, 1.0, np.pi]))
+
+
 def test_spmv_duplicates_and_unsorted_indices():
     n = 257
     rng = np.random.default_rng(5)
@@ -89,7 +120,7 @@ def test_spmv_duplicates_and_unsorted_indices():
     np.testing.assert_allclose(y, A @ x, rtol=0, atol=1e-12)
 
 
-@pytest.mark.parametrize("fmt", [nat.FMT_SELL, nat.FMT_SELL2, nat.FMT_CSR, nat.FMT_PATTERN])
+@pytest.mark.parametrize("fmt", [nat.FMT_SELL, nat.FMT_SELL2, nat.FMT_CSR, nat.FMT_PATTERN, nat.FMT_SELLD])
 def test_spmv_fem_operators(fmt):
     d, _ = lkdv.linforms(space="CG", M=33_350, mlength=0.8 * 33_350)        # n = 100 050
     h, _ = heat.linforms(M=150)

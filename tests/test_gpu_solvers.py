@@ -80,7 +80,7 @@ def test_fused_and_unfused_cgs2_agree():
     np.testing.assert_allclose(out[0][2], out[1][2], rtol=1e-4, atol=1e-12 * np.linalg.norm(dic["b"]))
 
 
-@pytest.mark.parametrize("fmt", ["sell", "sell2", "csr", "pattern"])
+@pytest.mark.parametrize("fmt", ["sell", "sell2", "csr", "pattern", "selld"])
 @pytest.mark.parametrize("name", ["lkdv_cg_tol8_n1500", "swe_rt_h08_n10800", "heat_tol7_jacobi"])
 def test_every_spmv_storage_reproduces_the_reference(name, fmt, golden):
     """The golden cases run with spmv_format=auto elsewhere (row patterns for these structured systems);
@@ -240,7 +240,7 @@ def test_full_size_properties_swe():
     x0 = np.zeros(n)
     cl = wrappers.swe.conlist(d, x0)
     xs = {}
-    for fmt in ("sell", "sell2", "auto"):
+    for fmt in ("sell", "sell2", "selld", "auto"):
         sess = solvers.DeviceSession(A, b, x0, 30, conlist=cl, spmv_format=fmt)
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")

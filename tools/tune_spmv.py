@@ -9,13 +9,17 @@ from structurepreservingiterativesolvers_b200.device import KrylovContext
 
 rows = []
 for wl in (sys.argv[1:] or ["lkdv", "swe"]):
-    dic, x0, cl, _ = bench.build_system(10_000_000, wl)
-    A = dic["A"]; n = A.shape[0]
+    dic, x0, cl, _ = bench.build_system(10_000_000, wl.split("_")[0])
+    A = dic["L"] if wl.endswith("_L") else dic["A"]; n = A.shape[0]
     with KrylovContext(n, 4) as ctx:
         ctx.upload_vec(nat.VEC_B, dic["b"])
-        for fmt, name in ((nat.FMT_SELL, "sell"), (nat.FMT_SELL2, "sell2"), (nat.FMT_PATTERN, "pattern")):
+        for fmt, name in ((nat.FMT_SELL, "sell"), (nat.FMT_SELLD, "selld"), (nat.FMT_PATTERN, "pattern")):
             ctx.set_option("spmv_format", fmt)
-            ctx.upload_matrix(nat.SLOT_A, A)
+            try:
+                ctx.upload_matrix(nat.SLOT_A, A)
+            except nat.SpisError as exc:
+                print(name, 'not applicable:', exc, flush=True)
+                continue
             print(name, 'npat', ctx.info('npat:0'), flush=True)
             for ctas in ((4, 8) if name != 'pattern' else (4, 5, 8, 10)):
                 ctx.set_option("spmv_ctas_per_sm", ctas)
