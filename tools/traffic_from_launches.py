@@ -3,7 +3,7 @@
 measured DRAM bytes per launch of every kernel class of bench.py's `kernels` object."""
 import collections, csv, json, os, re, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CLASS = [("spmv_sell_kernel", "spmv"), ("spmv_csr_kernel", "spmv"), ("mdotm_kernel", "mdot"), ("mdot_kernel", "mdot"),
+CLASS = [("spmv_sell", "spmv"), ("spmv_csr_kernel", "spmv"), ("spmv_pattern_kernel", "spmv"), ("reduce_partials", "spmv"), ("mdotm_kernel", "mdot"), ("mdot_kernel", "mdot"),
          ("lincomb_kernel", "lincomb"), ("orth_mid_kernel", "orthmid"), ("scale_kernel", "scale")]
 out = {}
 for wl, nrows in (("lkdv", 10_000_050), ("swe", 10_002_828)):
@@ -17,16 +17,16 @@ for wl, nrows in (("lkdv", 10_000_050), ("swe", 10_002_828)):
     agg = collections.defaultdict(lambda: dict(launches=0, ns=0.0, dram=0.0))
     # residual SpMVs (mode 2) always use the system matrix: their read volume minus b is what a mode-0
     # launch on A reads; mode-0 launches reading clearly less ran on a constraint matrix
-    mode2 = sorted(d["dram__bytes_read.sum"] for d in per.values() if "spmv_sell_kernel<2>" in d["k"])
+    mode2 = sorted(d["dram__bytes_read.sum"] for d in per.values() if "spmv_" in d["k"] and "kernel<2>" in d["k"])
     ref_read = mode2[len(mode2) // 2] - 8.0 * nrows
     for d in per.values():
         cls = next((c for pat, c in CLASS if pat in d["k"]), None)
         if cls is None:
             continue
         dram = d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
-        if cls == "spmv" and "kernel<0>" in d["k"] and d.get("dram__bytes_read.sum", 0.0) < 0.9 * ref_read:
+        if cls == "spmv" and "kernel<0>" in d["k"] and abs(d.get("dram__bytes_read.sum", 0.0) - ref_read) > 0.2 * ref_read:
             cls = "spmv_aux"                  # constraint matrix (a third of A's rows carry entries)
-        a = agg[cls]; a["launches"] += 1; a["ns"] += d["gpu__time_duration.sum"]; a["dram"] += dram
+        a = agg[cls]; a["launches"] += 0 if "reduce_partials" in d["k"] else 1; a["ns"] += d["gpu__time_duration.sum"]; a["dram"] += dram
     tot = sum(a["ns"] for a in agg.values())
     out[wl] = {c: {"launches": a["launches"], "traffic_bytes_per_launch": a["dram"] / a["launches"],
                    "ncu_us_per_launch": a["ns"] / a["launches"] * 1e-3, "share_of_kernel_time": a["ns"] / tot,
