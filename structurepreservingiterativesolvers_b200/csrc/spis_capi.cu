@@ -478,7 +478,10 @@ int launch_spmv_mode(spis_ctx* ctx, const Matrix& M, const double* x, const doub
     if (MODE != 0) reduce_partials_kernel<<<1, kThreads, 0, ctx->stream>>>(ctx->d_partial, grid, sumsq_out, xv, seq);
   } else if (M.fmt == SPIS_FMT_PATTERN) {
     const int grid = grid_for(ctx, (M.nrows + kThreads - 1) / kThreads, ctx->spmv_ctas_per_sm);
-    spmv_pattern_kernel<MODE><<<grid, kThreads, 0, ctx->stream>>>(M.pid, M.patW, M.tab_len, M.tab_off, M.tab_val, M.nrows, x, b, y, ctx->d_partial);
+#define SPIS_PAT_CASE(NC) case NC: spmv_pattern_kernel<MODE, NC><<<grid, kThreads, 0, ctx->stream>>>(M.pid, M.patW, M.tab_off, M.tab_val, (int)M.nrows, x, b, y, ctx->d_partial); break;
+    switch (M.patW / 4) { SPIS_PAT_CASE(1) SPIS_PAT_CASE(2) SPIS_PAT_CASE(3) SPIS_PAT_CASE(4)
+      default: spmv_pattern_kernel<MODE, 0><<<grid, kThreads, 0, ctx->stream>>>(M.pid, M.patW, M.tab_off, M.tab_val, (int)M.nrows, x, b, y, ctx->d_partial); }
+#undef SPIS_PAT_CASE
     if (MODE != 0) reduce_partials_kernel<<<1, kThreads, 0, ctx->stream>>>(ctx->d_partial, grid, sumsq_out, xv, seq);
   } else if (M.fmt == SPIS_FMT_SELL2) {
     const int64_t nslices = (M.nrows + 31) / 32;
