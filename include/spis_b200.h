@@ -154,6 +154,14 @@ int spis_solve_begin(spis_ctx* ctx, double* beta_out);
 int spis_arnoldi_launch(spis_ctx* ctx, int j);
 int spis_arnoldi_wait(spis_ctx* ctx, int j, double* hcol_out);
 int spis_arnoldi_step(spis_ctx* ctx, int j, double* hcol_out);
+/* spis_arnoldi_launch in two halves.  _begin queues z_j, w = A z_j and the first 1.5 projections; _finish
+ * queues the last projection, the normalisation and the copy of the Hessenberg column.  With m_it > 0 the
+ * last projection ALSO forms the iterate of the previous step, x = x0 + Z[:, :m_it] y_it (solvers.py:287),
+ * from the same sweep over the basis (CGS2, no preconditioner; spis_get_info "can_fuse_iterate"): follow it
+ * with spis_residual_launch (= the second half of spis_iterate_residual_launch) and _wait.              */
+int spis_arnoldi_begin(spis_ctx* ctx, int j);
+int spis_arnoldi_finish(spis_ctx* ctx, int j, int m_it, const double* y_it);
+int spis_residual_launch(spis_ctx* ctx);
 /* x_j = x0 + Z[:, :m] y ; resnorm = ||A x_j - b||                  (solvers.py:287,290) */
 int spis_iterate_residual(spis_ctx* ctx, int m, const double* y, double* resnorm_out);
 /* the same in two halves: after _launch the host may fetch the next Hessenberg column and queue the

@@ -57,6 +57,9 @@ SIGNATURES = {
     "spis_arnoldi_launch": (C.c_int, [_ctx, C.c_int]),
     "spis_arnoldi_wait": (C.c_int, [_ctx, C.c_int, _dp]),
     "spis_arnoldi_step": (C.c_int, [_ctx, C.c_int, _dp]),
+    "spis_arnoldi_begin": (C.c_int, [_ctx, C.c_int]),
+    "spis_arnoldi_finish": (C.c_int, [_ctx, C.c_int, C.c_int, _dp]),
+    "spis_residual_launch": (C.c_int, [_ctx]),
     "spis_iterate_residual": (C.c_int, [_ctx, C.c_int, _dp, _dp]),
     "spis_iterate_residual_launch": (C.c_int, [_ctx, C.c_int, _dp]),
     "spis_iterate_residual_wait": (C.c_int, [_ctx, _dp]),

@@ -82,6 +82,9 @@ struct spis_ctx {
   int mdot_variant = 0, lincomb_variant = 4;   // mdot 0 = auto (tools/tune.py sweep, profiles/tune_r1.md)
   int x0_is_zero = 0;
   int fuse_jacobi = 1;
+  int lincomb2_ctas_per_sm = 4;
+  int fuse_iterate = 1;         // form x_j inside the last projection pass of Arnoldi step j+1 (no preconditioner)
+  int arnoldi_part1 = -1;       // step whose first half (SpMV, first projection, middle pass) is queued
   int mdotm_ctas_per_sm = 4;       // tools/tune_mdotm.py: 5.1-5.5 TB/s at 4, 3.5-4.8 at 2, 3.8-4.3 at 8
   int bench_mdotm_nw = 0;       // tuning: spis_bench_kernel(SPIS_PROF_MDOT) times mdotm_kernel<nw> instead
   int auto_dict = 1;            // spmv_format=auto codes the values of a SELL matrix with <= 256 distinct ones in 8 bits
@@ -404,6 +407,21 @@ int launch_lincomb(spis_ctx* ctx, const double* V, int m, const double* coef, co
   TRY(prof_end(ctx));
   if (with_sumsq) return do_allreduce(ctx, sumsq_out, 1);
   return SPIS_OK;
+}
+
+// outA = baseA - V[0..m) coefA (+ ||outA||^2 -> sumsq_out), outB = baseB + V[0..mB) coefB, one sweep over V
+int launch_lincomb2(spis_ctx* ctx, const double* V, int m, const double* coefA, const double* coefB, int mB,
+                    const double* baseA, const double* baseB, double* outA, double* outB, double* sumsq_out) {
+  const int64_t ntiles = (ctx->n + kTile - 1) / kTile;
+  const int grid = grid_for(ctx, ntiles, ctx->lincomb2_ctas_per_sm);
+  const size_t smem = (size_t)(2 * (m + 2) + kWarps * 32) * sizeof(double);
+  TRY(prof_begin(ctx, SPIS_PROF_LINCOMB, (double)(m + 3 + (baseB ? 1 : 0)) * 8.0 * (double)ctx->n));
+  const XView xv = fused_view(ctx);
+  const unsigned long long seq = fused_seq(ctx);
+  lincomb2_kernel<4><<<grid, kThreads, smem, ctx->stream>>>(V, ctx->ld, m, coefA, coefB, mB, baseA, baseB, outA, outB, ctx->n, ctx->d_partial, ctx->d_counter, sumsq_out, xv, seq);
+  CU(cudaGetLastError());
+  TRY(prof_end(ctx));
+  return do_allreduce(ctx, sumsq_out, 1);
 }
 
 // Fused middle of CGS2 (orth_mid_kernel): w <- w - V coef, out[i] = V_i . w(new).  Picks the widest
@@ -895,6 +913,8 @@ int spis_set_option(spis_ctx* ctx, const char* key, int64_t value) {
   else if (k == "spmv_format") { REQUIRE(value >= 0 && value <= 5, "spmv_format must be 0..5"); ctx->fmt_pref = (int)value; }
   else if (k == "auto_sell2") { ctx->auto_sell2 = value ? 1 : 0; }
   else if (k == "auto_pattern") { ctx->auto_pattern = value ? 1 : 0; }
+  else if (k == "fuse_iterate") { ctx->fuse_iterate = value ? 1 : 0; }
+  else if (k == "lincomb2_ctas_per_sm") { REQUIRE(value >= 1 && value <= 8, "lincomb2_ctas_per_sm must be 1..8"); ctx->lincomb2_ctas_per_sm = (int)value; }
   else if (k == "auto_dict") { ctx->auto_dict = value ? 1 : 0; }
   else if (k == "mdotm_ctas_per_sm") { REQUIRE(value >= 1 && value <= 8, "mdotm_ctas_per_sm must be 1..8"); ctx->mdotm_ctas_per_sm = (int)value; }
   else if (k == "bench_mdotm_nw") { REQUIRE(value == 0 || value == 2 || value == 4, "bench_mdotm_nw must be 0, 2 or 4"); ctx->bench_mdotm_nw = (int)value; }
@@ -945,6 +965,7 @@ int spis_get_info(const spis_ctx* cctx, const char* key, int64_t* value_out) {
   else if (k == "alloc_hits") *value_out = g_dev_hits.load();
   else if (k == "alloc_misses") *value_out = g_dev_misses.load();
   else if (k == "alloc_miss_bytes") *value_out = g_dev_miss_bytes.load();
+  else if (k == "can_fuse_iterate") *value_out = (ctx->fuse_iterate && ctx->orth == SPIS_ORTH_CGS2 && ctx->pre_kind == SPIS_PRE_NONE) ? 1 : 0;
   else if (k == "device_ptr:small") *value_out = (int64_t)(intptr_t)ctx->d_small;
   else if (k == "stream") *value_out = (int64_t)(intptr_t)ctx->stream;
   else if (k == "n_send") *value_out = ctx->n_send;
@@ -1188,15 +1209,18 @@ int spis_solve_begin(spis_ctx* ctx, double* beta_out) {
   }
   ctx->began = true;
   ctx->arnoldi_inflight = -1;
+  ctx->arnoldi_part1 = -1;
   ctx->resid_inflight = false;
   return SPIS_OK;
 }
 
-int spis_arnoldi_launch(spis_ctx* ctx, int j) {
+// First half of Arnoldi step j: z_j, w = A z_j and (CGS2) h1 = V^T w, w -= V h1, h2 = V^T w.
+int spis_arnoldi_begin(spis_ctx* ctx, int j) {
   if (!ctx) return SPIS_E_INVALID;
   REQUIRE(ctx->began, "spis_solve_begin has not been called");
   REQUIRE(j >= 0 && j < ctx->kmax, "Arnoldi index %d out of range [0,%d)", j, ctx->kmax);
   REQUIRE(ctx->arnoldi_inflight < 0, "Arnoldi step %d is still in flight", ctx->arnoldi_inflight);
+  REQUIRE(ctx->arnoldi_part1 < 0, "the first half of Arnoldi step %d is queued and was never finished", ctx->arnoldi_part1);
   CU(cudaSetDevice(ctx->device));
   const int m = j + 1;
   const size_t ld = (size_t)ctx->ld;
@@ -1234,6 +1258,31 @@ int spis_arnoldi_launch(spis_ctx* ctx, int j) {
       TRY(launch_lincomb(ctx, ctx->V, m, h1, nullptr, -1.0, ctx->W, ctx->W, 0, nullptr));
       TRY(launch_mdot(ctx, ctx->V, m, nullptr, 0, ctx->W, h2));
     }
+  }
+  ctx->arnoldi_part1 = j;
+  return SPIS_OK;
+}
+
+// Second half: (CGS2) w -= V h2 -> q[j+1] with its norm, normalisation, Hessenberg column to the host.
+// With m_it > 0 the same sweep over the basis also forms the iterate x = x0 + Z[:, :m_it] y of the PREVIOUS
+// step (solvers.py:287) -- only without a preconditioner (Z is V) and m_it <= j + 1.
+int spis_arnoldi_finish(spis_ctx* ctx, int j, int m_it, const double* y_it) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(ctx->arnoldi_part1 == j, "spis_arnoldi_begin(%d) has not been called (queued: %d)", j, ctx->arnoldi_part1);
+  CU(cudaSetDevice(ctx->device));
+  const int m = j + 1;
+  const size_t ld = (size_t)ctx->ld;
+  double* qn = ctx->V + (size_t)(j + 1) * ld;
+  double* h2 = ctx->d_small + ctx->K;
+  double* scal = ctx->d_small + 2 * ctx->K;
+  if (m_it > 0) {
+    REQUIRE(y_it && m_it <= m, "bad iterate arguments (m_it=%d, step %d)", m_it, j);
+    REQUIRE(ctx->orth == SPIS_ORTH_CGS2 && ctx->pre_kind == SPIS_PRE_NONE && ctx->fuse_iterate,
+            "the fused iterate needs CGS2 and no preconditioner");
+    memcpy(ctx->h_y, y_it, (size_t)m_it * sizeof(double));
+    CU(cudaMemcpyAsync(ctx->d_y, ctx->h_y, (size_t)m_it * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    TRY(launch_lincomb2(ctx, ctx->V, m, h2, ctx->d_y, m_it, ctx->W, ctx->x0_is_zero ? nullptr : ctx->X0, qn, ctx->X, scal));
+  } else if (ctx->orth == SPIS_ORTH_CGS2) {
     TRY(launch_lincomb(ctx, ctx->V, m, h2, nullptr, -1.0, ctx->W, qn, 1, scal));
   }
   // q[j+1] = w / ||w||                                             (solvers.py:196-198)
@@ -1244,7 +1293,28 @@ int spis_arnoldi_launch(spis_ctx* ctx, int j) {
   if (ctx->xactive)   // peer-timeout word of the NVLink collectives rides along (slot scal[7] is unused)
     CU(cudaMemcpyAsync(ctx->h_small + 2 * ctx->K + 7, ctx->xbuf + ctx->xv.flags_off() + 4 * ctx->xv.world, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaEventRecord(ctx->ev_arnoldi, ctx->stream));
+  ctx->arnoldi_part1 = -1;
   ctx->arnoldi_inflight = j;
+  return SPIS_OK;
+}
+
+int spis_arnoldi_launch(spis_ctx* ctx, int j) {
+  TRY(spis_arnoldi_begin(ctx, j));
+  return spis_arnoldi_finish(ctx, j, 0, nullptr);
+}
+
+// ||A x - b|| of the iterate that is already in the X buffer (formed by spis_arnoldi_finish)
+int spis_residual_launch(spis_ctx* ctx) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(ctx->began, "spis_solve_begin has not been called");
+  REQUIRE(!ctx->resid_inflight, "an iterate/residual pair is still in flight");
+  CU(cudaSetDevice(ctx->device));
+  double* scal = ctx->d_small + 2 * ctx->K;
+  TRY(do_halo(ctx, ctx->X));
+  TRY(launch_spmv(ctx, SPIS_SLOT_A, 2, ctx->X, ctx->B, nullptr, scal + 2));
+  CU(cudaMemcpyAsync(ctx->h_resid, scal + 2, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaEventRecord(ctx->ev_resid, ctx->stream));
+  ctx->resid_inflight = true;
   return SPIS_OK;
 }
 

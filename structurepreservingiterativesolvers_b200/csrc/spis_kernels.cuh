@@ -459,6 +459,97 @@ lincomb_kernel(const double* __restrict__ V, int64_t ld, int m, const double* __
 }
 
 // ------------------------------------------------------------------------------------------
+// K3b + K5 in one pass: the last projection of Arnoldi step j+1 and the iterate of step j read the SAME
+// basis rows back to back (Z aliases V without a preconditioner):
+//     outA = baseA - sum_{i<m}  cA[i] V_i    (+ ||outA||^2)      w'' -> q[j+2]          (solvers.py:195)
+//     outB = baseB + sum_{i<mB} cB[i] V_i                        x_j = x0 + Z y_j       (solvers.py:287)
+// so they share one sweep over V: (m + 4) * 8 n bytes instead of (2m + 5) * 8 n.  Each output is the same
+// fma chain in the same row order as lincomb_kernel produces it (rows i >= mB add 0 * V_i to outB), so the
+// results are bit-identical to the two separate launches.
+// ------------------------------------------------------------------------------------------
+template <int IU, bool FULL>
+__device__ __forceinline__ void lincomb2_tile(const double* __restrict__ V, int64_t ld, int m,
+                                              const double* scA, const double* scB, const double* baseA,
+                                              const double* baseB, double* outA, double* outB,
+                                              int64_t n, int64_t tile, double& ss) {
+  const int64_t e0 = tile * kTile + 2 * threadIdx.x;
+  const int64_t e1 = e0 + 2 * kThreads;
+  const bool p0 = FULL || e0 < n, p1 = FULL || e1 < n;
+  double2 a0 = make_double2(0.0, 0.0), a1 = a0, b0 = a0, b1 = a0;
+  if (p0) { a0 = ld_keep(baseA + e0); if (baseB) b0 = ld_keep(baseB + e0); }
+  if (p1) { a1 = ld_keep(baseA + e1); if (baseB) b1 = ld_keep(baseB + e1); }
+  const double* row = V;
+  int i0 = 0;
+  for (; i0 + IU <= m; i0 += IU) {
+    double2 u[IU], v[IU];
+#pragma unroll
+    for (int q = 0; q < IU; ++q) {
+      if (FULL) {
+        u[q] = ld_stream(row + (size_t)q * ld + e0);
+        v[q] = ld_stream(row + (size_t)q * ld + e1);
+      } else {
+        u[q] = p0 ? ld_stream(row + (size_t)q * ld + e0) : make_double2(0.0, 0.0);
+        v[q] = p1 ? ld_stream(row + (size_t)q * ld + e1) : make_double2(0.0, 0.0);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < IU; ++q) {
+      const double ca = scA[i0 + q], cb = scB[i0 + q];
+      a0.x = fma(ca, u[q].x, a0.x); a0.y = fma(ca, u[q].y, a0.y);
+      a1.x = fma(ca, v[q].x, a1.x); a1.y = fma(ca, v[q].y, a1.y);
+      b0.x = fma(cb, u[q].x, b0.x); b0.y = fma(cb, u[q].y, b0.y);
+      b1.x = fma(cb, v[q].x, b1.x); b1.y = fma(cb, v[q].y, b1.y);
+    }
+    row += (size_t)IU * ld;
+  }
+  for (; i0 < m; ++i0) {
+    const double ca = scA[i0], cb = scB[i0];
+    if (p0) { const double2 u = ld_stream(row + e0); a0.x = fma(ca, u.x, a0.x); a0.y = fma(ca, u.y, a0.y); b0.x = fma(cb, u.x, b0.x); b0.y = fma(cb, u.y, b0.y); }
+    if (p1) { const double2 v = ld_stream(row + e1); a1.x = fma(ca, v.x, a1.x); a1.y = fma(ca, v.y, a1.y); b1.x = fma(cb, v.x, b1.x); b1.y = fma(cb, v.y, b1.y); }
+    row += ld;
+  }
+  if (p0) { *reinterpret_cast<double2*>(outA + e0) = a0; *reinterpret_cast<double2*>(outB + e0) = b0; ss = fma(a0.x, a0.x, ss); ss = fma(a0.y, a0.y, ss); }
+  if (p1) { *reinterpret_cast<double2*>(outA + e1) = a1; *reinterpret_cast<double2*>(outB + e1) = b1; ss = fma(a1.x, a1.x, ss); ss = fma(a1.y, a1.y, ss); }
+}
+
+template <int IU>
+__global__ void __launch_bounds__(kThreads)
+lincomb2_kernel(const double* __restrict__ V, int64_t ld, int m, const double* __restrict__ coefA,
+                const double* __restrict__ coefB, int mB, const double* baseA, const double* baseB,
+                double* outA, double* outB, int64_t n,
+                double* __restrict__ partial, unsigned* counter, double* sumsq_out,
+                XView xv, unsigned long long seq) {
+  extern __shared__ double smem[];
+  double* scA = smem;                        // [m]   -coefA
+  double* scB = smem + m + (m & 1);          // [m]   +coefB, zero beyond mB
+  double* sred = scB + m + (m & 1);          // [kWarps*32]
+  for (int i = threadIdx.x; i < m; i += kThreads) {
+    scA[i] = -coefA[i];
+    scB[i] = i < mB ? coefB[i] : 0.0;
+  }
+  __syncthreads();
+  double ss = 0.0;
+  const int64_t ntiles = (n + kTile - 1) / kTile;
+  const int64_t nfull = n / kTile;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    if (tile < nfull) lincomb2_tile<IU, true>(V, ld, m, scA, scB, baseA, baseB, outA, outB, n, tile, ss);
+    else lincomb2_tile<IU, false>(V, ld, m, scA, scB, baseA, baseB, outA, outB, n, tile, ss);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  ss = warp_sum(ss);
+  if (lane == 0) sred[warp] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int wv = 0; wv < kWarps; ++wv) t += sred[wv];
+    partial[blockIdx.x] = t;
+  }
+  __syncthreads();
+  finish_reduction(partial, 1, 1, counter, sumsq_out, sred, xv, seq);
+}
+
+// ------------------------------------------------------------------------------------------
 // K3c  middle of CGS2, one pass over the basis instead of two:
 //     w' = w - sum_i coef[i] V_i           (first projection applied,  solvers.py:195)
 //     out[i] = V_i . w'                     (second projection measured, solvers.py:194 again)

@@ -134,6 +134,19 @@ class KrylovContext:
     def arnoldi_launch(self, j: int):
         self._check(self._lib.spis_arnoldi_launch(self._h, j))
 
+    def arnoldi_begin(self, j: int):
+        self._check(self._lib.spis_arnoldi_begin(self._h, j))
+
+    def arnoldi_finish(self, j: int, y_iterate=None):
+        if y_iterate is None:
+            self._check(self._lib.spis_arnoldi_finish(self._h, j, 0, None))
+        else:
+            y = nat.as_f64(y_iterate)
+            self._check(self._lib.spis_arnoldi_finish(self._h, j, y.size, nat.dptr(y)))
+
+    def residual_launch(self):
+        self._check(self._lib.spis_residual_launch(self._h))
+
     def arnoldi_wait(self, j: int) -> np.ndarray:
         out = np.empty(j + 2, dtype=np.float64)
         self._check(self._lib.spis_arnoldi_wait(self._h, j, nat.dptr(out)))

@@ -368,6 +368,14 @@ class DeviceSession:
     def arnoldi_wait(self, j):
         return self.ctx.arnoldi_wait(j)
 
+    @property
+    def can_fuse_iterate(self):
+        """True when the iterate of step j can be formed by the last projection sweep of step j+1 (CGS2,
+        no preconditioner: Z is V).  Asked once per solve."""
+        ctx = self.ctx
+        return (self._host_pre is None and hasattr(ctx, "arnoldi_begin") and hasattr(ctx, "info")
+                and ctx.info("can_fuse_iterate") == 1)
+
     def close(self):
         try:
             self._join_setup()
@@ -432,8 +440,10 @@ class _Arnoldi:
     def __init__(self, sess, k, lookahead, beta=None):
         self.sess, self.k, self.lookahead = sess, k, bool(lookahead)
         self.H = np.zeros((k + 1, k))
-        self._inflight = None
+        self._inflight = None                 # step whose column is on its way to the host
+        self._begun = None                    # step with only its first half queued (fused-iterate mode)
         self._have = -1
+        self._fuse = self.lookahead and sess.can_fuse_iterate
         # Givens recurrence of the unconstrained least-squares residual |beta e1 - H y|_min: used only
         # to decide whether launching the NEXT Arnoldi step ahead of time can be wasted work
         self._cs = np.zeros(k)
@@ -443,6 +453,9 @@ class _Arnoldi:
     def column(self, j):
         if self._have == j:                   # fetched while the previous iterate/residual pair ran
             return self.H[: j + 2, j].copy()
+        if self._begun == j:                  # first half queued, nothing to fuse into the second
+            self.sess.ctx.arnoldi_finish(j)
+            self._begun, self._inflight = None, j
         if self._inflight != j:
             self.sess.arnoldi_launch(j)
         col = self.sess.arnoldi_wait(j)
@@ -473,7 +486,13 @@ class _Arnoldi:
         ctx = self.sess.ctx
         if not (self.lookahead and hasattr(ctx, "iterate_residual_launch")):
             return ctx.iterate_residual(yk)
-        ctx.iterate_residual_launch(yk)
+        if self._begun == j + 1:
+            # the last projection of step j+1 sweeps the same basis rows the iterate needs: one pass for both
+            ctx.arnoldi_finish(j + 1, yk)
+            self._begun, self._inflight = None, j + 1
+            ctx.residual_launch()
+        else:
+            ctx.iterate_residual_launch(yk)
         if self._inflight == j + 1:
             col = self.sess.arnoldi_wait(j + 1)
             self._inflight = None
@@ -482,8 +501,7 @@ class _Arnoldi:
             # one can only end if even its unconstrained minimiser is below tol (known now, from column j+1)
             next_may_end = tol is not None and self.ls_residual() < tol
             if not may_end and not next_may_end and col[j + 2] != 0 and j + 2 < self.k:
-                self.sess.arnoldi_launch(j + 2)
-                self._inflight = j + 2
+                self._queue(j + 2)
         return ctx.iterate_residual_wait()
 
     def ls_residual(self):
@@ -498,12 +516,22 @@ class _Arnoldi:
         r[0] += beta
         return float(np.linalg.norm(r))
 
-    def prefetch(self, j):
-        if self.lookahead and j < self.k and self._inflight is None:
+    def _queue(self, j):
+        if self._fuse:
+            self.sess.ctx.arnoldi_begin(j)        # second half follows once the iterate coefficients exist
+            self._begun = j
+        else:
             self.sess.arnoldi_launch(j)
             self._inflight = j
 
+    def prefetch(self, j):
+        if self.lookahead and j < self.k and self._inflight is None and self._begun is None and self._have != j:
+            self._queue(j)
+
     def drain(self):
+        if self._begun is not None:               # queued speculatively, not needed: finish it so the context is idle
+            self.sess.ctx.arnoldi_finish(self._begun)
+            self._inflight, self._begun = self._begun, None
         if self._inflight is not None:
             self.sess.arnoldi_wait(self._inflight)
             self._inflight = None

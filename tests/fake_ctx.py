@@ -51,6 +51,9 @@ class FakeKrylovContext:
         self.aux_threads = getattr(self, "aux_threads", set()) | {threading.get_ident()}
 
     def info(self, key):
+        if key == "can_fuse_iterate":
+            return int(self.pre_kind == nat.PRE_NONE and self.opts.get("orth", nat.ORTH_CGS2) == nat.ORTH_CGS2
+                       and self.opts.get("fuse_iterate", 1))
         return {"n": self.n, "k_max": self.k_max}.get(key, 0)
 
     def upload_matrix(self, slot, A):
@@ -126,9 +129,9 @@ class FakeKrylovContext:
         self.log.append(("begin",))
         return float(beta)
 
-    def arnoldi_launch(self, j):
-        assert self._pending is None
-        self.log.append(("launch", j))
+    def arnoldi_begin(self, j):
+        assert self._pending is None and getattr(self, "_begun", None) is None
+        self.log.append(("begin_step", j))
         m = j + 1
         n = self.n
         if self.pre_kind not in (nat.PRE_NONE, nat.PRE_HOST):
@@ -136,6 +139,7 @@ class FakeKrylovContext:
         w = self._spmv(nat.SLOT_A, self._Z()[j])
         Vm = self.V[:m, :n]
         orth = self.opts.get("orth", nat.ORTH_CGS2)
+        h2 = None
         if orth == nat.ORTH_MGS:
             h = np.zeros(m)
             for i in range(m):
@@ -146,14 +150,37 @@ class FakeKrylovContext:
             w = w - Vm.T @ h
             if orth == nat.ORTH_CGS2:
                 h2 = self._ar(Vm @ w)
-                w = w - Vm.T @ h2
                 h = h + h2
+        self._begun = (j, h, h2, w)
+
+    def arnoldi_finish(self, j, y_iterate=None):
+        bj, h, h2, w = self._begun
+        assert bj == j
+        self._begun = None
+        n = self.n
+        if y_iterate is not None:                      # the iterate of the previous step rides on the last sweep
+            assert self.pre_kind == nat.PRE_NONE and self.opts.get("orth", nat.ORTH_CGS2) == nat.ORTH_CGS2
+            assert len(y_iterate) <= j + 1
+            self.form_iterate(y_iterate)
+            self.log.append(("fused_iterate", len(y_iterate)))
+        if h2 is not None:
+            w = w - self.V[: j + 1, :n].T @ h2
         nrm = np.sqrt(self._ar(w @ w)[0])
         if nrm != 0:
             self.V[j + 1, :n] = w / nrm
         else:
             self.V[j + 1, :n] = w
         self._pending = (j, np.concatenate([h, [nrm]]))
+
+    def arnoldi_launch(self, j):
+        self.log.append(("launch", j))
+        self.arnoldi_begin(j)
+        self.arnoldi_finish(j)
+
+    def residual_launch(self):
+        r = self._spmv(nat.SLOT_A, self.Xfull) - self.vecs[nat.VEC_B]
+        self._resid = float(np.sqrt(self._ar(r @ r)[0]))
+        self.log.append(("residual_launch",))
 
     def arnoldi_wait(self, j):
         pj, col = self._pending

@@ -99,6 +99,32 @@ def test_every_spmv_storage_reproduces_the_reference(name, fmt, golden):
     assert helpers.rel_diff(x, golden[f"{name}/x_last"]) <= tolerance(name)
 
 
+def test_fused_iterate_is_bit_identical_to_separate_passes():
+    """fuse_iterate=1 forms x_j inside the last projection sweep of Arnoldi step j+1 (one pass over the
+    basis for both): the same fma chains per output, so every iterate, residual and Hessenberg entry is
+    bit-identical to the run that uses separate launches."""
+    spec, dic, prob, x0, pre = cases.instantiate("lkdv_cg_tol8_n1500")
+    x0 = 0.01 * np.cos(np.arange(dic["b"].size))                   # non-zero x0: the base vector of the iterate
+    cl = wrappers.lkdv.conlist(dic, x0)
+    out = []
+    for fuse in (1, 0):
+        sess = solvers.DeviceSession(dic["A"], dic["b"], x0, 50, conlist=cl, profile=True)
+        sess.ctx.set_option("fuse_iterate", fuse)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            x, info = solvers.cgmres(dic["A"], dic["b"], x0, 50, tol=1e-8, conlist=cl, session=sess, small_solver="kkt")
+        prof = sess.ctx.profile()
+        out.append((x, info["steps"], np.array(info["res"]), [np.array(info["x"][j]) for j in (1, 5, info["steps"])],
+                    prof["lincomb"]["launches"]))
+        sess.close()
+    assert out[0][1] == out[1][1]
+    np.testing.assert_array_equal(out[0][0], out[1][0])
+    np.testing.assert_array_equal(out[0][2], out[1][2])
+    for a, b in zip(out[0][3], out[1][3]):
+        np.testing.assert_array_equal(a, b)
+    assert out[0][4] < out[1][4]                                    # fewer sweeps over the basis
+
+
 def test_session_reuse_and_profile():
     spec, dic, prob, x0, pre = cases.instantiate("lkdv_cg_tol8_n1500")
     cl = wrappers.lkdv.conlist(dic, x0)

@@ -104,14 +104,18 @@ def test_lookahead_overlaps_but_keeps_results():
         outs.append((x, sess.ctx.log))
     np.testing.assert_array_equal(outs[0][0], outs[1][0])
     log = outs[0][1]
-    # with lookahead, Arnoldi step j+1 is launched before iterate j is formed
-    i_launch1 = log.index(("launch", 1))
-    i_iter1 = log.index(("iterate", 1))
-    assert i_launch1 < i_iter1
+    # with lookahead the first half of Arnoldi step j+1 is queued before iterate j exists, and the iterate is
+    # then formed by the last projection sweep of that step (no separate iterate pass)
+    assert log.index(("begin_step", 1)) < log.index(("fused_iterate", 1))
+    # (the last iterate has no following Arnoldi step to ride on: it is the only separate iterate pass)
+    assert [e for e in log if e[0] == "iterate"] == [("iterate", info["steps"])]
+    assert len([e for e in log if e[0] == "fused_iterate"]) == len([e for e in log if e[0] == "residual_launch"]) == info["steps"] - 1
     log_nl = outs[1][1]
     assert log_nl.index(("launch", 1)) > log_nl.index(("iterate", 1))
-    # every launch is waited for exactly once (also the speculative one after convergence)
-    assert sorted(e[1] for e in log if e[0] == "launch") == sorted(e[1] for e in log if e[0] == "wait")
+    assert not [e for e in log_nl if e[0] == "fused_iterate"]
+    # every step that was begun is waited for exactly once (also a speculative one after convergence)
+    for lg in (log, log_nl):
+        assert sorted(e[1] for e in lg if e[0] == "begin_step") == sorted(e[1] for e in lg if e[0] == "wait")
 
 
 def test_constraints_only_built_in_constrained_phase():
