@@ -41,7 +41,7 @@ struct Matrix {
   uint16_t* pid = nullptr; int32_t* tab_len = nullptr; int32_t* tab_off = nullptr; double* tab_val = nullptr;
   int npat = 0, patW = 0;
   // dictionary-coded values (SPIS_FMT_SELLD): scols as in SELL, one code per entry, table of <= 256 doubles
-  uint8_t* codes = nullptr; double* dict = nullptr; int ndict = 0;
+  uint32_t* codes = nullptr; int64_t* code_off = nullptr; double* dict = nullptr; int ndict = 0;
 };
 
 struct Constraint {
@@ -492,7 +492,7 @@ int launch_spmv_mode(spis_ctx* ctx, const Matrix& M, const double* x, const doub
   } else if (M.fmt == SPIS_FMT_SELLD) {
     const int64_t nslices = (M.nrows + 31) / 32;
     const int grid = grid_for(ctx, (nslices + kWarps - 1) / kWarps, ctx->spmv_ctas_per_sm);
-    spmv_selld_kernel<MODE><<<grid, kThreads, 0, ctx->stream>>>(M.slice_off, M.scols, M.codes, M.dict, M.nrows, x, b, y, ctx->d_partial);
+    spmv_selld_kernel<MODE><<<grid, kThreads, 0, ctx->stream>>>(M.slice_off, M.code_off, M.scols, M.codes, M.dict, M.nrows, x, b, y, ctx->d_partial);
     if (MODE != 0) reduce_partials_kernel<<<1, kThreads, 0, ctx->stream>>>(ctx->d_partial, grid, sumsq_out, xv, seq);
   } else if (M.fmt == SPIS_FMT_PATTERN) {
     const int grid = grid_for(ctx, (M.nrows + kThreads - 1) / kThreads, ctx->spmv_ctas_per_sm);
@@ -580,7 +580,7 @@ void free_matrix(spis_ctx* ctx, Matrix& M) {
   dfree(ctx, M.indptr); dfree(ctx, M.cols); dfree(ctx, M.vals);
   dfree(ctx, M.slice_off); dfree(ctx, M.scols); dfree(ctx, M.svals);
   dfree(ctx, M.pid); dfree(ctx, M.tab_len); dfree(ctx, M.tab_off); dfree(ctx, M.tab_val);
-  dfree(ctx, M.codes); dfree(ctx, M.dict);
+  dfree(ctx, M.codes); dfree(ctx, M.code_off); dfree(ctx, M.dict);
   M = Matrix();
 }
 
@@ -706,14 +706,16 @@ static bool is_pinned_host(const void* p) {
 // thread's upload stream
 static int device_any_nonzero(spis_ctx* ctx, const double* p, size_t n, int* out) {
   cudaStream_t s = up_stream(ctx);
-  int* flag = reinterpret_cast<int*>(ctx->d_counter + (tl_use_aux ? 2 : 1));
-  CU(cudaMemsetAsync(flag, 0, sizeof(int), s));
+  int* flag = nullptr;                         // per call: several helper threads may be scanning at once
+  TRY(dalloc(ctx, &flag, 1));
   const int64_t want = (int64_t)((n / 2 + 255) / 256);
   const int grid = (int)(want < 1 ? 1 : want > ctx->nsm ? ctx->nsm : want);
   any_nonzero_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const unsigned long long*>(p), (int64_t)n, flag);
-  CU(cudaGetLastError());
-  CU(cudaMemcpyAsync(out, flag, sizeof(int), cudaMemcpyDeviceToHost, s));
-  CU(cudaStreamSynchronize(s));
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, flag, sizeof(int), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  dfree(ctx, flag);
+  if (e != cudaSuccess) return fail(ctx, SPIS_E_CUDA, "zero test failed: %s", cudaGetErrorString(e));
   return SPIS_OK;
 }
 
@@ -726,8 +728,9 @@ static int pinned_any_nonzero(spis_ctx* ctx, const double* p, size_t n, int* out
   const size_t chunk = (size_t)8 << 20;                       // doubles per chunk
   double* scratch = nullptr;
   TRY(dalloc(ctx, &scratch, chunk < n ? chunk : n, false));
-  int* flag = reinterpret_cast<int*>(ctx->d_counter + (tl_use_aux ? 2 : 1));
-  cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(int), s);
+  int* flag = nullptr;
+  TRY(dalloc(ctx, &flag, 1));
+  cudaError_t e = cudaSuccess;
   size_t done = 0;
   int found = 0, k = 0;
   while (e == cudaSuccess && done < n && !found) {
@@ -746,6 +749,7 @@ static int pinned_any_nonzero(spis_ctx* ctx, const double* p, size_t n, int* out
     }
   }
   dfree(ctx, scratch);
+  dfree(ctx, flag);
   if (e != cudaSuccess) return fail(ctx, SPIS_E_CUDA, "zero scan failed: %s", cudaGetErrorString(e));
   *out = found;
   return SPIS_OK;
@@ -975,7 +979,7 @@ int spis_get_info(const spis_ctx* cctx, const char* key, int64_t* value_out) {
 
 // ---- uploads --------------------------------------------------------------------------
 // SELL matrix on the device -> dictionary-coded values if it holds at most 256 distinct doubles.
-static int try_value_dictionary(spis_ctx* ctx, Matrix& M, cudaStream_t s, int* ok_out) {
+static int try_value_dictionary(spis_ctx* ctx, Matrix& M, cudaStream_t s, const std::vector<int64_t>& off, int* ok_out) {
   *ok_out = 0;
   if (M.nnz_padded <= 0) return SPIS_OK;
   unsigned long long* keys = nullptr; int *dense = nullptr, *info = nullptr;
@@ -993,13 +997,21 @@ static int try_value_dictionary(spis_ctx* ctx, Matrix& M, cudaStream_t s, int* o
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
   if (e != cudaSuccess) { cleanup(); dfree(ctx, M.dict); return fail(ctx, SPIS_E_CUDA, "value dictionary failed: %s", cudaGetErrorString(e)); }
   if (h_info[1] || h_info[2] < 1 || h_info[2] > 256) { cleanup(); dfree(ctx, M.dict); return SPIS_OK; }
-  int rc = dalloc(ctx, &M.codes, (size_t)M.nnz_padded, false);
-  if (rc != SPIS_OK) { cleanup(); dfree(ctx, M.dict); return rc; }
-  dict_encode_kernel<<<grid, 256, 0, s>>>(M.svals, M.nnz_padded, keys, dense, M.codes);
-  e = cudaGetLastError();
-  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  // word offsets of the packed codes: ceil(width / 4) words per lane and slice
+  const int64_t nslices = (int64_t)off.size() - 1;
+  std::vector<int64_t> coff((size_t)nslices + 1);
+  coff[0] = 0;
+  for (int64_t q = 0; q < nslices; ++q) coff[q + 1] = coff[q] + (((off[q + 1] - off[q]) / 32 + 3) / 4) * 32;
+  int rc = dalloc(ctx, &M.codes, (size_t)coff[nslices], false);
+  if (rc == SPIS_OK) rc = dalloc(ctx, &M.code_off, (size_t)nslices + 1, false);
+  if (rc != SPIS_OK) { cleanup(); dfree(ctx, M.codes); dfree(ctx, M.dict); return rc; }
+  e = cudaMemcpyAsync(M.code_off, coff.data(), ((size_t)nslices + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s);
+  const int cgrid = (int)((nslices * 32 + 255) / 256);
+  dict_encode_kernel<<<cgrid, 256, 0, s>>>(M.svals, M.slice_off, M.code_off, nslices, keys, dense, M.codes);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);       // coff (pageable) must outlive the copy
   cleanup();
-  if (e != cudaSuccess) { dfree(ctx, M.codes); dfree(ctx, M.dict); return fail(ctx, SPIS_E_CUDA, "value encoding failed: %s", cudaGetErrorString(e)); }
+  if (e != cudaSuccess) { dfree(ctx, M.codes); dfree(ctx, M.code_off); dfree(ctx, M.dict); return fail(ctx, SPIS_E_CUDA, "value encoding failed: %s", cudaGetErrorString(e)); }
   dfree(ctx, M.svals);
   M.ndict = h_info[2];
   M.fmt = SPIS_FMT_SELLD;
@@ -1129,7 +1141,7 @@ int spis_upload_csr(spis_ctx* ctx, int slot, int64_t nrows, int64_t ncols, int64
     dfree(ctx, M.indptr); dfree(ctx, M.cols); dfree(ctx, M.vals);
     if (fmt == SPIS_FMT_SELL && (ctx->fmt_pref == SPIS_FMT_SELLD || (ctx->fmt_pref == SPIS_FMT_AUTO && ctx->auto_dict))) {
       int ok = 0;
-      TRY(try_value_dictionary(ctx, M, s, &ok));
+      TRY(try_value_dictionary(ctx, M, s, off, &ok));
       REQUIRE(ok || ctx->fmt_pref != SPIS_FMT_SELLD, "matrix in slot %d has more than 256 distinct values: spmv_format=selld does not apply", slot);
     }
   } else {

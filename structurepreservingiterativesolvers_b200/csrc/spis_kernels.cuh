@@ -1180,21 +1180,35 @@ __global__ void dict_number_kernel(const unsigned long long* __restrict__ keys, 
   if (lane == 0) info[2] = next;
 }
 
-__global__ void dict_encode_kernel(const double* __restrict__ vals, int64_t count, const unsigned long long* __restrict__ keys,
-                                   const int* __restrict__ dense, uint8_t* __restrict__ codes) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
-    const unsigned long long key = (unsigned long long)__double_as_longlong(vals[i]) ^ 0x8000000000000001ull;
-    unsigned slot = (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 40) % kDictSlots;
-    while (keys[slot] != key) slot = (slot + 1) % kDictSlots;
-    codes[i] = (uint8_t)dense[slot];
+// codes of a slice are packed four to a 32-bit word, [word][lane]: entry k of lane l sits in byte (k & 3) of
+// word code_off[slice] + (k >> 2) * 32 + l, so a warp fetches the codes of four entries with one 128-byte load
+__global__ void dict_encode_kernel(const double* __restrict__ vals, const int64_t* __restrict__ slice_off,
+                                   const int64_t* __restrict__ code_off, int64_t nslices,
+                                   const unsigned long long* __restrict__ keys, const int* __restrict__ dense,
+                                   uint32_t* __restrict__ codes) {
+  const int64_t slice = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (slice >= nslices) return;
+  const int64_t off = slice_off[slice];
+  const int width = (int)((slice_off[slice + 1] - off) >> 5);
+  const int64_t coff = code_off[slice];
+  for (int k0 = 0; k0 < width; k0 += 4) {
+    uint32_t word = 0;
+    for (int q = 0; q < 4 && k0 + q < width; ++q) {
+      const unsigned long long key = (unsigned long long)__double_as_longlong(vals[off + (int64_t)(k0 + q) * 32 + lane]) ^ 0x8000000000000001ull;
+      unsigned slot = (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 40) % kDictSlots;
+      while (keys[slot] != key) slot = (slot + 1) % kDictSlots;
+      word |= (uint32_t)dense[slot] << (8 * q);
+    }
+    codes[coff + (int64_t)(k0 >> 2) * 32 + lane] = word;
   }
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 8)
-spmv_selld_kernel(const int64_t* __restrict__ slice_off, const int32_t* __restrict__ cols,
-                  const uint8_t* __restrict__ codes, const double* __restrict__ table, int64_t nrows,
+spmv_selld_kernel(const int64_t* __restrict__ slice_off, const int64_t* __restrict__ code_off,
+                  const int32_t* __restrict__ cols, const uint32_t* __restrict__ codes,
+                  const double* __restrict__ table, int64_t nrows,
                   const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ y,
                   double* __restrict__ partial) {
   __shared__ double sdict[256];
@@ -1211,7 +1225,7 @@ spmv_selld_kernel(const int64_t* __restrict__ slice_off, const int32_t* __restri
       const int64_t off = __ldg(slice_off + slice);
       const int width = (int)((__ldg(slice_off + slice + 1) - off) >> 5);
       const int32_t* c = cols + off + lane;
-      const uint8_t* v = codes + off + lane;
+      const uint32_t* v = codes + __ldg(code_off + slice) + lane;
       const int64_t row = (slice << 5) + lane;
       double bv = 0.0;
       if (MODE != 0 && row < nrows) bv = __ldg(b + row);
@@ -1220,13 +1234,15 @@ spmv_selld_kernel(const int64_t* __restrict__ slice_off, const int32_t* __restri
       for (; k + 4 <= width; k += 4) {
         const int32_t c0 = __ldcs(c + (k + 0) * 32), c1 = __ldcs(c + (k + 1) * 32);
         const int32_t c2 = __ldcs(c + (k + 2) * 32), c3 = __ldcs(c + (k + 3) * 32);
-        const unsigned q0 = __ldcs(v + (k + 0) * 32), q1 = __ldcs(v + (k + 1) * 32);
-        const unsigned q2 = __ldcs(v + (k + 2) * 32), q3 = __ldcs(v + (k + 3) * 32);
+        const uint32_t q = __ldcs(v + (k >> 2) * 32);
         const double x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
-        acc0 = fma(sdict[q0], x0, acc0); acc1 = fma(sdict[q1], x1, acc1);
-        acc0 = fma(sdict[q2], x2, acc0); acc1 = fma(sdict[q3], x3, acc1);
+        acc0 = fma(sdict[q & 255u], x0, acc0); acc1 = fma(sdict[(q >> 8) & 255u], x1, acc1);
+        acc0 = fma(sdict[(q >> 16) & 255u], x2, acc0); acc1 = fma(sdict[q >> 24], x3, acc1);
       }
-      for (; k < width; ++k) acc0 = fma(sdict[__ldcs(v + k * 32)], __ldg(x + __ldcs(c + k * 32)), acc0);
+      if (k < width) {
+        uint32_t q = __ldcs(v + (k >> 2) * 32);
+        for (; k < width; ++k, q >>= 8) acc0 = fma(sdict[q & 255u], __ldg(x + __ldcs(c + k * 32)), acc0);
+      }
       const double ax = acc0 + acc1;
       if (row < nrows) {
         if (MODE == 0) {

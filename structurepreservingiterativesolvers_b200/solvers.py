@@ -213,7 +213,6 @@ class DeviceSession:
         self._host_pre = None
         self._setup_precond(pre)
         tr("preconditioner")
-        self._cons = []
         self._Zhost = None
         self._Zrows = 0
         # The constraint data is first needed at the first constrained step (solvers.py:242-247), many
@@ -225,12 +224,17 @@ class DeviceSession:
         conlist = list(conlist)
         if len(conlist) > nat.MAX_SLOTS - nat.SLOT_CON0:
             raise ValueError("too many constraints")
+        self._cons = [None] * len(conlist)
         if conlist and _opt("async_setup", async_setup) and type(self) is DeviceSession and hasattr(ctx, "use_aux_stream"):
-            self._bg = threading.Thread(target=self._setup_constraints_bg, args=(conlist,), daemon=True)
-            self._bg.start()
-            tr("constraints (handed to helper thread)")
+            # one helper per constraint: the host scan of one (`0*A`) overlaps the PCIe upload of another
+            self._bg = [threading.Thread(target=self._setup_constraints_bg, args=(idx, const), daemon=True)
+                        for idx, const in enumerate(conlist)]
+            for th in self._bg:
+                th.start()
+            tr("constraints (handed to helper threads)")
         else:
-            self._setup_constraints(conlist)
+            for idx, const in enumerate(conlist):
+                self._setup_constraint(idx, const)
             tr("constraints")
 
     def _any_rank(self, flag):
@@ -273,27 +277,29 @@ class DeviceSession:
             ctx.set_precond(nat.PRE_HOST)
 
     # -- constraints: solvers.py:22-40 -----------------------------------------------------------
-    def _setup_constraints_bg(self, conlist):
+    def _setup_constraints_bg(self, idx, const):
         try:
             self.ctx.use_aux_stream(True)
             try:
-                self._setup_constraints(conlist)
+                self._setup_constraint(idx, const)
             finally:
                 self.ctx.use_aux_stream(False)
         except BaseException as exc:                       # re-raised on the caller's thread by _join_setup
-            self._bg_error = exc
+            if self._bg_error is None:
+                self._bg_error = exc
 
     def _join_setup(self):
         if self._bg is not None:
-            self._bg.join()
+            for th in self._bg:
+                th.join()
             self._bg = None
         if self._bg_error is not None:
             exc, self._bg_error = self._bg_error, None
             raise exc
 
-    def _setup_constraints(self, conlist):
+    def _setup_constraint(self, idx, const):
         tr = _Trace()
-        for idx, const in enumerate(conlist):
+        if True:
             kind = _classify_constraint(const)
             entry = {"kind": kind, "const": const, "error": None}
             if kind == "class":
@@ -321,7 +327,7 @@ class DeviceSession:
                     raise
                 except Exception as exc:                    # surfaces where the reference builds containers
                     entry["error"] = exc
-            self._cons.append(entry)
+            self._cons[idx] = entry
 
     def containers(self, m):
         """Reduced constraints for Z = z[:m].T (the reference rebuilds these per step, solvers.py:242-247)."""

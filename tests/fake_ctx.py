@@ -48,7 +48,10 @@ class FakeKrylovContext:
     def use_aux_stream(self, on):
         """DeviceSession stages the constraints from a helper thread when the context offers this."""
         import threading
-        self.aux_threads = getattr(self, "aux_threads", set()) | {threading.get_ident()}
+        if on:
+            self.aux_switches = getattr(self, "aux_switches", 0) + 1          # one per helper thread
+            self.aux_on_caller_thread = getattr(self, "aux_on_caller_thread", False) or \
+                threading.current_thread() is threading.main_thread()
 
     def info(self, key):
         if key == "can_fuse_iterate":
