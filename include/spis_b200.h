@@ -34,7 +34,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define SPIS_ABI_VERSION 2
+#define SPIS_ABI_VERSION 3
 
 /* error codes */
 #define SPIS_OK            0
@@ -162,6 +162,11 @@ int spis_arnoldi_step(spis_ctx* ctx, int j, double* hcol_out);
 int spis_arnoldi_begin(spis_ctx* ctx, int j);
 int spis_arnoldi_finish(spis_ctx* ctx, int j, int m_it, const double* y_it);
 int spis_residual_launch(spis_ctx* ctx);
+/* spis_arnoldi_begin(j) whose SpMV ALSO measures ||A x - b|| of the iterate in the X buffer (formed by the
+ * preceding spis_arnoldi_finish(j-1, m_it, y_it)): w = A z_j (solvers.py:191) and the residual of the previous
+ * step's iterate (solvers.py:290) share one pass over the matrix.  Replaces the pair spis_residual_launch +
+ * spis_arnoldi_begin(j); collect the norm with spis_iterate_residual_wait.                                   */
+int spis_arnoldi_begin_residual(spis_ctx* ctx, int j);
 /* x_j = x0 + Z[:, :m] y ; resnorm = ||A x_j - b||                  (solvers.py:287,290) */
 int spis_iterate_residual(spis_ctx* ctx, int m, const double* y, double* resnorm_out);
 /* the same in two halves: after _launch the host may fetch the next Hessenberg column and queue the

@@ -79,6 +79,10 @@ struct spis_ctx {
   int profile = 0;
   int ctas_per_sm = 4;
   int spmv_ctas_per_sm = 8;
+  int spmv_variant = 1;         // 0: first-generation SpMV kernels; 1+: prefetching / software-pipelined ones (see launch_spmv_mode)
+  int spmv_pipe_ctas_per_sm = 0;   // 0 = the kernel's own default
+  int spmv_dual = 1;            // A q_{j+2} and ||A x_j - b|| from one pass over A (spis_arnoldi_begin_residual)
+  int spmv_dual_ctas_per_sm = 0;
   int mdot_variant = 0, lincomb_variant = 4;   // mdot 0 = auto (tools/tune.py sweep, profiles/tune_r1.md)
   int x0_is_zero = 0;
   int fuse_jacobi = 1;
@@ -485,25 +489,37 @@ template <int MODE>
 int launch_spmv_mode(spis_ctx* ctx, const Matrix& M, const double* x, const double* b, double* y, double* sumsq_out) {
   const XView xv = MODE != 0 ? fused_view(ctx) : XView();
   const unsigned long long seq = MODE != 0 ? fused_seq(ctx) : 0;
-  if (M.fmt == SPIS_FMT_SELL) {
+  if (M.fmt == SPIS_FMT_SELL && ctx->spmv_variant > 0) {
+    // software-pipelined kernel (4 CTAs per SM by its register budget)
     const int64_t nslices = (M.nrows + 31) / 32;
-    const int grid = grid_for(ctx, (nslices + kWarps - 1) / kWarps, ctx->spmv_ctas_per_sm);
+    const int per_sm = ctx->spmv_pipe_ctas_per_sm > 0 ? ctx->spmv_pipe_ctas_per_sm : 4;
+    const int grid = grid_for(ctx, (nslices + kWarps - 1) / kWarps, per_sm);
+    spmv_sellp_kernel<MODE, false><<<grid, kThreads, 0, ctx->stream>>>(M.slice_off, nullptr, M.scols, M.svals, nullptr, nullptr, M.nrows, x, b, y, ctx->d_partial);
+    if (MODE != 0) reduce_partials_kernel<<<1, kThreads, 0, ctx->stream>>>(ctx->d_partial, grid, sumsq_out, xv, seq);
+  } else if (M.fmt == SPIS_FMT_SELL) {
+    const int64_t nslices = (M.nrows + 31) / 32;
+    const int grid = grid_for(ctx, (nslices + kWarps - 1) / kWarps, (MODE != 0 && ctx->spmv_ctas_per_sm > 6) ? 6 : ctx->spmv_ctas_per_sm);
     spmv_sell_kernel<MODE><<<grid, kThreads, 0, ctx->stream>>>(M.slice_off, M.scols, M.svals, M.nrows, x, b, y, ctx->d_partial, ctx->d_counter, sumsq_out, xv, seq);
   } else if (M.fmt == SPIS_FMT_SELLD) {
     const int64_t nslices = (M.nrows + 31) / 32;
-    const int grid = grid_for(ctx, (nslices + kWarps - 1) / kWarps, ctx->spmv_ctas_per_sm);
+    const int grid = grid_for(ctx, (nslices + kWarps - 1) / kWarps, (MODE != 0 && ctx->spmv_ctas_per_sm > 6) ? 6 : ctx->spmv_ctas_per_sm);
     spmv_selld_kernel<MODE><<<grid, kThreads, 0, ctx->stream>>>(M.slice_off, M.code_off, M.scols, M.codes, M.dict, M.nrows, x, b, y, ctx->d_partial);
     if (MODE != 0) reduce_partials_kernel<<<1, kThreads, 0, ctx->stream>>>(ctx->d_partial, grid, sumsq_out, xv, seq);
   } else if (M.fmt == SPIS_FMT_PATTERN) {
-    const int grid = grid_for(ctx, (M.nrows + kThreads - 1) / kThreads, ctx->spmv_ctas_per_sm);
-#define SPIS_PAT_CASE(NC) case NC: spmv_pattern_kernel<MODE, NC><<<grid, kThreads, 0, ctx->stream>>>(M.pid, M.patW, M.tab_off, M.tab_val, (int)M.nrows, x, b, y, ctx->d_partial); break;
+    // variant 0: first-generation kernel; 1+: the id of the next round's row is prefetched
+    const bool pf = ctx->spmv_variant > 0;
+    int grid = grid_for(ctx, (M.nrows + kThreads - 1) / kThreads, ctx->spmv_ctas_per_sm);
+    while (grid > 1 && (int64_t)M.nrows + (int64_t)grid * kThreads >= (int64_t)INT32_MAX) grid /= 2;   // 32-bit row arithmetic of the prefetch
+#define SPIS_PAT_LAUNCH(NC, PF) spmv_pattern_kernel<MODE, NC, PF><<<grid, kThreads, 0, ctx->stream>>>(M.pid, M.patW, M.tab_off, M.tab_val, (int)M.nrows, x, b, y, ctx->d_partial)
+#define SPIS_PAT_CASE(NC) case NC: if (pf) SPIS_PAT_LAUNCH(NC, true); else SPIS_PAT_LAUNCH(NC, false); break;
     switch (M.patW / 4) { SPIS_PAT_CASE(1) SPIS_PAT_CASE(2) SPIS_PAT_CASE(3) SPIS_PAT_CASE(4)
-      default: spmv_pattern_kernel<MODE, 0><<<grid, kThreads, 0, ctx->stream>>>(M.pid, M.patW, M.tab_off, M.tab_val, (int)M.nrows, x, b, y, ctx->d_partial); }
+      default: if (pf) SPIS_PAT_LAUNCH(0, true); else SPIS_PAT_LAUNCH(0, false); }
 #undef SPIS_PAT_CASE
+#undef SPIS_PAT_LAUNCH
     if (MODE != 0) reduce_partials_kernel<<<1, kThreads, 0, ctx->stream>>>(ctx->d_partial, grid, sumsq_out, xv, seq);
   } else if (M.fmt == SPIS_FMT_SELL2) {
     const int64_t nslices = (M.nrows + 31) / 32;
-    const int grid = grid_for(ctx, (nslices + kWarps - 1) / kWarps, ctx->spmv_ctas_per_sm);
+    const int grid = grid_for(ctx, (nslices + kWarps - 1) / kWarps, (MODE != 0 && ctx->spmv_ctas_per_sm > 6) ? 6 : ctx->spmv_ctas_per_sm);
     spmv_sell2_kernel<MODE><<<grid, kThreads, 0, ctx->stream>>>(M.slice_off, reinterpret_cast<const int2*>(M.scols), reinterpret_cast<const double2*>(M.svals), M.nrows, x, b, y, ctx->d_partial, ctx->d_counter, sumsq_out, xv, seq);
   } else {
     const int T = M.csr_lanes;
@@ -529,6 +545,40 @@ int launch_spmv(spis_ctx* ctx, int slot, int mode, const double* x, const double
   TRY(prof_end(ctx));
   if (mode != 0) return do_allreduce(ctx, sumsq_out, 1);
   return SPIS_OK;
+}
+
+// y1 = A x1 and sumsq = ||A x2 - b||^2 from one pass over the system matrix (formats without a dual kernel: two launches)
+int launch_spmv_dual(spis_ctx* ctx, const double* x1, double* y1, const double* x2, const double* b, double* sumsq_out) {
+  const Matrix& M = ctx->mats[SPIS_SLOT_A];
+  REQUIRE(M.present, "matrix slot %d has not been uploaded", SPIS_SLOT_A);
+  const bool fused = ctx->spmv_dual && (M.fmt == SPIS_FMT_PATTERN || M.fmt == SPIS_FMT_SELL || M.fmt == SPIS_FMT_SELLD);
+  if (!fused) {
+    TRY(launch_spmv(ctx, SPIS_SLOT_A, 0, x1, nullptr, y1, nullptr));
+    return launch_spmv(ctx, SPIS_SLOT_A, 2, x2, b, nullptr, sumsq_out);
+  }
+  const double bytes = 2.0 * (12.0 * (double)M.nnz + 4.0 * (double)(M.nrows + 1) + 16.0 * (double)M.nrows);   // two SpMVs' worth
+  TRY(prof_begin(ctx, SPIS_PROF_SPMV, bytes));
+  const XView xv = fused_view(ctx);
+  const unsigned long long seq = fused_seq(ctx);
+  int grid = 1;
+  if (M.fmt == SPIS_FMT_PATTERN) {
+    grid = grid_for(ctx, (M.nrows + kThreads - 1) / kThreads, ctx->spmv_dual_ctas_per_sm > 0 ? ctx->spmv_dual_ctas_per_sm : 6);
+    while (grid > 1 && (int64_t)M.nrows + (int64_t)grid * kThreads >= (int64_t)INT32_MAX) grid /= 2;
+#define SPIS_PATD_CASE(NC) case NC: spmv_pattern_dual_kernel<NC><<<grid, kThreads, 0, ctx->stream>>>(M.pid, M.patW, M.tab_off, M.tab_val, (int)M.nrows, x1, y1, x2, b, ctx->d_partial); break;
+    switch (M.patW / 4) { SPIS_PATD_CASE(1) SPIS_PATD_CASE(2) SPIS_PATD_CASE(3) SPIS_PATD_CASE(4)
+      default: spmv_pattern_dual_kernel<0><<<grid, kThreads, 0, ctx->stream>>>(M.pid, M.patW, M.tab_off, M.tab_val, (int)M.nrows, x1, y1, x2, b, ctx->d_partial); }
+#undef SPIS_PATD_CASE
+  } else {
+    const int64_t nslices = (M.nrows + 31) / 32;
+    const bool coded = M.fmt == SPIS_FMT_SELLD;
+    grid = grid_for(ctx, (nslices + kWarps - 1) / kWarps, ctx->spmv_dual_ctas_per_sm > 0 ? ctx->spmv_dual_ctas_per_sm : (coded ? 5 : 4));
+    if (coded) spmv_sell_dual_kernel<true><<<grid, kThreads, 0, ctx->stream>>>(M.slice_off, M.code_off, M.scols, nullptr, M.codes, M.dict, M.nrows, x1, y1, x2, b, ctx->d_partial);
+    else spmv_sell_dual_kernel<false><<<grid, kThreads, 0, ctx->stream>>>(M.slice_off, nullptr, M.scols, M.svals, nullptr, nullptr, M.nrows, x1, y1, x2, b, ctx->d_partial);
+  }
+  reduce_partials_kernel<<<1, kThreads, 0, ctx->stream>>>(ctx->d_partial, grid, sumsq_out, xv, seq);
+  CU(cudaGetLastError());
+  TRY(prof_end(ctx));
+  return do_allreduce(ctx, sumsq_out, 1);
 }
 
 int launch_scale(spis_ctx* ctx, double* v, const double* sumsq, const double* jac, double* znext) {
@@ -925,6 +975,10 @@ int spis_set_option(spis_ctx* ctx, const char* key, int64_t value) {
   else if (k == "profile") { ctx->profile = value ? 1 : 0; }
   else if (k == "ctas_per_sm") { REQUIRE(value >= 1 && value <= 16, "ctas_per_sm must be 1..16"); ctx->ctas_per_sm = (int)value; }
   else if (k == "spmv_ctas_per_sm") { REQUIRE(value >= 1 && value <= 16, "spmv_ctas_per_sm must be 1..16"); ctx->spmv_ctas_per_sm = (int)value; }
+  else if (k == "spmv_variant") { REQUIRE(value >= 0 && value <= 1, "spmv_variant must be 0 or 1"); ctx->spmv_variant = (int)value; }
+  else if (k == "spmv_pipe_ctas_per_sm") { REQUIRE(value >= 0 && value <= 16, "spmv_pipe_ctas_per_sm must be 0..16"); ctx->spmv_pipe_ctas_per_sm = (int)value; }
+  else if (k == "spmv_dual") { ctx->spmv_dual = value ? 1 : 0; }
+  else if (k == "spmv_dual_ctas_per_sm") { REQUIRE(value >= 0 && value <= 16, "spmv_dual_ctas_per_sm must be 0..16"); ctx->spmv_dual_ctas_per_sm = (int)value; }
   else if (k == "mdot_variant") { REQUIRE(value == 0 || value == 2 || value == 4 || value == 8, "mdot_variant must be 0 (auto), 2, 4 or 8"); ctx->mdot_variant = (int)value; }
   else if (k == "lincomb_variant") { REQUIRE(value == 2 || value == 4 || value == 8, "lincomb_variant must be 2, 4 or 8"); ctx->lincomb_variant = (int)value; }
   else if (k == "x0_is_zero") { ctx->x0_is_zero = value ? 1 : 0; }
@@ -1227,11 +1281,14 @@ int spis_solve_begin(spis_ctx* ctx, double* beta_out) {
 }
 
 // First half of Arnoldi step j: z_j, w = A z_j and (CGS2) h1 = V^T w, w -= V h1, h2 = V^T w.
-int spis_arnoldi_begin(spis_ctx* ctx, int j) {
+// with_residual: the SpMV also measures ||A x - b|| of the iterate sitting in the X buffer (one pass over A for both).
+static int arnoldi_begin_impl(spis_ctx* ctx, int j, bool with_residual) {
   if (!ctx) return SPIS_E_INVALID;
   REQUIRE(ctx->began, "spis_solve_begin has not been called");
   REQUIRE(j >= 0 && j < ctx->kmax, "Arnoldi index %d out of range [0,%d)", j, ctx->kmax);
-  REQUIRE(ctx->arnoldi_inflight < 0, "Arnoldi step %d is still in flight", ctx->arnoldi_inflight);
+  // (a FINISHED step whose column has not been collected yet may still be in flight: its copy into the pinned
+  //  mirror is queued before anything this call launches; spis_arnoldi_finish is where the mirror is reused)
+  REQUIRE(ctx->arnoldi_inflight < 0 || ctx->arnoldi_inflight == j - 1, "Arnoldi step %d is still in flight", ctx->arnoldi_inflight);
   REQUIRE(ctx->arnoldi_part1 < 0, "the first half of Arnoldi step %d is queued and was never finished", ctx->arnoldi_part1);
   CU(cudaSetDevice(ctx->device));
   const int m = j + 1;
@@ -1247,7 +1304,16 @@ int spis_arnoldi_begin(spis_ctx* ctx, int j) {
     TRY(launch_precond(ctx, qj, zj));
   // w = A z[j]                                                     (solvers.py:191)
   TRY(do_halo(ctx, zj));
-  TRY(launch_spmv(ctx, SPIS_SLOT_A, 0, zj, nullptr, ctx->W, nullptr));
+  if (with_residual) {
+    REQUIRE(!ctx->resid_inflight, "an iterate/residual pair is still in flight");
+    TRY(do_halo(ctx, ctx->X));
+    TRY(launch_spmv_dual(ctx, zj, ctx->W, ctx->X, ctx->B, scal + 2));       // + ||A x - b||  (solvers.py:290)
+    CU(cudaMemcpyAsync(ctx->h_resid, scal + 2, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaEventRecord(ctx->ev_resid, ctx->stream));
+    ctx->resid_inflight = true;
+  } else {
+    TRY(launch_spmv(ctx, SPIS_SLOT_A, 0, zj, nullptr, ctx->W, nullptr));
+  }
   // orthogonalise w against q[0..j]                                (solvers.py:193-196)
   if (ctx->orth == SPIS_ORTH_MGS) {
     CU(cudaMemsetAsync(h2, 0, (size_t)ctx->K * sizeof(double), ctx->stream));
@@ -1275,12 +1341,16 @@ int spis_arnoldi_begin(spis_ctx* ctx, int j) {
   return SPIS_OK;
 }
 
+int spis_arnoldi_begin(spis_ctx* ctx, int j) { return arnoldi_begin_impl(ctx, j, false); }
+int spis_arnoldi_begin_residual(spis_ctx* ctx, int j) { return arnoldi_begin_impl(ctx, j, true); }
+
 // Second half: (CGS2) w -= V h2 -> q[j+1] with its norm, normalisation, Hessenberg column to the host.
 // With m_it > 0 the same sweep over the basis also forms the iterate x = x0 + Z[:, :m_it] y of the PREVIOUS
 // step (solvers.py:287) -- only without a preconditioner (Z is V) and m_it <= j + 1.
 int spis_arnoldi_finish(spis_ctx* ctx, int j, int m_it, const double* y_it) {
   if (!ctx) return SPIS_E_INVALID;
   REQUIRE(ctx->arnoldi_part1 == j, "spis_arnoldi_begin(%d) has not been called (queued: %d)", j, ctx->arnoldi_part1);
+  REQUIRE(ctx->arnoldi_inflight < 0, "the Hessenberg column of Arnoldi step %d has not been collected", ctx->arnoldi_inflight);
   CU(cudaSetDevice(ctx->device));
   const int m = j + 1;
   const size_t ld = (size_t)ctx->ld;

@@ -792,7 +792,7 @@ blockdiag_kernel(const double* __restrict__ blk, int64_t nblk, int64_t sb, int64
 // Algorithmic bytes: 12 nnz_padded + 8 (n/32) + 8 n (x) + 8 n (y or b) [+ 8 n b in mode 1].
 // ------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 8)   // 32 registers: all 2048 threads of an SM resident
+__global__ void __launch_bounds__(kThreads, MODE == 0 ? 8 : 6)   // mode 0: 32 registers, all 2048 threads of an SM resident; the reducing modes spill below 40
 spmv_sell_kernel(const int64_t* __restrict__ slice_off, const int32_t* __restrict__ cols,
                  const double* __restrict__ vals, int64_t nrows, const double* __restrict__ x,
                  const double* __restrict__ b, double* __restrict__ y,
@@ -859,7 +859,7 @@ spmv_sell_kernel(const int64_t* __restrict__ slice_off, const int32_t* __restric
 // 512 B of values and 256 B of columns per load instruction: half the memory instructions and half the
 // L1 requests of the scalar layout for the same bytes.  Slice widths are rounded up to even.
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 8)
+__global__ void __launch_bounds__(kThreads, MODE == 0 ? 8 : 6)
 spmv_sell2_kernel(const int64_t* __restrict__ slice_off, const int2* __restrict__ cols2,
                   const double2* __restrict__ vals2, int64_t nrows, const double* __restrict__ x,
                   const double* __restrict__ b, double* __restrict__ y,
@@ -985,7 +985,9 @@ __global__ void pattern_insert_kernel(const unsigned long long* __restrict__ has
       slot = (slot + 1) % kPatternSlots;
     }
     slot_of_row[r] = (int32_t)slot;
-    atomicMin(rep + slot, (int)r);
+    // a handful of stencils shared by millions of rows: unconditional atomics on the same few words ran for
+    // 4.9 ms (ncu); rows arrive in roughly increasing order, so almost every row sees a smaller representative
+    if (__ldcg(rep + slot) > (int)r) atomicMin(rep + slot, (int)r);
   }
 }
 
@@ -1061,7 +1063,29 @@ __global__ void pattern_assign_kernel(const int32_t* __restrict__ indptr, const 
 // (offset 0, value 0.0) -- a padded entry adds 0.0 * x[row] -- so there is no length test and, for W <= 16,
 // no loop; row + offset is 32-bit arithmetic (n < 2^31 is an invariant of the library).
 // Association: even positions -> acc0, odd positions -> acc1, in every mode.
-template <int MODE, int NCH>
+// One row of the pattern SpMV: stencil p applied at `row`; returns (A x)[row].
+template <int NCH>
+__device__ __forceinline__ double pattern_row(int p, int row, int W, const int32_t* __restrict__ tab_off,
+                                              const double* __restrict__ tab_val, const double* __restrict__ x) {
+  const int4* to = reinterpret_cast<const int4*>(tab_off + p * W);
+  const double2* tv = reinterpret_cast<const double2*>(tab_val + p * W);
+  double acc0 = 0.0, acc1 = 0.0;
+  const int nch = NCH > 0 ? NCH : W / 4;
+#pragma unroll
+  for (int c = 0; c < nch; ++c) {
+    const int4 o = __ldg(to + c);
+    const double2 va = __ldg(tv + 2 * c), vb = __ldg(tv + 2 * c + 1);
+    const double x0 = __ldg(x + (row + o.x)), x1 = __ldg(x + (row + o.y));
+    const double x2 = __ldg(x + (row + o.z)), x3 = __ldg(x + (row + o.w));
+    acc0 = fma(va.x, x0, acc0); acc1 = fma(va.y, x1, acc1);
+    acc0 = fma(vb.x, x2, acc0); acc1 = fma(vb.y, x3, acc1);
+  }
+  return acc0 + acc1;
+}
+
+// PF: the id of the NEXT round's row is fetched before this round's gathers, so that its HBM latency is off
+// the dependent chain id -> stencil -> x.
+template <int MODE, int NCH, bool PF>
 __global__ void __launch_bounds__(kThreads, 8)
 spmv_pattern_kernel(const uint16_t* __restrict__ pid, int W, const int32_t* __restrict__ tab_off,
                     const double* __restrict__ tab_val, int nrows,
@@ -1070,26 +1094,23 @@ spmv_pattern_kernel(const uint16_t* __restrict__ pid, int W, const int32_t* __re
   __shared__ double sred[kWarps];
   const int nblocks = (nrows + kThreads - 1) / kThreads;
   double ss = 0.0;
+  int pn = 0;
+  if (PF) {
+    const int row = blockIdx.x * kThreads + threadIdx.x;
+    if (row < nrows) pn = (int)__ldcs(pid + row);
+  }
   for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
     const int row = blk * kThreads + threadIdx.x;
+    int p = pn;
+    if (!PF && row < nrows) p = (int)__ldcs(pid + row);
+    if (PF) {
+      const int nrow = row + (int)gridDim.x * kThreads;             // nrows + grid * 256 < 2^31 (checked by the launcher)
+      pn = (blk + (int)gridDim.x < nblocks && nrow < nrows) ? (int)__ldcs(pid + nrow) : 0;
+    }
     if (row < nrows) {
-      const int p = (int)__ldcs(pid + row);
       double bv = 0.0;
       if (MODE != 0) bv = __ldg(b + row);
-      const int4* to = reinterpret_cast<const int4*>(tab_off + p * W);
-      const double2* tv = reinterpret_cast<const double2*>(tab_val + p * W);
-      double acc0 = 0.0, acc1 = 0.0;
-      const int nch = NCH > 0 ? NCH : W / 4;
-#pragma unroll
-      for (int c = 0; c < nch; ++c) {
-        const int4 o = __ldg(to + c);
-        const double2 va = __ldg(tv + 2 * c), vb = __ldg(tv + 2 * c + 1);
-        const double x0 = __ldg(x + (row + o.x)), x1 = __ldg(x + (row + o.y));
-        const double x2 = __ldg(x + (row + o.z)), x3 = __ldg(x + (row + o.w));
-        acc0 = fma(va.x, x0, acc0); acc1 = fma(va.y, x1, acc1);
-        acc0 = fma(vb.x, x2, acc0); acc1 = fma(vb.y, x3, acc1);
-      }
-      const double ax = acc0 + acc1;
+      const double ax = pattern_row<NCH>(p, row, W, tab_off, tab_val, x);
       if (MODE == 0) {
         y[row] = ax;
       } else if (MODE == 1) {
@@ -1113,6 +1134,14 @@ spmv_pattern_kernel(const uint16_t* __restrict__ pid, int W, const int32_t* __re
     partial[blockIdx.x] = t;
   }
 }
+
+// Measured and dropped (profiles/ncu_spmv_r1.md): ncu shows this kernel bound by the L1 data pipe (l1tex data-pipe
+// wavefronts at 80 % of peak, DRAM at 36 %): per warp and row, 24 of its 47 wavefronts are the six LDG.128 of the
+// stencil (a 128-bit load writes 512 bytes back to the register file even when all lanes read one address).  Two
+// ways around that were built and timed on the lkdv operator: the table passed by value and read with indexed
+// constant loads (LDC c[0][R]: 80 us, the indexed form is slow), and the stencil cached in registers across rounds
+// (86 us: 24 more registers halve the rows in flight and the kernel becomes latency bound).  Both lost to this
+// kernel with the id prefetch (61 us; 65 without), so they are not kept.
 
 // out[0] = sum of partial[0..nparts) in a fixed order (one CTA), then the cross-GPU part
 __global__ void __launch_bounds__(kThreads)
@@ -1204,8 +1233,9 @@ __global__ void dict_encode_kernel(const double* __restrict__ vals, const int64_
   }
 }
 
+// (ptxas: the reducing modes need 40 registers; at 32 they spilled 60 bytes and ran 261 instead of 210 us on swe)
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 8)
+__global__ void __launch_bounds__(kThreads, MODE == 0 ? 8 : 6)
 spmv_selld_kernel(const int64_t* __restrict__ slice_off, const int64_t* __restrict__ code_off,
                   const int32_t* __restrict__ cols, const uint32_t* __restrict__ codes,
                   const double* __restrict__ table, int64_t nrows,
@@ -1268,6 +1298,267 @@ spmv_selld_kernel(const int64_t* __restrict__ slice_off, const int64_t* __restri
     for (int wv = 0; wv < kWarps; ++wv) t += sred[wv];
     partial[blockIdx.x] = t;          // reduce_partials_kernel finishes (keeps this kernel at 32 registers)
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1, SELL-32 / SELLD, software-pipelined.  spmv_sell_kernel / spmv_selld_kernel walk a slice as a chain of
+// dependent loads -- slice offset -> columns + values -> x[column] -- once per chunk of four entries, and a
+// warp has nothing else in flight while it waits: with 64 warps per SM they ran at 4.4 (SELLD) / 5.2 (SELL)
+// TB/s.  Here the loads of the NEXT chunk (of this slice, or chunk 0 of the warp's next slice) are issued
+// before the gathers of the current one, and the offsets of the slice after next are fetched a whole slice
+// ahead, so the streaming loads, the gathers and the offset lookups of a warp overlap.
+// Summation order per row is that of spmv_sell_kernel (full chunks: even/odd positions into two
+// accumulators; a trailing partial chunk into the first one), so all SELL kernels give the same bits.
+// ------------------------------------------------------------------------------------------
+template <bool CODED> struct SellChunk;
+template <> struct SellChunk<false> { int32_t c[4]; double v[4]; };
+template <> struct SellChunk<true> { int32_t c[4]; uint32_t q; };
+
+template <bool CODED>
+__device__ __forceinline__ void sell_issue(SellChunk<CODED>& ch, const int32_t* __restrict__ cols,
+                                           const double* __restrict__ vals, const uint32_t* __restrict__ codes,
+                                           int64_t off, int64_t coff, int k, int width, int lane) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const bool ok = k + u < width;
+    ch.c[u] = ok ? __ldcs(cols + off + (int64_t)(k + u) * 32 + lane) : 0;
+    if constexpr (!CODED) ch.v[u] = ok ? __ldcs(vals + off + (int64_t)(k + u) * 32 + lane) : 0.0;
+  }
+  if constexpr (CODED) ch.q = k < width ? __ldcs(codes + coff + (int64_t)(k >> 2) * 32 + lane) : 0u;
+}
+
+template <int MODE, bool CODED>
+__global__ void __launch_bounds__(kThreads, 4)
+spmv_sellp_kernel(const int64_t* __restrict__ slice_off, const int64_t* __restrict__ code_off,
+                  const int32_t* __restrict__ cols, const double* __restrict__ vals,
+                  const uint32_t* __restrict__ codes, const double* __restrict__ table, int64_t nrows,
+                  const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ y,
+                  double* __restrict__ partial) {
+  __shared__ double sdict[CODED ? 256 : 1];
+  __shared__ double sred[kWarps];
+  if constexpr (CODED) {
+    sdict[threadIdx.x] = __ldg(table + threadIdx.x);
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t nslices = (nrows + 31) >> 5;
+  const int64_t sstride = (int64_t)gridDim.x * kWarps;
+  double ss = 0.0;
+  int64_t sA = (int64_t)blockIdx.x * kWarps + warp;
+  if (sA < nslices) {
+    int64_t offA = __ldg(slice_off + sA), coA = 0, offB = 0, coB = 0;
+    int widthA = (int)((__ldg(slice_off + sA + 1) - offA) >> 5), widthB = 0;
+    if constexpr (CODED) coA = __ldg(code_off + sA);
+    int64_t sB = sA + sstride;
+    bool haveB = sB < nslices;
+    if (haveB) {
+      offB = __ldg(slice_off + sB);
+      widthB = (int)((__ldg(slice_off + sB + 1) - offB) >> 5);
+      if constexpr (CODED) coB = __ldg(code_off + sB);
+    }
+    SellChunk<CODED> nx;
+    sell_issue<CODED>(nx, cols, vals, codes, offA, coA, 0, widthA, lane);
+    for (;;) {
+      const int64_t row = (sA << 5) + lane;
+      double bv = 0.0;
+      if (MODE != 0 && row < nrows) bv = __ldg(b + row);
+      double acc0 = 0.0, acc1 = 0.0;
+      if (widthA == 0 && haveB) sell_issue<CODED>(nx, cols, vals, codes, offB, coB, 0, widthB, lane);
+      for (int k = 0; k < widthA; k += 4) {
+        const SellChunk<CODED> cur = nx;
+        if (k + 4 < widthA) sell_issue<CODED>(nx, cols, vals, codes, offA, coA, k + 4, widthA, lane);
+        else if (haveB) sell_issue<CODED>(nx, cols, vals, codes, offB, coB, 0, widthB, lane);
+        double v0, v1, v2, v3;
+        if constexpr (CODED) {
+          v0 = sdict[cur.q & 255u]; v1 = sdict[(cur.q >> 8) & 255u]; v2 = sdict[(cur.q >> 16) & 255u]; v3 = sdict[cur.q >> 24];
+        } else {
+          v0 = cur.v[0]; v1 = cur.v[1]; v2 = cur.v[2]; v3 = cur.v[3];
+        }
+        const int rem = widthA - k;
+        if (rem >= 4) {
+          const double x0 = __ldg(x + cur.c[0]), x1 = __ldg(x + cur.c[1]), x2 = __ldg(x + cur.c[2]), x3 = __ldg(x + cur.c[3]);
+          acc0 = fma(v0, x0, acc0); acc1 = fma(v1, x1, acc1);
+          acc0 = fma(v2, x2, acc0); acc1 = fma(v3, x3, acc1);
+        } else {
+          acc0 = fma(v0, __ldg(x + cur.c[0]), acc0);
+          if (rem > 1) acc0 = fma(v1, __ldg(x + cur.c[1]), acc0);
+          if (rem > 2) acc0 = fma(v2, __ldg(x + cur.c[2]), acc0);
+        }
+      }
+      const double ax = acc0 + acc1;
+      if (row < nrows) {
+        if (MODE == 0) {
+          y[row] = ax;
+        } else if (MODE == 1) {
+          const double r = bv - ax;
+          y[row] = r;
+          ss = fma(r, r, ss);
+        } else {
+          const double r = ax - bv;
+          ss = fma(r, r, ss);
+        }
+      }
+      if (!haveB) break;
+      sA = sB; offA = offB; coA = coB; widthA = widthB;
+      sB += sstride;
+      haveB = sB < nslices;
+      if (haveB) {
+        offB = __ldg(slice_off + sB);
+        widthB = (int)((__ldg(slice_off + sB + 1) - offB) >> 5);
+        if constexpr (CODED) coB = __ldg(code_off + sB);
+      }
+    }
+  }
+  if (MODE == 0) return;
+  ss = warp_sum(ss);
+  if (lane == 0) sred[warp] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int wv = 0; wv < kWarps; ++wv) t += sred[wv];
+    partial[blockIdx.x] = t;          // reduce_partials_kernel finishes
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1 x 2: the two SpMVs of a Krylov iteration in ONE pass over the matrix.
+//     y1 = A x1                      the next Arnoldi vector            (solvers.py:191)
+//     sumsq = ||A x2 - b||^2         the true residual of the iterate   (solvers.py:290)
+// Once the iterate x_j and the basis vector q_{j+2} exist (both leave the same lincomb2 sweep) the two products
+// are independent, and everything that is per matrix entry -- column index, value or value code, dictionary
+// look-up, stencil -- is fetched once for both.  ncu showed the single-vector kernels bound by the L1 data pipe,
+// where those shared fetches are a third (row patterns: a half) of the wavefronts; for SELL/SELLD the matrix is
+// also streamed from HBM once instead of twice.  Per-row summation order is that of the single-vector kernels
+// (same bits for y1; the norm differs from the MODE 2 kernels only in the grouping of per-CTA partial sums).
+// Each CTA leaves one partial sum; reduce_partials_kernel finishes (and carries the cross-GPU part).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cta_partial_sum(double ss, double* sred, double* __restrict__ partial) {
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int wv = 0; wv < kWarps; ++wv) t += sred[wv];
+    partial[blockIdx.x] = t;
+  }
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(kThreads, 6)
+spmv_pattern_dual_kernel(const uint16_t* __restrict__ pid, int W, const int32_t* __restrict__ tab_off,
+                         const double* __restrict__ tab_val, int nrows,
+                         const double* __restrict__ x1, double* __restrict__ y1,
+                         const double* __restrict__ x2, const double* __restrict__ b,
+                         double* __restrict__ partial) {
+  __shared__ double sred[kWarps];
+  const int nblocks = (nrows + kThreads - 1) / kThreads;
+  double ss = 0.0;
+  int pn = 0;
+  {
+    const int row = blockIdx.x * kThreads + threadIdx.x;
+    if (row < nrows) pn = (int)__ldcs(pid + row);
+  }
+  for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    const int row = blk * kThreads + threadIdx.x;
+    const int p = pn;
+    const int nrow = row + (int)gridDim.x * kThreads;
+    pn = (blk + (int)gridDim.x < nblocks && nrow < nrows) ? (int)__ldcs(pid + nrow) : 0;
+    if (row < nrows) {
+      const double bv = __ldg(b + row);
+      const int4* to = reinterpret_cast<const int4*>(tab_off + p * W);
+      const double2* tv = reinterpret_cast<const double2*>(tab_val + p * W);
+      double a0 = 0.0, a1 = 0.0, r0 = 0.0, r1 = 0.0;
+      const int nch = NCH > 0 ? NCH : W / 4;
+#pragma unroll
+      for (int c = 0; c < nch; ++c) {
+        const int4 o = __ldg(to + c);
+        const double2 va = __ldg(tv + 2 * c), vb = __ldg(tv + 2 * c + 1);
+        const double u0 = __ldg(x1 + (row + o.x)), u1 = __ldg(x1 + (row + o.y));
+        const double u2 = __ldg(x1 + (row + o.z)), u3 = __ldg(x1 + (row + o.w));
+        const double w0 = __ldg(x2 + (row + o.x)), w1 = __ldg(x2 + (row + o.y));
+        const double w2 = __ldg(x2 + (row + o.z)), w3 = __ldg(x2 + (row + o.w));
+        a0 = fma(va.x, u0, a0); a1 = fma(va.y, u1, a1);
+        a0 = fma(vb.x, u2, a0); a1 = fma(vb.y, u3, a1);
+        r0 = fma(va.x, w0, r0); r1 = fma(va.y, w1, r1);
+        r0 = fma(vb.x, w2, r0); r1 = fma(vb.y, w3, r1);
+      }
+      y1[row] = a0 + a1;
+      const double r = (r0 + r1) - bv;
+      ss = fma(r, r, ss);
+    }
+  }
+  cta_partial_sum(ss, sred, partial);
+}
+
+// SELL-32 (CODED = false: 8-byte values) and SELLD (CODED = true: 8-bit codes + dictionary in shared memory)
+template <bool CODED>
+__global__ void __launch_bounds__(kThreads, CODED ? 5 : 4)
+spmv_sell_dual_kernel(const int64_t* __restrict__ slice_off, const int64_t* __restrict__ code_off,
+                      const int32_t* __restrict__ cols, const double* __restrict__ vals,
+                      const uint32_t* __restrict__ codes, const double* __restrict__ table, int64_t nrows,
+                      const double* __restrict__ x1, double* __restrict__ y1,
+                      const double* __restrict__ x2, const double* __restrict__ b,
+                      double* __restrict__ partial) {
+  __shared__ double sdict[CODED ? 256 : 1];
+  __shared__ double sred[kWarps];
+  if constexpr (CODED) {
+    sdict[threadIdx.x] = __ldg(table + threadIdx.x);
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t nslices = (nrows + 31) >> 5;
+  const int64_t nblocks = (nslices + kWarps - 1) / kWarps;
+  double ss = 0.0;
+  for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    const int64_t slice = blk * kWarps + warp;
+    if (slice < nslices) {
+      const int64_t off = __ldg(slice_off + slice);
+      const int width = (int)((__ldg(slice_off + slice + 1) - off) >> 5);
+      const int32_t* c = cols + off + lane;
+      const double* v = CODED ? nullptr : vals + off + lane;
+      const uint32_t* q = CODED ? codes + __ldg(code_off + slice) + lane : nullptr;
+      const int64_t row = (slice << 5) + lane;
+      double bv = 0.0;
+      if (row < nrows) bv = __ldg(b + row);
+      double a0 = 0.0, a1 = 0.0, r0 = 0.0, r1 = 0.0;
+      int k = 0;
+      for (; k + 4 <= width; k += 4) {
+        const int32_t c0 = __ldcs(c + (k + 0) * 32), c1 = __ldcs(c + (k + 1) * 32);
+        const int32_t c2 = __ldcs(c + (k + 2) * 32), c3 = __ldcs(c + (k + 3) * 32);
+        double v0, v1, v2, v3;
+        if constexpr (CODED) {
+          const uint32_t w = __ldcs(q + (k >> 2) * 32);
+          v0 = sdict[w & 255u]; v1 = sdict[(w >> 8) & 255u]; v2 = sdict[(w >> 16) & 255u]; v3 = sdict[w >> 24];
+        } else {
+          v0 = __ldcs(v + (k + 0) * 32); v1 = __ldcs(v + (k + 1) * 32);
+          v2 = __ldcs(v + (k + 2) * 32); v3 = __ldcs(v + (k + 3) * 32);
+        }
+        const double u0 = __ldg(x1 + c0), u1 = __ldg(x1 + c1), u2 = __ldg(x1 + c2), u3 = __ldg(x1 + c3);
+        const double w0 = __ldg(x2 + c0), w1 = __ldg(x2 + c1), w2 = __ldg(x2 + c2), w3 = __ldg(x2 + c3);
+        a0 = fma(v0, u0, a0); a1 = fma(v1, u1, a1); a0 = fma(v2, u2, a0); a1 = fma(v3, u3, a1);
+        r0 = fma(v0, w0, r0); r1 = fma(v1, w1, r1); r0 = fma(v2, w2, r0); r1 = fma(v3, w3, r1);
+      }
+      if (k < width) {
+        uint32_t w = 0u;
+        if constexpr (CODED) w = __ldcs(q + (k >> 2) * 32);
+        for (; k < width; ++k, w >>= 8) {
+          const int32_t ck = __ldcs(c + k * 32);
+          double vk;
+          if constexpr (CODED) vk = sdict[w & 255u]; else vk = __ldcs(v + k * 32);
+          a0 = fma(vk, __ldg(x1 + ck), a0);
+          r0 = fma(vk, __ldg(x2 + ck), r0);
+        }
+      }
+      if (row < nrows) {
+        y1[row] = a0 + a1;
+        const double r = (r0 + r1) - bv;
+        ss = fma(r, r, ss);
+      }
+    }
+  }
+  cta_partial_sum(ss, sred, partial);
 }
 
 // K1 fallback: CSR "vector" kernel, T lanes per row (T = 2..32), for matrices whose row

@@ -137,6 +137,10 @@ class KrylovContext:
     def arnoldi_begin(self, j: int):
         self._check(self._lib.spis_arnoldi_begin(self._h, j))
 
+    def arnoldi_begin_residual(self, j: int):
+        """arnoldi_begin(j) whose SpMV also measures ||A x - b|| of the iterate in X (iterate_residual_wait collects it)."""
+        self._check(self._lib.spis_arnoldi_begin_residual(self._h, j))
+
     def arnoldi_finish(self, j: int, y_iterate=None):
         if y_iterate is None:
             self._check(self._lib.spis_arnoldi_finish(self._h, j, 0, None))

@@ -52,6 +52,7 @@ _CONFIG = {
     "spmv_format": "auto",
     "profile": False,
     "async_setup": True,
+    "dual_spmv": True,
 }
 _ORTH = {"cgs2": nat.ORTH_CGS2, "cgs1": nat.ORTH_CGS1, "mgs": nat.ORTH_MGS}
 _FMT = {"auto": nat.FMT_AUTO, "sell": nat.FMT_SELL, "csr": nat.FMT_CSR, "sell2": nat.FMT_SELL2, "pattern": nat.FMT_PATTERN, "selld": nat.FMT_SELLD}
@@ -450,6 +451,9 @@ class _Arnoldi:
         self._begun = None                    # step with only its first half queued (fused-iterate mode)
         self._have = -1
         self._fuse = self.lookahead and sess.can_fuse_iterate
+        # residual of iterate j measured by the SpMV of Arnoldi step j+2 (one pass over A for both products)
+        self._dual = self._fuse and hasattr(sess.ctx, "arnoldi_begin_residual") and _opt("dual_spmv", None)
+        self._ls_prev = None                  # unconstrained least-squares residual one column earlier
         # Givens recurrence of the unconstrained least-squares residual |beta e1 - H y|_min: used only
         # to decide whether launching the NEXT Arnoldi step ahead of time can be wasted work
         self._cs = np.zeros(k)
@@ -472,6 +476,7 @@ class _Arnoldi:
     def _store(self, j, col):
         self._have = j
         self.H[: j + 2, j] = col
+        self._ls_prev = self._g if self._g is None else abs(self._g)
         if self._g is not None:
             r = np.array(col, dtype=np.float64)
             for i in range(j):
@@ -492,11 +497,20 @@ class _Arnoldi:
         ctx = self.sess.ctx
         if not (self.lookahead and hasattr(ctx, "iterate_residual_launch")):
             return ctx.iterate_residual(yk)
+        rides = False
         if self._begun == j + 1:
             # the last projection of step j+1 sweeps the same basis rows the iterate needs: one pass for both
             ctx.arnoldi_finish(j + 1, yk)
             self._begun, self._inflight = None, j + 1
-            ctx.residual_launch()
+            # x_j and q_{j+2} now exist: if step j+2 is going to run anyway, its SpMV measures ||A x_j - b|| on
+            # the way (one pass over A for both).  Column j+1 is not known yet, so "going to run" is a guess
+            # from the convergence rate; a wrong guess costs what a wasted lookahead always cost, half a step.
+            rides = bool(self._dual) and not may_end and j + 2 < self.k and self._next_step_expected(tol)
+            if rides:
+                ctx.arnoldi_begin_residual(j + 2)
+                self._begun = j + 2
+            else:
+                ctx.residual_launch()
         else:
             ctx.iterate_residual_launch(yk)
         if self._inflight == j + 1:
@@ -506,9 +520,18 @@ class _Arnoldi:
             # step j+2 is only useful if neither this iteration nor the next one ends the loop; the next
             # one can only end if even its unconstrained minimiser is below tol (known now, from column j+1)
             next_may_end = tol is not None and self.ls_residual() < tol
-            if not may_end and not next_may_end and col[j + 2] != 0 and j + 2 < self.k:
+            if not rides and not may_end and not next_may_end and col[j + 2] != 0 and j + 2 < self.k:
                 self._queue(j + 2)
         return ctx.iterate_residual_wait()
+
+    def _next_step_expected(self, tol):
+        """Will the iteration after this one need another Arnoldi step?  Extrapolates the unconstrained
+        least-squares residual by its last reduction factor (solvers that never stop early pass tol=None)."""
+        if tol is None or self._g is None:
+            return True
+        ls = abs(self._g)
+        rate = 1.0 if not self._ls_prev else min(1.0, ls / self._ls_prev)
+        return ls * rate * rate >= tol
 
     def ls_residual(self):
         """min_y |beta e1 - H_j y| after the last column() (inf when not tracked)."""

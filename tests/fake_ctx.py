@@ -132,8 +132,15 @@ class FakeKrylovContext:
         self.log.append(("begin",))
         return float(beta)
 
+    def arnoldi_begin_residual(self, j):
+        """Residual of the iterate in X measured by the SpMV of Arnoldi step j (one pass over A for both)."""
+        r = self._spmv(nat.SLOT_A, self.Xfull) - self.vecs[nat.VEC_B]
+        self._resid = float(np.sqrt(self._ar(r @ r)[0]))
+        self.log.append(("residual_rides", j))
+        self.arnoldi_begin(j)
+
     def arnoldi_begin(self, j):
-        assert self._pending is None and getattr(self, "_begun", None) is None
+        assert getattr(self, "_begun", None) is None       # (a finished step may still be waiting to be collected)
         self.log.append(("begin_step", j))
         m = j + 1
         n = self.n
@@ -158,7 +165,7 @@ class FakeKrylovContext:
 
     def arnoldi_finish(self, j, y_iterate=None):
         bj, h, h2, w = self._begun
-        assert bj == j
+        assert bj == j and self._pending is None
         self._begun = None
         n = self.n
         if y_iterate is not None:                      # the iterate of the previous step rides on the last sweep

@@ -139,6 +139,86 @@ def test_spmv_fem_operators(fmt):
         assert np.max(np.abs(y1 - A @ x) / scale) <= 1e-14
 
 
+@pytest.mark.parametrize("fmt", [nat.FMT_SELL, nat.FMT_SELLD, nat.FMT_PATTERN, nat.FMT_CSR])
+def test_spmv_dual_matches_the_two_separate_products(fmt):
+    """spis_arnoldi_begin_residual: w = A q_1 and ||A x - b|| from ONE pass over A.  Same Hessenberg column bits as
+    the separate SpMV (same per-row summation order), the norm to rounding (per-CTA partial sums grouped differently);
+    formats without a dual kernel (CSR) take two launches behind the same entry point."""
+    from structurepreservingiterativesolvers_b200.problems import swe
+    rng = np.random.default_rng(23)
+    A = (swe.linforms(M=40, mlength=32.0)[0]["A"] if fmt in (nat.FMT_SELLD, nat.FMT_CSR)
+         else lkdv.linforms(space="CG", M=33_350, mlength=0.8 * 33_350)[0]["A"])
+    n = A.shape[0]
+    b, x0, y = rng.standard_normal(n), rng.standard_normal(n), np.array([0.37])
+    out = []
+    for dual in (1, 0):
+        with KrylovContext(n, 4) as ctx:
+            ctx.set_option("spmv_format", fmt)
+            ctx.set_option("spmv_dual", dual)
+            ctx.upload_matrix(nat.SLOT_A, A)
+            ctx.upload_vec(nat.VEC_B, b)
+            ctx.upload_vec(nat.VEC_X0, x0)
+            beta = ctx.solve_begin()
+            col0 = ctx.arnoldi_step(0)
+            ctx.form_iterate(y)                                   # X = x0 + y[0] q_0
+            x = ctx.download(nat.VEC_X)
+            ctx.arnoldi_begin_residual(1)
+            res = ctx.iterate_residual_wait()
+            ctx.arnoldi_finish(1)
+            col1 = ctx.arnoldi_wait(1)
+            out.append((beta, col0, x, res, col1))
+    ref = np.linalg.norm(A @ out[0][2] - b)
+    for k in (0, 1):
+        assert abs(out[k][3] - ref) <= 1e-13 * ref
+    np.testing.assert_array_equal(out[0][2], out[1][2])
+    np.testing.assert_array_equal(out[0][4], out[1][4])
+
+
+def _modes_through_abi(ctx, A, b, x0):
+    """(A x0 via mode 0, ||b - A x0|| via mode 1, ||A x0 - b|| via mode 2) of whatever kernel the context picks."""
+    ctx.upload_vec(nat.VEC_B, b)
+    ctx.upload_vec(nat.VEC_X0, x0)
+    y = ctx.op_spmv(nat.SLOT_A, x0)
+    beta = ctx.solve_begin()
+    res = ctx.iterate_residual(np.zeros(0))
+    return y, beta, res
+
+
+@pytest.mark.parametrize("fmt", [nat.FMT_SELL, nat.FMT_SELLD, nat.FMT_PATTERN])
+def test_spmv_kernel_generations_agree(fmt):
+    """spmv_variant 0 (first-generation kernels) and 1 (id prefetch for row patterns, software-pipelined
+    slices for SELL) walk every row in the same order: same bits in mode 0; the fused norms of modes 1 and 2
+    differ only in how the per-CTA partial sums are grouped."""
+    from structurepreservingiterativesolvers_b200.problems import swe
+    rng = np.random.default_rng(17)
+    mats = []
+    if fmt != nat.FMT_PATTERN:
+        mats.append(swe.linforms(M=40, mlength=32.0)[0]["A"])                     # widths 16 / 9, <= 256 distinct values
+        R = ragged_matrix(4097, seed=3)
+        R.data[:] = rng.integers(-5, 6, size=R.nnz).astype(np.float64)           # few distinct values: SELLD applies
+        mats.append(R)
+        E = sps.csr_matrix((3000, 3000)); E = E.tolil(); E[5, 7] = 2.0; E[2999, 0] = -1.0   # slices that are entirely empty
+        mats.append(E.tocsr())
+    mats.append(lkdv.linforms(space="CG", M=33_350, mlength=0.8 * 33_350)[0]["A"])
+    mats.append(lkdv.linforms(space="DG", M=500)[0]["A"])
+    for A in mats:
+        n = A.shape[0]
+        b, x0 = rng.standard_normal(n), rng.standard_normal(n)
+        out = []
+        for var in (0, 1):
+            with KrylovContext(n, 2) as ctx:
+                ctx.set_option("spmv_format", fmt)
+                ctx.set_option("spmv_variant", var)
+                ctx.upload_matrix(nat.SLOT_A, A)
+                assert ctx.info(f"fmt:{nat.SLOT_A}") == fmt
+                out.append(_modes_through_abi(ctx, A, b, x0))
+        ref = np.linalg.norm(b - A @ x0)
+        for y, beta, res in out:
+            np.testing.assert_array_equal(y, out[0][0])
+            assert abs(beta - ref) <= 1e-13 * ref and abs(res - ref) <= 1e-13 * ref
+
+
+
 @pytest.mark.parametrize("n", [2, 1023, 1024, 1025, 2049, 300_007])
 @pytest.mark.parametrize("m", [0, 1, 3, 4, 5, 21])
 def test_mdot(n, m):

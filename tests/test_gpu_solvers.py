@@ -107,22 +107,33 @@ def test_fused_iterate_is_bit_identical_to_separate_passes():
     x0 = 0.01 * np.cos(np.arange(dic["b"].size))                   # non-zero x0: the base vector of the iterate
     cl = wrappers.lkdv.conlist(dic, x0)
     out = []
-    for fuse in (1, 0):
+    for fuse, dual in ((1, False), (0, False), (1, True)):
         sess = solvers.DeviceSession(dic["A"], dic["b"], x0, 50, conlist=cl, profile=True)
         sess.ctx.set_option("fuse_iterate", fuse)
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            x, info = solvers.cgmres(dic["A"], dic["b"], x0, 50, tol=1e-8, conlist=cl, session=sess, small_solver="kkt")
+            solvers.configure(dual_spmv=dual)
+            try:
+                x, info = solvers.cgmres(dic["A"], dic["b"], x0, 50, tol=1e-8, conlist=cl, session=sess, small_solver="kkt")
+            finally:
+                solvers.configure(dual_spmv=True)
         prof = sess.ctx.profile()
         out.append((x, info["steps"], np.array(info["res"]), [np.array(info["x"][j]) for j in (1, 5, info["steps"])],
-                    prof["lincomb"]["launches"]))
+                    prof["lincomb"]["launches"], prof["spmv"]["launches"]))
         sess.close()
-    assert out[0][1] == out[1][1]
+    assert out[0][1] == out[1][1] == out[2][1]
     np.testing.assert_array_equal(out[0][0], out[1][0])
     np.testing.assert_array_equal(out[0][2], out[1][2])
     for a, b in zip(out[0][3], out[1][3]):
         np.testing.assert_array_equal(a, b)
     assert out[0][4] < out[1][4]                                    # fewer sweeps over the basis
+    # dual SpMV (A q_{j+2} and ||A x_j - b|| from one pass over A): same rows, same order -> the same Hessenberg
+    # matrix, hence the same iterates; the residual norms differ only in how per-CTA partial sums are grouped
+    np.testing.assert_array_equal(out[0][0], out[2][0])
+    for a, b in zip(out[0][3], out[2][3]):
+        np.testing.assert_array_equal(a, b)
+    np.testing.assert_allclose(out[2][2], out[0][2], rtol=1e-12, atol=0)
+    assert out[2][5] < out[0][5]                                    # fewer passes over the matrix
 
 
 def test_session_reuse_and_profile():

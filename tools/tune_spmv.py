@@ -21,11 +21,21 @@ for wl in (sys.argv[1:] or ["lkdv", "swe"]):
                 print(name, 'not applicable:', exc, flush=True)
                 continue
             print(name, 'npat', ctx.info('npat:0'), flush=True)
-            for ctas in ((4, 8) if name != 'pattern' else (4, 5, 8, 10)):
+            # (variant, spmv_ctas_per_sm, spmv_pipe_ctas_per_sm); variant 0 = first-generation kernels
+            if name == 'pattern':
+                sweeps = [(0, 8, 0), (1, 8, 0)]
+            elif name == 'sell':
+                sweeps = [(0, 8, 0), (1, 8, 4)]
+            else:
+                sweeps = [(0, 8, 0), (0, 6, 0)]
+            print(name, 'ndict', ctx.info('ndict:0'), flush=True)
+            for var, ctas, pipe in sweeps:
+                ctx.set_option("spmv_variant", var)
                 ctx.set_option("spmv_ctas_per_sm", ctas)
+                ctx.set_option("spmv_pipe_ctas_per_sm", pipe)
                 for mode in (0, 2):
                     ms, by = ctx.bench_kernel(nat.PROF_SPMV, mode, reps=20)
-                    rows.append(dict(workload=wl, fmt=name, ctas=ctas, mode=mode, us=ms * 1e3, gbs=by / ms * 1e-6,
+                    rows.append(dict(workload=wl, fmt=name, variant=var, ctas=ctas, pipe=pipe, mode=mode, us=ms * 1e3, gbs=by / ms * 1e-6,
                                      nnz_padded=ctx.info("nnz_padded:0")))
                     print(json.dumps(rows[-1]), flush=True)
 json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "tune_spmv.json"), "w"), indent=1)
