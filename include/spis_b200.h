@@ -183,6 +183,16 @@ int spis_constraint_define(spis_ctx* ctx, int c, int mat_slot, const double* v, 
 /* term0 (scalar), term1 (m), term2 (m x m row-major) for Z = z[:m].T, incremental in m:
  * MZ = M@Z (:33), term0 (:34), term1 = v@Z + x0@MZ (:35), term2 = 1/2 Z.T@MZ (:36)      */
 int spis_constraint_terms(spis_ctx* ctx, int c, int m, double* term0, double* term1, double* term2);
+/* Class-form constraint c staged by a native helper thread on the auxiliary stream while the caller runs the
+ * Krylov loop: zero test of M's values (-> mat_slot < 0), spis_upload_csr into slot SPIS_SLOT_CON0 + c,
+ * spis_constraint_define.  Exception to the pointer rule above: the host arrays must stay valid until
+ * spis_constraint_setup_wait returns (it joins all helpers and reports the first failure); call it before the
+ * first spis_constraint_terms.  The constraint data is first needed at the first constrained step
+ * (solvers.py:242-247), many iterations after the solve has started.                                        */
+int spis_constraint_setup_async(spis_ctx* ctx, int c, int64_t nrows, int64_t ncols, int64_t nnz,
+                                const int32_t* indptr, const int32_t* indices, const double* data,
+                                const double* v, double cc);
+int spis_constraint_setup_wait(spis_ctx* ctx);
 
 /* ---- downloads / host bridges ------------------------------------------------------- */
 int spis_download_vec(spis_ctx* ctx, int which, int j, double* host, int64_t n);

@@ -58,6 +58,7 @@ struct Constraint {
 };
 
 struct ProfRec { int cls; double bytes; cudaEvent_t e0, e1; };
+struct AsyncJob { std::thread th; int rc = 0; std::string err; };   // spis_constraint_setup_async
 struct DevBlock { void* p; size_t bytes; int device; };
 
 }  // namespace
@@ -81,6 +82,7 @@ struct spis_ctx {
   int spmv_ctas_per_sm = 8;
   int spmv_variant = 1;         // 0: first-generation SpMV kernels; 1+: prefetching / software-pipelined ones (see launch_spmv_mode)
   int spmv_pipe_ctas_per_sm = 0;   // 0 = the kernel's own default
+  int pinned_scan_dma = 0;      // spis_any_nonzero on page-locked memory: 1 = copy engine + kernel, 0 = host threads
   int spmv_dual = 1;            // A q_{j+2} and ||A x_j - b|| from one pass over A (spis_arnoldi_begin_residual)
   int spmv_dual_ctas_per_sm = 0;
   int mdot_variant = 0, lincomb_variant = 4;   // mdot 0 = auto (tools/tune.py sweep, profiles/tune_r1.md)
@@ -135,6 +137,7 @@ struct spis_ctx {
   // profiling
   std::vector<ProfRec> recs; std::vector<cudaEvent_t> evpool;
   std::vector<DevBlock> owned;   // device blocks currently held by this context
+  std::vector<AsyncJob*> jobs;   // native helper threads staging constraint data (joined by spis_constraint_setup_wait)
   double prof_ms[SPIS_PROF_CLASSES] = {0}; double prof_bytes[SPIS_PROF_CLASSES] = {0}; int64_t prof_launch[SPIS_PROF_CLASSES] = {0};
   char err[512] = "";
 };
@@ -709,6 +712,19 @@ int spis_pinned_trim(void) {
 // 8*nnz bytes, which numpy's any() does at ~8 GB/s on one core.
 int spis_host_any_nonzero(const double* p, size_t n, int* out) {
   if (!out || (!p && n)) return SPIS_E_INVALID;
+  {
+    // Data that is not zero almost always says so in its first entries: look at 64 K of them on the calling
+    // thread before paying for a team of threads (which, next to another scan, waited milliseconds for cores).
+    const uint64_t* q0 = reinterpret_cast<const uint64_t*>(p);
+    const size_t probe = n < ((size_t)1 << 16) ? n : ((size_t)1 << 16);
+    uint64_t acc = 0;
+    for (size_t k = 0; k < probe; ++k) acc |= q0[k];
+    if (acc & 0x7fffffffffffffffull) {
+      for (size_t k = 0; k < probe; ++k)
+        if (q0[k] & 0x7fffffffffffffffull) { *out = 1; return SPIS_OK; }
+    }
+    if (probe == n) { *out = 0; return SPIS_OK; }
+  }
   std::atomic<int> found(0);
   auto scan = [&](size_t lo, size_t hi) {
     const uint64_t* q = reinterpret_cast<const uint64_t*>(p);
@@ -728,7 +744,7 @@ int spis_host_any_nonzero(const double* p, size_t n, int* out) {
   if (nt > 16) nt = 16;
   if (tl_use_aux) {                   // helper thread: leave cores to the thread that feeds the GPU
     const char* env = getenv("SPIS_HELPER_SCAN_THREADS");
-    unsigned cap = env ? (unsigned)atoi(env) : (nt > 4 ? nt - 2 : nt);
+    unsigned cap = env ? (unsigned)atoi(env) : (nt > 4 ? nt / 2 : nt);
     if (cap >= 1 && nt > cap) nt = cap;
   }
   if (n < (size_t)1 << 20) nt = 1;
@@ -811,7 +827,10 @@ int spis_any_nonzero(spis_ctx* ctx, const double* p, size_t n, int* out) {
   *out = 0;
   if (n == 0) return SPIS_OK;
   CU(cudaSetDevice(ctx->device));
-  if (n >= ((size_t)1 << 16) && is_pinned_host(p)) return pinned_any_nonzero(ctx, p, n, out);
+  // Page-locked buffers CAN be tested by the copy engine + a kernel (pinned_any_nonzero: no host CPU time), but
+  // measured on the GPU box the host threads scan 480 MB in 1.4-2.5 ms against 9.1 ms through PCIe, and in an
+  // end-to-end solve PCIe is the scarce resource (1.3 GB of operands to upload): option pinned_scan_dma = 0.
+  if (ctx->pinned_scan_dma && n >= ((size_t)1 << 16) && is_pinned_host(p)) return pinned_any_nonzero(ctx, p, n, out);
   return spis_host_any_nonzero(p, n, out);
 }
 
@@ -929,6 +948,7 @@ int spis_ctx_create(int device, int64_t n, int64_t n_halo, int k_max, void* stre
 int spis_ctx_destroy(spis_ctx* ctx) {
   if (!ctx) return SPIS_OK;
   cudaSetDevice(ctx->device);
+  spis_constraint_setup_wait(ctx);
   if (ctx->aux) cudaStreamSynchronize(ctx->aux);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (auto& r : ctx->recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
@@ -977,6 +997,7 @@ int spis_set_option(spis_ctx* ctx, const char* key, int64_t value) {
   else if (k == "spmv_ctas_per_sm") { REQUIRE(value >= 1 && value <= 16, "spmv_ctas_per_sm must be 1..16"); ctx->spmv_ctas_per_sm = (int)value; }
   else if (k == "spmv_variant") { REQUIRE(value >= 0 && value <= 1, "spmv_variant must be 0 or 1"); ctx->spmv_variant = (int)value; }
   else if (k == "spmv_pipe_ctas_per_sm") { REQUIRE(value >= 0 && value <= 16, "spmv_pipe_ctas_per_sm must be 0..16"); ctx->spmv_pipe_ctas_per_sm = (int)value; }
+  else if (k == "pinned_scan_dma") { ctx->pinned_scan_dma = value ? 1 : 0; }
   else if (k == "spmv_dual") { ctx->spmv_dual = value ? 1 : 0; }
   else if (k == "spmv_dual_ctas_per_sm") { REQUIRE(value >= 0 && value <= 16, "spmv_dual_ctas_per_sm must be 0..16"); ctx->spmv_dual_ctas_per_sm = (int)value; }
   else if (k == "mdot_variant") { REQUIRE(value == 0 || value == 2 || value == 4 || value == 8, "mdot_variant must be 0 (auto), 2, 4 or 8"); ctx->mdot_variant = (int)value; }
@@ -1503,6 +1524,56 @@ int spis_constraint_define(spis_ctx* ctx, int c, int mat_slot, const double* v, 
   C.T1.assign((size_t)ctx->kmax, 0.0);
   C.T2.assign((size_t)ctx->kmax * ctx->kmax, 0.0);
   return SPIS_OK;
+}
+
+// The whole staging of one class-form constraint -- is M identically zero (`0*A`, lkdv/LinearSolver.py:30)?
+// upload + conversion of M, zero test and upload of v -- on a NATIVE helper thread and the context's auxiliary
+// stream, so that the caller's thread can drive the Krylov loop meanwhile.  (Python helper threads did this
+// before; every step of theirs had to win the interpreter lock from the thread running the loop, and the
+// staging of a 10 ms job took 15-35 ms now and then, past the first constrained step.)
+// The host arrays must stay valid until spis_constraint_setup_wait returns.
+int spis_constraint_setup_async(spis_ctx* ctx, int c, int64_t nrows, int64_t ncols, int64_t nnz,
+                                const int32_t* indptr, const int32_t* indices, const double* data,
+                                const double* v, double cc) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(c >= 0 && SPIS_SLOT_CON0 + c < SPIS_MAX_SLOTS, "constraint index %d out of range", c);
+  REQUIRE(ctx->aux, "the context has no auxiliary stream");
+  REQUIRE(indptr && (nnz == 0 || (indices && data)), "null CSR arrays");
+  AsyncJob* job = new AsyncJob();
+  ctx->jobs.push_back(job);
+  job->th = std::thread([=]() {
+    PhaseTrace pt;
+    cudaSetDevice(ctx->device);
+    tl_use_aux = true;
+    int nz = 0;
+    int rc = nnz > 0 ? spis_host_any_nonzero(data, (size_t)nnz, &nz) : SPIS_OK;
+    pt.mark(nz ? "constraint: M is not zero" : "constraint: M is zero");
+    int slot = -1;
+    if (rc == SPIS_OK && nz) {
+      slot = SPIS_SLOT_CON0 + c;
+      rc = spis_upload_csr(ctx, slot, nrows, ncols, nnz, indptr, indices, data);
+      pt.mark("constraint: upload M");
+    }
+    if (rc == SPIS_OK) rc = spis_constraint_define(ctx, c, slot, v, cc);
+    if (cudaStreamSynchronize(ctx->aux) != cudaSuccess && rc == SPIS_OK) rc = SPIS_E_CUDA;
+    pt.mark("constraint: v");
+    job->rc = rc;
+    if (rc != SPIS_OK) job->err = ctx->err;
+    tl_use_aux = false;
+  });
+  return SPIS_OK;
+}
+
+int spis_constraint_setup_wait(spis_ctx* ctx) {
+  if (!ctx) return SPIS_E_INVALID;
+  int rc = SPIS_OK;
+  for (AsyncJob* job : ctx->jobs) {
+    if (job->th.joinable()) job->th.join();
+    if (job->rc != SPIS_OK && rc == SPIS_OK) { rc = job->rc; snprintf(ctx->err, sizeof(ctx->err), "%s", job->err.c_str()); }
+    delete job;
+  }
+  ctx->jobs.clear();
+  return rc;
 }
 
 // Is the constraint matrix symmetric?  u^T (M w) == w^T (M u) for two pseudo-random vectors, to

@@ -189,6 +189,26 @@ class KrylovContext:
             vp = nat.dptr(v)
         self._check(self._lib.spis_constraint_define(self._h, c, mat_slot, vp, float(cc)))
 
+    def constraint_setup_async(self, c: int, M, v, cc: float):
+        """Stage class-form constraint c (sparse M, vector v, scalar cc) on a native helper thread; the arrays
+        handed to the library are kept alive here until constraint_setup_wait()."""
+        self._live()
+        M, indptr, indices, data = _csr_arrays(M)
+        if M.shape[0] != self.n:
+            raise ValueError(f"constraint matrix has {M.shape[0]} rows, context owns {self.n}")
+        v = nat.as_f64(v, self.n)
+        self._async_refs = getattr(self, "_async_refs", [])
+        self._async_refs.append((indptr, indices, data, v))
+        self._check(self._lib.spis_constraint_setup_async(self._h, c, M.shape[0], M.shape[1], M.nnz, nat.iptr(indptr),
+                                                          nat.iptr(indices), nat.dptr(data), nat.dptr(v), float(cc)))
+
+    def constraint_setup_wait(self):
+        self._live()
+        try:
+            self._check(self._lib.spis_constraint_setup_wait(self._h))
+        finally:
+            self._async_refs = []
+
     def constraint_terms(self, c: int, m: int):
         t0 = C.c_double(0.0)
         t1 = np.empty(m, dtype=np.float64)

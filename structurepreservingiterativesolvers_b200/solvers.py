@@ -203,14 +203,21 @@ class DeviceSession:
             raise TypeError("A must be a scipy.sparse matrix (or a dense array); got %r" % type(A))
         if A.shape[0] != n or A.shape[1] != n + getattr(ctx, "n_halo", 0):
             raise ValueError(f"A has shape {A.shape}, expected {(n, n + getattr(ctx, 'n_halo', 0))}")
+        # the zero test of x0 (host threads) runs while the calling thread waits for the upload of A
+        x0_scan = {}
+        scanner = threading.Thread(target=lambda: x0_scan.setdefault("nz", nat.any_nonzero(self.x0_host)), daemon=True)
+        scanner.start()
         ctx.upload_matrix(nat.SLOT_A, A)
         tr("upload A")
         ctx.upload_vec(nat.VEC_B, b)
-        x0_nonzero = self._any_rank(nat.any_nonzero(self.x0_host))
+        tr("upload b")
+        scanner.join()
+        x0_nonzero = self._any_rank(x0_scan["nz"] if "nz" in x0_scan else nat.any_nonzero(self.x0_host))
+        tr("x0 zero scan")
         if x0_nonzero:                       # a new context's x0 buffer is already zero on the device
             ctx.upload_vec(nat.VEC_X0, self.x0_host)
         ctx.set_option("x0_is_zero", 0 if x0_nonzero else 1)
-        tr("upload b, x0")
+        tr("upload x0")
         self._host_pre = None
         self._setup_precond(pre)
         tr("preconditioner")
@@ -222,14 +229,30 @@ class DeviceSession:
         # decisions in _any_rank and stay on one thread.)
         self._bg = None
         self._bg_error = None
+        self._native_jobs = False
         conlist = list(conlist)
         if len(conlist) > nat.MAX_SLOTS - nat.SLOT_CON0:
             raise ValueError("too many constraints")
         self._cons = [None] * len(conlist)
         if conlist and _opt("async_setup", async_setup) and type(self) is DeviceSession and hasattr(ctx, "use_aux_stream"):
-            # one helper per constraint: the host scan of one (`0*A`) overlaps the PCIe upload of another
-            self._bg = [threading.Thread(target=self._setup_constraints_bg, args=(idx, const), daemon=True)
-                        for idx, const in enumerate(conlist)]
+            # one helper per constraint: the host scan of one (`0*A`) overlaps the PCIe upload of another.
+            # Class-form constraints with a sparse M go to NATIVE helper threads (one C call each: they never
+            # need the interpreter lock the loop's thread holds); anything else to a Python thread.
+            self._bg = []
+            for idx, const in enumerate(conlist):
+                if (hasattr(ctx, "constraint_setup_async") and _classify_constraint(const) == "class"
+                        and sps.issparse(getattr(const, "M", None))):
+                    entry = {"kind": "class", "const": const, "error": None}
+                    try:
+                        ctx.constraint_setup_async(idx, const.M, const.v, float(const.c))
+                        self._native_jobs = True
+                    except nat.NativeLibraryError:
+                        raise
+                    except Exception as exc:                # surfaces where the reference builds containers
+                        entry["error"] = exc
+                    self._cons[idx] = entry
+                else:
+                    self._bg.append(threading.Thread(target=self._setup_constraints_bg, args=(idx, const), daemon=True))
             for th in self._bg:
                 th.start()
             tr("constraints (handed to helper threads)")
@@ -294,6 +317,9 @@ class DeviceSession:
             for th in self._bg:
                 th.join()
             self._bg = None
+        if self._native_jobs:
+            self._native_jobs = False
+            self.ctx.constraint_setup_wait()
         if self._bg_error is not None:
             exc, self._bg_error = self._bg_error, None
             raise exc

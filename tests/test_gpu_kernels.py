@@ -344,12 +344,14 @@ def test_preconditioner_kernels():
 
 
 def test_any_nonzero_host_and_pinned_paths():
-    """Zero detection of constraint data (`0*A`, lkdv/LinearSolver.py:30): pageable buffers on the host
-    threads, page-locked ones by a kernel reading host memory over PCIe; -0.0 is zero, NaN is not."""
+    """Zero detection of constraint data (`0*A`, lkdv/LinearSolver.py:30): host threads by default (also
+    for page-locked buffers: PCIe is the scarce resource of an end-to-end solve), optionally the copy engine plus a
+    kernel for page-locked ones (pinned_scan_dma); -0.0 is zero, NaN is not."""
     import torch
     n = 300_001
     with KrylovContext(1000, 2) as ctx:
-        for pinned in (False, True):
+        for pinned in (False, True, "dma"):
+            ctx.set_option("pinned_scan_dma", 1 if pinned == "dma" else 0)   # page-locked: host threads (default) or copy engine + kernel
             def buf(a):
                 return torch.from_numpy(a).pin_memory().numpy() if pinned else a
             z = buf(np.zeros(n))
