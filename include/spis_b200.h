@@ -183,6 +183,8 @@ int spis_constraint_define(spis_ctx* ctx, int c, int mat_slot, const double* v, 
 /* term0 (scalar), term1 (m), term2 (m x m row-major) for Z = z[:m].T, incremental in m:
  * MZ = M@Z (:33), term0 (:34), term1 = v@Z + x0@MZ (:35), term2 = 1/2 Z.T@MZ (:36)      */
 int spis_constraint_terms(spis_ctx* ctx, int c, int m, double* term0, double* term1, double* term2);
+/* replaces the scalar of a defined constraint (time loops: same M and v, new invariant values per step) */
+int spis_constraint_set_constant(spis_ctx* ctx, int c, double cc);
 /* Class-form constraint c staged by a native helper thread on the auxiliary stream while the caller runs the
  * Krylov loop: zero test of M's values (-> mat_slot < 0), spis_upload_csr into slot SPIS_SLOT_CON0 + c,
  * spis_constraint_define.  Exception to the pointer rule above: the host arrays must stay valid until

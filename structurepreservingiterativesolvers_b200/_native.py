@@ -69,6 +69,7 @@ SIGNATURES = {
     "spis_constraint_terms": (C.c_int, [_ctx, C.c_int, C.c_int, _dp, _dp, _dp]),
     "spis_constraint_setup_async": (C.c_int, [_ctx, C.c_int, C.c_int64, C.c_int64, C.c_int64, _ip, _ip, _dp, _dp, C.c_double]),
     "spis_constraint_setup_wait": (C.c_int, [_ctx]),
+    "spis_constraint_set_constant": (C.c_int, [_ctx, C.c_int, C.c_double]),
     "spis_download_vec": (C.c_int, [_ctx, C.c_int, C.c_int, _dp, C.c_int64]),
     "spis_download_Z": (C.c_int, [_ctx, C.c_int, C.c_int, _dp]),
     "spis_host_pre_get": (C.c_int, [_ctx, C.c_int, _dp]),

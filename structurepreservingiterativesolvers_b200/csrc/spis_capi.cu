@@ -1526,6 +1526,17 @@ int spis_constraint_define(spis_ctx* ctx, int c, int mat_slot, const double* v, 
   return SPIS_OK;
 }
 
+// New scalar c of a defined constraint (a time loop re-derives the invariants of every step's initial state,
+// lkdv/Evolve.py:41 -> lkdv/lkdv.py:125-127, while M and v stay the same): nothing is uploaded again.
+int spis_constraint_set_constant(spis_ctx* ctx, int c, double cc) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(c >= 0 && c < SPIS_MAX_SLOTS && ctx->cons[c].defined, "constraint %d is not defined", c);
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->cons[c].cc = cc;
+  ctx->cons[c].term0_done = false;
+  return SPIS_OK;
+}
+
 // The whole staging of one class-form constraint -- is M identically zero (`0*A`, lkdv/LinearSolver.py:30)?
 // upload + conversion of M, zero test and upload of v -- on a NATIVE helper thread and the context's auxiliary
 // stream, so that the caller's thread can drive the Krylov loop meanwhile.  (Python helper threads did this

@@ -189,6 +189,10 @@ class KrylovContext:
             vp = nat.dptr(v)
         self._check(self._lib.spis_constraint_define(self._h, c, mat_slot, vp, float(cc)))
 
+    def constraint_set_constant(self, c: int, cc: float):
+        self._live()
+        self._check(self._lib.spis_constraint_set_constant(self._h, c, float(cc)))
+
     def constraint_setup_async(self, c: int, M, v, cc: float):
         """Stage class-form constraint c (sparse M, vector v, scalar cc) on a native helper thread; the arrays
         handed to the library are kept alive here until constraint_setup_wait()."""

@@ -261,6 +261,31 @@ class DeviceSession:
                 self._setup_constraint(idx, const)
             tr("constraints")
 
+    def update(self, b=None, x0=None, constants=None):
+        """Next system of a time loop over a FIXED operator (lkdv/Evolve.py:39-56 re-assembles every step, but
+        only b, x0 and the invariant values change): new right-hand side / initial guess / constraint scalars
+        `c` (one per class-form constraint, None = keep); A, the constraint matrices and vectors and the Krylov
+        workspace stay where they are."""
+        self._join_setup()
+        ctx = self.ctx
+        if b is not None:
+            ctx.upload_vec(nat.VEC_B, nat.as_f64(b, self.n))
+        if x0 is not None:
+            self.x0_host = nat.as_f64(x0, self.n)
+            x0_nonzero = self._any_rank(nat.any_nonzero(self.x0_host))
+            ctx.upload_vec(nat.VEC_X0, self.x0_host)      # (zeros included: the buffer may hold an older guess)
+            ctx.set_option("x0_is_zero", 0 if x0_nonzero else 1)
+        if constants is not None:
+            constants = list(constants)
+            if len(constants) != len(self._cons):
+                raise ValueError(f"{len(constants)} constants for {len(self._cons)} constraints")
+            for idx, (entry, cc) in enumerate(zip(self._cons, constants)):
+                if cc is None:
+                    continue
+                if entry["kind"] != "class" or entry["error"] is not None:
+                    raise ValueError(f"constraint {idx} is not a class-form constraint held on the device")
+                ctx.constraint_set_constant(idx, float(cc))
+
     def _any_rank(self, flag):
         """Logical OR of a host-side decision over all ranks (identity on one GPU).  Every decision
         that changes the sequence of device reductions must be taken identically on all ranks."""

@@ -230,6 +230,10 @@ class FakeKrylovContext:
                         "T1": np.zeros(self.k_max), "T2": np.zeros((self.k_max, self.k_max)),
                         "MZ": np.zeros((self.k_max, self.n))}
 
+    def constraint_set_constant(self, c, cc):
+        self.cons[c]["c"] = cc
+        self.cons[c]["t0"] = None
+
     def constraint_terms(self, c, m):
         C = self.cons[c]
         n = self.n

@@ -323,3 +323,28 @@ def test_symmetric_fast_path_equals_general_path(x0_zero):
         np.testing.assert_allclose(t2, ref.term2, rtol=1e-11, atol=1e-12 * np.abs(ref.term2).max())
         np.testing.assert_array_equal(out[force][0][2], t2[:7, :7])
     np.testing.assert_allclose(out[0][1][2], out[1][1][2], rtol=1e-12, atol=1e-13 * np.abs(ref.term2).max())
+
+
+def test_evolve_time_loop_resident_matches_oracle_loop():
+    """wrappers.evolve (lkdv/Evolve.py:18-65) with the system resident on the GPU: five time steps of the default
+    lkdv problem against the same loop driven by the oracle, and against the reference's call pattern
+    (everything uploaded again every step)."""
+    kw = dict(N=100, M=50, k=50, tol=1e-8, contol=10, steps=5)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        dev = wrappers.evolve(**kw, resident=True)
+        fresh = wrappers.evolve(**kw, resident=False)
+        # the oracle's loop: same re-assembly, reference arithmetic on the host
+        forms, _ = lkdv.linforms(N=100, M=50)
+        sol = [forms["z0"].copy()]
+        for i in range(1, 6):
+            forms, _ = lkdv.linforms(N=100, M=50, zinit=sol[-1])
+            x0 = np.zeros_like(forms["b"])
+            z, _info = orc.cgmres(forms["A"], forms["b"], x0, 50, tol=1e-8, contol=10, conlist=wrappers.lkdv.conlist(forms, x0))
+            sol.append(np.array(z))
+    for za, zb in zip(dev["sol"], fresh["sol"]):
+        np.testing.assert_array_equal(za, zb)                       # resident or re-uploaded: the same arithmetic
+    for i, (za, zo) in enumerate(zip(dev["sol"], sol)):
+        assert helpers.rel_diff(za, zo) <= 1e-9 * max(i, 1), i      # per-step 1e-10-level differences compound
+    scale = abs(forms["mo0"]) + abs(forms["e0"]) + abs(forms["m0"])
+    assert max(dev["dm"].max(), dev["dmo"].max(), dev["de"].max()) <= 1e-12 * scale

@@ -280,3 +280,21 @@ def test_system_export_roundtrip(tmp_path):
             assert (abs(d[key] - e[key])).nnz == 0 and e[key].nnz == d[key].nnz
         else:
             np.testing.assert_array_equal(np.asarray(d[key]), np.asarray(e[key]))
+
+
+def test_evolve_resident_session_equals_fresh_uploads():
+    """wrappers.evolve (lkdv/Evolve.py:18-65): with the system resident only b and the three invariant values are
+    sent per time step (DeviceSession.update); the results are those of a fresh session per step."""
+    outs = []
+    for resident in (True, False):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            outs.append(wrappers.evolve(N=100, M=20, k=30, tol=1e-8, steps=4, resident=resident,
+                                        ctx_factory=FakeKrylovContext, small_solver="kkt"))
+    a, b = outs
+    assert len(a["sol"]) == 5 and a["steps"] == b["steps"] and a["time"] == b["time"]
+    for za, zb in zip(a["sol"], b["sol"]):
+        np.testing.assert_array_equal(za, zb)
+    # CGMRES keeps the three invariants of every step's initial state: drift over four steps at round-off level
+    assert max(a["dm"].max(), a["dmo"].max(), a["de"].max()) < 1e-11
+    assert a["dm"][0] == 0 and np.all(np.diff(a["time"]) > 0)

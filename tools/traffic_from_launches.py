@@ -3,8 +3,9 @@
 measured DRAM bytes per launch of every kernel class of bench.py's `kernels` object."""
 import collections, csv, json, os, re, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CLASS = [("spmv_sell", "spmv"), ("spmv_csr_kernel", "spmv"), ("spmv_pattern_kernel", "spmv"), ("reduce_partials", "spmv"), ("mdotm_kernel", "mdot"), ("mdot_kernel", "mdot"),
-         ("lincomb_kernel", "lincomb"), ("orth_mid_kernel", "orthmid"), ("scale_kernel", "scale")]
+CLASS = [("spmv_", "spmv"), ("reduce_partials", "spmv"), ("mdotm_kernel", "mdot"), ("mdot_kernel", "mdot"),
+         ("lincomb_kernel", "lincomb"), ("lincomb2_kernel", "lincomb"), ("orth_mid_kernel", "orthmid"), ("scale_kernel", "scale")]
+MODE = re.compile(r"kernel<\(?(?:int\))?\s*(\d)")
 out = {}
 for wl, nrows in (("lkdv", 10_000_050), ("swe", 10_002_828)):
     path = os.path.join(ROOT, "profiles", f"launches_r1_{wl}.csv")
@@ -15,18 +16,23 @@ for wl, nrows in (("lkdv", 10_000_050), ("swe", 10_002_828)):
     for r in rows:
         per.setdefault(r[iid], {"k": r[ik]})[r[im]] = float(r[iv].replace(",", ""))
     agg = collections.defaultdict(lambda: dict(launches=0, ns=0.0, dram=0.0))
-    # residual SpMVs (mode 2) always use the system matrix: their read volume minus b is what a mode-0
-    # launch on A reads; mode-0 launches reading clearly less ran on a constraint matrix
-    mode2 = sorted(d["dram__bytes_read.sum"] for d in per.values() if "spmv_" in d["k"] and "kernel<2>" in d["k"])
-    ref_read = mode2[len(mode2) // 2] - 8.0 * nrows
+    # single-vector mode-0 SpMVs: the first one of the solve (Arnoldi step 0) is on the system matrix; launches
+    # that read clearly less ran on a constraint matrix (a third of A's rows carry entries)
+    ref_read = None
     for d in per.values():
-        cls = next((c for pat, c in CLASS if pat in d["k"]), None)
+        name = d["k"]
+        cls = next((c for pat, c in CLASS if pat in name), None)
         if cls is None:
             continue
         dram = d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
-        if cls == "spmv" and "kernel<0>" in d["k"] and abs(d.get("dram__bytes_read.sum", 0.0) - ref_read) > 0.2 * ref_read:
-            cls = "spmv_aux"                  # constraint matrix (a third of A's rows carry entries)
-        a = agg[cls]; a["launches"] += 0 if "reduce_partials" in d["k"] else 1; a["ns"] += d["gpu__time_duration.sum"]; a["dram"] += dram
+        single0 = cls == "spmv" and "dual" not in name and "reduce_partials" not in name and MODE.search(name) and MODE.search(name).group(1) == "0"
+        if single0:
+            rd = d.get("dram__bytes_read.sum", 0.0)
+            if ref_read is None:
+                ref_read = rd
+            elif abs(rd - ref_read) > 0.2 * ref_read:
+                cls = "spmv_aux"
+        a = agg[cls]; a["launches"] += 0 if "reduce_partials" in name else 1; a["ns"] += d["gpu__time_duration.sum"]; a["dram"] += dram
     tot = sum(a["ns"] for a in agg.values())
     out[wl] = {c: {"launches": a["launches"], "traffic_bytes_per_launch": a["dram"] / a["launches"],
                    "ncu_us_per_launch": a["ns"] / a["launches"] * 1e-3, "share_of_kernel_time": a["ns"] / tot,
