@@ -348,3 +348,21 @@ def test_evolve_time_loop_resident_matches_oracle_loop():
         assert helpers.rel_diff(za, zo) <= 1e-9 * max(i, 1), i      # per-step 1e-10-level differences compound
     scale = abs(forms["mo0"]) + abs(forms["e0"]) + abs(forms["m0"])
     assert max(dev["dm"].max(), dev["dmo"].max(), dev["de"].max()) <= 1e-12 * scale
+
+
+@pytest.mark.parametrize("engine", ["slsqp", "kkt"])
+def test_lkdvrk_structured_constraints_match_the_callbacks(engine, golden):
+    """lkdvRK's three constraints as class-form quadratics in the stage vector (wrappers.lkdvRK.conlist_structured:
+    B' S B, B'(S z0 + w), ...) instead of opaque callbacks on a host copy of Z (lkdvRK/LinearSolver.py:29-76): the
+    reduced problem is the same, so the solve still reproduces the reference's output -- without the n x m
+    download per constrained iteration."""
+    name = "lkdvrk_tol6"
+    spec, dic, prob, x0, pre = cases.instantiate(name)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        x, info = wrappers.lkdvRK.cgmresWrapper(dic, structured=True, small_solver=engine, **cases.wrapper_kwargs(spec, x0, pre, prob))
+    assert info["steps"] == int(golden[f"{name}/steps"])
+    assert helpers.rel_diff(x, golden[f"{name}/x_last"]) <= tolerance(name)
+    z1 = wrappers.lkdvRK._rk.z1calc(prob, x, dic["z0"])
+    assert abs(dic["omega"] @ z1 - dic["m0"]) <= 1e-12 * max(1.0, abs(dic["m0"]))
+    assert abs(0.5 * z1 @ (dic["M"] @ z1) - dic["mo0"]) <= 1e-12 * max(1.0, abs(dic["mo0"]))

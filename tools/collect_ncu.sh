@@ -19,5 +19,5 @@ cap() {  # name, env, ncu args...
 }
 cap r1_lkdv_iter "SPIS_WORKLOAD=lkdv" -k regex:"spmv_|mdot_kernel|lincomb|orth_mid|scale_kernel|reduce_partials" --launch-skip 96 --launch-count 8
 cap r1_lkdv_mdotm "SPIS_WORKLOAD=lkdv" -k regex:"mdotm" --launch-count 2
-cap r1_swe_spmv "SPIS_WORKLOAD=swe" -k regex:"spmv_" --launch-skip 20 --launch-count 3
+cap r1_swe_spmv "SPIS_WORKLOAD=swe" -k regex:"spmv_sell_dual|spmv_selld" --launch-skip 8 --launch-count 3
 ls -la /tmp/*.ncu-rep >> $OUT/ncu_sizes.log
