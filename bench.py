@@ -415,6 +415,11 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": d["bytes"] / d["launches"], "peak_source": peak_src,
                 "avg_launch_ms": d["ms"] / d["launches"], "launches": d["launches"],
                 "share_of_kernel_time": d["ms"] / kernel_ms}
+    if traffic:
+        # what the kernel really moved (ncu) over its live duration: with the compressed SpMV storage and the dual
+        # SpMV the ALGORITHMIC bytes of SURVEY 8d (12 bytes per entry, two passes) exceed the traffic, frac > 1
+        roofline["achieved_dram"] = traffic / (d["ms"] / d["launches"]) * 1e-6
+        roofline["frac_dram"] = roofline["achieved_dram"] / peak
     kernels = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
                    "gbs": v["gbs"], "frac_of_peak": (v["gbs"] / peak if v["gbs"] else None)} for k, v in classes.items()}
 
