@@ -83,6 +83,7 @@ struct spis_ctx {
   int spmv_variant = 1;         // 0: first-generation SpMV kernels; 1+: prefetching / software-pipelined ones (see launch_spmv_mode)
   int spmv_pipe_ctas_per_sm = 0;   // 0 = the kernel's own default
   int pinned_scan_dma = 0;      // spis_any_nonzero on page-locked memory: 1 = copy engine + kernel, 0 = host threads
+  int spmv_multi = 1;           // constraint stage: M z_j for a group of 2 / 4 Krylov columns from one pass over M
   int spmv_dual = 1;            // A q_{j+2} and ||A x_j - b|| from one pass over A (spis_arnoldi_begin_residual)
   int spmv_dual_ctas_per_sm = 0;
   int mdot_variant = 0, lincomb_variant = 4;   // mdot 0 = auto (tools/tune.py sweep, profiles/tune_r1.md)
@@ -584,6 +585,41 @@ int launch_spmv_dual(spis_ctx* ctx, const double* x1, double* y1, const double* 
   return do_allreduce(ctx, sumsq_out, 1);
 }
 
+// y_c = M x_c, c < nv (nv = 2 or 4), vectors `xstride` / `ystride` doubles apart: one pass over the matrix in `slot`
+// for the whole group (formats without a multi-vector kernel: nv launches)
+int launch_spmv_multi(spis_ctx* ctx, int slot, int nv, const double* x, int64_t xstride, double* y, int64_t ystride) {
+  const Matrix& M = ctx->mats[slot];
+  REQUIRE(M.present, "matrix slot %d has not been uploaded", slot);
+  const bool fused = ctx->spmv_multi && (nv == 2 || nv == 4) &&
+                     (M.fmt == SPIS_FMT_PATTERN || M.fmt == SPIS_FMT_SELL || M.fmt == SPIS_FMT_SELLD);
+  if (!fused) {
+    for (int c = 0; c < nv; ++c) TRY(launch_spmv(ctx, slot, 0, x + (size_t)c * xstride, nullptr, y + (size_t)c * ystride, nullptr));
+    return SPIS_OK;
+  }
+  const double bytes = (double)nv * (12.0 * (double)M.nnz + 4.0 * (double)(M.nrows + 1) + 16.0 * (double)M.nrows);   // nv SpMVs' worth
+  TRY(prof_begin(ctx, slot == SPIS_SLOT_A ? SPIS_PROF_SPMV : SPIS_PROF_SPMV_AUX, bytes));
+  if (M.fmt == SPIS_FMT_PATTERN) {
+    int grid = grid_for(ctx, (M.nrows + kThreads - 1) / kThreads, nv == 2 ? 6 : 4);
+    while (grid > 1 && (int64_t)M.nrows + (int64_t)grid * kThreads >= (int64_t)INT32_MAX) grid /= 2;
+#define SPIS_PATM(NC, NVV) spmv_pattern_multi_kernel<NC, NVV><<<grid, kThreads, 0, ctx->stream>>>(M.pid, M.patW, M.tab_off, M.tab_val, (int)M.nrows, x, xstride, y, ystride)
+#define SPIS_PATM_CASE(NC) case NC: if (nv == 2) SPIS_PATM(NC, 2); else SPIS_PATM(NC, 4); break;
+    switch (M.patW / 4) { SPIS_PATM_CASE(1) SPIS_PATM_CASE(2) SPIS_PATM_CASE(3) SPIS_PATM_CASE(4)
+      default: if (nv == 2) SPIS_PATM(0, 2); else SPIS_PATM(0, 4); }
+#undef SPIS_PATM_CASE
+#undef SPIS_PATM
+  } else {
+    const int64_t nslices = (M.nrows + 31) / 32;
+    const bool coded = M.fmt == SPIS_FMT_SELLD;
+    const int grid = grid_for(ctx, (nslices + kWarps - 1) / kWarps, nv == 2 ? 5 : 4);
+#define SPIS_SELLM(CD, NVV) spmv_sell_multi_kernel<CD, NVV><<<grid, kThreads, 0, ctx->stream>>>(M.slice_off, M.code_off, M.scols, M.svals, M.codes, M.dict, M.nrows, x, xstride, y, ystride)
+    if (coded) { if (nv == 2) SPIS_SELLM(true, 2); else SPIS_SELLM(true, 4); }
+    else { if (nv == 2) SPIS_SELLM(false, 2); else SPIS_SELLM(false, 4); }
+#undef SPIS_SELLM
+  }
+  CU(cudaGetLastError());
+  return prof_end(ctx);
+}
+
 int launch_scale(spis_ctx* ctx, double* v, const double* sumsq, const double* jac, double* znext) {
   const int grid = grid_for(ctx, (ctx->n + 2 * kThreads - 1) / (2 * kThreads), 8);
   TRY(prof_begin(ctx, SPIS_PROF_SCALE, (jac ? 32.0 : 16.0) * (double)ctx->n));
@@ -998,6 +1034,7 @@ int spis_set_option(spis_ctx* ctx, const char* key, int64_t value) {
   else if (k == "spmv_variant") { REQUIRE(value >= 0 && value <= 1, "spmv_variant must be 0 or 1"); ctx->spmv_variant = (int)value; }
   else if (k == "spmv_pipe_ctas_per_sm") { REQUIRE(value >= 0 && value <= 16, "spmv_pipe_ctas_per_sm must be 0..16"); ctx->spmv_pipe_ctas_per_sm = (int)value; }
   else if (k == "pinned_scan_dma") { ctx->pinned_scan_dma = value ? 1 : 0; }
+  else if (k == "spmv_multi") { ctx->spmv_multi = value ? 1 : 0; }
   else if (k == "spmv_dual") { ctx->spmv_dual = value ? 1 : 0; }
   else if (k == "spmv_dual_ctas_per_sm") { REQUIRE(value >= 0 && value <= 16, "spmv_dual_ctas_per_sm must be 0..16"); ctx->spmv_dual_ctas_per_sm = (int)value; }
   else if (k == "mdot_variant") { REQUIRE(value == 0 || value == 2 || value == 4 || value == 8, "mdot_variant must be 0 (auto), 2, 4 or 8"); ctx->mdot_variant = (int)value; }
@@ -1670,8 +1707,9 @@ int spis_constraint_terms(spis_ctx* ctx, int c, int m, double* term0, double* te
         const int nw = left >= 4 ? 4 : left >= 2 ? 2 : 1;
         const int g1 = g0 + nw;
         double* base = ctx->d_cout + (size_t)g0 * 2 * K;
-        for (int cc2 = 0; cc2 < nw && rc == SPIS_OK; ++cc2)      // M z_col (ghosts filled by the Arnoldi step) (:33)
-          rc = launch_spmv(ctx, C.slot, 0, Zb + (size_t)(g0 + cc2) * ld, nullptr, ctx->G + (size_t)cc2 * ld, nullptr);
+        // M z_col for the whole group, one pass over M (ghosts filled by the Arnoldi step)          (:33)
+        if (nw == 1) rc = launch_spmv(ctx, C.slot, 0, Zb + (size_t)g0 * ld, nullptr, ctx->G, nullptr);
+        else rc = launch_spmv_multi(ctx, C.slot, nw, Zb + (size_t)g0 * ld, (int64_t)ld, ctx->G, (int64_t)ld);
         const double* extra = x0nz ? ctx->X0 : nullptr;
         const int nr = g1 + (extra ? 1 : 0);
         if (rc == SPIS_OK) {

@@ -1561,6 +1561,118 @@ spmv_sell_dual_kernel(const int64_t* __restrict__ slice_off, const int64_t* __re
   cta_partial_sum(ss, sred, partial);
 }
 
+// ------------------------------------------------------------------------------------------
+// K6  y_c = M x_c for NV vectors at once (x_c = x + c*xstride, y_c = y + c*ystride): the constraint stage needs
+// M z_j for every Krylov column (solvers.py:33, `M @ Z`) and catches up four columns per group.  As in the dual
+// kernels everything per matrix entry is fetched once for the whole group; per row and vector the summation order
+// is that of the single-vector kernels (same bits).
+// ------------------------------------------------------------------------------------------
+template <int NCH, int NV>
+__global__ void __launch_bounds__(kThreads, NV == 2 ? 6 : 4)
+spmv_pattern_multi_kernel(const uint16_t* __restrict__ pid, int W, const int32_t* __restrict__ tab_off,
+                          const double* __restrict__ tab_val, int nrows,
+                          const double* __restrict__ x, int64_t xstride, double* __restrict__ y, int64_t ystride) {
+  const int nblocks = (nrows + kThreads - 1) / kThreads;
+  int pn = 0;
+  {
+    const int row = blockIdx.x * kThreads + threadIdx.x;
+    if (row < nrows) pn = (int)__ldcs(pid + row);
+  }
+  for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    const int row = blk * kThreads + threadIdx.x;
+    const int p = pn;
+    const int nrow = row + (int)gridDim.x * kThreads;
+    pn = (blk + (int)gridDim.x < nblocks && nrow < nrows) ? (int)__ldcs(pid + nrow) : 0;
+    if (row < nrows) {
+      const int4* to = reinterpret_cast<const int4*>(tab_off + p * W);
+      const double2* tv = reinterpret_cast<const double2*>(tab_val + p * W);
+      double a0[NV], a1[NV];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) { a0[v] = 0.0; a1[v] = 0.0; }
+      const int nch = NCH > 0 ? NCH : W / 4;
+#pragma unroll
+      for (int c = 0; c < nch; ++c) {
+        const int4 o = __ldg(to + c);
+        const double2 va = __ldg(tv + 2 * c), vb = __ldg(tv + 2 * c + 1);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const double* xv = x + (size_t)v * xstride + row;
+          const double u0 = __ldg(xv + o.x), u1 = __ldg(xv + o.y), u2 = __ldg(xv + o.z), u3 = __ldg(xv + o.w);
+          a0[v] = fma(va.x, u0, a0[v]); a1[v] = fma(va.y, u1, a1[v]);
+          a0[v] = fma(vb.x, u2, a0[v]); a1[v] = fma(vb.y, u3, a1[v]);
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < NV; ++v) y[(size_t)v * ystride + row] = a0[v] + a1[v];
+    }
+  }
+}
+
+template <bool CODED, int NV>
+__global__ void __launch_bounds__(kThreads, NV == 2 ? 5 : 4)
+spmv_sell_multi_kernel(const int64_t* __restrict__ slice_off, const int64_t* __restrict__ code_off,
+                       const int32_t* __restrict__ cols, const double* __restrict__ vals,
+                       const uint32_t* __restrict__ codes, const double* __restrict__ table, int64_t nrows,
+                       const double* __restrict__ x, int64_t xstride, double* __restrict__ y, int64_t ystride) {
+  __shared__ double sdict[CODED ? 256 : 1];
+  if constexpr (CODED) {
+    sdict[threadIdx.x] = __ldg(table + threadIdx.x);
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t nslices = (nrows + 31) >> 5;
+  const int64_t nblocks = (nslices + kWarps - 1) / kWarps;
+  for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    const int64_t slice = blk * kWarps + warp;
+    if (slice < nslices) {
+      const int64_t off = __ldg(slice_off + slice);
+      const int width = (int)((__ldg(slice_off + slice + 1) - off) >> 5);
+      const int32_t* c = cols + off + lane;
+      const double* vp = CODED ? nullptr : vals + off + lane;
+      const uint32_t* q = CODED ? codes + __ldg(code_off + slice) + lane : nullptr;
+      const int64_t row = (slice << 5) + lane;
+      double a0[NV], a1[NV];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) { a0[v] = 0.0; a1[v] = 0.0; }
+      int k = 0;
+      for (; k + 4 <= width; k += 4) {
+        const int32_t c0 = __ldcs(c + (k + 0) * 32), c1 = __ldcs(c + (k + 1) * 32);
+        const int32_t c2 = __ldcs(c + (k + 2) * 32), c3 = __ldcs(c + (k + 3) * 32);
+        double v0, v1, v2, v3;
+        if constexpr (CODED) {
+          const uint32_t w = __ldcs(q + (k >> 2) * 32);
+          v0 = sdict[w & 255u]; v1 = sdict[(w >> 8) & 255u]; v2 = sdict[(w >> 16) & 255u]; v3 = sdict[w >> 24];
+        } else {
+          v0 = __ldcs(vp + (k + 0) * 32); v1 = __ldcs(vp + (k + 1) * 32);
+          v2 = __ldcs(vp + (k + 2) * 32); v3 = __ldcs(vp + (k + 3) * 32);
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const double* xv = x + (size_t)v * xstride;
+          const double u0 = __ldg(xv + c0), u1 = __ldg(xv + c1), u2 = __ldg(xv + c2), u3 = __ldg(xv + c3);
+          a0[v] = fma(v0, u0, a0[v]); a1[v] = fma(v1, u1, a1[v]);
+          a0[v] = fma(v2, u2, a0[v]); a1[v] = fma(v3, u3, a1[v]);
+        }
+      }
+      if (k < width) {
+        uint32_t w = 0u;
+        if constexpr (CODED) w = __ldcs(q + (k >> 2) * 32);
+        for (; k < width; ++k, w >>= 8) {
+          const int32_t ck = __ldcs(c + k * 32);
+          double vk;
+          if constexpr (CODED) vk = sdict[w & 255u]; else vk = __ldcs(vp + k * 32);
+#pragma unroll
+          for (int v = 0; v < NV; ++v) a0[v] = fma(vk, __ldg(x + (size_t)v * xstride + ck), a0[v]);
+        }
+      }
+      if (row < nrows) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) y[(size_t)v * ystride + row] = a0[v] + a1[v];
+      }
+    }
+  }
+}
+
 // K1 fallback: CSR "vector" kernel, T lanes per row (T = 2..32), for matrices whose row
 // lengths vary so much inside a 32-row slice that SELL padding would waste bandwidth.
 template <int T, int MODE>

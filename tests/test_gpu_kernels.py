@@ -395,3 +395,46 @@ def test_bench_kernel_entry_point():
         for cls in (nat.PROF_SPMV, nat.PROF_MDOT, nat.PROF_LINCOMB, nat.PROF_SCALE, nat.PROF_ORTHMID):
             ms, by = ctx.bench_kernel(cls, 6, reps=3)
             assert ms > 0 and by > 0
+
+
+@pytest.mark.parametrize("fmt", [nat.FMT_SELL, nat.FMT_SELLD, nat.FMT_PATTERN, nat.FMT_CSR])
+def test_constraint_stage_multi_vector_spmv_is_bit_identical(fmt):
+    """The constraint stage forms M z_j for groups of four / two Krylov columns from ONE pass over M
+    (spmv_pattern_multi_kernel / spmv_sell_multi_kernel): same per-row summation order as the single-vector
+    kernels, so term1 and term2 (solvers.py:35-36) are the same bits with the grouping switched off; against
+    numpy to rounding.  m = 7 exercises groups of 4, 2 and 1."""
+    from structurepreservingiterativesolvers_b200.problems import swe
+    rng = np.random.default_rng(29)
+    if fmt in (nat.FMT_SELLD, nat.FMT_CSR):
+        d = swe.linforms(M=40, mlength=32.0)[0]
+    else:
+        d = lkdv.linforms(space="CG", M=33_350, mlength=0.8 * 33_350)[0]
+    A, L = d["A"], d["L"].tocsr()
+    n = A.shape[0]
+    b, x0, v = rng.standard_normal(n), 0.01 * rng.standard_normal(n), rng.standard_normal(n)
+    m = 7
+    out = []
+    for multi in (1, 0):
+        with KrylovContext(n, 8) as ctx:
+            ctx.set_option("spmv_format", fmt)
+            ctx.set_option("spmv_multi", multi)
+            ctx.upload_matrix(nat.SLOT_A, A)
+            ctx.upload_matrix(nat.SLOT_CON0, L)
+            ctx.upload_vec(nat.VEC_B, b)
+            ctx.upload_vec(nat.VEC_X0, x0)
+            ctx.constraint_define(0, nat.SLOT_CON0, v, 0.25)
+            ctx.solve_begin()
+            for j in range(m):
+                ctx.arnoldi_step(j)
+            t0, t1, t2 = ctx.constraint_terms(0, m)
+            Z = ctx.download_Z(0, m)
+            out.append((t0, t1, t2, Z))
+    np.testing.assert_array_equal(out[0][1], out[1][1])
+    np.testing.assert_array_equal(out[0][2], out[1][2])
+    t0, t1, t2, Z = out[0]
+    LZ = (L @ Z.T)
+    ref2 = 0.5 * Z @ LZ
+    ref1 = Z @ v + x0 @ LZ
+    assert np.max(np.abs(t2 - ref2)) <= 1e-13 * np.max(np.abs(ref2))
+    assert np.max(np.abs(t1 - ref1)) <= 1e-12 * np.max(np.abs(ref1))
+    assert abs(t0 - (0.5 * x0 @ (L @ x0) + v @ x0 + 0.25)) <= 1e-13 * max(1.0, abs(t0))
