@@ -510,6 +510,12 @@ class _Arnoldi:
         self._cs = np.zeros(k)
         self._sn = np.zeros(k)
         self._g = None if beta is None else float(beta)
+        # ... and, kept along, the triangular factor and the rotated right-hand side: the unconstrained minimiser
+        # of the 'kkt' engine is one back substitution (ls_solution) instead of an SVD-based lstsq per iteration
+        self._R = np.zeros((k, k))
+        self._gv = np.zeros(k + 1)
+        if beta is not None:
+            self._gv[0] = float(beta)
 
     def column(self, j):
         if self._have == j:                   # fetched while the previous iterate/residual pair ran
@@ -538,6 +544,10 @@ class _Arnoldi:
             if den > 0:
                 self._cs[j], self._sn[j] = r[j] / den, r[j + 1] / den
                 self._g = -self._sn[j] * self._g
+                self._R[: j, j] = r[:j]
+                self._R[j, j] = den
+                gj = self._gv[j]
+                self._gv[j], self._gv[j + 1] = self._cs[j] * gj, -self._sn[j] * gj
             else:
                 self._g = None
 
@@ -583,6 +593,17 @@ class _Arnoldi:
         ls = abs(self._g)
         rate = 1.0 if not self._ls_prev else min(1.0, ls / self._ls_prev)
         return ls * rate * rate >= tol
+
+    def ls_solution(self, m):
+        """argmin_y |beta e1 - H[:m+1, :m] y| from the Givens QR kept by _store (None when it is not tracked or R
+        is singular to working precision: the caller then takes the general least-squares route)."""
+        if self._g is None or self._have != m - 1:
+            return None
+        R = self._R[:m, :m]
+        d = np.abs(np.diag(R))
+        if m == 0 or not d.min() > 1e-14 * d.max():
+            return None
+        return np.linalg.solve(R, self._gv[:m])        # triangular: LU never swaps a row, i.e. back substitution
 
     def ls_residual(self):
         """min_y |beta e1 - H_j y| after the last column() (inf when not tracked)."""
@@ -635,9 +656,12 @@ def _finish_history(hist, history_mode, x_last):
     return hist
 
 
-def _unconstrained(engine, Hj, beta, y0, ftol):
+def _unconstrained(engine, Hj, beta, y0, ftol, arn=None):
     if engine == "slsqp":
         return smallsolve.slsqp(Hj, beta, y0, (), ftol=ftol, tol=None)
+    y = arn.ls_solution(Hj.shape[1]) if arn is not None else None
+    if y is not None:
+        return smallsolve.SmallResult(y)
     return smallsolve.lstsq(Hj, beta)
 
 
@@ -732,7 +756,7 @@ def cgmres(A, b, x0, k, tol=1e-8, contol=10, conlist=[], pre=None, timing=None, 
             y0[:-1] = yk                                  # warm start (solvers.py:225-227)
         if residual[-1] > contol * tol and j < k - 1 and safety is None:      # (solvers.py:230)
             arn.prefetch(j + 1)
-            res = _unconstrained(engine, Hj, beta, y0, ctol ** 2)
+            res = _unconstrained(engine, Hj, beta, y0, ctol ** 2, arn)
         else:
             try:
                 if timing:
@@ -774,7 +798,7 @@ def cgmres(A, b, x0, k, tol=1e-8, contol=10, conlist=[], pre=None, timing=None, 
                 if timing and len(jit["end_constraints"]) < len(jit["start_constraints"]):
                     jit["end_constraints"].append(time())
                 arn.prefetch(j + 1)
-                res = _unconstrained(engine, Hj, beta, y0, ctol ** 2)         # (solvers.py:274-278)
+                res = _unconstrained(engine, Hj, beta, y0, ctol ** 2, arn)         # (solvers.py:274-278)
         _warn_message(j, res)
         yk = res.x
         bk.mark("small solve + host")

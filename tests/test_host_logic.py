@@ -298,3 +298,20 @@ def test_evolve_resident_session_equals_fresh_uploads():
     # CGMRES keeps the three invariants of every step's initial state: drift over four steps at round-off level
     assert max(a["dm"].max(), a["dmo"].max(), a["de"].max()) < 1e-11
     assert a["dm"][0] == 0 and np.all(np.diff(a["time"]) > 0)
+
+
+def test_givens_least_squares_matches_lstsq():
+    """The 'kkt' engine takes the unconstrained minimiser from the Givens QR the Arnoldi driver keeps anyway (one
+    back substitution per iteration instead of an SVD-based lstsq): same y to rounding at every step."""
+    from structurepreservingiterativesolvers_b200 import smallsolve
+    spec, dic, prob, x0, pre = cases.instantiate("lkdv_cg_tol6")
+    sess = solvers.DeviceSession(dic["A"], dic["b"], x0, 30, ctx_factory=FakeKrylovContext)
+    beta = sess.begin()
+    arn = solvers._Arnoldi(sess, 30, False, beta)
+    for j in range(12):
+        arn.column(j)
+        y = arn.ls_solution(j + 1)
+        ref = smallsolve.lstsq(arn.H[: j + 2, : j + 1], beta).x
+        assert y is not None and np.max(np.abs(y - ref)) <= 1e-12 * np.max(np.abs(ref))
+        assert abs(arn.ls_residual() - arn.predicted_residual(y, beta)) <= 1e-10 * beta
+    assert arn.ls_solution(5) is None                      # only for the column count just stored
