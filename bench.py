@@ -120,7 +120,7 @@ def transfer_bytes(A, b, x0, conlist):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -139,7 +139,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -309,7 +309,7 @@ def run_ours(args):
     # ---- device-resident timing --------------------------------------------------------------
     sess = make_session(profile=False)
     ctx = sess.ctx
-    # the sampler (nvidia-smi -lms 200) is started before the warm-up so that its start-up cost
+    # the sampler (nvidia-smi -lms 100) is started before the warm-up so that its start-up cost
     # (process launch, NVML initialisation) is not inside the timed region
     with ClockSampler(local) as clk:
         for _ in range(args.warmup):

@@ -82,6 +82,8 @@ struct spis_ctx {
   int spmv_ctas_per_sm = 8;
   int spmv_variant = 1;         // 0: first-generation SpMV kernels; 1+: prefetching / software-pipelined ones (see launch_spmv_mode)
   int spmv_pipe_ctas_per_sm = 0;   // 0 = the kernel's own default
+  int mdot_reg_auto = 1;        // mdot_variant 0 (auto) may pick the register-accumulator kernel
+  int mdot_reg_ctas_per_sm = 0;
   int pinned_scan_dma = 0;      // spis_any_nonzero on page-locked memory: 1 = copy engine + kernel, 0 = host threads
   int spmv_multi = 1;           // constraint stage: M z_j for a group of 2 / 4 Krylov columns from one pass over M
   int spmv_dual = 1;            // A q_{j+2} and ||A x_j - b|| from one pass over A (spis_arnoldi_begin_residual)
@@ -356,6 +358,22 @@ int launch_mdot(spis_ctx* ctx, const double* V, int m, const double* extra, int 
   REQUIRE(nrows <= ctx->pstride, "mdot: %d rows exceed workspace %d", nrows, ctx->pstride);
   const int64_t ntiles = (ctx->n + kTile - 1) / kTile;
   // measured on B200 (n = 1e7): few rows want more loads per thread on fewer CTAs, many rows the opposite
+  // (tools/tune_mdot_reg.py, n = 1e7: register sums win by 3-8 % for 5..32 rows and by 20-35 % for 1-2 rows, lose 2-5 % at 3-4 and beyond 34)
+  if ((ctx->mdot_variant == 1 || (ctx->mdot_variant == 0 && ctx->mdot_reg_auto && (nrows <= 2 || (nrows >= 5 && nrows <= 32)))) && nrows <= 40) {
+    // partial sums in registers, one reduction at the end (mdot_reg_kernel)
+    const int MB = (nrows + 7) / 8 * 8;
+    const int per = ctx->mdot_reg_ctas_per_sm > 0 ? ctx->mdot_reg_ctas_per_sm : 2;
+    const int grid = grid_for(ctx, ntiles, per);
+    TRY(prof_begin(ctx, SPIS_PROF_MDOT, (double)(m + (extra ? 1 : 0) + 1) * 8.0 * (double)ctx->n));
+    const XView xv = fused_view(ctx);
+    const unsigned long long seq = fused_seq(ctx);
+#define SPIS_MDR(MBB) case MBB: mdot_reg_kernel<MBB><<<grid, kThreads, 0, ctx->stream>>>(V, ctx->ld, m, extra, with_sumsq, w, ctx->n, ctx->d_partial, ctx->pstride, ctx->d_counter, out, xv, seq); break;
+    switch (MB) { SPIS_MDR(8) SPIS_MDR(16) SPIS_MDR(24) SPIS_MDR(32) default: SPIS_MDR(40) }
+#undef SPIS_MDR
+    CU(cudaGetLastError());
+    TRY(prof_end(ctx));
+    return do_allreduce(ctx, out, nrows);
+  }
   int variant = ctx->mdot_variant, per_sm = ctx->ctas_per_sm;
   if (variant == 0) { variant = nrows <= 6 ? 4 : 2; per_sm = nrows <= 6 ? (ctx->ctas_per_sm > 2 ? 2 : ctx->ctas_per_sm) : ctx->ctas_per_sm; }
   const int grid = grid_for(ctx, ntiles, per_sm);
@@ -1037,7 +1055,9 @@ int spis_set_option(spis_ctx* ctx, const char* key, int64_t value) {
   else if (k == "spmv_multi") { ctx->spmv_multi = value ? 1 : 0; }
   else if (k == "spmv_dual") { ctx->spmv_dual = value ? 1 : 0; }
   else if (k == "spmv_dual_ctas_per_sm") { REQUIRE(value >= 0 && value <= 16, "spmv_dual_ctas_per_sm must be 0..16"); ctx->spmv_dual_ctas_per_sm = (int)value; }
-  else if (k == "mdot_variant") { REQUIRE(value == 0 || value == 2 || value == 4 || value == 8, "mdot_variant must be 0 (auto), 2, 4 or 8"); ctx->mdot_variant = (int)value; }
+  else if (k == "mdot_variant") { REQUIRE(value == 0 || value == 1 || value == 2 || value == 4 || value == 8, "mdot_variant must be 0 (auto), 1 (register sums), 2, 4 or 8"); ctx->mdot_variant = (int)value; }
+  else if (k == "mdot_reg_auto") { ctx->mdot_reg_auto = value ? 1 : 0; }
+  else if (k == "mdot_reg_ctas_per_sm") { REQUIRE(value >= 0 && value <= 8, "mdot_reg_ctas_per_sm must be 0..8"); ctx->mdot_reg_ctas_per_sm = (int)value; }
   else if (k == "lincomb_variant") { REQUIRE(value == 2 || value == 4 || value == 8, "lincomb_variant must be 2, 4 or 8"); ctx->lincomb_variant = (int)value; }
   else if (k == "x0_is_zero") { ctx->x0_is_zero = value ? 1 : 0; }
   else if (k == "fuse_jacobi") { ctx->fuse_jacobi = value ? 1 : 0; }

@@ -253,6 +253,83 @@ mdot_kernel(const double* __restrict__ V, int64_t ld, int m, const double* __res
 }
 
 // ------------------------------------------------------------------------------------------
+// K3a with the partial sums in REGISTERS.  mdot_kernel reduces every row of every tile across the warp (ten
+// shuffles and a shared-memory add per row, tile and warp); at m = 20 that is a few hundred shuffle instructions
+// per 168 KB tile and keeps the kernel at 0.85-0.95 of the copy bandwidth.  Here each thread owns MB running sums
+// (MB = rows rounded up to 8, a template parameter so that the indices are static), rows are taken four at a time
+// (8 independent 128-bit loads in flight per thread) and the warp / CTA reduction happens once, after the last
+// tile -- the scheme of orth_mid_kernel without the staging.
+// ------------------------------------------------------------------------------------------
+template <int MB, bool FULL>
+__device__ __forceinline__ void mdot_reg_tile(const double* __restrict__ V, int64_t ld, int m,
+                                              const double* __restrict__ extra, const double* __restrict__ w,
+                                              int64_t n, int nrows, int64_t tile, double (&acc)[MB]) {
+  const int64_t e0 = tile * kTile + 2 * threadIdx.x;
+  const int64_t e1 = e0 + 2 * kThreads;
+  const bool p0 = FULL || e0 < n, p1 = FULL || e1 < n;
+  double2 w0 = make_double2(0.0, 0.0), w1 = w0;
+  if (p0) w0 = ld_keep(w + e0);
+  if (p1) w1 = ld_keep(w + e1);
+#pragma unroll
+  for (int i0 = 0; i0 < MB; i0 += 4) {
+    if (i0 < nrows) {
+      double2 a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u;
+        const double* row = (i < m) ? (V + (size_t)i * ld) : ((extra && i == m) ? extra : w);
+        const bool on = i < nrows;
+        a[u] = (on && p0) ? ld_stream(row + e0) : make_double2(0.0, 0.0);
+        b[u] = (on && p1) ? ld_stream(row + e1) : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        double t = acc[i0 + u];
+        t = fma(a[u].x, w0.x, t); t = fma(a[u].y, w0.y, t);
+        t = fma(b[u].x, w1.x, t); t = fma(b[u].y, w1.y, t);
+        acc[i0 + u] = t;
+      }
+    }
+  }
+}
+
+template <int MB>
+__global__ void __launch_bounds__(kThreads, MB <= 8 ? 4 : (MB <= 16 ? 3 : 2))
+mdot_reg_kernel(const double* __restrict__ V, int64_t ld, int m, const double* __restrict__ extra,
+                int with_sumsq, const double* __restrict__ w, int64_t n,
+                double* __restrict__ partial, int pstride, unsigned* counter, double* out,
+                XView xv, unsigned long long seq) {
+  __shared__ double sacc[kWarps * MB];
+  __shared__ double sred[kWarps * 32];
+  const int nrows = m + (extra ? 1 : 0) + (with_sumsq ? 1 : 0);
+  double acc[MB];
+#pragma unroll
+  for (int i = 0; i < MB; ++i) acc[i] = 0.0;
+  const int64_t ntiles = (n + kTile - 1) / kTile;
+  const int64_t nfull = n / kTile;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    if (tile < nfull) mdot_reg_tile<MB, true>(V, ld, m, extra, w, n, nrows, tile, acc);
+    else mdot_reg_tile<MB, false>(V, ld, m, extra, w, n, nrows, tile, acc);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < MB; ++i) {
+    if (i < nrows) {
+      const double t = warp_sum(acc[i]);
+      if (lane == 0) sacc[warp * MB + i] = t;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nrows; i += kThreads) {
+    double t = 0.0;
+#pragma unroll
+    for (int wv = 0; wv < kWarps; ++wv) t += sacc[wv * MB + i];
+    partial[(size_t)blockIdx.x * pstride + i] = t;
+  }
+  finish_reduction(partial, pstride, nrows, counter, out, sred, xv, seq);
+}
+
+// ------------------------------------------------------------------------------------------
 // K7  multi-right-hand-side variant of mdot: out[c*nrows + i] = row_i . w_c for NW vectors
 // w_c = W + c*wstride at once, so every basis row is read ONCE for NW columns.  Used when the
 // constraint stage has to catch up several Krylov columns of Z^T (M Z) at the first constrained

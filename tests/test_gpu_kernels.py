@@ -220,12 +220,14 @@ def test_spmv_kernel_generations_agree(fmt):
 
 
 @pytest.mark.parametrize("n", [2, 1023, 1024, 1025, 2049, 300_007])
-@pytest.mark.parametrize("m", [0, 1, 3, 4, 5, 21])
-def test_mdot(n, m):
+@pytest.mark.parametrize("m", [0, 1, 3, 4, 5, 21, 39])
+@pytest.mark.parametrize("variant", [0, 1])            # 0: chosen by size; 1: per-thread register sums (mdot_reg_kernel)
+def test_mdot(n, m, variant):
     rng = np.random.default_rng(n + m)
     V = rng.standard_normal((m, n))
     w = rng.standard_normal(n)
-    with KrylovContext(n, 24) as ctx:
+    with KrylovContext(n, 40) as ctx:
+        ctx.set_option("mdot_variant", variant)
         out1 = ctx.op_mdot(V, w)
         out2 = ctx.op_mdot(V, w)
     np.testing.assert_array_equal(out1, out2)                      # fixed summation order
@@ -234,7 +236,7 @@ def test_mdot(n, m):
     assert np.max(np.abs(out1 - ref) / scale) <= 1e-13
 
 
-@pytest.mark.parametrize("variant", [2, 4, 8])
+@pytest.mark.parametrize("variant", [1, 2, 4, 8])
 def test_mdot_variants_and_grid_sizes(variant):
     n, m = 70_001, 13
     rng = np.random.default_rng(7)
