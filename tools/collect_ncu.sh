@@ -17,7 +17,7 @@ cap() {  # name, env, ncu args...
   env $envs ncu --set full --clock-control none "$@" -o /tmp/$name -f python tools/ncu_target.py 10000000 1 > $OUT/ncu_$name.log 2>&1
   ncu -i /tmp/$name.ncu-rep --page raw --csv > $OUT/ncu_full_$name.csv 2>> $OUT/ncu_$name.log
 }
-cap r1_lkdv_iter "SPIS_WORKLOAD=lkdv" -k regex:"spmv_|mdot_kernel|lincomb|orth_mid|scale_kernel|reduce_partials" --launch-skip 96 --launch-count 8
+cap r1_lkdv_iter "SPIS_WORKLOAD=lkdv" -k regex:"spmv_|mdot_|lincomb|orth_mid|scale_kernel|reduce_partials" --launch-skip 96 --launch-count 8
 cap r1_lkdv_mdotm "SPIS_WORKLOAD=lkdv" -k regex:"mdotm" --launch-count 2
 cap r1_swe_spmv "SPIS_WORKLOAD=swe" -k regex:"spmv_sell_dual|spmv_selld" --launch-skip 8 --launch-count 3
 ls -la /tmp/*.ncu-rep >> $OUT/ncu_sizes.log

@@ -3,7 +3,8 @@
 measured DRAM bytes per launch of every kernel class of bench.py's `kernels` object."""
 import collections, csv, json, os, re, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CLASS = [("spmv_", "spmv"), ("reduce_partials", "spmv"), ("mdotm_kernel", "mdot"), ("mdot_kernel", "mdot"),
+CLASS = [("spmv_pattern_multi", "spmv_aux"), ("spmv_sell_multi", "spmv_aux"), ("spmv_", "spmv"), ("reduce_partials", "spmv"),
+         ("mdotm_kernel", "mdot"), ("mdot_kernel", "mdot"), ("mdot_reg_kernel", "mdot"),
          ("lincomb_kernel", "lincomb"), ("lincomb2_kernel", "lincomb"), ("orth_mid_kernel", "orthmid"), ("scale_kernel", "scale")]
 MODE = re.compile(r"kernel<\(?(?:int\))?\s*(\d)")
 out = {}
