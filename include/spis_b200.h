@@ -103,8 +103,11 @@ int         spis_ctx_create(int device, int64_t n, int64_t n_halo, int k_max, vo
 int         spis_ctx_destroy(spis_ctx* ctx);
 const char* spis_last_error(const spis_ctx* ctx);
 const char* spis_last_global_error(void);            /* for failures of spis_ctx_create itself */
-/* keys: "orth", "spmv_format", "profile", "ctas_per_sm", "spmv_ctas_per_sm", "mdot_variant", "lincomb_variant",
- *       "x0_is_zero", "fuse_jacobi", "orth_fused", "orth_mid_max_stages", "force_nonsymmetric" */
+/* keys: "orth", "spmv_format", "profile", "x0_is_zero", "fuse_jacobi", "fuse_iterate", "orth_fused", "force_nonsymmetric",
+ *       "spmv_dual" (A q and ||A x - b|| from one pass), "spmv_multi" (grouped constraint SpMVs), "spmv_variant",
+ *       "pinned_scan_dma", and the tuning knobs "ctas_per_sm", "spmv_ctas_per_sm", "spmv_pipe_ctas_per_sm",
+ *       "spmv_dual_ctas_per_sm", "mdot_variant", "mdot_reg_auto", "mdot_reg_ctas_per_sm", "lincomb_variant",
+ *       "lincomb2_ctas_per_sm", "mdotm_ctas_per_sm", "orth_mid_max_stages", "auto_pattern", "auto_dict", "auto_sell2" */
 int         spis_set_option(spis_ctx* ctx, const char* key, int64_t value);
 int         spis_get_info(const spis_ctx* ctx, const char* key, int64_t* value_out);
 
