@@ -39,6 +39,17 @@ __device__ __forceinline__ double2 ld_keep(const double* p) {
   return __ldg(reinterpret_cast<const double2*>(p));
 }
 
+// SELL-C-sigma, sigma = 256: inside every window of 256 rows the rows are sorted by length (descending, stable),
+// so that the 32 rows of a slice have (nearly) the same length and the slice is not padded to its longest row --
+// swe's velocity block interleaves 16-entry edge rows with 9-entry interior rows and padded 18.7 % unsorted.
+// perm[slot] = position inside the window of the row stored at `slot` (8 bits per row).  The kernels map a slot
+// back with sell_row(); a null perm means "not sorted" (lkdv and every matrix that does not gain 5 %).
+constexpr int kSigma = 256;
+__device__ __forceinline__ int64_t sell_row(const uint8_t* __restrict__ perm, int64_t slot) {
+  return perm ? ((slot & ~(int64_t)(kSigma - 1)) + (int64_t)__ldg(perm + slot)) : slot;
+}
+
+
 // ------------------------------------------------------------------------------------------
 // Cross-GPU exchange over NVLink peer memory (row-sharded runs, one process per GPU).
 // Every rank owns one "comm buffer" (plain cudaMalloc, exported with CUDA IPC) that its peers
@@ -870,7 +881,7 @@ blockdiag_kernel(const double* __restrict__ blk, int64_t nblk, int64_t sb, int64
 // ------------------------------------------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, MODE == 0 ? 8 : 6)   // mode 0: 32 registers, all 2048 threads of an SM resident; the reducing modes spill below 40
-spmv_sell_kernel(const int64_t* __restrict__ slice_off, const int32_t* __restrict__ cols,
+spmv_sell_kernel(const int64_t* __restrict__ slice_off, const uint8_t* __restrict__ perm, const int32_t* __restrict__ cols,
                  const double* __restrict__ vals, int64_t nrows, const double* __restrict__ x,
                  const double* __restrict__ b, double* __restrict__ y,
                  double* __restrict__ partial, unsigned* counter, double* sumsq_out,
@@ -887,7 +898,7 @@ spmv_sell_kernel(const int64_t* __restrict__ slice_off, const int32_t* __restric
       const int width = (int)((__ldg(slice_off + slice + 1) - off) >> 5);
       const int32_t* c = cols + off + lane;
       const double* v = vals + off + lane;
-      const int64_t row = (slice << 5) + lane;
+      const int64_t row = sell_row(perm, (slice << 5) + lane);
       double bv = 0.0;                               // issued with the first matrix loads, not after the last fma
       if (MODE != 0 && row < nrows) bv = __ldg(b + row);
       double acc0 = 0.0, acc1 = 0.0;
@@ -1313,7 +1324,7 @@ __global__ void dict_encode_kernel(const double* __restrict__ vals, const int64_
 // (ptxas: the reducing modes need 40 registers; at 32 they spilled 60 bytes and ran 261 instead of 210 us on swe)
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, MODE == 0 ? 8 : 6)
-spmv_selld_kernel(const int64_t* __restrict__ slice_off, const int64_t* __restrict__ code_off,
+spmv_selld_kernel(const int64_t* __restrict__ slice_off, const uint8_t* __restrict__ perm, const int64_t* __restrict__ code_off,
                   const int32_t* __restrict__ cols, const uint32_t* __restrict__ codes,
                   const double* __restrict__ table, int64_t nrows,
                   const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ y,
@@ -1333,7 +1344,7 @@ spmv_selld_kernel(const int64_t* __restrict__ slice_off, const int64_t* __restri
       const int width = (int)((__ldg(slice_off + slice + 1) - off) >> 5);
       const int32_t* c = cols + off + lane;
       const uint32_t* v = codes + __ldg(code_off + slice) + lane;
-      const int64_t row = (slice << 5) + lane;
+      const int64_t row = sell_row(perm, (slice << 5) + lane);
       double bv = 0.0;
       if (MODE != 0 && row < nrows) bv = __ldg(b + row);
       double acc0 = 0.0, acc1 = 0.0;
@@ -1406,7 +1417,7 @@ __device__ __forceinline__ void sell_issue(SellChunk<CODED>& ch, const int32_t* 
 
 template <int MODE, bool CODED>
 __global__ void __launch_bounds__(kThreads, 4)
-spmv_sellp_kernel(const int64_t* __restrict__ slice_off, const int64_t* __restrict__ code_off,
+spmv_sellp_kernel(const int64_t* __restrict__ slice_off, const uint8_t* __restrict__ perm, const int64_t* __restrict__ code_off,
                   const int32_t* __restrict__ cols, const double* __restrict__ vals,
                   const uint32_t* __restrict__ codes, const double* __restrict__ table, int64_t nrows,
                   const double* __restrict__ x, const double* __restrict__ b, double* __restrict__ y,
@@ -1436,7 +1447,7 @@ spmv_sellp_kernel(const int64_t* __restrict__ slice_off, const int64_t* __restri
     SellChunk<CODED> nx;
     sell_issue<CODED>(nx, cols, vals, codes, offA, coA, 0, widthA, lane);
     for (;;) {
-      const int64_t row = (sA << 5) + lane;
+      const int64_t row = sell_row(perm, (sA << 5) + lane);
       double bv = 0.0;
       if (MODE != 0 && row < nrows) bv = __ldg(b + row);
       double acc0 = 0.0, acc1 = 0.0;
@@ -1572,7 +1583,7 @@ spmv_pattern_dual_kernel(const uint16_t* __restrict__ pid, int W, const int32_t*
 // SELL-32 (CODED = false: 8-byte values) and SELLD (CODED = true: 8-bit codes + dictionary in shared memory)
 template <bool CODED>
 __global__ void __launch_bounds__(kThreads, CODED ? 5 : 4)
-spmv_sell_dual_kernel(const int64_t* __restrict__ slice_off, const int64_t* __restrict__ code_off,
+spmv_sell_dual_kernel(const int64_t* __restrict__ slice_off, const uint8_t* __restrict__ perm, const int64_t* __restrict__ code_off,
                       const int32_t* __restrict__ cols, const double* __restrict__ vals,
                       const uint32_t* __restrict__ codes, const double* __restrict__ table, int64_t nrows,
                       const double* __restrict__ x1, double* __restrict__ y1,
@@ -1596,7 +1607,7 @@ spmv_sell_dual_kernel(const int64_t* __restrict__ slice_off, const int64_t* __re
       const int32_t* c = cols + off + lane;
       const double* v = CODED ? nullptr : vals + off + lane;
       const uint32_t* q = CODED ? codes + __ldg(code_off + slice) + lane : nullptr;
-      const int64_t row = (slice << 5) + lane;
+      const int64_t row = sell_row(perm, (slice << 5) + lane);
       double bv = 0.0;
       if (row < nrows) bv = __ldg(b + row);
       double a0 = 0.0, a1 = 0.0, r0 = 0.0, r1 = 0.0;
@@ -1687,7 +1698,7 @@ spmv_pattern_multi_kernel(const uint16_t* __restrict__ pid, int W, const int32_t
 
 template <bool CODED, int NV>
 __global__ void __launch_bounds__(kThreads, NV == 2 ? 5 : 4)
-spmv_sell_multi_kernel(const int64_t* __restrict__ slice_off, const int64_t* __restrict__ code_off,
+spmv_sell_multi_kernel(const int64_t* __restrict__ slice_off, const uint8_t* __restrict__ perm, const int64_t* __restrict__ code_off,
                        const int32_t* __restrict__ cols, const double* __restrict__ vals,
                        const uint32_t* __restrict__ codes, const double* __restrict__ table, int64_t nrows,
                        const double* __restrict__ x, int64_t xstride, double* __restrict__ y, int64_t ystride) {
@@ -1707,7 +1718,7 @@ spmv_sell_multi_kernel(const int64_t* __restrict__ slice_off, const int64_t* __r
       const int32_t* c = cols + off + lane;
       const double* vp = CODED ? nullptr : vals + off + lane;
       const uint32_t* q = CODED ? codes + __ldg(code_off + slice) + lane : nullptr;
-      const int64_t row = (slice << 5) + lane;
+      const int64_t row = sell_row(perm, (slice << 5) + lane);
       double a0[NV], a1[NV];
 #pragma unroll
       for (int v = 0; v < NV; ++v) { a0[v] = 0.0; a1[v] = 0.0; }
@@ -1813,6 +1824,28 @@ __global__ void remap_cols_kernel(int32_t* __restrict__ cols, int64_t nnz, int32
   }
 }
 
+// one CTA of 256 threads per window: rank of every row by (length desc, index asc), perm, slice widths
+__global__ void __launch_bounds__(kSigma)
+sell_sigma_kernel(const int32_t* __restrict__ indptr, int64_t nrows, uint8_t* __restrict__ perm,
+                  int32_t* __restrict__ width) {
+  __shared__ int slen[kSigma];
+  const int t = threadIdx.x;
+  const int64_t base = (int64_t)blockIdx.x * kSigma;
+  const int64_t row = base + t;
+  const int len = row < nrows ? indptr[row + 1] - indptr[row] : -1;     // rows beyond the end sort last
+  slen[t] = len;
+  __syncthreads();
+  int rank = 0;
+  for (int u = 0; u < kSigma; ++u) {
+    const int lu = slen[u];
+    rank += (lu > len || (lu == len && u < t)) ? 1 : 0;
+  }
+  perm[base + rank] = (uint8_t)t;
+  const int64_t nslices = (nrows + 31) >> 5;
+  const int64_t slice = (base >> 5) + (rank >> 5);
+  if ((rank & 31) == 0 && slice < nslices) width[slice] = len > 0 ? len : 0;   // first (longest) row of its slice
+}
+
 __global__ void sell_width_kernel(const int32_t* __restrict__ indptr, int64_t nrows, int32_t* __restrict__ width) {
   const int64_t slice = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -1828,13 +1861,13 @@ __global__ void sell_width_kernel(const int32_t* __restrict__ indptr, int64_t nr
 
 __global__ void sell_fill_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ cols_in,
                                  const double* __restrict__ vals_in, int64_t nrows,
-                                 const int64_t* __restrict__ slice_off, int32_t* __restrict__ cols,
-                                 double* __restrict__ vals) {
+                                 const int64_t* __restrict__ slice_off, const uint8_t* __restrict__ perm,
+                                 int32_t* __restrict__ cols, double* __restrict__ vals) {
   const int64_t slice = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int64_t nslices = (nrows + 31) >> 5;
   if (slice >= nslices) return;
-  const int64_t row = (slice << 5) + lane;
+  const int64_t row = sell_row(perm, (slice << 5) + lane);
   const int64_t off = slice_off[slice];
   const int width = (int)((slice_off[slice + 1] - off) >> 5);
   int32_t p0 = 0, len = 0;

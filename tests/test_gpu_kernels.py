@@ -440,3 +440,39 @@ def test_constraint_stage_multi_vector_spmv_is_bit_identical(fmt):
     assert np.max(np.abs(t2 - ref2)) <= 1e-13 * np.max(np.abs(ref2))
     assert np.max(np.abs(t1 - ref1)) <= 1e-12 * np.max(np.abs(ref1))
     assert abs(t0 - (0.5 * x0 @ (L @ x0) + v @ x0 + 0.25)) <= 1e-13 * max(1.0, abs(t0))
+
+
+@pytest.mark.parametrize("fmt", [nat.FMT_SELL, nat.FMT_SELLD])
+def test_sell_sigma_row_sorting(fmt):
+    """SELL-C-sigma (option sell_sigma, sigma = 256): rows sorted by length inside windows of 256 so that a slice is
+    not padded to its longest row.  Applied only when it removes >= 5 % of the stored entries (swe: 16- and 9-entry
+    rows interleaved; ragged rows).  A row keeps its entries in order; which of the two accumulators a trailing
+    entry lands in depends on the slice width, so results agree with the unsorted storage to rounding."""
+    from structurepreservingiterativesolvers_b200.problems import swe
+    rng = np.random.default_rng(31)
+    mats = [(swe.linforms(M=40, mlength=32.0)[0]["A"], True)]
+    R = ragged_matrix(4097, seed=5)
+    R.data[:] = rng.integers(-5, 6, size=R.nnz).astype(np.float64)
+    mats.append((R, True))
+    mats.append((lkdv.linforms(space="CG", M=33_350, mlength=0.8 * 33_350)[0]["A"], False))   # uniform rows: left alone
+    for A, expect_gain in mats:
+        n = A.shape[0]
+        b, x0 = rng.standard_normal(n), rng.standard_normal(n)
+        out = []
+        for sigma in (1, 0):
+            with KrylovContext(n, 2) as ctx:
+                ctx.set_option("spmv_format", fmt)
+                ctx.set_option("sell_sigma", sigma)
+                ctx.upload_matrix(nat.SLOT_A, A)
+                assert ctx.info(f"fmt:{nat.SLOT_A}") == fmt
+                out.append(_modes_through_abi(ctx, A, b, x0) + (ctx.info(f"nnz_padded:{nat.SLOT_A}"),))
+        scale = np.abs(A) @ np.abs(x0) + 1e-300
+        assert np.max(np.abs(out[0][0] - out[1][0]) / scale) <= 1e-15
+        assert np.max(np.abs(out[0][0] - A @ x0) / scale) <= 1e-14
+        ref = np.linalg.norm(b - A @ x0)
+        for y, beta, res, padded in out:
+            assert abs(beta - ref) <= 1e-13 * ref and abs(res - ref) <= 1e-13 * ref
+        if expect_gain:
+            assert out[0][3] <= 0.95 * out[1][3] and out[0][3] >= A.nnz
+        else:
+            assert out[0][3] == out[1][3]
