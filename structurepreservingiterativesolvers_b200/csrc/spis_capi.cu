@@ -90,8 +90,11 @@ struct spis_ctx {
                                 // Off by default: on swe it removes the 18.7 % padding (148.4 M -> 126.5 M entries) and the kernels that
                                 // only READ rows gain (mode 2: 211 -> 203 us, pipelined SELL 308 -> 288 us), but every kernel that
                                 // STORES y now scatters 8-byte stores over its 2 KB window (SELLD mode 0: 227 -> 278 us, the grouped
-                                // constraint SpMV 1.98 -> 2.55 ms per solve): 22.6 -> 23.3 ms per swe solve.  Needs y un-permuted
-                                // through shared memory per CTA before it pays.
+                                // constraint SpMV 1.98 -> 2.55 ms per solve): 22.6 -> 23.3 ms per swe solve.  Un-permuting y through
+                                // shared memory (one contiguous 2 KB store per CTA; built, 342 GPU tests green) did not rescue it
+                                // either: 23.7 ms -- rows sorted by length sit next to rows of the same TYPE from a 1.7x wider span,
+                                // and the x gathers of a slice touch more lines; on this L1-bound kernel that outweighs 18.7 %
+                                // fewer entries.
   int spmv_multi = 1;           // constraint stage: M z_j for a group of 2 / 4 Krylov columns from one pass over M
   int spmv_dual = 1;            // A q_{j+2} and ||A x_j - b|| from one pass over A (spis_arnoldi_begin_residual)
   int spmv_dual_ctas_per_sm = 0;
