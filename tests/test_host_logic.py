@@ -315,3 +315,29 @@ def test_givens_least_squares_matches_lstsq():
         assert y is not None and np.max(np.abs(y - ref)) <= 1e-12 * np.max(np.abs(ref))
         assert abs(arn.ls_residual() - arn.predicted_residual(y, beta)) <= 1e-10 * beta
     assert arn.ls_solution(5) is None                      # only for the column count just stored
+
+
+def test_session_update_and_evolve_gmres():
+    """DeviceSession.update: new right-hand side / guess / constraint scalars on a resident system; wrappers.evolve
+    in its GMRES flavour (the comparison lkdv/Evolve.py:72-86 makes)."""
+    spec, dic, prob, x0, pre = cases.instantiate("lkdv_cg_tol6")
+    cl = wrappers.lkdv.conlist(dic, x0)
+    sess = solvers.DeviceSession(dic["A"], dic["b"], x0, 40, conlist=cl, ctx_factory=FakeKrylovContext)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        xa, _ = solvers.cgmres(dic["A"], dic["b"], x0, 40, tol=1e-8, conlist=cl, session=sess, small_solver="kkt")
+        xa = np.array(xa)
+        b2 = 2.0 * dic["b"]
+        sess.update(b=b2, x0=0.1 * xa, constants=[2.0 * c.c if i == 0 else 4.0 * c.c for i, c in enumerate(cl)])
+        xb, _ = solvers.cgmres(dic["A"], b2, 0.1 * xa, 40, tol=1e-8, conlist=cl, session=sess, small_solver="kkt")
+    # the doubled system with consistently scaled invariants (mass linear, the others quadratic) has the doubled solution
+    assert np.linalg.norm(xb - 2.0 * xa) <= 1e-7 * np.linalg.norm(xa)
+    with pytest.raises(ValueError):
+        sess.update(constants=[1.0])
+    sess.close()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = wrappers.evolve(N=100, M=20, k=30, tol=1e-8, steps=3, solver="gmres", ctx_factory=FakeKrylovContext)
+    assert len(out["sol"]) == 4 and len(out["steps"]) == 3 and out["dm"][0] == 0
+    with pytest.raises(ValueError):
+        wrappers.evolve(solver="direct")
