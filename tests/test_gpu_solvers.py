@@ -366,3 +366,29 @@ def test_lkdvrk_structured_constraints_match_the_callbacks(engine, golden):
     z1 = wrappers.lkdvRK._rk.z1calc(prob, x, dic["z0"])
     assert abs(dic["omega"] @ z1 - dic["m0"]) <= 1e-12 * max(1.0, abs(dic["m0"]))
     assert abs(0.5 * z1 @ (dic["M"] @ z1) - dic["mo0"]) <= 1e-12 * max(1.0, abs(dic["mo0"]))
+
+
+def test_long_krylov_space_beyond_the_staged_kernels():
+    """72 Krylov vectors: past the 53 rows the TMA-staged middle pass can hold (two-kernel fallback), past the 40 rows
+    of the register-sum dots, constraint terms for m = 72.  An ill-conditioned system (lkdv P1 on the reference's
+    fixed domain, n = 6000) that uses every step; against the oracle."""
+    dic, _ = lkdv.linforms(space="CG", M=2000)
+    x0 = np.zeros(dic["b"].size)
+    cl = wrappers.lkdv.conlist(dic, x0)
+    k = 72
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        xg, ig = solvers.gmres(dic["A"], dic["b"], x0, k, tol=1e-50)
+        xo, io = orc.fgmres(dic["A"], dic["b"], x0, k, tol=1e-50)
+        xc, ic = solvers.cgmres(dic["A"], dic["b"], x0, k, tol=1e-13, contol=10, conlist=cl, small_solver="kkt")
+        xr, ir = orc.cgmres(dic["A"], dic["b"], x0, k, tol=1e-13, contol=10, conlist=cl)
+    assert ig["steps"] == io["steps"] == k and ic["steps"] == ir["steps"] == k
+    assert helpers.rel_diff(xg, xo) <= 1e-9
+    assert helpers.rel_diff(xc, xr) <= 1e-9
+    res = np.asarray(ig["res"])
+    assert np.all(res[1:] <= res[:-1] * (1 + 1e-8))                  # GMRES residuals never grow
+    # (the history flattens at the rounding floor of this ill-conditioned system, 7.8e-7: compare absolutely there)
+    np.testing.assert_allclose(ig["res"], io["res"], rtol=1e-6, atol=1e-8 * res[0])
+    inv = lkdv.compute_invariants(dic, xc)
+    scale = abs(dic["mo0"]) + abs(dic["e0"]) + abs(dic["m0"])
+    assert max(abs(inv["mass"] - dic["m0"]), abs(inv["momentum"] - dic["mo0"]), abs(inv["energy"] - dic["e0"])) <= 1e-11 * scale
