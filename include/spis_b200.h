@@ -199,6 +199,14 @@ int spis_constraint_setup_async(spis_ctx* ctx, int c, int64_t nrows, int64_t nco
                                 const double* v, double cc);
 int spis_constraint_setup_wait(spis_ctx* ctx);
 
+/* ---- the k-dimensional constrained minimisation (HOST code: solvers.py:251-255 keeps it off the device) ------
+ * min_y |beta e1 - H y|^2 subject to term0[c] + term1[c].y + y'term2[c] y = 0, c < nc (the reduced quadratic
+ * invariants of spis_constraint_terms); H is (m+1) x m row-major with row stride ldh.  Newton on the KKT system in
+ * QR coordinates (the caller settles the signs for the reference's signed 1e-12 acceptance test).  *handled = 0: not the
+ * plain converged case -- use the general (Python) solver; y_out is then untouched.                            */
+int spis_small_kkt(int m, int ldh, const double* H, double beta, int nc, const double* term0, const double* term1,
+                   const double* term2, double* y_out, double* fval_out, int* nit_out, int* handled);
+
 /* ---- downloads / host bridges ------------------------------------------------------- */
 int spis_download_vec(spis_ctx* ctx, int which, int j, double* host, int64_t n);
 /* rows z[j0..j1) as a (j1-j0) x n row-major block (dict-form constraints need Z on the

@@ -14,8 +14,12 @@ quadratic constraints  g_c(y) = term0 + term1.y + y^T term2 y = 0:
 """
 from __future__ import annotations
 
+import ctypes as _C
+
 import numpy as np
 import scipy.optimize as spo
+
+from . import _native as _nat
 
 SUCCESS_MESSAGE = "Optimization terminated successfully"
 _QUIET_MESSAGES = (SUCCESS_MESSAGE,
@@ -104,6 +108,9 @@ def kkt(Hj, beta, y0, constraints=(), max_newton=40):
     available), which still converges because they are quadratics of tiny curvature * lambda.
     """
     m = Hj.shape[1]
+    native = _kkt_native(Hj, beta, constraints)
+    if native is not None:
+        return native
     rhs = np.zeros(Hj.shape[0])
     rhs[0] = beta
     Q, R = np.linalg.qr(Hj)                       # reduced: Q (m+1, m), R (m, m)
@@ -187,6 +194,39 @@ def kkt(Hj, beta, y0, constraints=(), max_newton=40):
         y = _settle_signs(y, cons)
     msg = SUCCESS_MESSAGE if converged else "Iteration limit reached"
     return SmallResult(y, message=msg, success=converged, nit=nit, fun=fval)
+
+
+NATIVE_KKT = True          # tests switch this off to compare the two implementations
+
+
+def _kkt_native(Hj, beta, constraints):
+    """The plain case -- all constraints class-form quadratics, Newton converging from the least-squares start --
+    in C++ (spis_small_kkt: same algorithm, ~20 us instead of 0.4-1.2 ms of numpy calls; this solve sits on the
+    critical path of every constrained iteration with the GPU idle).  None: not handled, take the route below."""
+    if not NATIVE_KKT:
+        return None
+    cons = list(constraints)
+    m = Hj.shape[1]
+    if m < 1 or not cons or not all(c.quadratic for c in cons):
+        return None
+    try:
+        lib = _nat.load_library()
+    except Exception:
+        return None
+    H = np.ascontiguousarray(Hj, dtype=np.float64)
+    nc = len(cons)
+    t0 = np.array([float(c.term0) for c in cons], dtype=np.float64)
+    t1 = np.ascontiguousarray(np.stack([np.asarray(c.term1, dtype=np.float64).reshape(m) for c in cons]))
+    t2 = np.ascontiguousarray(np.stack([np.asarray(c.term2, dtype=np.float64).reshape(m, m) for c in cons]))
+    y = np.empty(m)
+    fval = _C.c_double(0.0)
+    nit, handled = _C.c_int(0), _C.c_int(0)
+    rc = lib.spis_small_kkt(m, m, _nat.dptr(H), float(beta), nc, _nat.dptr(t0), _nat.dptr(t1), _nat.dptr(t2),
+                            _nat.dptr(y), _C.byref(fval), _C.byref(nit), _C.byref(handled))
+    if rc != _nat.OK or not handled.value:
+        return None
+    # the signs are settled HERE, with the very evaluation the acceptance test of solvers.py:266 uses
+    return SmallResult(_settle_signs(y, cons), message=SUCCESS_MESSAGE, success=True, nit=nit.value, fun=fval.value)
 
 
 def _settle_signs(y, cons, tries=8):

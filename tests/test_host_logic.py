@@ -341,3 +341,39 @@ def test_session_update_and_evolve_gmres():
     assert len(out["sol"]) == 4 and len(out["steps"]) == 3 and out["dm"][0] == 0
     with pytest.raises(ValueError):
         wrappers.evolve(solver="direct")
+
+
+def test_native_kkt_matches_the_python_solver():
+    """spis_small_kkt (C++, host code of the library) against smallsolve.kkt's numpy implementation: same Newton
+    iteration, same answer to rounding; whatever is not the plain converged case is declined (handled = 0) and stays
+    with the Python solver."""
+    rng = np.random.default_rng(11)
+    for m, nc in ((3, 1), (7, 2), (12, 3), (25, 2), (50, 2)):
+        H = np.triu(rng.standard_normal((m + 1, m)), -1) + 3 * np.eye(m + 1, m)
+        beta = 1.7
+        y_ls = np.linalg.lstsq(H, np.r_[beta, np.zeros(m)], rcond=None)[0]
+        cons = []
+        for _ in range(nc):
+            S = rng.standard_normal((m, m)); T2 = 0.01 * (S + S.T)
+            t1 = rng.standard_normal(m)
+            t0 = -(t1 @ y_ls + y_ls @ T2 @ y_ls) + 1e-4 * rng.standard_normal()
+            cons.append(smallsolve.ReducedConstraint(t0, t1, T2))
+        Hbig = np.zeros((m + 5, m + 3)); Hbig[: m + 1, :m] = H                   # a strided view, as the solvers pass it
+        view = Hbig[: m + 1, :m]
+        try:
+            smallsolve.NATIVE_KKT = False
+            ref = smallsolve.kkt(view, beta, np.zeros(m), cons)
+            smallsolve.NATIVE_KKT = True
+            assert smallsolve._kkt_native(view, beta, cons) is not None          # the plain case is taken natively
+            out = smallsolve.kkt(view, beta, np.zeros(m), cons)
+        finally:
+            smallsolve.NATIVE_KKT = True
+        assert ref.success and out.success
+        assert np.linalg.norm(out.x - ref.x) <= 1e-12 * np.linalg.norm(ref.x)
+        assert max(abs(c.fun(out.x)) for c in cons) <= 1e-12
+    # declined: opaque callbacks, and an infeasible pair of constraints (Newton cannot converge)
+    cb = smallsolve.ReducedConstraint(callbacks={"func": lambda y, x0, Z: y[0] - 1.0, "jac": lambda y, x0, Z: np.eye(1, m)[0]}, x0=None, Z=None)
+    assert smallsolve._kkt_native(H, beta, [cb]) is None
+    t1 = rng.standard_normal(m)
+    bad = [smallsolve.ReducedConstraint(1.0, t1, np.zeros((m, m))), smallsolve.ReducedConstraint(-1.0, t1, np.zeros((m, m)))]
+    assert smallsolve._kkt_native(H, beta, bad) is None
