@@ -34,7 +34,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define SPIS_ABI_VERSION 3
+#define SPIS_ABI_VERSION 4
 
 /* error codes */
 #define SPIS_OK            0
@@ -179,9 +179,34 @@ int spis_iterate_residual_wait(spis_ctx* ctx, double* resnorm_out);
 /* only x = x0 + Z[:, :m] y (lazy re-materialisation of dict['x'][j], solvers.py:318)    */
 int spis_form_iterate(spis_ctx* ctx, int m, const double* y);
 
+/* ---- pipelined loop: whole Arnoldi steps queued ahead, Givens update + y on the device --------------------------
+ * Replaces, for the unconstrained phase (solvers.py:230-235), the per-iteration host round trip "Hessenberg column
+ * down, coefficients up": a one-warp kernel does the Givens update of solvers.py:113 and the back substitution, the
+ * last Gram-Schmidt sweep of the NEXT step forms x_j = x0 + Z y_j (solvers.py:287) from device-resident y_j, and the
+ * SpMV of the step after measures ||A x_j - b|| (solvers.py:290).  The device also takes the phase decision of
+ * solvers.py:230 (`residual[-1] > contol*tol`) for the steps that are already queued: once a measured residual is
+ * <= thr (or a pivot of the Hessenberg QR vanishes) it stops forming iterates and the host takes over.  h[j+1,j]
+ * comes out of the second Gram-Schmidt reduction (|w'|^2 - |h2|^2), so q[j+1] is written normalised by the last
+ * sweep: no scale pass, no reduction in it.  Records reach the host through mapped page-locked memory.
+ * Needs CGS2, a device preconditioner (or none) and the peer-memory transport (or one GPU): spis_get_info
+ * "device_pipeline".  At most 8 steps / 8 residual measurements may be outstanding.                          */
+int spis_pipe_begin(spis_ctx* ctx, double thr, int phase0);
+/* flags: 1 = the SpMV also measures ||A x - b|| of the iterate in the X buffer (*ticket_out: see spis_resid_wait);
+ *        2 = form an iterate with the device's y if the phase word allows: x_{j-1} from the same sweep over the basis
+ *            (no preconditioner), x_j from a sweep over Z (preconditioned)                                       */
+int spis_step_enqueue(spis_ctx* ctx, int j, int flags, int64_t* ticket_out);
+/* col_out: h[0..j+1, j]; y_out: argmin_y |beta e1 - H_j y| (j+1); info_out[8]: [1] y is valid, [2] the minimum,
+ * [3] h[j+1,j]^2, [4] |w'|^2, [5] |h2|^2, [6] phase word seen by the step's last sweep                           */
+int spis_step_wait(spis_ctx* ctx, int j, double* col_out, double* y_out, double* info_out);
+/* *res2_out = ||A x - b||^2 as reduced on the device (the number compared with thr^2); *go_out = 1 while the phase
+ * word still says "unconstrained"                                                                                  */
+int spis_resid_wait(spis_ctx* ctx, int64_t ticket, double* res2_out, int* go_out);
+
 /* ---- constraint stage (solvers.py:21-36, constraint_container.__init__) ------------- */
 /* class-form constraint c: 1/2 x^T M x + v^T x + cc.  mat_slot < 0: M is identically zero
- * (lkdv/LinearSolver.py:30 `0*A`); v may be NULL, and an all-zero v is recognised and dropped.      */
+ * (lkdv/LinearSolver.py:30 `0*A`); v may be NULL.  On a single GPU an all-zero v is recognised and dropped;
+ * a row-sharded context (halo / collectives configured) keeps whatever it is given, because "v is zero" is a
+ * global property that the caller decides collectively (a rank with an all-zero SLICE still joins the sums). */
 int spis_constraint_define(spis_ctx* ctx, int c, int mat_slot, const double* v, double cc);
 /* term0 (scalar), term1 (m), term2 (m x m row-major) for Z = z[:m].T, incremental in m:
  * MZ = M@Z (:33), term0 (:34), term1 = v@Z + x0@MZ (:35), term2 = 1/2 Z.T@MZ (:36)      */
@@ -243,6 +268,19 @@ int spis_xcomm_create(spis_ctx* ctx, int rank, int world, int64_t halo_cap, void
 int spis_xcomm_connect(spis_ctx* ctx, const void* handles);
 int spis_xcomm_set_halo(spis_ctx* ctx, const int32_t* dest_rank, const int32_t* dest_off,
                         const int32_t* send_to, const int32_t* recv_from);
+/* The same communicator as an object that OUTLIVES the contexts (one per process): created and connected once
+ * (handles all-gathered by the host language as above), then attached to every context of a solver call with
+ * spis_ctx_attach_comm -- nothing is allocated, exchanged, IPC-opened or barriered on the per-call path.  red_cap:
+ * doubles per fused reduction (>= k_max + 5); halo_cap: ghost entries per vector.  spis_comm_allreduce sums `count`
+ * host doubles over all ranks in place (the collective yes/no decisions of a session set-up).                   */
+typedef struct spis_comm spis_comm;
+int spis_comm_create(int device, int rank, int world, int64_t red_cap, int64_t halo_cap, void* handle_out,
+                     int64_t handle_capacity, spis_comm** comm_out);
+int spis_comm_connect(spis_comm* comm, const void* handles);
+int spis_comm_destroy(spis_comm* comm);
+int spis_comm_capacity(const spis_comm* comm, int64_t* red_cap_out, int64_t* halo_cap_out);
+int spis_comm_allreduce(spis_comm* comm, double* vals, int count);
+int spis_ctx_attach_comm(spis_ctx* ctx, spis_comm* comm);
 int spis_sync(spis_ctx* ctx);
 
 /* ---- measurement --------------------------------------------------------------------- */

@@ -8,13 +8,14 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 import numpy as np
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "lib", "libspis_b200.so")
 
 # constants mirrored from include/spis_b200.h
-ABI_VERSION = 3
+ABI_VERSION = 4
 OK, E_INVALID, E_CUDA, E_NOMEM, E_UNSUPPORTED = 0, -1, -2, -3, -4
 SLOT_A, SLOT_PRE, SLOT_CON0, MAX_SLOTS = 0, 1, 2, 18
 VEC_B, VEC_X0, VEC_R0, VEC_Q, VEC_Z, VEC_X, VEC_PRE_DIAG, VEC_W = range(8)
@@ -65,6 +66,10 @@ SIGNATURES = {
     "spis_iterate_residual_launch": (C.c_int, [_ctx, C.c_int, _dp]),
     "spis_iterate_residual_wait": (C.c_int, [_ctx, _dp]),
     "spis_form_iterate": (C.c_int, [_ctx, C.c_int, _dp]),
+    "spis_pipe_begin": (C.c_int, [_ctx, C.c_double, C.c_int]),
+    "spis_step_enqueue": (C.c_int, [_ctx, C.c_int, C.c_int, _lp]),
+    "spis_step_wait": (C.c_int, [_ctx, C.c_int, _dp, _dp, _dp]),
+    "spis_resid_wait": (C.c_int, [_ctx, C.c_int64, _dp, C.POINTER(C.c_int)]),
     "spis_constraint_define": (C.c_int, [_ctx, C.c_int, C.c_int, _dp, C.c_double]),
     "spis_constraint_terms": (C.c_int, [_ctx, C.c_int, C.c_int, _dp, _dp, _dp]),
     "spis_constraint_setup_async": (C.c_int, [_ctx, C.c_int, C.c_int64, C.c_int64, C.c_int64, _ip, _ip, _dp, _dp, C.c_double]),
@@ -80,6 +85,12 @@ SIGNATURES = {
     "spis_xcomm_create": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int64]),
     "spis_xcomm_connect": (C.c_int, [_ctx, C.c_void_p]),
     "spis_xcomm_set_halo": (C.c_int, [_ctx, _ip, _ip, _ip, _ip]),
+    "spis_comm_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]),
+    "spis_comm_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "spis_comm_destroy": (C.c_int, [C.c_void_p]),
+    "spis_comm_capacity": (C.c_int, [C.c_void_p, _lp, _lp]),
+    "spis_comm_allreduce": (C.c_int, [C.c_void_p, _dp, C.c_int]),
+    "spis_ctx_attach_comm": (C.c_int, [_ctx, C.c_void_p]),
     "spis_sync": (C.c_int, [_ctx]),
     "spis_get_profile": (C.c_int, [_ctx, _dp, _dp, _lp]),
     "spis_reset_profile": (C.c_int, [_ctx]),
@@ -167,28 +178,45 @@ class _PinnedOwner:
     """Owns one pooled page-locked buffer; exposes it to numpy through __array_interface__."""
 
     def __init__(self, lib, ptr, n):
-        self._lib, self._ptr = lib, ptr
+        self._lib, self._ptr, self._bytes = lib, ptr, n * 8
         self.__array_interface__ = {"data": (ptr, False), "shape": (n,), "typestr": "<f8", "version": 3}
 
     def __del__(self):  # pragma: no cover - finaliser
+        global _pinned_out
         try:
             self._lib.spis_pinned_free(C.c_void_p(self._ptr))
+            with _pinned_lock:
+                _pinned_out -= self._bytes
         except Exception:
             pass
 
 
-_PINNED_LIMIT = 2 << 30          # bytes of result buffers handed out from the pool at any time
+# Page-locked result buffers are owned by the CALLER once returned (x_last of every solve): a caller that keeps
+# the solution of every time step (the reference's Evolve `sol` list) must not pin unbounded host memory, so the
+# bytes outstanding are counted and requests over the budget get ordinary pageable arrays.
+_PINNED_LIMIT = 2 << 30          # bytes of result buffers handed out from the pool and still alive
 _pinned_out = 0
+_pinned_lock = threading.Lock()
+
+
+def pinned_outstanding() -> int:
+    """Bytes of page-locked result buffers currently owned by callers."""
+    return _pinned_out
 
 
 def pinned_empty(n: int) -> np.ndarray:
     """float64 vector in page-locked memory (falls back to a normal array over the budget)."""
     global _pinned_out
     lib = load_library()
-    if n * 8 > _PINNED_LIMIT:
-        return np.empty(n, dtype=np.float64)
+    nbytes = n * 8
+    with _pinned_lock:
+        if _pinned_out + nbytes > _PINNED_LIMIT:
+            return np.empty(n, dtype=np.float64)
+        _pinned_out += nbytes
     ptr = C.c_void_p()
-    if lib.spis_pinned_alloc(n * 8, C.byref(ptr)) != OK or not ptr.value:
+    if lib.spis_pinned_alloc(nbytes, C.byref(ptr)) != OK or not ptr.value:
+        with _pinned_lock:
+            _pinned_out -= nbytes
         return np.empty(n, dtype=np.float64)
     return np.asarray(_PinnedOwner(lib, ptr.value, n))
 

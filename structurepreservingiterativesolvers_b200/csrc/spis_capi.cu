@@ -67,6 +67,20 @@ struct DevBlock { void* p; size_t bytes; int device; };
 
 extern "C" int spis_device_trim(void);
 
+// NVLink peer-memory communicator that OUTLIVES the contexts (one per process and device): comm buffer, IPC mappings of
+// the peers' buffers and the sequence counters of the flag protocol.  A solver call creates a context and attaches it
+// (spis_ctx_attach_comm): no allocation, handle exchange, cudaIpcOpenMemHandle or barrier on the per-call path.
+struct spis_comm {
+  int device = 0;
+  double* xbuf = nullptr; void* xpeer[kMaxRanks] = {nullptr};
+  XView xv;
+  unsigned long long xseq = 1, hseq = 1;
+  cudaStream_t stream = nullptr;         // for spis_comm_allreduce
+  double* d_tmp = nullptr; double* h_tmp = nullptr;
+  bool connected = false;
+  char err[256] = "";
+};
+
 struct spis_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -133,6 +147,15 @@ struct spis_ctx {
   double* h_cout = nullptr;     // pinned kmax*2K
   cudaEvent_t ev_arnoldi = nullptr;
   cudaEvent_t ev_resid = nullptr; double* h_resid = nullptr; bool resid_inflight = false;   // pinned residual slot of its own
+  // pipelined loop (spis_pipe_begin / spis_step_enqueue): Givens state, least-squares coefficients and the phase word on
+  // the device, per-step and per-residual records in mapped page-locked memory (rings of kRecSlots)
+  double *hs_cs = nullptr, *hs_sn = nullptr, *hs_gv = nullptr, *hs_R = nullptr; int* hs_tracking = nullptr;
+  int* d_phase = nullptr; double* d_ydev = nullptr; double* d_rpartial = nullptr;
+  double* h_rec = nullptr; double* d_rec = nullptr; int rec_stride = 0;
+  unsigned long long rec_counter = 1;
+  unsigned long long step_seq[8] = {0}, res_seq[8] = {0};
+  long long res_tickets = 0;
+  double pipe_thr2 = 0.0; bool pipe_ready = false;
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
   int arnoldi_inflight = -1;
   bool began = false;
@@ -146,7 +169,9 @@ struct spis_ctx {
   bool xactive = false;
   double* xbuf = nullptr; void* xpeer[kMaxRanks] = {nullptr};
   XView xv;
-  unsigned long long xseq = 1, hseq = 1;
+  unsigned long long xseq_own = 1, hseq_own = 1;
+  unsigned long long* xseq_p = &xseq_own; unsigned long long* hseq_p = &hseq_own;   // the attached communicator's counters, if any
+  spis_comm* comm = nullptr;              // attached (not owned) communicator
   int32_t *d_dest_rank = nullptr, *d_dest_off = nullptr, *d_send_to = nullptr, *d_recv_from = nullptr;
   // profiling
   std::vector<ProfRec> recs; std::vector<cudaEvent_t> evpool;
@@ -315,7 +340,7 @@ int grid_for(spis_ctx* ctx, int64_t work_items, int per_sm) {
 // reduction is being batched (constraint stage)
 inline XView fused_view(spis_ctx* ctx) { return (ctx->xactive && !ctx->defer_allreduce) ? ctx->xv : XView(); }
 inline unsigned long long fused_seq(spis_ctx* ctx) {
-  if (ctx->xactive && !ctx->defer_allreduce) return ctx->xseq++;
+  if (ctx->xactive && !ctx->defer_allreduce) return (*ctx->xseq_p)++;
   return 0;
 }
 
@@ -323,9 +348,9 @@ int do_allreduce(spis_ctx* ctx, double* dev, int64_t count, bool force = false) 
   if (ctx->xactive) {
     if (!force) return SPIS_OK;                    // already reduced inside the producing kernel
     const unsigned long long chunks = (unsigned long long)((count + ctx->xv.red_cap - 1) / ctx->xv.red_cap);
-    xreduce_kernel<<<1, kThreads, 0, ctx->stream>>>(dev, count, ctx->xv, ctx->xseq);
+    xreduce_kernel<<<1, kThreads, 0, ctx->stream>>>(dev, count, ctx->xv, *ctx->xseq_p);
     CU(cudaGetLastError());
-    ctx->xseq += chunks;
+    *ctx->xseq_p += chunks;
     ctx->prof_launch[SPIS_PROF_OTHER] += 1;
     return SPIS_OK;
   }
@@ -337,7 +362,7 @@ int do_allreduce(spis_ctx* ctx, double* dev, int64_t count, bool force = false) 
 int do_halo(spis_ctx* ctx, double* vec) {
   if (ctx->xactive) {
     if (ctx->n_halo == 0 && ctx->n_send == 0) return SPIS_OK;
-    const unsigned long long seq = ctx->hseq++;
+    const unsigned long long seq = (*ctx->hseq_p)++;
     if (ctx->n_send > 0) {
       const int64_t g = (ctx->n_send + 255) / 256;
       const int grid = (int)(g < (int64_t)ctx->nsm * 8 ? g : (int64_t)ctx->nsm * 8);
@@ -361,11 +386,29 @@ int do_halo(spis_ctx* ctx, double* vec) {
   return SPIS_OK;
 }
 
+// ghosts of up to two vectors from ONE exchange (peer-memory transport only; b may be null)
+int do_halo2(spis_ctx* ctx, double* a, double* b) {
+  if (!ctx->xactive) {
+    TRY(do_halo(ctx, a));
+    return b ? do_halo(ctx, b) : SPIS_OK;
+  }
+  if (ctx->n_halo == 0 && ctx->n_send == 0) return SPIS_OK;
+  REQUIRE(ctx->xv.halo_cap / 2 >= ctx->n_halo, "comm buffer holds %lld ghost entries per vector, %lld needed", (long long)(ctx->xv.halo_cap / 2), (long long)ctx->n_halo);
+  const unsigned long long seq = (*ctx->hseq_p)++;
+  halo_xchg_kernel<<<1, 1024, 0, ctx->stream>>>(a, b, ctx->hoff, ctx->n_halo, ctx->d_send_idx, ctx->d_dest_rank, ctx->d_dest_off,
+                                                 ctx->n_send, ctx->d_send_to, ctx->d_recv_from, ctx->xv, seq);
+  CU(cudaGetLastError());
+  ctx->prof_launch[SPIS_PROF_OTHER] += 1;
+  return SPIS_OK;
+}
+
 // out[0..m) = V_i.w, then extra.w (if extra), then w.w (if with_sumsq); all-reduced over ranks
 int launch_mdot(spis_ctx* ctx, const double* V, int m, const double* extra, int with_sumsq,
-                const double* w, double* out) {
+                const double* w, double* out, const TailExtra* ride = nullptr) {
   const int nrows = m + (extra ? 1 : 0) + (with_sumsq ? 1 : 0);
   if (nrows == 0) return SPIS_OK;
+  const TailExtra tx = ride ? *ride : TailExtra{};
+  const int nred = nrows + (tx.rpart ? 1 : 0);
   REQUIRE(nrows <= ctx->pstride, "mdot: %d rows exceed workspace %d", nrows, ctx->pstride);
   const int64_t ntiles = (ctx->n + kTile - 1) / kTile;
   // measured on B200 (n = 1e7): few rows want more loads per thread on fewer CTAs, many rows the opposite
@@ -378,12 +421,12 @@ int launch_mdot(spis_ctx* ctx, const double* V, int m, const double* extra, int 
     TRY(prof_begin(ctx, SPIS_PROF_MDOT, (double)(m + (extra ? 1 : 0) + 1) * 8.0 * (double)ctx->n));
     const XView xv = fused_view(ctx);
     const unsigned long long seq = fused_seq(ctx);
-#define SPIS_MDR(MBB) case MBB: mdot_reg_kernel<MBB><<<grid, kThreads, 0, ctx->stream>>>(V, ctx->ld, m, extra, with_sumsq, w, ctx->n, ctx->d_partial, ctx->pstride, ctx->d_counter, out, xv, seq); break;
+#define SPIS_MDR(MBB) case MBB: mdot_reg_kernel<MBB><<<grid, kThreads, 0, ctx->stream>>>(V, ctx->ld, m, extra, with_sumsq, w, ctx->n, ctx->d_partial, ctx->pstride, ctx->d_counter, out, xv, seq, tx); break;
     switch (MB) { SPIS_MDR(8) SPIS_MDR(16) SPIS_MDR(24) SPIS_MDR(32) default: SPIS_MDR(40) }
 #undef SPIS_MDR
     CU(cudaGetLastError());
     TRY(prof_end(ctx));
-    return do_allreduce(ctx, out, nrows);
+    return do_allreduce(ctx, out, nred);
   }
   int variant = ctx->mdot_variant, per_sm = ctx->ctas_per_sm;
   if (variant == 0) { variant = nrows <= 6 ? 4 : 2; per_sm = nrows <= 6 ? (ctx->ctas_per_sm > 2 ? 2 : ctx->ctas_per_sm) : ctx->ctas_per_sm; }
@@ -393,14 +436,14 @@ int launch_mdot(spis_ctx* ctx, const double* V, int m, const double* extra, int 
   const XView xv = fused_view(ctx);
   const unsigned long long seq = fused_seq(ctx);
   if (variant == 8)
-    mdot_kernel<8><<<grid, kThreads, smem, ctx->stream>>>(V, ctx->ld, m, extra, with_sumsq, w, ctx->n, ctx->d_partial, ctx->pstride, ctx->d_counter, out, xv, seq);
+    mdot_kernel<8><<<grid, kThreads, smem, ctx->stream>>>(V, ctx->ld, m, extra, with_sumsq, w, ctx->n, ctx->d_partial, ctx->pstride, ctx->d_counter, out, xv, seq, tx);
   else if (variant == 2)
-    mdot_kernel<2><<<grid, kThreads, smem, ctx->stream>>>(V, ctx->ld, m, extra, with_sumsq, w, ctx->n, ctx->d_partial, ctx->pstride, ctx->d_counter, out, xv, seq);
+    mdot_kernel<2><<<grid, kThreads, smem, ctx->stream>>>(V, ctx->ld, m, extra, with_sumsq, w, ctx->n, ctx->d_partial, ctx->pstride, ctx->d_counter, out, xv, seq, tx);
   else
-    mdot_kernel<4><<<grid, kThreads, smem, ctx->stream>>>(V, ctx->ld, m, extra, with_sumsq, w, ctx->n, ctx->d_partial, ctx->pstride, ctx->d_counter, out, xv, seq);
+    mdot_kernel<4><<<grid, kThreads, smem, ctx->stream>>>(V, ctx->ld, m, extra, with_sumsq, w, ctx->n, ctx->d_partial, ctx->pstride, ctx->d_counter, out, xv, seq, tx);
   CU(cudaGetLastError());
   TRY(prof_end(ctx));
-  return do_allreduce(ctx, out, nrows);
+  return do_allreduce(ctx, out, nred);
 }
 
 // out[c*nrows + i] = row_i . W_c  for nw (2 or 4) vectors W_c = W + c*wstride; rows = V[0..m) (+ extra)
@@ -467,11 +510,11 @@ int launch_lincomb2(spis_ctx* ctx, const double* V, int m, const double* coefA, 
 constexpr size_t kOrthMidSmemBudget = 225 * 1024;
 template <int MB>
 int launch_orth_mid_mb(spis_ctx* ctx, int E, int grid, size_t smem, const double* V, int m, const double* coef,
-                       double* w, int nstages, double* out, const XView& xv, unsigned long long seq) {
+                       double* w, int nstages, double* out, const XView& xv, unsigned long long seq, int with_norm) {
   if (E == 2)
-    orth_mid_kernel<MB, 2><<<grid, kOrthMidThreads, smem, ctx->stream>>>(V, ctx->ld, m, coef, w, ctx->hoff, nstages, ctx->orth_mid_probe, ctx->d_partial, ctx->pstride, ctx->d_counter, out, xv, seq);
+    orth_mid_kernel<MB, 2><<<grid, kOrthMidThreads, smem, ctx->stream>>>(V, ctx->ld, m, coef, w, ctx->hoff, nstages, ctx->orth_mid_probe, with_norm, ctx->d_partial, ctx->pstride, ctx->d_counter, out, xv, seq);
   else
-    orth_mid_kernel<MB, 1><<<grid, kOrthMidThreads, smem, ctx->stream>>>(V, ctx->ld, m, coef, w, ctx->hoff, nstages, ctx->orth_mid_probe, ctx->d_partial, ctx->pstride, ctx->d_counter, out, xv, seq);
+    orth_mid_kernel<MB, 1><<<grid, kOrthMidThreads, smem, ctx->stream>>>(V, ctx->ld, m, coef, w, ctx->hoff, nstages, ctx->orth_mid_probe, with_norm, ctx->d_partial, ctx->pstride, ctx->d_counter, out, xv, seq);
   CU(cudaGetLastError());
   return SPIS_OK;
 }
@@ -493,7 +536,7 @@ bool orth_mid_plan(const spis_ctx* ctx, int m, int* E_out, int* stages_out, int*
   return false;
 }
 
-int launch_orth_mid(spis_ctx* ctx, const double* V, int m, const double* coef, double* w, double* out) {
+int launch_orth_mid(spis_ctx* ctx, const double* V, int m, const double* coef, double* w, double* out, int with_norm = 0) {
   int E = 0, stages = 0, MB = 0; size_t smem = 0;
   if (!orth_mid_plan(ctx, m, &E, &stages, &MB, &smem)) return fail(ctx, SPIS_E_UNSUPPORTED, "orth_mid: m=%d does not fit shared memory", m);
   const int T = kThreads * E;
@@ -504,18 +547,18 @@ int launch_orth_mid(spis_ctx* ctx, const double* V, int m, const double* coef, d
   const unsigned long long seq = fused_seq(ctx);
   int rc;
   switch (MB) {
-    case 8: rc = launch_orth_mid_mb<8>(ctx, E, grid, smem, V, m, coef, w, stages, out, xv, seq); break;
-    case 16: rc = launch_orth_mid_mb<16>(ctx, E, grid, smem, V, m, coef, w, stages, out, xv, seq); break;
-    case 24: rc = launch_orth_mid_mb<24>(ctx, E, grid, smem, V, m, coef, w, stages, out, xv, seq); break;
-    case 32: rc = launch_orth_mid_mb<32>(ctx, E, grid, smem, V, m, coef, w, stages, out, xv, seq); break;
-    case 40: rc = launch_orth_mid_mb<40>(ctx, E, grid, smem, V, m, coef, w, stages, out, xv, seq); break;
-    case 48: rc = launch_orth_mid_mb<48>(ctx, E, grid, smem, V, m, coef, w, stages, out, xv, seq); break;
-    case 56: rc = launch_orth_mid_mb<56>(ctx, E, grid, smem, V, m, coef, w, stages, out, xv, seq); break;
-    default: rc = launch_orth_mid_mb<64>(ctx, E, grid, smem, V, m, coef, w, stages, out, xv, seq); break;
+    case 8: rc = launch_orth_mid_mb<8>(ctx, E, grid, smem, V, m, coef, w, stages, out, xv, seq, with_norm); break;
+    case 16: rc = launch_orth_mid_mb<16>(ctx, E, grid, smem, V, m, coef, w, stages, out, xv, seq, with_norm); break;
+    case 24: rc = launch_orth_mid_mb<24>(ctx, E, grid, smem, V, m, coef, w, stages, out, xv, seq, with_norm); break;
+    case 32: rc = launch_orth_mid_mb<32>(ctx, E, grid, smem, V, m, coef, w, stages, out, xv, seq, with_norm); break;
+    case 40: rc = launch_orth_mid_mb<40>(ctx, E, grid, smem, V, m, coef, w, stages, out, xv, seq, with_norm); break;
+    case 48: rc = launch_orth_mid_mb<48>(ctx, E, grid, smem, V, m, coef, w, stages, out, xv, seq, with_norm); break;
+    case 56: rc = launch_orth_mid_mb<56>(ctx, E, grid, smem, V, m, coef, w, stages, out, xv, seq, with_norm); break;
+    default: rc = launch_orth_mid_mb<64>(ctx, E, grid, smem, V, m, coef, w, stages, out, xv, seq, with_norm); break;
   }
   TRY(rc);
   TRY(prof_end(ctx));
-  return do_allreduce(ctx, out, m);
+  return do_allreduce(ctx, out, m + (with_norm ? 1 : 0));
 }
 
 template <int MODE>
@@ -581,33 +624,44 @@ int launch_spmv(spis_ctx* ctx, int slot, int mode, const double* x, const double
 }
 
 // y1 = A x1 and sumsq = ||A x2 - b||^2 from one pass over the system matrix (formats without a dual kernel: two launches)
-int launch_spmv_dual(spis_ctx* ctx, const double* x1, double* y1, const double* x2, const double* b, double* sumsq_out) {
+// ride_partial != null: the per-CTA partial sums of the norm are left there (*ride_parts of them) for the tail of the
+// next reducing kernel to finish (TailExtra) instead of a reduce_partials launch; formats without a dual kernel finish
+// the norm themselves and report *ride_parts = 0.
+int launch_spmv_dual(spis_ctx* ctx, const double* x1, double* y1, const double* x2, const double* b, double* sumsq_out,
+                     double* ride_partial = nullptr, int* ride_parts = nullptr) {
   const Matrix& M = ctx->mats[SPIS_SLOT_A];
   REQUIRE(M.present, "matrix slot %d has not been uploaded", SPIS_SLOT_A);
   const bool fused = ctx->spmv_dual && (M.fmt == SPIS_FMT_PATTERN || M.fmt == SPIS_FMT_SELL || M.fmt == SPIS_FMT_SELLD);
+  if (ride_parts) *ride_parts = 0;
   if (!fused) {
     TRY(launch_spmv(ctx, SPIS_SLOT_A, 0, x1, nullptr, y1, nullptr));
     return launch_spmv(ctx, SPIS_SLOT_A, 2, x2, b, nullptr, sumsq_out);
   }
+  double* part = ride_partial ? ride_partial : ctx->d_partial;
   const double bytes = 2.0 * (12.0 * (double)M.nnz + 4.0 * (double)(M.nrows + 1) + 16.0 * (double)M.nrows);   // two SpMVs' worth
   TRY(prof_begin(ctx, SPIS_PROF_SPMV, bytes));
-  const XView xv = fused_view(ctx);
-  const unsigned long long seq = fused_seq(ctx);
   int grid = 1;
   if (M.fmt == SPIS_FMT_PATTERN) {
     grid = grid_for(ctx, (M.nrows + kThreads - 1) / kThreads, ctx->spmv_dual_ctas_per_sm > 0 ? ctx->spmv_dual_ctas_per_sm : 6);
     while (grid > 1 && (int64_t)M.nrows + (int64_t)grid * kThreads >= (int64_t)INT32_MAX) grid /= 2;
-#define SPIS_PATD_CASE(NC) case NC: spmv_pattern_dual_kernel<NC><<<grid, kThreads, 0, ctx->stream>>>(M.pid, M.patW, M.tab_off, M.tab_val, (int)M.nrows, x1, y1, x2, b, ctx->d_partial); break;
+#define SPIS_PATD_CASE(NC) case NC: spmv_pattern_dual_kernel<NC><<<grid, kThreads, 0, ctx->stream>>>(M.pid, M.patW, M.tab_off, M.tab_val, (int)M.nrows, x1, y1, x2, b, part); break;
     switch (M.patW / 4) { SPIS_PATD_CASE(1) SPIS_PATD_CASE(2) SPIS_PATD_CASE(3) SPIS_PATD_CASE(4)
-      default: spmv_pattern_dual_kernel<0><<<grid, kThreads, 0, ctx->stream>>>(M.pid, M.patW, M.tab_off, M.tab_val, (int)M.nrows, x1, y1, x2, b, ctx->d_partial); }
+      default: spmv_pattern_dual_kernel<0><<<grid, kThreads, 0, ctx->stream>>>(M.pid, M.patW, M.tab_off, M.tab_val, (int)M.nrows, x1, y1, x2, b, part); }
 #undef SPIS_PATD_CASE
   } else {
     const int64_t nslices = (M.nrows + 31) / 32;
     const bool coded = M.fmt == SPIS_FMT_SELLD;
     grid = grid_for(ctx, (nslices + kWarps - 1) / kWarps, ctx->spmv_dual_ctas_per_sm > 0 ? ctx->spmv_dual_ctas_per_sm : (coded ? 5 : 4));
-    if (coded) spmv_sell_dual_kernel<true><<<grid, kThreads, 0, ctx->stream>>>(M.slice_off, M.rowperm, M.code_off, M.scols, nullptr, M.codes, M.dict, M.nrows, x1, y1, x2, b, ctx->d_partial);
-    else spmv_sell_dual_kernel<false><<<grid, kThreads, 0, ctx->stream>>>(M.slice_off, M.rowperm, nullptr, M.scols, M.svals, nullptr, nullptr, M.nrows, x1, y1, x2, b, ctx->d_partial);
+    if (coded) spmv_sell_dual_kernel<true><<<grid, kThreads, 0, ctx->stream>>>(M.slice_off, M.rowperm, M.code_off, M.scols, nullptr, M.codes, M.dict, M.nrows, x1, y1, x2, b, part);
+    else spmv_sell_dual_kernel<false><<<grid, kThreads, 0, ctx->stream>>>(M.slice_off, M.rowperm, nullptr, M.scols, M.svals, nullptr, nullptr, M.nrows, x1, y1, x2, b, part);
   }
+  if (ride_partial) {
+    CU(cudaGetLastError());
+    if (ride_parts) *ride_parts = grid;
+    return prof_end(ctx);
+  }
+  const XView xv = fused_view(ctx);
+  const unsigned long long seq = fused_seq(ctx);
   reduce_partials_kernel<<<1, kThreads, 0, ctx->stream>>>(ctx->d_partial, grid, sumsq_out, xv, seq);
   CU(cudaGetLastError());
   TRY(prof_end(ctx));
@@ -1194,15 +1248,20 @@ int spis_ctx_destroy(spis_ctx* ctx) {
     dfree(ctx, ctx->d_send_idx); dfree(ctx, ctx->d_send);
     dfree(ctx, ctx->d_dest_rank); dfree(ctx, ctx->d_dest_off); dfree(ctx, ctx->d_send_to); dfree(ctx, ctx->d_recv_from);
     dfree(ctx, ctx->d_small); dfree(ctx, ctx->d_y); dfree(ctx, ctx->d_cout); dfree(ctx, ctx->d_partial); dfree(ctx, ctx->d_counter);
+    dfree(ctx, ctx->hs_cs); dfree(ctx, ctx->hs_sn); dfree(ctx, ctx->hs_gv); dfree(ctx, ctx->hs_R); dfree(ctx, ctx->hs_tracking);
+    dfree(ctx, ctx->d_phase); dfree(ctx, ctx->d_ydev); dfree(ctx, ctx->d_rpartial);
     cudaStreamSynchronize(ctx->stream);
     std::lock_guard<std::mutex> lk(g_dev_mu);
     for (auto& b : ctx->owned) g_dev_free.push_back(b);
     ctx->owned.clear();
   }
-  for (int r = 0; r < kMaxRanks; ++r)
-    if (ctx->xpeer[r]) cudaIpcCloseMemHandle(ctx->xpeer[r]);
-  if (ctx->xbuf) cudaFree(ctx->xbuf);
+  if (!ctx->comm) {
+    for (int r = 0; r < kMaxRanks; ++r)
+      if (ctx->xpeer[r]) cudaIpcCloseMemHandle(ctx->xpeer[r]);
+    if (ctx->xbuf) cudaFree(ctx->xbuf);
+  }
   spis_pinned_free(ctx->h_small); spis_pinned_free(ctx->h_y); spis_pinned_free(ctx->h_cout); spis_pinned_free(ctx->h_resid);
+  spis_pinned_free(ctx->h_rec);
   if (ctx->ev_arnoldi) cudaEventDestroy(ctx->ev_arnoldi);
   if (ctx->ev_resid) cudaEventDestroy(ctx->ev_resid);
   if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
@@ -1282,6 +1341,8 @@ int spis_get_info(const spis_ctx* cctx, const char* key, int64_t* value_out) {
   else if (k == "alloc_misses") *value_out = g_dev_misses.load();
   else if (k == "alloc_miss_bytes") *value_out = g_dev_miss_bytes.load();
   else if (k == "can_fuse_iterate") *value_out = (ctx->fuse_iterate && ctx->orth == SPIS_ORTH_CGS2 && ctx->pre_kind == SPIS_PRE_NONE) ? 1 : 0;
+  else if (k == "pipe_lag") *value_out = ctx->pre_kind == SPIS_PRE_NONE ? 1 : 0;
+  else if (k == "device_pipeline") *value_out = (ctx->orth == SPIS_ORTH_CGS2 && ctx->pre_kind != SPIS_PRE_HOST && !ctx->allreduce && !ctx->halo) ? 1 : 0;
   else if (k == "device_ptr:small") *value_out = (int64_t)(intptr_t)ctx->d_small;
   else if (k == "stream") *value_out = (int64_t)(intptr_t)ctx->stream;
   else if (k == "n_send") *value_out = ctx->n_send;
@@ -1550,6 +1611,7 @@ int spis_solve_begin(spis_ctx* ctx, double* beta_out) {
   ctx->arnoldi_inflight = -1;
   ctx->arnoldi_part1 = -1;
   ctx->resid_inflight = false;
+  ctx->pipe_ready = false;
   return SPIS_OK;
 }
 
@@ -1747,6 +1809,220 @@ int spis_iterate_residual(spis_ctx* ctx, int m, const double* y, double* resnorm
   return spis_iterate_residual_wait(ctx, resnorm_out);
 }
 
+// ---- pipelined Krylov loop -------------------------------------------------------------
+// The host queues whole Arnoldi steps ahead of time; everything an UNCONSTRAINED iteration needs (solvers.py:190-198,
+// 231-235, 287, 290) is computed on the device by kernels that were queued before their inputs existed:
+//   [halo]  one exchange for z_j and the iterate                                            (row-sharded runs)
+//   SpMV    w = A z_j and, in the same pass, ||A x - b||^2 of the iterate in X               (dual kernels)
+//   mdot    h1 = V^T w; its tail also finishes the residual norm, publishes it and flips the phase word
+//   orth    w' = w - V h1, h2 = V^T w', ||w'||^2                                              (one staged pass)
+//   hess    column j = h1 + h2, h[j+1,j]^2 = ||w'||^2 - |h2|^2, Givens update, y_j = argmin |beta e1 - H y|
+//   sweep   q[j+1] = (w' - V h2) / h[j+1,j]  and  x_{j-1} = x0 + Z y_{j-1}                    (lincomb2n_kernel)
+// i.e. four kernels and no host round trip per iteration (six kernels, a D2H, a host solve and an H2D before), and
+// three cross-GPU exchanges instead of six.  The host follows through records in mapped page-locked memory.
+namespace {
+constexpr int kRecSlots = 8;
+
+inline double* step_rec_host(spis_ctx* ctx, int j) { return ctx->h_rec + (size_t)(j % kRecSlots) * ctx->rec_stride; }
+inline double* step_rec_dev(spis_ctx* ctx, int j) { return ctx->d_rec + (size_t)(j % kRecSlots) * ctx->rec_stride; }
+inline double* res_rec_host(spis_ctx* ctx, long long t) { return ctx->h_rec + (size_t)kRecSlots * ctx->rec_stride + (size_t)(t % kRecSlots) * 8; }
+inline double* res_rec_dev(spis_ctx* ctx, long long t) { return ctx->d_rec + (size_t)kRecSlots * ctx->rec_stride + (size_t)(t % kRecSlots) * 8; }
+
+// spin until the device has published sequence word `want` into a mapped record
+int wait_record(spis_ctx* ctx, const double* rec, unsigned long long want, const char* what) {
+  const volatile unsigned long long* w = reinterpret_cast<const volatile unsigned long long*>(rec);
+  const auto t0 = std::chrono::steady_clock::now();
+  unsigned spins = 0;
+  while (*w != want) {
+    if ((++spins & 0xfffu) == 0) {
+      const cudaError_t e = cudaStreamQuery(ctx->stream);
+      if (e != cudaSuccess && e != cudaErrorNotReady)
+        return fail(ctx, SPIS_E_CUDA, "waiting for %s: %s", what, cudaGetErrorString(e));
+      if (e == cudaSuccess && *w != want)
+        return fail(ctx, SPIS_E_INVALID, "%s was never produced (the stream is idle)", what);
+      if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 120.0)
+        return fail(ctx, SPIS_E_CUDA, "timed out waiting for %s", what);
+    }
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  return SPIS_OK;
+}
+}  // namespace
+
+// Device side of the loop after spis_solve_begin: Givens state (g = beta e1), phase word (phase0 = 1: the very first
+// iteration is already constrained, i.e. beta <= contol*tol), threshold thr on the residual NORM below which the
+// device stops forming unconstrained iterates.
+int spis_pipe_begin(spis_ctx* ctx, double thr, int phase0) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(ctx->began, "spis_solve_begin has not been called");
+  REQUIRE(ctx->orth == SPIS_ORTH_CGS2, "the pipelined loop needs CGS2");
+  REQUIRE(ctx->pre_kind != SPIS_PRE_HOST, "the pipelined loop cannot call a host preconditioner");
+  REQUIRE(!ctx->allreduce && !ctx->halo, "the pipelined loop needs the peer-memory transport (or one GPU)");
+  REQUIRE(ctx->arnoldi_inflight < 0 && ctx->arnoldi_part1 < 0 && !ctx->resid_inflight, "an Arnoldi step is in flight");
+  CU(cudaSetDevice(ctx->device));
+  const size_t km = (size_t)ctx->kmax;
+  if (!ctx->hs_R) {
+    TRY(dalloc(ctx, &ctx->hs_cs, km));
+    TRY(dalloc(ctx, &ctx->hs_sn, km));
+    TRY(dalloc(ctx, &ctx->hs_gv, km + 1));
+    TRY(dalloc(ctx, &ctx->hs_R, km * km, false));
+    TRY(dalloc(ctx, &ctx->hs_tracking, 4));
+    TRY(dalloc(ctx, &ctx->d_phase, 4));
+    TRY(dalloc(ctx, &ctx->d_ydev, (size_t)2 * ctx->K));
+    TRY(dalloc(ctx, &ctx->d_rpartial, (size_t)ctx->max_grid));
+  }
+  if (!ctx->h_rec) {
+    ctx->rec_stride = 2 * ctx->K + 8;
+    const size_t bytes = ((size_t)kRecSlots * ctx->rec_stride + (size_t)kRecSlots * 8) * sizeof(double);
+    if (spis_pinned_alloc(bytes, (void**)&ctx->h_rec) != SPIS_OK) return fail(ctx, SPIS_E_NOMEM, "pinned record buffer: %s", g_global_err);
+    void* dp = nullptr;
+    if (cudaHostGetDevicePointer(&dp, ctx->h_rec, 0) != cudaSuccess) { cudaGetLastError(); dp = ctx->h_rec; }   // unified addressing: same pointer
+    ctx->d_rec = static_cast<double*>(dp);
+    memset(ctx->h_rec, 0, bytes);
+  }
+  for (int i = 0; i < kRecSlots; ++i) { ctx->step_seq[i] = 0; ctx->res_seq[i] = 0; }
+  ctx->res_tickets = 0;
+  ctx->pipe_thr2 = thr * thr;
+  HessState st{ctx->hs_cs, ctx->hs_sn, ctx->hs_gv, ctx->hs_R, ctx->hs_tracking, ctx->kmax};
+  pipe_init_kernel<<<1, 32, 0, ctx->stream>>>(st, ctx->d_small + 2 * ctx->K + 1, ctx->d_phase, phase0 ? 1 : 0);
+  CU(cudaGetLastError());
+  ctx->prof_launch[SPIS_PROF_OTHER] += 1;
+  ctx->pipe_ready = true;
+  return SPIS_OK;
+}
+
+// Queue Arnoldi step j.  flags & 1: the SpMV also measures ||A x - b|| of the iterate in X (*ticket_out identifies the
+// record, spis_resid_wait).  flags & 2: form an iterate with the device's least-squares coefficients if the phase word
+// still says "unconstrained": x_{j-1} (from the same sweep, no preconditioner) or x_j (a sweep over Z, preconditioned).
+int spis_step_enqueue(spis_ctx* ctx, int j, int flags, int64_t* ticket_out) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(ctx->pipe_ready, "spis_pipe_begin has not been called for this solve");
+  REQUIRE(j >= 0 && j < ctx->kmax, "Arnoldi index %d out of range [0,%d)", j, ctx->kmax);
+  REQUIRE(!ctx->resid_inflight || !(flags & 1), "an iterate/residual pair is still in flight");
+  CU(cudaSetDevice(ctx->device));
+  const int m = j + 1;
+  const int K = ctx->K;
+  const size_t ld = (size_t)ctx->ld;
+  const bool nopre = ctx->pre_kind == SPIS_PRE_NONE;
+  const bool want_res = (flags & 1) != 0, want_it = (flags & 2) != 0;
+  double* qj = ctx->V + (size_t)j * ld;
+  double* qn = ctx->V + (size_t)(j + 1) * ld;
+  double* zj = zbase(ctx) + (size_t)j * ld;
+  double* h1 = ctx->d_small;
+  double* h2 = ctx->d_small + K;
+  double* scal = ctx->d_small + 2 * K;
+  if (ticket_out) *ticket_out = -1;
+  // z[j] = P q[j]                                                  (solvers.py:190)
+  if (!nopre && ctx->z_ready_index != j) TRY(launch_precond(ctx, qj, zj));
+  TRY(do_halo2(ctx, zj, want_res ? ctx->X : nullptr));
+  // w = A z[j]  (+ ||A x - b||^2)                                   (solvers.py:191, 290)
+  TailExtra tx{};
+  bool rides = false;
+  if (want_res) {
+    const long long t = ctx->res_tickets++;
+    const unsigned long long sw = ctx->rec_counter++;
+    ctx->res_seq[t % kRecSlots] = sw;
+    *reinterpret_cast<volatile unsigned long long*>(res_rec_host(ctx, t)) = 0ull;
+    tx.res_out = scal + 2; tx.host_rec = res_rec_dev(ctx, t); tx.rec_seq = sw; tx.phase = ctx->d_phase; tx.thr2 = ctx->pipe_thr2;
+    int parts = 0;
+    TRY(launch_spmv_dual(ctx, zj, ctx->W, ctx->X, ctx->B, scal + 2, ctx->d_rpartial, &parts));
+    if (parts > 0) { tx.rpart = ctx->d_rpartial; tx.nrpart = parts; rides = true; }
+    else {
+      publish_res_kernel<<<1, 32, 0, ctx->stream>>>(scal + 2, tx);       // the norm is complete (and all-reduced) already
+      CU(cudaGetLastError());
+      ctx->prof_launch[SPIS_PROF_OTHER] += 1;
+    }
+    if (ticket_out) *ticket_out = (int64_t)t;
+  } else {
+    TRY(launch_spmv(ctx, SPIS_SLOT_A, 0, zj, nullptr, ctx->W, nullptr));
+  }
+  // CGS2: h1 = V^T w ; w' = w - V h1, h2 = V^T w', ||w'||^2        (solvers.py:193-196)
+  TRY(launch_mdot(ctx, ctx->V, m, nullptr, 0, ctx->W, h1, rides ? &tx : nullptr));
+  int E_ = 0, st_ = 0, mb_ = 0; size_t sm_ = 0;
+  if (ctx->orth_fused && orth_mid_plan(ctx, m, &E_, &st_, &mb_, &sm_)) {
+    TRY(launch_orth_mid(ctx, ctx->V, m, h1, ctx->W, h2, 1));
+  } else {
+    TRY(launch_lincomb(ctx, ctx->V, m, h1, nullptr, -1.0, ctx->W, ctx->W, 0, nullptr));
+    TRY(launch_mdot(ctx, ctx->V, m, nullptr, 1, ctx->W, h2));              // h2[m] = w'.w'
+  }
+  // column j, h[j+1,j], Givens update, y_j                          (solvers.py:113 / 231-235)
+  {
+    const unsigned long long sw = ctx->rec_counter++;
+    ctx->step_seq[j % kRecSlots] = sw;
+    *reinterpret_cast<volatile unsigned long long*>(step_rec_host(ctx, j)) = 0ull;
+    HessState st{ctx->hs_cs, ctx->hs_sn, ctx->hs_gv, ctx->hs_R, ctx->hs_tracking, ctx->kmax};
+    const size_t smem = (size_t)(2 * K + 4) * sizeof(double);
+    const unsigned long long* errw = ctx->xactive ? reinterpret_cast<const unsigned long long*>(ctx->xbuf + ctx->xv.flags_off()) + 4 * ctx->xv.world : nullptr;
+    hess_kernel<<<1, 32, smem, ctx->stream>>>(j, st, h1, h2, scal, ctx->d_ydev + (size_t)(j & 1) * K, ctx->d_phase,
+                                               step_rec_dev(ctx, j), sw, K, errw);
+    CU(cudaGetLastError());
+    ctx->prof_launch[SPIS_PROF_OTHER] += 1;
+  }
+  // q[j+1] = (w' - V h2) / h[j+1,j]  (+ x_{j-1} = x0 + Z y_{j-1})  (solvers.py:195-198, 287)
+  {
+    const int64_t ntiles = (ctx->n + kTile - 1) / kTile;
+    const int grid = grid_for(ctx, ntiles, ctx->lincomb2_ctas_per_sm);
+    const size_t smem = (size_t)(2 * (m + 2)) * sizeof(double);
+    const int mB = (nopre && want_it && j >= 1) ? j : 0;
+    const bool fusej = ctx->pre_kind == SPIS_PRE_JACOBI && ctx->fuse_jacobi && ctx->pre_diag && (j + 1 < ctx->kmax);
+    TRY(prof_begin(ctx, SPIS_PROF_LINCOMB, (double)(m + 2 + (mB ? 1 : 0) + ((mB && !ctx->x0_is_zero) ? 1 : 0) + (fusej ? 2 : 0)) * 8.0 * (double)ctx->n));
+    lincomb2n_kernel<4><<<grid, kThreads, smem, ctx->stream>>>(ctx->V, ctx->ld, m, h2, scal, ctx->d_ydev + (size_t)((j + 1) & 1) * K, mB,
+                                                               ctx->d_phase, ctx->W, ctx->x0_is_zero ? nullptr : ctx->X0, qn, ctx->X,
+                                                               fusej ? ctx->pre_diag : nullptr, fusej ? ctx->Z + (size_t)(j + 1) * ld : nullptr, ctx->n);
+    CU(cudaGetLastError());
+    TRY(prof_end(ctx));
+    ctx->z_ready_index = fusej ? j + 1 : -1;
+  }
+  if (!nopre && want_it) {
+    // preconditioned: Z is not V, the iterate x_j = x0 + Z y_j takes its own sweep (skipped once the phase word is set)
+    const int64_t ntiles = (ctx->n + kTile - 1) / kTile;
+    const int grid = grid_for(ctx, ntiles, ctx->ctas_per_sm);
+    const size_t smem = (size_t)(m + 2 + kWarps * 32) * sizeof(double);
+    TRY(prof_begin(ctx, SPIS_PROF_LINCOMB, (double)(m + (ctx->x0_is_zero ? 0 : 1) + 1) * 8.0 * (double)ctx->n));
+    lincomb_kernel<4><<<grid, kThreads, smem, ctx->stream>>>(ctx->Z, ctx->ld, m, ctx->d_ydev + (size_t)(j & 1) * K, nullptr, 1.0,
+                                                             ctx->x0_is_zero ? nullptr : ctx->X0, ctx->X, ctx->n, 0, ctx->d_partial,
+                                                             ctx->d_counter, nullptr, XView(), 0ull, ctx->d_phase);
+    CU(cudaGetLastError());
+    TRY(prof_end(ctx));
+  }
+  return SPIS_OK;
+}
+
+// Blocks until step j's record has arrived.  col_out: h[0..j+1, j] (j + 2 doubles); y_out: argmin_y |beta e1 - H y|
+// (j + 1 doubles, only meaningful when info_out[1] != 0); info_out[8]: [1] valid, [2] min_y |beta e1 - H y|,
+// [3] h[j+1,j]^2, [4] ||w'||^2, [5] |h2|^2, [6] phase word when the step's last sweep ran.
+int spis_step_wait(spis_ctx* ctx, int j, double* col_out, double* y_out, double* info_out) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(ctx->pipe_ready && j >= 0 && j < ctx->kmax && ctx->step_seq[j % kRecSlots] != 0, "step %d was not queued", j);
+  REQUIRE(col_out && y_out && info_out, "null output");
+  const double* rec = step_rec_host(ctx, j);
+  TRY(wait_record(ctx, rec, ctx->step_seq[j % kRecSlots], "an Arnoldi step record"));
+  const int K = ctx->K;
+  for (int i = 0; i < 8; ++i) info_out[i] = rec[i];
+  info_out[0] = (double)j;
+  for (int i = 0; i <= j + 1; ++i) col_out[i] = rec[8 + i];
+  for (int i = 0; i <= j; ++i) y_out[i] = rec[8 + K + i];
+  if (rec[7] != 0.0) return fail(ctx, SPIS_E_CUDA, "an NVLink collective timed out waiting for a peer rank (before Arnoldi step %d)", j);
+  return SPIS_OK;
+}
+
+// SQUARED residual norm measured by the step that returned `ticket` (the very number the device compared with thr^2);
+// *go_out = 1 while the phase word still says "unconstrained"
+int spis_resid_wait(spis_ctx* ctx, int64_t ticket, double* res_out, int* go_out) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(ctx->pipe_ready && ticket >= 0 && ticket < ctx->res_tickets && ticket + kRecSlots >= ctx->res_tickets,
+          "residual ticket %lld is not pending", (long long)ticket);
+  REQUIRE(res_out && go_out, "null output");
+  const double* rec = res_rec_host(ctx, ticket);
+  TRY(wait_record(ctx, rec, ctx->res_seq[ticket % kRecSlots], "a residual record"));
+  *res_out = rec[1];
+  *go_out = rec[2] == 0.0 ? 1 : 0;
+  return SPIS_OK;
+}
+
 // ---- constraint stage -----------------------------------------------------------------
 int spis_constraint_define(spis_ctx* ctx, int c, int mat_slot, const double* v, double cc) {
   if (!ctx) return SPIS_E_INVALID;
@@ -1762,13 +2038,17 @@ int spis_constraint_define(spis_ctx* ctx, int c, int mat_slot, const double* v, 
   if (v) {
     // an all-zero v is dropped (term1 then needs no v.Z pass).  Page-locked source: upload, then test the
     // device copy at HBM speed; pageable source: scan on the host first and skip the slow staged copy.
+    // Row-sharded contexts never drop v on their own: whether v is zero is a GLOBAL question (a rank whose slice of v
+    // is all zero still takes part in the all-reduced v.Z / v.x0 sums), so only the caller's NULL -- a decision it
+    // takes collectively -- switches the v passes off there.
+    const bool sharded = ctx->allreduce || ctx->halo || ctx->xbuf || ctx->n_halo > 0 || ctx->n_send > 0;
     int nz = 1;
     const bool pinned = is_pinned_host(v);
-    if (!pinned) TRY(spis_host_any_nonzero(v, (size_t)ctx->n, &nz));
+    if (!pinned && !sharded) TRY(spis_host_any_nonzero(v, (size_t)ctx->n, &nz));
     if (nz) {
       if (!C.v) TRY(dalloc(ctx, &C.v, (size_t)ctx->ld));
       TRY(h2d(ctx, C.v, v, (size_t)ctx->n * sizeof(double)));
-      if (pinned) TRY(device_any_nonzero(ctx, C.v, (size_t)ctx->n, &nz));
+      if (pinned && !sharded) TRY(device_any_nonzero(ctx, C.v, (size_t)ctx->n, &nz));
     }
     if (!nz && C.v) dfree(ctx, C.v);
   } else if (C.v) { dfree(ctx, C.v); }
@@ -2078,7 +2358,7 @@ int spis_xcomm_create(spis_ctx* ctx, int rank, int world, int64_t halo_cap, void
   XView xv;
   xv.world = world; xv.rank = rank;
   xv.red_cap = ctx->K > 1024 ? ctx->K : 1024;
-  xv.halo_cap = halo_cap > 0 ? roundup(halo_cap, 16) : 16;
+  xv.halo_cap = halo_cap > 0 ? 2 * roundup(halo_cap, 16) : 32;      // two vectors per exchange (halo_xchg_kernel)
   const size_t bytes = xv.total_doubles() * sizeof(double);
   CU(cudaMalloc((void**)&ctx->xbuf, bytes));          // plain cudaMalloc: pool memory cannot be exported
   CU(cudaMemset(ctx->xbuf, 0, bytes));
@@ -2105,7 +2385,122 @@ int spis_xcomm_connect(spis_ctx* ctx, const void* handles) {
     ctx->xv.base[r] = static_cast<double*>(p);
   }
   ctx->xactive = ctx->xv.world > 1;
-  ctx->xseq = 1; ctx->hseq = 1;
+  ctx->xseq_own = 1; ctx->hseq_own = 1;
+  return SPIS_OK;
+}
+
+// ---- persistent communicator -----------------------------------------------------------------------------
+int spis_comm_create(int device, int rank, int world, int64_t red_cap, int64_t halo_cap, void* handle_out,
+                     int64_t handle_capacity, spis_comm** comm_out) {
+  spis_ctx* ctx = nullptr;
+  if (!comm_out || !handle_out) return fail(ctx, SPIS_E_INVALID, "null argument");
+  *comm_out = nullptr;
+  REQUIRE(world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world, "bad rank %d / world %d (max %d ranks)", rank, world, kMaxRanks);
+  REQUIRE(handle_capacity >= (int64_t)sizeof(cudaIpcMemHandle_t), "handle buffer too small (%zu bytes needed)", sizeof(cudaIpcMemHandle_t));
+  REQUIRE(red_cap >= 1 && red_cap < (1 << 24) && halo_cap >= 0, "bad capacities");
+  CU(cudaSetDevice(device));
+  spis_comm* c = new spis_comm();
+  c->device = device;
+  c->xv.world = world; c->xv.rank = rank;
+  c->xv.red_cap = (int)(red_cap < 1024 ? 1024 : red_cap);
+  c->xv.halo_cap = halo_cap > 0 ? 2 * roundup(halo_cap, 16) : 32;
+  const size_t bytes = c->xv.total_doubles() * sizeof(double);
+  cudaError_t e = cudaMalloc((void**)&c->xbuf, bytes);            // plain cudaMalloc: pool memory cannot be exported
+  if (e == cudaSuccess) e = cudaMemset(c->xbuf, 0, bytes);
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, c->xbuf);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_tmp, (size_t)c->xv.red_cap * sizeof(double));
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_tmp, (size_t)c->xv.red_cap * sizeof(double));
+  if (e != cudaSuccess) {
+    if (c->xbuf) cudaFree(c->xbuf);
+    if (c->d_tmp) cudaFree(c->d_tmp);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return fail(ctx, e == cudaErrorMemoryAllocation ? SPIS_E_NOMEM : SPIS_E_CUDA, "communicator: %s", cudaGetErrorString(e));
+  }
+  memcpy(handle_out, &h, sizeof(h));
+  c->xv.base[rank] = c->xbuf;
+  *comm_out = c;
+  return SPIS_OK;
+}
+
+int spis_comm_connect(spis_comm* comm, const void* handles) {
+  spis_ctx* ctx = nullptr;
+  if (!comm || !handles) return fail(ctx, SPIS_E_INVALID, "null argument");
+  CU(cudaSetDevice(comm->device));
+  const char* hb = static_cast<const char*>(handles);
+  for (int r = 0; r < comm->xv.world; ++r) {
+    if (r == comm->xv.rank || comm->xpeer[r]) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, hb + (size_t)r * sizeof(h), sizeof(h));
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    comm->xpeer[r] = p;
+    comm->xv.base[r] = static_cast<double*>(p);
+  }
+  comm->connected = true;
+  return SPIS_OK;
+}
+
+int spis_comm_destroy(spis_comm* comm) {
+  if (!comm) return SPIS_OK;
+  cudaSetDevice(comm->device);
+  if (comm->stream) cudaStreamSynchronize(comm->stream);
+  for (int r = 0; r < kMaxRanks; ++r)
+    if (comm->xpeer[r]) cudaIpcCloseMemHandle(comm->xpeer[r]);
+  if (comm->xbuf) cudaFree(comm->xbuf);
+  if (comm->d_tmp) cudaFree(comm->d_tmp);
+  if (comm->h_tmp) cudaFreeHost(comm->h_tmp);
+  if (comm->stream) cudaStreamDestroy(comm->stream);
+  delete comm;
+  return SPIS_OK;
+}
+
+// capacities: doubles per reduction (>= k_max + 5 of every context that attaches) and ghost entries per vector
+int spis_comm_capacity(const spis_comm* comm, int64_t* red_cap_out, int64_t* halo_cap_out) {
+  if (!comm) return SPIS_E_INVALID;
+  if (red_cap_out) *red_cap_out = comm->xv.red_cap;
+  if (halo_cap_out) *halo_cap_out = comm->xv.halo_cap / 2;
+  return SPIS_OK;
+}
+
+// in-place sum over all ranks of `count` host doubles (collective decisions of a session set-up: "is x0 zero on every
+// rank?", ...): one tiny kernel on the communicator's own stream.  Every rank must call it, with the same count, at
+// the same point of its sequence of collectives (the contexts' streams are idle between solves).
+int spis_comm_allreduce(spis_comm* comm, double* vals, int count) {
+  spis_ctx* ctx = nullptr;
+  if (!comm || !vals) return fail(ctx, SPIS_E_INVALID, "null argument");
+  REQUIRE(comm->connected || comm->xv.world == 1, "the communicator is not connected");
+  REQUIRE(count >= 1 && count <= comm->xv.red_cap, "count %d exceeds the reduction capacity %d", count, comm->xv.red_cap);
+  if (comm->xv.world == 1) return SPIS_OK;
+  CU(cudaSetDevice(comm->device));
+  memcpy(comm->h_tmp, vals, (size_t)count * sizeof(double));
+  CU(cudaMemcpyAsync(comm->d_tmp, comm->h_tmp, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, comm->stream));
+  xreduce_kernel<<<1, kThreads, 0, comm->stream>>>(comm->d_tmp, count, comm->xv, comm->xseq);
+  CU(cudaGetLastError());
+  comm->xseq += 1;
+  CU(cudaMemcpyAsync(comm->h_tmp, comm->d_tmp, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, comm->stream));
+  CU(cudaStreamSynchronize(comm->stream));
+  memcpy(vals, comm->h_tmp, (size_t)count * sizeof(double));
+  unsigned long long w = 0;
+  CU(cudaMemcpy(&w, comm->xbuf + comm->xv.flags_off() + 4 * comm->xv.world, sizeof(w), cudaMemcpyDeviceToHost));
+  if (w >> 63) return fail(ctx, SPIS_E_CUDA, "NVLink collective %llu timed out waiting for a peer rank", w & ~(1ull << 63));
+  return SPIS_OK;
+}
+
+int spis_ctx_attach_comm(spis_ctx* ctx, spis_comm* comm) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(comm && (comm->connected || comm->xv.world == 1), "the communicator is not connected");
+  REQUIRE(!ctx->xbuf && !ctx->comm, "the context already has a communicator");
+  REQUIRE(comm->device == ctx->device, "communicator lives on device %d, context on %d", comm->device, ctx->device);
+  REQUIRE(comm->xv.red_cap >= ctx->K + 1, "communicator reduces %d doubles at a time, k_max = %d needs %d", comm->xv.red_cap, ctx->kmax, ctx->K + 1);
+  REQUIRE(comm->xv.halo_cap / 2 >= ctx->n_halo, "communicator holds %lld ghost entries per vector, the context has %lld", (long long)(comm->xv.halo_cap / 2), (long long)ctx->n_halo);
+  ctx->comm = comm;
+  ctx->xbuf = comm->xbuf;
+  ctx->xv = comm->xv;
+  ctx->xseq_p = &comm->xseq; ctx->hseq_p = &comm->hseq;
+  ctx->xactive = comm->xv.world > 1;
   return SPIS_OK;
 }
 

@@ -138,13 +138,44 @@ __device__ __forceinline__ void cta_xreduce(double* buf, int count, const XView&
   __syncthreads();
 }
 
+// A reduction that RIDES on the tail of another kernel's reduction (pipelined Krylov loop): the dual SpMV of an
+// Arnoldi step leaves one partial sum of ||A x - b||^2 per CTA, and the first Gram-Schmidt reduction of the same step
+// (mdot) finishes it -- one cross-GPU exchange for both -- then publishes the norm to the host through mapped
+// page-locked memory and flips the device-side phase word when the residual has reached the constraint threshold
+// (solvers.py:230: `residual[-1] > contol*tol`), so that steps queued ahead stop forming unconstrained iterates.
+struct TailExtra {
+  const double* rpart;          // per-CTA partial sums of the preceding kernel (null: nothing rides)
+  int nrpart;
+  double* res_out;              // device copy of the finished sum
+  double* host_rec;             // mapped host record: [0] sequence word (written last), [1] sum, [2] phase afterwards
+  unsigned long long rec_seq;
+  int* phase;                   // device phase word: 0 = the device forms the iterates, 1 = the host has taken over
+  double thr2;                  // *phase = 1 when !(sum > thr2)
+};
+
+__device__ __forceinline__ void publish_residual(double res2, const TailExtra& tx) {
+  int ph = 0;
+  if (tx.phase) {
+    if (!(res2 > tx.thr2)) *tx.phase = 1;        // (NaN lands here too)
+    ph = *tx.phase;
+  }
+  if (tx.res_out) *tx.res_out = res2;
+  if (tx.host_rec) {
+    tx.host_rec[1] = res2;
+    tx.host_rec[2] = (double)ph;
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(tx.host_rec) = tx.rec_seq;
+  }
+}
+
 // Deterministic cross-CTA reduction tail.  Each CTA has already written its `nout` partial
 // sums to partial[blockIdx.x*pstride + i].  The last CTA to take a ticket sums them in a
 // fixed order (8 warps over contiguous CTA ranges, then warp 0..7 in order) into out[i].
 __device__ __forceinline__ void finish_reduction(double* __restrict__ partial, int pstride, int nout,
                                                  unsigned* counter, double* out,
                                                  double* sred /* 32 doubles per warp of the CTA */,
-                                                 const XView& xv, unsigned long long seq) {
+                                                 const XView& xv, unsigned long long seq,
+                                                 const TailExtra* tx = nullptr) {
   __shared__ unsigned s_ticket;
   __threadfence();
   __syncthreads();
@@ -181,8 +212,21 @@ __device__ __forceinline__ void finish_reduction(double* __restrict__ partial, i
     __syncthreads();
   }
   if (threadIdx.x == 0) *counter = 0u;   // ready for the next launch on this stream
+  int nred = nout;
+  if (tx && tx->rpart) {
+    // the sum that rides along: lane-strided partial sums, then a butterfly (every lane ends with the same bits)
+    if (warp == 0) {
+      double t = 0.0;
+      for (int i = lane; i < tx->nrpart; i += 32) t += __ldcg(tx->rpart + i);
+      t = warp_sum(t);
+      if (lane == 0) out[nout] = t;
+    }
+    nred = nout + 1;
+    __syncthreads();
+  }
   // row-sharded runs: the same CTA finishes the job across GPUs over NVLink (fused dot + all-reduce)
-  cta_xreduce(out, nout, xv, seq);
+  cta_xreduce(out, nred, xv, seq);
+  if (tx && tx->rpart && threadIdx.x == 0) publish_residual(out[nout], *tx);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -237,7 +281,7 @@ __global__ void __launch_bounds__(kThreads)
 mdot_kernel(const double* __restrict__ V, int64_t ld, int m, const double* __restrict__ extra,
             int with_sumsq, const double* __restrict__ w, int64_t n,
             double* __restrict__ partial, int pstride, unsigned* counter, double* out,
-            XView xv, unsigned long long seq) {
+            const __grid_constant__ XView xv, unsigned long long seq, const __grid_constant__ TailExtra tx) {
   extern __shared__ double smem[];
   const int nrows = m + (extra ? 1 : 0) + (with_sumsq ? 1 : 0);
   double* sacc = smem;                       // [kWarps][nrows]
@@ -260,7 +304,7 @@ mdot_kernel(const double* __restrict__ V, int64_t ld, int m, const double* __res
     for (int wv = 0; wv < kWarps; ++wv) s += sacc[wv * nrows + i];
     partial[(size_t)blockIdx.x * pstride + i] = s;
   }
-  finish_reduction(partial, pstride, nrows, counter, out, sred, xv, seq);
+  finish_reduction(partial, pstride, nrows, counter, out, sred, xv, seq, &tx);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -309,7 +353,7 @@ __global__ void __launch_bounds__(kThreads, MB <= 8 ? 4 : (MB <= 16 ? 3 : 2))
 mdot_reg_kernel(const double* __restrict__ V, int64_t ld, int m, const double* __restrict__ extra,
                 int with_sumsq, const double* __restrict__ w, int64_t n,
                 double* __restrict__ partial, int pstride, unsigned* counter, double* out,
-                XView xv, unsigned long long seq) {
+                const __grid_constant__ XView xv, unsigned long long seq, const __grid_constant__ TailExtra tx) {
   __shared__ double sacc[kWarps * MB];
   __shared__ double sred[kWarps * 32];
   const int nrows = m + (extra ? 1 : 0) + (with_sumsq ? 1 : 0);
@@ -337,7 +381,7 @@ mdot_reg_kernel(const double* __restrict__ V, int64_t ld, int m, const double* _
     for (int wv = 0; wv < kWarps; ++wv) t += sacc[wv * MB + i];
     partial[(size_t)blockIdx.x * pstride + i] = t;
   }
-  finish_reduction(partial, pstride, nrows, counter, out, sred, xv, seq);
+  finish_reduction(partial, pstride, nrows, counter, out, sred, xv, seq, &tx);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -427,7 +471,7 @@ __global__ void __launch_bounds__(kThreads)
 mdotm_kernel(const double* __restrict__ V, int64_t ld, int m, const double* __restrict__ extra,
              const double* __restrict__ W, int64_t wstride, int64_t n,
              double* __restrict__ partial, int pstride, unsigned* counter, double* out,
-             XView xv, unsigned long long seq) {
+             const __grid_constant__ XView xv, unsigned long long seq) {
   extern __shared__ double smem[];
   const int nrows = m + (extra ? 1 : 0);
   const int nout = NW * nrows;
@@ -516,8 +560,9 @@ lincomb_kernel(const double* __restrict__ V, int64_t ld, int m, const double* __
                const double* __restrict__ coef2 /* optional, added to coef */, double sign,
                const double* base, double* out, int64_t n, int with_sumsq,
                double* __restrict__ partial, unsigned* counter, double* sumsq_out,
-               XView xv, unsigned long long seq) {
+               const __grid_constant__ XView xv, unsigned long long seq, const int* __restrict__ skip_if = nullptr) {
   extern __shared__ double smem[];
+  if (skip_if && *skip_if) return;    // the host has taken over the iterates (pipelined loop, constrained phase)
   double* sc = smem;                  // [m]
   double* sred = smem + m + (m & 1);  // [kWarps*32]
   for (int i = threadIdx.x; i < m; i += kThreads)
@@ -606,7 +651,7 @@ lincomb2_kernel(const double* __restrict__ V, int64_t ld, int m, const double* _
                 const double* __restrict__ coefB, int mB, const double* baseA, const double* baseB,
                 double* outA, double* outB, int64_t n,
                 double* __restrict__ partial, unsigned* counter, double* sumsq_out,
-                XView xv, unsigned long long seq) {
+                const __grid_constant__ XView xv, unsigned long long seq) {
   extern __shared__ double smem[];
   double* scA = smem;                        // [m]   -coefA
   double* scB = smem + m + (m & 1);          // [m]   +coefB, zero beyond mB
@@ -635,6 +680,240 @@ lincomb2_kernel(const double* __restrict__ V, int64_t ld, int m, const double* _
   }
   __syncthreads();
   finish_reduction(partial, 1, 1, counter, sumsq_out, sred, xv, seq);
+}
+
+// ------------------------------------------------------------------------------------------
+// K3b + K4 + K5 in one pass -- the last sweep of the PIPELINED Arnoldi step:
+//     outA = (baseA - sum_{i<m} cA[i] V_i) / h      q[j+1], already normalised   (solvers.py:195-198)
+//     outB = baseB + sum_{i<mB} cB[i] V_i           x_{j-1} = x0 + Z y_{j-1}      (solvers.py:287)
+// h = h[j+1,j] is known BEFORE the sweep: orth_mid_kernel delivers ||w'||^2 with h2 = V^T w' in one reduction, and with
+// V orthonormal ||w' - V h2||^2 = ||w'||^2 - |h2|^2 (hess_kernel forms it; h2 is the O(eps) correction of the second
+// Gram-Schmidt pass, so there is no cancellation except at breakdown).  So there is no separate normalisation pass
+// (scale_kernel: 16 n bytes and a launch per iteration) and no reduction / cross-GPU exchange in this kernel.
+// cB = the least-squares coefficients hess_kernel computed on the device; the iterate is formed only while the device
+// phase word says "unconstrained" (see TailExtra).  Optionally also z[j+1] = d (.) q[j+1] (fused Jacobi).
+// Same fma chains, in the same row order, as lincomb_kernel / lincomb2_kernel.
+// ------------------------------------------------------------------------------------------
+template <int IU, bool FULL, bool DOB>
+__device__ __forceinline__ void lincomb2n_tile(const double* __restrict__ V, int64_t ld, int m,
+                                               const double* scA, const double* scB, double inv, const double* baseA,
+                                               const double* baseB, double* outA, double* outB,
+                                               const double* __restrict__ jac, double* __restrict__ znext,
+                                               int64_t n, int64_t tile) {
+  const int64_t e0 = tile * kTile + 2 * threadIdx.x;
+  const int64_t e1 = e0 + 2 * kThreads;
+  const bool p0 = FULL || e0 < n, p1 = FULL || e1 < n;
+  double2 a0 = make_double2(0.0, 0.0), a1 = a0, b0 = a0, b1 = a0;
+  if (p0) { a0 = ld_keep(baseA + e0); if (DOB && baseB) b0 = ld_keep(baseB + e0); }
+  if (p1) { a1 = ld_keep(baseA + e1); if (DOB && baseB) b1 = ld_keep(baseB + e1); }
+  const double* row = V;
+  int i0 = 0;
+  for (; i0 + IU <= m; i0 += IU) {
+    double2 u[IU], v[IU];
+#pragma unroll
+    for (int q = 0; q < IU; ++q) {
+      if (FULL) {
+        u[q] = ld_stream(row + (size_t)q * ld + e0);
+        v[q] = ld_stream(row + (size_t)q * ld + e1);
+      } else {
+        u[q] = p0 ? ld_stream(row + (size_t)q * ld + e0) : make_double2(0.0, 0.0);
+        v[q] = p1 ? ld_stream(row + (size_t)q * ld + e1) : make_double2(0.0, 0.0);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < IU; ++q) {
+      const double ca = scA[i0 + q];
+      a0.x = fma(ca, u[q].x, a0.x); a0.y = fma(ca, u[q].y, a0.y);
+      a1.x = fma(ca, v[q].x, a1.x); a1.y = fma(ca, v[q].y, a1.y);
+      if (DOB) {
+        const double cb = scB[i0 + q];
+        b0.x = fma(cb, u[q].x, b0.x); b0.y = fma(cb, u[q].y, b0.y);
+        b1.x = fma(cb, v[q].x, b1.x); b1.y = fma(cb, v[q].y, b1.y);
+      }
+    }
+    row += (size_t)IU * ld;
+  }
+  for (; i0 < m; ++i0) {
+    const double ca = scA[i0], cb = DOB ? scB[i0] : 0.0;
+    if (p0) { const double2 u = ld_stream(row + e0); a0.x = fma(ca, u.x, a0.x); a0.y = fma(ca, u.y, a0.y); if (DOB) { b0.x = fma(cb, u.x, b0.x); b0.y = fma(cb, u.y, b0.y); } }
+    if (p1) { const double2 v = ld_stream(row + e1); a1.x = fma(ca, v.x, a1.x); a1.y = fma(ca, v.y, a1.y); if (DOB) { b1.x = fma(cb, v.x, b1.x); b1.y = fma(cb, v.y, b1.y); } }
+    row += ld;
+  }
+  a0.x *= inv; a0.y *= inv; a1.x *= inv; a1.y *= inv;
+  if (p0) {
+    *reinterpret_cast<double2*>(outA + e0) = a0;
+    if (DOB) *reinterpret_cast<double2*>(outB + e0) = b0;
+    if (jac) { const double2 d = ld_keep(jac + e0); *reinterpret_cast<double2*>(znext + e0) = make_double2(a0.x * d.x, a0.y * d.y); }
+  }
+  if (p1) {
+    *reinterpret_cast<double2*>(outA + e1) = a1;
+    if (DOB) *reinterpret_cast<double2*>(outB + e1) = b1;
+    if (jac) { const double2 d = ld_keep(jac + e1); *reinterpret_cast<double2*>(znext + e1) = make_double2(a1.x * d.x, a1.y * d.y); }
+  }
+}
+
+template <int IU>
+__global__ void __launch_bounds__(kThreads)
+lincomb2n_kernel(const double* __restrict__ V, int64_t ld, int m, const double* __restrict__ coefA,
+                 const double* __restrict__ norm2 /* h[j+1,j]^2, written by hess_kernel */,
+                 const double* __restrict__ coefB, int mB, const int* __restrict__ phase,
+                 const double* baseA, const double* baseB, double* outA, double* outB,
+                 const double* __restrict__ jac, double* __restrict__ znext, int64_t n) {
+  extern __shared__ double smem[];
+  double* scA = smem;                        // [m]   -coefA
+  double* scB = smem + m + (m & 1);          // [m]   +coefB, zero beyond mB
+  const bool dob = mB > 0 && (phase == nullptr || *phase == 0);
+  for (int i = threadIdx.x; i < m; i += kThreads) {
+    scA[i] = -coefA[i];
+    scB[i] = (dob && i < mB) ? coefB[i] : 0.0;
+  }
+  const double h2 = *norm2;
+  const double inv = h2 > 0.0 ? 1.0 / sqrt(h2) : 0.0;     // breakdown: q[j+1] = 0 as in the reference (solvers.py:197-198, 376-377)
+  __syncthreads();
+  const int64_t ntiles = (n + kTile - 1) / kTile;
+  const int64_t nfull = n / kTile;
+  if (dob) {
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      if (tile < nfull) lincomb2n_tile<IU, true, true>(V, ld, m, scA, scB, inv, baseA, baseB, outA, outB, jac, znext, n, tile);
+      else lincomb2n_tile<IU, false, true>(V, ld, m, scA, scB, inv, baseA, baseB, outA, outB, jac, znext, n, tile);
+    }
+  } else {
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      if (tile < nfull) lincomb2n_tile<IU, true, false>(V, ld, m, scA, scB, inv, baseA, baseB, outA, outB, jac, znext, n, tile);
+      else lincomb2n_tile<IU, false, false>(V, ld, m, scA, scB, inv, baseA, baseB, outA, outB, jac, znext, n, tile);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// H1 on the device: the Givens least-squares update of the Hessenberg matrix (solvers.py:113, and the unconstrained
+// minimisation of solvers.py:231-235, whose minimiser is the least-squares solution).  north_star keeps "the Givens
+// least-squares update" on the host; it stays there as the reference semantics (smallsolve.py), but a host round trip
+// per Krylov iteration -- Hessenberg column down, coefficients up -- is what paces a row-sharded solve once the
+// kernels of an iteration take only ~100 us.  One warp per Arnoldi step does the same O(m^2) arithmetic here, so the
+// unconstrained iterate x_j = x0 + Z y_j is formed by kernels that were queued before y_j existed; the host only
+// reads the records (mapped page-locked memory) to follow the residual and to decide the phase switch.
+//   in : h1, h2 (the two CGS2 projections), h2[m] = ||w'||^2
+//   out: norm2_out[0] = h[j+1,j]^2 = ||w'||^2 - |h2|^2, norm2_out[1] = |h2|^2, the rotated column in R, y_j = R^{-1} g
+//        in ydst, and the host record [0] seq, [1] valid, [2] |g_{j+1}| = min_y |beta e1 - H y|, [3] h[j+1,j]^2,
+//        [4] ||w'||^2, [5] |h2|^2, [8..8+K) the column h[0..j+1, j], [8+K..8+2K) y_j.
+// valid = 0 (a vanishing pivot: R singular to working precision) also sets the phase word: the host takes over.
+// ------------------------------------------------------------------------------------------
+struct HessState {
+  double* cs; double* sn;       // rotations (kmax each)
+  double* gv;                   // rotated right-hand side beta e1 (kmax + 1)
+  double* R;                    // triangular factor, column-major kmax x kmax
+  int* tracking;                // 1 while every pivot so far was non-zero
+  int kmax;
+};
+
+__global__ void __launch_bounds__(32)
+hess_kernel(int j, HessState st, const double* __restrict__ h1, const double* __restrict__ h2, double* norm2_out,
+            double* ydst, int* phase, double* host_rec, unsigned long long rec_seq, int K,
+            const unsigned long long* __restrict__ peer_err) {
+  extern __shared__ double hsm[];
+  double* r = hsm;                       // [m + 1] the new column
+  double* t = hsm + (K + 2);             // [m] right-hand side of the back substitution
+  const int lane = threadIdx.x;
+  const int m = j + 1;
+  const int kmax = st.kmax;
+  double s2 = 0.0;
+  for (int i = lane; i < m; i += 32) {
+    const double b = h2[i];
+    r[i] = h1[i] + b;
+    s2 = fma(b, b, s2);
+  }
+  s2 = warp_sum(s2);
+  const double nw2 = h2[m];
+  double n2 = nw2 - s2;
+  if (!(n2 > 0.0)) n2 = 0.0;
+  const double hn = sqrt(n2);
+  if (lane == 0) { r[m] = hn; norm2_out[0] = n2; norm2_out[1] = s2; }
+  __syncwarp();
+  if (host_rec) for (int i = lane; i <= m; i += 32) host_rec[8 + i] = r[i];
+  __syncwarp();
+  int valid = *st.tracking;
+  double ls = 0.0;
+  if (lane == 0 && valid) {
+    for (int i = 0; i < j; ++i) {
+      const double a = r[i], b = r[i + 1], c = st.cs[i], s = st.sn[i];
+      r[i] = c * a + s * b;
+      r[i + 1] = -s * a + c * b;
+    }
+    const double den = hypot(r[j], r[j + 1]);
+    if (den > 0.0) {
+      const double c = r[j] / den, s = r[j + 1] / den;
+      st.cs[j] = c; st.sn[j] = s;
+      r[j] = den;
+      const double gj = st.gv[j];
+      st.gv[j] = c * gj;
+      st.gv[j + 1] = -s * gj;
+    } else {
+      *st.tracking = 0;
+    }
+  }
+  __syncwarp();
+  valid = *st.tracking;
+  if (valid) {
+    for (int i = lane; i <= j; i += 32) st.R[(size_t)i + (size_t)j * kmax] = r[i];
+    ls = fabs(st.gv[j + 1]);
+    // pivots: the least-squares solution is trusted only while min |R_ii| > 1e-14 max |R_ii| (as smallsolve does)
+    double dmin = 1e300, dmax = 0.0;
+    for (int i = lane; i < m; i += 32) {
+      const double d = fabs(i == j ? r[j] : st.R[(size_t)i + (size_t)i * kmax]);
+      dmin = fmin(dmin, d); dmax = fmax(dmax, d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, o)); dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o)); }
+    if (!(dmin > 1e-14 * dmax)) valid = 0;
+  }
+  if (valid) {
+    // y = R^{-1} g, column-oriented back substitution: m dependent steps, the updates of a step spread over the warp
+    for (int i = lane; i < m; i += 32) t[i] = st.gv[i];
+    __syncwarp();
+    for (int i = m - 1; i >= 0; --i) {
+      const double* col = st.R + (size_t)i * kmax;
+      const double yi = t[i] / (i == j ? r[j] : col[i]);
+      __syncwarp();
+      if (lane == 0) t[i] = yi;
+      for (int l = lane; l < i; l += 32) t[l] = fma(-(i == j ? r[l] : col[l]), yi, t[l]);
+      __syncwarp();
+    }
+    for (int i = lane; i < m; i += 32) {
+      const double yi = t[i];
+      ydst[i] = yi;
+      if (host_rec) host_rec[8 + K + i] = yi;
+    }
+  } else if (lane == 0 && phase) {
+    *phase = 1;
+  }
+  if (host_rec && lane == 0) {
+    host_rec[1] = (double)valid;
+    host_rec[2] = ls;
+    host_rec[3] = n2;
+    host_rec[4] = nw2;
+    host_rec[5] = s2;
+    host_rec[6] = phase ? (double)*phase : 0.0;
+    host_rec[7] = (peer_err && (ld_acquire_sys(peer_err) >> 63)) ? 1.0 : 0.0;     // a cross-GPU wait gave up (wait_flag)
+  }
+  __syncwarp();
+  __threadfence_system();
+  __syncwarp();
+  if (host_rec && lane == 0) *reinterpret_cast<volatile unsigned long long*>(host_rec) = rec_seq;
+}
+
+// publishes a residual norm that was reduced by a kernel without a riding tail (formats without a dual SpMV)
+__global__ void publish_res_kernel(const double* __restrict__ res2, const __grid_constant__ TailExtra tx) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) publish_residual(*res2, tx);
+}
+
+// sets up the device side of the pipelined loop: gv = beta e1, tracking on, phase word
+__global__ void pipe_init_kernel(HessState st, const double* __restrict__ beta2, int* phase, int phase0) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    st.gv[0] = sqrt(*beta2);
+    *st.tracking = 1;
+    *phase = phase0;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -707,9 +986,9 @@ __host__ __device__ inline size_t orth_mid_smem(int MB, int E, int m, int nstage
 template <int MB, int E>
 __global__ void __launch_bounds__(kOrthMidThreads, 1)
 orth_mid_kernel(const double* __restrict__ V, int64_t ld, int m, const double* __restrict__ coef,
-                double* w, int64_t npad /* roundup(n,16): pads are zero */, int nstages, int probe,
+                double* w, int64_t npad /* roundup(n,16): pads are zero */, int nstages, int probe, int with_norm,
                 double* __restrict__ partial, int pstride, unsigned* counter, double* out,
-                XView xv, unsigned long long seq) {
+                const __grid_constant__ XView xv, unsigned long long seq) {
   constexpr int T = kThreads * E;
   using vec_t = typename VecE<E>::type;
   extern __shared__ __align__(128) unsigned char smraw[];
@@ -734,6 +1013,7 @@ orth_mid_kernel(const double* __restrict__ V, int64_t ld, int m, const double* _
   double acc[MB];
 #pragma unroll
   for (int i = 0; i < MB; ++i) acc[i] = 0.0;
+  double accn = 0.0;                     // ||w'||^2 of this thread's entries (with_norm)
 
   if (warp >= kWarps) {
     // ---- producer warps: one elected lane each, rows dealt round-robin, keep the ring full ----
@@ -779,6 +1059,8 @@ orth_mid_kernel(const double* __restrict__ V, int64_t ld, int m, const double* _
           else r = fma(c, a, r);
         }
         *reinterpret_cast<vec_t*>(w + start + (int64_t)threadIdx.x * E) = r;
+        if constexpr (E == 2) accn = fma(r.y, r.y, fma(r.x, r.x, accn));
+        else accn = fma(r, r, accn);
         // second look at the same staged rows: partial dots with w'
 #pragma unroll
         for (int i = 0; i < MB; ++i) {
@@ -802,6 +1084,8 @@ orth_mid_kernel(const double* __restrict__ V, int64_t ld, int m, const double* _
       const double s = warp_sum(acc[i]);
       if (lane == 0) sacc[warp * MB + i] = s;
     }
+    const double sn = warp_sum(accn);
+    if (lane == 0) sred[warp] = sn;      // (sred is free until finish_reduction, which starts with a barrier)
   }
   __syncthreads();
   for (int i = threadIdx.x; i < m; i += kOrthMidThreads) {
@@ -810,7 +1094,15 @@ orth_mid_kernel(const double* __restrict__ V, int64_t ld, int m, const double* _
     for (int wv = 0; wv < kWarps; ++wv) s += sacc[wv * MB + i];
     partial[(size_t)blockIdx.x * pstride + i] = s;
   }
-  finish_reduction(partial, pstride, m, counter, out, sred, xv, seq);
+  if (with_norm && threadIdx.x == 0) {
+    // ||w'||^2 as output m: with V orthonormal ||w' - V h2||^2 = ||w'||^2 - |h2|^2, so the norm of the new basis
+    // vector (solvers.py:196) comes out of THIS reduction and the last sweep can write it already normalised
+    double s = 0.0;
+#pragma unroll
+    for (int wv = 0; wv < kWarps; ++wv) s += sred[wv];
+    partial[(size_t)blockIdx.x * pstride + m] = s;
+  }
+  finish_reduction(partial, pstride, m + (with_norm ? 1 : 0), counter, out, sred, xv, seq);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -823,8 +1115,9 @@ __global__ void __launch_bounds__(kThreads)
 scale_kernel(double* __restrict__ v, const double* __restrict__ sumsq, int64_t n,
              const double* __restrict__ jac_diag, double* __restrict__ z_next) {
   const double s2 = *sumsq;
-  if (!(s2 != 0.0)) return;
-  const double inv = 1.0 / sqrt(s2);
+  // exact breakdown (solvers.py:199-202, 376-377): the reference leaves q[j+1] at its initial zeros; w is zero
+  // here as well (its squared norm is), but the fused Jacobi vector of the next step must be cleared too
+  const double inv = (s2 != 0.0) ? 1.0 / sqrt(s2) : 0.0;
   const int64_t stride = (int64_t)gridDim.x * kThreads * 2;
   for (int64_t e = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 2; e < n; e += stride) {
     double2 a = *reinterpret_cast<const double2*>(v + e);
@@ -885,7 +1178,7 @@ spmv_sell_kernel(const int64_t* __restrict__ slice_off, const uint8_t* __restric
                  const double* __restrict__ vals, int64_t nrows, const double* __restrict__ x,
                  const double* __restrict__ b, double* __restrict__ y,
                  double* __restrict__ partial, unsigned* counter, double* sumsq_out,
-                 XView xv, unsigned long long seq) {
+                 const __grid_constant__ XView xv, unsigned long long seq) {
   __shared__ double sred[kWarps * 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t nslices = (nrows + 31) >> 5;
@@ -952,7 +1245,7 @@ spmv_sell2_kernel(const int64_t* __restrict__ slice_off, const int2* __restrict_
                   const double2* __restrict__ vals2, int64_t nrows, const double* __restrict__ x,
                   const double* __restrict__ b, double* __restrict__ y,
                   double* __restrict__ partial, unsigned* counter, double* sumsq_out,
-                  XView xv, unsigned long long seq) {
+                  const __grid_constant__ XView xv, unsigned long long seq) {
   __shared__ double sred[kWarps * 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t nslices = (nrows + 31) >> 5;
@@ -1233,7 +1526,7 @@ spmv_pattern_kernel(const uint16_t* __restrict__ pid, int W, const int32_t* __re
 
 // out[0] = sum of partial[0..nparts) in a fixed order (one CTA), then the cross-GPU part
 __global__ void __launch_bounds__(kThreads)
-reduce_partials_kernel(const double* __restrict__ partial, int nparts, double* out, XView xv, unsigned long long seq) {
+reduce_partials_kernel(const double* __restrict__ partial, int nparts, double* out, const __grid_constant__ XView xv, unsigned long long seq) {
   __shared__ double sred[kThreads];
   double t = 0.0;
   for (int i = threadIdx.x; i < nparts; i += kThreads) t += __ldcg(partial + i);
@@ -1769,7 +2062,7 @@ spmv_csr_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
                 const double* __restrict__ vals, int64_t nrows, const double* __restrict__ x,
                 const double* __restrict__ b, double* __restrict__ y,
                 double* __restrict__ partial, unsigned* counter, double* sumsq_out,
-                XView xv, unsigned long long seq) {
+                const __grid_constant__ XView xv, unsigned long long seq) {
   __shared__ double sred[kWarps * 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = threadIdx.x & (T - 1);
@@ -1910,7 +2203,7 @@ __global__ void sell2_fill_kernel(const int32_t* __restrict__ indptr, const int3
 
 // stand-alone all-reduce of a device buffer in chunks of red_cap (batched constraint terms)
 __global__ void __launch_bounds__(kThreads)
-xreduce_kernel(double* buf, int64_t count, XView xv, unsigned long long seq0) {
+xreduce_kernel(double* buf, int64_t count, const __grid_constant__ XView xv, unsigned long long seq0) {
   unsigned long long seq = seq0;
   for (int64_t c0 = 0; c0 < count; c0 += xv.red_cap, ++seq) {
     const int cnt = (int)((count - c0) < xv.red_cap ? (count - c0) : xv.red_cap);
@@ -1922,7 +2215,7 @@ xreduce_kernel(double* buf, int64_t count, XView xv, unsigned long long seq0) {
 // NVLink (dest_rank[i], dest_off[i] = position in that rank's ghost ordering)
 __global__ void halo_push_kernel(const double* __restrict__ vec, const int32_t* __restrict__ idx,
                                  const int32_t* __restrict__ dest_rank, const int32_t* __restrict__ dest_off,
-                                 int64_t n_send, XView xv, unsigned long long seq) {
+                                 int64_t n_send, const __grid_constant__ XView xv, unsigned long long seq) {
   const int phase = (int)(seq & 1ull);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_send; i += stride)
@@ -1934,7 +2227,7 @@ __global__ void halo_push_kernel(const double* __restrict__ vec, const int32_t* 
 // completed), wait for every source, then copy the ghosts next to the owned part of the vector
 __global__ void __launch_bounds__(1024)
 halo_pull_kernel(double* __restrict__ ghost_dst, int64_t n_halo, const int32_t* __restrict__ send_to,
-                 const int32_t* __restrict__ recv_from, XView xv, unsigned long long seq) {
+                 const int32_t* __restrict__ recv_from, const __grid_constant__ XView xv, unsigned long long seq) {
   const int phase = (int)(seq & 1ull);
   __threadfence_system();
   if ((int)threadIdx.x < xv.world) {
@@ -1944,6 +2237,36 @@ halo_pull_kernel(double* __restrict__ ghost_dst, int64_t n_halo, const int32_t* 
   __syncthreads();
   const double* src = xv.base[xv.rank] + xv.halo_off(phase);
   for (int64_t i = threadIdx.x; i < n_halo; i += blockDim.x) ghost_dst[i] = ld_volatile(src + i);
+}
+
+// One exchange for up to TWO vectors (the Arnoldi vector z_j and the iterate x, which the dual SpMV multiplies in the
+// same pass): push my entries into the neighbours' comm buffers, flag, wait for theirs, copy the ghosts in place.
+// One CTA: a row-sharded strip sends a few thousand doubles (lkdv: 6) -- four launches and two flag rounds become one.
+__global__ void __launch_bounds__(1024)
+halo_xchg_kernel(double* vecA, double* vecB, int64_t hoff, int64_t n_halo, const int32_t* __restrict__ idx,
+                 const int32_t* __restrict__ dest_rank, const int32_t* __restrict__ dest_off, int64_t n_send,
+                 const int32_t* __restrict__ send_to, const int32_t* __restrict__ recv_from,
+                 const __grid_constant__ XView xv, unsigned long long seq) {
+  const int phase = (int)(seq & 1ull);
+  const size_t hb = xv.halo_off(phase);
+  const size_t half = (size_t)(xv.halo_cap / 2);
+  for (int64_t i = threadIdx.x; i < n_send; i += blockDim.x) {
+    double* dst = xv.base[dest_rank[i]] + hb + dest_off[i];
+    dst[0] = vecA[idx[i]];
+    if (vecB) dst[half] = vecB[idx[i]];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < xv.world) {
+    if (send_to[threadIdx.x]) st_release_sys(xv.halo_flag(threadIdx.x, phase, xv.rank), seq);
+    if (recv_from[threadIdx.x]) wait_flag(xv.halo_flag(xv.rank, phase, threadIdx.x), seq, xv.err_word(xv.rank));
+  }
+  __syncthreads();
+  const double* src = xv.base[xv.rank] + hb;
+  for (int64_t i = threadIdx.x; i < n_halo; i += blockDim.x) {
+    vecA[hoff + i] = ld_volatile(src + i);
+    if (vecB) vecB[hoff + i] = ld_volatile(src + half + i);
+  }
 }
 
 // halo pack: send[i] = vec[idx[i]]  (entries of a vector that neighbouring ranks need as ghosts)

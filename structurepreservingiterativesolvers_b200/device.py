@@ -180,6 +180,35 @@ class KrylovContext:
         y = nat.as_f64(y)
         self._check(self._lib.spis_form_iterate(self._h, y.size, nat.dptr(y)))
 
+    # -- pipelined loop (include/spis_b200.h: spis_pipe_begin ...) ----------------------------------
+    def pipe_begin(self, thr: float, phase0: bool):
+        """Device-side Givens state and phase word for this solve; thr = residual norm at or below which the
+        device stops forming unconstrained iterates (contol*tol for cgmres, tol for gmres)."""
+        self._check(self._lib.spis_pipe_begin(self._h, float(thr), 1 if phase0 else 0))
+
+    def step_enqueue(self, j: int, want_residual: bool, want_iterate: bool) -> int:
+        """Queue Arnoldi step j; returns the ticket of its residual measurement (-1 without one)."""
+        t = C.c_int64(-1)
+        self._check(self._lib.spis_step_enqueue(self._h, j, (1 if want_residual else 0) | (2 if want_iterate else 0), C.byref(t)))
+        return t.value
+
+    def step_wait(self, j: int):
+        """(h[:j+2, j], y_ls (j+1), info) once step j's record is there; info: valid, ls, h2next, nw2, s2, phase."""
+        col = np.empty(j + 2, dtype=np.float64)
+        y = np.empty(j + 1, dtype=np.float64)
+        info = np.empty(8, dtype=np.float64)
+        self._check(self._lib.spis_step_wait(self._h, j, nat.dptr(col), nat.dptr(y), nat.dptr(info)))
+        return col, y, {"valid": bool(info[1]), "ls": float(info[2]), "norm2": float(info[3]), "nw2": float(info[4]),
+                        "s2": float(info[5]), "phase": int(info[6])}
+
+    def resid_wait(self, ticket: int):
+        """(||A x - b||, its square as reduced on the device, go) of a residual measurement queued by step_enqueue;
+        go = the device is still forming iterates."""
+        res2 = C.c_double(0.0)
+        go = C.c_int(0)
+        self._check(self._lib.spis_resid_wait(self._h, int(ticket), C.byref(res2), C.byref(go)))
+        return float(np.sqrt(res2.value)), res2.value, bool(go.value)
+
     # -- constraints ------------------------------------------------------------------------------
     def constraint_define(self, c: int, mat_slot: int, v, cc: float):
         self._live()
@@ -285,6 +314,11 @@ class KrylovContext:
     def xcomm_connect(self, handles: bytes):
         self._live()
         self._check(self._lib.spis_xcomm_connect(self._h, C.c_char_p(handles)))
+
+    def attach_comm(self, comm_handle):
+        """Use a persistent NVLink communicator (spis_comm_create, owned by distributed.TorchComm)."""
+        self._live()
+        self._check(self._lib.spis_ctx_attach_comm(self._h, comm_handle))
 
     def xcomm_set_halo(self, dest_rank, dest_off, send_to, recv_from):
         self._live()

@@ -20,7 +20,11 @@ ordering; the kernels themselves are covered by the single-GPU tests.
 """
 from __future__ import annotations
 
+import collections
+import ctypes as C
+
 import numpy as np
+import scipy.sparse as sps
 
 from . import _native as nat
 from . import solvers
@@ -52,7 +56,9 @@ class TorchComm:
             torch.cuda.set_device(device)
             self.stream = torch.cuda.Stream(device=device)      # non-default: its handle is not NULL
         self._views = {}
-        self.counts = {"allreduce": 0, "halo": 0}
+        self.counts = {"allreduce": 0, "halo": 0, "plans_built": 0, "peer_comms_built": 0}
+        self._peer = None                    # persistent NVLink communicator: (handle, red_cap, halo_cap)
+        self._plans = collections.OrderedDict()
 
     # -- views ----------------------------------------------------------------------------------
     def _view(self, buf, count):
@@ -120,27 +126,98 @@ class TorchComm:
         self.dist.all_gather_object(gathered, [np.asarray(r, dtype=np.int64) for r in requests], group=self.group)
         return [gathered[s][self.rank] for s in range(self.world)]
 
-    def setup_peer_memory(self, ctx, plan):
-        """Switch a context to the NVLink peer-memory collectives (spis_xcomm_*): all-reduces fused
-        into the reducing kernels, halo pushed straight into the neighbours' buffers.  Only the
-        one-off exchange of IPC handles and ghost offsets goes through torch.distributed."""
-        handle = ctx.xcomm_create(self.rank, self.world, plan.n_halo)
-        info = [None] * self.world
-        self.dist.all_gather_object(info, (handle, [int(c) for c in plan.recv_counts]), group=self.group)
-        ctx.xcomm_connect(b"".join(h for h, _ in info))
-        dest_rank, dest_off = [], []
-        for peer in range(self.world):
-            cnt = int(plan.send_counts[peer])
-            if cnt:
-                # my entries land after those of lower-ranked sources in the peer's ghost ordering
-                base = sum(info[peer][1][:self.rank])
-                dest_rank.append(np.full(cnt, peer, dtype=np.int32))
-                dest_off.append(base + np.arange(cnt, dtype=np.int32))
-        dest_rank = np.concatenate(dest_rank) if dest_rank else np.zeros(0, dtype=np.int32)
-        dest_off = np.concatenate(dest_off) if dest_off else np.zeros(0, dtype=np.int32)
-        ctx.xcomm_set_halo(dest_rank, dest_off, (plan.send_counts > 0).astype(np.int32),
-                           (plan.recv_counts > 0).astype(np.int32))
-        self.dist.barrier(group=self.group)          # every rank connected before the first collective
+    def any_rank_many(self, flags):
+        """Logical OR over all ranks of several yes/no decisions, ONE collective for all of them."""
+        flags = [bool(f) for f in flags]
+        if self.world == 1 or not flags:
+            return flags
+        if self._peer is not None:
+            vals = np.array([1.0 if f else 0.0 for f in flags], dtype=np.float64)
+            lib = nat.load_library()
+            rc = lib.spis_comm_allreduce(self._peer[0], nat.dptr(vals), vals.size)
+            if rc != nat.OK:
+                raise nat.SpisError(rc, lib.spis_last_global_error().decode())
+            return [v > 0 for v in vals]
+        t = self.torch.tensor([1.0 if f else 0.0 for f in flags], dtype=self.torch.float64,
+                              device=(f"cuda:{self.device}" if self.cuda else "cpu"))
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+        return [bool(v > 0) for v in t.tolist()]
+
+    # -- persistent peer-memory communicator --------------------------------------------------------
+    def peer_comm(self, red_need, halo_need):
+        """The process-wide NVLink communicator (spis_comm_*): comm buffer, IPC mappings and flag counters are set
+        up ONCE; every later session only attaches its context.  `red_need` / `halo_need` must be the same on all
+        ranks (k_max + 5 and the largest ghost count of any rank, which the sharding plan records): the communicator
+        is rebuilt, collectively, only when one of them outgrows it."""
+        lib = nat.load_library()
+        if self._peer is not None and self._peer[1] >= red_need and self._peer[2] >= halo_need:
+            return self._peer[0]
+        if self._peer is not None:
+            self.dist.barrier(group=self.group)              # nobody is inside a collective of the old buffer
+            lib.spis_comm_destroy(self._peer[0])
+            self._peer = None
+        red_cap = max(4096, int(red_need))
+        halo_cap = max(1 << 16, 2 * int(halo_need))
+        handle = C.create_string_buffer(64)
+        comm = C.c_void_p()
+        rc = lib.spis_comm_create(self.device, self.rank, self.world, red_cap, halo_cap, handle, 64, C.byref(comm))
+        if rc != nat.OK:
+            raise nat.SpisError(rc, lib.spis_last_global_error().decode())
+        handles = [None] * self.world
+        self.dist.all_gather_object(handles, handle.raw, group=self.group)
+        rc = lib.spis_comm_connect(comm, C.c_char_p(b"".join(handles)))
+        if rc != nat.OK:
+            raise nat.SpisError(rc, lib.spis_last_global_error().decode())
+        self.dist.barrier(group=self.group)                  # every rank connected before the first collective
+        self._peer = (comm, red_cap, halo_cap)
+        self.counts["peer_comms_built"] += 1
+        return comm
+
+    def close(self):
+        if self._peer is not None:
+            nat.load_library().spis_comm_destroy(self._peer[0])
+            self._peer = None
+
+    # -- sharding plan: column localisation + halo lists, cached per system ---------------------------
+    def sharded_plan(self, mats, part):
+        """Local matrices (owned columns first, then ghosts) and the halo plan for THIS rank's rows of `mats`.
+        Building it costs host work on every index array plus two exchanges of index lists; the reference's call pattern
+        is one solver call per time step on the SAME sparsity structure (lkdv/Evolve.py:39-56), so the plan is kept,
+        keyed by the identity of the index arrays, and a later call only pairs the cached local column indices with
+        the new value arrays."""
+        mats = [sps.csr_matrix(m) for m in mats]
+        key = (id(part),) + tuple((m.shape, int(m.nnz), m.indptr.ctypes.data, m.indices.ctypes.data) for m in mats)
+        entry = self._plans.get(key)
+        if entry is None:
+            local, plan = localize(mats, part, self.rank)
+            plan.set_send_side(self.exchange_requests(plan.requests), part)
+            info = [None] * self.world
+            self.dist.all_gather_object(info, [int(c) for c in plan.recv_counts], group=self.group)
+            dest_rank, dest_off = [], []
+            for peer in range(self.world):
+                cnt = int(plan.send_counts[peer])
+                if cnt:
+                    base = sum(info[peer][:self.rank])      # my entries land after those of lower-ranked sources
+                    dest_rank.append(np.full(cnt, peer, dtype=np.int32))
+                    dest_off.append(base + np.arange(cnt, dtype=np.int32))
+            entry = {"indices": [m.indices for m in local], "ncols": local[0].shape[1] if local else 0, "plan": plan,
+                     "dest_rank": np.concatenate(dest_rank) if dest_rank else np.zeros(0, dtype=np.int32),
+                     "dest_off": np.concatenate(dest_off) if dest_off else np.zeros(0, dtype=np.int32),
+                     "send_to": (plan.send_counts > 0).astype(np.int32), "recv_from": (plan.recv_counts > 0).astype(np.int32),
+                     "halo_max": max(sum(c) for c in info), "keep": [(m.indptr, m.indices) for m in mats]}
+            self._plans[key] = entry
+            self.counts["plans_built"] += 1
+            while len(self._plans) > 4:
+                self._plans.popitem(last=False)
+        else:
+            self._plans.move_to_end(key)
+        n_r = part.n_local(self.rank)
+        local = [sps.csr_matrix((m.data, idx, m.indptr), shape=(n_r, entry["ncols"]), copy=False)
+                 for m, idx in zip(mats, entry["indices"])]
+        return local, entry
+
+    def clear_plans(self):
+        self._plans.clear()
 
     def allgather_vec(self, local):
         parts = [None] * self.world
@@ -173,21 +250,31 @@ class DistributedSession(solvers.DeviceSession):
         if pre is not None and not isinstance(pre, (solvers.JacobiPreconditioner, solvers.BlockJacobiPreconditioner)):
             raise NotImplementedError("row-sharded solves support None / Jacobi / block-Jacobi preconditioners")
         mats = [A_rows] + [c.M for c in conlist]
-        local, plan = localize(mats, part, rank)
-        plan.set_send_side(comm.exchange_requests(plan.requests), part)
+        local, entry = comm.sharded_plan(mats, part)          # cached per sparsity structure
+        plan = entry["plan"]
         self.plan = plan
         A_loc = local[0]
         cons_loc = []
         for c, M_loc in zip(conlist, local[1:]):
             cons_loc.append(type("ShardedInvariant", (), {})())
             cons_loc[-1].M, cons_loc[-1].v, cons_loc[-1].c = M_loc, c.v, c.c
+        peer = comm.peer_comm(int(k) + 5, entry["halo_max"]) if transport == "p2p" else None
+        # every decision that changes the sequence of device reductions is taken by ALL ranks together, and all of
+        # them in ONE collective: is x0 zero? which constraint matrices are identically zero (`0*A`)? which v?
+        keys, flags = ["x0"], [nat.any_nonzero(nat.as_f64(x0_loc))]
+        for idx, c in enumerate(cons_loc):
+            M = c.M
+            keys.append(("M", idx)); flags.append(bool(M.nnz != 0 and nat.any_nonzero(M.data)))
+            keys.append(("v", idx)); flags.append(nat.any_nonzero(nat.as_f64(c.v)))
+        self._preflags = dict(zip(keys, comm.any_rank_many(flags)))
 
         def factory(n, kk, device=None):
             ctx = ctx_factory(n, kk, device=(comm.device if comm.cuda else 0), n_halo=plan.n_halo,
                               stream=comm.stream_handle())
             ctx.halo_set_plan(plan.send_idx)
             if transport == "p2p":
-                comm.setup_peer_memory(ctx, plan)
+                ctx.attach_comm(peer)
+                ctx.xcomm_set_halo(entry["dest_rank"], entry["dest_off"], entry["send_to"], entry["recv_from"])
             else:
                 ctx.set_collectives(comm.allreduce, comm.make_halo(plan))
             return ctx
@@ -195,8 +282,10 @@ class DistributedSession(solvers.DeviceSession):
         super().__init__(A_loc, b_loc, x0_loc, k, conlist=cons_loc, pre=pre, orth=orth,
                          spmv_format=spmv_format, profile=profile, ctx_factory=factory)
 
-    def _any_rank(self, flag):
-        return self.comm.any_rank(flag)
+    def _any_rank(self, flag, key=None):
+        if key is not None and key in self._preflags:
+            return self._preflags[key]
+        return self.comm.any_rank(flag() if callable(flag) else flag)
 
     def gather(self, x_loc):
         """Assemble the global vector (global ordering) from the local pieces on every rank."""

@@ -30,6 +30,7 @@ import os
 import sys
 import threading
 import warnings
+import weakref
 from time import time
 
 import numpy as np
@@ -53,6 +54,8 @@ _CONFIG = {
     "profile": False,
     "async_setup": True,
     "dual_spmv": True,
+    "lazy_sessions": 2,        # solver-created sessions kept resident for lazy dict['x'] access (the newest ones)
+    "pipeline": True,          # device-resident loop (Givens update and unconstrained iterates on the GPU) with small_solver='kkt'
 }
 _ORTH = {"cgs2": nat.ORTH_CGS2, "cgs1": nat.ORTH_CGS1, "mgs": nat.ORTH_MGS}
 _FMT = {"auto": nat.FMT_AUTO, "sell": nat.FMT_SELL, "csr": nat.FMT_CSR, "sell2": nat.FMT_SELL2, "pattern": nat.FMT_PATTERN, "selld": nat.FMT_SELLD}
@@ -212,7 +215,7 @@ class DeviceSession:
         ctx.upload_vec(nat.VEC_B, b)
         tr("upload b")
         scanner.join()
-        x0_nonzero = self._any_rank(x0_scan["nz"] if "nz" in x0_scan else nat.any_nonzero(self.x0_host))
+        x0_nonzero = self._any_rank(lambda: x0_scan["nz"] if "nz" in x0_scan else nat.any_nonzero(self.x0_host), "x0")
         tr("x0 zero scan")
         if x0_nonzero:                       # a new context's x0 buffer is already zero on the device
             ctx.upload_vec(nat.VEC_X0, self.x0_host)
@@ -286,10 +289,12 @@ class DeviceSession:
                     raise ValueError(f"constraint {idx} is not a class-form constraint held on the device")
                 ctx.constraint_set_constant(idx, float(cc))
 
-    def _any_rank(self, flag):
+    def _any_rank(self, flag, key=None):
         """Logical OR of a host-side decision over all ranks (identity on one GPU).  Every decision
-        that changes the sequence of device reductions must be taken identically on all ranks."""
-        return bool(flag)
+        that changes the sequence of device reductions must be taken identically on all ranks.
+        (`key` names the decision: a row-sharded session takes all of them in one collective up front and does not
+        evaluate a callable `flag` again.)"""
+        return bool(flag() if callable(flag) else flag)
 
     # -- preconditioner: solvers.py:149-161 ------------------------------------------------------
     def _setup_precond(self, pre):
@@ -359,10 +364,10 @@ class DeviceSession:
                     M, v, c = const.M, const.v, const.c
                     anynz = getattr(self.ctx, "any_nonzero", nat.any_nonzero)
                     if sps.issparse(M):
-                        M_zero = not self._any_rank(M.nnz != 0 and anynz(M.data))
+                        M_zero = not self._any_rank(lambda: M.nnz != 0 and anynz(M.data), ("M", idx))
                     else:
                         M = np.asarray(M, dtype=np.float64)
-                        M_zero = not self._any_rank(M.any())
+                        M_zero = not self._any_rank(lambda: M.any(), ("M", idx))
                     tr("  constraint %d: is M zero? %s" % (idx, M_zero))
                     slot = -1
                     if not M_zero:
@@ -373,7 +378,7 @@ class DeviceSession:
                     if type(self) is DeviceSession:        # the library recognises an all-zero v itself
                         self.ctx.constraint_define(idx, slot, v, float(c))
                     else:                                  # row-sharded: every rank must take the same decision
-                        self.ctx.constraint_define(idx, slot, v if self._any_rank(nat.any_nonzero(v)) else None, float(c))
+                        self.ctx.constraint_define(idx, slot, v if self._any_rank(lambda: nat.any_nonzero(v), ("v", idx)) else None, float(c))
                     tr("  constraint %d: v" % idx)
                 except nat.NativeLibraryError:
                     raise
@@ -487,6 +492,12 @@ class IterateHistory(collections.abc.Sequence):
 
     def materialise(self):
         return [self[i] for i in range(len(self))]
+
+    def detach(self):
+        """Copy every iterate to the host; the history no longer needs (or pins) the device session."""
+        for i in range(len(self)):
+            self[i]
+        return self
 
 
 # ==============================================================================================
@@ -638,22 +649,238 @@ class _Arnoldi:
             self._inflight = None
 
 
+class _Pipeline:
+    """Drives the device-resident Krylov loop (spis_pipe_begin / spis_step_enqueue, include/spis_b200.h).
+
+    Whole Arnoldi steps are queued AHEAD of the host: the Givens update and the least-squares coefficients y_j are
+    computed by a one-warp kernel, the unconstrained iterate x_j = x0 + Z y_j (solvers.py:287) is formed by a sweep that
+    was queued before y_j existed, and its true residual (solvers.py:290) is measured by the SpMV of a later step.  The
+    host reads records (Hessenberg column, y_j, min |beta e1 - H y|, residual norms) from mapped memory, follows the
+    reference's control flow with them and decides how far ahead to queue.  Index conventions:
+        lag = 1 without a preconditioner: step s forms x_{s-1} in its last sweep (Z is V) and measures x_{s-2};
+        lag = 0 with a device preconditioner: step s forms x_s with a sweep over Z and measures x_{s-1}.
+    The device stops forming iterates by itself (phase word) once a measured residual is <= thr, so steps queued
+    ahead of the host's decision never overwrite an iterate the host is responsible for.
+    """
+
+    DEPTH = 3                      # steps queued beyond the last record the host has seen (records live in rings of 8)
+
+    def __init__(self, sess, k, beta, thr, tol, last_unconstrained):
+        self.sess, self.ctx, self.k = sess, sess.ctx, k
+        self.beta, self.thr, self.tol = float(beta), float(thr), tol
+        self.thr2 = self.thr * self.thr
+        self.last_it = last_unconstrained          # largest iterate index the device may form (cgmres: k-2, gmres: k-1)
+        self.lag = int(sess.ctx.info("pipe_lag"))
+        self.H = np.zeros((k + 1, k))
+        self.enq = 0
+        self.rec = {}                              # step -> (col, y, info)
+        self.it_step = {}                          # iterate index -> step that was asked to form it
+        self.res_ticket = {}                       # iterate index -> ticket of its residual measurement
+        self.measured = set()
+        self.device_iter = True                    # False once the host forms the iterates itself
+        self.x_holds = None                        # iterate index known to be in the X buffer
+        self._ls_prev = None
+        self.ctx.pipe_begin(self.thr, not (self.beta > self.thr))
+
+    # -- queueing ---------------------------------------------------------------------------------------------
+    def _enqueue(self):
+        s = self.enq
+        i = s - self.lag
+        want_it = self.device_iter and 0 <= i <= self.last_it
+        ip = s - 1 - self.lag                      # the iterate step s-1 was asked to form sits in X when step s multiplies
+        want_res = ip >= 0 and self.it_step.get(ip) == s - 1 and ip not in self.res_ticket and ip not in self.measured
+        ticket = self.ctx.step_enqueue(s, want_res, want_it)
+        if want_res:
+            self.res_ticket[ip] = ticket
+        if want_it:
+            self.it_step[i] = s
+        self.enq = s + 1
+
+    def _record(self, s):
+        if s not in self.rec:
+            while self.enq <= s:
+                self._enqueue()
+            self.rec[s] = self.ctx.step_wait(s)
+            self.rec.pop(s - 16, None)
+        return self.rec[s]
+
+    def column(self, j):
+        col, y, info = self._record(j)
+        self.H[: j + 2, j] = col
+        self._speculate(j, info)
+        return col
+
+    def _speculate(self, j, info):
+        """Queue the steps that are (almost) certainly needed so that the device never waits for the host: step s is
+        needed iff iteration s-1 does not end the loop, which it cannot while even the unconstrained minimiser
+        |beta e1 - H y|_min (known for step j, extrapolated by the last reduction factor beyond) stays above tol."""
+        if not info["valid"]:
+            return
+        ls = info["ls"]
+        rate = 1.0 if not self._ls_prev else min(1.0, ls / self._ls_prev)
+        self._ls_prev = ls
+        est = ls
+        for s in range(j + 1, min(self.k, j + 1 + self.DEPTH)):
+            if self.tol is not None:
+                need = est >= self.tol if s == j + 1 else est * rate >= self.tol
+                if not need:
+                    break
+            if self.enq <= s:
+                self._enqueue()
+            est *= rate
+
+    def prefetch(self, s):
+        if s < self.k:
+            while self.enq <= s:
+                self._enqueue()
+
+    # -- small problem ------------------------------------------------------------------------------------------
+    def ls_solution(self, m):
+        col, y, info = self._record(m - 1)
+        return y.copy() if info["valid"] else None
+
+    def ls_residual(self, j):
+        info = self._record(j)[2]
+        return info["ls"] if info["valid"] else np.inf
+
+    def predicted_residual(self, y):
+        m = len(y)
+        r = -(self.H[: m + 1, :m] @ y)
+        r[0] += self.beta
+        return float(np.linalg.norm(r))
+
+    # -- iterates -------------------------------------------------------------------------------------------------
+    def device_iterate_residual(self, j, yk, cannot_end):
+        """||A x_j - b|| of the UNCONSTRAINED iterate x_j = x0 + Z yk.  Normally the device has formed (or is about to
+        form) it from its own copy of yk; the norm rides on the SpMV of the next step when that step is needed anyway,
+        else it takes a pass of its own.  `cannot_end`: iteration j cannot be the last one (cgmres only stops on a
+        constrained step).  Returns (norm, go): go = the next iteration is still unconstrained as far as the residual
+        is concerned (solvers.py:230)."""
+        ctx = self.ctx
+        s_form = j + self.lag
+        formed = False
+        if self.device_iter and j <= self.last_it and s_form < self.k:
+            while self.enq <= s_form:
+                self._enqueue()
+            if self.it_step.get(j) == s_form:
+                formed = self._record(s_form)[2]["phase"] == 0
+        if not formed:
+            # the device did not form this one (phase word set by a vanishing pivot, last Krylov vector, ...)
+            self.device_iter = False
+            res = ctx.iterate_residual(yk)
+            self.x_holds = j
+            self.measured.add(j)
+            return res, res > self.thr
+        self.x_holds = j
+        if j not in self.res_ticket and s_form + 1 < self.k and self.enq == s_form + 1:
+            # step s_form+1 is needed iff iteration s_form does not end the loop
+            need = self.tol is None or (cannot_end and self.lag == 0) or self.ls_residual(s_form) >= self.tol
+            if need:
+                self._enqueue()                   # its SpMV measures x_j on the way
+        if j in self.res_ticket:
+            res, res2, go = ctx.resid_wait(self.res_ticket[j])
+            self.measured.add(j)
+            if not go and res2 > self.thr2:       # the phase word was set for another reason: the host forms the iterates from now on
+                self.device_iter = False
+            return res, res2 > self.thr2
+        if self.enq > s_form + 1:
+            # a later step is queued without the measurement (cannot happen with the rules above); re-form to be safe
+            res = ctx.iterate_residual(yk)
+        else:
+            ctx.residual_launch()
+            res = ctx.iterate_residual_wait()
+        self.measured.add(j)
+        return res, res > self.thr
+
+    def host_iterate_residual(self, j, yk):
+        """x_j = x0 + Z yk with coefficients from the host (constrained steps, fallbacks) and its residual norm."""
+        self.device_iter = False
+        self.ctx.iterate_residual_launch(yk)
+        res = self.ctx.iterate_residual_wait()
+        self.x_holds = j
+        self.measured.add(j)
+        return res
+
+    def host_takes_over(self):
+        """From now on the host forms every iterate (constrained phase): steps queued later do not touch X."""
+        self.device_iter = False
+
+    def finish(self, j_last, y_last):
+        """Leave x_{j_last} in the X buffer (a step queued ahead may have formed a later iterate)."""
+        if j_last is not None and self.x_holds != j_last:
+            self.ctx.form_iterate(y_last)
+            self.x_holds = j_last
+
+
+def _use_pipeline(sess, lookahead, engine):
+    ctx = sess.ctx
+    return (bool(lookahead) and engine == "kkt" and _opt("pipeline", None) and sess._host_pre is None
+            and hasattr(ctx, "step_enqueue") and ctx.info("device_pipeline") == 1)
+
+
 def _acquire(session, A, b, x0, k, conlist, pre, device, orth):
     if session is not None:
         if session.k < k:
             raise ValueError(f"session was created for k={session.k} < {k}")
         return session
-    return DeviceSession(A, b, x0, k, conlist=conlist, pre=pre, device=device, orth=orth)
+    sess = DeviceSession(A, b, x0, k, conlist=conlist, pre=pre, device=device, orth=orth)
+    sess._owned_by_solver = True
+    return sess
+
+
+# Sessions the solvers created themselves and that are kept alive only because a lazy dict['x'] may still be read:
+# the newest `lazy_sessions` of them.  A caller that keeps many info dicts (convergence studies, SingleSolve-style
+# scripts) would otherwise pin one multi-GB device workspace per call until the dicts are dropped.
+_LAZY_SESSIONS = collections.OrderedDict()
+_EAGER_BYTES = 32 << 20          # histories up to this size are simply copied to the host (and the session closed)
+_EVICT_COPY_BYTES = 1 << 30      # an evicted history up to this size is copied to the host first, larger ones lapse
+
+
+def _retire_lazy(keep):
+    for key in list(_LAZY_SESSIONS):
+        sess, href = _LAZY_SESSIONS[key]
+        hist = href()
+        if hist is None or sess.ctx.closed:
+            _LAZY_SESSIONS.pop(key)
+            if not sess.ctx.closed:
+                sess.close()
+    while len(_LAZY_SESSIONS) > keep:
+        key, (sess, href) = _LAZY_SESSIONS.popitem(last=False)
+        hist = href()
+        if hist is not None and len(hist) * sess.n * 8 <= _EVICT_COPY_BYTES:
+            hist.detach()
+        sess.close()
 
 
 def _finish_history(hist, history_mode, x_last):
+    """dict['x'] for the caller.  'lazy' (default) keeps the iterates on the device as Krylov coefficients; for a
+    session the solver created itself that pins the device workspace ((k+1) n doubles of basis and more), so small
+    histories are copied eagerly and only the newest `lazy_sessions` lazy ones stay resident (older ones are copied to
+    the host if they fit 1 GiB, else they lapse and say so when read)."""
     if x_last is not None:
         hist._set_cached(len(hist) - 1, x_last)
-    if history_mode == "eager":
-        return hist.materialise()
-    if history_mode != "lazy":
+    if history_mode not in ("lazy", "eager"):
         raise ValueError("history must be 'lazy' or 'eager'")
+    sess = hist._session
+    own = getattr(sess, "_owned_by_solver", False)
+    if history_mode == "eager" or (own and len(hist) * sess.n * 8 <= _EAGER_BYTES):
+        out = hist.materialise()
+        if own:
+            sess.close()
+        return out if history_mode == "eager" else hist.detach()
+    if own:
+        _retire_lazy(max(int(_opt("lazy_sessions", None)), 1) - 1)
+        _LAZY_SESSIONS[id(sess)] = (sess, weakref.ref(hist))
     return hist
+
+
+def _abandon(sess):
+    """An exception is leaving a solver: do not leave a session it created to the garbage collector."""
+    if getattr(sess, "_owned_by_solver", False):
+        try:
+            sess.close()
+        except Exception:
+            pass
 
 
 def _unconstrained(engine, Hj, beta, y0, ftol, arn=None):
@@ -683,7 +910,17 @@ def gmres(A, b, x0, k, tol=1e-50, pre=None, *, session=None, lookahead=None, his
           device=None, orth=None, small_solver=None):
     """Right-preconditioned flexible GMRES; returns (x_last, {'name','x','res','steps'})."""
     sess = _acquire(session, A, b, x0, k, (), pre, device, orth)
+    try:
+        return _gmres_run(sess, k, tol, lookahead, history)
+    except BaseException:
+        _abandon(sess)
+        raise
+
+
+def _gmres_run(sess, k, tol, lookahead, history):
     beta = sess.begin()                                   # r0, ||r0||, q0       (solvers.py:78-88)
+    if _use_pipeline(sess, _opt("lookahead", lookahead), "kkt"):
+        return _gmres_pipelined(sess, k, tol, beta, _opt("history", history))
     arn = _Arnoldi(sess, k, _opt("lookahead", lookahead), beta)
     hist = IterateHistory(sess)
     residual = [beta]
@@ -714,6 +951,39 @@ def gmres(A, b, x0, k, tol=1e-50, pre=None, *, session=None, lookahead=None, his
     return x_last, info
 
 
+def _gmres_pipelined(sess, k, tol, beta, history_mode):
+    """gmres on the device-resident loop: y_j is the Givens least-squares solution (what np.linalg.lstsq returns for
+    a full-rank Hessenberg matrix, solvers.py:113) computed on the GPU; a vanishing pivot hands it back to lstsq."""
+    pipe = _Pipeline(sess, k, beta, tol, tol, last_unconstrained=k - 1)
+    hist = IterateHistory(sess)
+    residual = [beta]
+    steps = 0
+    yk = None
+    for j in range(k):
+        steps = j + 1
+        col = pipe.column(j)                              # (solvers.py:94-100)
+        if not col[j + 1] != 0:
+            warnings.warn(_BREAKDOWN)                     # (solvers.py:104-106)
+            break
+        yk = pipe.ls_solution(j + 1)
+        if yk is None:
+            yk = smallsolve.lstsq(pipe.H[: j + 2, : j + 1], beta).x        # (solvers.py:113)
+            res = pipe.host_iterate_residual(j, yk)
+        else:
+            res, _go = pipe.device_iterate_residual(j, yk, cannot_end=False)
+        residual.append(res)                              # (solvers.py:115-116)
+        hist._append(yk)
+        if residual[-1] < tol:
+            break
+    pipe.finish(len(hist) - 2 if len(hist) > 1 else None, hist._ys[-1] if len(hist) > 1 else None)
+    x_last = sess.ctx.download(nat.VEC_X, pinned=True) if len(hist) > 1 else hist[0]
+    info = {"name": "gmres",
+            "x": _finish_history(hist, history_mode, x_last),
+            "res": residual[1:],
+            "steps": steps}
+    return x_last, info
+
+
 # ==============================================================================================
 # CGMRES (solvers.py:131-323)
 # ==============================================================================================
@@ -721,17 +991,28 @@ def cgmres(A, b, x0, k, tol=1e-8, contol=10, conlist=[], pre=None, timing=None, 
            session=None, small_solver=None, lookahead=None, history=None, device=None, orth=None):
     """Conservative FGMRES: unconstrained until residual <= contol*tol, then the reduced
     quadratic invariants are imposed as equality constraints on the Krylov coefficients."""
-    ctol = 1e-12                                          # (solvers.py:138)
     engine = _opt("small_solver", small_solver)
     if engine not in ("slsqp", "kkt"):
         raise ValueError("small_solver must be 'slsqp' or 'kkt'")
+    jit = None
     if timing:
         jit = {"start": time(), "start_iter": [], "end_iter": [],
                "start_constraints": [], "end_constraints": []}
     tr = _Trace()
     sess = _acquire(session, A, b, x0, k, conlist, pre, device, orth)
+    try:
+        return _cgmres_run(sess, k, tol, contol, timing, jit, engine, lookahead, history, tr)
+    except BaseException:
+        _abandon(sess)
+        raise
+
+
+def _cgmres_run(sess, k, tol, contol, timing, jit, engine, lookahead, history, tr):
+    ctol = 1e-12                                          # (solvers.py:138)
     safety = None                                         # (solvers.py:163)
     beta = sess.begin()
+    if _use_pipeline(sess, _opt("lookahead", lookahead), engine):
+        return _cgmres_pipelined(sess, k, tol, contol, beta, timing, jit, _opt("history", history), tr)
     arn = _Arnoldi(sess, k, _opt("lookahead", lookahead), beta)
     tr("cgmres: session + r0")
     hist = IterateHistory(sess)
@@ -840,6 +1121,130 @@ def cgmres(A, b, x0, k, tol=1e-8, contol=10, conlist=[], pre=None, timing=None, 
     return x_last, info
 
 
+def _cgmres_timings(jit, constrained_steps):
+    """The reference's timing dictionary (solvers.py:300-312)."""
+    jit["end"] = time()
+    iter_time = np.asarray(jit["end_iter"]) - np.asarray(jit["start_iter"][: len(jit["end_iter"])])
+    iter_unconstrained = iter_time[:-constrained_steps]
+    assembly = np.asarray(jit["end_constraints"]) - np.asarray(jit["start_constraints"])
+    iter_constrained = iter_time[len(iter_unconstrained):] - assembly
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        return {"runtime": jit["end"] - jit["start"],
+                "iter_time_unconstrained": np.mean(iter_unconstrained),
+                "iter_time_constrained": np.mean(iter_constrained),
+                "constraint_building": np.mean(assembly),
+                "constrained_steps": constrained_steps}
+
+
+def _cgmres_pipelined(sess, k, tol, contol, beta, timing, jit, history_mode, tr):
+    """cgmres (solvers.py:186-297) on the device-resident loop, small_solver='kkt'.  The control flow is the
+    reference's; what changes is who computes what in an UNCONSTRAINED iteration: the device (Givens update, y_j, x_j,
+    the residual norm, and the `residual[-1] > contol*tol` test for the steps it has already been given), while this
+    loop follows through the records and owns every constrained step."""
+    ctol = 1e-12                                          # (solvers.py:138)
+    thr = contol * tol
+    pipe = _Pipeline(sess, k, beta, thr, tol, last_unconstrained=k - 2)
+    tr("cgmres: session + r0")
+    hist = IterateHistory(sess)
+    residual = [beta]
+    go = beta > thr                                       # `residual[-1] > contol*tol` for the next iteration
+    safety = None                                         # (solvers.py:163)
+    constrained_steps = 0
+    steps = 0
+    yk = None
+    bk = _Buckets()
+    for j in range(k):
+        if timing:
+            jit["start_iter"].append(time())
+        steps = j + 1
+        bk.mark("host")
+        col = pipe.column(j)
+        bk.mark("arnoldi wait")
+        if not col[j + 1] != 0:
+            warnings.warn(_BREAKDOWN)                     # (solvers.py:199-202)
+            break
+        Hj = pipe.H[: j + 2, : j + 1]
+        y0 = np.zeros(j + 1)
+        if j != 0:
+            y0[:-1] = yk                                  # warm start (solvers.py:225-227)
+
+        def unconstrained():
+            y = pipe.ls_solution(j + 1)
+            return smallsolve.SmallResult(y) if y is not None else smallsolve.lstsq(Hj, beta)
+
+        if go and j < k - 1 and safety is None:           # (solvers.py:230)
+            res = unconstrained()
+            yk = res.x
+            bk.mark("small solve + host")
+            if pipe.ls_solution(j + 1) is not None:
+                r, go = pipe.device_iterate_residual(j, yk, cannot_end=True)
+            else:
+                r = pipe.host_iterate_residual(j, yk)
+                go = r > thr
+            residual.append(r)                            # (solvers.py:287,290)
+        else:
+            pipe.host_takes_over()
+            try:
+                if timing:
+                    constrained_steps += 1
+                    jit["start_constraints"].append(time())
+                bk.mark("host")
+                cons = sess.containers(j + 1)             # (solvers.py:242-247)
+                bk.mark("constraint terms")
+                if timing:
+                    jit["end_constraints"].append(time())
+                # the loop can only end in this branch (solvers.py:296): see cgmres above
+                may_end = pipe.ls_residual(j) < tol
+                if not may_end:
+                    pipe.prefetch(j + 1)
+                res = _constrained("kkt", Hj, beta, y0, cons, ctol ** 2, None)   # (solvers.py:251-255)
+                if may_end and not pipe.predicted_residual(res.x) < tol:
+                    pipe.prefetch(j + 1)
+                if not timing and np.isnan(max(res.x)):
+                    raise ValueError("constrained solve returned NaN")           # (solvers.py:258-260)
+                safety = True
+                if not timing:
+                    dev = constraint_checker(res.x, [c.as_scipy() for c in cons])
+                    if dev > ctol:
+                        safety = False                    # (solvers.py:266-278, quirk Q4: unconstrained fallback)
+                        raise RuntimeError("Iteration %d failed to preserve constraints with "
+                                           "deviation of %e" % (j, dev))
+            except (nat.SpisError, nat.NativeLibraryError):
+                raise                                     # device failures are never swallowed
+            except Exception:
+                warnings.warn("Constrained solve failed, defaulted to standard solve for iteration %d."
+                              " Problem likely overconstrained, a smaller solver tolerance may be "
+                              "required." % j, RuntimeWarning)
+                if timing and len(jit["end_constraints"]) < len(jit["start_constraints"]):
+                    jit["end_constraints"].append(time())
+                pipe.prefetch(j + 1)
+                res = unconstrained()                     # (solvers.py:274-278)
+            _warn_message(j, res)
+            yk = res.x
+            bk.mark("small solve + host")
+            residual.append(pipe.host_iterate_residual(j, yk))                   # (solvers.py:287,290)
+            go = residual[-1] > thr
+        bk.mark("iterate+residual")
+        hist._append(yk)
+        if timing:
+            jit["end_iter"].append(time())
+        if residual[-1] < tol and safety is True:         # (solvers.py:296-297)
+            break
+    pipe.finish(len(hist) - 2 if len(hist) > 1 else None, hist._ys[-1] if len(hist) > 1 else None)
+    bk.report("cgmres")
+    tr("cgmres: Krylov loop (%d steps)" % steps)
+    timings = _cgmres_timings(jit, constrained_steps) if timing else None
+    x_last = sess.ctx.download(nat.VEC_X, pinned=True) if len(hist) > 1 else hist[0]
+    tr("cgmres: download x")
+    info = {"name": "cgmres",
+            "x": _finish_history(hist, history_mode, x_last),
+            "res": residual[1:],
+            "steps": steps,
+            "timings": timings}
+    return x_last, info
+
+
 # ==============================================================================================
 # prototypical CGMRES (solvers.py:328-445)
 # ==============================================================================================
@@ -850,6 +1255,14 @@ def cgmres_p(A, b, x0, k, conlist=[], pre=None, *, session=None, small_solver=No
     if engine not in ("slsqp", "kkt"):
         raise ValueError("small_solver must be 'slsqp' or 'kkt'")
     sess = _acquire(session, A, b, x0, k, conlist, pre, device, orth)
+    try:
+        return _cgmres_p_run(sess, k, engine, lookahead, history)
+    except BaseException:
+        _abandon(sess)
+        raise
+
+
+def _cgmres_p_run(sess, k, engine, lookahead, history):
     arn = _Arnoldi(sess, k, _opt("lookahead", lookahead))
     beta = sess.begin()
     hist = IterateHistory(sess)

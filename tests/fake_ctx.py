@@ -54,6 +54,11 @@ class FakeKrylovContext:
                 threading.current_thread() is threading.main_thread()
 
     def info(self, key):
+        if key == "device_pipeline":
+            return int(self.opts.get("orth", nat.ORTH_CGS2) == nat.ORTH_CGS2 and self.pre_kind != nat.PRE_HOST
+                       and self.allreduce is None and self.halo_cb is None)
+        if key == "pipe_lag":
+            return int(self.pre_kind == nat.PRE_NONE)
         if key == "can_fuse_iterate":
             return int(self.pre_kind == nat.PRE_NONE and self.opts.get("orth", nat.ORTH_CGS2) == nat.ORTH_CGS2
                        and self.opts.get("fuse_iterate", 1))
@@ -223,6 +228,85 @@ class FakeKrylovContext:
         self.log.append(("iterate", len(y)))
         r = self._spmv(nat.SLOT_A, self.Xfull) - self.vecs[nat.VEC_B]
         return float(np.sqrt(self._ar(r @ r)[0]))
+
+    # ---- pipelined loop (spis_pipe_begin / spis_step_enqueue): same records, computed at enqueue time
+    def pipe_begin(self, thr, phase0):
+        k = self.k_max
+        beta = float(np.sqrt(self.r0 @ self.r0))
+        self._pipe = {"thr2": float(thr) * float(thr), "phase": 1 if phase0 else 0, "cs": np.zeros(k), "sn": np.zeros(k),
+                      "gv": np.concatenate([[beta], np.zeros(k)]), "R": np.zeros((k, k)), "tracking": True,
+                      "y": {}, "rec": {}, "res": []}
+        self.log.append(("pipe_begin", bool(phase0)))
+
+    def step_enqueue(self, j, want_residual, want_iterate):
+        P = self._pipe
+        n, m = self.n, j + 1
+        nopre = self.pre_kind == nat.PRE_NONE
+        ticket = -1
+        if not nopre:
+            self.Zs[j, :n] = self._apply_pre(self.V[j, :n])
+        if want_residual:
+            r = self._spmv(nat.SLOT_A, self.Xfull) - self.vecs[nat.VEC_B]
+            res2 = float(self._ar(r @ r)[0])
+            if not res2 > P["thr2"]:
+                P["phase"] = 1
+            P["res"].append((res2, P["phase"]))
+            ticket = len(P["res"]) - 1
+        w = self._spmv(nat.SLOT_A, self._Z()[j])
+        Vm = self.V[:m, :n]
+        h1 = self._ar(Vm @ w)
+        w = w - Vm.T @ h1
+        h2 = self._ar(Vm @ w)
+        nw2 = float(self._ar(w @ w)[0])
+        s2 = float(h2 @ h2)
+        n2 = nw2 - s2
+        if not n2 > 0.0:
+            n2 = 0.0
+        col = np.concatenate([h1 + h2, [np.sqrt(n2)]])
+        # Givens update and back substitution (hess_kernel)
+        valid, ls, y = P["tracking"], 0.0, np.zeros(m)
+        if valid:
+            r = col.copy()
+            for i in range(j):
+                a, b = r[i], r[i + 1]
+                r[i] = P["cs"][i] * a + P["sn"][i] * b
+                r[i + 1] = -P["sn"][i] * a + P["cs"][i] * b
+            den = np.hypot(r[j], r[j + 1])
+            if den > 0:
+                P["cs"][j], P["sn"][j] = r[j] / den, r[j + 1] / den
+                P["R"][:j, j] = r[:j]
+                P["R"][j, j] = den
+                gj = P["gv"][j]
+                P["gv"][j], P["gv"][j + 1] = P["cs"][j] * gj, -P["sn"][j] * gj
+                ls = abs(P["gv"][j + 1])
+                d = np.abs(np.diag(P["R"][:m, :m]))
+                valid = bool(d.min() > 1e-14 * d.max())
+                if valid:
+                    y = np.linalg.solve(P["R"][:m, :m], P["gv"][:m])
+            else:
+                P["tracking"] = valid = False
+        if not valid:
+            P["phase"] = 1
+        P["y"][j] = y
+        P["rec"][j] = (col, y.copy(), {"valid": valid, "ls": float(ls), "norm2": n2, "nw2": nw2, "s2": s2, "phase": P["phase"]})
+        w = w - Vm.T @ h2
+        self.V[j + 1, :n] = w / col[m] if col[m] > 0 else 0.0
+        formed = None
+        if want_iterate and P["phase"] == 0:
+            if nopre and j >= 1:
+                self.form_iterate(P["y"][j - 1]); formed = j - 1
+            elif not nopre:
+                self.form_iterate(P["y"][j]); formed = j
+        self.log.append(("step", j, bool(want_residual), bool(want_iterate), formed))
+        return ticket
+
+    def step_wait(self, j):
+        col, y, info = self._pipe["rec"][j]
+        return col.copy(), y.copy(), dict(info)
+
+    def resid_wait(self, ticket):
+        res2, phase = self._pipe["res"][ticket]
+        return float(np.sqrt(res2)), res2, phase == 0
 
     # ---- constraints
     def constraint_define(self, c, slot, v, cc):
