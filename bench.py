@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Headline benchmark: conservative FGMRES (CGMRES) on the 1e7-DOF linear-KdV system.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n 10000000]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--dofs 10000000] [--workload lkdv|swe|lkdvRK]
 
 Workload (BASELINE.json configs[1]): periodic P1 linear KdV midpoint step re-assembled in numpy
 (structurepreservingiterativesolvers_b200/problems/lkdv.py, h = 0.8 and dt = 0.01 held fixed, field-blocked
@@ -13,6 +13,16 @@ One "step" = one full solve.  `value` = Krylov iterations per second with the sy
 HBM (DeviceSession built before the timed region); `e2e` = the same metric through the public
 `solvers.cgmres(A, b, x0, ...)` call with pinned HOST buffers, i.e. including the upload of the CSR
 matrix, vectors and constraint matrices, the solve, and the download of the solution.
+
+On one GPU the same run also carries (all in the one JSON line):
+  cpu_baseline + parity   the oracle (numpy/scipy restatement of the reference, pinned to outputs of the unmodified
+                          reference) solving the SAME full workload once on the host cores, and the GPU solution
+                          compared with it: rel_diff, steps_equal, invariant deviations, residual histories;
+  extra                   the other BASELINE configurations and SURVEY 8(d) runs on the same box: the general-matrix
+                          path (values perturbed by one ulp: SELL storage), fixed-k = 50, the reference's three-constraint
+                          list, Jacobi on, swe at 1e7 (configs[2]) and the lkdvRK stage system (configs[3]).
+On N > 1 GPUs: the same 1e7 system row-sharded (strong scaling), `parity_vs_single` (the gathered solution against a
+single-GPU solve on rank 0) and `extra.swe_1e8` (configs[4]).
 
 The inputs (basis 4 GB, matrix 0.8 GB) are far larger than the 126 MB L2, so no L2 flush is needed
 between timed iterations.
@@ -36,20 +46,31 @@ if ROOT not in sys.path:
 
 K_KRYLOV = 50
 CONTOL = 10
-TOL = 1e-6                       # default workload (lkdv); WORKLOADS[...]["tol"] is what the code uses
+T_START = time.perf_counter()
 WORKLOADS = {
     # BASELINE.json configs[1]: the configuration the metric is quoted on
-    "lkdv": dict(tol=1e-6, label="lkdv P1 periodic linear KdV", cons="mass+energy"),
+    "lkdv": dict(tol=1e-6, label="lkdv P1 periodic linear KdV", cons="mass+energy", pre="no preconditioner"),
     # configs[2] / configs[4]: swe/TimedSolve.py:17 tolerance, RT_2 x DG_0 on the periodic square
-    "swe": dict(tol=1e-7, label="swe RT2xDG0 linearised rotating shallow water", cons="mass+energy"),
+    "swe": dict(tol=1e-7, label="swe RT2xDG0 linearised rotating shallow water", cons="mass+energy", pre="no preconditioner"),
+    # configs[3]: two-stage Gauss-Legendre stage system of lkdvRK/lkdvRK.py:107-118, constraints on the RK update
+    # (lkdvRK/LinearSolver.py:29-76) as class-form quadratics in the stage vector, 6x6 node-block Jacobi
+    # (the reference preconditions with SuperLU ILU, lkdvRK/Evolve.py:51), x0 = 0.01 tile(z0) (Evolve.py:37)
+    "lkdvRK": dict(tol=None, label="lkdvRK Gauss-Legendre(2) stage system of linear KdV (P1)", cons="mass+momentum+energy (structured)",
+                   pre="6x6 node-block Jacobi"),
 }
 
 
+def elapsed():
+    return time.perf_counter() - T_START
+
+
 # ------------------------------------------------------------------------------------------------
-def build_system(n_target, workload="lkdv", rank=0, world=1):
-    """Returns (dic, x0, conlist, part).  world == 1: the global system.  world > 1: THIS RANK'S rows
-    (global column ids) -- lkdv slices the global matrix, swe assembles its strip directly."""
+def build_system(n_target, workload="lkdv", rank=0, world=1, keep_global=False):
+    """Returns (dic, x0, conlist, part, pre, glob).  world == 1: the global system.  world > 1: THIS RANK'S rows
+    (global column ids) -- lkdv slices the global matrix, swe assembles its strip directly.  glob: the global
+    (dic, x0, conlist) when keep_global (rank 0's single-GPU comparison solve), else None."""
     from structurepreservingiterativesolvers_b200 import wrappers
+    glob = None
     if workload == "lkdv":
         from structurepreservingiterativesolvers_b200.problems import lkdv
         M = lkdv.benchmark_size(n_target)
@@ -57,16 +78,29 @@ def build_system(n_target, workload="lkdv", rank=0, world=1):
         x0 = np.zeros(dic["b"].size)
         full = wrappers.lkdv.conlist(dic, x0)
         conlist = [full[0], full[2]]                       # mass + energy (BASELINE.json configs[1])
+        dic["conlist3"] = full
         part = None
         if world > 1:
             from structurepreservingiterativesolvers_b200.partition import FieldBlockPartition
+            if keep_global:
+                glob = (dic, x0, conlist)
             part = FieldBlockPartition(3, dic["b"].size // 3, world)
             ids = part.global_ids(rank)
-            glob = dict(n=int(dic["b"].size), nnz=int(dic["A"].nnz))
-            dic = {"A": dic["A"][ids], "b": dic["b"][ids], **glob}
+            meta = dict(n=int(dic["b"].size), nnz=int(dic["A"].nnz))
+            dic = {"A": dic["A"][ids], "b": dic["b"][ids], **meta}
             x0 = x0[ids]
             conlist = [type(c)(c.M.tocsr()[ids], np.asarray(c.v, dtype=np.float64).reshape(-1)[ids], c.c, c.name) for c in conlist]
-        return dic, x0, conlist, part
+        return dic, x0, conlist, part, None, glob
+    if workload == "lkdvRK":
+        from structurepreservingiterativesolvers_b200.preconditioners import BlockJacobiPreconditioner
+        from structurepreservingiterativesolvers_b200.problems import lkdvRK
+        M = max(8, int(round(n_target / 6)))
+        dic, prob = lkdvRK.linforms(M=M, space="CG", mlength=0.8 * M)
+        x0 = 0.01 * np.tile(dic["z0"], prob.ns)
+        conlist = wrappers.lkdvRK.conlist_structured(dic, x0, prob)
+        dic["tol"] = 1e-6 * float(np.sqrt(dic["b"].size / 600.0))     # the residual scales like sqrt(n): 1e-6 at the reference's n = 600
+        dic["prob"] = prob
+        return dic, x0, conlist, None, BlockJacobiPreconditioner(dic["A"], 6, "field"), None
     from structurepreservingiterativesolvers_b200.problems import swe
     M = swe.benchmark_size(n_target)
     part = None
@@ -75,12 +109,16 @@ def build_system(n_target, workload="lkdv", rank=0, world=1):
         from structurepreservingiterativesolvers_b200.partition import StripPartition
         part = StripPartition((swe.NU * M, swe.NR * M), M, world)
         rows = part.block_range(rank)
+        if keep_global:
+            gd, _ = swe.linforms(M=M, mlength=0.8 * M, sort=False)
+            gx0 = np.zeros(gd["b"].size)
+            glob = (gd, gx0, wrappers.swe.conlist(gd, gx0))
     dic, prob = swe.linforms(M=M, mlength=0.8 * M, rows=rows, sort=False)
     dic["n"] = 12 * M * M
     dic["nnz"] = int(12.5 * 12 * M * M)
     x0 = np.zeros(dic["b"].size)
     conlist = wrappers.swe.conlist(dic, x0)                # mass + energy (swe/LinearSolver.py:23-36)
-    return dic, x0, conlist, part
+    return dic, x0, conlist, part, None, glob
 
 
 def pin_inputs(dic, x0, conlist):
@@ -201,20 +239,22 @@ def peak_hbm():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def workload_tol(workload, dic):
+    return WORKLOADS[workload]["tol"] if WORKLOADS[workload]["tol"] is not None else float(dic["tol"])
+
+
+def workload_config(workload, dic, where, tol):
+    w = WORKLOADS[workload]
+    n = int(dic.get("n", dic["b"].size))
+    nnz = int(dic.get("nnz", dic["A"].nnz))
+    return {"workload": f"{w['label']}, n={n}, nnz={nnz}, cgmres k={K_KRYLOV} tol={tol:g} contol={CONTOL} "
+                        f"{w['cons']} constraints, x0={'0' if workload != 'lkdvRK' else '0.01*tile(z0)'}, {w['pre']}",
+            "n": n, "nnz": nnz, "k": K_KRYLOV,
+            "l2": f"working set (basis {8e-9 * (K_KRYLOV + 1) * n:.1f} GB + matrix {12e-9 * nnz:.1f} GB) >> 126 MB L2: no flush between iterations",
+            "where": where}
+
+
 # ------------------------------------------------------------------------------------------------
-def time_oracle(dic, x0, conlist, k_sample, tol=TOL):
-    """Reference algorithm (numpy/scipy oracle port) on the host cores: a bounded sample of the same
-    workload -- the first `k_sample` Krylov iterations of the same call (k = k_sample makes the last
-    one constrained, exactly like iteration 50 of the full run)."""
-    from oracle import cgmres_oracle as orc
-    t0 = time.perf_counter()
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        x, info = orc.cgmres(dic["A"], dic["b"], x0, k_sample, tol=tol, contol=CONTOL, conlist=conlist, timing=True)
-    dt = time.perf_counter() - t0
-    return info["steps"] / dt, dt, info
-
-
 def blas_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -223,47 +263,128 @@ def blas_threads():
         return os.cpu_count() or 1
 
 
+def oracle_solve(dic, x0, conlist, tol, pre=None, k=K_KRYLOV):
+    """The reference algorithm (oracle/cgmres_oracle.py: numpy/scipy restatement of solvers.py:131-323, pinned to
+    outputs of the unmodified reference) on the host cores: the FULL call, same k, tol, contol, constraints."""
+    from oracle import cgmres_oracle as orc
+    t0 = time.perf_counter()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        x, info = orc.cgmres(dic["A"], dic["b"], x0, k, tol=tol, contol=CONTOL, conlist=conlist, pre=pre, timing=True)
+    return x, info, time.perf_counter() - t0
+
+
 def run_reference(args):
+    """The reference arm: the reference's CPU implementation of the path (the pinned oracle port -- the reference is
+    pure Python and needs Firedrake stubs to import) on the SAME workload, full solves."""
     rank, world, local = dist_env()
     if rank != 0:
         return
-    tol = WORKLOADS[args.workload]["tol"]
-    dic, x0, conlist, _ = build_system(args.n, args.workload)
-    k_sample = args.cpu_sample_iters
-    for _ in range(min(args.warmup, 1)):
-        time_oracle(dic, x0, conlist, 1, tol)
-    its, secs = 0, 0.0
+    dic, x0, conlist, _, pre, _ = build_system(args.n, args.workload)
+    tol = workload_tol(args.workload, dic)
+    from oracle import cgmres_oracle as orc
+    for _ in range(min(args.warmup, 1)):                        # BLAS thread pools, page faults of the big temporaries
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            orc.cgmres(dic["A"], dic["b"], x0, 1, tol=tol, contol=CONTOL, conlist=conlist, pre=pre, timing=True)
+    its, secs, done = 0, 0.0, 0
     for _ in range(args.steps):
-        rate, dt, info = time_oracle(dic, x0, conlist, k_sample, tol)
-        its += info["steps"]; secs += dt
+        x, info, dt = oracle_solve(dic, x0, conlist, tol, pre)
+        its += info["steps"]; secs += dt; done += 1
+        if secs > args.reference_budget_s:                      # a full solve takes ~1 min at 1e7 unknowns
+            break
     value = its / secs
-    sample = (f"first {k_sample} of {K_KRYLOV} Krylov iterations of the same cgmres call (n={dic['b'].size}, "
-              f"last one constrained); early iterations are the cheapest (m small), so this favours the CPU")
+    sample = (f"{done} full solve(s) of the workload (k={K_KRYLOV}, tol={tol:g}: {info['steps']} Krylov iterations each, "
+              f"{info['timings']['constrained_steps']} constrained), {secs / done:.1f} s per solve"
+              + ("" if done == args.steps else f"; {args.steps} steps were asked for, stopped after {done} at the {args.reference_budget_s:.0f} s budget"))
     line = {
         "impl": "reference", "metric": "krylov_iters_per_s", "value": value, "unit": "it/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+        "n_gpus": args.gpus, "steps": done, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * secs / done,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.workload, dic, "cpu"),
+        "config": workload_config(args.workload, dic, "host cores (numpy/scipy)", tol),
         "cpu_baseline": {"value": value, "unit": "it/s", "cores": blas_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "krylov_steps": int(info["steps"]), "final_residual": float(info["res"][-1]),
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(workload, dic, where):
-    w = WORKLOADS[workload]
-    n = int(dic.get("n", dic["b"].size))
-    nnz = int(dic.get("nnz", dic["A"].nnz))
-    return {"workload": f"{w['label']}, n={n}, nnz={nnz}, cgmres k={K_KRYLOV} tol={w['tol']:g} contol={CONTOL} "
-                        f"{w['cons']} constraints, x0=0, no preconditioner",
-            "n": n, "nnz": nnz, "k": K_KRYLOV,
-            "l2": f"working set (basis {8e-9 * (K_KRYLOV + 1) * n:.1f} GB + matrix {12e-9 * nnz:.1f} GB) >> 126 MB L2: no flush between iterations",
-            "where": where}
+# ------------------------------------------------------------------------------------------------
+def kernel_table(prof, steps, peak):
+    """Per kernel class: time, launches, bandwidth against the SURVEY 8(d) byte model AND against the bytes the
+    launches move with the storage they run on (`frac_of_peak`: a real roofline fraction)."""
+    out = {}
+    for k, v in prof.items():
+        if not v["launches"]:
+            continue
+        out[k] = {"ms_per_step": v["ms"] / steps, "launches_per_step": v["launches"] / steps,
+                  "gbs_model_csr": v["gbs"], "gbs": v.get("gbs_moved"),
+                  "frac_of_peak": (v["gbs_moved"] / peak if v.get("gbs_moved") else None)}
+    return out
+
+
+def timed_solves(sess, solve, steps, warmup, barrier=lambda: None):
+    """(iterations, seconds, per-solve ms, last x, last info) of `steps` device-resident solves after `warmup`."""
+    ctx = sess.ctx
+    for _ in range(warmup):
+        x, info = solve(sess)
+    ctx.reset_profile()
+    barrier(); ctx.sync()
+    iters, per = 0, []
+    t0 = time.perf_counter()
+    ctx.timer_start()
+    for _ in range(steps):
+        ts = time.perf_counter()
+        x, info = solve(sess)
+        iters += info["steps"]
+        per.append(1e3 * (time.perf_counter() - ts))
+    ctx.sync()
+    ev_ms = ctx.timer_stop()
+    wall = time.perf_counter() - t0
+    return iters, max(wall, ev_ms * 1e-3), per, x, info, ev_ms
+
+
+def extra_run(name, A, b, x0, conlist, tol, local, pre=None, k=K_KRYLOV, steps=3, warmup=1, spmv_format=None, peak=1.0, note=""):
+    """One more configuration on the same box: device-resident solves + per-kernel fractions."""
+    from structurepreservingiterativesolvers_b200 import solvers
+    t_in = time.perf_counter()
+    sess = solvers.DeviceSession(A, b, x0, k, conlist=conlist, pre=pre, device=local, spmv_format=spmv_format)
+
+    def solve(s):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return solvers.cgmres(A, b, x0, k, tol=tol, contol=CONTOL, conlist=conlist, pre=pre, timing=True,
+                                  small_solver="kkt", session=s, device=local)
+    iters, secs, per, x, info, _ = timed_solves(sess, solve, steps, warmup)
+    sess.ctx.set_option("profile", 1)
+    sess.ctx.reset_profile()
+    solve(sess)
+    sess.ctx.sync()
+    prof = sess.ctx.profile()
+    fmt = {0: "auto", 1: "sell", 2: "csr", 3: "sell2", 4: "pattern", 5: "selld"}.get(sess.ctx.info("fmt:0"), "?")
+    sess.close()
+    out = {"value": iters / secs, "unit": "it/s", "ms_per_step": 1e3 * secs / steps, "krylov_steps": int(info["steps"]),
+           "constrained_steps": int(info["timings"]["constrained_steps"]), "final_residual": float(info["res"][-1]),
+           "n": int(b.size), "k": k, "tol": tol, "spmv_format": fmt, "steps": steps, "warmup": warmup,
+           "kernels": kernel_table(prof, 1, peak), "wall_s": round(time.perf_counter() - t_in, 1)}
+    if "spmv" in out["kernels"]:
+        out["spmv_frac_dram"] = out["kernels"]["spmv"]["frac_of_peak"]
+    if note:
+        out["note"] = note
+    return out, x, info
+
+
+def invariant_devs(workload, dic, x, conlist):
+    """Relative deviation of every constrained invariant at x (the quantities CGMRES preserves)."""
+    out = {}
+    for c in conlist:
+        val = 0.5 * x @ (c.M @ x) + np.asarray(c.v).reshape(-1) @ x + c.c
+        out[getattr(c, "name", "c")] = float(abs(val) / max(abs(c.c), 1e-300))
+    return out
 
 
 def run_ours(args):
-    from structurepreservingiterativesolvers_b200 import _native as nat
     from structurepreservingiterativesolvers_b200 import solvers
     rank, world, local = dist_env()
     dist = None
@@ -272,8 +393,8 @@ def run_ours(args):
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    tol = WORKLOADS[args.workload]["tol"]
-    dic, x0, conlist, part = build_system(args.n, args.workload, rank, world)
+    dic, x0, conlist, part, pre, glob = build_system(args.n, args.workload, rank, world, keep_global=(rank == 0 and not args.skip_parity))
+    tol = workload_tol(args.workload, dic)
     A, b = dic["A"], dic["b"]
     n = int(dic.get("n", b.size))
     engine = args.small_solver
@@ -287,20 +408,24 @@ def run_ours(args):
     def make_session(mats=None, profile=False):
         Ax, bx, x0x, cl = mats if mats is not None else (A, b, x0, conlist)
         if world > 1:
-            return DistributedSession(Ax, bx, x0x, K_KRYLOV, part, comm, conlist=cl, profile=profile,
+            return DistributedSession(Ax, bx, x0x, K_KRYLOV, part, comm, conlist=cl, pre=pre, profile=profile,
                                       transport=args.transport)
-        return solvers.DeviceSession(Ax, bx, x0x, K_KRYLOV, conlist=cl, device=local, profile=profile)
+        return solvers.DeviceSession(Ax, bx, x0x, K_KRYLOV, conlist=cl, pre=pre, device=local, profile=profile)
 
     def solve(session=None, mats=None, eng=engine):
         Ax, bx, x0x, cl = mats if mats is not None else (A, b, x0, conlist)
+        own = session is None
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            if session is None:
+            if own:
                 session = make_session(mats)            # end-to-end: uploads happen inside the timed call
             # timing=True: the reference's TimedSolve protocol and the survey's 0.27 it/s measurement;
             # it also skips the absolute 1e-12 violation check (solvers.py:266, quirk Q6)
-            return solvers.cgmres(Ax, bx, x0x, K_KRYLOV, tol=tol, contol=CONTOL, conlist=cl, timing=True,
-                                  small_solver=eng, session=session, device=local)
+            out = solvers.cgmres(Ax, bx, x0x, K_KRYLOV, tol=tol, contol=CONTOL, conlist=cl, pre=pre, timing=True,
+                                 small_solver=eng, session=session, device=local)
+        if own:
+            session.close()
+        return out
 
     def barrier():
         if dist is not None:
@@ -329,6 +454,7 @@ def run_ours(args):
         ctx.sync()
         ev_ms = ctx.timer_stop()
         wall = time.perf_counter() - t0
+        launches = int(sum(v["launches"] for v in ctx.profile().values()))
         # same K solves once more with one CUDA-event pair around every kernel launch (on the
         # launching stream): per-kernel durations for the roofline.  The event pairs cost ~10 % of
         # the solve, so they are kept out of the headline region above.
@@ -342,7 +468,9 @@ def run_ours(args):
         wall_profiled = time.perf_counter() - tp0
         clk.mark_stop()
     prof = ctx.profile()
+    ctx.set_option("profile", 0)
     final_res = float(info["res"][-1])
+    x_gpu, info_gpu = np.array(x, copy=True), info
     secs = max(wall, ev_ms * 1e-3)
     if dist is not None:
         import torch
@@ -351,17 +479,38 @@ def run_ours(args):
         secs = float(t.item())
     iters_all = float(iters)        # one global solve: every rank counts the same Krylov iterations
     value = iters_all / secs
-    launches = int(sum(v["launches"] for v in prof.values()))
+    fmt_a = {0: "auto", 1: "sell", 2: "csr", 3: "sell2", 4: "pattern", 5: "selld"}.get(ctx.info("fmt:0"), "?")
 
     # parity-mode (scipy SLSQP small solves, the reference's exact host arithmetic) for context
-    parity = None
+    parity_mode = None
     if world == 1 and engine != "slsqp" and not args.skip_parity_mode:
         t0 = time.perf_counter()
         xs, infos = solve(sess, eng="slsqp")
         ctx.sync()
         ps = time.perf_counter() - t0
-        parity = {"small_solver": "slsqp", "value": infos["steps"] / ps, "unit": "it/s", "solve_s": ps,
-                  "rel_diff_vs_headline_solver": float(np.linalg.norm(xs - x) / np.linalg.norm(x))}
+        parity_mode = {"small_solver": "slsqp", "value": infos["steps"] / ps, "unit": "it/s", "solve_s": ps,
+                       "rel_diff_vs_headline_solver": float(np.linalg.norm(xs - x_gpu) / np.linalg.norm(x_gpu))}
+
+    # ---- N > 1: the gathered solution against a single-GPU solve of the same system on rank 0 -----------------
+    parity_vs_single = None
+    if world > 1 and not args.skip_parity:
+        xg = sess.gather(x_gpu)
+        if rank == 0:
+            gd, gx0, gcl = glob
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                s1 = solvers.DeviceSession(gd["A"], gd["b"], gx0, K_KRYLOV, conlist=gcl, pre=pre, device=local)
+                x1, info1 = solvers.cgmres(gd["A"], gd["b"], gx0, K_KRYLOV, tol=tol, contol=CONTOL, conlist=gcl, pre=pre,
+                                           timing=True, small_solver=engine, session=s1, device=local)
+                s1.close()
+            parity_vs_single = {"rel_diff": float(np.linalg.norm(xg - x1) / np.linalg.norm(x1)),
+                                "steps_equal": bool(info1["steps"] == info_gpu["steps"]),
+                                "steps": [int(info_gpu["steps"]), int(info1["steps"])],
+                                "res_history_maxabs": float(np.max(np.abs(np.asarray(info1["res"]) - np.asarray(info_gpu["res"])))) if info1["steps"] == info_gpu["steps"] else None,
+                                "invariant_rel_dev": invariant_devs(args.workload, gd, xg, gcl),
+                                "tolerance": 1e-10}
+            glob = None
+        barrier()                      # the other ranks wait here, not inside a device-side flag spin
     sess.close()
 
     # ---- end-to-end through the public API, pinned host buffers --------------------------------
@@ -390,6 +539,16 @@ def run_ours(args):
             h2d, d2h = int(hb[0].item()), int(hb[1].item())
         e2e = {"value": e_it / e_secs, "unit": "it/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "solve_s": e_secs / args.e2e_steps}
+        del mats, xe
+
+    peak, peak_src = peak_hbm()
+    extra = {}
+    # ---- N > 1: swe at 1e8 unknowns (BASELINE configs[4]): every rank assembles only its own strip ------------------
+    if world > 1 and args.workload == "lkdv" and not args.skip_extras:
+        try:
+            extra["swe_1e8"] = swe_1e8(args, rank, world, local, comm, dist, peak)
+        except Exception as exc:                                   # the headline line must survive an extra
+            extra["swe_1e8"] = {"error": repr(exc)[:300]}
 
     if rank != 0:
         if dist is not None:
@@ -397,57 +556,148 @@ def run_ours(args):
         return
 
     # ---- roofline of the dominant kernel class ---------------------------------------------------
-    peak, peak_src = peak_hbm()
     classes = {k: v for k, v in prof.items() if v["launches"] > 0}
     dom = max(classes, key=lambda k: classes[k]["ms"])
     d = classes[dom]
     kernel_ms = sum(v["ms"] for v in classes.values())
     traffic, traffic_src = None, None
-    try:        # measured DRAM bytes per launch of this kernel class: ncu launch list of one solve of this workload
-        with open(os.path.join(ROOT, "profiles", "traffic_r1.json")) as fh:
-            tr = json.load(fh)[args.workload]
-        if world == 1 and args.n == 10_000_000:
-            traffic, traffic_src = tr[dom]["traffic_bytes_per_launch"], tr["_source"]
-    except Exception:
-        pass
+    for tf in ("traffic_r2.json", "traffic_r1.json"):   # measured DRAM bytes per launch of this kernel class: ncu launch list of one solve
+        try:
+            with open(os.path.join(ROOT, "profiles", tf)) as fh:
+                tr = json.load(fh)[args.workload]
+            if world == 1 and args.n == 10_000_000:
+                traffic, traffic_src = tr[dom]["traffic_bytes_per_launch"], tr["_source"]
+            break
+        except Exception:
+            continue
     roofline = {"bound": "hbm", "kernel": dom, "achieved": d["gbs"], "peak": peak, "unit": "GB/s",
                 "frac": d["gbs"] / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": d["bytes"] / d["launches"], "peak_source": peak_src,
                 "avg_launch_ms": d["ms"] / d["launches"], "launches": d["launches"],
                 "share_of_kernel_time": d["ms"] / kernel_ms}
     if traffic:
-        # what the kernel really moved (ncu) over its live duration: with the compressed SpMV storage and the dual
-        # SpMV the ALGORITHMIC bytes of SURVEY 8d (12 bytes per entry, two passes) exceed the traffic, frac > 1
         roofline["achieved_dram"] = traffic / (d["ms"] / d["launches"]) * 1e-6
         roofline["frac_dram"] = roofline["achieved_dram"] / peak
-    kernels = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
-                   "gbs": v["gbs"], "frac_of_peak": (v["gbs"] / peak if v["gbs"] else None)} for k, v in classes.items()}
+    moved_total = sum(v["moved_bytes"] for v in classes.values())
+    roofline["whole_solve"] = {"moved_bytes_per_solve": moved_total / args.steps, "kernel_ms_per_solve": kernel_ms / args.steps,
+                               "frac_of_peak_over_kernel_time": moved_total / (kernel_ms * 1e-3) / (peak * 1e9),
+                               "frac_of_peak_over_solve_time": (moved_total / args.steps) / (secs / args.steps) / (peak * 1e9)}
+    kernels = kernel_table(prof, args.steps, peak)
 
-    # ---- CPU baseline: the oracle port on this box's host cores (bounded sample) -----------------
-    cpu = None
-    if not args.skip_cpu and world == 1:
-        rate, dt, cinfo = time_oracle(dic, x0, conlist, args.cpu_sample_iters, tol)   # world == 1: global system
-        cpu = {"value": rate, "unit": "it/s", "cores": blas_threads(), "kind": "port",
-               "sample": (f"first {args.cpu_sample_iters} of {K_KRYLOV} Krylov iterations of the same cgmres call "
-                          f"(n={n}, last one constrained), {dt:.1f} s; early iterations are the cheapest, so this favours the CPU")}
+    # ---- CPU baseline + parity: the oracle on this box's host cores, the FULL workload, once ------------------------
+    cpu, parity = None, None
+    if world == 1 and not args.skip_cpu:
+        xo, infoo, dt = oracle_solve(dic, x0, conlist, tol, pre)
+        cpu = {"value": infoo["steps"] / dt, "unit": "it/s", "cores": blas_threads(), "kind": "port",
+               "sample": (f"one full solve of the workload (k={K_KRYLOV}, tol={tol:g}): {infoo['steps']} Krylov iterations, "
+                          f"{infoo['timings']['constrained_steps']} constrained, {dt:.1f} s"),
+               "solve_s": dt, "timings": {k2: float(v2) for k2, v2 in infoo["timings"].items()}}
+        same = infoo["steps"] == info_gpu["steps"]
+        parity = {"against": "oracle/cgmres_oracle.py (pinned to outputs of the unmodified reference), same system, same call",
+                  "rel_diff": float(np.linalg.norm(x_gpu - xo) / np.linalg.norm(xo)),
+                  "steps_equal": bool(same), "steps": [int(info_gpu["steps"]), int(infoo["steps"])],
+                  "res_history_maxabs": float(np.max(np.abs(np.asarray(infoo["res"]) - np.asarray(info_gpu["res"])))) if same else None,
+                  "res_final": [float(info_gpu["res"][-1]), float(infoo["res"][-1])],
+                  "invariant_rel_dev": invariant_devs(args.workload, dic, x_gpu, conlist),
+                  "invariant_rel_dev_oracle": invariant_devs(args.workload, dic, xo, conlist),
+                  "tolerance": 1e-10}
+        del xo
+
+    # ---- the other configurations --------------------------------------------------------------------------
+    if world == 1 and not args.skip_extras and args.workload == "lkdv":
+        def guarded(name, fn):
+            if elapsed() > args.extras_budget_s:
+                extra[name] = {"skipped": f"time budget ({args.extras_budget_s:.0f} s) reached"}
+                return
+            try:
+                extra[name] = fn()
+            except Exception as exc:
+                extra[name] = {"error": repr(exc)[:300]}
+
+        from structurepreservingiterativesolvers_b200.preconditioners import JacobiPreconditioner
+
+        def general_matrix():
+            # the path a real `getValuesCSR` export takes (lkdv/lkdv.py:109-111): assembly round-off in the values, so
+            # neither row patterns nor a value dictionary exist -- every value moved by <= 1 ulp, SELL-32 storage
+            rng = np.random.default_rng(1)
+            Ap = A.copy()
+            Ap.data = Ap.data * (1.0 + (rng.integers(-1, 2, Ap.data.size) * np.finfo(float).eps))
+            out, xg, _ = extra_run("general_matrix", Ap, b, x0, conlist, tol, local, peak=peak,
+                                   note="same system, values perturbed by <= 1 ulp so that pattern / dictionary detection fails")
+            out["rel_diff_vs_headline"] = float(np.linalg.norm(xg - x_gpu) / np.linalg.norm(x_gpu))
+            out["slowdown_vs_headline"] = out["ms_per_step"] / (1e3 * secs / args.steps)
+            return out
+        guarded("general_matrix", general_matrix)
+        guarded("fixed_k50", lambda: extra_run("fixed_k50", A, b, x0, conlist, 1e-30, local, peak=peak,
+                                               note="tol tiny: all 50 iterations run (the survey's 0.27 it/s CPU protocol), the last one constrained")[0])
+        guarded("three_constraints", lambda: extra_run("three_constraints", A, b, x0, dic["conlist3"], tol, local, peak=peak,
+                                                       note="the reference's list: mass, momentum, energy (lkdv/LinearSolver.py:28-47)")[0])
+        guarded("jacobi", lambda: extra_run("jacobi", A, b, x0, conlist, tol, local, pre=JacobiPreconditioner(A), peak=peak,
+                                            note="point Jacobi on the device (fused into the last sweep)")[0])
+
+        def other(workload, n_target):
+            d2, x02, cl2, _, pre2, _ = build_system(n_target, workload)
+            tol2 = workload_tol(workload, d2)
+            out, _, _ = extra_run(workload, d2["A"], d2["b"], x02, cl2, tol2, local, pre=pre2, peak=peak)
+            out["config"] = workload_config(workload, d2, "1 B200", tol2)["workload"]
+            return out
+        guarded("swe", lambda: other("swe", 10_000_000))
+        guarded("lkdvRK", lambda: other("lkdvRK", 6_000_000))
 
     line = {
         "metric": "krylov_iters_per_s", "value": value, "unit": "it/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": dict(workload_config(args.workload, dic, "1 B200 per rank"), small_solver=engine,
+        "config": dict(workload_config(args.workload, dic, "1 B200 per rank", tol), small_solver=engine, spmv_format=fmt_a,
+                       pipeline=("device-resident loop (Givens update + unconstrained iterates on the GPU)" if solvers._CONFIG["pipeline"] else "host-driven loop"),
                        parallelism=("single GPU" if world == 1 else
                                     f"row-sharded over {world} GPUs by mesh block, {sess.transport} transport, halo {sess.plan.n_halo} doubles/rank")),
         "solve_time_s": secs / args.steps, "device_event_ms_per_step": ev_ms / args.steps,
+        "krylov_steps": int(info_gpu["steps"]), "constrained_steps": int(info_gpu["timings"]["constrained_steps"]),
         "roofline_region": "second pass of the same K solves with per-kernel CUDA events (%.2f ms/solve)" % (1e3 * wall_profiled / args.steps),
         "kernel_ms_per_step": kernel_ms / args.steps, "final_residual": final_res,
         "ms_each_step": [round(t, 3) for t in per_solve],
-        "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
-        "gpu_launches": launches, "clocks": clk.summary(), "parity_mode": parity,
+        "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "parity": parity, "parity_vs_single": parity_vs_single,
+        "e2e": e2e, "gpu_launches": launches, "clocks": clk.summary(), "parity_mode": parity_mode, "extra": extra,
+        "bench_wall_s": round(elapsed(), 1),
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def swe_1e8(args, rank, world, local, comm, dist, peak):
+    """BASELINE configs[4]: swe at 1e8 unknowns row-sharded by strips of squares; every rank assembles its own strip."""
+    import torch
+    from structurepreservingiterativesolvers_b200 import solvers
+    from structurepreservingiterativesolvers_b200.distributed import DistributedSession
+    t_in = time.perf_counter()
+    dic, x0, conlist, part, pre, _ = build_system(100_000_000, "swe", rank, world)
+    tol = WORKLOADS["swe"]["tol"]
+    t_asm = time.perf_counter() - t_in
+    sess = DistributedSession(dic["A"], dic["b"], x0, K_KRYLOV, part, comm, conlist=conlist, transport=args.transport)
+
+    def solve(s):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return solvers.cgmres(dic["A"], dic["b"], x0, K_KRYLOV, tol=tol, contol=CONTOL, conlist=conlist, timing=True,
+                                  small_solver="kkt", session=s, device=local)
+    iters, secs, per, x, info, _ = timed_solves(sess, solve, 3, 2, barrier=dist.barrier)
+    t = torch.tensor([secs], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    secs = float(t.item())
+    sess.ctx.set_option("profile", 1)
+    sess.ctx.reset_profile()
+    solve(sess)
+    sess.ctx.sync()
+    prof = sess.ctx.profile()
+    halo = sess.plan.n_halo
+    sess.close()
+    return {"value": iters / secs, "unit": "it/s", "ms_per_step": 1e3 * secs / 3, "krylov_steps": int(info["steps"]),
+            "final_residual": float(info["res"][-1]), "n": int(dic["n"]), "nnz": int(dic["nnz"]), "n_gpus": world,
+            "halo_doubles_per_rank": int(halo), "assembly_s": round(t_asm, 1), "kernels": kernel_table(prof, 1, peak),
+            "kernel_ms_per_step": sum(v["ms"] for v in prof.values()), "wall_s": round(time.perf_counter() - t_in, 1),
+            "config": f"swe RT2xDG0, n={dic['n']}, nnz={dic['nnz']}, cgmres k={K_KRYLOV} tol={tol:g}, strips of squares, strong scaling"}
 
 
 def main():
@@ -460,12 +710,19 @@ def main():
     ap.add_argument("--workload", default="lkdv", choices=sorted(WORKLOADS))
     ap.add_argument("--small-solver", default="kkt", choices=["kkt", "slsqp"])
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-sample-iters", type=int, default=8)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-parity-mode", action="store_true")
+    ap.add_argument("--skip-parity", action="store_true", help="N > 1: no single-GPU comparison solve on rank 0")
+    ap.add_argument("--skip-extras", action="store_true")
+    ap.add_argument("--extras-budget-s", type=float, default=600.0, help="no further extra configuration is started after this much wall time")
+    ap.add_argument("--reference-budget-s", type=float, default=240.0, help="--impl reference stops after the solve that crosses this")
+    ap.add_argument("--host-loop", action="store_true", help="host-driven Krylov loop (round-1 path) instead of the device-resident one")
     ap.add_argument("--transport", default="auto", choices=["auto", "p2p", "nccl"])
     args = ap.parse_args()
+    if args.host_loop:
+        from structurepreservingiterativesolvers_b200 import solvers
+        solvers.configure(pipeline=False)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -288,6 +288,9 @@ int spis_sync(spis_ctx* ctx);
  * launches_out[c] kernel launches since the last spis_reset_profile.                    */
 int spis_get_profile(spis_ctx* ctx, double* ms_out, double* bytes_out, int64_t* launches_out);
 int spis_reset_profile(spis_ctx* ctx);
+/* moved_out[c]: bytes the launches of class c move with the storage format they ran on (row-pattern ids, value codes,
+ * one pass over the matrix for two products); equals bytes_out of spis_get_profile for everything but SpMV          */
+int spis_get_profile_moved(spis_ctx* ctx, double* moved_out);
 /* CUDA-event stopwatch on the context's stream: device time between the two calls.      */
 int spis_timer_start(spis_ctx* ctx);
 int spis_timer_stop(spis_ctx* ctx, double* ms_out);

@@ -178,6 +178,7 @@ struct spis_ctx {
   std::vector<DevBlock> owned;   // device blocks currently held by this context
   std::vector<AsyncJob*> jobs;   // native helper threads staging constraint data (joined by spis_constraint_setup_wait)
   double prof_ms[SPIS_PROF_CLASSES] = {0}; double prof_bytes[SPIS_PROF_CLASSES] = {0}; int64_t prof_launch[SPIS_PROF_CLASSES] = {0};
+  double prof_moved[SPIS_PROF_CLASSES] = {0};   // bytes the launches move with the storage format they actually run on (== prof_bytes except SpMV)
   char err[512] = "";
 };
 
@@ -297,9 +298,10 @@ int d2h(spis_ctx* ctx, void* dst, const void* src, size_t bytes) {
 }
 
 // ---- profiling ------------------------------------------------------------------------
-int prof_begin(spis_ctx* ctx, int cls, double bytes) {
+int prof_begin(spis_ctx* ctx, int cls, double bytes, double moved = -1.0) {
   ctx->prof_launch[cls] += 1;
   ctx->prof_bytes[cls] += bytes;
+  ctx->prof_moved[cls] += moved >= 0.0 ? moved : bytes;
   if (!ctx->profile) return SPIS_OK;
   ProfRec r; r.cls = cls; r.bytes = bytes;
   for (cudaEvent_t* e : {&r.e0, &r.e1}) {
@@ -561,6 +563,17 @@ int launch_orth_mid(spis_ctx* ctx, const double* V, int m, const double* coef, d
   return do_allreduce(ctx, out, m + (with_norm ? 1 : 0));
 }
 
+// bytes one pass over the STORED matrix moves (format-specific; the CSR model of SURVEY 8d is 12 nnz + 4 (n + 1))
+double matrix_bytes(const Matrix& M) {
+  const double nsl = (double)((M.nrows + 31) / 32);
+  switch (M.fmt) {
+    case SPIS_FMT_PATTERN: return 2.0 * (double)M.nrows;                                   // 16-bit stencil id per row (the table stays in L1)
+    case SPIS_FMT_SELLD: return 5.0 * (double)M.nnz_padded + 16.0 * nsl;                    // 32-bit column + 8-bit value code
+    case SPIS_FMT_SELL: case SPIS_FMT_SELL2: return 12.0 * (double)M.nnz_padded + 8.0 * nsl;
+    default: return 12.0 * (double)M.nnz + 4.0 * (double)(M.nrows + 1);
+  }
+}
+
 template <int MODE>
 int launch_spmv_mode(spis_ctx* ctx, const Matrix& M, const double* x, const double* b, double* y, double* sumsq_out) {
   const XView xv = MODE != 0 ? fused_view(ctx) : XView();
@@ -614,7 +627,8 @@ int launch_spmv(spis_ctx* ctx, int slot, int mode, const double* x, const double
   const Matrix& M = ctx->mats[slot];
   REQUIRE(M.present, "matrix slot %d has not been uploaded", slot);
   const double bytes = 12.0 * (double)M.nnz + 4.0 * (double)(M.nrows + 1) + (mode == 1 ? 24.0 : 16.0) * (double)M.nrows;
-  TRY(prof_begin(ctx, slot == SPIS_SLOT_A ? SPIS_PROF_SPMV : SPIS_PROF_SPMV_AUX, bytes));
+  const double moved = matrix_bytes(M) + (mode == 1 ? 24.0 : 16.0) * (double)M.nrows;
+  TRY(prof_begin(ctx, slot == SPIS_SLOT_A ? SPIS_PROF_SPMV : SPIS_PROF_SPMV_AUX, bytes, moved));
   if (mode == 0) TRY(launch_spmv_mode<0>(ctx, M, x, b, y, sumsq_out));
   else if (mode == 1) TRY(launch_spmv_mode<1>(ctx, M, x, b, y, sumsq_out));
   else TRY(launch_spmv_mode<2>(ctx, M, x, b, y, sumsq_out));
@@ -639,7 +653,8 @@ int launch_spmv_dual(spis_ctx* ctx, const double* x1, double* y1, const double* 
   }
   double* part = ride_partial ? ride_partial : ctx->d_partial;
   const double bytes = 2.0 * (12.0 * (double)M.nnz + 4.0 * (double)(M.nrows + 1) + 16.0 * (double)M.nrows);   // two SpMVs' worth
-  TRY(prof_begin(ctx, SPIS_PROF_SPMV, bytes));
+  const double moved = matrix_bytes(M) + 32.0 * (double)M.nrows;      // the matrix once, x1, x2 and b read, y1 written
+  TRY(prof_begin(ctx, SPIS_PROF_SPMV, bytes, moved));
   int grid = 1;
   if (M.fmt == SPIS_FMT_PATTERN) {
     grid = grid_for(ctx, (M.nrows + kThreads - 1) / kThreads, ctx->spmv_dual_ctas_per_sm > 0 ? ctx->spmv_dual_ctas_per_sm : 6);
@@ -680,7 +695,8 @@ int launch_spmv_multi(spis_ctx* ctx, int slot, int nv, const double* x, int64_t 
     return SPIS_OK;
   }
   const double bytes = (double)nv * (12.0 * (double)M.nnz + 4.0 * (double)(M.nrows + 1) + 16.0 * (double)M.nrows);   // nv SpMVs' worth
-  TRY(prof_begin(ctx, slot == SPIS_SLOT_A ? SPIS_PROF_SPMV : SPIS_PROF_SPMV_AUX, bytes));
+  const double moved = matrix_bytes(M) + (double)nv * 16.0 * (double)M.nrows;
+  TRY(prof_begin(ctx, slot == SPIS_SLOT_A ? SPIS_PROF_SPMV : SPIS_PROF_SPMV_AUX, bytes, moved));
   if (M.fmt == SPIS_FMT_PATTERN) {
     int grid = grid_for(ctx, (M.nrows + kThreads - 1) / kThreads, nv == 2 ? 6 : 4);
     while (grid > 1 && (int64_t)M.nrows + (int64_t)grid * kThreads >= (int64_t)INT32_MAX) grid /= 2;
@@ -2559,7 +2575,15 @@ int spis_get_profile(spis_ctx* ctx, double* ms_out, double* bytes_out, int64_t* 
 int spis_reset_profile(spis_ctx* ctx) {
   if (!ctx) return SPIS_E_INVALID;
   TRY(prof_resolve(ctx));
-  for (int i = 0; i < SPIS_PROF_CLASSES; ++i) { ctx->prof_ms[i] = 0; ctx->prof_bytes[i] = 0; ctx->prof_launch[i] = 0; }
+  for (int i = 0; i < SPIS_PROF_CLASSES; ++i) { ctx->prof_ms[i] = 0; ctx->prof_bytes[i] = 0; ctx->prof_launch[i] = 0; ctx->prof_moved[i] = 0; }
+  return SPIS_OK;
+}
+
+// per class: bytes the launches moved with the storage format they ran on (16-bit stencil ids, 8-bit value codes, one
+// pass over the matrix for two products ...); equals the algorithmic bytes of spis_get_profile except for SpMV
+int spis_get_profile_moved(spis_ctx* ctx, double* moved_out) {
+  if (!ctx || !moved_out) return SPIS_E_INVALID;
+  for (int i = 0; i < SPIS_PROF_CLASSES; ++i) moved_out[i] = ctx->prof_moved[i];
   return SPIS_OK;
 }
 

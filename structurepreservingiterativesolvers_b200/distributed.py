@@ -296,19 +296,42 @@ class DistributedSession(solvers.DeviceSession):
         return out
 
 
+def _own_session(ext, make):
+    sess = ext.pop("session", None)
+    if sess is not None:
+        return sess, False
+    sess = make()
+    sess._owned_by_solver = True          # solvers._finish_history / _abandon manage its lifetime
+    return sess, True
+
+
 def cgmres_distributed(A_rows, b_loc, x0_loc, k, part, comm, tol=1e-8, contol=10, conlist=(), pre=None,
-                       timing=None, gather=False, **ext):
+                       timing=None, gather=False, transport="auto", **ext):
     """solvers.cgmres on a row-sharded system; returns this rank's piece of x (or the gathered
-    global vector with gather=True) and the usual info dict (identical on every rank)."""
-    sess = ext.pop("session", None) or DistributedSession(A_rows, b_loc, x0_loc, k, part, comm, conlist=conlist, pre=pre,
-                                                          orth=ext.pop("orth", None), profile=ext.pop("profile", None))
-    x_loc, info = solvers.cgmres(A_rows, b_loc, x0_loc, k, tol=tol, contol=contol, conlist=conlist, pre=pre,
-                                 timing=timing, session=sess, **ext)
-    return (sess.gather(x_loc) if gather else x_loc), info
+    global vector with gather=True) and the usual info dict (identical on every rank).  Without `session=` a
+    DistributedSession is built for the call: the communicator and the sharding plan it needs are cached in `comm`,
+    so from the second call on a system with the same sparsity structure this is upload time only."""
+    orth, profile = ext.pop("orth", None), ext.pop("profile", None)
+    sess, own = _own_session(ext, lambda: DistributedSession(A_rows, b_loc, x0_loc, k, part, comm, conlist=conlist, pre=pre,
+                                                             orth=orth, profile=profile, transport=transport))
+    try:
+        x_loc, info = solvers.cgmres(A_rows, b_loc, x0_loc, k, tol=tol, contol=contol, conlist=conlist, pre=pre,
+                                     timing=timing, session=sess, **ext)
+        return (sess.gather(x_loc) if gather else x_loc), info
+    except BaseException:
+        if own:
+            solvers._abandon(sess)
+        raise
 
 
-def gmres_distributed(A_rows, b_loc, x0_loc, k, part, comm, tol=1e-50, pre=None, gather=False, **ext):
-    sess = ext.pop("session", None) or DistributedSession(A_rows, b_loc, x0_loc, k, part, comm, pre=pre,
-                                                          orth=ext.pop("orth", None), profile=ext.pop("profile", None))
-    x_loc, info = solvers.gmres(A_rows, b_loc, x0_loc, k, tol=tol, pre=pre, session=sess, **ext)
-    return (sess.gather(x_loc) if gather else x_loc), info
+def gmres_distributed(A_rows, b_loc, x0_loc, k, part, comm, tol=1e-50, pre=None, gather=False, transport="auto", **ext):
+    orth, profile = ext.pop("orth", None), ext.pop("profile", None)
+    sess, own = _own_session(ext, lambda: DistributedSession(A_rows, b_loc, x0_loc, k, part, comm, pre=pre, orth=orth,
+                                                             profile=profile, transport=transport))
+    try:
+        x_loc, info = solvers.gmres(A_rows, b_loc, x0_loc, k, tol=tol, pre=pre, session=sess, **ext)
+        return (sess.gather(x_loc) if gather else x_loc), info
+    except BaseException:
+        if own:
+            solvers._abandon(sess)
+        raise

@@ -54,10 +54,13 @@ class Problem:
         return np.sin(beta * (x - (1 - beta ** 2) * t)) + 1
 
 
-def linforms(N=100, M=50, degree=1, tstages=2, T=10, zinit=None, space="DG"):
+def linforms(N=100, M=50, degree=1, tstages=2, T=10, zinit=None, space="DG", mlength=None):
+    """`mlength=None` keeps the reference's domain length 40 (lkdvRK/lkdvRK.py:17); pass mlength=0.8*M to hold the
+    mesh width fixed when scaling the stage system up."""
     if degree != 1:
         raise NotImplementedError("only degree 1 is re-assembled")
-    prob = Problem(N=N, M=M, T=T, degree=degree, tstages=tstages, space=space)
+    prob = Problem(N=N, M=M, T=T, degree=degree, tstages=tstages, space=space,
+                   mlength=(40.0 if mlength is None else float(mlength)))
     h, dt = prob.h, prob.dt
     if space == "DG":
         Mm, G, omega_u = _lkdv._field_matrices_dg1(M, h)

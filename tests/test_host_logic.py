@@ -377,3 +377,97 @@ def test_native_kkt_matches_the_python_solver():
     t1 = rng.standard_normal(m)
     bad = [smallsolve.ReducedConstraint(1.0, t1, np.zeros((m, m))), smallsolve.ReducedConstraint(-1.0, t1, np.zeros((m, m)))]
     assert smallsolve._kkt_native(H, beta, bad) is None
+
+
+# ---- round 2: the device-resident loop (solvers._Pipeline) on the numpy stand-in ---------------------------------
+_PIPE_CASES = ["lkdv_cg_tol6", "lkdv_cg_tol8_n1500", "heat_tol7", "heat_tol7_jacobi", "lkdv_cg_kcap", "lkdv_cg_x0",
+               "swe_rt_tol7", "swe_rt_h08_n10800", "lkdv_cg_gmres_n1500", "heat_gmres_jacobi", "lkdv_dg1_gmres"]
+
+
+def _solve_case(name, pipeline, **ext):
+    spec, dic, prob, x0, pre = cases.instantiate(name)
+    wrap = getattr(wrappers, spec["exp"])
+    cl = wrap.conlist(dic, x0) if spec["kind"] == "cgmres" else []
+    solvers.configure(pipeline=pipeline)
+    try:
+        sess = solvers.DeviceSession(dic["A"], dic["b"], x0, spec["k"], conlist=cl, pre=pre, ctx_factory=FakeKrylovContext)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            if spec["kind"] == "cgmres":
+                x, info = solvers.cgmres(dic["A"], dic["b"], x0, spec["k"], tol=spec["tol"], contol=spec.get("contol", 10), conlist=cl,
+                                         pre=pre, session=sess, small_solver="kkt", timing=spec.get("timing"), **ext)
+            else:
+                x, info = solvers.gmres(dic["A"], dic["b"], x0, spec["k"], tol=spec["tol"], pre=pre, session=sess, **ext)
+    finally:
+        solvers.configure(pipeline=True)
+    return x, info, sess.ctx.log, dic
+
+
+@pytest.mark.parametrize("name", _PIPE_CASES)
+def test_pipelined_loop_follows_the_reference_flow(name, golden):
+    """Givens update, y_j, x_j and the phase test computed "on the device" (at queueing time in the stand-in), the host
+    only reading records: same step counts as the reference, same final iterate as the host-driven loop, and every
+    unconstrained iterate but the stragglers formed by a step that was queued ahead."""
+    x, info, log, dic = _solve_case(name, True)
+    xh, infoh, logh, _ = _solve_case(name, False)
+    assert any(e[0] == "pipe_begin" for e in log) and not any(e[0] == "pipe_begin" for e in logh)
+    assert info["steps"] == infoh["steps"] == int(golden[f"{name}/steps"])
+    assert helpers.rel_diff(x, golden[f"{name}/x_last"]) <= tolerance(name)
+    assert helpers.rel_diff(x, xh) <= max(1e-12, tolerance(name))
+    np.testing.assert_array_equal(info["x"][-1], x)
+    helpers.check_histories(name, info, dic, golden)
+    steps = [e for e in log if e[0] == "step"]
+    assert [e[1] for e in steps] == list(range(len(steps)))                    # queued in order, each once
+    assert info["steps"] <= len(steps) <= info["steps"] + 1                    # at most one step the loop did not use
+    formed = [e[4] for e in steps if e[4] is not None]
+    assert formed == sorted(set(formed))                                       # every device-formed iterate once, in order
+    host_formed = [e for e in log if e[0] == "iterate"]
+    assert len(formed) + len(host_formed) >= info["steps"]
+    if info["name"] == "gmres":
+        assert len(formed) >= info["steps"] - 1
+    # residuals of device-formed iterates ride on the SpMV of a later step, except at the end of the solve
+    assert sum(1 for e in steps if e[2]) >= len(formed) - 2
+
+
+def test_pipelined_loop_hands_over_at_the_phase_switch():
+    """Once a measured residual is <= contol*tol the stand-in device stops forming iterates BY ITSELF (phase word), for
+    steps that were queued before the host knew; the host forms every constrained iterate and nothing queued ahead
+    overwrites it."""
+    x, info, log, dic = _solve_case("lkdv_cg_tol6", True)
+    steps = [e for e in log if e[0] == "step"]
+    asked = [e for e in steps if e[3]]
+    refused = [e for e in asked if e[4] is None and e[1] >= 1]
+    assert refused, "a step queued ahead with `want_iterate` must have met the phase word"
+    first_host = next(i for i, e in enumerate(log) if e[0] == "iterate")
+    assert not any(e[0] == "step" and e[4] is not None for e in log[first_host:])
+    r = np.linalg.norm(dic["A"] @ x - dic["b"])
+    assert abs(r - info["res"][-1]) <= 1e-10 * np.linalg.norm(dic["b"])
+
+
+def test_pipelined_loop_invalid_record_falls_back_to_the_host():
+    """A device record with `valid = 0` (a vanishing or tiny Givens pivot: hess_kernel also sets the phase word) makes the
+    host take the general least-squares route (solvers.py:113) and form that and every later iterate itself."""
+    class Flaky(FakeKrylovContext):
+        def step_enqueue(self, j, want_residual, want_iterate):
+            t = super().step_enqueue(j, want_residual, want_iterate)
+            if j == 2:
+                col, y, info = self._pipe["rec"][j]
+                self._pipe["rec"][j] = (col, np.full_like(y, np.nan), dict(info, valid=False, ls=0.0, phase=1))
+                self._pipe["phase"] = 1
+            return t
+
+    spec, dic, prob, x0, pre = cases.instantiate("lkdv_cg_gmres_n1500")
+    out = []
+    for factory in (Flaky, FakeKrylovContext):
+        sess = solvers.DeviceSession(dic["A"], dic["b"], x0, spec["k"], ctx_factory=factory)
+        x, info = solvers.gmres(dic["A"], dic["b"], x0, spec["k"], tol=spec["tol"], session=sess)
+        out.append((x, info, sess.ctx.log))
+    (xf, inf, logf), (xr, inr, logr) = out
+    assert inf["steps"] == inr["steps"]
+    assert helpers.rel_diff(xf, xr) <= 1e-10
+    np.testing.assert_allclose(inf["res"], inr["res"], rtol=1e-8)
+    host_formed = [e[1] for e in logf if e[0] == "iterate"]
+    # the phase word is set before step 2's last sweep, which would have formed x_1: x_1 and everything after it are the host's
+    assert host_formed[0] == 2 and len(host_formed) == inf["steps"] - 1
+    assert not any(e[0] == "step" and e[4] is not None and e[4] >= 2 for e in logf)
+    assert not any(e[0] == "step" and e[3] and e[1] > 3 for e in logf)       # and the host stops asking

@@ -65,6 +65,8 @@ def main():
         A_loc, b_loc, x0_loc = d["A"][ids], d["b"][ids], x0[ids]
         problem_mod = lkdv
     transport = sys.argv[2] if len(sys.argv) > 2 else "auto"
+    if len(sys.argv) > 4 and sys.argv[4] == "soak":
+        sys.exit(soak(comm, part, A_loc, b_loc, x0_loc, cl_loc, tol, transport, int(sys.argv[5]) if len(sys.argv) > 5 else 200))
     sess = DistributedSession(A_loc, b_loc, x0_loc, 50, part, comm, conlist=cl_loc, profile=True,
                               transport=transport)
     for rep in range(3):
@@ -92,9 +94,61 @@ def main():
               f"solve={dt*1e3:.1f} ms transport={sess.transport} collectives={comm.counts} halo={sess.plan.n_halo} -> {'OK' if ok else 'FAIL'}", flush=True)
         prof = sess.ctx.profile()
         print({k: (round(v['ms'], 2), v['launches']) for k, v in prof.items() if v['launches']}, flush=True)
+    sess.close()
+    # ---- the per-call path: a fresh DistributedSession per solve (the public call pattern) must not rebuild the
+    # communicator or the sharding plan, and a constraint whose v is zero on every rank but one must still be reduced
+    # on all of them (include/spis_b200.h, spis_constraint_define)
+    if workload == "lkdv":
+        vmask = np.zeros(n)
+        own0 = part.global_ids(0)
+        vmask[own0[: own0.size // 3]] = 1.0                         # non-zero only on rank 0's nodes of the first field
+        cz = float(-(vmask @ np.asarray(d["z0"] if "z0" in d else np.ones(n))))
+        cl2_loc = cl_loc + [Inv(0 * A_loc, vmask[ids], cz)]
+        times = []
+        for rep in range(3):
+            dist.barrier(); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            x2_loc, info2 = cgmres_distributed(A_loc, b_loc, x0_loc, 50, part, comm, tol=tol, contol=10, conlist=cl2_loc,
+                                               small_solver="kkt", timing=True, transport=transport)
+            torch.cuda.synchronize()
+            times.append(time.perf_counter() - t0)
+        s2 = DistributedSession(A_loc, b_loc, x0_loc, 50, part, comm, conlist=cl2_loc, transport=transport)
+        x2g = s2.gather(x2_loc)
+        s2.close()
+        if rank == 0:
+            cl2 = cl + [Inv(0 * d["A"], vmask, cz)]
+            xs2, infos2 = solvers.cgmres(d["A"], d["b"], x0, 50, tol=tol, contol=10, conlist=cl2, small_solver="kkt", timing=True, device=local)
+            rel2 = np.linalg.norm(x2g - xs2) / np.linalg.norm(xs2)
+            ok2 = info2["steps"] == infos2["steps"] and rel2 <= 1e-10 and comm.counts["plans_built"] <= 2 and comm.counts["peer_comms_built"] == (1 if sess.transport == "p2p" else 0)
+            print(f"per-call sessions + zero-v-slice constraint: steps={info2['steps']} (single {infos2['steps']}) rel.diff={rel2:.2e} "
+                  f"|v.x + c|={abs(vmask @ x2g + cz):.2e} e2e per call {[round(t * 1e3, 1) for t in times]} ms counts={comm.counts} -> {'OK' if ok2 else 'FAIL'}", flush=True)
+            ok = ok and ok2
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
+
+
+def soak(comm, part, A_loc, b_loc, x0_loc, cl_loc, tol, transport, reps):
+    """Many back-to-back sharded solves through fresh sessions (the NVLink flag protocol, the persistent communicator
+    and the plan cache under repetition): every solve must return the bits of the first one."""
+    ref, t0 = None, time.perf_counter()
+    bad = 0
+    for rep in range(reps):
+        x_loc, info = cgmres_distributed(A_loc, b_loc, x0_loc, 50, part, comm, tol=tol, contol=10, conlist=cl_loc,
+                                         small_solver="kkt", timing=True, transport=transport)
+        sig = (info["steps"], float(np.asarray(x_loc) @ np.asarray(x_loc)), float(info["res"][-1]))
+        if ref is None:
+            ref = sig
+        bad += sig != ref
+    dt = time.perf_counter() - t0
+    flag = torch.tensor([float(bad)], device="cuda")
+    dist.all_reduce(flag)
+    if comm.rank == 0:
+        print(f"soak: {reps} sharded solves on {comm.world} GPUs, {dt / reps * 1e3:.2f} ms each, mismatching solves summed over ranks: {int(flag.item())}, "
+              f"counts={comm.counts} -> {'OK' if flag.item() == 0 else 'FAIL'}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0 if flag.item() == 0 else 1
 
 
 if __name__ == "__main__":
