@@ -440,6 +440,8 @@ def run_ours(args):
         for _ in range(args.warmup):
             x, info = solve(sess)      # bound like the timed loop: two result buffers stay alive
         ctx.reset_profile()
+        if world > 1 and hasattr(ctx, "xcomm_stats"):
+            ctx.xcomm_stats()              # clears the counters of the NVLink flag waits
         barrier(); ctx.sync()
         iters = 0
         clk.mark_start()
@@ -455,6 +457,7 @@ def run_ours(args):
         ev_ms = ctx.timer_stop()
         wall = time.perf_counter() - t0
         launches = int(sum(v["launches"] for v in ctx.profile().values()))
+        xstats = ctx.xcomm_stats() if (world > 1 and hasattr(ctx, "xcomm_stats")) else None
         # same K solves once more with one CUDA-event pair around every kernel launch (on the
         # launching stream): per-kernel durations for the roofline.  The event pairs cost ~10 % of
         # the solve, so they are kept out of the headline region above.
@@ -644,6 +647,14 @@ def run_ours(args):
         guarded("swe", lambda: other("swe", 10_000_000))
         guarded("lkdvRK", lambda: other("lkdvRK", 6_000_000))
 
+    xcomm = None
+    if xstats is not None:
+        mhz = clk.summary().get("sm_mhz") or 1965.0
+        xcomm = {"what": "rank 0, timed region: time its reducing kernels / halo exchanges spent waiting for the peers' NVLink flags (clock64)",
+                 "reduce_wait_ms_per_step": xstats["reduce_wait_cycles"] / (mhz * 1e3) / args.steps,
+                 "reductions_per_step": xstats["reductions"] / args.steps,
+                 "halo_wait_ms_per_step": xstats["halo_wait_cycles"] / (mhz * 1e3) / args.steps,
+                 "halo_exchanges_per_step": xstats["halo_exchanges"] / args.steps}
     line = {
         "metric": "krylov_iters_per_s", "value": value, "unit": "it/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
@@ -659,6 +670,7 @@ def run_ours(args):
         "ms_each_step": [round(t, 3) for t in per_solve],
         "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "parity": parity, "parity_vs_single": parity_vs_single,
         "e2e": e2e, "gpu_launches": launches, "clocks": clk.summary(), "parity_mode": parity_mode, "extra": extra,
+        "xcomm": xcomm,
         "bench_wall_s": round(elapsed(), 1),
     }
     print(json.dumps(line), flush=True)

@@ -222,6 +222,11 @@ int spis_constraint_set_constant(spis_ctx* ctx, int c, double cc);
 int spis_constraint_setup_async(spis_ctx* ctx, int c, int64_t nrows, int64_t ncols, int64_t nnz,
                                 const int32_t* indptr, const int32_t* indices, const double* data,
                                 const double* v, double cc);
+/* the same with the answer to "is M identically zero?" supplied (m_is_zero = 0 / 1; -1 = scan): row-sharded
+ * sessions take that decision collectively, once, for all ranks                                              */
+int spis_constraint_setup_async2(spis_ctx* ctx, int c, int64_t nrows, int64_t ncols, int64_t nnz,
+                                 const int32_t* indptr, const int32_t* indices, const double* data,
+                                 const double* v, double cc, int m_is_zero);
 int spis_constraint_setup_wait(spis_ctx* ctx);
 
 /* ---- the k-dimensional constrained minimisation (HOST code: solvers.py:251-255 keeps it off the device) ------
@@ -281,6 +286,10 @@ int spis_comm_destroy(spis_comm* comm);
 int spis_comm_capacity(const spis_comm* comm, int64_t* red_cap_out, int64_t* halo_cap_out);
 int spis_comm_allreduce(spis_comm* comm, double* vals, int count);
 int spis_ctx_attach_comm(spis_ctx* ctx, spis_comm* comm);
+/* out[4]: SM cycles this rank spent waiting for its peers inside fused reductions, number of fused reductions, the same
+ * two numbers for halo exchanges, since the last call (cleared by the call).  Evidence for where a sharded solve's time
+ * goes: streaming versus waiting on NVLink flags.                                                                     */
+int spis_xcomm_stats(spis_ctx* ctx, uint64_t* out);
 int spis_sync(spis_ctx* ctx);
 
 /* ---- measurement --------------------------------------------------------------------- */

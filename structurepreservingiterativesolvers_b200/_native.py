@@ -73,6 +73,7 @@ SIGNATURES = {
     "spis_constraint_define": (C.c_int, [_ctx, C.c_int, C.c_int, _dp, C.c_double]),
     "spis_constraint_terms": (C.c_int, [_ctx, C.c_int, C.c_int, _dp, _dp, _dp]),
     "spis_constraint_setup_async": (C.c_int, [_ctx, C.c_int, C.c_int64, C.c_int64, C.c_int64, _ip, _ip, _dp, _dp, C.c_double]),
+    "spis_constraint_setup_async2": (C.c_int, [_ctx, C.c_int, C.c_int64, C.c_int64, C.c_int64, _ip, _ip, _dp, _dp, C.c_double, C.c_int]),
     "spis_constraint_setup_wait": (C.c_int, [_ctx]),
     "spis_constraint_set_constant": (C.c_int, [_ctx, C.c_int, C.c_double]),
     "spis_small_kkt": (C.c_int, [C.c_int, C.c_int, _dp, C.c_double, C.c_int, _dp, _dp, _dp, _dp, _dp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -91,6 +92,7 @@ SIGNATURES = {
     "spis_comm_capacity": (C.c_int, [C.c_void_p, _lp, _lp]),
     "spis_comm_allreduce": (C.c_int, [C.c_void_p, _dp, C.c_int]),
     "spis_ctx_attach_comm": (C.c_int, [_ctx, C.c_void_p]),
+    "spis_xcomm_stats": (C.c_int, [_ctx, C.POINTER(C.c_uint64)]),
     "spis_sync": (C.c_int, [_ctx]),
     "spis_get_profile": (C.c_int, [_ctx, _dp, _dp, _lp]),
     "spis_reset_profile": (C.c_int, [_ctx]),

@@ -1358,7 +1358,8 @@ int spis_get_info(const spis_ctx* cctx, const char* key, int64_t* value_out) {
   else if (k == "alloc_miss_bytes") *value_out = g_dev_miss_bytes.load();
   else if (k == "can_fuse_iterate") *value_out = (ctx->fuse_iterate && ctx->orth == SPIS_ORTH_CGS2 && ctx->pre_kind == SPIS_PRE_NONE) ? 1 : 0;
   else if (k == "pipe_lag") *value_out = ctx->pre_kind == SPIS_PRE_NONE ? 1 : 0;
-  else if (k == "device_pipeline") *value_out = (ctx->orth == SPIS_ORTH_CGS2 && ctx->pre_kind != SPIS_PRE_HOST && !ctx->allreduce && !ctx->halo) ? 1 : 0;
+  else if (k == "device_pipeline") *value_out = (ctx->orth == SPIS_ORTH_CGS2 && ctx->pre_kind != SPIS_PRE_HOST && !ctx->allreduce && !ctx->halo &&
+                                                 (ctx->fuse_iterate || ctx->pre_kind != SPIS_PRE_NONE)) ? 1 : 0;
   else if (k == "device_ptr:small") *value_out = (int64_t)(intptr_t)ctx->d_small;
   else if (k == "stream") *value_out = (int64_t)(intptr_t)ctx->stream;
   else if (k == "n_send") *value_out = ctx->n_send;
@@ -2094,6 +2095,14 @@ int spis_constraint_set_constant(spis_ctx* ctx, int c, double cc) {
 int spis_constraint_setup_async(spis_ctx* ctx, int c, int64_t nrows, int64_t ncols, int64_t nnz,
                                 const int32_t* indptr, const int32_t* indices, const double* data,
                                 const double* v, double cc) {
+  return spis_constraint_setup_async2(ctx, c, nrows, ncols, nnz, indptr, indices, data, v, cc, -1);
+}
+
+// m_is_zero: -1 = find out (scan M's values), 0 / 1 = the caller knows -- a row-sharded session decides "is M zero?"
+// for ALL ranks together (one collective for every such question of the set-up) and passes the answer down.
+int spis_constraint_setup_async2(spis_ctx* ctx, int c, int64_t nrows, int64_t ncols, int64_t nnz,
+                                 const int32_t* indptr, const int32_t* indices, const double* data,
+                                 const double* v, double cc, int m_is_zero) {
   if (!ctx) return SPIS_E_INVALID;
   REQUIRE(c >= 0 && SPIS_SLOT_CON0 + c < SPIS_MAX_SLOTS, "constraint index %d out of range", c);
   REQUIRE(ctx->aux, "the context has no auxiliary stream");
@@ -2105,7 +2114,9 @@ int spis_constraint_setup_async(spis_ctx* ctx, int c, int64_t nrows, int64_t nco
     cudaSetDevice(ctx->device);
     tl_use_aux = true;
     int nz = 0;
-    int rc = nnz > 0 ? spis_host_any_nonzero(data, (size_t)nnz, &nz) : SPIS_OK;
+    int rc = SPIS_OK;
+    if (m_is_zero >= 0) nz = m_is_zero ? 0 : 1;
+    else if (nnz > 0) rc = spis_host_any_nonzero(data, (size_t)nnz, &nz);
     pt.mark(nz ? "constraint: M is not zero" : "constraint: M is zero");
     int slot = -1;
     if (rc == SPIS_OK && nz) {
@@ -2539,6 +2550,23 @@ int spis_xcomm_set_halo(spis_ctx* ctx, const int32_t* dest_rank, const int32_t* 
   TRY(dalloc(ctx, &ctx->d_recv_from, (size_t)kMaxRanks));
   TRY(h2d(ctx, ctx->d_send_to, send_to, (size_t)ctx->xv.world * sizeof(int32_t)));
   TRY(h2d(ctx, ctx->d_recv_from, recv_from, (size_t)ctx->xv.world * sizeof(int32_t)));
+  return SPIS_OK;
+}
+
+// out[0..3]: SM cycles this rank's reducing kernels spent waiting for their peers' contributions and the number of
+// fused reductions, the same for halo exchanges -- since the last call (the counters are cleared).
+int spis_xcomm_stats(spis_ctx* ctx, uint64_t* out) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(out, "null output");
+  for (int i = 0; i < 4; ++i) out[i] = 0;
+  if (!ctx->xbuf) return SPIS_OK;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  unsigned long long w[8] = {0};
+  double* at = ctx->xbuf + ctx->xv.flags_off() + 4 * ctx->xv.world;
+  CU(cudaMemcpy(w, at, sizeof(w), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 4; ++i) out[i] = w[1 + i];
+  CU(cudaMemset(at + 1, 0, 6 * sizeof(double)));
   return SPIS_OK;
 }
 

@@ -85,6 +85,11 @@ struct XView {
   __device__ unsigned long long* err_word(int owner) const {
     return reinterpret_cast<unsigned long long*>(base[owner] + flags_off()) + 4 * world;
   }
+  // statistics words behind the error word: [1] SM cycles spent waiting for peers inside fused reductions, [2] number of
+  // such reductions, [3] / [4] the same for halo exchanges (read and cleared by spis_xcomm_stats)
+  __device__ unsigned long long* stat_word(int owner, int i) const {
+    return reinterpret_cast<unsigned long long*>(base[owner] + flags_off()) + 4 * world + i;
+  }
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
@@ -126,9 +131,15 @@ __device__ __forceinline__ void cta_xreduce(double* buf, int count, const XView&
   __syncthreads();
   if ((int)threadIdx.x < xv.world) {
     st_release_sys(xv.red_flag(threadIdx.x, phase, xv.rank), seq);
+    const long long t0 = clock64();
     wait_flag(xv.red_flag(xv.rank, phase, threadIdx.x), seq, xv.err_word(xv.rank));
+    atomicMax(xv.stat_word(xv.rank, 5), (unsigned long long)(clock64() - t0));      // longest wait of this reduction
   }
   __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long* st = xv.stat_word(xv.rank, 0);
+    st[1] += st[5]; st[5] = 0ull; st[2] += 1ull;
+  }
   const double* mine = xv.base[xv.rank];
   for (int i = threadIdx.x; i < count; i += blockDim.x) {
     double s = 0.0;
@@ -794,7 +805,7 @@ lincomb2n_kernel(const double* __restrict__ V, int64_t ld, int m, const double* 
 // unconstrained iterate x_j = x0 + Z y_j is formed by kernels that were queued before y_j existed; the host only
 // reads the records (mapped page-locked memory) to follow the residual and to decide the phase switch.
 //   in : h1, h2 (the two CGS2 projections), h2[m] = ||w'||^2
-//   out: norm2_out[0] = h[j+1,j]^2 = ||w'||^2 - |h2|^2, norm2_out[1] = |h2|^2, the rotated column in R, y_j = R^{-1} g
+//   out: norm2_out[0] = h[j+1,j]^2 = ||w'||^2 - |h2|^2, the rotated column in R, y_j = R^{-1} g
 //        in ydst, and the host record [0] seq, [1] valid, [2] |g_{j+1}| = min_y |beta e1 - H y|, [3] h[j+1,j]^2,
 //        [4] ||w'||^2, [5] |h2|^2, [8..8+K) the column h[0..j+1, j], [8+K..8+2K) y_j.
 // valid = 0 (a vanishing pivot: R singular to working precision) also sets the phase word: the host takes over.
@@ -828,7 +839,7 @@ hess_kernel(int j, HessState st, const double* __restrict__ h1, const double* __
   double n2 = nw2 - s2;
   if (!(n2 > 0.0)) n2 = 0.0;
   const double hn = sqrt(n2);
-  if (lane == 0) { r[m] = hn; norm2_out[0] = n2; norm2_out[1] = s2; }
+  if (lane == 0) { r[m] = hn; norm2_out[0] = n2; }
   __syncwarp();
   if (host_rec) for (int i = lane; i <= m; i += 32) host_rec[8 + i] = r[i];
   __syncwarp();
@@ -2259,9 +2270,15 @@ halo_xchg_kernel(double* vecA, double* vecB, int64_t hoff, int64_t n_halo, const
   __syncthreads();
   if ((int)threadIdx.x < xv.world) {
     if (send_to[threadIdx.x]) st_release_sys(xv.halo_flag(threadIdx.x, phase, xv.rank), seq);
+    const long long t0 = clock64();
     if (recv_from[threadIdx.x]) wait_flag(xv.halo_flag(xv.rank, phase, threadIdx.x), seq, xv.err_word(xv.rank));
+    atomicMax(xv.stat_word(xv.rank, 6), (unsigned long long)(clock64() - t0));
   }
   __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long* st = xv.stat_word(xv.rank, 0);
+    st[3] += st[6]; st[6] = 0ull; st[4] += 1ull;
+  }
   const double* src = xv.base[xv.rank] + hb;
   for (int64_t i = threadIdx.x; i < n_halo; i += blockDim.x) {
     vecA[hoff + i] = ld_volatile(src + i);

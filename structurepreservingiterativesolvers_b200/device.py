@@ -222,18 +222,20 @@ class KrylovContext:
         self._live()
         self._check(self._lib.spis_constraint_set_constant(self._h, c, float(cc)))
 
-    def constraint_setup_async(self, c: int, M, v, cc: float):
+    def constraint_setup_async(self, c: int, M, v, cc: float, m_is_zero=None, v_is_zero=None):
         """Stage class-form constraint c (sparse M, vector v, scalar cc) on a native helper thread; the arrays
-        handed to the library are kept alive here until constraint_setup_wait()."""
+        handed to the library are kept alive here until constraint_setup_wait().  m_is_zero / v_is_zero: answers a
+        row-sharded session has already agreed on with the other ranks (None: the library scans)."""
         self._live()
         M, indptr, indices, data = _csr_arrays(M)
         if M.shape[0] != self.n:
             raise ValueError(f"constraint matrix has {M.shape[0]} rows, context owns {self.n}")
-        v = nat.as_f64(v, self.n)
+        v = None if v_is_zero else nat.as_f64(v, self.n)
         self._async_refs = getattr(self, "_async_refs", [])
         self._async_refs.append((indptr, indices, data, v))
-        self._check(self._lib.spis_constraint_setup_async(self._h, c, M.shape[0], M.shape[1], M.nnz, nat.iptr(indptr),
-                                                          nat.iptr(indices), nat.dptr(data), nat.dptr(v), float(cc)))
+        self._check(self._lib.spis_constraint_setup_async2(self._h, c, M.shape[0], M.shape[1], M.nnz, nat.iptr(indptr),
+                                                           nat.iptr(indices), nat.dptr(data), nat.dptr(v) if v is not None else None,
+                                                           float(cc), -1 if m_is_zero is None else int(bool(m_is_zero))))
 
     def constraint_setup_wait(self):
         self._live()
@@ -325,6 +327,13 @@ class KrylovContext:
         a = [np.ascontiguousarray(x, dtype=np.int32) for x in (dest_rank, dest_off, send_to, recv_from)]
         self._check(self._lib.spis_xcomm_set_halo(self._h, nat.iptr(a[0]) if a[0].size else None,
                                                   nat.iptr(a[1]) if a[1].size else None, nat.iptr(a[2]), nat.iptr(a[3])))
+
+    def xcomm_stats(self) -> dict:
+        """Cycles spent waiting for peers inside fused reductions / halo exchanges since the last call (and their counts)."""
+        self._live()
+        out = (C.c_uint64 * 4)()
+        self._check(self._lib.spis_xcomm_stats(self._h, out))
+        return {"reduce_wait_cycles": int(out[0]), "reductions": int(out[1]), "halo_wait_cycles": int(out[2]), "halo_exchanges": int(out[3])}
 
     def sync(self):
         self._live()

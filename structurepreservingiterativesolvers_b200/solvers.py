@@ -237,7 +237,10 @@ class DeviceSession:
         if len(conlist) > nat.MAX_SLOTS - nat.SLOT_CON0:
             raise ValueError("too many constraints")
         self._cons = [None] * len(conlist)
-        if conlist and _opt("async_setup", async_setup) and type(self) is DeviceSession and hasattr(ctx, "use_aux_stream"):
+        sharded = type(self) is not DeviceSession          # row-sharded: the yes/no decisions were taken collectively (_preflags)
+        if conlist and _opt("async_setup", async_setup) and hasattr(ctx, "use_aux_stream") and \
+                (not sharded or (hasattr(ctx, "constraint_setup_async") and getattr(self, "_preflags", None) is not None
+                                 and all(_classify_constraint(c) == "class" and sps.issparse(getattr(c, "M", None)) for c in conlist))):
             # one helper per constraint: the host scan of one (`0*A`) overlaps the PCIe upload of another.
             # Class-form constraints with a sparse M go to NATIVE helper threads (one C call each: they never
             # need the interpreter lock the loop's thread holds); anything else to a Python thread.
@@ -247,7 +250,11 @@ class DeviceSession:
                         and sps.issparse(getattr(const, "M", None))):
                     entry = {"kind": "class", "const": const, "error": None}
                     try:
-                        ctx.constraint_setup_async(idx, const.M, const.v, float(const.c))
+                        if sharded:
+                            ctx.constraint_setup_async(idx, const.M, const.v, float(const.c),
+                                                       m_is_zero=not self._preflags[("M", idx)], v_is_zero=not self._preflags[("v", idx)])
+                        else:
+                            ctx.constraint_setup_async(idx, const.M, const.v, float(const.c))
                         self._native_jobs = True
                     except nat.NativeLibraryError:
                         raise
@@ -680,6 +687,7 @@ class _Pipeline:
         self.device_iter = True                    # False once the host forms the iterates itself
         self.x_holds = None                        # iterate index known to be in the X buffer
         self._ls_prev = None
+        self.ctx.set_option("spmv_dual", 1 if _opt("dual_spmv", None) else 0)
         self.ctx.pipe_begin(self.thr, not (self.beta > self.thr))
 
     # -- queueing ---------------------------------------------------------------------------------------------
@@ -1165,26 +1173,27 @@ def _cgmres_pipelined(sess, k, tol, contol, beta, timing, jit, history_mode, tr)
             warnings.warn(_BREAKDOWN)                     # (solvers.py:199-202)
             break
         Hj = pipe.H[: j + 2, : j + 1]
-        y0 = np.zeros(j + 1)
-        if j != 0:
-            y0[:-1] = yk                                  # warm start (solvers.py:225-227)
 
         def unconstrained():
             y = pipe.ls_solution(j + 1)
             return smallsolve.SmallResult(y) if y is not None else smallsolve.lstsq(Hj, beta)
 
         if go and j < k - 1 and safety is None:           # (solvers.py:230)
-            res = unconstrained()
-            yk = res.x
+            y_dev = pipe.ls_solution(j + 1)               # the device's least-squares coefficients (None: pivot trouble)
             bk.mark("small solve + host")
-            if pipe.ls_solution(j + 1) is not None:
+            if y_dev is not None:
+                yk = y_dev
                 r, go = pipe.device_iterate_residual(j, yk, cannot_end=True)
             else:
+                yk = smallsolve.lstsq(Hj, beta).x
                 r = pipe.host_iterate_residual(j, yk)
                 go = r > thr
             residual.append(r)                            # (solvers.py:287,290)
         else:
             pipe.host_takes_over()
+            y0 = np.zeros(j + 1)
+            if j != 0:
+                y0[:-1] = yk                              # warm start (solvers.py:225-227)
             try:
                 if timing:
                     constrained_steps += 1

@@ -56,7 +56,8 @@ class FakeKrylovContext:
     def info(self, key):
         if key == "device_pipeline":
             return int(self.opts.get("orth", nat.ORTH_CGS2) == nat.ORTH_CGS2 and self.pre_kind != nat.PRE_HOST
-                       and self.allreduce is None and self.halo_cb is None)
+                       and self.allreduce is None and self.halo_cb is None
+                       and (self.opts.get("fuse_iterate", 1) or self.pre_kind != nat.PRE_NONE))
         if key == "pipe_lag":
             return int(self.pre_kind == nat.PRE_NONE)
         if key == "can_fuse_iterate":
