@@ -319,6 +319,7 @@ def kernel_table(prof, steps, peak):
         if not v["launches"]:
             continue
         out[k] = {"ms_per_step": v["ms"] / steps, "launches_per_step": v["launches"] / steps,
+                  "idle_before_ms_per_step": v.get("idle_before_ms", 0.0) / steps,
                   "gbs_model_csr": v["gbs"], "gbs": v.get("gbs_moved"),
                   "frac_of_peak": (v["gbs_moved"] / peak if v.get("gbs_moved") else None)}
     return out
@@ -345,7 +346,7 @@ def timed_solves(sess, solve, steps, warmup, barrier=lambda: None):
     return iters, max(wall, ev_ms * 1e-3), per, x, info, ev_ms
 
 
-def extra_run(name, A, b, x0, conlist, tol, local, pre=None, k=K_KRYLOV, steps=3, warmup=1, spmv_format=None, peak=1.0, note=""):
+def extra_run(name, A, b, x0, conlist, tol, local, pre=None, k=K_KRYLOV, steps=3, warmup=2, spmv_format=None, peak=1.0, note=""):
     """One more configuration on the same box: device-resident solves + per-kernel fractions."""
     from structurepreservingiterativesolvers_b200 import solvers
     t_in = time.perf_counter()
@@ -621,12 +622,13 @@ def run_ours(args):
 
         def general_matrix():
             # the path a real `getValuesCSR` export takes (lkdv/lkdv.py:109-111): assembly round-off in the values, so
-            # neither row patterns nor a value dictionary exist -- every value moved by <= 1 ulp, SELL-32 storage
+            # neither row patterns nor a value dictionary exist -- plain SELL-32 storage
             rng = np.random.default_rng(1)
             Ap = A.copy()
-            Ap.data = Ap.data * (1.0 + (rng.integers(-1, 2, Ap.data.size) * np.finfo(float).eps))
+            Ap.data = Ap.data * (1.0 + 1e-13 * rng.uniform(-1.0, 1.0, Ap.data.size))
             out, xg, _ = extra_run("general_matrix", Ap, b, x0, conlist, tol, local, peak=peak,
-                                   note="same system, values perturbed by <= 1 ulp so that pattern / dictionary detection fails")
+                                   note="same system, every value perturbed by a relative 1e-13 (assembly round-off): no two rows share a "
+                                        "stencil and there are millions of distinct values, so row-pattern and dictionary storage do not apply")
             out["rel_diff_vs_headline"] = float(np.linalg.norm(xg - x_gpu) / np.linalg.norm(x_gpu))
             out["slowdown_vs_headline"] = out["ms_per_step"] / (1e3 * secs / args.steps)
             return out

@@ -300,6 +300,9 @@ int spis_reset_profile(spis_ctx* ctx);
 /* moved_out[c]: bytes the launches of class c move with the storage format they ran on (row-pattern ids, value codes,
  * one pass over the matrix for two products); equals bytes_out of spis_get_profile for everything but SpMV          */
 int spis_get_profile_moved(spis_ctx* ctx, double* moved_out);
+/* profile mode: gaps_out[c] = milliseconds the device was idle right before the launches of class c (from the end of the
+ * previous profiled kernel): where a solve waits for the host, for a copy or for another stream                       */
+int spis_get_profile_gaps(spis_ctx* ctx, double* gaps_out);
 /* CUDA-event stopwatch on the context's stream: device time between the two calls.      */
 int spis_timer_start(spis_ctx* ctx);
 int spis_timer_stop(spis_ctx* ctx, double* ms_out);

@@ -178,6 +178,7 @@ struct spis_ctx {
   std::vector<DevBlock> owned;   // device blocks currently held by this context
   std::vector<AsyncJob*> jobs;   // native helper threads staging constraint data (joined by spis_constraint_setup_wait)
   double prof_ms[SPIS_PROF_CLASSES] = {0}; double prof_bytes[SPIS_PROF_CLASSES] = {0}; int64_t prof_launch[SPIS_PROF_CLASSES] = {0};
+  double prof_gap_ms[SPIS_PROF_CLASSES] = {0};  // profile mode: device idle time BEFORE the launches of each class (end of the previous kernel -> start)
   double prof_moved[SPIS_PROF_CLASSES] = {0};   // bytes the launches move with the storage format they actually run on (== prof_bytes except SpMV)
   char err[512] = "";
 };
@@ -320,12 +321,18 @@ int prof_end(spis_ctx* ctx) {
 int prof_resolve(spis_ctx* ctx) {
   if (ctx->recs.empty()) return SPIS_OK;
   CU(cudaStreamSynchronize(ctx->stream));
-  for (auto& r : ctx->recs) {
+  for (size_t i = 0; i < ctx->recs.size(); ++i) {
+    auto& r = ctx->recs[i];
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, r.e0, r.e1));
     ctx->prof_ms[r.cls] += ms;
-    ctx->evpool.push_back(r.e0); ctx->evpool.push_back(r.e1);
+    if (i > 0) {
+      float gap = 0.f;
+      if (cudaEventElapsedTime(&gap, ctx->recs[i - 1].e1, r.e0) == cudaSuccess && gap > 0.f) ctx->prof_gap_ms[r.cls] += gap;
+      else cudaGetLastError();
+    }
   }
+  for (auto& r : ctx->recs) { ctx->evpool.push_back(r.e0); ctx->evpool.push_back(r.e1); }
   ctx->recs.clear();
   return SPIS_OK;
 }
@@ -361,21 +368,9 @@ int do_allreduce(spis_ctx* ctx, double* dev, int64_t count, bool force = false) 
   if (r != 0) return fail(ctx, SPIS_E_INVALID, "allreduce callback failed (%d)", r);
   return SPIS_OK;
 }
+int do_halo2(spis_ctx* ctx, double* a, double* b);
 int do_halo(spis_ctx* ctx, double* vec) {
-  if (ctx->xactive) {
-    if (ctx->n_halo == 0 && ctx->n_send == 0) return SPIS_OK;
-    const unsigned long long seq = (*ctx->hseq_p)++;
-    if (ctx->n_send > 0) {
-      const int64_t g = (ctx->n_send + 255) / 256;
-      const int grid = (int)(g < (int64_t)ctx->nsm * 8 ? g : (int64_t)ctx->nsm * 8);
-      halo_push_kernel<<<grid, 256, 0, ctx->stream>>>(vec, ctx->d_send_idx, ctx->d_dest_rank, ctx->d_dest_off, ctx->n_send, ctx->xv, seq);
-      CU(cudaGetLastError());
-    }
-    halo_pull_kernel<<<1, 1024, 0, ctx->stream>>>(vec + ctx->hoff, ctx->n_halo, ctx->d_send_to, ctx->d_recv_from, ctx->xv, seq);
-    CU(cudaGetLastError());
-    ctx->prof_launch[SPIS_PROF_OTHER] += 2;
-    return SPIS_OK;
-  }
+  if (ctx->xactive) return do_halo2(ctx, vec, nullptr);
   if (!ctx->halo || (ctx->n_halo == 0 && ctx->n_send == 0)) return SPIS_OK;
   if (ctx->n_send > 0) {
     const int grid = (int)((ctx->n_send + 255) / 256 < (int64_t)ctx->nsm * 8 ? (ctx->n_send + 255) / 256 : (int64_t)ctx->nsm * 8);
@@ -395,10 +390,10 @@ int do_halo2(spis_ctx* ctx, double* a, double* b) {
     return b ? do_halo(ctx, b) : SPIS_OK;
   }
   if (ctx->n_halo == 0 && ctx->n_send == 0) return SPIS_OK;
-  REQUIRE(ctx->xv.halo_cap / 2 >= ctx->n_halo, "comm buffer holds %lld ghost entries per vector, %lld needed", (long long)(ctx->xv.halo_cap / 2), (long long)ctx->n_halo);
+  REQUIRE(ctx->xv.halo_cap / 4 >= ctx->n_halo, "comm buffer holds %lld ghost entries per vector, %lld needed", (long long)(ctx->xv.halo_cap / 4), (long long)ctx->n_halo);
   const unsigned long long seq = (*ctx->hseq_p)++;
   halo_xchg_kernel<<<1, 1024, 0, ctx->stream>>>(a, b, ctx->hoff, ctx->n_halo, ctx->d_send_idx, ctx->d_dest_rank, ctx->d_dest_off,
-                                                 ctx->n_send, ctx->d_send_to, ctx->d_recv_from, ctx->xv, seq);
+                                                 ctx->n_send, ctx->xv, seq);
   CU(cudaGetLastError());
   ctx->prof_launch[SPIS_PROF_OTHER] += 1;
   return SPIS_OK;
@@ -2385,7 +2380,7 @@ int spis_xcomm_create(spis_ctx* ctx, int rank, int world, int64_t halo_cap, void
   XView xv;
   xv.world = world; xv.rank = rank;
   xv.red_cap = ctx->K > 1024 ? ctx->K : 1024;
-  xv.halo_cap = halo_cap > 0 ? 2 * roundup(halo_cap, 16) : 32;      // two vectors per exchange (halo_xchg_kernel)
+  xv.halo_cap = halo_cap > 0 ? 4 * roundup(halo_cap, 16) : 64;      // two vectors per exchange, 16 bytes per value (halo_xchg_kernel)
   const size_t bytes = xv.total_doubles() * sizeof(double);
   CU(cudaMalloc((void**)&ctx->xbuf, bytes));          // plain cudaMalloc: pool memory cannot be exported
   CU(cudaMemset(ctx->xbuf, 0, bytes));
@@ -2430,7 +2425,7 @@ int spis_comm_create(int device, int rank, int world, int64_t red_cap, int64_t h
   c->device = device;
   c->xv.world = world; c->xv.rank = rank;
   c->xv.red_cap = (int)(red_cap < 1024 ? 1024 : red_cap);
-  c->xv.halo_cap = halo_cap > 0 ? 2 * roundup(halo_cap, 16) : 32;
+  c->xv.halo_cap = halo_cap > 0 ? 4 * roundup(halo_cap, 16) : 64;
   const size_t bytes = c->xv.total_doubles() * sizeof(double);
   cudaError_t e = cudaMalloc((void**)&c->xbuf, bytes);            // plain cudaMalloc: pool memory cannot be exported
   if (e == cudaSuccess) e = cudaMemset(c->xbuf, 0, bytes);
@@ -2488,7 +2483,7 @@ int spis_comm_destroy(spis_comm* comm) {
 int spis_comm_capacity(const spis_comm* comm, int64_t* red_cap_out, int64_t* halo_cap_out) {
   if (!comm) return SPIS_E_INVALID;
   if (red_cap_out) *red_cap_out = comm->xv.red_cap;
-  if (halo_cap_out) *halo_cap_out = comm->xv.halo_cap / 2;
+  if (halo_cap_out) *halo_cap_out = comm->xv.halo_cap / 4;
   return SPIS_OK;
 }
 
@@ -2522,7 +2517,7 @@ int spis_ctx_attach_comm(spis_ctx* ctx, spis_comm* comm) {
   REQUIRE(!ctx->xbuf && !ctx->comm, "the context already has a communicator");
   REQUIRE(comm->device == ctx->device, "communicator lives on device %d, context on %d", comm->device, ctx->device);
   REQUIRE(comm->xv.red_cap >= ctx->K + 1, "communicator reduces %d doubles at a time, k_max = %d needs %d", comm->xv.red_cap, ctx->kmax, ctx->K + 1);
-  REQUIRE(comm->xv.halo_cap / 2 >= ctx->n_halo, "communicator holds %lld ghost entries per vector, the context has %lld", (long long)(comm->xv.halo_cap / 2), (long long)ctx->n_halo);
+  REQUIRE(comm->xv.halo_cap / 4 >= ctx->n_halo, "communicator holds %lld ghost entries per vector, the context has %lld", (long long)(comm->xv.halo_cap / 4), (long long)ctx->n_halo);
   ctx->comm = comm;
   ctx->xbuf = comm->xbuf;
   ctx->xv = comm->xv;
@@ -2603,7 +2598,7 @@ int spis_get_profile(spis_ctx* ctx, double* ms_out, double* bytes_out, int64_t* 
 int spis_reset_profile(spis_ctx* ctx) {
   if (!ctx) return SPIS_E_INVALID;
   TRY(prof_resolve(ctx));
-  for (int i = 0; i < SPIS_PROF_CLASSES; ++i) { ctx->prof_ms[i] = 0; ctx->prof_bytes[i] = 0; ctx->prof_launch[i] = 0; ctx->prof_moved[i] = 0; }
+  for (int i = 0; i < SPIS_PROF_CLASSES; ++i) { ctx->prof_ms[i] = 0; ctx->prof_bytes[i] = 0; ctx->prof_launch[i] = 0; ctx->prof_moved[i] = 0; ctx->prof_gap_ms[i] = 0; }
   return SPIS_OK;
 }
 
@@ -2612,6 +2607,16 @@ int spis_reset_profile(spis_ctx* ctx) {
 int spis_get_profile_moved(spis_ctx* ctx, double* moved_out) {
   if (!ctx || !moved_out) return SPIS_E_INVALID;
   for (int i = 0; i < SPIS_PROF_CLASSES; ++i) moved_out[i] = ctx->prof_moved[i];
+  return SPIS_OK;
+}
+
+// profile mode: gaps_out[c] = milliseconds the device sat idle right before the launches of class c (end of the previous
+// profiled kernel to the start of this one: waiting for the host, a copy, or another stream)
+int spis_get_profile_gaps(spis_ctx* ctx, double* gaps_out) {
+  if (!ctx || !gaps_out) return SPIS_E_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  TRY(prof_resolve(ctx));
+  for (int i = 0; i < SPIS_PROF_CLASSES; ++i) gaps_out[i] = ctx->prof_gap_ms[i];
   return SPIS_OK;
 }
 

@@ -72,9 +72,10 @@ struct XView {
   int red_cap = 0;               // doubles per reduce slot
   long long halo_cap = 0;        // doubles per halo phase
   double* base[kMaxRanks] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  __host__ __device__ size_t red_off(int phase, int src) const { return ((size_t)phase * world + src) * (size_t)red_cap; }
-  __host__ __device__ size_t halo_off(int phase) const { return (size_t)2 * world * red_cap + (size_t)phase * halo_cap; }
-  __host__ __device__ size_t flags_off() const { return (size_t)2 * world * red_cap + (size_t)2 * halo_cap; }
+  // a reduce slot holds red_cap values of 16 bytes each: the two 32-bit halves of a double, each paired with a 32-bit flag
+  __host__ __device__ size_t red_off(int phase, int src) const { return ((size_t)phase * world + src) * (size_t)red_cap * 2; }
+  __host__ __device__ size_t halo_off(int phase) const { return (size_t)4 * world * red_cap + (size_t)phase * halo_cap; }
+  __host__ __device__ size_t flags_off() const { return (size_t)4 * world * red_cap + (size_t)2 * halo_cap; }
   __host__ __device__ size_t total_doubles() const { return flags_off() + 4 * (size_t)world + 8; }
   __device__ unsigned long long* red_flag(int owner, int phase, int src) const {
     return reinterpret_cast<unsigned long long*>(base[owner] + flags_off()) + phase * world + src;
@@ -119,32 +120,59 @@ __device__ __forceinline__ bool wait_flag(const unsigned long long* flag, unsign
 
 // All-reduce (sum) of buf[0..count) across ranks, executed by ONE CTA; count <= red_cap.
 // Must be called by all threads of the CTA.  On return buf holds the global sums.
+// Low-latency protocol (the "LL" scheme of NCCL): every double travels as two 8-byte words, {low half, flag} and
+// {high half, flag}, with flag = the low 32 bits of the sequence number, written straight into the peer's slot with one
+// 16-byte store.  An 8-byte store is atomic across NVLink, so a receiver that sees the right flag in BOTH words has the
+// value: no system fence, no separate flag round trip -- one NVLink write latency per reduction instead of three.
+__device__ __forceinline__ void st_ll(unsigned long long* dst, double v, unsigned flag) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+  const unsigned long long f = (unsigned long long)flag << 32;
+  const unsigned long long lo = (bits & 0xffffffffull) | f, hi = (bits >> 32) | f;
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(lo), "l"(hi) : "memory");
+}
+__device__ __forceinline__ bool ld_ll(const unsigned long long* src, unsigned flag, double* v) {
+  unsigned long long lo, hi;
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(src) : "memory");
+  if ((unsigned)(lo >> 32) != flag || (unsigned)(hi >> 32) != flag) return false;
+  *v = __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
+  return true;
+}
+
 __device__ __forceinline__ void cta_xreduce(double* buf, int count, const XView& xv, unsigned long long seq) {
   if (xv.world <= 1) return;
   const int phase = (int)(seq & 1ull);
+  const unsigned flag = (unsigned)seq;
   __syncthreads();
   for (int p = 0; p < xv.world; ++p) {
-    double* dst = xv.base[p] + xv.red_off(phase, xv.rank);
-    for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = buf[i];
+    if (p == xv.rank) continue;
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(xv.base[p] + xv.red_off(phase, xv.rank));
+    for (int i = threadIdx.x; i < count; i += blockDim.x) st_ll(dst + 2 * i, buf[i], flag);
   }
-  __threadfence_system();
-  __syncthreads();
-  if ((int)threadIdx.x < xv.world) {
-    st_release_sys(xv.red_flag(threadIdx.x, phase, xv.rank), seq);
-    const long long t0 = clock64();
-    wait_flag(xv.red_flag(xv.rank, phase, threadIdx.x), seq, xv.err_word(xv.rank));
-    atomicMax(xv.stat_word(xv.rank, 5), (unsigned long long)(clock64() - t0));      // longest wait of this reduction
+  const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(xv.base[xv.rank]);
+  unsigned long long waited = 0ull;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) {
+    double s = 0.0;
+    for (int r = 0; r < xv.world; ++r) {                     // rank order: the same sum, bit for bit, on every rank
+      double v = buf[i];
+      if (r != xv.rank) {
+        const unsigned long long* src = mine + xv.red_off(phase, r) + 2 * (size_t)i;
+        if (!ld_ll(src, flag, &v)) {
+          const long long t0 = clock64();
+          while (!ld_ll(src, flag, &v)) {
+            if (clock64() - t0 > 40000000000ll) { *xv.err_word(xv.rank) = seq | (1ull << 63); v = 0.0; break; }
+          }
+          waited += (unsigned long long)(clock64() - t0);
+        }
+      }
+      s += v;
+    }
+    buf[i] = s;
   }
+  if (waited) atomicMax(xv.stat_word(xv.rank, 5), waited);    // longest wait of this reduction
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned long long* st = xv.stat_word(xv.rank, 0);
     st[1] += st[5]; st[5] = 0ull; st[2] += 1ull;
-  }
-  const double* mine = xv.base[xv.rank];
-  for (int i = threadIdx.x; i < count; i += blockDim.x) {
-    double s = 0.0;
-    for (int r = 0; r < xv.world; ++r) s += ld_volatile(mine + xv.red_off(phase, r) + i);
-    buf[i] = s;
   }
   __syncthreads();
 }
@@ -196,32 +224,26 @@ __device__ __forceinline__ void finish_reduction(double* __restrict__ partial, i
   __threadfence();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nb = gridDim.x;
-  const int per = (nb + kWarps - 1) / kWarps;
-  const int b0 = warp * per;
-  const int b1 = min(nb, b0 + per);
-  for (int i0 = 0; i0 < nout; i0 += 32) {
-    const int i = i0 + lane;
+  const int nwarps = blockDim.x >> 5;
+  // Output i is summed by warp i % nwarps: lane l adds the partials of CTAs l, l + 32, ... (eight independent loads in
+  // flight at a time, four running sums), then a butterfly over the lanes -- a fixed order, so the result does not depend
+  // on CTA scheduling, and one round trip to L2 per eight CTAs-per-lane instead of one per four CTAs of a serial walk.
+  for (int i = warp; i < nout; i += nwarps) {
+    const double* col = partial + i;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    if (i < nout) {
-      int b = b0;
-      for (; b + 4 <= b1; b += 4) {
-        a0 += __ldcg(partial + (size_t)(b + 0) * pstride + i);
-        a1 += __ldcg(partial + (size_t)(b + 1) * pstride + i);
-        a2 += __ldcg(partial + (size_t)(b + 2) * pstride + i);
-        a3 += __ldcg(partial + (size_t)(b + 3) * pstride + i);
-      }
-      for (; b < b1; ++b) a0 += __ldcg(partial + (size_t)b * pstride + i);
+    int b = lane;
+    for (; b + 224 < nb; b += 256) {
+      const double v0 = __ldcg(col + (size_t)(b) * pstride), v1 = __ldcg(col + (size_t)(b + 32) * pstride);
+      const double v2 = __ldcg(col + (size_t)(b + 64) * pstride), v3 = __ldcg(col + (size_t)(b + 96) * pstride);
+      const double v4 = __ldcg(col + (size_t)(b + 128) * pstride), v5 = __ldcg(col + (size_t)(b + 160) * pstride);
+      const double v6 = __ldcg(col + (size_t)(b + 192) * pstride), v7 = __ldcg(col + (size_t)(b + 224) * pstride);
+      a0 += v0; a1 += v1; a2 += v2; a3 += v3; a0 += v4; a1 += v5; a2 += v6; a3 += v7;
     }
-    sred[warp * 32 + lane] = (a0 + a1) + (a2 + a3);
-    __syncthreads();
-    if (warp == 0 && i < nout) {
-      double s = 0.0;
-#pragma unroll
-      for (int w = 0; w < kWarps; ++w) s += sred[w * 32 + lane];
-      out[i] = s;
-    }
-    __syncthreads();
+    for (; b < nb; b += 32) a0 += __ldcg(col + (size_t)b * pstride);
+    const double t = warp_sum((a0 + a1) + (a2 + a3));
+    if (lane == 0) out[i] = t;
   }
+  __syncthreads();
   if (threadIdx.x == 0) *counter = 0u;   // ready for the next launch on this stream
   int nred = nout;
   if (tx && tx->rpart) {
@@ -2222,67 +2244,47 @@ xreduce_kernel(double* buf, int64_t count, const __grid_constant__ XView xv, uns
   }
 }
 
-// halo push: the entries of `vec` my neighbours need go straight into THEIR comm buffers over
-// NVLink (dest_rank[i], dest_off[i] = position in that rank's ghost ordering)
-__global__ void halo_push_kernel(const double* __restrict__ vec, const int32_t* __restrict__ idx,
-                                 const int32_t* __restrict__ dest_rank, const int32_t* __restrict__ dest_off,
-                                 int64_t n_send, const __grid_constant__ XView xv, unsigned long long seq) {
-  const int phase = (int)(seq & 1ull);
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_send; i += stride)
-    xv.base[dest_rank[i]][xv.halo_off(phase) + dest_off[i]] = vec[idx[i]];
-  __threadfence_system();
-}
-
-// halo pull (one CTA): tell every destination that my entries have landed (the push kernel has
-// completed), wait for every source, then copy the ghosts next to the owned part of the vector
-__global__ void __launch_bounds__(1024)
-halo_pull_kernel(double* __restrict__ ghost_dst, int64_t n_halo, const int32_t* __restrict__ send_to,
-                 const int32_t* __restrict__ recv_from, const __grid_constant__ XView xv, unsigned long long seq) {
-  const int phase = (int)(seq & 1ull);
-  __threadfence_system();
-  if ((int)threadIdx.x < xv.world) {
-    if (send_to[threadIdx.x]) st_release_sys(xv.halo_flag(threadIdx.x, phase, xv.rank), seq);
-    if (recv_from[threadIdx.x]) wait_flag(xv.halo_flag(xv.rank, phase, threadIdx.x), seq, xv.err_word(xv.rank));
-  }
-  __syncthreads();
-  const double* src = xv.base[xv.rank] + xv.halo_off(phase);
-  for (int64_t i = threadIdx.x; i < n_halo; i += blockDim.x) ghost_dst[i] = ld_volatile(src + i);
-}
-
 // One exchange for up to TWO vectors (the Arnoldi vector z_j and the iterate x, which the dual SpMV multiplies in the
-// same pass): push my entries into the neighbours' comm buffers, flag, wait for theirs, copy the ghosts in place.
-// One CTA: a row-sharded strip sends a few thousand doubles (lkdv: 6) -- four launches and two flag rounds become one.
+// same pass), one CTA, low-latency protocol as in cta_xreduce: every ghost value is pushed into the neighbour's comm
+// buffer as two {32-bit half, 32-bit flag} words (one 16-byte store), the receiver polls each of its ghost slots until
+// both flags carry this exchange's sequence number.  No fences, no flag round, no second kernel: a row-sharded strip
+// sends a few thousand doubles (lkdv: 6), so the exchange costs one NVLink write latency.
+// Slot reuse (two phases): a neighbour can only write exchange seq + 2 after the fused reductions of the Arnoldi step in
+// between, to which this rank contributes after it has read exchange seq.
 __global__ void __launch_bounds__(1024)
 halo_xchg_kernel(double* vecA, double* vecB, int64_t hoff, int64_t n_halo, const int32_t* __restrict__ idx,
                  const int32_t* __restrict__ dest_rank, const int32_t* __restrict__ dest_off, int64_t n_send,
-                 const int32_t* __restrict__ send_to, const int32_t* __restrict__ recv_from,
                  const __grid_constant__ XView xv, unsigned long long seq) {
   const int phase = (int)(seq & 1ull);
+  const unsigned flag = (unsigned)seq;
   const size_t hb = xv.halo_off(phase);
-  const size_t half = (size_t)(xv.halo_cap / 2);
+  const size_t half = (size_t)(xv.halo_cap / 2);              // doubles: second vector's slots
   for (int64_t i = threadIdx.x; i < n_send; i += blockDim.x) {
-    double* dst = xv.base[dest_rank[i]] + hb + dest_off[i];
-    dst[0] = vecA[idx[i]];
-    if (vecB) dst[half] = vecB[idx[i]];
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(xv.base[dest_rank[i]] + hb) + 2 * (size_t)dest_off[i];
+    st_ll(dst, vecA[idx[i]], flag);
+    if (vecB) st_ll(dst + half, vecB[idx[i]], flag);
   }
-  __threadfence_system();
-  __syncthreads();
-  if ((int)threadIdx.x < xv.world) {
-    if (send_to[threadIdx.x]) st_release_sys(xv.halo_flag(threadIdx.x, phase, xv.rank), seq);
-    const long long t0 = clock64();
-    if (recv_from[threadIdx.x]) wait_flag(xv.halo_flag(xv.rank, phase, threadIdx.x), seq, xv.err_word(xv.rank));
-    atomicMax(xv.stat_word(xv.rank, 6), (unsigned long long)(clock64() - t0));
+  const unsigned long long* src = reinterpret_cast<const unsigned long long*>(xv.base[xv.rank] + hb);
+  unsigned long long waited = 0ull;
+  for (int64_t i = threadIdx.x; i < n_halo; i += blockDim.x) {
+    for (int w = 0; w < (vecB ? 2 : 1); ++w) {
+      const unsigned long long* at = src + (w ? half : 0) + 2 * (size_t)i;
+      double v = 0.0;
+      if (!ld_ll(at, flag, &v)) {
+        const long long t0 = clock64();
+        while (!ld_ll(at, flag, &v)) {
+          if (clock64() - t0 > 40000000000ll) { *xv.err_word(xv.rank) = seq | (1ull << 63); v = 0.0; break; }
+        }
+        waited += (unsigned long long)(clock64() - t0);
+      }
+      (w ? vecB : vecA)[hoff + i] = v;
+    }
   }
+  if (waited) atomicMax(xv.stat_word(xv.rank, 6), waited);
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned long long* st = xv.stat_word(xv.rank, 0);
     st[3] += st[6]; st[6] = 0ull; st[4] += 1ull;
-  }
-  const double* src = xv.base[xv.rank] + hb;
-  for (int64_t i = threadIdx.x; i < n_halo; i += blockDim.x) {
-    vecA[hoff + i] = ld_volatile(src + i);
-    if (vecB) vecB[hoff + i] = ld_volatile(src + half + i);
   }
 }
 

@@ -349,11 +349,14 @@ class KrylovContext:
         self._check(self._lib.spis_get_profile(self._h, nat.dptr(ms), nat.dptr(by), ln.ctypes.data_as(C.POINTER(C.c_int64))))
         mv = np.zeros(nat.PROF_CLASSES)
         self._check(self._lib.spis_get_profile_moved(self._h, nat.dptr(mv)))
+        gp = np.zeros(nat.PROF_CLASSES)
+        self._check(self._lib.spis_get_profile_gaps(self._h, nat.dptr(gp)))
         out = {}
         for i, name in enumerate(nat.PROF_NAMES):
             out[name] = {"ms": float(ms[i]), "bytes": float(by[i]), "launches": int(ln[i]),
                          "gbs": float(by[i] / ms[i] * 1e-6) if ms[i] > 0 else None,
-                         "moved_bytes": float(mv[i]), "gbs_moved": float(mv[i] / ms[i] * 1e-6) if ms[i] > 0 else None}
+                         "moved_bytes": float(mv[i]), "gbs_moved": float(mv[i] / ms[i] * 1e-6) if ms[i] > 0 else None,
+                         "idle_before_ms": float(gp[i])}
         return out
 
     def timer_start(self):
