@@ -213,6 +213,8 @@ int spis_constraint_define(spis_ctx* ctx, int c, int mat_slot, const double* v, 
 int spis_constraint_terms(spis_ctx* ctx, int c, int m, double* term0, double* term1, double* term2);
 /* replaces the scalar of a defined constraint (time loops: same M and v, new invariant values per step) */
 int spis_constraint_set_constant(spis_ctx* ctx, int c, double cc);
+/* replaces the linear term v of a defined constraint (NULL: no linear term); the matrix stays where it is */
+int spis_constraint_set_vector(spis_ctx* ctx, int c, const double* v);
 /* Class-form constraint c staged by a native helper thread on the auxiliary stream while the caller runs the
  * Krylov loop: zero test of M's values (-> mat_slot < 0), spis_upload_csr into slot SPIS_SLOT_CON0 + c,
  * spis_constraint_define.  Exception to the pointer rule above: the host arrays must stay valid until

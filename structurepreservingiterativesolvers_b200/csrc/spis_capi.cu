@@ -2081,6 +2081,25 @@ int spis_constraint_set_constant(spis_ctx* ctx, int c, double cc) {
   return SPIS_OK;
 }
 
+// New linear term v of a defined constraint (same matrix, same slot): lkdvRK's structured constraints depend on the
+// step's initial state through v and c (wrappers/lkdvRK.py, conlist_structured), the matrix B'SB does not.
+// v == NULL drops the linear term.
+int spis_constraint_set_vector(spis_ctx* ctx, int c, const double* v) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(c >= 0 && c < SPIS_MAX_SLOTS && ctx->cons[c].defined, "constraint %d is not defined", c);
+  CU(cudaSetDevice(ctx->device));
+  Constraint& C = ctx->cons[c];
+  if (v) {
+    if (!C.v) TRY(dalloc(ctx, &C.v, (size_t)ctx->ld));
+    TRY(h2d(ctx, C.v, v, (size_t)ctx->n * sizeof(double)));
+  } else if (C.v) {
+    dfree(ctx, C.v);
+  }
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  C.cols_done = 0; C.term0_done = false;
+  return SPIS_OK;
+}
+
 // The whole staging of one class-form constraint -- is M identically zero (`0*A`, lkdv/LinearSolver.py:30)?
 // upload + conversion of M, zero test and upload of v -- on a NATIVE helper thread and the context's auxiliary
 // stream, so that the caller's thread can drive the Krylov loop meanwhile.  (Python helper threads did this

@@ -222,6 +222,14 @@ class KrylovContext:
         self._live()
         self._check(self._lib.spis_constraint_set_constant(self._h, c, float(cc)))
 
+    def constraint_set_vector(self, c: int, v):
+        self._live()
+        if v is None:
+            self._check(self._lib.spis_constraint_set_vector(self._h, c, None))
+        else:
+            v = nat.as_f64(v, self.n)
+            self._check(self._lib.spis_constraint_set_vector(self._h, c, nat.dptr(v)))
+
     def constraint_setup_async(self, c: int, M, v, cc: float, m_is_zero=None, v_is_zero=None):
         """Stage class-form constraint c (sparse M, vector v, scalar cc) on a native helper thread; the arrays
         handed to the library are kept alive here until constraint_setup_wait().  m_is_zero / v_is_zero: answers a

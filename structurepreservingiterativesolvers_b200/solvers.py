@@ -271,11 +271,11 @@ class DeviceSession:
                 self._setup_constraint(idx, const)
             tr("constraints")
 
-    def update(self, b=None, x0=None, constants=None):
+    def update(self, b=None, x0=None, constants=None, vectors=None):
         """Next system of a time loop over a FIXED operator (lkdv/Evolve.py:39-56 re-assembles every step, but
         only b, x0 and the invariant values change): new right-hand side / initial guess / constraint scalars
-        `c` (one per class-form constraint, None = keep); A, the constraint matrices and vectors and the Krylov
-        workspace stay where they are."""
+        `c` and linear terms `v` (one per class-form constraint, None = keep); A, the constraint matrices and the
+        Krylov workspace stay where they are."""
         self._join_setup()
         ctx = self.ctx
         if b is not None:
@@ -295,6 +295,17 @@ class DeviceSession:
                 if entry["kind"] != "class" or entry["error"] is not None:
                     raise ValueError(f"constraint {idx} is not a class-form constraint held on the device")
                 ctx.constraint_set_constant(idx, float(cc))
+        if vectors is not None:
+            vectors = list(vectors)
+            if len(vectors) != len(self._cons):
+                raise ValueError(f"{len(vectors)} vectors for {len(self._cons)} constraints")
+            for idx, (entry, vv) in enumerate(zip(self._cons, vectors)):
+                if vv is None:
+                    continue
+                if entry["kind"] != "class" or entry["error"] is not None:
+                    raise ValueError(f"constraint {idx} is not a class-form constraint held on the device")
+                vv = nat.as_f64(vv, self.n)
+                ctx.constraint_set_vector(idx, vv if self._any_rank(nat.any_nonzero(vv)) else None)
 
     def _any_rank(self, flag, key=None):
         """Logical OR of a host-side decision over all ranks (identity on one GPU).  Every decision

@@ -6,4 +6,4 @@ B200 solvers in ``..solvers``.  ``conlist(...)`` returns just the constraint lis
 hand identical constraints to the oracle.
 """
 from . import lkdv, swe, heat, lkdvRK  # noqa: F401
-from .evolve import evolve  # noqa: F401
+from .evolve import evolve, evolve_lkdvRK, evolve_swe  # noqa: F401

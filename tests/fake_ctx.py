@@ -315,6 +315,11 @@ class FakeKrylovContext:
                         "T1": np.zeros(self.k_max), "T2": np.zeros((self.k_max, self.k_max)),
                         "MZ": np.zeros((self.k_max, self.n))}
 
+    def constraint_set_vector(self, c, v):
+        self.cons[c]["v"] = None if v is None else np.array(v, dtype=float)
+        self.cons[c]["t0"] = None
+        self.cons[c]["done"] = 0
+
     def constraint_set_constant(self, c, cc):
         self.cons[c]["c"] = cc
         self.cons[c]["t0"] = None

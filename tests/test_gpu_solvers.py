@@ -699,3 +699,38 @@ def test_pinned_result_buffers_are_accounted():
         assert np.isfinite(x).all()
     finally:
         nat._PINNED_LIMIT = old
+
+
+def test_evolve_mirrors_of_swe_and_lkdvrk_on_the_device():
+    """The resident time loops of swe/Evolve.py:18-60 and lkdvRK/Evolve.py:19-93 (non-zero initial guess = the previous
+    stage vector, ILU through the host bridge) on the GPU, against the same loops driven by the oracle."""
+    import scipy.sparse.linalg as spsla
+    from structurepreservingiterativesolvers_b200.problems import lkdvRK
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = wrappers.evolve_swe(N=100, M=6, k=40, tol=1e-7, steps=4, small_solver="kkt")
+        fresh = wrappers.evolve_swe(N=100, M=6, k=40, tol=1e-7, steps=4, small_solver="kkt", resident=False)
+        forms, _ = swe.linforms(N=100, M=6)
+        sol = [forms["z0"].copy()]
+        for i in range(1, 5):
+            forms, _ = swe.linforms(N=100, M=6, zinit=sol[-1])
+            x0 = np.zeros_like(forms["b"])
+            z, _info = orc.cgmres(forms["A"], forms["b"], x0, 40, tol=1e-7, conlist=wrappers.swe.conlist(forms, x0))
+            sol.append(np.array(z))
+        for i, (a, b, c) in enumerate(zip(out["sol"], sol, fresh["sol"])):
+            assert helpers.rel_diff(a, b) <= 1e-10 * max(i, 1), i
+            assert helpers.rel_diff(a, c) <= 1e-12 * max(i, 1), i                  # resident or re-uploaded
+        forms, prob = lkdvRK.linforms(N=10, M=20, T=1)
+        ref = [forms["z0"].copy()]
+        z = np.tile(forms["z0"], prob.ns)
+        P = spsla.spilu(forms["A"].tocsc(), drop_tol=1e-4, fill_factor=10)
+        for i in range(1, 5):
+            forms, _ = lkdvRK.linforms(N=10, M=20, T=1, zinit=ref[-1])
+            z, _info = orc.cgmres(forms["A"], forms["b"], z, 30, tol=1e-6, contol=10, conlist=wrappers.lkdvRK.conlist(forms, z, prob), pre=P)
+            z = np.array(z)
+            ref.append(lkdvRK.z1calc(prob, z, ref[-1]))
+        for structured, pre in ((True, "ilu"), (False, "ilu"), (True, "block")):
+            o2 = wrappers.evolve_lkdvRK(N=10, M=20, k=30, tol=1e-6, steps=4, structured=structured, pre=pre, small_solver="kkt")
+            for i, (a, b) in enumerate(zip(o2["sol"], ref)):
+                assert helpers.rel_diff(a, b) <= 1e-9 * max(i, 1), (structured, pre, i)
+            assert max(o2["dm"].max(), o2["dmo"].max(), o2["de"].max()) <= 1e-12 * abs(ref[0]).sum()

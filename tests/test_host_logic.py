@@ -471,3 +471,52 @@ def test_pipelined_loop_invalid_record_falls_back_to_the_host():
     assert host_formed[0] == 2 and len(host_formed) == inf["steps"] - 1
     assert not any(e[0] == "step" and e[4] is not None and e[4] >= 2 for e in logf)
     assert not any(e[0] == "step" and e[3] and e[1] > 2 + solvers._Pipeline.DEPTH for e in logf)       # and the host stops asking (steps queued ahead excepted)
+
+
+def _oracle_loop_swe(N, M, k, tol, steps):
+    from oracle import cgmres_oracle as orc
+    from structurepreservingiterativesolvers_b200.problems import swe
+    forms, _ = swe.linforms(N=N, M=M)
+    sol = [forms["z0"].copy()]
+    for i in range(1, steps + 1):
+        forms, _ = swe.linforms(N=N, M=M, zinit=sol[-1])                       # swe/Evolve.py:39
+        x0 = np.zeros_like(forms["b"])
+        z, _info = orc.cgmres(forms["A"], forms["b"], x0, k, tol=tol, conlist=wrappers.swe.conlist(forms, x0))
+        sol.append(np.array(z))
+    return sol
+
+
+def _oracle_loop_lkdvrk(N, M, k, tol, steps):
+    import scipy.sparse.linalg as spsla
+    from oracle import cgmres_oracle as orc
+    from structurepreservingiterativesolvers_b200.problems import lkdvRK
+    forms, prob = lkdvRK.linforms(N=N, M=M, T=1)
+    sol = [forms["z0"].copy()]
+    z = np.tile(forms["z0"], prob.ns)                                          # lkdvRK/Evolve.py:37
+    P = spsla.spilu(forms["A"].tocsc(), drop_tol=1e-4, fill_factor=10)         # lkdvRK/Evolve.py:51-52
+    for i in range(1, steps + 1):
+        forms, _ = lkdvRK.linforms(N=N, M=M, T=1, zinit=sol[-1])
+        z, _info = orc.cgmres(forms["A"], forms["b"], z, k, tol=tol, contol=10, conlist=wrappers.lkdvRK.conlist(forms, z, prob), pre=P)
+        z = np.array(z)
+        sol.append(lkdvRK.z1calc(prob, z, sol[-1]))
+    return sol
+
+
+def test_evolve_mirrors_of_swe_and_lkdvrk_follow_the_oracle_loops():
+    """wrappers.evolve_swe (swe/Evolve.py:18-60) and wrappers.evolve_lkdvRK (lkdvRK/Evolve.py:19-93: previous stage vector
+    as the initial guess, one ILU factorisation for all steps, z <- z1calc) with the session resident across the steps,
+    against the same loops driven by the oracle."""
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = wrappers.evolve_swe(N=100, M=6, k=40, tol=1e-7, steps=4, ctx_factory=FakeKrylovContext, small_solver="kkt")
+        ref = _oracle_loop_swe(100, 6, 40, 1e-7, 4)
+        for i, (a, b) in enumerate(zip(out["sol"], ref)):
+            assert helpers.rel_diff(a, b) <= 1e-10 * max(i, 1), i
+        assert max(out["dm"].max(), out["de"].max()) <= 1e-12 * (abs(ref[0]).sum())
+        ref = _oracle_loop_lkdvrk(10, 20, 30, 1e-6, 4)
+        for structured in (True, False):
+            out = wrappers.evolve_lkdvRK(N=10, M=20, k=30, tol=1e-6, steps=4, structured=structured,
+                                         ctx_factory=FakeKrylovContext, small_solver="kkt")
+            for i, (a, b) in enumerate(zip(out["sol"], ref)):
+                assert helpers.rel_diff(a, b) <= 1e-10 * max(i, 1), (structured, i)
+            assert max(out["dm"].max(), out["dmo"].max(), out["de"].max()) <= 1e-12 * abs(ref[0]).sum()
