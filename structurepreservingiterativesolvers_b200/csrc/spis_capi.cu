@@ -42,6 +42,8 @@ struct Matrix {
   // row-pattern storage (SPIS_FMT_PATTERN)
   uint16_t* pid = nullptr; int32_t* tab_len = nullptr; int32_t* tab_off = nullptr; double* tab_val = nullptr;
   int npat = 0, patW = 0;
+  // field-window twin of the row-pattern storage (spmv_fw_kernel): F fields of N nodes, node shifts |d| <= D
+  FwEntry* fw_tab = nullptr; int fwF = 0, fwN = 0, fwD = 0;
   // dictionary-coded values (SPIS_FMT_SELLD): scols as in SELL, one code per entry, table of <= 256 doubles
   uint32_t* codes = nullptr; int64_t* code_off = nullptr; double* dict = nullptr; int ndict = 0;
 };
@@ -113,6 +115,12 @@ struct spis_ctx {
   int spmv_multi = 1;           // constraint stage: M z_j for a group of 2 / 4 Krylov columns from one pass over M
   int spmv_dual = 1;            // A q_{j+2} and ||A x_j - b|| from one pass over A (spis_arnoldi_begin_residual)
   int spmv_dual_ctas_per_sm = 0;
+  int spmv_fw = 1;              // row patterns on field-blocked systems, x windows staged in shared memory by TMA (spmv_fw_kernel).
+                                // Bit mask: 1 = the dual product of an Arnoldi step, 2 = single products, 4 = grouped constraint products.
+                                // Measured on the 1e7 lkdv operator (tools/tune_fw.py): dual 97 us against 109 us for the L1-gather kernel
+                                // (each x entry travels from HBM once instead of once per field block), single products 65 / 80 / 70 us
+                                // against 63 / 79 / 65 us, four columns per pass slower (the shared-memory data pipe, which every
+                                // gather crosses as an LDS, is as busy as the L1 pipe was) -- so only the dual product takes it by default.
   int mdot_variant = 0, lincomb_variant = 4;   // mdot 0 = auto (tools/tune.py sweep, profiles/tune_r1.md)
   int x0_is_zero = 0;
   int fuse_jacobi = 1;
@@ -569,6 +577,50 @@ double matrix_bytes(const Matrix& M) {
   }
 }
 
+// Field-window SpMV (spmv_fw_kernel).  Tile width T and window stride WS from the shared-memory budget; *grid_out CTAs
+// each leave one partial sum (KIND != 0).  Returns false when the matrix has no field-window table or nothing fits.
+constexpr size_t kFwSmemBudget = 110 * 1024;       // two CTAs per SM
+bool fw_plan(const spis_ctx* ctx, const Matrix& M, int NV, int* T_out, int* WS_out, size_t* smem_out, int use = 7) {
+  if (!M.fw_tab || !(ctx->spmv_fw & use) || M.fmt != SPIS_FMT_PATTERN || M.patW > 16 || M.fwF * M.npat > kFwMaxTable / 4) return false;
+  for (int T = 8 * kFwThreads; T >= kFwThreads; T /= 2) {
+    if (M.fwF * (T / kFwThreads) > kFwRows) continue;
+    const int WS = (T + 2 * M.fwD + 2 + 7) / 8 * 8;
+    const size_t smem = fw_smem_bytes(NV, M.npat, M.patW, M.fwF, WS);
+    if (smem > kFwSmemBudget) continue;
+    *T_out = T; *WS_out = WS; *smem_out = smem;
+    return true;
+  }
+  return false;
+}
+
+template <int NV, int KIND>
+int launch_fw(spis_ctx* ctx, const Matrix& M, const FwVecs& vv, const double* b, double* partial, int* grid_out) {
+  int T = 0, WS = 0; size_t smem = 0;
+  if (!fw_plan(ctx, M, NV, &T, &WS, &smem)) return fail(ctx, SPIS_E_UNSUPPORTED, "field-window SpMV does not apply");   // (callers checked their bit)
+  FwArgs P;
+  P.pid = M.pid; P.tab_len = M.tab_len; P.tab = M.fw_tab;
+  P.npat = M.npat; P.W = M.patW; P.F = M.fwF; P.N = M.fwN; P.D = M.fwD; P.T = T; P.WS = WS; P.ld = ctx->ld;
+  const int ntiles = (M.fwN + T - 1) / T;
+  const int grid = ntiles < 2 * ctx->nsm ? ntiles : 2 * ctx->nsm;
+  static bool attr_done = false;     // per template instance
+  if (!attr_done) {
+    CU(cudaFuncSetAttribute(spmv_fw_kernel<NV, KIND, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwSmemBudget));
+    CU(cudaFuncSetAttribute(spmv_fw_kernel<NV, KIND, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwSmemBudget));
+    CU(cudaFuncSetAttribute(spmv_fw_kernel<NV, KIND, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwSmemBudget));
+    CU(cudaFuncSetAttribute(spmv_fw_kernel<NV, KIND, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwSmemBudget));
+    attr_done = true;
+  }
+  switch (M.patW / 4) {
+    case 1: spmv_fw_kernel<NV, KIND, 1><<<grid, kFwThreads, smem, ctx->stream>>>(P, vv, b, partial); break;
+    case 2: spmv_fw_kernel<NV, KIND, 2><<<grid, kFwThreads, smem, ctx->stream>>>(P, vv, b, partial); break;
+    case 3: spmv_fw_kernel<NV, KIND, 3><<<grid, kFwThreads, smem, ctx->stream>>>(P, vv, b, partial); break;
+    default: spmv_fw_kernel<NV, KIND, 4><<<grid, kFwThreads, smem, ctx->stream>>>(P, vv, b, partial); break;
+  }
+  CU(cudaGetLastError());
+  if (grid_out) *grid_out = grid;
+  return SPIS_OK;
+}
+
 template <int MODE>
 int launch_spmv_mode(spis_ctx* ctx, const Matrix& M, const double* x, const double* b, double* y, double* sumsq_out) {
   const XView xv = MODE != 0 ? fused_view(ctx) : XView();
@@ -588,6 +640,12 @@ int launch_spmv_mode(spis_ctx* ctx, const Matrix& M, const double* x, const doub
     const int64_t nslices = (M.nrows + 31) / 32;
     const int grid = grid_for(ctx, (nslices + kWarps - 1) / kWarps, (MODE != 0 && ctx->spmv_ctas_per_sm > 6) ? 6 : ctx->spmv_ctas_per_sm);
     spmv_selld_kernel<MODE><<<grid, kThreads, 0, ctx->stream>>>(M.slice_off, M.rowperm, M.code_off, M.scols, M.codes, M.dict, M.nrows, x, b, y, ctx->d_partial);
+    if (MODE != 0) reduce_partials_kernel<<<1, kThreads, 0, ctx->stream>>>(ctx->d_partial, grid, sumsq_out, xv, seq);
+  } else if (int T_ = 0, WS_ = 0; M.fmt == SPIS_FMT_PATTERN && [&] { size_t sm_ = 0; return fw_plan(ctx, M, 1, &T_, &WS_, &sm_, 2); }()) {
+    // field-blocked system: x windows staged in shared memory, every field block of a node range by one CTA
+    FwVecs vv{}; vv.x[0] = x; vv.y[0] = y;
+    int grid = 1;
+    TRY((launch_fw<1, MODE>(ctx, M, vv, b, ctx->d_partial, &grid)));
     if (MODE != 0) reduce_partials_kernel<<<1, kThreads, 0, ctx->stream>>>(ctx->d_partial, grid, sumsq_out, xv, seq);
   } else if (M.fmt == SPIS_FMT_PATTERN) {
     // variant 0: first-generation kernel; 1+: the id of the next round's row is prefetched
@@ -651,7 +709,11 @@ int launch_spmv_dual(spis_ctx* ctx, const double* x1, double* y1, const double* 
   const double moved = matrix_bytes(M) + 32.0 * (double)M.nrows;      // the matrix once, x1, x2 and b read, y1 written
   TRY(prof_begin(ctx, SPIS_PROF_SPMV, bytes, moved));
   int grid = 1;
-  if (M.fmt == SPIS_FMT_PATTERN) {
+  int fwT = 0, fwWS = 0; size_t fwsm = 0;
+  if (fw_plan(ctx, M, 2, &fwT, &fwWS, &fwsm, 1)) {
+    FwVecs vv{}; vv.x[0] = x1; vv.x[1] = x2; vv.y[0] = y1;
+    TRY((launch_fw<2, 3>(ctx, M, vv, b, part, &grid)));
+  } else if (M.fmt == SPIS_FMT_PATTERN) {
     grid = grid_for(ctx, (M.nrows + kThreads - 1) / kThreads, ctx->spmv_dual_ctas_per_sm > 0 ? ctx->spmv_dual_ctas_per_sm : 6);
     while (grid > 1 && (int64_t)M.nrows + (int64_t)grid * kThreads >= (int64_t)INT32_MAX) grid /= 2;
 #define SPIS_PATD_CASE(NC) case NC: spmv_pattern_dual_kernel<NC><<<grid, kThreads, 0, ctx->stream>>>(M.pid, M.patW, M.tab_off, M.tab_val, (int)M.nrows, x1, y1, x2, b, part); break;
@@ -692,7 +754,13 @@ int launch_spmv_multi(spis_ctx* ctx, int slot, int nv, const double* x, int64_t 
   const double bytes = (double)nv * (12.0 * (double)M.nnz + 4.0 * (double)(M.nrows + 1) + 16.0 * (double)M.nrows);   // nv SpMVs' worth
   const double moved = matrix_bytes(M) + (double)nv * 16.0 * (double)M.nrows;
   TRY(prof_begin(ctx, slot == SPIS_SLOT_A ? SPIS_PROF_SPMV : SPIS_PROF_SPMV_AUX, bytes, moved));
-  if (M.fmt == SPIS_FMT_PATTERN) {
+  int fwT = 0, fwWS = 0; size_t fwsm = 0;
+  if (fw_plan(ctx, M, nv, &fwT, &fwWS, &fwsm, 4)) {
+    FwVecs vv{};
+    for (int c = 0; c < nv; ++c) { vv.x[c] = x + (size_t)c * xstride; vv.y[c] = y + (size_t)c * ystride; }
+    if (nv == 2) TRY((launch_fw<2, 0>(ctx, M, vv, nullptr, nullptr, nullptr)));
+    else TRY((launch_fw<4, 0>(ctx, M, vv, nullptr, nullptr, nullptr)));
+  } else if (M.fmt == SPIS_FMT_PATTERN) {
     int grid = grid_for(ctx, (M.nrows + kThreads - 1) / kThreads, nv == 2 ? 6 : 4);
     while (grid > 1 && (int64_t)M.nrows + (int64_t)grid * kThreads >= (int64_t)INT32_MAX) grid /= 2;
 #define SPIS_PATM(NC, NVV) spmv_pattern_multi_kernel<NC, NVV><<<grid, kThreads, 0, ctx->stream>>>(M.pid, M.patW, M.tab_off, M.tab_val, (int)M.nrows, x, xstride, y, ystride)
@@ -760,7 +828,7 @@ int launch_precond(spis_ctx* ctx, const double* q, double* z) {
 }
 
 void free_matrix(spis_ctx* ctx, Matrix& M) {
-  dfree(ctx, M.indptr); dfree(ctx, M.cols); dfree(ctx, M.vals);
+  dfree(ctx, M.indptr); dfree(ctx, M.cols); dfree(ctx, M.vals); dfree(ctx, M.fw_tab);
   dfree(ctx, M.slice_off); dfree(ctx, M.scols); dfree(ctx, M.svals); dfree(ctx, M.rowperm);
   dfree(ctx, M.pid); dfree(ctx, M.tab_len); dfree(ctx, M.tab_off); dfree(ctx, M.tab_val);
   dfree(ctx, M.codes); dfree(ctx, M.code_off); dfree(ctx, M.dict);
@@ -1304,6 +1372,7 @@ int spis_set_option(spis_ctx* ctx, const char* key, int64_t value) {
   else if (k == "sell_sigma") { ctx->sell_sigma = value ? 1 : 0; }
   else if (k == "spmv_multi") { ctx->spmv_multi = value ? 1 : 0; }
   else if (k == "spmv_dual") { ctx->spmv_dual = value ? 1 : 0; }
+  else if (k == "spmv_fw") { REQUIRE(value >= 0 && value <= 7, "spmv_fw is a bit mask 0..7"); ctx->spmv_fw = (int)value; }
   else if (k == "spmv_dual_ctas_per_sm") { REQUIRE(value >= 0 && value <= 16, "spmv_dual_ctas_per_sm must be 0..16"); ctx->spmv_dual_ctas_per_sm = (int)value; }
   else if (k == "mdot_variant") { REQUIRE(value == 0 || value == 1 || value == 2 || value == 4 || value == 8, "mdot_variant must be 0 (auto), 1 (register sums), 2, 4 or 8"); ctx->mdot_variant = (int)value; }
   else if (k == "mdot_reg_auto") { ctx->mdot_reg_auto = value ? 1 : 0; }
@@ -1342,6 +1411,11 @@ int spis_get_info(const spis_ctx* cctx, const char* key, int64_t* value_out) {
     const int slot = atoi(k.c_str() + 6);
     REQUIRE(slot >= 0 && slot < SPIS_MAX_SLOTS && ctx->mats[slot].present, "slot %d not uploaded", slot);
     *value_out = ctx->mats[slot].ndict;
+  }
+  else if (k.rfind("fw_fields:", 0) == 0) {
+    const int slot = atoi(k.c_str() + 10);
+    REQUIRE(slot >= 0 && slot < SPIS_MAX_SLOTS && ctx->mats[slot].present, "slot %d not uploaded", slot);
+    *value_out = (ctx->mats[slot].fw_tab && ctx->spmv_fw) ? ctx->mats[slot].fwF : 0;
   }
   else if (k.rfind("npat:", 0) == 0) {
     const int slot = atoi(k.c_str() + 5);
@@ -1457,6 +1531,69 @@ static int try_pattern_storage(spis_ctx* ctx, Matrix& M, cudaStream_t s, int* ok
   return SPIS_OK;
 }
 
+// Row-pattern matrix on the device -> field-window table for spmv_fw_kernel, if the unknowns are F fields of N nodes
+// (n = F N) and (nearly) every stencil offset is q N + d with a small node shift d: the reference's field-blocked
+// systems [u; v; w] (lkdv/refd.py:17), the stage-block systems of lkdvRK, and any banded single-field matrix (F = 1).
+static int try_field_windows(spis_ctx* ctx, Matrix& M, cudaStream_t s) {
+  if (!ctx->spmv_fw || M.npat < 1 || M.npat > kFwMaxPat || M.npat * M.patW > kFwMaxTable || M.nrows < 32) return SPIS_OK;
+  const int npat = M.npat, W = M.patW;
+  std::vector<int32_t> len(npat), off((size_t)npat * W);
+  std::vector<double> val((size_t)npat * W);
+  std::vector<unsigned long long> cnt(npat, 0ull);
+  unsigned long long* d_hist = nullptr;
+  TRY(dalloc(ctx, &d_hist, (size_t)npat));
+  pid_hist_kernel<<<ctx->nsm * 4, 256, 0, s>>>(M.pid, M.nrows, npat, d_hist);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(cnt.data(), d_hist, (size_t)npat * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(len.data(), M.tab_len, (size_t)npat * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(off.data(), M.tab_off, off.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(val.data(), M.tab_val, val.size() * sizeof(double), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  dfree(ctx, d_hist);
+  if (e != cudaSuccess) return fail(ctx, SPIS_E_CUDA, "field-window analysis failed: %s", cudaGetErrorString(e));
+  constexpr int kDmax = 64;
+  const long long n = M.nrows;
+  int bestF = 0, bestD = 0;
+  for (int F = 1; F <= 8 && !bestF; ++F) {
+    if (n % F) continue;
+    const long long N = n / F;
+    if (N < 8) break;
+    unsigned long long covered = 0;
+    int Dm = 0;
+    for (int p = 0; p < npat; ++p) {
+      bool regular = true;
+      int dm = 0;
+      for (int k = 0; k < len[p] && regular; ++k) {
+        const long long o = off[(size_t)p * W + k];
+        const long long q = (o >= 0 ? o + N / 2 : o - N / 2) / N;
+        const long long d = o - q * N;
+        if (d < -kDmax || d > kDmax || q < -63 || q > 63) regular = false;
+        else dm = std::max<int>(dm, (int)std::llabs(d));
+      }
+      if (regular) { covered += cnt[p]; Dm = std::max(Dm, dm); }
+    }
+    if ((double)covered >= 0.98 * (double)n) { bestF = F; bestD = Dm; }
+  }
+  if (!bestF) return SPIS_OK;
+  const long long N = n / bestF;
+  const int D = std::max(2, (bestD + 1) / 2 * 2);
+  std::vector<FwEntry> tab((size_t)npat * W);
+  for (int p = 0; p < npat; ++p)
+    for (int k = 0; k < W; ++k) {
+      FwEntry t; t.val = k < len[p] ? val[(size_t)p * W + k] : 0.0;
+      const long long o = k < len[p] ? off[(size_t)p * W + k] : 0;
+      const long long q = (o >= 0 ? o + N / 2 : o - N / 2) / N;
+      const long long d = o - q * N;
+      if (d >= -D && d <= D && q >= -63 && q <= 63) { t.reg = (int)(2 * (q + 64) + 1); t.soff = (int)(d + D); }
+      else { t.reg = 0; t.soff = (int)o; }
+      tab[(size_t)p * W + k] = t;
+    }
+  TRY(dalloc(ctx, &M.fw_tab, tab.size(), false));
+  TRY(h2d(ctx, M.fw_tab, tab.data(), tab.size() * sizeof(FwEntry)));
+  M.fwF = bestF; M.fwN = (int)N; M.fwD = D;
+  return SPIS_OK;
+}
+
 int spis_upload_csr(spis_ctx* ctx, int slot, int64_t nrows, int64_t ncols, int64_t nnz,
                     const int32_t* indptr, const int32_t* indices, const double* data) {
   if (!ctx) return SPIS_E_INVALID;
@@ -1487,6 +1624,7 @@ int spis_upload_csr(spis_ctx* ctx, int slot, int64_t nrows, int64_t ncols, int64
       dfree(ctx, M.indptr); dfree(ctx, M.cols); dfree(ctx, M.vals);
       M.fmt = SPIS_FMT_PATTERN;
       M.nnz_padded = nnz;
+      TRY(try_field_windows(ctx, M, s));
       M.present = true;
       return SPIS_OK;
     }

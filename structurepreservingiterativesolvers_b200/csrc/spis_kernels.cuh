@@ -1976,6 +1976,261 @@ spmv_sell_dual_kernel(const int64_t* __restrict__ slice_off, const uint8_t* __re
 }
 
 // ------------------------------------------------------------------------------------------
+// K1, row patterns on FIELD-BLOCKED systems with x staged through shared memory ("FW": field windows).
+// north_star (a): "vectorised coalesced loads ... with x staged through shared memory".  The row-pattern kernels above
+// gather x through L1 and are bound by the L1 data pipe (profiles/ncu_spmv_r1.md: 47-65 wavefronts per warp and row),
+// and -- worse -- a field-blocked system [u; v; w] (lkdv/refd.py:17) makes every x entry travel from HBM once per FIELD
+// BLOCK that couples to it: the rows of u, v and w that read x[node i of field g] are n/3 rows apart, far beyond L2.
+// Here the unknowns are seen as F fields of N nodes (n = F N, detected from the stencil offsets: every offset is
+// q N + d with a small node shift |d| <= D).  One CTA takes a NODE range [a0, a0 + T) and computes the rows of ALL F
+// fields over it: the x windows  g N + [a0 - D, a0 + T + D),  g = -1 .. F  (the two extra ones catch the periodic
+// wrap-around), are brought into shared memory ONCE by the TMA engine (cp.async.bulk, double-buffered against the
+// arithmetic) and every gather becomes an LDS: two wavefronts per 32 rows and entry, no tag look-ups.  HBM then moves
+// what the algorithm needs -- 2 (stencil id) + 8 (y) + 8 per input vector (+ 8 for b) bytes per row -- instead of F times
+// the x traffic.  Entries that do not fit the scheme (ghost columns of a row-sharded strip, |d| > D) are gathered from
+// global memory one by one, so correctness never depends on the detection.
+// Per-row summation order is that of the row-pattern kernels (even / odd positions into two accumulators): same bits.
+// ------------------------------------------------------------------------------------------
+constexpr int kFwThreads = 256;
+constexpr int kFwRows = 8;                 // rows per thread and tile: F * T / kFwThreads <= kFwRows
+constexpr int kFwMaxTable = 1024;          // stencil table entries kept in shared memory
+constexpr int kFwMaxPat = 256;
+
+struct __align__(16) FwEntry { int soff; int reg; double val; };   // reg = 0: gather x[row + soff] from global memory;
+                                                                  // else reg = 2 (q + 64) + 1 and soff = d + D for the offset q N + d
+struct FwArgs {
+  const uint16_t* pid; const int32_t* tab_len; const FwEntry* tab;
+  int npat, W, F, N, D, T, WS;
+  int64_t ld;                              // length of the vector buffers (windows are clipped to [0, ld))
+};
+struct FwVecs { const double* x[4]; double* y[4]; };
+
+__host__ __device__ inline size_t fw_smem_bytes(int NV, int npat, int W, int F, int WS) {
+  return (size_t)(F + 1) * npat * W * sizeof(FwEntry) + (size_t)(kFwMaxPat + kFwMaxTable / 4) * sizeof(int) + 64 +
+         (size_t)2 * NV * (F + 2) * WS * sizeof(double);
+}
+
+// rows per stencil (upload-time analysis): hist[p] += #rows with id p, npat <= kFwMaxPat
+__global__ void pid_hist_kernel(const uint16_t* __restrict__ pid, int64_t nrows, int npat, unsigned long long* hist) {
+  __shared__ unsigned sh[kFwMaxPat];
+  for (int i = threadIdx.x; i < kFwMaxPat; i += blockDim.x) sh[i] = 0u;
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += stride) {
+    const int p = pid[r];
+    if (p < npat) atomicAdd(sh + p, 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < npat; i += blockDim.x)
+    if (sh[i]) atomicAdd(hist + i, (unsigned long long)sh[i]);
+}
+
+// One row whose stencil has an entry outside the staged windows (ghost column, |d| > D): entry by entry, windows
+// where they apply, global memory otherwise.  Rare (boundary rows of a row-sharded strip), kept out of line.
+template <int NV>
+__device__ __noinline__ void fw_row_generic(const FwEntry* te, int len, int f, int F, int N, int D, int WS, int nodd, int al,
+                                            int64_t row, const double* wst, int nwin, const FwVecs& Vv, double* ax) {
+  double acc0[NV], acc1[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) { acc0[v] = 0.0; acc1[v] = 0.0; }
+  for (int e = 0; e < len; ++e) {
+    const FwEntry t = te[e];
+    double xv[NV];
+    const int g = f + (t.reg >> 1) - 64;
+    if (t.reg && g >= -1 && g <= F) {
+      const int idx = (g + 1) * WS + t.soff + al + (nodd & g & 1);
+#pragma unroll
+      for (int v = 0; v < NV; ++v) xv[v] = wst[(size_t)v * nwin * WS + idx];
+    } else {
+      const long long off = t.reg ? (long long)((t.reg >> 1) - 64) * N + (t.soff - D) : (long long)t.soff;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) xv[v] = __ldg(Vv.x[v] + row + off);
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      if (e & 1) acc1[v] = fma(t.val, xv[v], acc1[v]);
+      else acc0[v] = fma(t.val, xv[v], acc0[v]);
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v) ax[v] = acc0[v] + acc1[v];
+}
+
+// KIND 0: y_v = A x_v for every v < NV;  1: y = b - A x, sumsq;  2: sumsq = ||A x - b||^2;
+// KIND 3 (NV = 2): y_0 = A x_0 and sumsq = ||A x_1 - b||^2  (the dual product of an Arnoldi step)
+// Two CTAs of 256 threads per SM, each double-buffering its own windows; the stencil ids and b of the NEXT tile are
+// fetched into registers while the current tile is computed, so no global-load latency sits between two tiles.
+// The stencil table is resolved ONCE per CTA into window coordinates per (field, stencil): rt[f][p][e] = {index of the
+// entry's x value in the staged windows relative to the row's node, value}, padded to NCH chunks of four entries with
+// zero values, so that a row is NCH * 4 x (LDS.128 of the entry, one LDS.64 per vector, one fma per vector), unrolled.
+template <int NV, int KIND, int NCH>
+__global__ void __launch_bounds__(kFwThreads, 2)
+spmv_fw_kernel(const __grid_constant__ FwArgs P, const __grid_constant__ FwVecs Vv, const double* __restrict__ b,
+               double* __restrict__ partial) {
+  extern __shared__ __align__(128) unsigned char fwraw[];
+  constexpr int W = NCH * 4;
+  const int F = P.F, N = P.N, D = P.D, T = P.T, WS = P.WS, npat = P.npat;
+  FwEntry* tab = reinterpret_cast<FwEntry*>(fwraw);                    // [npat][W] as uploaded (generic path)
+  FwEntry* rt = tab + npat * W;                                        // [F][npat][W] resolved: soff = window index, reg = 1: fast
+  int* s_len = reinterpret_cast<int*>(rt + F * npat * W);              // [npat]
+  int* s_fast = s_len + kFwMaxPat;                                     // [F][npat] (<= kFwMaxTable / 4 entries)
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_fast + kFwMaxTable / 4);
+  double* win = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(full) + 64);
+  __shared__ double sred[kFwThreads / 32];
+  const int tid = threadIdx.x;
+  const int nwin = F + 2;
+  const size_t stage_doubles = (size_t)NV * nwin * WS;
+  const int nodd = N & 1;
+  for (int i = tid; i < npat * W; i += kFwThreads) tab[i] = P.tab[i];
+  for (int i = tid; i < npat; i += kFwThreads) s_len[i] = P.tab_len[i];
+  if (tid == 0) {
+    mbar_init(full + 0, 1); mbar_init(full + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  for (int i = tid; i < F * npat; i += kFwThreads) {
+    const int f = i / npat, p = i - f * npat;
+    const int len = s_len[p];
+    int fast = 1, first = 0;
+    for (int e = 0; e < W; ++e) {
+      FwEntry t = tab[p * W + e], o;
+      const int g = f + (t.reg >> 1) - 64;
+      if (e < len) {
+        if (!(t.reg && g >= -1 && g <= F)) fast = 0;
+        o.soff = (g + 1) * WS + t.soff + (nodd & g & 1);
+        o.val = t.val;
+        if (e == 0) first = o.soff;
+      } else {
+        o.soff = first;                                                // padding: a location that is certainly loaded, times zero
+        o.val = 0.0;
+      }
+      o.reg = 1;
+      rt[(size_t)i * W + e] = o;
+    }
+    s_fast[i] = fast && len > 0;
+  }
+  __syncthreads();
+  const int ntiles = (N + T - 1) / T;
+  const int kts = __ffs(T / kFwThreads) - 1;          // T / kFwThreads is 1, 2, 4 or 8
+  const uint64_t pol = l2_policy_evict_first();
+
+  // the x windows of node range [a0, a0 + T) for every vector, one bulk copy each (clipped to the buffer)
+  auto issue = [&](int tile, int stage) {
+    const long long a0 = (long long)tile * T;
+    uint32_t total = 0;
+    for (int g = -1; g <= F; ++g) {
+      long long lo = (long long)g * N + a0 - D;
+      lo -= (lo & 1);
+      const long long clo = lo < 0 ? 0 : lo, chi = lo + WS > P.ld ? P.ld : lo + WS;
+      if (chi > clo) total += (uint32_t)((chi - clo) * sizeof(double)) * NV;
+    }
+    mbar_arrive_expect_tx(full + stage, total);
+    for (int v = 0; v < NV; ++v)
+      for (int g = -1; g <= F; ++g) {
+        long long lo = (long long)g * N + a0 - D;
+        lo -= (lo & 1);
+        const long long clo = lo < 0 ? 0 : lo, chi = lo + WS > P.ld ? P.ld : lo + WS;
+        if (chi > clo)
+          bulk_g2s(win + (size_t)stage * stage_doubles + ((size_t)v * nwin + (g + 1)) * WS + (clo - lo), Vv.x[v] + clo,
+                   (uint32_t)((chi - clo) * sizeof(double)), full + stage, pol);
+      }
+  };
+  // this thread's rows of a tile: slot r -> field f = r >> kts, node a0 + tid + (r & (KT - 1)) * kFwThreads
+  int pid_n[kFwRows];
+  double b_n[kFwRows];
+  auto fetch = [&](int tile) {
+    const int a0 = tile * T;
+#pragma unroll
+    for (int r = 0; r < kFwRows; ++r) {
+      const int f = r >> kts, kk = r - (f << kts);
+      const int a = a0 + tid + kk * kFwThreads;
+      const bool on = f < F && a < N && a < a0 + T;
+      const int64_t row = (int64_t)f * N + a;
+      pid_n[r] = on ? (int)__ldcs(P.pid + row) : -1;
+      b_n[r] = (on && KIND != 0) ? __ldg(b + row) : 0.0;
+    }
+  };
+
+  double ss = 0.0;
+  int k = 0;
+  if ((int)blockIdx.x < ntiles) {
+    if (tid == 0) issue(blockIdx.x, 0);
+    fetch(blockIdx.x);
+  }
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
+    const int stage = k & 1;
+    int pidv[kFwRows];
+    double bv[kFwRows];
+#pragma unroll
+    for (int r = 0; r < kFwRows; ++r) { pidv[r] = pid_n[r]; bv[r] = b_n[r]; }
+    if (tile + (int)gridDim.x < ntiles) {
+      if (tid == 0) issue(tile + gridDim.x, stage ^ 1);
+      fetch(tile + gridDim.x);                         // in flight while this tile is computed
+    }
+    const int a0 = tile * T;
+    mbar_wait(full + stage, (uint32_t)((k >> 1) & 1));
+    const double* wst = win + (size_t)stage * stage_doubles;
+#pragma unroll
+    for (int r = 0; r < kFwRows; ++r) {
+      const int p = pidv[r];
+      if (p < 0) continue;
+      const int f = r >> kts, kk = r - (f << kts);
+      const int al = tid + kk * kFwThreads;            // node - a0
+      const int64_t row = (int64_t)f * N + a0 + al;
+      double ax[NV];
+      if (s_fast[f * npat + p]) {
+        const FwEntry* te = rt + (size_t)(f * npat + p) * W;
+        const double* wr = wst + al;
+        double acc0[NV], acc1[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) { acc0[v] = 0.0; acc1[v] = 0.0; }
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const FwEntry t0 = te[4 * c], t1 = te[4 * c + 1], t2 = te[4 * c + 2], t3 = te[4 * c + 3];
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            const double* wv = wr + (size_t)v * nwin * WS;
+            const double x0 = wv[t0.soff], x1 = wv[t1.soff], x2 = wv[t2.soff], x3 = wv[t3.soff];
+            acc0[v] = fma(t0.val, x0, acc0[v]); acc1[v] = fma(t1.val, x1, acc1[v]);
+            acc0[v] = fma(t2.val, x2, acc0[v]); acc1[v] = fma(t3.val, x3, acc1[v]);
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v) ax[v] = acc0[v] + acc1[v];
+      } else {
+        fw_row_generic<NV>(tab + p * W, s_len[p], f, F, N, D, WS, nodd, al, row, wst, nwin, Vv, ax);
+      }
+      if (KIND == 0) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) Vv.y[v][row] = ax[v];
+      } else if (KIND == 1) {
+        const double rr = bv[r] - ax[0];
+        Vv.y[0][row] = rr;
+        ss = fma(rr, rr, ss);
+      } else if (KIND == 2) {
+        const double rr = ax[0] - bv[r];
+        ss = fma(rr, rr, ss);
+      } else {
+        Vv.y[0][row] = ax[0];
+        const double rr = ax[NV - 1] - bv[r];
+        ss = fma(rr, rr, ss);
+      }
+    }
+    __syncthreads();                                   // the stage may be refilled now
+  }
+  if (KIND == 0) return;
+  ss = warp_sum(ss);
+  if ((tid & 31) == 0) sred[tid >> 5] = ss;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int wv = 0; wv < kFwThreads / 32; ++wv) t += sred[wv];
+    partial[blockIdx.x] = t;                           // reduce_partials_kernel / the riding tail finishes
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // K6  y_c = M x_c for NV vectors at once (x_c = x + c*xstride, y_c = y + c*ystride): the constraint stage needs
 // M z_j for every Krylov column (solvers.py:33, `M @ Z`) and catches up four columns per group.  As in the dual
 // kernels everything per matrix entry is fetched once for the whole group; per row and vector the summation order

@@ -476,3 +476,94 @@ def test_sell_sigma_row_sorting(fmt):
             assert out[0][3] <= 0.95 * out[1][3] and out[0][3] >= A.nnz
         else:
             assert out[0][3] == out[1][3]
+
+
+# ---- round 2: row patterns with x staged through shared memory (spmv_fw_kernel) -----------------------------------------
+def _fw_matrices():
+    from structurepreservingiterativesolvers_b200.problems import heat, lkdvRK
+    out = [("lkdv P1, 3 fields", lkdv.linforms(space="CG", M=33_350, mlength=0.8 * 33_350)[0], 3),
+           ("lkdv P1, N odd", lkdv.linforms(space="CG", M=4_097, mlength=0.8 * 4_097)[0], 3),
+           ("lkdv DG1", lkdv.linforms(space="DG", M=1_500)[0], 3),
+           ("lkdvRK P1, 2 stages x 3 fields", lkdvRK.linforms(M=5_000, space="CG", mlength=4000.0)[0], 6),
+           ("heat P1 on a 30 x 30 grid", heat.linforms(M=29)[0], None)]          # boundary rows: too many stencils for the table, gather kernels
+    return out
+
+
+@pytest.mark.parametrize("case", range(5))
+def test_field_window_spmv_is_bit_identical_to_the_gather_kernels(case):
+    """spmv_fw_kernel (x windows of every field block staged in shared memory by TMA bulk copies, all field blocks of a
+    node range by one CTA) against the L1-gather row-pattern kernels: same per-row summation order, so mode 0, the dual
+    product and the grouped constraint products give the same bits; the fused norms agree to rounding."""
+    name, dic, fields = _fw_matrices()[case]
+    A = sps.csr_matrix(dic["A"])
+    n = A.shape[0]
+    rng = np.random.default_rng(5 + case)
+    b, x0 = rng.standard_normal(n), rng.standard_normal(n)
+    out = []
+    for fw in (1, 0):
+        with KrylovContext(n, 6) as ctx:
+            ctx.set_option("spmv_format", nat.FMT_PATTERN)
+            ctx.set_option("spmv_fw", 7 if fw else 0)             # every product kind through the staged kernel
+            ctx.upload_matrix(nat.SLOT_A, A)
+            if fields is not None:
+                assert ctx.info(f"fw_fields:{nat.SLOT_A}") == (fields if fw else 0), name
+            y, beta, res = _modes_through_abi(ctx, A, b, x0)
+            # the dual product of an Arnoldi step and a few more steps (grouped products come with the constraint stage below)
+            col0 = ctx.arnoldi_step(0)
+            ctx.form_iterate(np.array([0.37]))
+            ctx.arnoldi_begin_residual(1)
+            res1 = ctx.iterate_residual_wait()
+            ctx.arnoldi_finish(1)
+            col1 = ctx.arnoldi_wait(1)
+            w = ctx.download(nat.VEC_W)
+            out.append((y, beta, res, col0, col1, res1, w))
+    ref = np.linalg.norm(b - A @ x0)
+    np.testing.assert_allclose(out[0][0], A @ x0, rtol=0, atol=1e-13 * np.abs(A).dot(np.abs(x0)).max())
+    np.testing.assert_array_equal(out[0][0], out[1][0])
+    # (beta comes out of a fused norm whose per-CTA grouping differs: everything after q0 = r0 / beta agrees to rounding)
+    np.testing.assert_allclose(out[0][3], out[1][3], rtol=1e-13)
+    np.testing.assert_allclose(out[0][4], out[1][4], rtol=1e-12, atol=1e-13 * np.abs(out[1][4]).max())
+    for o in out:
+        assert abs(o[1] - ref) <= 1e-13 * ref and abs(o[2] - ref) <= 1e-13 * ref
+    assert abs(out[0][5] - out[1][5]) <= 1e-13 * max(out[1][5], 1e-300)
+
+
+def test_field_window_spmv_in_the_constraint_stage_and_with_ghost_columns():
+    """Grouped products M z_j (4 and 2 Krylov columns per pass) through the field-window kernel, and a matrix with ghost
+    columns as a row-sharded strip has them (entries that fit no window are gathered one by one): terms and products
+    equal the gather kernels' bit for bit."""
+    from structurepreservingiterativesolvers_b200 import solvers, wrappers
+    d, _ = lkdv.linforms(space="CG", M=20_000, mlength=16_000.0)
+    A, b = d["A"], d["b"]
+    n = b.size
+    x0 = 0.01 * np.cos(np.arange(n))
+    cl = wrappers.lkdv.conlist(d, x0)
+    terms = []
+    for fw in (1, 0):
+        sess = solvers.DeviceSession(A, b, x0, 12, conlist=cl, spmv_format="pattern", async_setup=False)
+        sess.ctx.set_option("spmv_fw", 7 if fw else 0)
+        sess.begin()
+        for j in range(8):
+            sess.arnoldi_launch(j); sess.arnoldi_wait(j)
+        terms.append([sess.ctx.constraint_terms(c, 7) for c in range(3)] + [sess.ctx.constraint_terms(c, 8) for c in range(3)])
+        sess.close()
+    for a, c in zip(*terms):
+        assert abs(a[0] - c[0]) <= 1e-13 * max(abs(c[0]), 1.0)
+        np.testing.assert_allclose(a[1], c[1], rtol=1e-11, atol=1e-13 * np.abs(c[1]).max())
+        np.testing.assert_allclose(a[2], c[2], rtol=1e-11, atol=1e-13 * np.abs(c[2]).max())
+    # ghost columns: the first rank's strip of a 2-way sharded system (owned columns first, ghosts behind them)
+    from structurepreservingiterativesolvers_b200.partition import FieldBlockPartition, localize, take_rows
+    part = FieldBlockPartition(3, 20_000, 2)
+    (A_loc,), plan = localize([take_rows(A, part, 0)], part, 0)
+    n_loc = A_loc.shape[0]
+    xx = np.random.default_rng(0).standard_normal(A_loc.shape[1])
+    ys = []
+    for fw in (1, 0):
+        with KrylovContext(n_loc, 2, n_halo=plan.n_halo) as ctx:
+            ctx.set_option("spmv_format", nat.FMT_PATTERN)
+            ctx.set_option("spmv_fw", 7 if fw else 0)
+            ctx.upload_matrix(nat.SLOT_A, A_loc)
+            assert ctx.info(f"fw_fields:{nat.SLOT_A}") == (3 if fw else 0)
+            ys.append(ctx.op_spmv(nat.SLOT_A, xx))
+    np.testing.assert_array_equal(ys[0], ys[1])
+    np.testing.assert_allclose(ys[0], A_loc @ xx, rtol=0, atol=1e-12 * np.abs(A_loc @ xx).max())

@@ -732,5 +732,6 @@ def test_evolve_mirrors_of_swe_and_lkdvrk_on_the_device():
         for structured, pre in ((True, "ilu"), (False, "ilu"), (True, "block")):
             o2 = wrappers.evolve_lkdvRK(N=10, M=20, k=30, tol=1e-6, steps=4, structured=structured, pre=pre, small_solver="kkt")
             for i, (a, b) in enumerate(zip(o2["sol"], ref)):
-                assert helpers.rel_diff(a, b) <= 1e-9 * max(i, 1), (structured, pre, i)
+                # (another preconditioner stops at another iterate inside the tolerance: 1e-6-level differences)
+                assert helpers.rel_diff(a, b) <= (1e-9 if pre == "ilu" else 1e-5) * max(i, 1), (structured, pre, i)
             assert max(o2["dm"].max(), o2["dmo"].max(), o2["de"].max()) <= 1e-12 * abs(ref[0]).sum()
