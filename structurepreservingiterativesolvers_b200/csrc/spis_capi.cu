@@ -42,6 +42,8 @@ struct Matrix {
   // row-pattern storage (SPIS_FMT_PATTERN)
   uint16_t* pid = nullptr; int32_t* tab_len = nullptr; int32_t* tab_off = nullptr; double* tab_val = nullptr;
   int npat = 0, patW = 0;
+  // SELLW: per-tile x windows + 16-bit window-local columns (spmv_sellw_kernel), built next to SELL / SELLD storage
+  SwTile* sw_tiles = nullptr; uint16_t* sw_lcol = nullptr; int sw_cap = 0;
   // field-window twin of the row-pattern storage (spmv_fw_kernel): F fields of N nodes, node shifts |d| <= D
   FwEntry* fw_tab = nullptr; int fwF = 0, fwN = 0, fwD = 0;
   // dictionary-coded values (SPIS_FMT_SELLD): scols as in SELL, one code per entry, table of <= 256 doubles
@@ -115,6 +117,13 @@ struct spis_ctx {
   int spmv_multi = 1;           // constraint stage: M z_j for a group of 2 / 4 Krylov columns from one pass over M
   int spmv_dual = 1;            // A q_{j+2} and ||A x_j - b|| from one pass over A (spis_arnoldi_begin_residual)
   int spmv_dual_ctas_per_sm = 0;
+  int spmv_sellw = 0;           // SELL / SELLD with x windows staged in shared memory and 16-bit columns (spmv_sellw_kernel).
+                                // Bit mask like spmv_fw: 1 = dual product, 2 = single products, 4 = grouped constraint products.
+                                // OFF by default: measured on the 1e7 operators (tools/tune_sellw.py, profiles/tune_sellw_r2.json) the staged
+                                // kernels LOSE to the L1-gather ones although they move 2 bytes less per entry -- swe (SELLD) 7.08 ms of SpMV
+                                // per solve against 6.63, lkdv forced to SELL 5.78 against 5.16: an LDS crosses the same data pipe as an
+                                // L1 hit, the TMA writes of the windows add to it, and two CTAs of 8 consumer warps hide the latency of
+                                // the matrix stream worse than four to five CTAs of the plain kernels.
   int spmv_fw = 1;              // row patterns on field-blocked systems, x windows staged in shared memory by TMA (spmv_fw_kernel).
                                 // Bit mask: 1 = the dual product of an Arnoldi step, 2 = single products, 4 = grouped constraint products.
                                 // Measured on the 1e7 lkdv operator (tools/tune_fw.py): dual 97 us against 109 us for the L1-gather kernel
@@ -571,8 +580,9 @@ double matrix_bytes(const Matrix& M) {
   const double nsl = (double)((M.nrows + 31) / 32);
   switch (M.fmt) {
     case SPIS_FMT_PATTERN: return 2.0 * (double)M.nrows;                                   // 16-bit stencil id per row (the table stays in L1)
-    case SPIS_FMT_SELLD: return 5.0 * (double)M.nnz_padded + 16.0 * nsl;                    // 32-bit column + 8-bit value code
-    case SPIS_FMT_SELL: case SPIS_FMT_SELL2: return 12.0 * (double)M.nnz_padded + 8.0 * nsl;
+    case SPIS_FMT_SELLD: return (M.sw_lcol ? 3.0 : 5.0) * (double)M.nnz_padded + 16.0 * nsl;    // 32- (16-) bit column + 8-bit value code
+    case SPIS_FMT_SELL: return (M.sw_lcol ? 10.0 : 12.0) * (double)M.nnz_padded + 8.0 * nsl;
+    case SPIS_FMT_SELL2: return 12.0 * (double)M.nnz_padded + 8.0 * nsl;
     default: return 12.0 * (double)M.nnz + 4.0 * (double)(M.nrows + 1);
   }
 }
@@ -621,11 +631,45 @@ int launch_fw(spis_ctx* ctx, const Matrix& M, const FwVecs& vv, const double* b,
   return SPIS_OK;
 }
 
+// SELLW SpMV (spmv_sellw_kernel): SELL / SELLD storage with staged x windows and 16-bit columns
+constexpr size_t kSwSmemBudget = 110 * 1024;       // two CTAs per SM
+inline size_t sw_smem_bytes(int NV, int cap) { return 2112 + (size_t)2 * NV * cap * sizeof(double); }
+bool sw_plan(const spis_ctx* ctx, const Matrix& M, int NV, int use) {
+  return M.sw_lcol && (ctx->spmv_sellw & use) && (M.fmt == SPIS_FMT_SELL || M.fmt == SPIS_FMT_SELLD) && !M.rowperm &&
+         sw_smem_bytes(NV, M.sw_cap) <= kSwSmemBudget;
+}
+
+template <int NV, int KIND>
+int launch_sellw(spis_ctx* ctx, const Matrix& M, const FwVecs& vv, const double* b, double* partial, int* grid_out) {
+  const int64_t nslices = (M.nrows + 31) / 32;
+  const int64_t ntiles = (nslices + kSwSlices - 1) / kSwSlices;
+  const int grid = (int)(ntiles < 2 * (int64_t)ctx->nsm ? ntiles : 2 * (int64_t)ctx->nsm);
+  const size_t smem = sw_smem_bytes(NV, M.sw_cap);
+  static bool attr_done = false;     // per template instance
+  if (!attr_done) {
+    CU(cudaFuncSetAttribute(spmv_sellw_kernel<NV, KIND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSwSmemBudget));
+    CU(cudaFuncSetAttribute(spmv_sellw_kernel<NV, KIND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSwSmemBudget));
+    attr_done = true;
+  }
+  if (M.fmt == SPIS_FMT_SELLD)
+    spmv_sellw_kernel<NV, KIND, true><<<grid, kSwThreads, smem, ctx->stream>>>(M.slice_off, M.code_off, M.sw_lcol, nullptr, M.codes, M.dict, M.sw_tiles, M.nrows, M.sw_cap, vv, b, partial);
+  else
+    spmv_sellw_kernel<NV, KIND, false><<<grid, kSwThreads, smem, ctx->stream>>>(M.slice_off, nullptr, M.sw_lcol, M.svals, nullptr, nullptr, M.sw_tiles, M.nrows, M.sw_cap, vv, b, partial);
+  CU(cudaGetLastError());
+  if (grid_out) *grid_out = grid;
+  return SPIS_OK;
+}
+
 template <int MODE>
 int launch_spmv_mode(spis_ctx* ctx, const Matrix& M, const double* x, const double* b, double* y, double* sumsq_out) {
   const XView xv = MODE != 0 ? fused_view(ctx) : XView();
   const unsigned long long seq = MODE != 0 ? fused_seq(ctx) : 0;
-  if (M.fmt == SPIS_FMT_SELL && ctx->spmv_variant > 0) {
+  if (sw_plan(ctx, M, 1, 2)) {
+    FwVecs vv{}; vv.x[0] = x; vv.y[0] = y;
+    int grid = 1;
+    TRY((launch_sellw<1, MODE>(ctx, M, vv, b, ctx->d_partial, &grid)));
+    if (MODE != 0) reduce_partials_kernel<<<1, kThreads, 0, ctx->stream>>>(ctx->d_partial, grid, sumsq_out, xv, seq);
+  } else if (M.fmt == SPIS_FMT_SELL && ctx->spmv_variant > 0) {
     // software-pipelined kernel (4 CTAs per SM by its register budget)
     const int64_t nslices = (M.nrows + 31) / 32;
     const int per_sm = ctx->spmv_pipe_ctas_per_sm > 0 ? ctx->spmv_pipe_ctas_per_sm : 4;
@@ -713,6 +757,9 @@ int launch_spmv_dual(spis_ctx* ctx, const double* x1, double* y1, const double* 
   if (fw_plan(ctx, M, 2, &fwT, &fwWS, &fwsm, 1)) {
     FwVecs vv{}; vv.x[0] = x1; vv.x[1] = x2; vv.y[0] = y1;
     TRY((launch_fw<2, 3>(ctx, M, vv, b, part, &grid)));
+  } else if (sw_plan(ctx, M, 2, 1)) {
+    FwVecs vv{}; vv.x[0] = x1; vv.x[1] = x2; vv.y[0] = y1;
+    TRY((launch_sellw<2, 3>(ctx, M, vv, b, part, &grid)));
   } else if (M.fmt == SPIS_FMT_PATTERN) {
     grid = grid_for(ctx, (M.nrows + kThreads - 1) / kThreads, ctx->spmv_dual_ctas_per_sm > 0 ? ctx->spmv_dual_ctas_per_sm : 6);
     while (grid > 1 && (int64_t)M.nrows + (int64_t)grid * kThreads >= (int64_t)INT32_MAX) grid /= 2;
@@ -760,6 +807,11 @@ int launch_spmv_multi(spis_ctx* ctx, int slot, int nv, const double* x, int64_t 
     for (int c = 0; c < nv; ++c) { vv.x[c] = x + (size_t)c * xstride; vv.y[c] = y + (size_t)c * ystride; }
     if (nv == 2) TRY((launch_fw<2, 0>(ctx, M, vv, nullptr, nullptr, nullptr)));
     else TRY((launch_fw<4, 0>(ctx, M, vv, nullptr, nullptr, nullptr)));
+  } else if (sw_plan(ctx, M, nv, 4)) {
+    FwVecs vv{};
+    for (int c = 0; c < nv; ++c) { vv.x[c] = x + (size_t)c * xstride; vv.y[c] = y + (size_t)c * ystride; }
+    if (nv == 2) TRY((launch_sellw<2, 0>(ctx, M, vv, nullptr, nullptr, nullptr)));
+    else TRY((launch_sellw<4, 0>(ctx, M, vv, nullptr, nullptr, nullptr)));
   } else if (M.fmt == SPIS_FMT_PATTERN) {
     int grid = grid_for(ctx, (M.nrows + kThreads - 1) / kThreads, nv == 2 ? 6 : 4);
     while (grid > 1 && (int64_t)M.nrows + (int64_t)grid * kThreads >= (int64_t)INT32_MAX) grid /= 2;
@@ -828,7 +880,7 @@ int launch_precond(spis_ctx* ctx, const double* q, double* z) {
 }
 
 void free_matrix(spis_ctx* ctx, Matrix& M) {
-  dfree(ctx, M.indptr); dfree(ctx, M.cols); dfree(ctx, M.vals); dfree(ctx, M.fw_tab);
+  dfree(ctx, M.indptr); dfree(ctx, M.cols); dfree(ctx, M.vals); dfree(ctx, M.fw_tab); dfree(ctx, M.sw_tiles); dfree(ctx, M.sw_lcol);
   dfree(ctx, M.slice_off); dfree(ctx, M.scols); dfree(ctx, M.svals); dfree(ctx, M.rowperm);
   dfree(ctx, M.pid); dfree(ctx, M.tab_len); dfree(ctx, M.tab_off); dfree(ctx, M.tab_val);
   dfree(ctx, M.codes); dfree(ctx, M.code_off); dfree(ctx, M.dict);
@@ -1372,6 +1424,7 @@ int spis_set_option(spis_ctx* ctx, const char* key, int64_t value) {
   else if (k == "sell_sigma") { ctx->sell_sigma = value ? 1 : 0; }
   else if (k == "spmv_multi") { ctx->spmv_multi = value ? 1 : 0; }
   else if (k == "spmv_dual") { ctx->spmv_dual = value ? 1 : 0; }
+  else if (k == "spmv_sellw") { REQUIRE(value >= 0 && value <= 7, "spmv_sellw is a bit mask 0..7"); ctx->spmv_sellw = (int)value; }
   else if (k == "spmv_fw") { REQUIRE(value >= 0 && value <= 7, "spmv_fw is a bit mask 0..7"); ctx->spmv_fw = (int)value; }
   else if (k == "spmv_dual_ctas_per_sm") { REQUIRE(value >= 0 && value <= 16, "spmv_dual_ctas_per_sm must be 0..16"); ctx->spmv_dual_ctas_per_sm = (int)value; }
   else if (k == "mdot_variant") { REQUIRE(value == 0 || value == 1 || value == 2 || value == 4 || value == 8, "mdot_variant must be 0 (auto), 1 (register sums), 2, 4 or 8"); ctx->mdot_variant = (int)value; }
@@ -1411,6 +1464,11 @@ int spis_get_info(const spis_ctx* cctx, const char* key, int64_t* value_out) {
     const int slot = atoi(k.c_str() + 6);
     REQUIRE(slot >= 0 && slot < SPIS_MAX_SLOTS && ctx->mats[slot].present, "slot %d not uploaded", slot);
     *value_out = ctx->mats[slot].ndict;
+  }
+  else if (k.rfind("sellw_cap:", 0) == 0) {
+    const int slot = atoi(k.c_str() + 10);
+    REQUIRE(slot >= 0 && slot < SPIS_MAX_SLOTS && ctx->mats[slot].present, "slot %d not uploaded", slot);
+    *value_out = (ctx->mats[slot].sw_lcol && ctx->spmv_sellw) ? ctx->mats[slot].sw_cap : 0;
   }
   else if (k.rfind("fw_fields:", 0) == 0) {
     const int slot = atoi(k.c_str() + 10);
@@ -1528,6 +1586,28 @@ static int try_pattern_storage(spis_ctx* ctx, Matrix& M, cudaStream_t s, int* ok
   if ((double)h_info[5] * 8.0 > (double)nrows && ctx->fmt_pref != SPIS_FMT_PATTERN) { drop(); return SPIS_OK; }
   M.npat = npat; M.patW = W;
   *ok_out = 1;
+  return SPIS_OK;
+}
+
+// SELL / SELLD matrix on the device -> per-tile x windows and 16-bit window-local columns (spmv_sellw_kernel), if every
+// tile of 256 rows decomposes into at most 12 windows of at most kSwCapMax doubles together.
+static int try_sellw(spis_ctx* ctx, Matrix& M, cudaStream_t s) {
+  const int64_t nslices = (M.nrows + 31) / 32;
+  const int64_t ntiles = (nslices + kSwSlices - 1) / kSwSlices;
+  if (ntiles < 1 || ntiles > 0x7fffffff) return SPIS_OK;
+  int* info = nullptr;
+  TRY(dalloc(ctx, &info, 4));
+  TRY(dalloc(ctx, &M.sw_tiles, (size_t)ntiles, false));
+  TRY(dalloc(ctx, &M.sw_lcol, (size_t)M.nnz_padded, false));
+  sellw_analyse_kernel<<<(unsigned)ntiles, 256, 0, s>>>(M.slice_off, M.scols, M.nrows, M.sw_tiles, M.sw_lcol, kSwCapMax, info);
+  int h[4] = {0};
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h, info, sizeof(h), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  dfree(ctx, info);
+  if (e != cudaSuccess) { dfree(ctx, M.sw_tiles); dfree(ctx, M.sw_lcol); return fail(ctx, SPIS_E_CUDA, "window analysis failed: %s", cudaGetErrorString(e)); }
+  if (h[0] || h[1] < 2) { dfree(ctx, M.sw_tiles); dfree(ctx, M.sw_lcol); return SPIS_OK; }     // some tile does not decompose: plain kernels
+  M.sw_cap = (h[1] + 15) / 16 * 16;
   return SPIS_OK;
 }
 
@@ -1682,6 +1762,7 @@ int spis_upload_csr(spis_ctx* ctx, int slot, int64_t nrows, int64_t ncols, int64
       TRY(try_value_dictionary(ctx, M, s, off, &ok));
       REQUIRE(ok || ctx->fmt_pref != SPIS_FMT_SELLD, "matrix in slot %d has more than 256 distinct values: spmv_format=selld does not apply", slot);
     }
+    if (fmt == SPIS_FMT_SELL && ctx->spmv_sellw && !M.rowperm && M.nnz_padded > 0) TRY(try_sellw(ctx, M, s));
   } else {
     const double avg = nrows ? (double)nnz / (double)nrows : 0.0;
     M.csr_lanes = avg <= 3 ? 2 : avg <= 6 ? 4 : avg <= 12 ? 8 : avg <= 24 ? 16 : 32;
@@ -2033,6 +2114,11 @@ int spis_pipe_begin(spis_ctx* ctx, double thr, int phase0) {
     ctx->d_rec = static_cast<double*>(dp);
     memset(ctx->h_rec, 0, bytes);
   }
+  {
+    const size_t need = (size_t)(4 * ctx->K + 4 + 70 * 70) * sizeof(double);      // hess_kernel's dynamic shared memory at most
+    REQUIRE(need <= 227 * 1024, "k_max = %d is too large for the pipelined loop", ctx->kmax);
+    if (need > 48 * 1024) CU(cudaFuncSetAttribute(hess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+  }
   for (int i = 0; i < kRecSlots; ++i) { ctx->step_seq[i] = 0; ctx->res_seq[i] = 0; }
   ctx->res_tickets = 0;
   ctx->pipe_thr2 = thr * thr;
@@ -2104,10 +2190,12 @@ int spis_step_enqueue(spis_ctx* ctx, int j, int flags, int64_t* ticket_out) {
     ctx->step_seq[j % kRecSlots] = sw;
     *reinterpret_cast<volatile unsigned long long*>(step_rec_host(ctx, j)) = 0ull;
     HessState st{ctx->hs_cs, ctx->hs_sn, ctx->hs_gv, ctx->hs_R, ctx->hs_tracking, ctx->kmax};
-    const size_t smem = (size_t)(2 * K + 4) * sizeof(double);
+    // the leading block of R travels through shared memory while it fits 40 KB (m <= 64 and then some)
+    const int rcache = m <= 70 ? (m + 1) / 2 * 2 : 0;
+    const size_t smem = (size_t)(4 * K + 4 + rcache * rcache) * sizeof(double);
     const unsigned long long* errw = ctx->xactive ? reinterpret_cast<const unsigned long long*>(ctx->xbuf + ctx->xv.flags_off()) + 4 * ctx->xv.world : nullptr;
     hess_kernel<<<1, 32, smem, ctx->stream>>>(j, st, h1, h2, scal, ctx->d_ydev + (size_t)(j & 1) * K, ctx->d_phase,
-                                               step_rec_dev(ctx, j), sw, K, errw);
+                                               step_rec_dev(ctx, j), sw, K, errw, rcache);
     CU(cudaGetLastError());
     ctx->prof_launch[SPIS_PROF_OTHER] += 1;
   }

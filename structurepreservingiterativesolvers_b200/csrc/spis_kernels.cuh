@@ -843,19 +843,32 @@ struct HessState {
 __global__ void __launch_bounds__(32)
 hess_kernel(int j, HessState st, const double* __restrict__ h1, const double* __restrict__ h2, double* norm2_out,
             double* ydst, int* phase, double* host_rec, unsigned long long rec_seq, int K,
-            const unsigned long long* __restrict__ peer_err) {
+            const unsigned long long* __restrict__ peer_err, int rcache /* rows of R cached in shared memory (0: read global) */) {
   extern __shared__ double hsm[];
   double* r = hsm;                       // [m + 1] the new column
   double* t = hsm + (K + 2);             // [m] right-hand side of the back substitution
+  double* scs = t + K;                   // [m] rotations so far (cosines, sines)
+  double* ssn = scs + K;
+  double* sR = ssn + K;                  // [rcache x rcache] leading block of R, column-major (when it fits)
   const int lane = threadIdx.x;
   const int m = j + 1;
   const int kmax = st.kmax;
+  // everything the sequential parts touch comes into shared memory with independent loads first: a dependent chain
+  // of global loads costs ~0.6 us per link, and this kernel sits between two sweeps of every Arnoldi step
   double s2 = 0.0;
   for (int i = lane; i < m; i += 32) {
-    const double b = h2[i];
-    r[i] = h1[i] + b;
-    s2 = fma(b, b, s2);
+    const double bq = h2[i];
+    r[i] = h1[i] + bq;
+    s2 = fma(bq, bq, s2);
+    t[i] = st.gv[i];
   }
+  for (int i = lane; i < j; i += 32) { scs[i] = st.cs[i]; ssn[i] = st.sn[i]; }
+  const bool cached = rcache >= m;
+  if (cached)
+    for (int idx = lane; idx < j * j; idx += 32) {        // columns 0 .. j-1 (column j is produced below)
+      const int col = idx / j, row = idx - col * j;
+      if (row <= col) sR[row + col * rcache] = st.R[(size_t)row + (size_t)col * kmax];
+    }
   s2 = warp_sum(s2);
   const double nw2 = h2[m];
   double n2 = nw2 - s2;
@@ -869,18 +882,20 @@ hess_kernel(int j, HessState st, const double* __restrict__ h1, const double* __
   double ls = 0.0;
   if (lane == 0 && valid) {
     for (int i = 0; i < j; ++i) {
-      const double a = r[i], b = r[i + 1], c = st.cs[i], s = st.sn[i];
-      r[i] = c * a + s * b;
-      r[i + 1] = -s * a + c * b;
+      const double a = r[i], bb = r[i + 1], c = scs[i], s = ssn[i];
+      r[i] = c * a + s * bb;
+      r[i + 1] = -s * a + c * bb;
     }
     const double den = hypot(r[j], r[j + 1]);
     if (den > 0.0) {
       const double c = r[j] / den, s = r[j + 1] / den;
       st.cs[j] = c; st.sn[j] = s;
       r[j] = den;
-      const double gj = st.gv[j];
+      const double gj = t[j];
+      t[j] = c * gj;
       st.gv[j] = c * gj;
       st.gv[j + 1] = -s * gj;
+      r[j + 1] = -s * gj;                  // (kept for ls below)
     } else {
       *st.tracking = 0;
     }
@@ -888,28 +903,32 @@ hess_kernel(int j, HessState st, const double* __restrict__ h1, const double* __
   __syncwarp();
   valid = *st.tracking;
   if (valid) {
-    for (int i = lane; i <= j; i += 32) st.R[(size_t)i + (size_t)j * kmax] = r[i];
-    ls = fabs(st.gv[j + 1]);
+    for (int i = lane; i <= j; i += 32) {
+      st.R[(size_t)i + (size_t)j * kmax] = r[i];
+      if (cached) sR[i + j * rcache] = r[i];
+    }
+    ls = fabs(r[j + 1]);
     // pivots: the least-squares solution is trusted only while min |R_ii| > 1e-14 max |R_ii| (as smallsolve does)
     double dmin = 1e300, dmax = 0.0;
     for (int i = lane; i < m; i += 32) {
-      const double d = fabs(i == j ? r[j] : st.R[(size_t)i + (size_t)i * kmax]);
+      const double d = fabs(i == j ? r[j] : (cached ? sR[i + i * rcache] : st.R[(size_t)i + (size_t)i * kmax]));
       dmin = fmin(dmin, d); dmax = fmax(dmax, d);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, o)); dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o)); }
     if (!(dmin > 1e-14 * dmax)) valid = 0;
   }
+  __syncwarp();
   if (valid) {
     // y = R^{-1} g, column-oriented back substitution: m dependent steps, the updates of a step spread over the warp
-    for (int i = lane; i < m; i += 32) t[i] = st.gv[i];
-    __syncwarp();
     for (int i = m - 1; i >= 0; --i) {
-      const double* col = st.R + (size_t)i * kmax;
-      const double yi = t[i] / (i == j ? r[j] : col[i]);
+      const double* colg = st.R + (size_t)i * kmax;
+      const double* cols = sR + (size_t)i * rcache;
+      const double piv = (i == j) ? r[j] : (cached ? cols[i] : colg[i]);
+      const double yi = t[i] / piv;
       __syncwarp();
       if (lane == 0) t[i] = yi;
-      for (int l = lane; l < i; l += 32) t[l] = fma(-(i == j ? r[l] : col[l]), yi, t[l]);
+      for (int l = lane; l < i; l += 32) t[l] = fma(-((i == j) ? r[l] : (cached ? cols[l] : colg[l])), yi, t[l]);
       __syncwarp();
     }
     for (int i = lane; i < m; i += 32) {
@@ -2227,6 +2246,253 @@ spmv_fw_kernel(const __grid_constant__ FwArgs P, const __grid_constant__ FwVecs 
 #pragma unroll
     for (int wv = 0; wv < kFwThreads / 32; ++wv) t += sred[wv];
     partial[blockIdx.x] = t;                           // reduce_partials_kernel / the riding tail finishes
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1, SELL-32 / SELLD with x staged through shared memory and 16-bit column indices ("SELLW").
+// The general-matrix twin of the field-window kernel: nothing is assumed about the ordering.  Rows are taken in tiles
+// of 8 slices (256 rows, one slice per warp).  At upload a kernel looks at the columns of every tile: FEM rows couple to
+// a few contiguous index ranges (neighbouring nodes of each field block), so the columns of a tile fall into a handful
+// of WINDOWS; they are found on the device (coarse 256-wide buckets in a small hash set, sorted, adjacent buckets
+// merged, then the exact min / max column of each run), and every entry's 32-bit column becomes a 16-bit position in
+// the concatenation of the tile's windows.  The SpMV kernels bring the windows of a tile into shared memory with TMA
+// bulk copies (a producer warp, two stages, full / empty mbarriers as in orth_mid_kernel) and gather with LDS.
+//   * HBM: 2 instead of 4 bytes of index per entry (SELL 12 -> 10 bytes per entry, SELLD 5 -> 3), and x is streamed
+//     window by window (each window once per tile) instead of being gathered through L1 tags;
+//   * a matrix whose tiles do not decompose (more than 12 windows or more than `cap` staged doubles in some tile)
+//     keeps its plain SELL / SELLD kernels: spis_upload_csr decides per matrix.
+// Per-row summation order is that of the SELL kernels (chunks of four entries, even / odd positions into two
+// accumulators, a trailing partial chunk into the first): same bits.
+// ------------------------------------------------------------------------------------------
+constexpr int kSwSlices = 8;
+constexpr int kSwMaxWin = 12;
+constexpr int kSwCapMax = 4096;             // staged doubles per tile and vector, at most (16-bit positions would allow 65535)
+constexpr int kSwHash = 128;
+constexpr int kSwThreads = 32 * (kSwSlices + 1);   // 8 consumer warps + 1 producer warp
+
+struct SwTile { int nwin; int total; int start[kSwMaxWin]; int base[kSwMaxWin]; int len[kSwMaxWin]; int pad[2]; };   // 40 ints
+
+// one CTA of 256 threads per tile: windows of the tile and the 16-bit positions of its entries
+// info[0] = 1 if some tile does not decompose, info[1] = largest window total of any tile
+__global__ void __launch_bounds__(256)
+sellw_analyse_kernel(const int64_t* __restrict__ slice_off, const int32_t* __restrict__ cols, int64_t nrows,
+                     SwTile* __restrict__ tiles, uint16_t* __restrict__ lcol, int cap, int* info) {
+  __shared__ int hkeys[kSwHash];
+  __shared__ int arr[kSwHash];
+  __shared__ int run_hi[kSwMaxWin], smin[kSwMaxWin], smax[kSwMaxWin], sstart[kSwMaxWin], sbase[kSwMaxWin];
+  __shared__ int s_n, s_fail;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t nslices = (nrows + 31) >> 5;
+  const int64_t tile = blockIdx.x;
+  const int64_t slice = tile * kSwSlices + warp;
+  for (int i = tid; i < kSwHash; i += 256) hkeys[i] = -1;
+  if (tid == 0) { s_n = 0; s_fail = 0; }
+  __syncthreads();
+  int64_t off = 0; int width = 0;
+  if (slice < nslices) { off = slice_off[slice]; width = (int)((slice_off[slice + 1] - off) >> 5); }
+  // 1. coarse buckets of 256 columns
+  int last = -2;
+  for (int k = 0; k < width; ++k) {
+    const int bk = cols[off + (int64_t)k * 32 + lane] >> 8;
+    if (bk == last) continue;
+    last = bk;
+    unsigned slot = ((unsigned)bk * 2654435761u) >> 25;
+    for (int probes = 0;; ++probes) {
+      const int cur = hkeys[slot];
+      if (cur == bk) break;
+      if (cur == -1) {
+        const int prev = atomicCAS(&hkeys[slot], -1, bk);
+        if (prev == -1 || prev == bk) break;
+      }
+      if (probes >= kSwHash) { s_fail = 1; break; }
+      slot = (slot + 1) & (kSwHash - 1);
+    }
+  }
+  __syncthreads();
+  // 2. sort the distinct buckets, merge neighbours into runs
+  if (tid == 0) {
+    int n = 0;
+    for (int i = 0; i < kSwHash; ++i) if (hkeys[i] != -1) arr[n++] = hkeys[i];
+    for (int i = 1; i < n; ++i) { const int v = arr[i]; int j = i - 1; while (j >= 0 && arr[j] > v) { arr[j + 1] = arr[j]; --j; } arr[j + 1] = v; }
+    int nr = 0;
+    for (int i = 0; i < n; ++i) {
+      if (i > 0 && arr[i] <= arr[i - 1] + 1) { run_hi[nr - 1] = arr[i]; continue; }
+      if (nr == kSwMaxWin) { s_fail = 1; break; }
+      run_hi[nr] = arr[i]; smin[nr] = 0x7fffffff; smax[nr] = -1; ++nr;
+    }
+    s_n = nr;
+  }
+  __syncthreads();
+  const int nr = s_n;
+  // 3. exact column range of every run
+  if (!s_fail) {
+    int lr = 0; last = -2;
+    for (int k = 0; k < width; ++k) {
+      const int c = cols[off + (int64_t)k * 32 + lane];
+      const int bk = c >> 8;
+      if (bk != last) { last = bk; lr = 0; while (lr < nr - 1 && bk > run_hi[lr]) ++lr; }
+      atomicMin(&smin[lr], c); atomicMax(&smax[lr], c);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    SwTile t;
+    int tot = 0;
+    t.nwin = s_fail ? 0 : nr;
+    for (int r = 0; r < kSwMaxWin; ++r) {
+      int st = 0, ln = 0;
+      if (!s_fail && r < nr && smax[r] >= 0) { st = smin[r] & ~1; ln = ((smax[r] - st + 1) + 1) & ~1; }
+      t.start[r] = st; t.base[r] = tot; t.len[r] = ln;
+      sstart[r] = st; sbase[r] = tot;
+      tot += ln;
+    }
+    t.total = tot; t.pad[0] = t.pad[1] = 0;
+    if (tot > cap) s_fail = 1;
+    tiles[tile] = t;
+    if (s_fail) atomicExch(info, 1);
+    atomicMax(info + 1, tot);
+  }
+  __syncthreads();
+  // 4. 16-bit positions
+  if (!s_fail) {
+    int lr = 0; last = -2;
+    for (int k = 0; k < width; ++k) {
+      const int64_t at = off + (int64_t)k * 32 + lane;
+      const int c = cols[at];
+      const int bk = c >> 8;
+      if (bk != last) { last = bk; lr = 0; while (lr < nr - 1 && bk > run_hi[lr]) ++lr; }
+      lcol[at] = (uint16_t)(sbase[lr] + (c - sstart[lr]));
+    }
+  }
+}
+
+// KIND as in spmv_fw_kernel: 0: y_v = A x_v; 1: y = b - A x, sumsq; 2: sumsq = ||A x - b||^2; 3: y_0 = A x_0 and ||A x_1 - b||^2
+template <int NV, int KIND, bool CODED>
+__global__ void __launch_bounds__(kSwThreads, 2)
+spmv_sellw_kernel(const int64_t* __restrict__ slice_off, const int64_t* __restrict__ code_off, const uint16_t* __restrict__ lcol,
+                  const double* __restrict__ vals, const uint32_t* __restrict__ codes, const double* __restrict__ table,
+                  const SwTile* __restrict__ tiles, int64_t nrows, int cap, const __grid_constant__ FwVecs Vv,
+                  const double* __restrict__ b, double* __restrict__ partial) {
+  extern __shared__ __align__(128) unsigned char swraw[];
+  double* sdict = reinterpret_cast<double*>(swraw);                         // [256]
+  uint64_t* full = reinterpret_cast<uint64_t*>(sdict + 256);                // [2]
+  uint64_t* empty = full + 2;                                               // [2]
+  double* win = reinterpret_cast<double*>(empty + 2 + 4);                   // [2 stages][NV][cap]  (16-byte aligned: 2048 + 64 bytes in)
+  __shared__ double sred[kSwSlices];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (CODED && tid < 256) sdict[tid] = __ldg(table + tid);
+  if (tid == 0) {
+    mbar_init(full + 0, 1); mbar_init(full + 1, 1);
+    mbar_init(empty + 0, kSwSlices); mbar_init(empty + 1, kSwSlices);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int64_t nslices = (nrows + 31) >> 5;
+  const int64_t ntiles = (nslices + kSwSlices - 1) / kSwSlices;
+  const int64_t my_count = ntiles > (int64_t)blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  double ss = 0.0;
+  if (warp == kSwSlices) {
+    // ---- producer: the windows of my tiles, two stages ahead of nobody: stage k & 1 is refilled once its eight
+    //      consumer warps have released it
+    if (lane == 0) {
+      const uint64_t pol = l2_policy_evict_first();
+      for (int64_t k = 0; k < my_count; ++k) {
+        const int stage = (int)(k & 1);
+        if (k >= 2) mbar_wait(empty + stage, (uint32_t)(((k >> 1) - 1) & 1));
+        const SwTile* tp = tiles + (blockIdx.x + k * gridDim.x);
+        const int nwin = __ldg(&tp->nwin), total = __ldg(&tp->total);
+        mbar_arrive_expect_tx(full + stage, (uint32_t)total * (uint32_t)sizeof(double) * NV);
+        for (int r = 0; r < nwin; ++r) {
+          const int st = __ldg(&tp->start[r]), bs = __ldg(&tp->base[r]), ln = __ldg(&tp->len[r]);
+          if (ln == 0) continue;
+#pragma unroll
+          for (int v = 0; v < NV; ++v)
+            bulk_g2s(win + ((size_t)stage * NV + v) * cap + bs, Vv.x[v] + st, (uint32_t)ln * (uint32_t)sizeof(double), full + stage, pol);
+        }
+      }
+    }
+  } else {
+    for (int64_t k = 0; k < my_count; ++k) {
+      const int stage = (int)(k & 1);
+      const int64_t slice = (blockIdx.x + k * gridDim.x) * kSwSlices + warp;
+      int64_t off = 0; int width = 0;
+      double bv = 0.0;
+      const int64_t row = (slice << 5) + lane;
+      if (slice < nslices) {
+        off = __ldg(slice_off + slice);
+        width = (int)((__ldg(slice_off + slice + 1) - off) >> 5);
+        if (KIND != 0 && row < nrows) bv = __ldg(b + row);
+      }
+      const uint16_t* lc = lcol + off + lane;
+      const double* vp = CODED ? nullptr : vals + off + lane;
+      const uint32_t* q = CODED ? codes + (slice < nslices ? __ldg(code_off + slice) : 0) + lane : nullptr;
+      mbar_wait(full + stage, (uint32_t)((k >> 1) & 1));
+      const double* ws = win + (size_t)stage * NV * cap;
+      double a0[NV], a1[NV];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) { a0[v] = 0.0; a1[v] = 0.0; }
+      int kk = 0;
+      for (; kk + 4 <= width; kk += 4) {
+        const int c0 = __ldcs(lc + (kk + 0) * 32), c1 = __ldcs(lc + (kk + 1) * 32);
+        const int c2 = __ldcs(lc + (kk + 2) * 32), c3 = __ldcs(lc + (kk + 3) * 32);
+        double v0, v1, v2, v3;
+        if constexpr (CODED) {
+          const uint32_t w = __ldcs(q + (kk >> 2) * 32);
+          v0 = sdict[w & 255u]; v1 = sdict[(w >> 8) & 255u]; v2 = sdict[(w >> 16) & 255u]; v3 = sdict[w >> 24];
+        } else {
+          v0 = __ldcs(vp + (kk + 0) * 32); v1 = __ldcs(vp + (kk + 1) * 32);
+          v2 = __ldcs(vp + (kk + 2) * 32); v3 = __ldcs(vp + (kk + 3) * 32);
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const double* wv = ws + (size_t)v * cap;
+          const double x0 = wv[c0], x1 = wv[c1], x2 = wv[c2], x3 = wv[c3];
+          a0[v] = fma(v0, x0, a0[v]); a1[v] = fma(v1, x1, a1[v]);
+          a0[v] = fma(v2, x2, a0[v]); a1[v] = fma(v3, x3, a1[v]);
+        }
+      }
+      if (kk < width) {
+        uint32_t w = 0u;
+        if constexpr (CODED) w = __ldcs(q + (kk >> 2) * 32);
+        for (; kk < width; ++kk, w >>= 8) {
+          const int ck = __ldcs(lc + kk * 32);
+          double vk;
+          if constexpr (CODED) vk = sdict[w & 255u]; else vk = __ldcs(vp + kk * 32);
+#pragma unroll
+          for (int v = 0; v < NV; ++v) a0[v] = fma(vk, ws[(size_t)v * cap + ck], a0[v]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + stage);          // this warp is done with the stage
+      if (slice < nslices && row < nrows) {
+        if (KIND == 0) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) Vv.y[v][row] = a0[v] + a1[v];
+        } else if (KIND == 1) {
+          const double rr = bv - (a0[0] + a1[0]);
+          Vv.y[0][row] = rr;
+          ss = fma(rr, rr, ss);
+        } else if (KIND == 2) {
+          const double rr = (a0[0] + a1[0]) - bv;
+          ss = fma(rr, rr, ss);
+        } else {
+          Vv.y[0][row] = a0[0] + a1[0];
+          const double rr = (a0[NV - 1] + a1[NV - 1]) - bv;
+          ss = fma(rr, rr, ss);
+        }
+      }
+    }
+  }
+  if (KIND == 0) return;
+  ss = warp_sum(ss);
+  if (warp < kSwSlices && lane == 0) sred[warp] = ss;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int wv = 0; wv < kSwSlices; ++wv) t += sred[wv];
+    partial[blockIdx.x] = t;
   }
 }
 

@@ -567,3 +567,74 @@ def test_field_window_spmv_in_the_constraint_stage_and_with_ghost_columns():
             ys.append(ctx.op_spmv(nat.SLOT_A, xx))
     np.testing.assert_array_equal(ys[0], ys[1])
     np.testing.assert_allclose(ys[0], A_loc @ xx, rtol=0, atol=1e-12 * np.abs(A_loc @ xx).max())
+
+
+# ---- round 2: SELL / SELLD with per-tile x windows in shared memory and 16-bit columns (spmv_sellw_kernel) ---------------
+@pytest.mark.parametrize("fmt", [nat.FMT_SELL, nat.FMT_SELLD])
+@pytest.mark.parametrize("case", ["swe", "lkdv", "lkdvRK", "ragged"])
+def test_sellw_spmv_is_bit_identical_to_the_plain_sell_kernels(case, fmt):
+    """Window analysis at upload + staged kernels against the L1-gather SELL / SELLD kernels: mode 0, the dual product
+    and the grouped products give the same bits (same per-row order); the fused norms agree to rounding.  A matrix
+    whose tiles do not decompose into a few windows (random columns) silently keeps the plain kernels."""
+    from structurepreservingiterativesolvers_b200.problems import lkdvRK, swe
+    rng = np.random.default_rng(11)
+    if case == "swe":
+        A = swe.linforms(M=40, mlength=32.0)[0]["A"]
+    elif case == "lkdv":
+        A = lkdv.linforms(space="CG", M=33_350, mlength=0.8 * 33_350)[0]["A"]
+    elif case == "lkdvRK":
+        A = lkdvRK.linforms(M=5_000, space="CG", mlength=4000.0)[0]["A"]
+    else:
+        A = ragged_matrix(20_011, seed=5)
+        A.data[:] = rng.integers(-5, 6, size=A.nnz).astype(np.float64)
+    A = sps.csr_matrix(A)
+    n = A.shape[0]
+    b, x0 = rng.standard_normal(n), rng.standard_normal(n)
+    out = []
+    for sw in (7, 0):
+        with KrylovContext(n, 6) as ctx:
+            ctx.set_option("spmv_format", fmt)
+            ctx.set_option("spmv_sellw", sw)
+            ctx.upload_matrix(nat.SLOT_A, A)
+            assert ctx.info(f"fmt:{nat.SLOT_A}") == fmt
+            cap = ctx.info(f"sellw_cap:{nat.SLOT_A}")
+            assert (cap > 0) == (sw != 0 and case != "ragged"), (case, cap)
+            y, beta, res = _modes_through_abi(ctx, A, b, x0)
+            col0 = ctx.arnoldi_step(0)
+            ctx.form_iterate(np.array([0.37]))
+            ctx.arnoldi_begin_residual(1)
+            res1 = ctx.iterate_residual_wait()
+            ctx.arnoldi_finish(1)
+            col1 = ctx.arnoldi_wait(1)
+            out.append((y, beta, res, col0, col1, res1))
+    ref = np.linalg.norm(b - A @ x0)
+    np.testing.assert_array_equal(out[0][0], out[1][0])
+    np.testing.assert_allclose(out[0][0], A @ x0, rtol=0, atol=1e-13 * abs(A).dot(np.abs(x0)).max())
+    np.testing.assert_allclose(out[0][3], out[1][3], rtol=1e-13)
+    np.testing.assert_allclose(out[0][4], out[1][4], rtol=1e-12, atol=1e-13 * np.abs(out[1][4]).max())
+    for o in out:
+        assert abs(o[1] - ref) <= 1e-13 * ref and abs(o[2] - ref) <= 1e-13 * ref
+    assert abs(out[0][5] - out[1][5]) <= 1e-13 * max(out[1][5], 1e-300)
+
+
+def test_sellw_in_the_constraint_stage():
+    """Grouped products M z_j of the constraint stage (4 / 2 columns per pass over M) through the staged SELL kernel."""
+    from structurepreservingiterativesolvers_b200 import solvers, wrappers
+    from structurepreservingiterativesolvers_b200.problems import swe
+    d, _ = swe.linforms(M=30, mlength=24.0)
+    A, b = d["A"], d["b"]
+    x0 = 0.01 * np.cos(np.arange(b.size))
+    cl = wrappers.swe.conlist(d, x0)
+    terms = []
+    for sw in (7, 0):
+        sess = solvers.DeviceSession(A, b, x0, 12, conlist=cl, async_setup=False)
+        sess.ctx.set_option("spmv_sellw", sw)
+        sess.begin()
+        for j in range(8):
+            sess.arnoldi_launch(j); sess.arnoldi_wait(j)
+        terms.append([sess.ctx.constraint_terms(c, 7) for c in range(2)] + [sess.ctx.constraint_terms(c, 8) for c in range(2)])
+        sess.close()
+    for a, c in zip(*terms):
+        assert abs(a[0] - c[0]) <= 1e-13 * max(abs(c[0]), 1.0)
+        np.testing.assert_allclose(a[1], c[1], rtol=1e-11, atol=1e-13 * max(np.abs(c[1]).max(), 1e-300))
+        np.testing.assert_allclose(a[2], c[2], rtol=1e-11, atol=1e-13 * max(np.abs(c[2]).max(), 1e-300))
