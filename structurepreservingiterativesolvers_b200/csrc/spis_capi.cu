@@ -124,6 +124,7 @@ struct spis_ctx {
                                 // per solve against 6.63, lkdv forced to SELL 5.78 against 5.16: an LDS crosses the same data pipe as an
                                 // L1 hit, the TMA writes of the windows add to it, and two CTAs of 8 consumer warps hide the latency of
                                 // the matrix stream worse than four to five CTAs of the plain kernels.
+  int spmv_fw_rows = 4;         // spmv_fw_kernel: rows per thread and tile (4: narrow tiles, three CTAs per SM; 8: wide tiles, two)
   int spmv_fw = 1;              // row patterns on field-blocked systems, x windows staged in shared memory by TMA (spmv_fw_kernel).
                                 // Bit mask: 1 = the dual product of an Arnoldi step, 2 = single products, 4 = grouped constraint products.
                                 // Measured on the 1e7 lkdv operator (tools/tune_fw.py): dual 97 us against 109 us for the L1-gather kernel
@@ -592,8 +593,9 @@ double matrix_bytes(const Matrix& M) {
 constexpr size_t kFwSmemBudget = 110 * 1024;       // two CTAs per SM
 bool fw_plan(const spis_ctx* ctx, const Matrix& M, int NV, int* T_out, int* WS_out, size_t* smem_out, int use = 7) {
   if (!M.fw_tab || !(ctx->spmv_fw & use) || M.fmt != SPIS_FMT_PATTERN || M.patW > 16 || M.fwF * M.npat > kFwMaxTable / 4) return false;
+  const int rows = (ctx->spmv_fw_rows == 4 && M.fwF <= 4) ? 4 : 8;
   for (int T = 8 * kFwThreads; T >= kFwThreads; T /= 2) {
-    if (M.fwF * (T / kFwThreads) > kFwRows) continue;
+    if (M.fwF * (T / kFwThreads) > rows) continue;
     const int WS = (T + 2 * M.fwD + 2 + 7) / 8 * 8;
     const size_t smem = fw_smem_bytes(NV, M.npat, M.patW, M.fwF, WS);
     if (smem > kFwSmemBudget) continue;
@@ -611,21 +613,25 @@ int launch_fw(spis_ctx* ctx, const Matrix& M, const FwVecs& vv, const double* b,
   P.pid = M.pid; P.tab_len = M.tab_len; P.tab = M.fw_tab;
   P.npat = M.npat; P.W = M.patW; P.F = M.fwF; P.N = M.fwN; P.D = M.fwD; P.T = T; P.WS = WS; P.ld = ctx->ld;
   const int ntiles = (M.fwN + T - 1) / T;
-  const int grid = ntiles < 2 * ctx->nsm ? ntiles : 2 * ctx->nsm;
+  const int per_sm = (M.fwF * (T / kFwThreads) <= 4 && ctx->spmv_fw_rows == 4) ? 3 : 2;
+  const int grid = ntiles < per_sm * ctx->nsm ? ntiles : per_sm * ctx->nsm;
   static bool attr_done = false;     // per template instance
   if (!attr_done) {
-    CU(cudaFuncSetAttribute(spmv_fw_kernel<NV, KIND, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwSmemBudget));
-    CU(cudaFuncSetAttribute(spmv_fw_kernel<NV, KIND, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwSmemBudget));
-    CU(cudaFuncSetAttribute(spmv_fw_kernel<NV, KIND, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwSmemBudget));
-    CU(cudaFuncSetAttribute(spmv_fw_kernel<NV, KIND, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwSmemBudget));
+#define SPIS_FW_ATTR(NCHV, RV) CU(cudaFuncSetAttribute(spmv_fw_kernel<NV, KIND, NCHV, RV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwSmemBudget));
+    SPIS_FW_ATTR(1, 4) SPIS_FW_ATTR(2, 4) SPIS_FW_ATTR(3, 4) SPIS_FW_ATTR(4, 4) SPIS_FW_ATTR(1, 8) SPIS_FW_ATTR(2, 8) SPIS_FW_ATTR(3, 8) SPIS_FW_ATTR(4, 8)
+#undef SPIS_FW_ATTR
     attr_done = true;
   }
+  const bool r4 = M.fwF * (T / kFwThreads) <= 4 && ctx->spmv_fw_rows == 4;
+#define SPIS_FW_LAUNCH(NCHV) if (r4) spmv_fw_kernel<NV, KIND, NCHV, 4><<<grid, kFwThreads, smem, ctx->stream>>>(P, vv, b, partial); \
+                             else spmv_fw_kernel<NV, KIND, NCHV, 8><<<grid, kFwThreads, smem, ctx->stream>>>(P, vv, b, partial);
   switch (M.patW / 4) {
-    case 1: spmv_fw_kernel<NV, KIND, 1><<<grid, kFwThreads, smem, ctx->stream>>>(P, vv, b, partial); break;
-    case 2: spmv_fw_kernel<NV, KIND, 2><<<grid, kFwThreads, smem, ctx->stream>>>(P, vv, b, partial); break;
-    case 3: spmv_fw_kernel<NV, KIND, 3><<<grid, kFwThreads, smem, ctx->stream>>>(P, vv, b, partial); break;
-    default: spmv_fw_kernel<NV, KIND, 4><<<grid, kFwThreads, smem, ctx->stream>>>(P, vv, b, partial); break;
+    case 1: SPIS_FW_LAUNCH(1) break;
+    case 2: SPIS_FW_LAUNCH(2) break;
+    case 3: SPIS_FW_LAUNCH(3) break;
+    default: SPIS_FW_LAUNCH(4) break;
   }
+#undef SPIS_FW_LAUNCH
   CU(cudaGetLastError());
   if (grid_out) *grid_out = grid;
   return SPIS_OK;
@@ -1424,6 +1430,7 @@ int spis_set_option(spis_ctx* ctx, const char* key, int64_t value) {
   else if (k == "sell_sigma") { ctx->sell_sigma = value ? 1 : 0; }
   else if (k == "spmv_multi") { ctx->spmv_multi = value ? 1 : 0; }
   else if (k == "spmv_dual") { ctx->spmv_dual = value ? 1 : 0; }
+  else if (k == "spmv_fw_rows") { REQUIRE(value == 4 || value == 8, "spmv_fw_rows must be 4 or 8"); ctx->spmv_fw_rows = (int)value; }
   else if (k == "spmv_sellw") { REQUIRE(value >= 0 && value <= 7, "spmv_sellw is a bit mask 0..7"); ctx->spmv_sellw = (int)value; }
   else if (k == "spmv_fw") { REQUIRE(value >= 0 && value <= 7, "spmv_fw is a bit mask 0..7"); ctx->spmv_fw = (int)value; }
   else if (k == "spmv_dual_ctas_per_sm") { REQUIRE(value >= 0 && value <= 16, "spmv_dual_ctas_per_sm must be 0..16"); ctx->spmv_dual_ctas_per_sm = (int)value; }

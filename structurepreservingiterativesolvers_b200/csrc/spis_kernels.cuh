@@ -2011,7 +2011,7 @@ spmv_sell_dual_kernel(const int64_t* __restrict__ slice_off, const uint8_t* __re
 // Per-row summation order is that of the row-pattern kernels (even / odd positions into two accumulators): same bits.
 // ------------------------------------------------------------------------------------------
 constexpr int kFwThreads = 256;
-constexpr int kFwRows = 8;                 // rows per thread and tile: F * T / kFwThreads <= kFwRows
+constexpr int kFwRows = 8;                 // rows per thread and tile at most: F * T / kFwThreads <= ROWS (template: 4 or 8)
 constexpr int kFwMaxTable = 1024;          // stencil table entries kept in shared memory
 constexpr int kFwMaxPat = 256;
 
@@ -2082,8 +2082,8 @@ __device__ __noinline__ void fw_row_generic(const FwEntry* te, int len, int f, i
 // The stencil table is resolved ONCE per CTA into window coordinates per (field, stencil): rt[f][p][e] = {index of the
 // entry's x value in the staged windows relative to the row's node, value}, padded to NCH chunks of four entries with
 // zero values, so that a row is NCH * 4 x (LDS.128 of the entry, one LDS.64 per vector, one fma per vector), unrolled.
-template <int NV, int KIND, int NCH>
-__global__ void __launch_bounds__(kFwThreads, 2)
+template <int NV, int KIND, int NCH, int ROWS>
+__global__ void __launch_bounds__(kFwThreads, ROWS == 4 ? 3 : 2)
 spmv_fw_kernel(const __grid_constant__ FwArgs P, const __grid_constant__ FwVecs Vv, const double* __restrict__ b,
                double* __restrict__ partial) {
   extern __shared__ __align__(128) unsigned char fwraw[];
@@ -2155,12 +2155,12 @@ spmv_fw_kernel(const __grid_constant__ FwArgs P, const __grid_constant__ FwVecs 
       }
   };
   // this thread's rows of a tile: slot r -> field f = r >> kts, node a0 + tid + (r & (KT - 1)) * kFwThreads
-  int pid_n[kFwRows];
-  double b_n[kFwRows];
+  int pid_n[ROWS];
+  double b_n[ROWS];
   auto fetch = [&](int tile) {
     const int a0 = tile * T;
 #pragma unroll
-    for (int r = 0; r < kFwRows; ++r) {
+    for (int r = 0; r < ROWS; ++r) {
       const int f = r >> kts, kk = r - (f << kts);
       const int a = a0 + tid + kk * kFwThreads;
       const bool on = f < F && a < N && a < a0 + T;
@@ -2178,10 +2178,10 @@ spmv_fw_kernel(const __grid_constant__ FwArgs P, const __grid_constant__ FwVecs 
   }
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
     const int stage = k & 1;
-    int pidv[kFwRows];
-    double bv[kFwRows];
+    int pidv[ROWS];
+    double bv[ROWS];
 #pragma unroll
-    for (int r = 0; r < kFwRows; ++r) { pidv[r] = pid_n[r]; bv[r] = b_n[r]; }
+    for (int r = 0; r < ROWS; ++r) { pidv[r] = pid_n[r]; bv[r] = b_n[r]; }
     if (tile + (int)gridDim.x < ntiles) {
       if (tid == 0) issue(tile + gridDim.x, stage ^ 1);
       fetch(tile + gridDim.x);                         // in flight while this tile is computed
@@ -2190,7 +2190,7 @@ spmv_fw_kernel(const __grid_constant__ FwArgs P, const __grid_constant__ FwVecs 
     mbar_wait(full + stage, (uint32_t)((k >> 1) & 1));
     const double* wst = win + (size_t)stage * stage_doubles;
 #pragma unroll
-    for (int r = 0; r < kFwRows; ++r) {
+    for (int r = 0; r < ROWS; ++r) {
       const int p = pidv[r];
       if (p < 0) continue;
       const int f = r >> kts, kk = r - (f << kts);

@@ -1,15 +1,16 @@
 #!/usr/bin/env python
-"""profiles/launches_r1_<workload>.csv (ncu launch list with dram bytes) -> profiles/traffic_r1.json:
+"""profiles/launches_r2_<workload>.csv (ncu launch list with dram bytes) -> profiles/traffic_r2.json:
 measured DRAM bytes per launch of every kernel class of bench.py's `kernels` object."""
 import collections, csv, json, os, re, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CLASS = [("spmv_pattern_multi", "spmv_aux"), ("spmv_sell_multi", "spmv_aux"), ("spmv_", "spmv"), ("reduce_partials", "spmv"),
          ("mdotm_kernel", "mdot"), ("mdot_kernel", "mdot"), ("mdot_reg_kernel", "mdot"),
-         ("lincomb_kernel", "lincomb"), ("lincomb2_kernel", "lincomb"), ("orth_mid_kernel", "orthmid"), ("scale_kernel", "scale")]
+         ("lincomb_kernel", "lincomb"), ("lincomb2_kernel", "lincomb"), ("lincomb2n_kernel", "lincomb"), ("orth_mid_kernel", "orthmid"),
+         ("scale_kernel", "scale"), ("hess_kernel", "other"), ("pipe_init_kernel", "other")]
 MODE = re.compile(r"kernel<\(?(?:int\))?\s*(\d)")
 out = {}
 for wl, nrows in (("lkdv", 10_000_050), ("swe", 10_002_828)):
-    path = os.path.join(ROOT, "profiles", f"launches_r1_{wl}.csv")
+    path = os.path.join(ROOT, "profiles", f"launches_r2_{wl}.csv")
     rows = [r for r in csv.reader(open(path)) if len(r) > 10]
     hdr, rows = rows[0], rows[1:]
     ik, im, iv, iid = (hdr.index(k) for k in ("Kernel Name", "Metric Name", "Metric Value", "ID"))
@@ -38,8 +39,8 @@ for wl, nrows in (("lkdv", 10_000_050), ("swe", 10_002_828)):
     out[wl] = {c: {"launches": a["launches"], "traffic_bytes_per_launch": a["dram"] / a["launches"],
                    "ncu_us_per_launch": a["ns"] / a["launches"] * 1e-3, "share_of_kernel_time": a["ns"] / tot,
                    "dram_gbs_under_ncu": a["dram"] / a["ns"]} for c, a in agg.items()}
-    out[wl]["_source"] = f"profiles/launches_r1_{wl}.csv (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none; one solve)"
-json.dump(out, open(os.path.join(ROOT, "profiles", "traffic_r1.json"), "w"), indent=1)
+    out[wl]["_source"] = f"profiles/launches_r2_{wl}.csv (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none; one solve)"
+json.dump(out, open(os.path.join(ROOT, "profiles", "traffic_r2.json"), "w"), indent=1)
 for wl in out:
     for c, v in out[wl].items():
         if c[0] != "_":
