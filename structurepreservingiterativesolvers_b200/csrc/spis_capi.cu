@@ -124,7 +124,8 @@ struct spis_ctx {
                                 // per solve against 6.63, lkdv forced to SELL 5.78 against 5.16: an LDS crosses the same data pipe as an
                                 // L1 hit, the TMA writes of the windows add to it, and two CTAs of 8 consumer warps hide the latency of
                                 // the matrix stream worse than four to five CTAs of the plain kernels.
-  int spmv_fw_rows = 4;         // spmv_fw_kernel: rows per thread and tile (4: narrow tiles, three CTAs per SM; 8: wide tiles, two)
+  int hess_async = 1;           // pipelined loop: the Givens / least-squares kernel runs beside the normalising sweep
+  int spmv_fw_rows = 8;         // spmv_fw_kernel: rows per thread and tile (4: narrow tiles, three CTAs per SM; 8: wide tiles, two)
   int spmv_fw = 1;              // row patterns on field-blocked systems, x windows staged in shared memory by TMA (spmv_fw_kernel).
                                 // Bit mask: 1 = the dual product of an Arnoldi step, 2 = single products, 4 = grouped constraint products.
                                 // Measured on the 1e7 lkdv operator (tools/tune_fw.py): dual 97 us against 109 us for the L1-gather kernel
@@ -164,6 +165,7 @@ struct spis_ctx {
   double* h_y = nullptr;        // pinned K
   double* h_cout = nullptr;     // pinned kmax*2K
   cudaEvent_t ev_arnoldi = nullptr;
+  cudaStream_t hstream = nullptr; cudaEvent_t ev_orth = nullptr, ev_hess = nullptr;   // hess_kernel runs beside the normalising sweep
   cudaEvent_t ev_resid = nullptr; double* h_resid = nullptr; bool resid_inflight = false;   // pinned residual slot of its own
   // pipelined loop (spis_pipe_begin / spis_step_enqueue): Givens state, least-squares coefficients and the phase word on
   // the device, per-step and per-residual records in mapped page-locked memory (rings of kRecSlots)
@@ -1310,6 +1312,9 @@ int spis_ctx_create(int device, int64_t n, int64_t n_halo, int k_max, void* stre
   CCU(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
   CCU(cudaEventCreateWithFlags(&c->ev_arnoldi, cudaEventDisableTiming));
   CCU(cudaEventCreateWithFlags(&c->ev_resid, cudaEventDisableTiming));
+  { int lo = 0, hi = 0; CCU(cudaDeviceGetStreamPriorityRange(&lo, &hi)); CCU(cudaStreamCreateWithPriority(&c->hstream, cudaStreamNonBlocking, hi)); }
+  CCU(cudaEventCreateWithFlags(&c->ev_orth, cudaEventDisableTiming));
+  CCU(cudaEventCreateWithFlags(&c->ev_hess, cudaEventDisableTiming));
   CCU(cudaEventCreate(&c->ev_t0));
   CCU(cudaEventCreate(&c->ev_t1));
   pt.mark("streams + events");
@@ -1401,6 +1406,9 @@ int spis_ctx_destroy(spis_ctx* ctx) {
   spis_pinned_free(ctx->h_rec);
   if (ctx->ev_arnoldi) cudaEventDestroy(ctx->ev_arnoldi);
   if (ctx->ev_resid) cudaEventDestroy(ctx->ev_resid);
+  if (ctx->ev_orth) cudaEventDestroy(ctx->ev_orth);
+  if (ctx->ev_hess) cudaEventDestroy(ctx->ev_hess);
+  if (ctx->hstream) cudaStreamDestroy(ctx->hstream);
   if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
   if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
   if (ctx->aux) cudaStreamDestroy(ctx->aux);
@@ -1430,6 +1438,7 @@ int spis_set_option(spis_ctx* ctx, const char* key, int64_t value) {
   else if (k == "sell_sigma") { ctx->sell_sigma = value ? 1 : 0; }
   else if (k == "spmv_multi") { ctx->spmv_multi = value ? 1 : 0; }
   else if (k == "spmv_dual") { ctx->spmv_dual = value ? 1 : 0; }
+  else if (k == "hess_async") ctx->hess_async = value != 0;
   else if (k == "spmv_fw_rows") { REQUIRE(value == 4 || value == 8, "spmv_fw_rows must be 4 or 8"); ctx->spmv_fw_rows = (int)value; }
   else if (k == "spmv_sellw") { REQUIRE(value >= 0 && value <= 7, "spmv_sellw is a bit mask 0..7"); ctx->spmv_sellw = (int)value; }
   else if (k == "spmv_fw") { REQUIRE(value >= 0 && value <= 7, "spmv_fw is a bit mask 0..7"); ctx->spmv_fw = (int)value; }
@@ -2201,9 +2210,15 @@ int spis_step_enqueue(spis_ctx* ctx, int j, int flags, int64_t* ticket_out) {
     const int rcache = m <= 70 ? (m + 1) / 2 * 2 : 0;
     const size_t smem = (size_t)(4 * K + 4 + rcache * rcache) * sizeof(double);
     const unsigned long long* errw = ctx->xactive ? reinterpret_cast<const unsigned long long*>(ctx->xbuf + ctx->xv.flags_off()) + 4 * ctx->xv.world : nullptr;
-    hess_kernel<<<1, 32, smem, ctx->stream>>>(j, st, h1, h2, scal, ctx->d_ydev + (size_t)(j & 1) * K, ctx->d_phase,
-                                               step_rec_dev(ctx, j), sw, K, errw, rcache);
+    // The sweep below needs nothing from this kernel (it forms h[j+1,j] itself, and takes y_{j-1} from the previous
+    // step), so the ~10 us of sequential Givens arithmetic run beside it on a stream of their own; the main stream
+    // joins again after the sweep, which orders everything queued later behind this step's state, y_j and phase word.
+    cudaStream_t hs = ctx->hess_async ? ctx->hstream : ctx->stream;
+    if (ctx->hess_async) { CU(cudaEventRecord(ctx->ev_orth, ctx->stream)); CU(cudaStreamWaitEvent(hs, ctx->ev_orth, 0)); }
+    hess_kernel<<<1, 32, smem, hs>>>(j, st, h1, h2, scal, ctx->d_ydev + (size_t)(j & 1) * K, ctx->d_phase,
+                                     step_rec_dev(ctx, j), sw, K, errw, rcache);
     CU(cudaGetLastError());
+    if (ctx->hess_async) CU(cudaEventRecord(ctx->ev_hess, hs));
     ctx->prof_launch[SPIS_PROF_OTHER] += 1;
   }
   // q[j+1] = (w' - V h2) / h[j+1,j]  (+ x_{j-1} = x0 + Z y_{j-1})  (solvers.py:195-198, 287)
@@ -2214,13 +2229,14 @@ int spis_step_enqueue(spis_ctx* ctx, int j, int flags, int64_t* ticket_out) {
     const int mB = (nopre && want_it && j >= 1) ? j : 0;
     const bool fusej = ctx->pre_kind == SPIS_PRE_JACOBI && ctx->fuse_jacobi && ctx->pre_diag && (j + 1 < ctx->kmax);
     TRY(prof_begin(ctx, SPIS_PROF_LINCOMB, (double)(m + 2 + (mB ? 1 : 0) + ((mB && !ctx->x0_is_zero) ? 1 : 0) + (fusej ? 2 : 0)) * 8.0 * (double)ctx->n));
-    lincomb2n_kernel<4><<<grid, kThreads, smem, ctx->stream>>>(ctx->V, ctx->ld, m, h2, scal, ctx->d_ydev + (size_t)((j + 1) & 1) * K, mB,
+    lincomb2n_kernel<4><<<grid, kThreads, smem, ctx->stream>>>(ctx->V, ctx->ld, m, h2, ctx->d_ydev + (size_t)((j + 1) & 1) * K, mB,
                                                                ctx->d_phase, ctx->W, ctx->x0_is_zero ? nullptr : ctx->X0, qn, ctx->X,
                                                                fusej ? ctx->pre_diag : nullptr, fusej ? ctx->Z + (size_t)(j + 1) * ld : nullptr, ctx->n);
     CU(cudaGetLastError());
     TRY(prof_end(ctx));
     ctx->z_ready_index = fusej ? j + 1 : -1;
   }
+  if (ctx->hess_async) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_hess, 0));
   if (!nopre && want_it) {
     // preconditioned: Z is not V, the iterate x_j = x0 + Z y_j takes its own sweep (skipped once the phase word is set)
     const int64_t ntiles = (ctx->n + kTile - 1) / kTile;

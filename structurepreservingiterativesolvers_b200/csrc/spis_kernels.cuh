@@ -787,8 +787,7 @@ __device__ __forceinline__ void lincomb2n_tile(const double* __restrict__ V, int
 
 template <int IU>
 __global__ void __launch_bounds__(kThreads)
-lincomb2n_kernel(const double* __restrict__ V, int64_t ld, int m, const double* __restrict__ coefA,
-                 const double* __restrict__ norm2 /* h[j+1,j]^2, written by hess_kernel */,
+lincomb2n_kernel(const double* __restrict__ V, int64_t ld, int m, const double* __restrict__ coefA /* h2[0..m), h2[m] = ||w'||^2 */,
                  const double* __restrict__ coefB, int mB, const int* __restrict__ phase,
                  const double* baseA, const double* baseB, double* outA, double* outB,
                  const double* __restrict__ jac, double* __restrict__ znext, int64_t n) {
@@ -800,9 +799,20 @@ lincomb2n_kernel(const double* __restrict__ V, int64_t ld, int m, const double* 
     scA[i] = -coefA[i];
     scB[i] = (dob && i < mB) ? coefB[i] : 0.0;
   }
-  const double h2 = *norm2;
-  const double inv = h2 > 0.0 ? 1.0 / sqrt(h2) : 0.0;     // breakdown: q[j+1] = 0 as in the reference (solvers.py:197-198, 376-377)
+  // h[j+1,j]^2 = ||w'||^2 - |h2|^2, in exactly the arithmetic of hess_kernel (which runs beside this sweep, on its own
+  // stream, and publishes the same number to the host): lane-strided fma chains, then the butterfly
+  __shared__ double s_n2;
+  if (threadIdx.x < 32) {
+    double s2 = 0.0;
+    for (int i = threadIdx.x; i < m; i += 32) { const double bq = coefA[i]; s2 = fma(bq, bq, s2); }
+    s2 = warp_sum(s2);
+    double n2 = coefA[m] - s2;
+    if (!(n2 > 0.0)) n2 = 0.0;
+    if (threadIdx.x == 0) s_n2 = n2;
+  }
   __syncthreads();
+  const double h2 = s_n2;
+  const double inv = h2 > 0.0 ? 1.0 / sqrt(h2) : 0.0;     // breakdown: q[j+1] = 0 as in the reference (solvers.py:197-198, 376-377)
   const int64_t ntiles = (n + kTile - 1) / kTile;
   const int64_t nfull = n / kTile;
   if (dob) {

@@ -56,6 +56,7 @@ _CONFIG = {
     "dual_spmv": True,
     "lazy_sessions": 2,        # solver-created sessions kept resident for lazy dict['x'] access (the newest ones)
     "pipeline": True,          # device-resident loop (Givens update and unconstrained iterates on the GPU) with small_solver='kkt'
+    "ctx_options": {},         # raw spis_set_option pairs applied to every context a session creates (tuning / A-B runs)
 }
 _ORTH = {"cgs2": nat.ORTH_CGS2, "cgs1": nat.ORTH_CGS1, "mgs": nat.ORTH_MGS}
 _FMT = {"auto": nat.FMT_AUTO, "sell": nat.FMT_SELL, "csr": nat.FMT_CSR, "sell2": nat.FMT_SELL2, "pattern": nat.FMT_PATTERN, "selld": nat.FMT_SELLD}
@@ -202,6 +203,8 @@ class DeviceSession:
         ctx.set_option("orth", _ORTH[_opt("orth", orth)])
         ctx.set_option("spmv_format", _FMT[_opt("spmv_format", spmv_format)])
         ctx.set_option("profile", 1 if _opt("profile", profile) else 0)
+        for key, val in dict(_CONFIG.get("ctx_options") or {}).items():
+            ctx.set_option(key, val)
         if not (sps.issparse(A) or isinstance(A, np.ndarray)):
             raise TypeError("A must be a scipy.sparse matrix (or a dense array); got %r" % type(A))
         if A.shape[0] != n or A.shape[1] != n + getattr(ctx, "n_halo", 0):

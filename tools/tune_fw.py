@@ -11,10 +11,11 @@ x0 = np.zeros(d["b"].size)
 full = wrappers.lkdv.conlist(d, x0)
 cl = [full[0], full[2]]
 out = {}
-for fw in (7, 1, 0):
+for fw, rows in ((7, 4), (7, 8), (0, 8)):
     sess = solvers.DeviceSession(d["A"], d["b"], x0, 50, conlist=cl, profile=True)
     ctx = sess.ctx
     ctx.set_option("spmv_fw", fw)
+    ctx.set_option("spmv_fw_rows", rows)
     r = {"fw_fields": ctx.info("fw_fields:0")}
     for mode in (0, 1, 2):
         ms, by = ctx.bench_kernel(nat.PROF_SPMV, mode, 50)
@@ -27,6 +28,6 @@ for fw in (7, 1, 0):
     r["solve_spmv_ms"] = round(p["spmv"]["ms"], 3); r["solve_spmv_launches"] = p["spmv"]["launches"]
     r["solve_spmv_aux_ms"] = round(p["spmv_aux"]["ms"], 3); r["steps"] = info["steps"]
     r["spmv_gbs_moved"] = round(p["spmv"]["gbs_moved"], 1)
-    out[{7: "fw_all", 1: "fw_dual_only", 0: "gather"}[fw]] = r
+    out[{7: f"fw_all_rows{rows}", 0: "gather"}[fw]] = r
     sess.close()
 print(json.dumps(out, indent=1))
