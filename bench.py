@@ -472,6 +472,16 @@ def run_ours(args):
         wall_profiled = time.perf_counter() - tp0
         clk.mark_stop()
     prof = ctx.profile()
+    if args.trace_file:
+        # diagnostic: the device timeline of ONE more profiled solve on this rank (class, start ms, duration ms per launch)
+        ctx.reset_profile()
+        barrier()
+        tw = time.perf_counter()
+        solve(sess); ctx.sync()
+        tw = 1e3 * (time.perf_counter() - tw)
+        ctx.profile()
+        with open(args.trace_file + (".rank%d" % rank if world > 1 else ""), "w") as fh:
+            json.dump({"wall_ms": tw, "launches": ctx.profile_trace()}, fh)
     ctx.set_option("profile", 0)
     final_res = float(info["res"][-1])
     x_gpu, info_gpu = np.array(x, copy=True), info
@@ -733,6 +743,7 @@ def main():
     ap.add_argument("--reference-budget-s", type=float, default=240.0, help="--impl reference stops after the solve that crosses this")
     ap.add_argument("--host-loop", action="store_true", help="host-driven Krylov loop (round-1 path) instead of the device-resident one")
     ap.add_argument("--transport", default="auto", choices=["auto", "p2p", "nccl"])
+    ap.add_argument("--trace-file", default=None, help="write the per-launch device timeline of one profiled solve here (diagnostic)")
     ap.add_argument("--ctx-option", action="append", default=[], metavar="KEY=INT", help="raw device-context option for A/B runs (repeatable)")
     args = ap.parse_args()
     if args.host_loop:

@@ -305,6 +305,10 @@ int spis_get_profile_moved(spis_ctx* ctx, double* moved_out);
 /* profile mode: gaps_out[c] = milliseconds the device was idle right before the launches of class c (from the end of the
  * previous profiled kernel): where a solve waits for the host, for a copy or for another stream                       */
 int spis_get_profile_gaps(spis_ctx* ctx, double* gaps_out);
+/* profile mode: the launches resolved by the last spis_get_profile* call, in launch order -- kernel class, start (ms
+ * after the first of them) and duration; *n_out = how many there are (at most cap are written).  A diagnostic for
+ * the reference's `timing=True` question (solvers.py:300-312): where on the device timeline a solve waits for the host */
+int spis_get_profile_trace(spis_ctx* ctx, int32_t* cls_out, double* start_ms_out, double* dur_ms_out, int64_t cap, int64_t* n_out);
 /* CUDA-event stopwatch on the context's stream: device time between the two calls.      */
 int spis_timer_start(spis_ctx* ctx);
 int spis_timer_stop(spis_ctx* ctx, double* ms_out);

@@ -99,6 +99,7 @@ SIGNATURES = {
     "spis_reset_profile": (C.c_int, [_ctx]),
     "spis_get_profile_moved": (C.c_int, [_ctx, _dp]),
     "spis_get_profile_gaps": (C.c_int, [_ctx, _dp]),
+    "spis_get_profile_trace": (C.c_int, [_ctx, _ip, _dp, _dp, C.c_int64, _lp]),
     "spis_timer_start": (C.c_int, [_ctx]),
     "spis_timer_stop": (C.c_int, [_ctx, _dp]),
     "spis_op_spmv": (C.c_int, [_ctx, C.c_int, _dp, _dp]),

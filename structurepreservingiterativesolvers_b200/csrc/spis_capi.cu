@@ -151,6 +151,9 @@ struct spis_ctx {
   // vectors
   double *V = nullptr, *Z = nullptr, *W = nullptr, *T = nullptr, *R0 = nullptr, *B = nullptr, *X0 = nullptr, *X = nullptr;
   double* G = nullptr;          // 4 x ld group buffer of the constraint stage (lazy)
+  double* GW = nullptr; int gw_cols = 0;   // M Z[c0..m) of the one-pass constraint reduction (gram_kernel), gw_cols x ld (lazy)
+  double* d_gpartial = nullptr; unsigned int* d_gcounter = nullptr;
+  int gram = 1;                 // constraint stage: 8 or more new columns of a symmetric M go through gram_kernel
   double* pre_diag = nullptr;
   double* pre_blocks = nullptr; int pre_bs = 0; int64_t pre_nblk = 0, pre_sb = 0, pre_sf = 0;
   int pre_kind = SPIS_PRE_NONE;
@@ -195,6 +198,8 @@ struct spis_ctx {
   int32_t *d_dest_rank = nullptr, *d_dest_off = nullptr, *d_send_to = nullptr, *d_recv_from = nullptr;
   // profiling
   std::vector<ProfRec> recs; std::vector<cudaEvent_t> evpool;
+  struct TraceRec { int cls; double start_ms, dur_ms; };
+  std::vector<TraceRec> trace;   // profile mode: per-launch timeline of the batch resolved last (spis_get_profile_trace)
   std::vector<DevBlock> owned;   // device blocks currently held by this context
   std::vector<AsyncJob*> jobs;   // native helper threads staging constraint data (joined by spis_constraint_setup_wait)
   double prof_ms[SPIS_PROF_CLASSES] = {0}; double prof_bytes[SPIS_PROF_CLASSES] = {0}; int64_t prof_launch[SPIS_PROF_CLASSES] = {0};
@@ -341,11 +346,17 @@ int prof_end(spis_ctx* ctx) {
 int prof_resolve(spis_ctx* ctx) {
   if (ctx->recs.empty()) return SPIS_OK;
   CU(cudaStreamSynchronize(ctx->stream));
+  ctx->trace.clear();
   for (size_t i = 0; i < ctx->recs.size(); ++i) {
     auto& r = ctx->recs[i];
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, r.e0, r.e1));
     ctx->prof_ms[r.cls] += ms;
+    if (ctx->recs.size() <= 100000) {
+      float t0 = 0.f;
+      if (i > 0 && cudaEventElapsedTime(&t0, ctx->recs[0].e0, r.e0) != cudaSuccess) { cudaGetLastError(); t0 = 0.f; }
+      ctx->trace.push_back({r.cls, (double)t0, (double)ms});
+    }
     if (i > 0) {
       float gap = 0.f;
       if (cudaEventElapsedTime(&gap, ctx->recs[i - 1].e1, r.e0) == cudaSuccess && gap > 0.f) ctx->prof_gap_ms[r.cls] += gap;
@@ -484,6 +495,42 @@ int launch_mdotm(spis_ctx* ctx, int nw, const double* V, int m, const double* ex
   CU(cudaGetLastError());
   TRY(prof_end(ctx));
   return do_allreduce(ctx, out, nout);
+}
+
+// out[j * ra + i] = row_i . B_j for rows = A[0..ma) (+ extra) and ALL mb columns B_j = B + j*ldb, one pass over A per
+// 24 columns (gram_kernel); tri: only entries with i <= c0 + j (and the extra row) are needed.  No cross-rank
+// reduction here: the caller batches it (spis_constraint_terms).
+bool gram_applicable(spis_ctx* ctx, int ma, bool extra) { return ctx->gram && (ma + (extra ? 1 : 0) + 7) / 8 <= kGramMaxIB; }
+int launch_gram(spis_ctx* ctx, const double* A, int ma, const double* extra, const double* B, int mb, int c0, int tri,
+                double* out, int ra) {
+  const int nib_all = (ma + (extra ? 1 : 0) + 7) / 8;
+  REQUIRE(nib_all >= 1 && nib_all <= kGramMaxIB && ra >= nib_all * 8 - 7, "gram: %d rows not supported", ma);
+  const size_t pmax = (size_t)2 * ctx->nsm * kGramMaxIB * kGramJB * 64;
+  if (!ctx->d_gpartial) { TRY(dalloc(ctx, &ctx->d_gpartial, pmax, false)); TRY(dalloc(ctx, &ctx->d_gcounter, 64)); }
+  for (int j0 = 0; j0 < mb; j0 += 8 * kGramJB) {
+    const int mbp = std::min(mb - j0, 8 * kGramJB);
+    // rows this launch needs: i <= c0 + j0 + mbp - 1 (the extra row keeps every tile row alive)
+    int nib = nib_all;
+    int rows_a = ma;
+    if (tri && !extra) { rows_a = std::min(ma, c0 + j0 + mbp); nib = (rows_a + 7) / 8; }
+    GramArgs g{A, ctx->ld, rows_a, extra, B + (size_t)j0 * ctx->ld, ctx->ld, mbp, c0 + j0, tri, ctx->n,
+               ctx->d_gpartial, ctx->d_gcounter, out + (size_t)j0 * ra, ra};
+    const int grid = ctx->nsm * (nib <= 3 ? 2 : 1);
+    const size_t smem = (size_t)nib * kGramJB * 64 * sizeof(double);
+    TRY(prof_begin(ctx, SPIS_PROF_MDOT, (double)(rows_a + (extra ? 1 : 0) + mbp) * 8.0 * (double)ctx->n));
+    switch (nib) {
+      case 1: gram_kernel<1><<<grid, kGramThreads, smem, ctx->stream>>>(g); break;
+      case 2: gram_kernel<2><<<grid, kGramThreads, smem, ctx->stream>>>(g); break;
+      case 3: gram_kernel<3><<<grid, kGramThreads, smem, ctx->stream>>>(g); break;
+      case 4: gram_kernel<4><<<grid, kGramThreads, smem, ctx->stream>>>(g); break;
+      case 5: gram_kernel<5><<<grid, kGramThreads, smem, ctx->stream>>>(g); break;
+      case 6: gram_kernel<6><<<grid, kGramThreads, smem, ctx->stream>>>(g); break;
+      default: gram_kernel<7><<<grid, kGramThreads, smem, ctx->stream>>>(g); break;
+    }
+    CU(cudaGetLastError());
+    TRY(prof_end(ctx));
+  }
+  return SPIS_OK;
 }
 
 int launch_lincomb(spis_ctx* ctx, const double* V, int m, const double* coef, const double* coef2,
@@ -1386,7 +1433,7 @@ int spis_ctx_destroy(spis_ctx* ctx) {
     for (auto& M : ctx->mats) free_matrix(ctx, M);
     for (auto& c : ctx->cons) { dfree(ctx, c.v); dfree(ctx, c.MZ); }
     dfree(ctx, ctx->V); dfree(ctx, ctx->Z); dfree(ctx, ctx->W); dfree(ctx, ctx->T); dfree(ctx, ctx->R0);
-    dfree(ctx, ctx->B); dfree(ctx, ctx->X0); dfree(ctx, ctx->X); dfree(ctx, ctx->G); dfree(ctx, ctx->pre_diag); dfree(ctx, ctx->pre_blocks);
+    dfree(ctx, ctx->B); dfree(ctx, ctx->X0); dfree(ctx, ctx->X); dfree(ctx, ctx->G); dfree(ctx, ctx->GW); dfree(ctx, ctx->d_gpartial); dfree(ctx, ctx->d_gcounter); dfree(ctx, ctx->pre_diag); dfree(ctx, ctx->pre_blocks);
     dfree(ctx, ctx->d_send_idx); dfree(ctx, ctx->d_send);
     dfree(ctx, ctx->d_dest_rank); dfree(ctx, ctx->d_dest_off); dfree(ctx, ctx->d_send_to); dfree(ctx, ctx->d_recv_from);
     dfree(ctx, ctx->d_small); dfree(ctx, ctx->d_y); dfree(ctx, ctx->d_cout); dfree(ctx, ctx->d_partial); dfree(ctx, ctx->d_counter);
@@ -1439,6 +1486,7 @@ int spis_set_option(spis_ctx* ctx, const char* key, int64_t value) {
   else if (k == "spmv_multi") { ctx->spmv_multi = value ? 1 : 0; }
   else if (k == "spmv_dual") { ctx->spmv_dual = value ? 1 : 0; }
   else if (k == "hess_async") ctx->hess_async = value != 0;
+  else if (k == "gram") ctx->gram = value != 0;
   else if (k == "spmv_fw_rows") { REQUIRE(value == 4 || value == 8, "spmv_fw_rows must be 4 or 8"); ctx->spmv_fw_rows = (int)value; }
   else if (k == "spmv_sellw") { REQUIRE(value >= 0 && value <= 7, "spmv_sellw is a bit mask 0..7"); ctx->spmv_sellw = (int)value; }
   else if (k == "spmv_fw") { REQUIRE(value >= 0 && value <= 7, "spmv_fw is a bit mask 0..7"); ctx->spmv_fw = (int)value; }
@@ -2484,7 +2532,36 @@ int spis_constraint_terms(spis_ctx* ctx, int c, int m, double* term0, double* te
     std::vector<Group> groups;
     ctx->defer_allreduce = true;
     int rc = SPIS_OK;
-    if (sym) {
+    // many new columns of a symmetric M (the switch to the constrained phase): M Z[c0..m) is kept, and ONE pass over
+    // Z and M Z gives every entry (gram_kernel) instead of one pass over Z per four columns
+    const double* gx = x0nz ? ctx->X0 : nullptr;
+    bool use_gram = sym && (m - c0) >= 8 && gram_applicable(ctx, m, gx != nullptr);
+    int gram_ra = 0;
+    if (use_gram) {
+      const int want = (m - c0 + 7) / 8 * 8;
+      if (ctx->gw_cols < want) {
+        if (ctx->GW) dfree(ctx, ctx->GW);
+        ctx->gw_cols = 0;
+        const int rcw = dalloc(ctx, &ctx->GW, (size_t)want * ld, false);
+        if (rcw == SPIS_OK) ctx->gw_cols = want;
+        else if (rcw == SPIS_E_NOMEM) { ctx->err[0] = 0; use_gram = false; }     // no room for M Z: four columns at a time
+        else { ctx->defer_allreduce = false; return rcw; }
+      }
+    }
+    if (use_gram) {
+      gram_ra = (m + (gx ? 1 : 0) + 7) / 8 * 8;
+      for (int g0 = c0; g0 < m && rc == SPIS_OK;) {
+        const int left = m - g0;
+        const int nw = left >= 4 ? 4 : left >= 2 ? 2 : 1;
+        double* dst = ctx->GW + (size_t)(g0 - c0) * ld;
+        if (nw == 1) rc = launch_spmv(ctx, C.slot, 0, Zb + (size_t)g0 * ld, nullptr, dst, nullptr);
+        else rc = launch_spmv_multi(ctx, C.slot, nw, Zb + (size_t)g0 * ld, (int64_t)ld, dst, (int64_t)ld);
+        g0 += nw;
+      }
+      if (rc == SPIS_OK) rc = launch_gram(ctx, Zb, m, gx, ctx->GW, m - c0, c0, 1, ctx->d_cout + (size_t)c0 * 2 * K, gram_ra);
+      if (rc == SPIS_OK && C.v)
+        rc = launch_mdot(ctx, Zb + (size_t)c0 * ld, m - c0, nullptr, 0, C.v, ctx->d_cout + (size_t)(m - 1) * 2 * K + K);
+    } else if (sym) {
       // symmetric M: groups of up to 4 new columns; M z_col lives only in the group buffer; one
       // pass over Z[0..g1) serves the whole group (each basis row is read once per group)
       for (int g0 = c0; g0 < m && rc == SPIS_OK;) {
@@ -2531,7 +2608,21 @@ int spis_constraint_terms(spis_ctx* ctx, int c, int m, double* term0, double* te
     // one all-reduce for every dot block of this call (row-sharded runs)
     TRY(do_allreduce(ctx, ctx->d_cout + (size_t)c0 * 2 * K, (int64_t)(m - c0) * 2 * K, true));
     TRY(d2h(ctx, ctx->h_cout + (size_t)c0 * 2 * K, ctx->d_cout + (size_t)c0 * 2 * K, (size_t)(m - c0) * 2 * K * sizeof(double)));
-    if (sym) {
+    if (use_gram) {
+      const double* vz = ctx->h_cout + (size_t)(m - 1) * 2 * K + K;      // v.z_col, col = c0 .. m-1
+      const double* base = ctx->h_cout + (size_t)c0 * 2 * K;
+      for (int col = c0; col < m; ++col) {
+        const double* oA = base + (size_t)(col - c0) * gram_ra;
+        for (int i = 0; i <= col; ++i) {
+          C.T2[(size_t)i * km + col] = 0.5 * oA[i];
+          C.T2[(size_t)col * km + i] = 0.5 * oA[i];
+        }
+        double t1 = 0.0;
+        if (x0nz) t1 += oA[m];
+        if (C.v) t1 += vz[col - c0];
+        C.T1[col] = t1;
+      }
+    } else if (sym) {
       const double* vz = ctx->h_cout + (size_t)(m - 1) * 2 * K + K;      // v.z_col, col = c0 .. m-1
       for (const Group& g : groups) {
         const int nw = g.g1 - g.g0;
@@ -2885,6 +2976,22 @@ int spis_get_profile_gaps(spis_ctx* ctx, double* gaps_out) {
   CU(cudaSetDevice(ctx->device));
   TRY(prof_resolve(ctx));
   for (int i = 0; i < SPIS_PROF_CLASSES; ++i) gaps_out[i] = ctx->prof_gap_ms[i];
+  return SPIS_OK;
+}
+
+// profile mode: the launches resolved by the last spis_get_profile / _gaps call, in launch order -- class, start (ms
+// after the first of them) and duration.  A diagnostic: where on the timeline the device waits for the host.
+int spis_get_profile_trace(spis_ctx* ctx, int32_t* cls_out, double* start_ms_out, double* dur_ms_out, int64_t cap, int64_t* n_out) {
+  if (!ctx || !n_out) return SPIS_E_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  if (!ctx->recs.empty()) TRY(prof_resolve(ctx));
+  const int64_t n = (int64_t)ctx->trace.size();
+  *n_out = n;
+  for (int64_t i = 0; i < n && i < cap; ++i) {
+    if (cls_out) cls_out[i] = ctx->trace[i].cls;
+    if (start_ms_out) start_ms_out[i] = ctx->trace[i].start_ms;
+    if (dur_ms_out) dur_ms_out[i] = ctx->trace[i].dur_ms;
+  }
   return SPIS_OK;
 }
 

@@ -829,6 +829,153 @@ lincomb2n_kernel(const double* __restrict__ V, int64_t ld, int m, const double* 
 }
 
 // ------------------------------------------------------------------------------------------
+// K5g, the constraint reduction in ONE pass: G = A^T B for two tall blocks of vectors, A = the Krylov basis Z[0..ma)
+// (+ optionally x0 as one more row) and B = M Z[c0..c0+mb), i.e. every entry of term2 = Z^T M Z and x0.MZ
+// (solvers.py:33-36) that the switch to the constrained phase needs.  mdotm_kernel serves four columns of B per pass
+// over A, so the basis is read (m - c0)/4 times (108 vector reads for m = 21: 1.7 of the 17.6 ms of the headline
+// solve); here each vector of A and of B is read once per group of 24 columns.  That needs a 24 x 8*NIB block of
+// accumulators per thread group, which only the FP64 tensor-core fragments provide: mma.sync m8n8k4 keeps an 8 x 8
+// tile of doubles in two registers per lane (a warp holds up to 21 tiles here).  The long dimension n is the mma's k;
+// the sum over k does not care which row sits in which k slot as long as A and B agree, so lane (g, t) loads four
+// CONSECUTIVE rows of vector g (two 16-byte loads; a quad covers one 128-byte line) and the four mma's of a chunk
+// take element 0..3 of every lane.  3 flop/byte at m = 24: 23 of the 45 TFLOP/s of DMMA when HBM-bound, and the
+// symmetric case (tri = 1: only tiles that touch the upper triangle are computed) needs two thirds of that.
+// Deterministic: fixed chunk -> warp map, warps of a CTA summed in order, CTAs summed in order by the last CTA.
+// ------------------------------------------------------------------------------------------
+constexpr int kGramThreads = 256;
+constexpr int kGramJB = 3;                     // column tiles (of 8) per launch
+constexpr int kGramMaxIB = 7;                  // row tiles: up to 56 rows of A (kmax = 50, + x0)
+
+struct GramArgs {
+  const double* A; int64_t lda; int ma;        // rows 0 .. ma-1
+  const double* extra;                         // row ma (x0), or null
+  const double* B; int64_t ldb; int mb;        // the columns of this launch
+  int c0;                                      // global index of column 0 (triangle test: row i is needed for column c iff i <= c)
+  int tri;
+  int64_t n;
+  double* partial; unsigned int* counter;
+  double* out; int ra;                         // out[j * ra + i]
+};
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void gram_load4(const double* __restrict__ v, int64_t r, int64_t n, bool full, double (&o)[4]) {
+  if (v == nullptr) { o[0] = o[1] = o[2] = o[3] = 0.0; return; }
+  if (full) {
+    const double2 a = ld_stream(v + r), b = ld_stream(v + r + 2);
+    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[e] = (r + e < n) ? __ldcs(v + r + e) : 0.0;
+  }
+}
+
+template <int NIB>
+__global__ void __launch_bounds__(kGramThreads, NIB <= 3 ? 2 : 1)
+gram_kernel(GramArgs g) {
+  extern __shared__ double gsm[];              // [NIB * kGramJB * 64]
+  __shared__ int s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gq = lane >> 2, t = lane & 3;
+  constexpr int NW = kGramThreads / 32;
+  const int njb = (g.mb + 7) / 8;              // <= kGramJB
+  // which tiles are computed (uniform)
+  const int xb = g.extra ? g.ma / 8 : -1;      // the tile row holding x0
+  unsigned need = 0;
+#pragma unroll
+  for (int ib = 0; ib < NIB; ++ib)
+#pragma unroll
+    for (int jb = 0; jb < kGramJB; ++jb)
+      if (jb < njb && (!g.tri || ib * 8 <= g.c0 + jb * 8 + 7 || ib == xb)) need |= 1u << (ib * kGramJB + jb);
+  unsigned need_row = 0;
+#pragma unroll
+  for (int ib = 0; ib < NIB; ++ib) if ((need >> (ib * kGramJB)) & 7u) need_row |= 1u << ib;
+  // this lane's vectors
+  const double* pa[NIB];
+#pragma unroll
+  for (int ib = 0; ib < NIB; ++ib) {
+    const int vi = ib * 8 + gq;
+    pa[ib] = !((need_row >> ib) & 1u) ? nullptr : vi < g.ma ? g.A + (size_t)vi * g.lda : (vi == g.ma ? g.extra : nullptr);
+  }
+  const double* pb[kGramJB];
+#pragma unroll
+  for (int jb = 0; jb < kGramJB; ++jb) {
+    const int vj = jb * 8 + gq;
+    pb[jb] = vj < g.mb ? g.B + (size_t)vj * g.ldb : nullptr;
+  }
+  double acc[NIB][kGramJB][2];
+#pragma unroll
+  for (int ib = 0; ib < NIB; ++ib)
+#pragma unroll
+    for (int jb = 0; jb < kGramJB; ++jb) acc[ib][jb][0] = acc[ib][jb][1] = 0.0;
+  const int64_t nchunks = (g.n + 15) / 16;
+  const int64_t W = (int64_t)gridDim.x * NW;
+  for (int64_t c = (int64_t)blockIdx.x * NW + warp; c < nchunks; c += W) {
+    const int64_t r = c * 16 + 4 * t;
+    const bool full = c * 16 + 16 <= g.n;
+    double av[NIB][4], bv[kGramJB][4];
+#pragma unroll
+    for (int jb = 0; jb < kGramJB; ++jb) gram_load4(pb[jb], r, g.n, full, bv[jb]);
+#pragma unroll
+    for (int ib = 0; ib < NIB; ++ib) gram_load4(pa[ib], r, g.n, full, av[ib]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int ib = 0; ib < NIB; ++ib)
+#pragma unroll
+        for (int jb = 0; jb < kGramJB; ++jb)
+          if ((need >> (ib * kGramJB + jb)) & 1u) dmma884(acc[ib][jb][0], acc[ib][jb][1], av[ib][k], bv[jb][k]);
+  }
+  // CTA: warps in order
+  for (int wv = 0; wv < NW; ++wv) {
+    if (warp == wv) {
+#pragma unroll
+      for (int ib = 0; ib < NIB; ++ib)
+#pragma unroll
+        for (int jb = 0; jb < kGramJB; ++jb) {
+          double* d = gsm + (ib * kGramJB + jb) * 64 + gq * 8 + 2 * t;
+          if (wv == 0) { d[0] = acc[ib][jb][0]; d[1] = acc[ib][jb][1]; }
+          else { d[0] += acc[ib][jb][0]; d[1] += acc[ib][jb][1]; }
+        }
+    }
+    __syncthreads();
+  }
+  constexpr int NOUT = NIB * kGramJB * 64;
+  double* mine = g.partial + (size_t)blockIdx.x * NOUT;
+  for (int i = threadIdx.x; i < NOUT; i += kGramThreads) mine[i] = gsm[i];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(g.counter, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int rows = g.ma + (g.extra ? 1 : 0);
+  for (int i = threadIdx.x; i < NOUT; i += kGramThreads) {
+    const int blk = i >> 6, il = (i >> 3) & 7, jl = i & 7;
+    const int ib = blk / kGramJB, jb = blk - ib * kGramJB;
+    const int row = ib * 8 + il, col = jb * 8 + jl;
+    if (row >= rows || col >= g.mb) continue;
+    double sum = 0.0;
+    if ((need >> blk) & 1u) {
+      const double* src = g.partial + i;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      unsigned int b = 0;
+      for (; b + 4 <= gridDim.x; b += 4) {
+        s0 += __ldcg(src + (size_t)(b + 0) * NOUT); s1 += __ldcg(src + (size_t)(b + 1) * NOUT);
+        s2 += __ldcg(src + (size_t)(b + 2) * NOUT); s3 += __ldcg(src + (size_t)(b + 3) * NOUT);
+      }
+      for (; b < gridDim.x; ++b) s0 += __ldcg(src + (size_t)b * NOUT);
+      sum = (s0 + s1) + (s2 + s3);
+    }
+    g.out[(size_t)col * g.ra + row] = sum;
+  }
+  if (threadIdx.x == 0) *g.counter = 0u;
+}
+
+// ------------------------------------------------------------------------------------------
 // H1 on the device: the Givens least-squares update of the Hessenberg matrix (solvers.py:113, and the unconstrained
 // minimisation of solvers.py:231-235, whose minimiser is the least-squares solution).  north_star keeps "the Givens
 // least-squares update" on the host; it stays there as the reference semantics (smallsolve.py), but a host round trip

@@ -367,6 +367,17 @@ class KrylovContext:
                          "idle_before_ms": float(gp[i])}
         return out
 
+    def profile_trace(self):
+        """Profile mode: [(class name, start ms, duration ms)] of the launches the last profile() call resolved."""
+        self._live()
+        n = C.c_int64(0)
+        self._check(self._lib.spis_get_profile_trace(self._h, None, None, None, 0, C.byref(n)))
+        cls = np.zeros(max(n.value, 1), dtype=np.int32)
+        t0 = np.zeros(max(n.value, 1)); dt = np.zeros(max(n.value, 1))
+        self._check(self._lib.spis_get_profile_trace(self._h, cls.ctypes.data_as(C.POINTER(C.c_int32)), nat.dptr(t0), nat.dptr(dt),
+                                                     n.value, C.byref(n)))
+        return [(nat.PROF_NAMES[int(c)], float(a), float(b)) for c, a, b in zip(cls[:n.value], t0[:n.value], dt[:n.value])]
+
     def timer_start(self):
         self._check(self._lib.spis_timer_start(self._h))
 

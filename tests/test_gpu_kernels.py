@@ -442,6 +442,53 @@ def test_constraint_stage_multi_vector_spmv_is_bit_identical(fmt):
     assert abs(t0 - (0.5 * x0 @ (L @ x0) + v @ x0 + 0.25)) <= 1e-13 * max(1.0, abs(t0))
 
 
+@pytest.mark.parametrize("m,first,x0_zero", [(21, 0, True), (24, 0, False), (9, 0, True), (40, 3, False), (49, 0, True), (17, 9, True)])
+def test_one_pass_constraint_reduction(m, first, x0_zero):
+    """gram_kernel (FP64 mma.sync m8n8k4 tiles): term2 = Z^T M Z and x0.MZ for >= 8 new columns of a symmetric M in
+    one pass over Z and M Z (solvers.py:33-36), against the four-columns-per-pass path (option gram = 0) and numpy.
+    `first` columns are reduced beforehand (the incremental case c0 > 0: only rows i <= column are formed, the rest
+    is mirrored); n is not a multiple of the 16-row chunk, m of the 8-row tile."""
+    rng = np.random.default_rng(31 + m)
+    d = lkdv.linforms(space="CG", M=3_337, mlength=0.8 * 3_337)[0]
+    A, L = d["A"], d["L"].tocsr()
+    L = (L + L.T).tocsr() * 0.5
+    n = A.shape[0]
+    assert n % 16 != 0
+    b, v = rng.standard_normal(n), rng.standard_normal(n)
+    x0 = np.zeros(n) if x0_zero else 0.01 * rng.standard_normal(n)
+    out = []
+    for gram in (1, 0):
+        with KrylovContext(n, 50) as ctx:
+            ctx.set_option("gram", gram)
+            ctx.upload_matrix(nat.SLOT_A, A)
+            ctx.upload_matrix(nat.SLOT_CON0, L)
+            ctx.upload_vec(nat.VEC_B, b)
+            ctx.upload_vec(nat.VEC_X0, x0)
+            ctx.set_option("x0_is_zero", 1 if x0_zero else 0)
+            ctx.constraint_define(0, nat.SLOT_CON0, v, 0.25)
+            ctx.solve_begin()
+            for j in range(m):
+                ctx.arnoldi_step(j)
+            if first:
+                ctx.constraint_terms(0, first)
+            ctx.reset_profile()
+            t0, t1, t2 = ctx.constraint_terms(0, m)
+            launches = ctx.profile()["mdot"]["launches"]
+            Z = ctx.download_Z(0, m)
+            out.append((t0, t1, t2, Z, launches))
+    t0, t1, t2, Z, launches = out[0]
+    assert out[1][4] > launches                            # one gram launch per 24 columns instead of one mdotm per 4
+    LZ = (L @ Z.T)
+    ref2 = 0.5 * Z @ LZ
+    ref1 = Z @ v + x0 @ LZ
+    assert np.max(np.abs(t2 - ref2)) <= 1e-13 * np.max(np.abs(ref2))
+    assert np.max(np.abs(t1 - ref1)) <= 1e-12 * np.max(np.abs(ref1))
+    np.testing.assert_array_equal(t2, t2.T)
+    np.testing.assert_allclose(t2, out[1][2], rtol=0, atol=1e-13 * np.max(np.abs(ref2)))
+    np.testing.assert_allclose(t1, out[1][1], rtol=0, atol=1e-12 * np.max(np.abs(ref1)))
+    assert t0 == out[1][0]
+
+
 @pytest.mark.parametrize("fmt", [nat.FMT_SELL, nat.FMT_SELLD])
 def test_sell_sigma_row_sorting(fmt):
     """SELL-C-sigma (option sell_sigma, sigma = 256): rows sorted by length inside windows of 256 so that a slice is
