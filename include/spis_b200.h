@@ -239,6 +239,12 @@ int spis_constraint_setup_wait(spis_ctx* ctx);
 int spis_small_kkt(int m, int ldh, const double* H, double beta, int nc, const double* term0, const double* term1,
                    const double* term2, double* y_out, double* fval_out, int* nit_out, int* handled);
 
+/* The sign settling that follows (smallsolve._settle_signs; solvers.py:14-18,266 accept a constrained step only if
+ * max_c g_c(y) <= 1e-12, signed): y moves by minimum-norm corrections of a few ulps until every g_c(y) <= 0 in this
+ * routine's arithmetic (at most `tries` times).  The caller checks the signs once more with its own evaluation.      */
+int spis_small_settle(int m, int nc, const double* term0, const double* term1, const double* term2, double* y, int tries,
+                      int* moved_out);
+
 /* ---- downloads / host bridges ------------------------------------------------------- */
 int spis_download_vec(spis_ctx* ctx, int which, int j, double* host, int64_t n);
 /* rows z[j0..j1) as a (j1-j0) x n row-major block (dict-form constraints need Z on the

@@ -1174,29 +1174,83 @@ bool lu_solve(std::vector<double>& A, int n, std::vector<double>& b) {
 struct KktProblem {
   int m, nc;
   const double *t0, *t1, *t2;            // nc, nc x m, nc x m x m
-  std::vector<double> S, c;              // R^{-1} (m x m, row-major), Q'(beta e1)
-  // y = S (c + u); g_c(y); Ju = (t1_c + 2 y'T2_c) S
+  std::vector<double> S, c;              // R^{-1} (m x m, row-major, upper triangular), Q'(beta e1)
+  std::vector<char> linear;              // T2_c == 0 (mass-type invariants): no curvature, no quadratic form
+  mutable std::vector<double> cu, Jy, yT;
+  // y = S (c + u); g_c(y); Ju = (t1_c + 2 y'T2_c) S.  Every sum runs over its index in ascending order (the loops
+  // are arranged as row updates so that the compiler vectorises them; exact zeros of the triangle are skipped).
   void evaluate(const std::vector<double>& u, std::vector<double>& y, std::vector<double>& g, std::vector<double>& Ju) const {
-    std::vector<double> cu(m), Jy(m);
+    cu.resize(m); Jy.resize(m); yT.resize(m);
     for (int i = 0; i < m; ++i) cu[i] = c[i] + u[i];
-    for (int i = 0; i < m; ++i) { double t = 0.0; for (int j = 0; j < m; ++j) t += S[(size_t)i * m + j] * cu[j]; y[i] = t; }
+    for (int i = 0; i < m; ++i) { double t = 0.0; const double* Si = &S[(size_t)i * m]; for (int j = i; j < m; ++j) t += Si[j] * cu[j]; y[i] = t; }
     for (int q = 0; q < nc; ++q) {
       const double* T1 = t1 + (size_t)q * m; const double* T2 = t2 + (size_t)q * m * m;
       double lin = 0.0, quad = 0.0;
+      std::fill(yT.begin(), yT.end(), 0.0);
+      if (!linear[q])
+        for (int i = 0; i < m; ++i) { const double yi = y[i]; const double* Ti = T2 + (size_t)i * m; for (int j = 0; j < m; ++j) yT[j] += yi * Ti[j]; }
       for (int j = 0; j < m; ++j) {
-        double yT = 0.0;
-        for (int i = 0; i < m; ++i) yT += y[i] * T2[(size_t)i * m + j];
-        Jy[j] = T1[j] + 2.0 * yT;
-        quad += yT * y[j];
+        Jy[j] = T1[j] + 2.0 * yT[j];
+        quad += yT[j] * y[j];
         lin += T1[j] * y[j];
       }
       g[q] = (t0[q] + lin) + quad;
-      for (int j = 0; j < m; ++j) { double t = 0.0; for (int i = 0; i < m; ++i) t += Jy[i] * S[(size_t)i * m + j]; Ju[(size_t)q * m + j] = t; }
+      double* Jq = &Ju[(size_t)q * m];
+      std::fill(Jq, Jq + m, 0.0);
+      for (int i = 0; i < m; ++i) { const double a = Jy[i]; const double* Si = &S[(size_t)i * m]; for (int j = i; j < m; ++j) Jq[j] += a * Si[j]; }
     }
   }
 };
 
 }  // namespace
+
+// The sign settling of smallsolve._settle_signs (solvers.py:14-18,266: the reference accepts a constrained step only
+// if max_c g_c(y) <= 1e-12, SIGNED): y moves by the minimum-norm correction dy = J'(J J')^{-1}(target - g) that puts
+// every g_c a few ulps below zero.  The caller re-evaluates g_c(y) with its own arithmetic afterwards (that evaluation
+// is the one the acceptance test uses) and repeats in Python if a sign still disagrees.  *moved_out = corrections made.
+int spis_small_settle(int m, int nc, const double* term0, const double* term1, const double* term2, double* y, int tries,
+                      int* moved_out) {
+  if (!term0 || !term1 || !term2 || !y || m < 1 || nc < 1) return SPIS_E_INVALID;
+  if (moved_out) *moved_out = 0;
+  const double eps = 2.220446049250313e-16;
+  std::vector<double> g(nc), J((size_t)nc * m), yT(m), G((size_t)nc * nc), rhs(nc), ynew(m);
+  for (int k = 0; k < tries; ++k) {
+    double gmax = -1e300; bool finite = true;
+    for (int q = 0; q < nc; ++q) {
+      const double* T1 = term1 + (size_t)q * m; const double* T2 = term2 + (size_t)q * m * m;
+      std::fill(yT.begin(), yT.end(), 0.0);
+      for (int i = 0; i < m; ++i) { const double yi = y[i]; const double* Ti = T2 + (size_t)i * m; for (int j = 0; j < m; ++j) yT[j] += yi * Ti[j]; }
+      double lin = 0.0, quad = 0.0;
+      for (int j = 0; j < m; ++j) { J[(size_t)q * m + j] = T1[j] + 2.0 * yT[j]; lin += T1[j] * y[j]; quad += yT[j] * y[j]; }
+      g[q] = (term0[q] + lin) + quad;
+      finite = finite && std::isfinite(g[q]);
+      gmax = std::max(gmax, g[q]);
+    }
+    // "safely negative": the caller's evaluation of g_c differs from this one by an ulp or two of |term0|, so a value
+    // within one ulp below zero still counts as positive here and the target sits four ulps below (the caller's own
+    // loop aims two ulps below)
+    bool settled = finite;
+    for (int q = 0; q < nc && settled; ++q) settled = g[q] <= -eps * std::max(std::fabs(term0[q]), std::fabs(g[q]));
+    (void)gmax;
+    if (!finite || settled) return SPIS_OK;
+    for (int q = 0; q < nc; ++q)
+      rhs[q] = -std::ldexp(4.0 * eps * std::max(std::fabs(term0[q]), std::fabs(g[q])), k) - g[q];
+    for (int a = 0; a < nc; ++a) for (int b = 0; b < nc; ++b) {
+      double t = 0.0; for (int j = 0; j < m; ++j) t += J[(size_t)a * m + j] * J[(size_t)b * m + j];
+      G[(size_t)a * nc + b] = t;
+    }
+    if (!lu_solve(G, nc, rhs)) return SPIS_OK;       // dependent gradients: the caller's lstsq handles it
+    bool ok = true;
+    for (int j = 0; j < m; ++j) {
+      double t = 0.0; for (int q = 0; q < nc; ++q) t += J[(size_t)q * m + j] * rhs[q];
+      ynew[j] = y[j] + t; ok = ok && std::isfinite(ynew[j]);
+    }
+    if (!ok) return SPIS_OK;
+    for (int j = 0; j < m; ++j) y[j] = ynew[j];
+    if (moved_out) *moved_out += 1;
+  }
+  return SPIS_OK;
+}
 
 int spis_small_kkt(int m, int ldh, const double* H, double beta, int nc, const double* term0, const double* term1,
                    const double* term2, double* y_out, double* fval_out, int* nit_out, int* handled) {
@@ -1241,17 +1295,30 @@ int spis_small_kkt(int m, int ldh, const double* H, double beta, int nc, const d
       P.S[(size_t)i * m + col] = t / A[(size_t)i * m + i];
     }
   }
-  // curvature S'(T2 + T2')S per constraint
-  std::vector<double> curv((size_t)nc * m * m), tmp((size_t)m * m);
+  // curvature S'(T2 + T2')S per constraint (S is upper triangular; sums over l ascending, as row updates)
+  std::vector<double> curv((size_t)nc * m * m, 0.0), tmp((size_t)m * m);
+  P.linear.assign(nc, 1);
   for (int q = 0; q < nc; ++q) {
     const double* T2 = term2 + (size_t)q * m * m;
-    for (int i = 0; i < m; ++i) for (int j = 0; j < m; ++j) {
-      double t = 0.0; for (int l = 0; l < m; ++l) t += (T2[(size_t)i * m + l] + T2[(size_t)l * m + i]) * P.S[(size_t)l * m + j];
-      tmp[(size_t)i * m + j] = t;
+    for (size_t e = 0; e < (size_t)m * m; ++e) if (T2[e] != 0.0) { P.linear[q] = 0; break; }
+    if (P.linear[q]) continue;
+    std::fill(tmp.begin(), tmp.end(), 0.0);
+    for (int i = 0; i < m; ++i) {
+      double* ti = &tmp[(size_t)i * m];
+      for (int l = 0; l < m; ++l) {
+        const double a = T2[(size_t)i * m + l] + T2[(size_t)l * m + i];
+        const double* Sl = &P.S[(size_t)l * m];
+        for (int j = l; j < m; ++j) ti[j] += a * Sl[j];
+      }
     }
-    for (int i = 0; i < m; ++i) for (int j = 0; j < m; ++j) {
-      double t = 0.0; for (int l = 0; l < m; ++l) t += P.S[(size_t)l * m + i] * tmp[(size_t)l * m + j];
-      curv[((size_t)q * m + i) * m + j] = t;
+    double* Cq = &curv[(size_t)q * m * m];
+    for (int l = 0; l < m; ++l) {
+      const double* tl = &tmp[(size_t)l * m];
+      for (int i = l; i < m; ++i) {
+        const double sli = P.S[(size_t)l * m + i];
+        double* ci = Cq + (size_t)i * m;
+        for (int j = 0; j < m; ++j) ci[j] += sli * tl[j];
+      }
     }
   }
   auto nrm2 = [](const std::vector<double>& a) { double t = 0.0; for (double x : a) t += x * x; return std::sqrt(t); };
@@ -1298,9 +1365,10 @@ int spis_small_kkt(int m, int ldh, const double* H, double beta, int nc, const d
   if (!converged) return SPIS_OK;
   double fval = 0.0; for (double t : u) fval += t * t;
   if (fval > 1e-4 * cnorm * cnorm) return SPIS_OK;          // strongly active constraints: the caller also tries its warm start
-  // (the sign settling of smallsolve._settle_signs stays with the caller: it must see the constraint values exactly as
-  //  the acceptance test of solvers.py:266 evaluates them -- one ulp of a 1e4-sized invariant is 1.8e-12 > 1e-12)
+  // (the final word on the signs stays with the caller, smallsolve._settle_signs: it must see the constraint values
+  //  exactly as the acceptance test of solvers.py:266 evaluates them -- one ulp of a 1e4-sized invariant is 1.8e-12)
   for (int j = 0; j < m; ++j) y_out[j] = y[j];
+  spis_small_settle(m, nc, term0, term1, term2, y_out, 8, nullptr);   // (the caller verifies the signs with its own evaluation)
   if (fval_out) *fval_out = fval;
   if (nit_out) *nit_out = nit;
   *handled = 1;

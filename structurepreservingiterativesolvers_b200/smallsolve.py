@@ -225,7 +225,9 @@ def _kkt_native(Hj, beta, constraints):
                             _nat.dptr(y), _C.byref(fval), _C.byref(nit), _C.byref(handled))
     if rc != _nat.OK or not handled.value:
         return None
-    # the signs are settled HERE, with the very evaluation the acceptance test of solvers.py:266 uses
+    # (spis_small_kkt has already moved y a few ulps to the accepted side of every constraint, spis_small_settle;)
+    # the signs are settled HERE, with the very evaluation the acceptance test of solvers.py:266 uses -- normally
+    # that is one look at g_c(y) and no further move
     return SmallResult(_settle_signs(y, cons), message=SUCCESS_MESSAGE, success=True, nit=nit.value, fun=fval.value)
 
 
