@@ -176,6 +176,14 @@ int spis_iterate_residual(spis_ctx* ctx, int m, const double* y, double* resnorm
  * Arnoldi step after it; _wait blocks only until the residual norm of THIS pair has arrived           */
 int spis_iterate_residual_launch(spis_ctx* ctx, int m, const double* y);
 int spis_iterate_residual_wait(spis_ctx* ctx, double* resnorm_out);
+/* _launch for an iterate the caller expects to be the LAST one (the loop ends on its residual, solvers.py:296-297, and
+ * the solver returns it, :313): x_j is formed in `chunks` row blocks and every block is streamed to host_dst (n doubles
+ * of page-locked memory) as soon as it is complete, so the device-to-host copy of the result overlaps its formation
+ * and its residual check.  *started_out = 0: host_dst is not page-locked, plain launch.  spis_download_join blocks
+ * until the copy is complete (host_dst must stay alive until then); an iterate that turns out not to be the last
+ * one is joined and dropped.                                                                                        */
+int spis_iterate_residual_launch_dl(spis_ctx* ctx, int m, const double* y, double* host_dst, int chunks, int* started_out);
+int spis_download_join(spis_ctx* ctx);
 /* only x = x0 + Z[:, :m] y (lazy re-materialisation of dict['x'][j], solvers.py:318)    */
 int spis_form_iterate(spis_ctx* ctx, int m, const double* y);
 

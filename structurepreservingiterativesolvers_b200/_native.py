@@ -64,6 +64,8 @@ SIGNATURES = {
     "spis_residual_launch": (C.c_int, [_ctx]),
     "spis_iterate_residual": (C.c_int, [_ctx, C.c_int, _dp, _dp]),
     "spis_iterate_residual_launch": (C.c_int, [_ctx, C.c_int, _dp]),
+    "spis_iterate_residual_launch_dl": (C.c_int, [_ctx, C.c_int, _dp, _dp, C.c_int, C.POINTER(C.c_int)]),
+    "spis_download_join": (C.c_int, [_ctx]),
     "spis_iterate_residual_wait": (C.c_int, [_ctx, _dp]),
     "spis_form_iterate": (C.c_int, [_ctx, C.c_int, _dp]),
     "spis_pipe_begin": (C.c_int, [_ctx, C.c_double, C.c_int]),

@@ -168,6 +168,7 @@ struct spis_ctx {
   double* h_y = nullptr;        // pinned K
   double* h_cout = nullptr;     // pinned kmax*2K
   cudaEvent_t ev_arnoldi = nullptr;
+  cudaStream_t dstream = nullptr; cudaEvent_t ev_dl = nullptr, ev_chunk = nullptr; bool dl_inflight = false;   // early download of a final-candidate iterate
   cudaStream_t hstream = nullptr; cudaEvent_t ev_orth = nullptr, ev_hess = nullptr;   // hess_kernel runs beside the normalising sweep
   cudaEvent_t ev_resid = nullptr; double* h_resid = nullptr; bool resid_inflight = false;   // pinned residual slot of its own
   // pipelined loop (spis_pipe_begin / spis_step_enqueue): Givens state, least-squares coefficients and the phase word on
@@ -365,6 +366,13 @@ int prof_resolve(spis_ctx* ctx) {
   }
   for (auto& r : ctx->recs) { ctx->evpool.push_back(r.e0); ctx->evpool.push_back(r.e1); }
   ctx->recs.clear();
+  return SPIS_OK;
+}
+
+// An early download (spis_iterate_residual_launch_dl) may still be reading X on the copy stream: whatever writes X next
+// on the main stream waits for it (device-side; the host does not block).
+int dl_fence(spis_ctx* ctx) {
+  if (ctx->dl_inflight) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_dl, 0));
   return SPIS_OK;
 }
 
@@ -1428,6 +1436,9 @@ int spis_ctx_create(int device, int64_t n, int64_t n_halo, int k_max, void* stre
   CCU(cudaEventCreateWithFlags(&c->ev_arnoldi, cudaEventDisableTiming));
   CCU(cudaEventCreateWithFlags(&c->ev_resid, cudaEventDisableTiming));
   { int lo = 0, hi = 0; CCU(cudaDeviceGetStreamPriorityRange(&lo, &hi)); CCU(cudaStreamCreateWithPriority(&c->hstream, cudaStreamNonBlocking, hi)); }
+  CCU(cudaStreamCreateWithFlags(&c->dstream, cudaStreamNonBlocking));
+  CCU(cudaEventCreateWithFlags(&c->ev_dl, cudaEventDisableTiming));
+  CCU(cudaEventCreateWithFlags(&c->ev_chunk, cudaEventDisableTiming));
   CCU(cudaEventCreateWithFlags(&c->ev_orth, cudaEventDisableTiming));
   CCU(cudaEventCreateWithFlags(&c->ev_hess, cudaEventDisableTiming));
   CCU(cudaEventCreate(&c->ev_t0));
@@ -1521,6 +1532,9 @@ int spis_ctx_destroy(spis_ctx* ctx) {
   spis_pinned_free(ctx->h_rec);
   if (ctx->ev_arnoldi) cudaEventDestroy(ctx->ev_arnoldi);
   if (ctx->ev_resid) cudaEventDestroy(ctx->ev_resid);
+  if (ctx->dstream) { cudaStreamSynchronize(ctx->dstream); cudaStreamDestroy(ctx->dstream); }
+  if (ctx->ev_dl) cudaEventDestroy(ctx->ev_dl);
+  if (ctx->ev_chunk) cudaEventDestroy(ctx->ev_chunk);
   if (ctx->ev_orth) cudaEventDestroy(ctx->ev_orth);
   if (ctx->ev_hess) cudaEventDestroy(ctx->ev_hess);
   if (ctx->hstream) cudaStreamDestroy(ctx->hstream);
@@ -2061,6 +2075,7 @@ int spis_arnoldi_finish(spis_ctx* ctx, int j, int m_it, const double* y_it) {
             "the fused iterate needs CGS2 and no preconditioner");
     memcpy(ctx->h_y, y_it, (size_t)m_it * sizeof(double));
     CU(cudaMemcpyAsync(ctx->d_y, ctx->h_y, (size_t)m_it * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    TRY(dl_fence(ctx));
     TRY(launch_lincomb2(ctx, ctx->V, m, h2, ctx->d_y, m_it, ctx->W, ctx->x0_is_zero ? nullptr : ctx->X0, qn, ctx->X, scal));
   } else if (ctx->orth == SPIS_ORTH_CGS2) {
     TRY(launch_lincomb(ctx, ctx->V, m, h2, nullptr, -1.0, ctx->W, qn, 1, scal));
@@ -2119,10 +2134,11 @@ int spis_arnoldi_step(spis_ctx* ctx, int j, double* hcol_out) {
   return spis_arnoldi_wait(ctx, j, hcol_out);
 }
 
-static int form_iterate_impl(spis_ctx* ctx, int m, const double* y) {
+static int form_iterate_impl(spis_ctx* ctx, int m, const double* y, double* dl_dst = nullptr, int chunks = 1) {
   REQUIRE(ctx->began, "spis_solve_begin has not been called");
   REQUIRE(m >= 0 && m <= ctx->kmax && (y || m == 0), "bad iterate arguments (m=%d)", m);
   CU(cudaSetDevice(ctx->device));
+  TRY(dl_fence(ctx));
   if (m) {
     // h_y may still be the source of an earlier async copy only if the stream has not
     // drained; every path that uses it synchronises before returning, so it is free here.
@@ -2130,7 +2146,34 @@ static int form_iterate_impl(spis_ctx* ctx, int m, const double* y) {
     CU(cudaMemcpyAsync(ctx->d_y, ctx->h_y, (size_t)m * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   }
   // x_j = x0 + Z y                                                 (solvers.py:287)
-  TRY(launch_lincomb(ctx, zbase(ctx), m, ctx->d_y, nullptr, 1.0, ctx->x0_is_zero ? nullptr : ctx->X0, ctx->X, 0, nullptr));
+  if (!dl_dst) {
+    TRY(launch_lincomb(ctx, zbase(ctx), m, ctx->d_y, nullptr, 1.0, ctx->x0_is_zero ? nullptr : ctx->X0, ctx->X, 0, nullptr));
+    return SPIS_OK;
+  }
+  // the same sweep in row chunks (whole tiles, so every element sees the identical fma chain), each chunk handed to
+  // the copy stream as soon as it is complete: the 8n-byte download of a final candidate overlaps its own formation
+  // and the residual check instead of following them
+  const int64_t ntiles = (ctx->n + kTile - 1) / kTile;
+  if (chunks < 1) chunks = 1;
+  if ((int64_t)chunks > ntiles) chunks = (int)ntiles;
+  const int64_t per = (ntiles + chunks - 1) / chunks * kTile;
+  for (int64_t r0 = 0; r0 < ctx->n; r0 += per) {
+    const int64_t nr = std::min<int64_t>(per, ctx->n - r0);
+    const int64_t nt = (nr + kTile - 1) / kTile;
+    const int grid = grid_for(ctx, nt, ctx->ctas_per_sm);
+    const size_t smem = (size_t)(m + 2 + kWarps * 32) * sizeof(double);
+    TRY(prof_begin(ctx, SPIS_PROF_LINCOMB, (double)(m + (ctx->x0_is_zero ? 0 : 1) + 1) * 8.0 * (double)nr));
+    lincomb_kernel<4><<<grid, kThreads, smem, ctx->stream>>>(zbase(ctx) + r0, ctx->ld, m, ctx->d_y, nullptr, 1.0,
+                                                             ctx->x0_is_zero ? nullptr : ctx->X0 + r0, ctx->X + r0, nr, 0,
+                                                             ctx->d_partial, ctx->d_counter, nullptr, XView(), 0ull);
+    CU(cudaGetLastError());
+    TRY(prof_end(ctx));
+    CU(cudaEventRecord(ctx->ev_chunk, ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->dstream, ctx->ev_chunk, 0));
+    CU(cudaMemcpyAsync(dl_dst + r0, ctx->X + r0, (size_t)nr * sizeof(double), cudaMemcpyDeviceToHost, ctx->dstream));
+  }
+  CU(cudaEventRecord(ctx->ev_dl, ctx->dstream));
+  ctx->dl_inflight = true;
   return SPIS_OK;
 }
 
@@ -2141,10 +2184,37 @@ int spis_form_iterate(spis_ctx* ctx, int m, const double* y) {
   return SPIS_OK;
 }
 
+static int iterate_residual_launch_impl(spis_ctx* ctx, int m, const double* y, double* dl_dst, int chunks);
 int spis_iterate_residual_launch(spis_ctx* ctx, int m, const double* y) {
   if (!ctx) return SPIS_E_INVALID;
+  return iterate_residual_launch_impl(ctx, m, y, nullptr, 1);
+}
+
+// As spis_iterate_residual_launch, and x_j is also streamed to host_dst (page-locked, n doubles) while it is formed and
+// checked: for an iterate the caller expects to be the last one (solvers.py:296-297 ends the loop on its residual).
+// *started_out = 0: host_dst is not page-locked, nothing was copied (plain launch).  spis_download_join waits for the
+// copy; until then host_dst must stay alive.  If the iterate is NOT the last one the caller joins and drops host_dst.
+int spis_iterate_residual_launch_dl(spis_ctx* ctx, int m, const double* y, double* host_dst, int chunks, int* started_out) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(host_dst && started_out, "null argument");
+  const bool ok = is_pinned_host(host_dst) && m > 0;
+  *started_out = ok ? 1 : 0;
+  return iterate_residual_launch_impl(ctx, m, y, ok ? host_dst : nullptr, chunks);
+}
+
+int spis_download_join(spis_ctx* ctx) {
+  if (!ctx) return SPIS_E_INVALID;
+  if (!ctx->dl_inflight) return SPIS_OK;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaEventSynchronize(ctx->ev_dl));
+  ctx->dl_inflight = false;
+  return SPIS_OK;
+}
+
+static int iterate_residual_launch_impl(spis_ctx* ctx, int m, const double* y, double* dl_dst, int chunks) {
   REQUIRE(!ctx->resid_inflight, "an iterate/residual pair is still in flight");
-  TRY(form_iterate_impl(ctx, m, y));
+  if (dl_dst && ctx->dl_inflight) TRY(spis_download_join(ctx));     // one early download at a time
+  TRY(form_iterate_impl(ctx, m, y, dl_dst, chunks));
   double* scal = ctx->d_small + 2 * ctx->K;
   // ||A x_j - b||                                                  (solvers.py:290)
   TRY(do_halo(ctx, ctx->X));
@@ -2338,6 +2408,7 @@ int spis_step_enqueue(spis_ctx* ctx, int j, int flags, int64_t* ticket_out) {
     ctx->prof_launch[SPIS_PROF_OTHER] += 1;
   }
   // q[j+1] = (w' - V h2) / h[j+1,j]  (+ x_{j-1} = x0 + Z y_{j-1})  (solvers.py:195-198, 287)
+  if (want_it) TRY(dl_fence(ctx));
   {
     const int64_t ntiles = (ctx->n + kTile - 1) / kTile;
     const int grid = grid_for(ctx, ntiles, ctx->lincomb2_ctas_per_sm);

@@ -171,6 +171,18 @@ class KrylovContext:
         y = nat.as_f64(y)
         self._check(self._lib.spis_iterate_residual_launch(self._h, y.size, nat.dptr(y)))
 
+    def iterate_residual_launch_dl(self, y, chunks: int = 4):
+        """iterate_residual_launch for a final candidate: returns the page-locked array x_j is being streamed into
+        (valid after download_join), or None when no page-locked buffer was available (plain launch)."""
+        y = nat.as_f64(y)
+        buf = nat.pinned_empty(self.n)
+        started = C.c_int(0)
+        self._check(self._lib.spis_iterate_residual_launch_dl(self._h, y.size, nat.dptr(y), nat.dptr(buf), int(chunks), C.byref(started)))
+        return buf if started.value else None
+
+    def download_join(self):
+        self._check(self._lib.spis_download_join(self._h))
+
     def iterate_residual_wait(self) -> float:
         res = C.c_double(0.0)
         self._check(self._lib.spis_iterate_residual_wait(self._h, C.byref(res)))

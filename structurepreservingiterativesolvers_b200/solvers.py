@@ -56,6 +56,7 @@ _CONFIG = {
     "dual_spmv": True,
     "lazy_sessions": 2,        # solver-created sessions kept resident for lazy dict['x'] access (the newest ones)
     "pipeline": True,          # device-resident loop (Givens update and unconstrained iterates on the GPU) with small_solver='kkt'
+    "early_download": True,    # cgmres: the result starts travelling to the host while the last iterate is formed and checked
     "ctx_options": {},         # raw spis_set_option pairs applied to every context a session creates (tuning / A-B runs)
 }
 _ORTH = {"cgs2": nat.ORTH_CGS2, "cgs1": nat.ORTH_CGS1, "mgs": nat.ORTH_MGS}
@@ -700,6 +701,7 @@ class _Pipeline:
         self.measured = set()
         self.device_iter = True                    # False once the host forms the iterates itself
         self.x_holds = None                        # iterate index known to be in the X buffer
+        self.early = None                          # (iterate index, page-locked array) of a download started early
         self._ls_prev = None
         self.ctx.set_option("spmv_dual", 1 if _opt("dual_spmv", None) else 0)
         self.ctx.pipe_begin(self.thr, not (self.beta > self.thr))
@@ -814,14 +816,37 @@ class _Pipeline:
         self.measured.add(j)
         return res, res > self.thr
 
-    def host_iterate_residual(self, j, yk):
-        """x_j = x0 + Z yk with coefficients from the host (constrained steps, fallbacks) and its residual norm."""
+    def host_iterate_residual(self, j, yk, likely_last=False):
+        """x_j = x0 + Z yk with coefficients from the host (constrained steps, fallbacks) and its residual norm.
+        likely_last: the loop is expected to end on this iterate (solvers.py:296-297), so its download -- 8n bytes
+        over PCIe, the largest non-kernel item of a solve -- starts while it is being formed and checked."""
         self.device_iter = False
-        self.ctx.iterate_residual_launch(yk)
+        self.drop_download()
+        if likely_last and _opt("early_download", None) and hasattr(self.ctx, "iterate_residual_launch_dl"):
+            buf = self.ctx.iterate_residual_launch_dl(yk)
+            if buf is not None:
+                self.early = (j, buf)
+        else:
+            self.ctx.iterate_residual_launch(yk)
         res = self.ctx.iterate_residual_wait()
         self.x_holds = j
         self.measured.add(j)
         return res
+
+    def drop_download(self):
+        """An early download whose iterate was not the last one: wait for the copy and forget the buffer."""
+        if self.early is not None:
+            self.ctx.download_join()
+            self.early = None
+
+    def take_download(self, j_last):
+        """The host copy of x_{j_last} if its early download was started (complete on return), else None."""
+        if self.early is None:
+            return None
+        j, buf = self.early
+        self.ctx.download_join()
+        self.early = None
+        return buf if (j == j_last and self.x_holds == j_last) else None
 
     def host_takes_over(self):
         """From now on the host forms every iterate (constrained phase): steps queued later do not touch X."""
@@ -830,6 +855,7 @@ class _Pipeline:
     def finish(self, j_last, y_last):
         """Leave x_{j_last} in the X buffer (a step queued ahead may have formed a later iterate)."""
         if j_last is not None and self.x_holds != j_last:
+            self.drop_download()
             self.ctx.form_iterate(y_last)
             self.x_holds = j_last
 
@@ -1208,6 +1234,7 @@ def _cgmres_pipelined(sess, k, tol, contol, beta, timing, jit, history_mode, tr)
             y0 = np.zeros(j + 1)
             if j != 0:
                 y0[:-1] = yk                              # warm start (solvers.py:225-227)
+            likely_last = False
             try:
                 if timing:
                     constrained_steps += 1
@@ -1222,7 +1249,8 @@ def _cgmres_pipelined(sess, k, tol, contol, beta, timing, jit, history_mode, tr)
                 if not may_end:
                     pipe.prefetch(j + 1)
                 res = _constrained("kkt", Hj, beta, y0, cons, ctol ** 2, None)   # (solvers.py:251-255)
-                if may_end and not pipe.predicted_residual(res.x) < tol:
+                likely_last = bool(may_end and pipe.predicted_residual(res.x) < tol)
+                if may_end and not likely_last:
                     pipe.prefetch(j + 1)
                 if not timing and np.isnan(max(res.x)):
                     raise ValueError("constrained solve returned NaN")           # (solvers.py:258-260)
@@ -1242,11 +1270,12 @@ def _cgmres_pipelined(sess, k, tol, contol, beta, timing, jit, history_mode, tr)
                 if timing and len(jit["end_constraints"]) < len(jit["start_constraints"]):
                     jit["end_constraints"].append(time())
                 pipe.prefetch(j + 1)
+                likely_last = False
                 res = unconstrained()                     # (solvers.py:274-278)
             _warn_message(j, res)
             yk = res.x
             bk.mark("small solve + host")
-            residual.append(pipe.host_iterate_residual(j, yk))                   # (solvers.py:287,290)
+            residual.append(pipe.host_iterate_residual(j, yk, likely_last and safety is True))   # (solvers.py:287,290)
             go = residual[-1] > thr
         bk.mark("iterate+residual")
         hist._append(yk)
@@ -1254,11 +1283,14 @@ def _cgmres_pipelined(sess, k, tol, contol, beta, timing, jit, history_mode, tr)
             jit["end_iter"].append(time())
         if residual[-1] < tol and safety is True:         # (solvers.py:296-297)
             break
-    pipe.finish(len(hist) - 2 if len(hist) > 1 else None, hist._ys[-1] if len(hist) > 1 else None)
+    j_last = len(hist) - 2 if len(hist) > 1 else None
+    pipe.finish(j_last, hist._ys[-1] if len(hist) > 1 else None)
     bk.report("cgmres")
     tr("cgmres: Krylov loop (%d steps)" % steps)
     timings = _cgmres_timings(jit, constrained_steps) if timing else None
-    x_last = sess.ctx.download(nat.VEC_X, pinned=True) if len(hist) > 1 else hist[0]
+    x_last = pipe.take_download(j_last)
+    if x_last is None:
+        x_last = sess.ctx.download(nat.VEC_X, pinned=True) if len(hist) > 1 else hist[0]
     tr("cgmres: download x")
     info = {"name": "cgmres",
             "x": _finish_history(hist, history_mode, x_last),

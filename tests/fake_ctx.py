@@ -219,6 +219,16 @@ class FakeKrylovContext:
         self._resid = self.iterate_residual(y)
         self.log.append(("iterate_residual_launch", len(y)))
 
+    def iterate_residual_launch_dl(self, y, chunks=4):
+        """Early download of a final candidate: here the copy is complete at once."""
+        self.iterate_residual_launch(y)
+        self.log.append(("early_download", len(y)))
+        self._early = self.X.copy()
+        return self._early
+
+    def download_join(self):
+        self.log.append(("download_join",))
+
     def iterate_residual_wait(self):
         r, self._resid = self._resid, None
         assert r is not None

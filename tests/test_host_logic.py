@@ -444,6 +444,27 @@ def test_pipelined_loop_hands_over_at_the_phase_switch():
     assert abs(r - info["res"][-1]) <= 1e-10 * np.linalg.norm(dic["b"])
 
 
+def test_last_iterate_is_downloaded_while_it_is_checked():
+    """cgmres ends on a constrained iterate whose residual is < tol (solvers.py:296-297).  When the small solve
+    predicts that, the iterate is launched through iterate_residual_launch_dl (its download overlaps its formation
+    and check) and the array that call filled IS the returned x; with early_download off the plain download gives
+    the same bits.  An early download whose iterate was not the last one is joined and dropped."""
+    x, info, log, dic = _solve_case("lkdv_cg_tol6", True)
+    early = [i for i, e in enumerate(log) if e[0] == "early_download"]
+    assert len(early) >= 1
+    assert sum(1 for e in log if e[0] == "download_join") >= len(early)      # every early download is joined
+    assert not any(e[0] == "iterate_residual_launch" for e in log[early[-1] + 2:])   # nothing was formed after the last one
+    solvers.configure(early_download=False)
+    try:
+        x2, info2, log2, _ = _solve_case("lkdv_cg_tol6", True)
+    finally:
+        solvers.configure(early_download=True)
+    assert not any(e[0] == "early_download" for e in log2)
+    np.testing.assert_array_equal(x, x2)
+    np.testing.assert_array_equal(info["x"][-1], x)
+    assert info["res"] == info2["res"]
+
+
 def test_pipelined_loop_invalid_record_falls_back_to_the_host():
     """A device record with `valid = 0` (a vanishing or tiny Givens pivot: hess_kernel also sets the phase word) makes the
     host take the general least-squares route (solvers.py:113) and form that and every later iterate itself."""
