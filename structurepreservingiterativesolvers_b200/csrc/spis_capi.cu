@@ -151,6 +151,7 @@ struct spis_ctx {
   // vectors
   double *V = nullptr, *Z = nullptr, *W = nullptr, *T = nullptr, *R0 = nullptr, *B = nullptr, *X0 = nullptr, *X = nullptr;
   double* G = nullptr;          // 4 x ld group buffer of the constraint stage (lazy)
+  std::vector<int> piggy;       // linear constraints whose v.Z rides in the next one-pass reduction (spis_constraint_terms)
   double* GW = nullptr; int gw_cols = 0;   // M Z[c0..m) of the one-pass constraint reduction (gram_kernel), gw_cols x ld (lazy)
   double* d_gpartial = nullptr; unsigned int* d_gcounter = nullptr;
   int gram = 1;                 // constraint stage: 8 or more new columns of a symmetric M go through gram_kernel
@@ -510,22 +511,27 @@ int launch_mdotm(spis_ctx* ctx, int nw, const double* V, int m, const double* ex
 // reduction here: the caller batches it (spis_constraint_terms).
 bool gram_applicable(spis_ctx* ctx, int ma, bool extra) { return ctx->gram && (ma + (extra ? 1 : 0) + 7) / 8 <= kGramMaxIB; }
 int launch_gram(spis_ctx* ctx, const double* A, int ma, const double* extra, const double* B, int mb, int c0, int tri,
-                double* out, int ra) {
+                double* out, int ra, const double* const* xcols = nullptr, int nxcols = 0) {
   const int nib_all = (ma + (extra ? 1 : 0) + 7) / 8;
   REQUIRE(nib_all >= 1 && nib_all <= kGramMaxIB && ra >= nib_all * 8 - 7, "gram: %d rows not supported", ma);
+  REQUIRE(nxcols >= 0 && nxcols <= 4, "gram: at most 4 extra columns");
   const size_t pmax = (size_t)2 * ctx->nsm * kGramMaxIB * kGramJB * 64;
   if (!ctx->d_gpartial) { TRY(dalloc(ctx, &ctx->d_gpartial, pmax, false)); TRY(dalloc(ctx, &ctx->d_gcounter, 64)); }
-  for (int j0 = 0; j0 < mb; j0 += 8 * kGramJB) {
-    const int mbp = std::min(mb - j0, 8 * kGramJB);
-    // rows this launch needs: i <= c0 + j0 + mbp - 1 (the extra row keeps every tile row alive)
+  const int ncols = mb + nxcols;               // columns j < mb: B + j*ld; then the extra columns (every row of A is needed for those)
+  for (int j0 = 0; j0 < ncols; j0 += 8 * kGramJB) {
+    const int ncp = std::min(ncols - j0, 8 * kGramJB);
+    const int mbp = std::max(0, std::min(mb - j0, ncp));
+    const int nxp = ncp - mbp;
+    // rows this launch needs: i <= c0 + j0 + mbp - 1 (the extra row and the extra columns keep every tile row alive)
     int nib = nib_all;
     int rows_a = ma;
-    if (tri && !extra) { rows_a = std::min(ma, c0 + j0 + mbp); nib = (rows_a + 7) / 8; }
-    GramArgs g{A, ctx->ld, rows_a, extra, B + (size_t)j0 * ctx->ld, ctx->ld, mbp, c0 + j0, tri, ctx->n,
-               ctx->d_gpartial, ctx->d_gcounter, out + (size_t)j0 * ra, ra};
+    if (tri && !extra && nxp == 0) { rows_a = std::min(ma, c0 + j0 + mbp); nib = (rows_a + 7) / 8; }
+    GramArgs g{A, ctx->ld, rows_a, extra, B + (size_t)j0 * ctx->ld, ctx->ld, mbp, {nullptr, nullptr, nullptr, nullptr}, nxp,
+               c0 + j0, tri, ctx->n, ctx->d_gpartial, ctx->d_gcounter, out + (size_t)j0 * ra, ra};
+    for (int x = 0; x < nxp; ++x) g.bx[x] = xcols[j0 + mbp + x - mb];
     const int grid = ctx->nsm * (nib <= 3 ? 2 : 1);
     const size_t smem = (size_t)nib * kGramJB * 64 * sizeof(double);
-    TRY(prof_begin(ctx, SPIS_PROF_MDOT, (double)(rows_a + (extra ? 1 : 0) + mbp) * 8.0 * (double)ctx->n));
+    TRY(prof_begin(ctx, SPIS_PROF_MDOT, (double)(rows_a + (extra ? 1 : 0) + ncp) * 8.0 * (double)ctx->n));
     switch (nib) {
       case 1: gram_kernel<1><<<grid, kGramThreads, smem, ctx->stream>>>(g); break;
       case 2: gram_kernel<2><<<grid, kGramThreads, smem, ctx->stream>>>(g); break;
@@ -2624,7 +2630,33 @@ static int test_symmetry(spis_ctx* ctx, Constraint& C) {
   return SPIS_OK;
 }
 
+static int constraint_terms_impl(spis_ctx* ctx, int c, int m, double* term0, double* term1, double* term2);
+
+// A linear invariant (M == 0: term1 = v.Z only) asked for FIRST is served by the one-pass reduction of a quadratic
+// constraint with the same columns pending: v rides as one more column of that pass (one more vector read instead of
+// a pass of its own over Z), and the quadratic constraint's terms are kept for when they are asked for.
 int spis_constraint_terms(spis_ctx* ctx, int c, int m, double* term0, double* term1, double* term2) {
+  if (!ctx) return SPIS_E_INVALID;
+  if (c >= 0 && c < SPIS_MAX_SLOTS && ctx->cons[c].defined && ctx->began && m >= 1 && m <= ctx->kmax && ctx->gram) {
+    const Constraint& C = ctx->cons[c];
+    if (C.slot < 0 && C.v && m - C.cols_done >= 8) {
+      for (int o = 0; o < SPIS_MAX_SLOTS; ++o) {
+        const Constraint& O = ctx->cons[o];
+        if (o == c || !O.defined || O.slot < 0 || O.symmetric == 0 || O.cols_done != C.cols_done) continue;
+        std::vector<double> t1((size_t)m), t2((size_t)m * m);
+        double t0 = 0.0;
+        ctx->piggy.assign(1, c);
+        const int rc = constraint_terms_impl(ctx, o, m, &t0, t1.data(), t2.data());
+        ctx->piggy.clear();
+        if (rc != SPIS_OK) return rc;
+        break;
+      }
+    }
+  }
+  return constraint_terms_impl(ctx, c, m, term0, term1, term2);
+}
+
+static int constraint_terms_impl(spis_ctx* ctx, int c, int m, double* term0, double* term1, double* term2) {
   if (!ctx) return SPIS_E_INVALID;
   REQUIRE(c >= 0 && c < SPIS_MAX_SLOTS && ctx->cons[c].defined, "constraint %d not defined", c);
   REQUIRE(ctx->began, "spis_solve_begin has not been called");
@@ -2676,6 +2708,7 @@ int spis_constraint_terms(spis_ctx* ctx, int c, int m, double* term0, double* te
     const double* gx = x0nz ? ctx->X0 : nullptr;
     bool use_gram = sym && (m - c0) >= 8 && gram_applicable(ctx, m, gx != nullptr);
     int gram_ra = 0;
+    std::vector<const double*> gram_x; std::vector<int> gram_xc; bool gram_own_v_separate = false;
     if (use_gram) {
       const int want = (m - c0 + 7) / 8 * 8;
       if (ctx->gw_cols < want) {
@@ -2697,9 +2730,20 @@ int spis_constraint_terms(spis_ctx* ctx, int c, int m, double* term0, double* te
         else rc = launch_spmv_multi(ctx, C.slot, nw, Zb + (size_t)g0 * ld, (int64_t)ld, dst, (int64_t)ld);
         g0 += nw;
       }
-      if (rc == SPIS_OK) rc = launch_gram(ctx, Zb, m, gx, ctx->GW, m - c0, c0, 1, ctx->d_cout + (size_t)c0 * 2 * K, gram_ra);
-      if (rc == SPIS_OK && C.v)
-        rc = launch_mdot(ctx, Zb + (size_t)c0 * ld, m - c0, nullptr, 0, C.v, ctx->d_cout + (size_t)(m - 1) * 2 * K + K);
+      // v.Z of this constraint, and of the linear ones that asked to ride along, as extra columns of the same pass
+      for (int pgy : ctx->piggy) {
+        const Constraint& P = ctx->cons[pgy];
+        if (gram_x.size() < 3 && P.defined && P.slot < 0 && P.v && P.cols_done == c0) { gram_x.push_back(P.v); gram_xc.push_back(pgy); }
+      }
+      if (C.v) { gram_x.push_back(C.v); gram_xc.push_back(c); }
+      if ((size_t)(m - c0 + (int)gram_x.size()) * gram_ra > (size_t)(m - c0) * 2 * K) {     // no room in the output block: own v only, as a pass of its own
+        gram_x.clear(); gram_xc.clear();
+        if (rc == SPIS_OK && C.v)
+          rc = launch_mdot(ctx, Zb + (size_t)c0 * ld, m - c0, nullptr, 0, C.v, ctx->d_cout + (size_t)(m - 1) * 2 * K + K);
+        gram_own_v_separate = true;
+      }
+      if (rc == SPIS_OK) rc = launch_gram(ctx, Zb, m, gx, ctx->GW, m - c0, c0, 1, ctx->d_cout + (size_t)c0 * 2 * K, gram_ra,
+                                          gram_x.data(), (int)gram_x.size());
     } else if (sym) {
       // symmetric M: groups of up to 4 new columns; M z_col lives only in the group buffer; one
       // pass over Z[0..g1) serves the whole group (each basis row is read once per group)
@@ -2748,8 +2792,16 @@ int spis_constraint_terms(spis_ctx* ctx, int c, int m, double* term0, double* te
     TRY(do_allreduce(ctx, ctx->d_cout + (size_t)c0 * 2 * K, (int64_t)(m - c0) * 2 * K, true));
     TRY(d2h(ctx, ctx->h_cout + (size_t)c0 * 2 * K, ctx->d_cout + (size_t)c0 * 2 * K, (size_t)(m - c0) * 2 * K * sizeof(double)));
     if (use_gram) {
-      const double* vz = ctx->h_cout + (size_t)(m - 1) * 2 * K + K;      // v.z_col, col = c0 .. m-1
+      const double* vz = ctx->h_cout + (size_t)(m - 1) * 2 * K + K;      // v.z_col, col = c0 .. m-1 (own pass)
       const double* base = ctx->h_cout + (size_t)c0 * 2 * K;
+      const double* own = nullptr;                                       // v.z_row, row = 0 .. m-1 (rode along)
+      for (size_t x = 0; x < gram_xc.size(); ++x) {
+        const double* colx = base + (size_t)(m - c0 + (int)x) * gram_ra;
+        if (gram_xc[x] == c) { own = colx; continue; }
+        Constraint& P = ctx->cons[gram_xc[x]];
+        for (int col = c0; col < m; ++col) P.T1[col] = colx[col];        // M == 0: term1 = v.Z (solvers.py:36)
+        P.cols_done = m;
+      }
       for (int col = c0; col < m; ++col) {
         const double* oA = base + (size_t)(col - c0) * gram_ra;
         for (int i = 0; i <= col; ++i) {
@@ -2758,7 +2810,7 @@ int spis_constraint_terms(spis_ctx* ctx, int c, int m, double* term0, double* te
         }
         double t1 = 0.0;
         if (x0nz) t1 += oA[m];
-        if (C.v) t1 += vz[col - c0];
+        if (C.v) t1 += (gram_own_v_separate || !own) ? vz[col - c0] : own[col];
         C.T1[col] = t1;
       }
     } else if (sym) {

@@ -849,7 +849,8 @@ constexpr int kGramMaxIB = 7;                  // row tiles: up to 56 rows of A 
 struct GramArgs {
   const double* A; int64_t lda; int ma;        // rows 0 .. ma-1
   const double* extra;                         // row ma (x0), or null
-  const double* B; int64_t ldb; int mb;        // the columns of this launch
+  const double* B; int64_t ldb; int mb;        // the regular columns of this launch (M z_j)
+  const double* bx[4]; int nx;                 // then nx more columns at arbitrary addresses (the vectors v_c: v.Z rides along); every row
   int c0;                                      // global index of column 0 (triangle test: row i is needed for column c iff i <= c)
   int tri;
   int64_t n;
@@ -881,7 +882,8 @@ gram_kernel(GramArgs g) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gq = lane >> 2, t = lane & 3;
   constexpr int NW = kGramThreads / 32;
-  const int njb = (g.mb + 7) / 8;              // <= kGramJB
+  const int ncol = g.mb + g.nx;
+  const int njb = (ncol + 7) / 8;              // <= kGramJB
   // which tiles are computed (uniform)
   const int xb = g.extra ? g.ma / 8 : -1;      // the tile row holding x0
   unsigned need = 0;
@@ -889,7 +891,7 @@ gram_kernel(GramArgs g) {
   for (int ib = 0; ib < NIB; ++ib)
 #pragma unroll
     for (int jb = 0; jb < kGramJB; ++jb)
-      if (jb < njb && (!g.tri || ib * 8 <= g.c0 + jb * 8 + 7 || ib == xb)) need |= 1u << (ib * kGramJB + jb);
+      if (jb < njb && (!g.tri || ib * 8 <= g.c0 + jb * 8 + 7 || ib == xb || (g.nx > 0 && jb * 8 + 7 >= g.mb))) need |= 1u << (ib * kGramJB + jb);
   unsigned need_row = 0;
 #pragma unroll
   for (int ib = 0; ib < NIB; ++ib) if ((need >> (ib * kGramJB)) & 7u) need_row |= 1u << ib;
@@ -904,7 +906,7 @@ gram_kernel(GramArgs g) {
 #pragma unroll
   for (int jb = 0; jb < kGramJB; ++jb) {
     const int vj = jb * 8 + gq;
-    pb[jb] = vj < g.mb ? g.B + (size_t)vj * g.ldb : nullptr;
+    pb[jb] = vj < g.mb ? g.B + (size_t)vj * g.ldb : (vj < ncol ? g.bx[vj - g.mb] : nullptr);
   }
   double acc[NIB][kGramJB][2];
 #pragma unroll
@@ -957,7 +959,7 @@ gram_kernel(GramArgs g) {
     const int blk = i >> 6, il = (i >> 3) & 7, jl = i & 7;
     const int ib = blk / kGramJB, jb = blk - ib * kGramJB;
     const int row = ib * 8 + il, col = jb * 8 + jl;
-    if (row >= rows || col >= g.mb) continue;
+    if (row >= rows || col >= ncol) continue;
     double sum = 0.0;
     if ((need >> blk) & 1u) {
       const double* src = g.partial + i;

@@ -489,6 +489,56 @@ def test_one_pass_constraint_reduction(m, first, x0_zero):
     assert t0 == out[1][0]
 
 
+@pytest.mark.parametrize("m,x0_zero,own_v", [(21, True, False), (24, False, True), (12, True, True)])
+def test_linear_invariants_ride_in_the_one_pass_reduction(m, x0_zero, own_v):
+    """A linear invariant (M == 0, term1 = v.Z: lkdv's mass, lkdv/LinearSolver.py:28-32) that is asked for before the
+    quadratic one with the same columns pending costs no pass over Z of its own: v is one more column of the
+    quadratic constraint's Gram pass, whose terms are kept for the following call.  Same numbers as the separate
+    passes (option gram = 0) to rounding, and as numpy."""
+    rng = np.random.default_rng(131 + m)
+    d = lkdv.linforms(space="CG", M=3_337, mlength=0.8 * 3_337)[0]
+    A, L = d["A"], d["L"].tocsr()
+    L = (L + L.T).tocsr() * 0.5
+    n = A.shape[0]
+    b, v_lin, v_q = rng.standard_normal(n), rng.standard_normal(n), rng.standard_normal(n)
+    x0 = np.zeros(n) if x0_zero else 0.01 * rng.standard_normal(n)
+    out = []
+    for gram in (1, 0):
+        with KrylovContext(n, 30) as ctx:
+            ctx.set_option("gram", gram)
+            ctx.upload_matrix(nat.SLOT_A, A)
+            ctx.upload_matrix(nat.SLOT_CON0 + 1, L)
+            ctx.upload_vec(nat.VEC_B, b)
+            ctx.upload_vec(nat.VEC_X0, x0)
+            ctx.set_option("x0_is_zero", 1 if x0_zero else 0)
+            ctx.constraint_define(0, -1, v_lin, 0.5)
+            ctx.constraint_define(1, nat.SLOT_CON0 + 1, v_q if own_v else None, 0.25)
+            ctx.solve_begin()
+            for j in range(m):
+                ctx.arnoldi_step(j)
+            ctx.constraint_terms(1, 2)                     # settles the symmetry test and term0 of the quadratic one ...
+            ctx.constraint_terms(0, 2)                     # ... and both are two columns in: c0 = 2 for the batch below
+            ctx.reset_profile()
+            lin = ctx.constraint_terms(0, m)
+            after_lin = ctx.profile()["mdot"]["launches"]
+            quad = ctx.constraint_terms(1, m)
+            after_quad = ctx.profile()["mdot"]["launches"]
+            Z = ctx.download_Z(0, m)
+            out.append((lin, quad, Z, after_lin, after_quad))
+    (lin, quad, Z, after_lin, after_quad), ref = out
+    assert after_lin == 1 and after_quad == 1              # one Gram launch served both calls
+    assert ref[4] > 1
+    LZ = L @ Z.T
+    np.testing.assert_allclose(lin[1], Z @ v_lin, rtol=0, atol=1e-12 * np.abs(Z @ v_lin).max())
+    assert lin[0] == ref[0][0] and np.all(lin[2] == 0.0)
+    ref1 = (Z @ v_q if own_v else 0.0) + x0 @ LZ
+    np.testing.assert_allclose(quad[1], ref1, rtol=0, atol=1e-12 * max(np.abs(ref1).max(), 1e-300))
+    np.testing.assert_allclose(quad[2], 0.5 * Z @ LZ, rtol=0, atol=1e-13 * np.abs(Z @ LZ).max())
+    np.testing.assert_allclose(lin[1], ref[0][1], rtol=0, atol=1e-12 * np.abs(ref[0][1]).max())
+    np.testing.assert_allclose(quad[1], ref[1][1], rtol=0, atol=1e-12 * max(np.abs(ref[1][1]).max(), 1e-300))
+    np.testing.assert_allclose(quad[2], ref[1][2], rtol=0, atol=1e-13 * np.abs(ref[1][2]).max())
+
+
 @pytest.mark.parametrize("fmt", [nat.FMT_SELL, nat.FMT_SELLD])
 def test_sell_sigma_row_sorting(fmt):
     """SELL-C-sigma (option sell_sigma, sigma = 256): rows sorted by length inside windows of 256 so that a slice is
