@@ -744,6 +744,7 @@ def main():
     ap.add_argument("--host-loop", action="store_true", help="host-driven Krylov loop (round-1 path) instead of the device-resident one")
     ap.add_argument("--transport", default="auto", choices=["auto", "p2p", "nccl"])
     ap.add_argument("--no-early-download", action="store_true", help="A/B: download the result only after the last residual check")
+    ap.add_argument("--early-download-chunks", type=int, default=0, help="A/B: row chunks of the early download (default 4)")
     ap.add_argument("--trace-file", default=None, help="write the per-launch device timeline of one profiled solve here (diagnostic)")
     ap.add_argument("--ctx-option", action="append", default=[], metavar="KEY=INT", help="raw device-context option for A/B runs (repeatable)")
     args = ap.parse_args()
@@ -753,6 +754,9 @@ def main():
     if args.no_early_download and args.impl != "reference":
         from structurepreservingiterativesolvers_b200 import solvers
         solvers.configure(early_download=False)
+    if args.early_download_chunks and args.impl != "reference":
+        from structurepreservingiterativesolvers_b200 import solvers
+        solvers.configure(early_download=args.early_download_chunks)
     if args.ctx_option and args.impl != "reference":
         from structurepreservingiterativesolvers_b200 import solvers
         solvers.configure(ctx_options={kv.split("=")[0]: int(kv.split("=")[1]) for kv in args.ctx_option})

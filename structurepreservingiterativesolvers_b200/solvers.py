@@ -56,7 +56,7 @@ _CONFIG = {
     "dual_spmv": True,
     "lazy_sessions": 2,        # solver-created sessions kept resident for lazy dict['x'] access (the newest ones)
     "pipeline": True,          # device-resident loop (Givens update and unconstrained iterates on the GPU) with small_solver='kkt'
-    "early_download": True,    # cgmres: the result starts travelling to the host while the last iterate is formed and checked
+    "early_download": True,    # cgmres: the result starts travelling to the host while the last iterate is formed and checked (int: row chunks)
     "ctx_options": {},         # raw spis_set_option pairs applied to every context a session creates (tuning / A-B runs)
 }
 _ORTH = {"cgs2": nat.ORTH_CGS2, "cgs1": nat.ORTH_CGS1, "mgs": nat.ORTH_MGS}
@@ -823,7 +823,8 @@ class _Pipeline:
         self.device_iter = False
         self.drop_download()
         if likely_last and _opt("early_download", None) and hasattr(self.ctx, "iterate_residual_launch_dl"):
-            buf = self.ctx.iterate_residual_launch_dl(yk)
+            ed = _opt("early_download", None)
+            buf = self.ctx.iterate_residual_launch_dl(yk, 4 if ed is True else int(ed))
             if buf is not None:
                 self.early = (j, buf)
         else:
