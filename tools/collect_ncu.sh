@@ -22,7 +22,7 @@ cap() {  # name, env, size, ncu args...
 # one mid-solve iteration of the pipelined loop: dual SpMV (field windows), mdot with the riding residual, orth_mid with
 # the norm, hess_kernel, lincomb2n (5 kernels per step; step 15 starts near launch 3 + 15 * 5)
 cap ${R}_lkdv_iter "SPIS_WORKLOAD=lkdv" 10000000 -k regex:"spmv_|mdot_|lincomb|orth_mid|hess_kernel" --launch-skip 78 --launch-count 10
-cap ${R}_lkdv_mdotm "SPIS_WORKLOAD=lkdv" 10000000 -k regex:"mdotm|spmv_pattern_multi" --launch-count 4
+cap ${R}_lkdv_gram "SPIS_WORKLOAD=lkdv" 10000000 -k regex:"gram_kernel|mdotm|spmv_pattern_multi" --launch-count 7
 cap ${R}_swe_iter "SPIS_WORKLOAD=swe" 10000000 -k regex:"spmv_|mdot_|lincomb|orth_mid|hess_kernel" --launch-skip 53 --launch-count 6
 cap ${R}_pre_jacobi "SPIS_WORKLOAD=jacobi" 10000000 -k regex:"lincomb2n|lincomb_kernel|jacobi" --launch-skip 4 --launch-count 4
 cap ${R}_pre_block "SPIS_WORKLOAD=lkdvRK" 6000000 -k regex:"blockdiag|lincomb_kernel" --launch-skip 2 --launch-count 3

@@ -4,7 +4,7 @@ measured DRAM bytes per launch of every kernel class of bench.py's `kernels` obj
 import collections, csv, json, os, re, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CLASS = [("spmv_pattern_multi", "spmv_aux"), ("spmv_sell_multi", "spmv_aux"), ("spmv_", "spmv"), ("reduce_partials", "spmv"),
-         ("mdotm_kernel", "mdot"), ("mdot_kernel", "mdot"), ("mdot_reg_kernel", "mdot"),
+         ("gram_kernel", "mdot"), ("mdotm_kernel", "mdot"), ("mdot_kernel", "mdot"), ("mdot_reg_kernel", "mdot"),
          ("lincomb_kernel", "lincomb"), ("lincomb2_kernel", "lincomb"), ("lincomb2n_kernel", "lincomb"), ("orth_mid_kernel", "orthmid"),
          ("scale_kernel", "scale"), ("hess_kernel", "other"), ("pipe_init_kernel", "other")]
 MODE = re.compile(r"kernel<\(?(?:int\))?\s*(\d)")
