@@ -824,7 +824,10 @@ class _Pipeline:
         self.drop_download()
         if likely_last and _opt("early_download", None) and hasattr(self.ctx, "iterate_residual_launch_dl"):
             ed = _opt("early_download", None)
-            buf = self.ctx.iterate_residual_launch_dl(yk, 4 if ed is True else int(ed))
+            # row chunks: ~2.5M rows each, at most 4 (a row-sharded strip of a million rows goes in one piece: the
+            # chunk kernels and their copy hand-overs would cost more than the overlap gains)
+            chunks = max(1, min(4, self.ctx.n // 2_500_000)) if ed is True else int(ed)
+            buf = self.ctx.iterate_residual_launch_dl(yk, chunks)
             if buf is not None:
                 self.early = (j, buf)
         else:
