@@ -34,7 +34,7 @@ extern "C" {
 #pragma GCC visibility push(default)
 #endif
 
-#define SPIS_ABI_VERSION 4
+#define SPIS_ABI_VERSION 5
 
 /* error codes */
 #define SPIS_OK            0
