@@ -1637,6 +1637,7 @@ int spis_get_info(const spis_ctx* cctx, const char* key, int64_t* value_out) {
   else if (k == "alloc_miss_bytes") *value_out = g_dev_miss_bytes.load();
   else if (k == "can_fuse_iterate") *value_out = (ctx->fuse_iterate && ctx->orth == SPIS_ORTH_CGS2 && ctx->pre_kind == SPIS_PRE_NONE) ? 1 : 0;
   else if (k == "pipe_lag") *value_out = ctx->pre_kind == SPIS_PRE_NONE ? 1 : 0;
+  else if (k == "sharded") *value_out = (ctx->xactive || ctx->allreduce != nullptr || ctx->n_halo > 0) ? 1 : 0;
   else if (k == "device_pipeline") *value_out = (ctx->orth == SPIS_ORTH_CGS2 && ctx->pre_kind != SPIS_PRE_HOST && !ctx->allreduce && !ctx->halo &&
                                                  (ctx->fuse_iterate || ctx->pre_kind != SPIS_PRE_NONE)) ? 1 : 0;
   else if (k == "device_ptr:small") *value_out = (int64_t)(intptr_t)ctx->d_small;
@@ -2220,7 +2221,12 @@ int spis_download_join(spis_ctx* ctx) {
 static int iterate_residual_launch_impl(spis_ctx* ctx, int m, const double* y, double* dl_dst, int chunks) {
   REQUIRE(!ctx->resid_inflight, "an iterate/residual pair is still in flight");
   if (dl_dst && ctx->dl_inflight) TRY(spis_download_join(ctx));     // one early download at a time
-  TRY(form_iterate_impl(ctx, m, y, dl_dst, chunks));
+  // chunks == 0: the copy is queued BEHIND the residual check (it starts when the check ends, without waiting for
+  // the host to look at the result).  Row-sharded runs use this form: while a device-to-host copy is in flight the
+  // peers' NVLink stores into this GPU are held up with it (measured: the 20-us residual check of a 4-GPU run took
+  // 260 us, about the length of the copy, when the copy ran beside it), and the check ends in an exchange.
+  const bool after = dl_dst && chunks == 0;
+  TRY(form_iterate_impl(ctx, m, y, after ? nullptr : dl_dst, chunks));
   double* scal = ctx->d_small + 2 * ctx->K;
   // ||A x_j - b||                                                  (solvers.py:290)
   TRY(do_halo(ctx, ctx->X));
@@ -2228,6 +2234,12 @@ static int iterate_residual_launch_impl(spis_ctx* ctx, int m, const double* y, d
   CU(cudaMemcpyAsync(ctx->h_resid, scal + 2, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaEventRecord(ctx->ev_resid, ctx->stream));
   ctx->resid_inflight = true;
+  if (after) {
+    CU(cudaStreamWaitEvent(ctx->dstream, ctx->ev_resid, 0));
+    CU(cudaMemcpyAsync(dl_dst, ctx->X, (size_t)ctx->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->dstream));
+    CU(cudaEventRecord(ctx->ev_dl, ctx->dstream));
+    ctx->dl_inflight = true;
+  }
   return SPIS_OK;
 }
 

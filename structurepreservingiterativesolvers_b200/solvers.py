@@ -826,7 +826,12 @@ class _Pipeline:
             ed = _opt("early_download", None)
             # row chunks: ~2.5M rows each, at most 4 (a row-sharded strip of a million rows goes in one piece: the
             # chunk kernels and their copy hand-overs would cost more than the overlap gains)
-            chunks = max(1, min(4, self.ctx.n // 2_500_000)) if ed is True else int(ed)
+            # A row-sharded run queues the copy behind the residual check instead (chunks = 0): a device-to-host copy
+            # in flight holds up the peers' NVLink stores, and the check ends in an exchange (see the C side).
+            if ed is True:
+                chunks = 0 if self.ctx.info("sharded") else max(1, min(4, self.ctx.n // 2_500_000))
+            else:
+                chunks = int(ed)
             buf = self.ctx.iterate_residual_launch_dl(yk, chunks)
             if buf is not None:
                 self.early = (j, buf)
