@@ -122,6 +122,19 @@ int         spis_device_trim(void);
 /* host utility: *out = 1 if any of the n doubles is non-zero (multi-threaded scan; used to
  * recognise the explicit-zero constraint matrix `0*A` of lkdv/LinearSolver.py:30)             */
 int         spis_host_any_nonzero(const double* data, size_t n, int* out);
+/* bytes the upload entry points of this process have actually sent to devices (a matrix stored by row patterns found on
+ * the host crosses as 2 bytes per row); reset != 0 also clears the counter                                          */
+long long   spis_h2d_bytes(int reset);
+/* Row stencils of a host CSR matrix, found by host threads (what spis_upload_csr does before it uploads anything when
+ * option host_pattern is set -- off by default, see DESIGN -- : a
+ * matrix assembled on a uniform mesh with constant coefficients -- lkdv/lkdv.py:109-111 exports such a one -- crosses
+ * PCIe as a 16-bit id per row and a table instead of 12 bytes per entry).  Two rows share a stencil iff their
+ * (column - row, value bits) lists are identical.  pid_out[nrows]; rep_out[<= 4096] = one representative row per stencil;
+ * *npat_out = 0: more than 4096 stencils or a row longer than 64 entries.  Columns >= n_local move by col_shift
+ * (ghost columns of a row-sharded strip).  No device is touched.                                                   */
+int         spis_host_find_patterns(const int32_t* indptr, const int32_t* indices, const double* data, int64_t nrows,
+                                    int64_t n_local, int64_t col_shift, int nthreads, uint16_t* pid_out, int32_t* rep_out,
+                                    int* npat_out, int* maxlen_out, int64_t* changes_out);
 /* same question, answered where it is cheapest: page-locked host buffers are pulled through a device
  * scratch block by the copy engine and tested there (no host CPU time; runs on the calling thread's
  * upload stream), pageable ones are scanned by host threads                                        */

@@ -79,6 +79,9 @@ SIGNATURES = {
     "spis_constraint_setup_wait": (C.c_int, [_ctx]),
     "spis_constraint_set_constant": (C.c_int, [_ctx, C.c_int, C.c_double]),
     "spis_constraint_set_vector": (C.c_int, [_ctx, C.c_int, _dp]),
+    "spis_h2d_bytes": (C.c_longlong, [C.c_int]),
+    "spis_host_find_patterns": (C.c_int, [_ip, _ip, _dp, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.POINTER(C.c_uint16), _ip,
+                                          C.POINTER(C.c_int), C.POINTER(C.c_int), _lp]),
     "spis_small_settle": (C.c_int, [C.c_int, C.c_int, _dp, _dp, _dp, _dp, C.c_int, C.POINTER(C.c_int)]),
     "spis_small_kkt": (C.c_int, [C.c_int, C.c_int, _dp, C.c_double, C.c_int, _dp, _dp, _dp, _dp, _dp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "spis_download_vec": (C.c_int, [_ctx, C.c_int, C.c_int, _dp, C.c_int64]),

@@ -125,6 +125,14 @@ struct spis_ctx {
                                 // L1 hit, the TMA writes of the windows add to it, and two CTAs of 8 consumer warps hide the latency of
                                 // the matrix stream worse than four to five CTAs of the plain kernels.
   int hess_async = 1;           // pipelined loop: the Givens / least-squares kernel runs beside the normalising sweep
+  // Look for row patterns in the caller's CSR arrays with host threads before anything is uploaded.  OFF by default:
+  // on the bench box (16 hardware threads, PCIe 5) the detection alone runs at 94 GB/s (8.1 ms for the 760 MB lkdv
+  // operator against 14.4 ms of PCIe), but inside an end-to-end solve it took 12.3 ms + 4 ms for the ids to arrive
+  // (36.7-37.8 ms per solve against 34.6).  It cuts the bytes sent per solve from 1.28 GB to 0.28 GB: worth it where
+  // PCIe is the scarcer resource (slower links, more host cores).
+  int host_pattern = 0;
+  int64_t host_pattern_min_nnz = 1 << 20;
+  int host_threads = 0;         // 0: hardware threads, at most 16 (half of that on a helper thread)
   int spmv_fw_rows = 8;         // spmv_fw_kernel: rows per thread and tile (4: narrow tiles, three CTAs per SM; 8: wide tiles, two)
   int spmv_fw = 1;              // row patterns on field-blocked systems, x windows staged in shared memory by TMA (spmv_fw_kernel).
                                 // Bit mask: 1 = the dual product of an Arnoldi step, 2 = single products, 4 = grouped constraint products.
@@ -249,6 +257,7 @@ struct PhaseTrace {
 // stream-ordered pool (cudaMallocAsync) stalled for up to a second when it had to grow or could not
 // coalesce.  Freed blocks are kept (spis_device_trim releases them) and handed out again on an
 // exact size match, so from the second solve on allocation is free.
+std::atomic<long long> g_h2d_bytes(0);     // bytes the upload entry points actually sent to a device (spis_h2d_bytes)
 std::mutex g_dev_mu;
 std::vector<DevBlock> g_dev_free;
 std::atomic<long long> g_dev_hits(0), g_dev_misses(0), g_dev_miss_bytes(0);
@@ -315,6 +324,7 @@ template <class Tp> void dfree(spis_ctx* ctx, Tp*& p) {
 }
 
 int h2d(spis_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  g_h2d_bytes += (long long)bytes;
   CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, up_stream(ctx)));
   CU(cudaStreamSynchronize(up_stream(ctx)));
   return SPIS_OK;
@@ -1081,6 +1091,196 @@ int spis_host_any_nonzero(const double* p, size_t n, int* out) {
   return SPIS_OK;
 }
 
+}  // extern "C" (templates below)
+
+// ---- row patterns found on the HOST ------------------------------------------------------------------------------
+// try_pattern_storage (below) finds the row stencils of a CSR matrix on the device, AFTER all of it has crossed PCIe:
+// 760 MB and 14.4 ms for the 1e7 lkdv operator, of which 20 MB survive (a 16-bit id per row and a table).  The same
+// question is answered here by a team of host threads reading the caller's arrays in place: consecutive rows almost
+// always share their stencil, so a row is first compared, entry by entry, with the stencil of the row before it
+// (column - row and the value's bits: lossless, exactly the device's criterion), and only a row that differs is
+// hashed and looked up in the thread's own small dictionary.  The threads' dictionaries are merged afterwards.  A
+// matrix that is not of this kind (more than kMaxPatterns distinct rows: unstructured, variable coefficients,
+// assembly round-off) makes every thread give up within a few thousand rows, and the device path takes over.
+// col_shift: column indices >= n_local are ghosts and move by this much (remap_cols_kernel does it on the device).
+namespace {
+
+struct HostPatterns {
+  int npat = 0, maxlen = 0;
+  int64_t changes = 0;                       // rows whose stencil differs from the row before (pattern_assign_kernel's info[5])
+  std::vector<int32_t> rep;                  // representative row of every pattern
+  uint16_t* pid = nullptr;                   // IN: the caller's buffer of nrows entries
+};
+
+inline unsigned long long hmix64(unsigned long long h, unsigned long long e) {
+  h = (h ^ e) * 0xFF51AFD7ED558CCDull;
+  return h ^ (h >> 32);
+}
+
+inline bool same_stencil(const int32_t* indptr, const int32_t* cols, const double* vals, int64_t r, int64_t q,
+                         int32_t n_local, int32_t col_shift) {
+  const int32_t p0 = indptr[r], q0 = indptr[q];
+  const int32_t len = indptr[r + 1] - p0;
+  if (len != indptr[q + 1] - q0) return false;
+  const int32_t dr = (int32_t)(r - q);
+  const uint64_t* vr = reinterpret_cast<const uint64_t*>(vals + p0);
+  const uint64_t* vq = reinterpret_cast<const uint64_t*>(vals + q0);
+  unsigned diff = 0;
+  for (int32_t k = 0; k < len; ++k) {
+    int32_t cr = cols[p0 + k], cq = cols[q0 + k];
+    if (cr >= n_local) cr += col_shift;
+    if (cq >= n_local) cq += col_shift;
+    diff |= (unsigned)((cr - cq) != dr) | (unsigned)(vr[k] != vq[k]);
+  }
+  return diff == 0;
+}
+
+// Row r against the row right before it, whose entries sit right before its own in the CSR arrays: same stencil iff
+// every column is the previous row's + 1 and every value has the same bits (equality with the previous row is equality
+// with its representative).  Fixed lengths are unrolled and vectorised by the compiler; no ghost-column shift here.
+template <int L>
+inline bool same_as_previous_fixed(const int32_t* c, const uint64_t* v) {
+  uint64_t diff = 0;
+#pragma unroll
+  for (int k = 0; k < L; ++k) diff |= (uint64_t)(uint32_t)(c[k] - c[k - L] - 1) | (v[k] ^ v[k - L]);
+  return diff == 0;
+}
+inline bool same_as_previous(const int32_t* c, const uint64_t* v, int len) {
+  switch (len) {
+    case 1: return same_as_previous_fixed<1>(c, v);   case 2: return same_as_previous_fixed<2>(c, v);
+    case 3: return same_as_previous_fixed<3>(c, v);   case 4: return same_as_previous_fixed<4>(c, v);
+    case 5: return same_as_previous_fixed<5>(c, v);   case 6: return same_as_previous_fixed<6>(c, v);
+    case 7: return same_as_previous_fixed<7>(c, v);   case 8: return same_as_previous_fixed<8>(c, v);
+    case 9: return same_as_previous_fixed<9>(c, v);   case 10: return same_as_previous_fixed<10>(c, v);
+    case 11: return same_as_previous_fixed<11>(c, v); case 12: return same_as_previous_fixed<12>(c, v);
+    case 13: return same_as_previous_fixed<13>(c, v); case 14: return same_as_previous_fixed<14>(c, v);
+    case 15: return same_as_previous_fixed<15>(c, v); case 16: return same_as_previous_fixed<16>(c, v);
+    default: {
+      uint64_t diff = 0;
+      for (int k = 0; k < len; ++k) diff |= (uint64_t)(uint32_t)(c[k] - c[k - len] - 1) | (v[k] ^ v[k - len]);
+      return diff == 0;
+    }
+  }
+}
+
+// returns false: not a pattern matrix (or not worth it) -- nothing is kept
+bool host_find_patterns(const int32_t* indptr, const int32_t* cols, const double* vals, int64_t nrows, int32_t n_local,
+                        int32_t col_shift, unsigned nthreads, HostPatterns& out, bool early_reject = true) {
+  if (nrows <= 0 || !out.pid) return false;
+  uint16_t* pid = out.pid;                   // the caller's buffer, nrows entries
+  struct Local { std::vector<unsigned long long> key; std::vector<int32_t> rep; std::vector<int32_t> slot; int count = 0; int64_t changes = 0; bool failed = false; };
+  constexpr int kSlots = 16384;
+  if (nthreads < 1) nthreads = 1;
+  if ((int64_t)nthreads > nrows / 4096 + 1) nthreads = (unsigned)(nrows / 4096 + 1);
+  std::vector<Local> loc(nthreads);
+  std::atomic<int> give_up(0);
+  const int64_t per = (nrows + nthreads - 1) / nthreads;
+  auto work = [&](unsigned t) {
+    Local& L = loc[t];
+    L.key.assign(kSlots, 0ull); L.rep.assign(kSlots, -1);
+    const int64_t lo = (int64_t)t * per, hi = std::min(nrows, lo + per);
+    int64_t last_rep = -1; int last_slot = -1;
+    const uint64_t* vbits = reinterpret_cast<const uint64_t*>(vals);
+    int32_t prevlen = -1;
+    for (int64_t r = lo; r < hi; ++r) {
+      if ((r & 1023) == 0) {
+        if (give_up.load(std::memory_order_relaxed)) { L.failed = true; return; }
+        // storage by patterns needs neighbouring rows to share their stencil (at most one change per eight rows over
+        // the matrix, try_pattern_storage): a range where more than every fourth row changes so far ends the attempt
+        // (swe: ten row types in sequence; a matrix with assembly round-off: every row its own stencil)
+        if (early_reject && r - lo >= 1024 && L.changes * 4 > r - lo) { L.failed = true; give_up.store(1); return; }
+      }
+      const int32_t p0 = indptr[r], p1 = indptr[r + 1];
+      const int32_t len = p1 - p0;
+      if (last_rep >= 0 && len == prevlen) {
+        const bool same = len == 0 ? true
+                          : col_shift == 0 ? same_as_previous(cols + p0, vbits + p0, len)
+                                           : same_stencil(indptr, cols, vals, r, last_rep, n_local, col_shift);
+        if (same) { pid[r] = (uint16_t)last_slot; continue; }
+      }
+      prevlen = len;
+      if (p1 - p0 > kMaxPatternWidth) { L.failed = true; give_up.store(1); return; }
+      unsigned long long h = hmix64(0x9E3779B97F4A7C15ull, (unsigned long long)(p1 - p0));
+      for (int32_t p = p0; p < p1; ++p) {
+        int32_t c = cols[p]; if (c >= n_local) c += col_shift;
+        unsigned long long bits; memcpy(&bits, vals + p, 8);
+        h = hmix64(h, (unsigned long long)(unsigned)(c - (int32_t)r) * 0xD6E8FEB86659FD93ull ^ bits);
+      }
+      h |= 1ull;
+      unsigned slot = (unsigned)(h >> 17) % kSlots;
+      for (int probes = 0;; ++probes) {
+        if (L.key[slot] == 0ull) {
+          if (L.count >= kMaxPatterns) { L.failed = true; give_up.store(1); return; }
+          L.key[slot] = h; L.rep[slot] = (int32_t)r; ++L.count;
+          break;
+        }
+        if (L.key[slot] == h && same_stencil(indptr, cols, vals, r, L.rep[slot], n_local, col_shift)) break;
+        if (probes > 512) { L.failed = true; give_up.store(1); return; }
+        slot = (slot + 1) % kSlots;
+      }
+      if (r > lo) ++L.changes;
+      pid[r] = (uint16_t)slot; last_slot = (int)slot; last_rep = L.rep[slot];
+    }
+  };
+  if (nthreads == 1) work(0);
+  else {
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nthreads; ++t) th.emplace_back(work, t);
+    for (auto& x : th) x.join();
+  }
+  bool failed = give_up.load() != 0;
+  for (auto& L : loc) failed = failed || L.failed;
+  // merge: global patterns in order of (thread, slot); a thread's stencil equal to an earlier one takes its id
+  std::vector<int32_t> grep_;                            // representative rows of the global patterns
+  std::vector<std::vector<int>> map(nthreads);
+  if (!failed) {
+    std::vector<unsigned long long> gkey;
+    for (unsigned t = 0; t < nthreads && !failed; ++t) {
+      map[t].assign(kSlots, -1);
+      for (int sl = 0; sl < kSlots && !failed; ++sl) {
+        if (!loc[t].key[sl]) continue;
+        int g = -1;
+        for (size_t i = 0; i < gkey.size(); ++i)
+          if (gkey[i] == loc[t].key[sl] && same_stencil(indptr, cols, vals, loc[t].rep[sl], grep_[i], n_local, col_shift)) { g = (int)i; break; }
+        if (g < 0) {
+          if ((int)gkey.size() >= kMaxPatterns) { failed = true; break; }
+          g = (int)gkey.size(); gkey.push_back(loc[t].key[sl]); grep_.push_back(loc[t].rep[sl]);
+        }
+        map[t][sl] = g;
+      }
+    }
+  }
+  if (failed) return false;
+  // local slot numbers -> global ids; stencil changes across the seams between the threads' ranges
+  int64_t changes = 0;
+  auto remap = [&](unsigned t) {
+    const int64_t lo = (int64_t)t * per, hi = std::min(nrows, lo + per);
+    const std::vector<int>& m = map[t];
+    for (int64_t r = lo; r < hi; ++r) pid[r] = (uint16_t)m[pid[r]];
+  };
+  if (nthreads == 1) remap(0);
+  else {
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nthreads; ++t) th.emplace_back(remap, t);
+    for (auto& x : th) x.join();
+  }
+  for (unsigned t = 0; t < nthreads; ++t) {
+    changes += loc[t].changes;
+    const int64_t lo = (int64_t)t * per;
+    if (t > 0 && lo < nrows && pid[lo] != pid[lo - 1]) ++changes;
+  }
+  out.npat = (int)grep_.size();
+  out.rep = grep_;
+  out.maxlen = 0;
+  for (int32_t r : grep_) out.maxlen = std::max(out.maxlen, (int)(indptr[r + 1] - indptr[r]));
+  out.changes = changes;
+  return out.npat >= 1;
+}
+
+}  // namespace
+
+extern "C" {
+
 static bool is_pinned_host(const void* p) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -1389,6 +1589,11 @@ int spis_small_kkt(int m, int ldh, const double* H, double beta, int nc, const d
   return SPIS_OK;
 }
 
+// bytes the upload entry points (matrices, vectors, preconditioner data) have sent to devices since the last reset
+long long spis_h2d_bytes(int reset) {
+  return reset ? g_h2d_bytes.exchange(0) : g_h2d_bytes.load();
+}
+
 int spis_abi_version(void) { return SPIS_ABI_VERSION; }
 
 const char* spis_last_error(const spis_ctx* ctx) { return ctx ? ctx->err : g_global_err; }
@@ -1574,6 +1779,9 @@ int spis_set_option(spis_ctx* ctx, const char* key, int64_t value) {
   else if (k == "spmv_multi") { ctx->spmv_multi = value ? 1 : 0; }
   else if (k == "spmv_dual") { ctx->spmv_dual = value ? 1 : 0; }
   else if (k == "hess_async") ctx->hess_async = value != 0;
+  else if (k == "host_pattern") ctx->host_pattern = value != 0;
+  else if (k == "host_pattern_min_nnz") ctx->host_pattern_min_nnz = value;
+  else if (k == "host_threads") { REQUIRE(value >= 0 && value <= 256, "host_threads out of range"); ctx->host_threads = (int)value; }
   else if (k == "gram") ctx->gram = value != 0;
   else if (k == "spmv_fw_rows") { REQUIRE(value == 4 || value == 8, "spmv_fw_rows must be 4 or 8"); ctx->spmv_fw_rows = (int)value; }
   else if (k == "spmv_sellw") { REQUIRE(value >= 0 && value <= 7, "spmv_sellw is a bit mask 0..7"); ctx->spmv_sellw = (int)value; }
@@ -1827,6 +2035,86 @@ static int try_field_windows(spis_ctx* ctx, Matrix& M, cudaStream_t s) {
   return SPIS_OK;
 }
 
+// The host-side detection alone (no device involved): pid_out[nrows], rep_out[<= 4096] representative rows.  *npat_out = 0:
+// the matrix is not a pattern matrix.  For tests and for callers that want to know before they build a context.
+int spis_host_find_patterns(const int32_t* indptr, const int32_t* indices, const double* data, int64_t nrows, int64_t n_local,
+                            int64_t col_shift, int nthreads, uint16_t* pid_out, int32_t* rep_out, int* npat_out,
+                            int* maxlen_out, int64_t* changes_out) {
+  if (!indptr || !npat_out || nrows < 0 || (nrows > 0 && indptr[nrows] > 0 && (!indices || !data))) return SPIS_E_INVALID;
+  *npat_out = 0;
+  HostPatterns hp;
+  std::vector<uint16_t> tmp;
+  if (!pid_out) { tmp.resize((size_t)nrows); pid_out = tmp.data(); }
+  hp.pid = pid_out;
+  if (!host_find_patterns(indptr, indices, data, nrows, (int32_t)n_local, (int32_t)col_shift, nthreads > 0 ? (unsigned)nthreads : 1u, hp)) return SPIS_OK;
+  if (rep_out) for (int p = 0; p < hp.npat; ++p) rep_out[p] = hp.rep[p];
+  *npat_out = hp.npat;
+  if (maxlen_out) *maxlen_out = hp.maxlen;
+  if (changes_out) *changes_out = hp.changes;
+  return SPIS_OK;
+}
+
+// Row patterns of a HOST CSR matrix (host_find_patterns) -> pattern storage on the device, under the acceptance rules of
+// try_pattern_storage.  *ok_out = 0: not applicable, nothing allocated, the caller uploads the CSR arrays.
+static int host_pattern_upload(spis_ctx* ctx, Matrix& M, cudaStream_t s, const int32_t* indptr, const int32_t* cols,
+                               const double* vals, int* ok_out) {
+  *ok_out = 0;
+  PhaseTrace pt;
+  unsigned nt = std::thread::hardware_concurrency();
+  if (nt == 0) nt = 4;
+  if (nt > 16) nt = 16;
+  if (ctx->host_threads > 0) nt = (unsigned)ctx->host_threads;
+  else if (tl_use_aux && nt > 4) nt /= 2;          // helper thread: leave cores to the thread that feeds the GPU
+  const int32_t shift = (ctx->n_halo > 0 && ctx->hoff != ctx->n) ? (int32_t)(ctx->hoff - ctx->n) : 0;
+  HostPatterns hp;
+  void* pinned = nullptr;
+  if (spis_pinned_alloc((size_t)M.nrows * sizeof(uint16_t), &pinned) != SPIS_OK) { ctx->err[0] = 0; return SPIS_OK; }
+  hp.pid = static_cast<uint16_t*>(pinned);
+  pt.mark("host patterns: id buffer");
+  if (!host_find_patterns(indptr, cols, vals, M.nrows, (int32_t)ctx->n, shift, nt, hp, ctx->fmt_pref != SPIS_FMT_PATTERN)) {
+    spis_pinned_free(pinned); pt.mark("host patterns: not applicable"); return SPIS_OK;
+  }
+  pt.mark("host patterns: found");
+  const int npat = hp.npat, maxlen = hp.maxlen;
+  const int W = maxlen < 4 ? 4 : (maxlen + 3) / 4 * 4;
+  const bool forced = ctx->fmt_pref == SPIS_FMT_PATTERN;
+  if (npat > kMaxPatterns || maxlen > kMaxPatternWidth ||
+      (!forced && ((double)npat * W * 8.0 > (double)M.nnz || (double)hp.changes * 8.0 > (double)M.nrows))) {
+    spis_pinned_free(hp.pid);
+    return SPIS_OK;
+  }
+  std::vector<int32_t> len(npat), off((size_t)npat * W, 0);
+  std::vector<double> val((size_t)npat * W, 0.0);
+  for (int p = 0; p < npat; ++p) {
+    const int32_t r = hp.rep[p], p0 = indptr[r];
+    len[p] = indptr[r + 1] - p0;
+    for (int k = 0; k < len[p]; ++k) {
+      int32_t c = cols[p0 + k]; if (c >= (int32_t)ctx->n) c += shift;
+      off[(size_t)p * W + k] = c - r;
+      val[(size_t)p * W + k] = vals[p0 + k];
+    }
+  }
+  auto drop = [&]() { dfree(ctx, M.pid); dfree(ctx, M.tab_len); dfree(ctx, M.tab_off); dfree(ctx, M.tab_val); spis_pinned_free(hp.pid); };
+  int rc = dalloc(ctx, &M.pid, (size_t)M.nrows, false);
+  if (rc == SPIS_OK) rc = dalloc(ctx, &M.tab_len, (size_t)npat, false);
+  if (rc == SPIS_OK) rc = dalloc(ctx, &M.tab_off, (size_t)npat * W, false);
+  if (rc == SPIS_OK) rc = dalloc(ctx, &M.tab_val, (size_t)npat * W, false);
+  if (rc != SPIS_OK) { drop(); return rc; }
+  pt.mark("host patterns: device blocks");
+  cudaError_t e = cudaMemcpyAsync(M.pid, hp.pid, (size_t)M.nrows * sizeof(uint16_t), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(M.tab_len, len.data(), (size_t)npat * sizeof(int32_t), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(M.tab_off, off.data(), off.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(M.tab_val, val.data(), val.size() * sizeof(double), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);           // the staging arrays must outlive the copies
+  if (e != cudaSuccess) { drop(); return fail(ctx, SPIS_E_CUDA, "pattern upload failed: %s", cudaGetErrorString(e)); }
+  spis_pinned_free(hp.pid);
+  g_h2d_bytes += (long long)((size_t)M.nrows * sizeof(uint16_t) + (size_t)npat * (4 + (size_t)W * 12));
+  M.npat = npat; M.patW = W;
+  pt.mark("host patterns: uploaded");
+  *ok_out = 1;
+  return SPIS_OK;
+}
+
 int spis_upload_csr(spis_ctx* ctx, int slot, int64_t nrows, int64_t ncols, int64_t nnz,
                     const int32_t* indptr, const int32_t* indices, const double* data) {
   if (!ctx) return SPIS_E_INVALID;
@@ -1840,10 +2128,24 @@ int spis_upload_csr(spis_ctx* ctx, int slot, int64_t nrows, int64_t ncols, int64
   Matrix& M = ctx->mats[slot];
   free_matrix(ctx, M);
   M.nrows = nrows; M.ncols = ncols; M.nnz = nnz;
+  // Row patterns found by host threads in the caller's arrays: 2 bytes per row cross PCIe instead of 12 per entry
+  if (ctx->host_pattern && nnz >= ctx->host_pattern_min_nnz &&
+      (ctx->fmt_pref == SPIS_FMT_PATTERN || (ctx->fmt_pref == SPIS_FMT_AUTO && ctx->auto_pattern))) {
+    int ok = 0;
+    TRY(host_pattern_upload(ctx, M, s, indptr, indices, data, &ok));
+    if (ok) {
+      M.fmt = SPIS_FMT_PATTERN;
+      M.nnz_padded = nnz;
+      TRY(try_field_windows(ctx, M, s));
+      M.present = true;
+      return SPIS_OK;
+    }
+  }
   TRY(dalloc(ctx, &M.indptr, (size_t)nrows + 1, false));
   TRY(dalloc(ctx, &M.cols, (size_t)nnz, false));
   TRY(dalloc(ctx, &M.vals, (size_t)nnz, false));
   CU(cudaMemcpyAsync(M.indptr, indptr, ((size_t)nrows + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  g_h2d_bytes += (long long)(((size_t)nrows + 1) * sizeof(int32_t) + (size_t)nnz * 12);
   if (nnz) {
     CU(cudaMemcpyAsync(M.cols, indices, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(M.vals, data, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, s));

@@ -20,6 +20,7 @@ ordering; the kernels themselves are covered by the single-GPU tests.
 """
 from __future__ import annotations
 
+import os
 import collections
 import ctypes as C
 
@@ -272,6 +273,9 @@ class DistributedSession(solvers.DeviceSession):
             ctx = ctx_factory(n, kk, device=(comm.device if comm.cuda else 0), n_halo=plan.n_halo,
                               stream=comm.stream_handle())
             ctx.halo_set_plan(plan.send_idx)
+            # the ranks of one node share its cores: the host threads that look for row patterns are divided among them
+            local_world = int(os.environ.get("LOCAL_WORLD_SIZE", comm.world) or comm.world)
+            ctx.set_option("host_threads", max(1, min(16, (os.cpu_count() or 4) // max(1, local_world))))
             if transport == "p2p":
                 ctx.attach_comm(peer)
                 ctx.xcomm_set_halo(entry["dest_rank"], entry["dest_off"], entry["send_to"], entry["recv_from"])

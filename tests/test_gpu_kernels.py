@@ -75,6 +75,43 @@ def test_spmv_pattern_storage_detection_and_fallback():
     np.testing.assert_allclose(y, W @ x, rtol=1e-14, atol=1e-14)
 
 
+@pytest.mark.parametrize("case", ["tridiag", "lkdv", "perturbed", "swe"])
+def test_row_patterns_found_on_the_host_equal_the_device_detection(case):
+    """With option host_pattern = 1 spis_upload_csr looks for the row stencils in the caller's arrays with host threads
+    first (matrices above host_pattern_min_nnz entries): the CSR arrays then never cross PCIe.  Same storage decision,
+    same number of stencils and the same SpMV bits as the detection on the device (the default)."""
+    from structurepreservingiterativesolvers_b200.problems import swe
+    rng = np.random.default_rng(17)
+    if case == "tridiag":
+        n = 50_001
+        T = sps.diags([np.full(n - 1, -1.0), np.full(n, 2.5), np.full(n - 1, -1.25)], [-1, 0, 1], format="lil")
+        T[0, n - 1] = -1.0; T[n - 1, 0] = -1.25
+        A = T.tocsr()
+    elif case in ("lkdv", "perturbed"):
+        A = lkdv.linforms(space="CG", M=33_350, mlength=0.8 * 33_350)[0]["A"].tocsr()
+        if case == "perturbed":
+            A = A.copy(); A.data = A.data * (1.0 + 1e-13 * rng.standard_normal(A.nnz))
+    else:
+        A = swe.linforms(M=40, mlength=32.0)[0]["A"].tocsr()       # column - row drifts from row to row: no patterns
+    n = A.shape[0]
+    x = rng.standard_normal(n)
+    out = []
+    for host in (1, 0):
+        with KrylovContext(n, 2) as ctx:
+            ctx.set_option("host_pattern", host)
+            ctx.set_option("host_pattern_min_nnz", 0)
+            ctx.set_option("host_threads", 3)
+            ctx.upload_matrix(nat.SLOT_A, A)
+            fmt = ctx.info(f"fmt:{nat.SLOT_A}")
+            out.append((fmt, ctx.info(f"npat:{nat.SLOT_A}") if fmt == nat.FMT_PATTERN else -1, ctx.info(f"fw_fields:{nat.SLOT_A}"),
+                        ctx.op_spmv(nat.SLOT_A, x)))
+    assert out[0][:3] == out[1][:3]
+    assert (out[0][0] == nat.FMT_PATTERN) == (case in ("tridiag", "lkdv"))
+    np.testing.assert_array_equal(out[0][3], out[1][3])
+    scale = np.abs(A) @ np.abs(x)
+    assert np.max(np.abs(out[0][3] - A @ x) / scale) <= 1e-14
+
+
 def test_spmv_value_dictionary_storage():
     """SELLD: 8-bit codes for the values when the matrix holds at most 256 distinct doubles (bit patterns)."""
     from structurepreservingiterativesolvers_b200.problems import swe

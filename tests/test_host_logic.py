@@ -541,3 +541,58 @@ def test_evolve_mirrors_of_swe_and_lkdvrk_follow_the_oracle_loops():
             for i, (a, b) in enumerate(zip(out["sol"], ref)):
                 assert helpers.rel_diff(a, b) <= 1e-10 * max(i, 1), (structured, i)
             assert max(out["dm"].max(), out["dmo"].max(), out["de"].max()) <= 1e-12 * abs(ref[0]).sum()
+
+
+def test_host_side_row_pattern_detection():
+    """spis_host_find_patterns (no device): rows with identical (column - row, value bits) lists share an id, the ids of
+    every thread count describe the same partition, a value that differs in its last bit is its own stencil, ghost
+    columns move by col_shift, and matrices whose neighbouring rows do not share stencils are given up early."""
+    import ctypes as C
+    import scipy.sparse as sps
+    from structurepreservingiterativesolvers_b200 import _native as nat
+    from structurepreservingiterativesolvers_b200.problems import lkdv
+    lib = nat.load_library()
+
+    def detect(A, nthreads, n_local=None, shift=0):
+        A = A.tocsr(); n = A.shape[0]
+        ip = np.ascontiguousarray(A.indptr, dtype=np.int32); ci = np.ascontiguousarray(A.indices, dtype=np.int32)
+        da = np.ascontiguousarray(A.data, dtype=np.float64)
+        pid = np.zeros(n, dtype=np.uint16); rep = np.zeros(4096, dtype=np.int32)
+        npat, ml, ch = C.c_int(0), C.c_int(0), C.c_int64(0)
+        rc = lib.spis_host_find_patterns(ip.ctypes.data_as(C.POINTER(C.c_int32)), ci.ctypes.data_as(C.POINTER(C.c_int32)), nat.dptr(da), n,
+                                         n if n_local is None else n_local, shift, nthreads, pid.ctypes.data_as(C.POINTER(C.c_uint16)),
+                                         rep.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(npat), C.byref(ml), C.byref(ch))
+        assert rc == 0
+        return pid, rep[: npat.value], npat.value, ml.value, ch.value
+
+    def signature(A, r, n_local=None, shift=0):
+        c = A.indices[A.indptr[r]: A.indptr[r + 1]].astype(np.int64)
+        if n_local is not None:
+            c = np.where(c >= n_local, c + shift, c)
+        return tuple(c - r) + tuple(A.data[A.indptr[r]: A.indptr[r + 1]].view(np.int64))
+
+    A = lkdv.linforms(space="CG", M=7_001, mlength=0.8 * 7_001)[0]["A"].tocsr()
+    n = A.shape[0]
+    sigs = [signature(A, r) for r in range(n)]
+    truth = len(set(sigs))
+    for nt in (1, 2, 5):
+        pid, rep, npat, ml, ch = detect(A, nt)
+        assert npat == truth and ml == np.diff(A.indptr).max()
+        assert all(sigs[r] == sigs[rep[pid[r]]] for r in range(n))
+        assert len({sigs[q] for q in rep}) == npat                         # no stencil twice in the table
+        assert ch == int(np.sum(pid[1:] != pid[:-1]))
+    B = A.copy(); B.data[B.indptr[1234]] = np.nextafter(B.data[B.indptr[1234]], np.inf)
+    assert detect(B, 3)[2] == truth + 1
+    # ghost columns: the last 5 columns belong to a neighbour and live 11 entries further out in the device vector
+    S = sps.lil_matrix((60, 65))
+    for r in range(60):
+        S[r, r] = 1.0; S[r, r + 1] = -2.0                                # row 59 reaches ghost column 60
+    S[0, 64] = 3.0
+    S = S.tocsr()
+    pid, rep, npat, ml, ch = detect(S, 2, n_local=60, shift=11)
+    sg = [signature(S, r, 60, 11) for r in range(60)]
+    assert npat == len(set(sg)) and all(sg[r] == sg[rep[pid[r]]] for r in range(60))
+    # every row its own stencil: given up (npat = 0) without reading the matrix to the end
+    rng = np.random.default_rng(5)
+    V = sps.diags([rng.standard_normal(49_999), rng.standard_normal(50_000)], [-1, 0], format="csr")
+    assert detect(V, 4)[2] == 0
