@@ -656,6 +656,36 @@ def run_ours(args):
         guarded("jacobi", lambda: extra_run("jacobi", A, b, x0, conlist, tol, local, pre=JacobiPreconditioner(A), peak=peak,
                                             note="point Jacobi on the device (fused into the last sweep)")[0])
 
+        def other_solver(which):
+            # the path's other two entry points on the same system: gmres (solvers.py:58-127) to the same tolerance,
+            # cgmres_p (solvers.py:328-445: always k iterations, one more constraint switched on per iteration) at k = 20
+            def run():
+                sess2 = solvers.DeviceSession(A, b, x0, K_KRYLOV if which == "gmres" else 20,
+                                              conlist=() if which == "gmres" else dic["conlist3"], device=local)
+
+                def one(s2):
+                    with warnings.catch_warnings():
+                        warnings.simplefilter("ignore")
+                        if which == "gmres":
+                            return solvers.gmres(A, b, x0, K_KRYLOV, tol=tol, session=s2, small_solver="kkt", device=local)
+                        xp, ip = solvers.cgmres_p(A, b, x0, 20, conlist=dic["conlist3"], session=s2, small_solver="kkt", device=local)
+                        return xp, dict(ip, steps=20)          # (the reference's dict has no 'steps': it always runs k)
+                iters, secs2, per, xs, infos, _ = timed_solves(sess2, one, 3, 2)
+                sess2.ctx.set_option("profile", 1); sess2.ctx.reset_profile()
+                one(sess2); sess2.ctx.sync()
+                prof2 = sess2.ctx.profile()
+                sess2.close()
+                res = float(np.linalg.norm(A @ xs - b))
+                return {"value": iters / secs2, "unit": "it/s", "ms_per_step": 1e3 * secs2 / 3, "krylov_steps": int(infos["steps"]),
+                        "final_residual": float(infos["res"][-1]), "true_residual_on_host": res, "steps": 3, "warmup": 2,
+                        "invariant_rel_dev": invariant_devs(args.workload, dic, xs, dic["conlist3"]) if which != "gmres" else None,
+                        "kernels": kernel_table(prof2, 1, peak),
+                        "note": ("solvers.gmres, same system and tolerance, device-resident loop" if which == "gmres" else
+                                 "solvers.cgmres_p, k = 20, mass + momentum + energy switched on one per iteration, KKT small solve, host-driven loop")}
+            return run
+        guarded("gmres", other_solver("gmres"))
+        guarded("cgmres_p", other_solver("cgmres_p"))
+
         def other(workload, n_target):
             d2, x02, cl2, _, pre2, _ = build_system(n_target, workload)
             tol2 = workload_tol(workload, d2)

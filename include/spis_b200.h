@@ -232,6 +232,11 @@ int spis_constraint_define(spis_ctx* ctx, int c, int mat_slot, const double* v, 
 /* term0 (scalar), term1 (m), term2 (m x m row-major) for Z = z[:m].T, incremental in m:
  * MZ = M@Z (:33), term0 (:34), term1 = v@Z + x0@MZ (:35), term2 = 1/2 Z.T@MZ (:36)      */
 int spis_constraint_terms(spis_ctx* ctx, int c, int m, double* term0, double* term1, double* term2);
+/* The same for nc constraints cs[0..nc) at once: term0[nc], term1[nc][m], term2[nc][m][m].  When every constraint is one
+ * column behind m (a constrained iteration, solvers.py:242-247; every iteration of cgmres_p, :398-407) the quadratic ones
+ * share ONE pass over Z (their M z_col as up to four right-hand sides), one cross-rank reduction and one
+ * synchronisation; otherwise this is spis_constraint_terms per constraint.                                            */
+int spis_constraint_terms_batch(spis_ctx* ctx, int nc, const int32_t* cs, int m, double* term0, double* term1, double* term2);
 /* replaces the scalar of a defined constraint (time loops: same M and v, new invariant values per step) */
 int spis_constraint_set_constant(spis_ctx* ctx, int c, double cc);
 /* replaces the linear term v of a defined constraint (NULL: no linear term); the matrix stays where it is */

@@ -82,6 +82,7 @@ SIGNATURES = {
     "spis_h2d_bytes": (C.c_longlong, [C.c_int]),
     "spis_host_find_patterns": (C.c_int, [_ip, _ip, _dp, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.POINTER(C.c_uint16), _ip,
                                           C.POINTER(C.c_int), C.POINTER(C.c_int), _lp]),
+    "spis_constraint_terms_batch": (C.c_int, [_ctx, C.c_int, _ip, C.c_int, _dp, _dp, _dp]),
     "spis_small_settle": (C.c_int, [C.c_int, C.c_int, _dp, _dp, _dp, _dp, C.c_int, C.POINTER(C.c_int)]),
     "spis_small_kkt": (C.c_int, [C.c_int, C.c_int, _dp, C.c_double, C.c_int, _dp, _dp, _dp, _dp, _dp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "spis_download_vec": (C.c_int, [_ctx, C.c_int, C.c_int, _dp, C.c_int64]),

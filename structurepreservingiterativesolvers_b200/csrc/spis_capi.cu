@@ -124,6 +124,7 @@ struct spis_ctx {
                                 // per solve against 6.63, lkdv forced to SELL 5.78 against 5.16: an LDS crosses the same data pipe as an
                                 // L1 hit, the TMA writes of the windows add to it, and two CTAs of 8 consumer warps hide the latency of
                                 // the matrix stream worse than four to five CTAs of the plain kernels.
+  int batch_terms = 1;          // spis_constraint_terms_batch: one pass over Z for all quadratic constraints when one column is new
   int hess_async = 1;           // pipelined loop: the Givens / least-squares kernel runs beside the normalising sweep
   // Look for row patterns in the caller's CSR arrays with host threads before anything is uploaded.  OFF by default:
   // on the bench box (16 hardware threads, PCIe 5) the detection alone runs at 94 GB/s (8.1 ms for the 760 MB lkdv
@@ -1779,6 +1780,7 @@ int spis_set_option(spis_ctx* ctx, const char* key, int64_t value) {
   else if (k == "spmv_multi") { ctx->spmv_multi = value ? 1 : 0; }
   else if (k == "spmv_dual") { ctx->spmv_dual = value ? 1 : 0; }
   else if (k == "hess_async") ctx->hess_async = value != 0;
+  else if (k == "batch_terms") ctx->batch_terms = value != 0;
   else if (k == "host_pattern") ctx->host_pattern = value != 0;
   else if (k == "host_pattern_min_nnz") ctx->host_pattern_min_nnz = value;
   else if (k == "host_threads") { REQUIRE(value >= 0 && value <= 256, "host_threads out of range"); ctx->host_threads = (int)value; }
@@ -3166,6 +3168,94 @@ static int constraint_terms_impl(spis_ctx* ctx, int c, int m, double* term0, dou
   for (int i = 0; i < m; ++i) term1[i] = C.T1[i];
   for (int i = 0; i < m; ++i)
     for (int k = 0; k < m; ++k) term2[(size_t)i * m + k] = C.T2[(size_t)i * ctx->kmax + k];
+  return SPIS_OK;
+}
+
+// The reduced terms of SEVERAL constraints for the same m in one call.  The common case of a constrained iteration -- one
+// new basis column, every constraint one column behind (solvers.py:242-247 rebuilds them all every iteration; cgmres_p
+// does nothing else) -- is served in ONE pass over Z for all quadratic constraints together (mdotm_kernel: M_c z_col as
+// up to four right-hand sides) with one cross-rank reduction, one copy to the host and one synchronisation, instead of
+// a pass, a reduction and a synchronisation per constraint.  Anything else goes through spis_constraint_terms per
+// constraint.  term1: nc x m, term2: nc x m x m (row-major, constraint by constraint).
+int spis_constraint_terms_batch(spis_ctx* ctx, int nc, const int32_t* cs, int m, double* term0, double* term1, double* term2) {
+  if (!ctx) return SPIS_E_INVALID;
+  REQUIRE(nc >= 1 && nc <= SPIS_MAX_SLOTS && cs && term0 && term1 && term2, "bad batch arguments");
+  REQUIRE(m >= 1 && m <= ctx->kmax, "m=%d out of range", m);
+  for (int i = 0; i < nc; ++i)
+    REQUIRE(cs[i] >= 0 && cs[i] < SPIS_MAX_SLOTS && ctx->cons[cs[i]].defined, "constraint %d not defined", cs[i]);
+  REQUIRE(ctx->began, "spis_solve_begin has not been called");
+  CU(cudaSetDevice(ctx->device));
+  int quad[4]; int nq = 0;
+  bool fast = ctx->batch_terms != 0;
+  for (int i = 0; i < nc && fast; ++i) {
+    const Constraint& C = ctx->cons[cs[i]];
+    fast = C.term0_done && C.cols_done == m - 1;
+    for (int k = 0; k < i && fast; ++k) fast = cs[k] != cs[i];
+    if (fast && C.slot >= 0) {
+      if (C.symmetric == 1 && nq < 4) quad[nq++] = i; else fast = false;
+    }
+  }
+  const size_t ld = (size_t)ctx->ld;
+  const bool x0nz = !ctx->x0_is_zero;
+  const double* extra = x0nz ? ctx->X0 : nullptr;
+  const int nrows = m + (extra ? 1 : 0);
+  const int nw = nq <= 1 ? nq : nq == 2 ? 2 : 4;
+  const int64_t count = (int64_t)nw * nrows + 2 * nc;
+  if (fast && (nq == 0 || nw * nrows > ctx->pstride || count > (int64_t)ctx->kmax * 2 * ctx->K)) fast = false;
+  if (!fast) {
+    for (int i = 0; i < nc; ++i)
+      TRY(spis_constraint_terms(ctx, cs[i], m, term0 + i, term1 + (size_t)i * m, term2 + (size_t)i * m * m));
+    return SPIS_OK;
+  }
+  const int col = m - 1;
+  const int km = ctx->kmax;
+  double* Zb = zbase(ctx);
+  double* zc = Zb + (size_t)col * ld;
+  if (!ctx->G) TRY(dalloc(ctx, &ctx->G, 4 * ld));
+  double* o_m = ctx->d_cout;                       // [nw][nrows]: row_i . (M_q z_col), then x0 . (M_q z_col)
+  double* o_v = ctx->d_cout + (size_t)nw * nrows;  // [nc][2]: v_c . z_col
+  if (ctx->allreduce || ctx->xactive) CU(cudaMemsetAsync(ctx->d_cout, 0, (size_t)count * sizeof(double), ctx->stream));
+  ctx->defer_allreduce = true;
+  int rc = SPIS_OK;
+  for (int q = 0; q < nq && rc == SPIS_OK; ++q)      // M_q z_col (ghosts of z_col were filled by its Arnoldi step)   (:33)
+    rc = launch_spmv(ctx, ctx->cons[cs[quad[q]]].slot, 0, zc, nullptr, ctx->G + (size_t)q * ld, nullptr);
+  if (rc == SPIS_OK) {                               // column `col` of every Z^T M_q Z, and x0 . M_q z_col          (:35-36)
+    if (nq == 1) rc = launch_mdot(ctx, Zb, m, extra, 0, ctx->G, o_m);
+    else rc = launch_mdotm(ctx, nw, Zb, m, extra, ctx->G, (int64_t)ld, o_m);
+  }
+  for (int i = 0; i < nc && rc == SPIS_OK; ++i) {
+    const Constraint& C = ctx->cons[cs[i]];
+    if (C.v) rc = launch_mdot(ctx, zc, 1, nullptr, 0, C.v, o_v + 2 * i);
+  }
+  ctx->defer_allreduce = false;
+  if (rc != SPIS_OK) return rc;
+  TRY(do_allreduce(ctx, ctx->d_cout, count, true));
+  TRY(d2h(ctx, ctx->h_cout, ctx->d_cout, (size_t)count * sizeof(double)));
+  const double* hv = ctx->h_cout + (size_t)nw * nrows;
+  for (int i = 0; i < nc; ++i) {
+    Constraint& C = ctx->cons[cs[i]];
+    double t1 = 0.0;
+    int q = -1;
+    for (int k = 0; k < nq; ++k) if (quad[k] == i) q = k;
+    if (q >= 0) {
+      const double* oA = ctx->h_cout + (size_t)q * nrows;
+      for (int r = 0; r <= col; ++r) {
+        C.T2[(size_t)r * km + col] = 0.5 * oA[r];
+        C.T2[(size_t)col * km + r] = 0.5 * oA[r];
+      }
+      if (x0nz) t1 += oA[m];
+    }
+    if (C.v) t1 += hv[2 * i];
+    C.T1[col] = t1;
+    C.cols_done = m;
+  }
+  for (int i = 0; i < nc; ++i) {
+    const Constraint& C = ctx->cons[cs[i]];
+    term0[i] = C.term0;
+    for (int r = 0; r < m; ++r) term1[(size_t)i * m + r] = C.T1[r];
+    for (int r = 0; r < m; ++r)
+      for (int k = 0; k < m; ++k) term2[((size_t)i * m + r) * m + k] = C.T2[(size_t)r * km + k];
+  }
   return SPIS_OK;
 }
 

@@ -271,6 +271,16 @@ class KrylovContext:
         self._check(self._lib.spis_constraint_terms(self._h, c, m, C.byref(t0), nat.dptr(t1), nat.dptr(t2)))
         return t0.value, t1, t2
 
+    def constraint_terms_batch(self, cs, m: int):
+        """[(term0, term1, term2)] for the constraints cs, one device round trip when each is one column behind m."""
+        cs = np.ascontiguousarray(cs, dtype=np.int32)
+        nc = cs.size
+        t0 = np.empty(nc, dtype=np.float64)
+        t1 = np.empty((nc, m), dtype=np.float64)
+        t2 = np.empty((nc, m, m), dtype=np.float64)
+        self._check(self._lib.spis_constraint_terms_batch(self._h, nc, nat.iptr(cs), m, nat.dptr(t0), nat.dptr(t1), nat.dptr(t2)))
+        return [(float(t0[i]), t1[i], t2[i]) for i in range(nc)]
+
     # -- downloads / bridges ------------------------------------------------------------------------
     def download(self, which: int, j: int = 0, pinned: bool = False) -> np.ndarray:
         self._live()

@@ -412,13 +412,18 @@ class DeviceSession:
         """Reduced constraints for Z = z[:m].T (the reference rebuilds these per step, solvers.py:242-247)."""
         self._join_setup()
         out = []
-        for idx, entry in enumerate(self._cons):
+        for entry in self._cons:
             if entry["kind"] == "invalid":
                 raise NotImplementedError("Constraints must be either dictionaries or classes")
             if entry["error"] is not None:
                 raise entry["error"]
+        classes = [idx for idx, entry in enumerate(self._cons) if entry["kind"] == "class"]
+        batch = {}
+        if len(classes) > 1 and hasattr(self.ctx, "constraint_terms_batch"):
+            batch = dict(zip(classes, self.ctx.constraint_terms_batch(classes, m)))    # one device round trip for all of them
+        for idx, entry in enumerate(self._cons):
             if entry["kind"] == "class":
-                t0, t1, t2 = self.ctx.constraint_terms(idx, m)
+                t0, t1, t2 = batch[idx] if idx in batch else self.ctx.constraint_terms(idx, m)
                 out.append(smallsolve.ReducedConstraint(t0, t1, t2))
             else:
                 out.append(smallsolve.ReducedConstraint(callbacks=entry["const"], x0=self.x0_host,

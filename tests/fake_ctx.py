@@ -334,6 +334,10 @@ class FakeKrylovContext:
         self.cons[c]["c"] = cc
         self.cons[c]["t0"] = None
 
+    def constraint_terms_batch(self, cs, m):
+        self.log.append(("constraint_terms_batch", tuple(int(c) for c in cs), m))
+        return [self.constraint_terms(int(c), m) for c in cs]
+
     def constraint_terms(self, c, m):
         C = self.cons[c]
         n = self.n

@@ -576,6 +576,68 @@ def test_linear_invariants_ride_in_the_one_pass_reduction(m, x0_zero, own_v):
     np.testing.assert_allclose(quad[2], ref[1][2], rtol=0, atol=1e-13 * np.abs(ref[1][2]).max())
 
 
+@pytest.mark.parametrize("x0_zero,nquad", [(True, 2), (False, 2), (True, 3), (False, 1)])
+def test_constraint_terms_of_all_constraints_in_one_pass(x0_zero, nquad):
+    """spis_constraint_terms_batch: when every constraint is one column behind (a constrained iteration,
+    solvers.py:242-247; every iteration of cgmres_p) the quadratic ones share one pass over Z -- their M z_col as the
+    right-hand sides of one mdotm launch -- one reduction and one synchronisation.  Same terms as the per-constraint
+    calls (option batch_terms = 0) to rounding, and as numpy; fewer launches."""
+    rng = np.random.default_rng(41 + nquad)
+    d = lkdv.linforms(space="CG", M=3_337, mlength=0.8 * 3_337)[0]
+    A = d["A"]
+    n = A.shape[0]
+    Ms = []
+    for q in range(nquad):
+        L = (d["L"] if q % 2 == 0 else d["A"]).tocsr() * (1.0 + 0.25 * q)
+        Ms.append(((L + L.T) * 0.5).tocsr())
+    b = rng.standard_normal(n)
+    x0 = np.zeros(n) if x0_zero else 0.01 * rng.standard_normal(n)
+    vs = [rng.standard_normal(n) if q != 1 else None for q in range(nquad)] + [rng.standard_normal(n)]
+    steps = 11
+    out = []
+    for batch in (1, 0):
+        with KrylovContext(n, 16) as ctx:
+            ctx.set_option("batch_terms", batch)
+            ctx.upload_matrix(nat.SLOT_A, A)
+            for q, Mq in enumerate(Ms):
+                ctx.upload_matrix(nat.SLOT_CON0 + q, Mq)
+            ctx.upload_vec(nat.VEC_B, b)
+            ctx.upload_vec(nat.VEC_X0, x0)
+            ctx.set_option("x0_is_zero", 1 if x0_zero else 0)
+            for q in range(nquad):
+                ctx.constraint_define(q, nat.SLOT_CON0 + q, vs[q], 0.25 + q)
+            ctx.constraint_define(nquad, -1, vs[nquad], -0.5)                      # a linear one
+            ctx.solve_begin()
+            cs = list(range(nquad + 1))
+            terms, launches = [], 0
+            for j in range(steps):
+                ctx.arnoldi_step(j)
+                ctx.reset_profile()
+                terms.append(ctx.constraint_terms_batch(cs, j + 1))
+                launches += ctx.profile()["mdot"]["launches"]
+            out.append((terms, ctx.download_Z(0, steps), launches))
+    (tb, Z, lb), (ts, _, ls) = out
+    if nquad > 1:
+        assert lb < ls
+    for j in range(steps):
+        Zj = Z[: j + 1]
+        for c in range(nquad + 1):
+            t0, t1, t2 = tb[j][c]
+            s0, s1, s2 = ts[j][c]
+            assert t0 == s0
+            if c < nquad:
+                MZ = Ms[c] @ Zj.T
+                ref2 = 0.5 * Zj @ MZ
+                ref1 = (Zj @ vs[c] if vs[c] is not None else 0.0) + x0 @ MZ
+            else:
+                ref2 = np.zeros((j + 1, j + 1)); ref1 = Zj @ vs[c]
+            sc2 = max(np.abs(ref2).max(), 1e-300); sc1 = max(np.abs(ref1).max(), 1e-300)
+            np.testing.assert_allclose(t2, ref2, rtol=0, atol=1e-13 * sc2)
+            np.testing.assert_allclose(t1, ref1, rtol=0, atol=1e-12 * sc1)
+            np.testing.assert_allclose(t2, s2, rtol=0, atol=1e-13 * sc2)
+            np.testing.assert_allclose(t1, s1, rtol=0, atol=1e-12 * sc1)
+
+
 @pytest.mark.parametrize("fmt", [nat.FMT_SELL, nat.FMT_SELLD])
 def test_sell_sigma_row_sorting(fmt):
     """SELL-C-sigma (option sell_sigma, sigma = 256): rows sorted by length inside windows of 256 so that a slice is
