@@ -125,6 +125,7 @@ struct spis_ctx {
                                 // L1 hit, the TMA writes of the windows add to it, and two CTAs of 8 consumer warps hide the latency of
                                 // the matrix stream worse than four to five CTAs of the plain kernels.
   int batch_terms = 1;          // spis_constraint_terms_batch: one pass over Z for all quadratic constraints when one column is new
+  int sweep_reverse = 3;        // pipelined loop: bit 0 = the first projection, bit 1 = the last sweep walk their tiles back to front (L2 reuse)
   int hess_async = 1;           // pipelined loop: the Givens / least-squares kernel runs beside the normalising sweep
   // Look for row patterns in the caller's CSR arrays with host threads before anything is uploaded.  OFF by default:
   // on the bench box (16 hardware threads, PCIe 5) the detection alone runs at 94 GB/s (8.1 ms for the 760 MB lkdv
@@ -1780,6 +1781,7 @@ int spis_set_option(spis_ctx* ctx, const char* key, int64_t value) {
   else if (k == "spmv_multi") { ctx->spmv_multi = value ? 1 : 0; }
   else if (k == "spmv_dual") { ctx->spmv_dual = value ? 1 : 0; }
   else if (k == "hess_async") ctx->hess_async = value != 0;
+  else if (k == "sweep_reverse") ctx->sweep_reverse = (int)value & 3;
   else if (k == "batch_terms") ctx->batch_terms = value != 0;
   else if (k == "host_pattern") ctx->host_pattern = value != 0;
   else if (k == "host_pattern_min_nnz") ctx->host_pattern_min_nnz = value;
@@ -2680,6 +2682,7 @@ int spis_step_enqueue(spis_ctx* ctx, int j, int flags, int64_t* ticket_out) {
   TRY(do_halo2(ctx, zj, want_res ? ctx->X : nullptr));
   // w = A z[j]  (+ ||A x - b||^2)                                   (solvers.py:191, 290)
   TailExtra tx{};
+  tx.reverse = ctx->sweep_reverse & 1;
   bool rides = false;
   if (want_res) {
     const long long t = ctx->res_tickets++;
@@ -2700,7 +2703,9 @@ int spis_step_enqueue(spis_ctx* ctx, int j, int flags, int64_t* ticket_out) {
     TRY(launch_spmv(ctx, SPIS_SLOT_A, 0, zj, nullptr, ctx->W, nullptr));
   }
   // CGS2: h1 = V^T w ; w' = w - V h1, h2 = V^T w', ||w'||^2        (solvers.py:193-196)
-  TRY(launch_mdot(ctx, ctx->V, m, nullptr, 0, ctx->W, h1, rides ? &tx : nullptr));
+  TailExtra plain{};
+  plain.reverse = tx.reverse;
+  TRY(launch_mdot(ctx, ctx->V, m, nullptr, 0, ctx->W, h1, rides ? &tx : &plain));
   int E_ = 0, st_ = 0, mb_ = 0; size_t sm_ = 0;
   if (ctx->orth_fused && orth_mid_plan(ctx, m, &E_, &st_, &mb_, &sm_)) {
     TRY(launch_orth_mid(ctx, ctx->V, m, h1, ctx->W, h2, 1));
@@ -2740,7 +2745,8 @@ int spis_step_enqueue(spis_ctx* ctx, int j, int flags, int64_t* ticket_out) {
     TRY(prof_begin(ctx, SPIS_PROF_LINCOMB, (double)(m + 2 + (mB ? 1 : 0) + ((mB && !ctx->x0_is_zero) ? 1 : 0) + (fusej ? 2 : 0)) * 8.0 * (double)ctx->n));
     lincomb2n_kernel<4><<<grid, kThreads, smem, ctx->stream>>>(ctx->V, ctx->ld, m, h2, ctx->d_ydev + (size_t)((j + 1) & 1) * K, mB,
                                                                ctx->d_phase, ctx->W, ctx->x0_is_zero ? nullptr : ctx->X0, qn, ctx->X,
-                                                               fusej ? ctx->pre_diag : nullptr, fusej ? ctx->Z + (size_t)(j + 1) * ld : nullptr, ctx->n);
+                                                               fusej ? ctx->pre_diag : nullptr, fusej ? ctx->Z + (size_t)(j + 1) * ld : nullptr, ctx->n,
+                                                               (ctx->sweep_reverse >> 1) & 1);
     CU(cudaGetLastError());
     TRY(prof_end(ctx));
     ctx->z_ready_index = fusej ? j + 1 : -1;

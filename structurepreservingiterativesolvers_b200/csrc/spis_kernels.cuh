@@ -190,6 +190,8 @@ struct TailExtra {
   unsigned long long rec_seq;
   int* phase;                   // device phase word: 0 = the device forms the iterates, 1 = the host has taken over
   double thr2;                  // *phase = 1 when !(sum > thr2)
+  int reverse;                  // the sweep walks its tiles from the last to the first (the vector the previous kernel
+                                // wrote front to back is freshest in L2 at its tail)
 };
 
 __device__ __forceinline__ void publish_residual(double res2, const TailExtra& tx) {
@@ -395,7 +397,8 @@ mdot_reg_kernel(const double* __restrict__ V, int64_t ld, int m, const double* _
   for (int i = 0; i < MB; ++i) acc[i] = 0.0;
   const int64_t ntiles = (n + kTile - 1) / kTile;
   const int64_t nfull = n / kTile;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  for (int64_t k = blockIdx.x; k < ntiles; k += gridDim.x) {
+    const int64_t tile = tx.reverse ? ntiles - 1 - k : k;
     if (tile < nfull) mdot_reg_tile<MB, true>(V, ld, m, extra, w, n, nrows, tile, acc);
     else mdot_reg_tile<MB, false>(V, ld, m, extra, w, n, nrows, tile, acc);
   }
@@ -790,7 +793,7 @@ __global__ void __launch_bounds__(kThreads)
 lincomb2n_kernel(const double* __restrict__ V, int64_t ld, int m, const double* __restrict__ coefA /* h2[0..m), h2[m] = ||w'||^2 */,
                  const double* __restrict__ coefB, int mB, const int* __restrict__ phase,
                  const double* baseA, const double* baseB, double* outA, double* outB,
-                 const double* __restrict__ jac, double* __restrict__ znext, int64_t n) {
+                 const double* __restrict__ jac, double* __restrict__ znext, int64_t n, int reverse) {
   extern __shared__ double smem[];
   double* scA = smem;                        // [m]   -coefA
   double* scB = smem + m + (m & 1);          // [m]   +coefB, zero beyond mB
@@ -816,12 +819,14 @@ lincomb2n_kernel(const double* __restrict__ V, int64_t ld, int m, const double* 
   const int64_t ntiles = (n + kTile - 1) / kTile;
   const int64_t nfull = n / kTile;
   if (dob) {
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int64_t k = blockIdx.x; k < ntiles; k += gridDim.x) {
+      const int64_t tile = reverse ? ntiles - 1 - k : k;
       if (tile < nfull) lincomb2n_tile<IU, true, true>(V, ld, m, scA, scB, inv, baseA, baseB, outA, outB, jac, znext, n, tile);
       else lincomb2n_tile<IU, false, true>(V, ld, m, scA, scB, inv, baseA, baseB, outA, outB, jac, znext, n, tile);
     }
   } else {
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int64_t k = blockIdx.x; k < ntiles; k += gridDim.x) {
+      const int64_t tile = reverse ? ntiles - 1 - k : k;
       if (tile < nfull) lincomb2n_tile<IU, true, false>(V, ld, m, scA, scB, inv, baseA, baseB, outA, outB, jac, znext, n, tile);
       else lincomb2n_tile<IU, false, false>(V, ld, m, scA, scB, inv, baseA, baseB, outA, outB, jac, znext, n, tile);
     }
